@@ -1,0 +1,573 @@
+/*
+ * cw_oracle.c -- CPU ORACLE for the cogsworth galactic-dynamics hot path.
+ *
+ * THIS FILE IS TEST INFRASTRUCTURE, NOT PRODUCT.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it.  The product path
+ * (cogsworth_b200/) never links, imports or calls anything in oracle/.
+ *
+ * It restates, in plain C with gala's operation order, the algorithm that
+ *   cogsworth.kicks.integrate_orbit_with_events   (/root/reference/src/cogsworth/kicks.py:52-209)
+ * runs per orbit on the CPU:  time grid -> segment-by-segment gala integration ->
+ * velocity kick at each supernova -> stitch.
+ *
+ * The arithmetic itself lives in a third-party dependency that is NOT under /root/reference
+ * and is not installed here:  gala (PyPI `gala`, pinned only as `>= 1.11.0`,
+ * /root/reference/pyproject.toml:24).  The functions below therefore restate gala's
+ * published algorithms (file names as in the gala source tree):
+ *   gala/integrate/timespec.py                  parse_time_specification   -> cwo_time_grid
+ *   gala/potential/potential/builtin/builtin_potentials.c
+ *        hernquist_gradient / miyamotonagai_gradient / mn3_gradient / sphericalnfw_gradient
+ *                                                                        -> cwo_gradient
+ *   gala/potential/potential/src/cpotential.c   c_gradient (component loop) -> cwo_gradient
+ *   gala/integrate/cyintegrators/leapfrog.pyx   c_init_velocity / c_leapfrog_step -> cwo_leapfrog
+ *   gala/integrate/cyintegrators/dop853.pyx     dop853_integrate_hamiltonian  -> cwo_dop853_segment
+ *   gala/integrate/cyintegrators/dopri/dop853.c Hairer's dopcor            -> cwo_dop853
+ *
+ * PARITY PINNING: the reference's own tests hold no golden trajectories.  The
+ * oracle is pinned against the numeric outputs printed in the reference's executed notebook
+ * docs/tutorials/visualisation/gala.ipynb (circular velocity, time grid, six phase-space
+ * samples of a DOPRI853 orbit), the tests/test_events.py fixture, and scipy's compiled Hairer
+ * DOP853 (tests/test_oracle_*.py).  It has NOT been compared with gala run here, because gala
+ * cannot be installed in this container: at the gala boundary parity is "unpinned".
+ *
+ * Build:  gcc -O2 -ffp-contract=off -pthread -shared -fPIC (see oracle/Makefile).
+ * -ffp-contract=off keeps gcc from fusing a*b+c, matching gala's x86-64 wheels.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+#include <pthread.h>
+#include <unistd.h>
+
+#include "../include/cw_dop853_coeffs.h"
+
+#define CWO_MAX_COMP 16
+#define CWO_COMP_MN 1
+#define CWO_COMP_HERNQUIST 2
+#define CWO_COMP_NFW 3
+
+#define CWO_LEAPFROG 0
+#define CWO_DOP853 1
+
+#define CWO_FLAG_APPEND_T2 1
+
+/* per-orbit status, Hairer's return codes plus two of ours */
+#define CWO_OK 0
+#define CWO_E_INCONSISTENT (-1)
+#define CWO_E_NMAX (-2)
+#define CWO_E_STEP_TOO_SMALL (-3)
+#define CWO_E_STIFF (-4)
+#define CWO_E_NONFINITE (-5)
+#define CWO_E_CAPACITY (-6)
+
+typedef struct {
+    double G;
+    int32_t n;
+    int32_t type[CWO_MAX_COMP];
+    double p[CWO_MAX_COMP][3];
+} cwo_potential;
+
+typedef struct {
+    int64_t n_accepted, n_rejected, n_fcn;
+} cwo_stats;
+
+/* ------------------------------------------------------------------ potentials */
+
+/* builtin_potentials.c: miyamotonagai_gradient, pars = (G, m, a, b) */
+static void mn_gradient(double G, const double *p, const double *q, double *grad)
+{
+    double sqrtz = sqrt(q[2] * q[2] + p[2] * p[2]);
+    double zd = p[1] + sqrtz;
+    double fac = G * p[0] * pow(q[0] * q[0] + q[1] * q[1] + zd * zd, -1.5);
+    grad[0] = grad[0] + fac * q[0];
+    grad[1] = grad[1] + fac * q[1];
+    grad[2] = grad[2] + fac * q[2] * (1. + p[1] / sqrtz);
+}
+
+/* builtin_potentials.c: hernquist_gradient, pars = (G, m, c) */
+static void hernquist_gradient(double G, const double *p, const double *q, double *grad)
+{
+    double R = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    double fac = G * p[0] / ((R + p[1]) * (R + p[1]) * R);
+    grad[0] = grad[0] + fac * q[0];
+    grad[1] = grad[1] + fac * q[1];
+    grad[2] = grad[2] + fac * q[2];
+}
+
+/* builtin_potentials.c: sphericalnfw_gradient, pars = (G, m, r_s) */
+static void nfw_gradient(double G, const double *p, const double *q, double *grad)
+{
+    double v_h2 = G * p[0] / p[1];
+    double u = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]) / p[1];
+    double fac = v_h2 / (u * u * u) / (p[1] * p[1]) * (log(1 + u) - u / (1 + u));
+    grad[0] = grad[0] + fac * q[0];
+    grad[1] = grad[1] + fac * q[1];
+    grad[2] = grad[2] + fac * q[2];
+}
+
+/* cpotential.c: c_gradient -- zero, then accumulate components in order */
+void cwo_gradient(const cwo_potential *P, const double *q, double *grad)
+{
+    grad[0] = 0.; grad[1] = 0.; grad[2] = 0.;
+    for (int i = 0; i < P->n; i++) {
+        switch (P->type[i]) {
+        case CWO_COMP_MN: mn_gradient(P->G, P->p[i], q, grad); break;
+        case CWO_COMP_HERNQUIST: hernquist_gradient(P->G, P->p[i], q, grad); break;
+        case CWO_COMP_NFW: nfw_gradient(P->G, P->p[i], q, grad); break;
+        default: grad[0] = grad[1] = grad[2] = NAN;
+        }
+    }
+}
+
+/* builtin_potentials.c *_value: Phi of the same components (used by the "next" rows N3) */
+double cwo_value(const cwo_potential *P, const double *q)
+{
+    double v = 0.;
+    for (int i = 0; i < P->n; i++) {
+        const double *p = P->p[i];
+        if (P->type[i] == CWO_COMP_MN) {
+            double zd = p[1] + sqrt(q[2] * q[2] + p[2] * p[2]);
+            v += -P->G * p[0] / sqrt(q[0] * q[0] + q[1] * q[1] + zd * zd);
+        } else if (P->type[i] == CWO_COMP_HERNQUIST) {
+            double R = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+            v += -P->G * p[0] / (R + p[1]);
+        } else if (P->type[i] == CWO_COMP_NFW) {
+            double u = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]) / p[1];
+            double v_h2 = -P->G * p[0] / p[1];
+            v += v_h2 * log(1 + u) / u;
+        } else v = NAN;
+    }
+    return v;
+}
+
+/* PotentialBase.circular_velocity: sqrt(r * |dPhi/dr|), dPhi/dr = sum(q * grad) / r */
+double cwo_circular_velocity(const cwo_potential *P, const double *q)
+{
+    double g[3];
+    cwo_gradient(P, q, g);
+    double r = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    double dPhi_dr = (q[0] * g[0] + q[1] * g[1] + q[2] * g[2]) / r;
+    return sqrt(r * fabs(dPhi_dr));
+}
+
+/* ------------------------------------------------------------------ time grid */
+
+/* timespec.py parse_time_specification(dt, t1, t2), forward branch:
+ *     t_i = t1; while (t_i < t2) and (ii < 1e6): times.append(t_i); t_i += dt; ii += 1
+ * followed by kicks.py:121-122 (append t2 if the last node is < t2) when `append_t2`.
+ * Returns the number of nodes; writes at most `cap` of them to T (T may be NULL to count). */
+int64_t cwo_time_grid(double t1, double t2, double dt, int append_t2, double *T, int64_t cap)
+{
+    int64_t n = 0;
+    double t_i = t1, last = t1;
+    while (t_i < t2 && n < 1000000) {
+        if (T && n < cap) T[n] = t_i;
+        last = t_i;
+        n++;
+        t_i += dt;
+    }
+    if (n == 0) return 0;           /* t2 <= t1: gala raises ValueError */
+    if (append_t2 && last < t2) {
+        if (T && n < cap) T[n] = t2;
+        n++;
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------ leapfrog */
+
+/* leapfrog.pyx leapfrog_integrate_hamiltonian for ONE orbit over t[0..nt-1] (Myr).
+ * w = (x,y,z,vx,vy,vz) is advanced in place to t[nt-1]; when `out` != NULL sample j is
+ * written to out[c*stride + j] for c = 0..5 (sample 0 is the input state).
+ * nt == 1 is returned unchanged (gala reads t[1] out of bounds but never steps). */
+void cwo_leapfrog(const cwo_potential *P, double *w, const double *t, int64_t nt,
+                  double *out, int64_t stride)
+{
+    double grad[3], vh[3];
+    if (out) for (int c = 0; c < 6; c++) out[c * stride] = w[c];
+    if (nt < 2) return;
+    double dt = t[1] - t[0];
+    /* c_init_velocity */
+    cwo_gradient(P, w, grad);
+    for (int k = 0; k < 3; k++) vh[k] = w[3 + k] - grad[k] * dt / 2.;
+    for (int64_t j = 1; j < nt; j++) {
+        /* c_leapfrog_step */
+        for (int k = 0; k < 3; k++) w[k] = w[k] + vh[k] * dt;
+        cwo_gradient(P, w, grad);
+        for (int k = 0; k < 3; k++) {
+            w[3 + k] = vh[k] - grad[k] * dt / 2.;
+            vh[k] = vh[k] - grad[k] * dt;
+        }
+        if (out) for (int c = 0; c < 6; c++) out[c * stride + j] = w[c];
+    }
+}
+
+/* ------------------------------------------------------------------ DOP853 (Hairer) */
+
+#define NEQ 6
+
+/* Fwrapper in gala's dop853.pyx: f = (dH/dp, -dH/dq) = (v, -grad Phi) */
+static void fcn(const cwo_potential *P, const double *y, double *f)
+{
+    double g[3];
+    cwo_gradient(P, y, g);
+    f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
+    f[3] = -g[0]; f[4] = -g[1]; f[5] = -g[2];
+}
+
+static double sign_d(double a, double b) { return (b > 0.0) ? fabs(a) : -fabs(a); }
+static double min_d(double a, double b) { return (a < b) ? a : b; }
+static double max_d(double a, double b) { return (a > b) ? a : b; }
+
+/* Hairer dop853.c: dop853() argument checks + dopcor(), specialised to what gala passes:
+ * itoler=0 (scalar tolerances), iout=0, uround/safe/fac1/fac2/beta/hmax = 0 -> defaults,
+ * h = dt0 (non-zero so hinit is skipped), meth=0 -> 1, nstiff=1, no dense output.
+ * Integrates y from x to xend in place.  Returns 1 on success or a negative Hairer code. */
+int cwo_dop853(const cwo_potential *P, double x, double *y, double xend, double rtol, double atol,
+               double h, int64_t nmax, cwo_stats *st)
+{
+    const int n = NEQ;
+    double k1[NEQ], k2[NEQ], k3[NEQ], k4[NEQ], k5[NEQ], k6[NEQ], k7[NEQ], k8[NEQ], k9[NEQ], k10[NEQ];
+    double yy1[NEQ];
+    /* dop853(): defaults */
+    if (nmax <= 0) nmax = 100000;
+    const int64_t nstiff = 1;
+    const double uround = 2.3E-16, safe = 0.9, fac1 = 0.333, fac2 = 6.0, beta = 0.0;
+    double hmax = xend - x;
+    /* dopcor() */
+    double facold = 1.0E-4, expo1 = 1.0 / 8.0 - beta * 0.2, facc1 = 1.0 / fac1, facc2 = 1.0 / fac2;
+    double posneg = sign_d(1.0, xend - x);
+    double atoli = atol, rtoli = rtol;
+    int last = 0, reject = 0, nonsti = 0, iasti = 0;
+    int64_t nstep = 0, naccpt = 0, nrejct = 0, nfcn = 0;
+    double hlamb = 0.0, hnew, xph, err, err2, sk, erri, sqr, deno, fac, fac11;
+    int i;
+
+    fcn(P, y, k1);
+    hmax = fabs(hmax);
+    if (h == 0.0) return CWO_E_INCONSISTENT;   /* gala always passes dt0 != 0 (hinit not restated) */
+    nfcn += 2;
+
+    while (1) {
+        if (nstep > nmax) { if (st) { st->n_accepted += naccpt; st->n_rejected += nrejct; st->n_fcn += nfcn; } return CWO_E_NMAX; }
+        if (0.1 * fabs(h) <= fabs(x) * uround) { if (st) { st->n_accepted += naccpt; st->n_rejected += nrejct; st->n_fcn += nfcn; } return CWO_E_STEP_TOO_SMALL; }
+        if ((x + 1.01 * h - xend) * posneg > 0.0) { h = xend - x; last = 1; }
+        nstep++;
+
+        /* the twelve stages */
+        for (i = 0; i < n; i++) yy1[i] = y[i] + h * CW_A0201 * k1[i];
+        fcn(P, yy1, k2);
+        for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A0301 * k1[i] + CW_A0302 * k2[i]);
+        fcn(P, yy1, k3);
+        for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A0401 * k1[i] + CW_A0403 * k3[i]);
+        fcn(P, yy1, k4);
+        for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A0501 * k1[i] + CW_A0503 * k3[i] + CW_A0504 * k4[i]);
+        fcn(P, yy1, k5);
+        for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A0601 * k1[i] + CW_A0604 * k4[i] + CW_A0605 * k5[i]);
+        fcn(P, yy1, k6);
+        for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A0701 * k1[i] + CW_A0704 * k4[i] + CW_A0705 * k5[i] + CW_A0706 * k6[i]);
+        fcn(P, yy1, k7);
+        for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A0801 * k1[i] + CW_A0804 * k4[i] + CW_A0805 * k5[i] + CW_A0806 * k6[i] + CW_A0807 * k7[i]);
+        fcn(P, yy1, k8);
+        for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A0901 * k1[i] + CW_A0904 * k4[i] + CW_A0905 * k5[i] + CW_A0906 * k6[i] + CW_A0907 * k7[i] + CW_A0908 * k8[i]);
+        fcn(P, yy1, k9);
+        for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A1001 * k1[i] + CW_A1004 * k4[i] + CW_A1005 * k5[i] + CW_A1006 * k6[i] + CW_A1007 * k7[i] + CW_A1008 * k8[i] + CW_A1009 * k9[i]);
+        fcn(P, yy1, k10);
+        for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A1101 * k1[i] + CW_A1104 * k4[i] + CW_A1105 * k5[i] + CW_A1106 * k6[i] + CW_A1107 * k7[i] + CW_A1108 * k8[i] + CW_A1109 * k9[i] + CW_A1110 * k10[i]);
+        fcn(P, yy1, k2);
+        xph = x + h;
+        for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A1201 * k1[i] + CW_A1204 * k4[i] + CW_A1205 * k5[i] + CW_A1206 * k6[i] + CW_A1207 * k7[i] + CW_A1208 * k8[i] + CW_A1209 * k9[i] + CW_A1210 * k10[i] + CW_A1211 * k2[i]);
+        fcn(P, yy1, k3);
+        nfcn += 11;
+        for (i = 0; i < n; i++) {
+            k4[i] = CW_B01 * k1[i] + CW_B06 * k6[i] + CW_B07 * k7[i] + CW_B08 * k8[i] + CW_B09 * k9[i] + CW_B10 * k10[i] + CW_B11 * k2[i] + CW_B12 * k3[i];
+            k5[i] = y[i] + h * k4[i];
+        }
+
+        /* error estimation */
+        err = 0.0; err2 = 0.0;
+        for (i = 0; i < n; i++) {
+            sk = atoli + rtoli * max_d(fabs(y[i]), fabs(k5[i]));
+            erri = k4[i] - CW_BHH1 * k1[i] - CW_BHH2 * k9[i] - CW_BHH3 * k3[i];
+            sqr = erri / sk;
+            err2 += sqr * sqr;
+            erri = CW_ER01 * k1[i] + CW_ER06 * k6[i] + CW_ER07 * k7[i] + CW_ER08 * k8[i] + CW_ER09 * k9[i] + CW_ER10 * k10[i] + CW_ER11 * k2[i] + CW_ER12 * k3[i];
+            sqr = erri / sk;
+            err += sqr * sqr;
+        }
+        deno = err + 0.01 * err2;
+        if (deno <= 0.0) deno = 1.0;
+        err = fabs(h) * err * sqrt(1.0 / (deno * (double)n));
+        if (!(err == err) || isinf(err)) {  /* not in Hairer: NaN would spin to nmax; both end as a failed orbit */
+            if (st) { st->n_accepted += naccpt; st->n_rejected += nrejct; st->n_fcn += nfcn; }
+            return CWO_E_NONFINITE;
+        }
+
+        /* computation of hnew */
+        fac11 = pow(err, expo1);
+        fac = fac11 / pow(facold, beta);            /* Lund stabilisation (beta = 0 -> 1) */
+        fac = max_d(facc2, min_d(facc1, fac / safe));
+        hnew = h / fac;
+
+        if (err <= 1.0) {
+            /* step accepted */
+            facold = max_d(err, 1.0E-4);
+            naccpt++;
+            fcn(P, k5, k4);
+            nfcn++;
+            /* stiffness detection */
+            if (!(naccpt % nstiff) || (iasti > 0)) {
+                double stnum = 0.0, stden = 0.0;
+                for (i = 0; i < n; i++) {
+                    sqr = k4[i] - k3[i]; stnum += sqr * sqr;
+                    sqr = k5[i] - yy1[i]; stden += sqr * sqr;
+                }
+                if (stden > 0.0) hlamb = h * sqrt(stnum / stden);
+                if (hlamb > 6.1) {
+                    nonsti = 0; iasti++;
+                    if (iasti == 15) { if (st) { st->n_accepted += naccpt; st->n_rejected += nrejct; st->n_fcn += nfcn; } return CWO_E_STIFF; }
+                } else {
+                    nonsti++;
+                    if (nonsti == 6) iasti = 0;
+                }
+            }
+            memcpy(k1, k4, n * sizeof(double));
+            memcpy(y, k5, n * sizeof(double));
+            x = xph;
+            if (last) {
+                if (st) { st->n_accepted += naccpt; st->n_rejected += nrejct; st->n_fcn += nfcn; }
+                return 1;
+            }
+            if (fabs(hnew) > hmax) hnew = posneg * hmax;
+            if (reject) hnew = posneg * min_d(fabs(hnew), fabs(h));
+            reject = 0;
+        } else {
+            /* step rejected */
+            hnew = h / min_d(facc1, fac11 / safe);
+            reject = 1;
+            if (naccpt >= 1) nrejct = nrejct + 1;
+            last = 0;
+        }
+        h = hnew;
+    }
+}
+
+/* dop853.pyx dop853_integrate_hamiltonian for one orbit over t[0..nt-1] (Myr):
+ * dt0 = t[1]-t[0]; a fresh dop853(x=t[j-1], xend=t[j], h=dt0) per output interval. */
+int cwo_dop853_segment(const cwo_potential *P, double *w, const double *t, int64_t nt,
+                       double rtol, double atol, int64_t nmax, double *out, int64_t stride,
+                       cwo_stats *st)
+{
+    if (out) for (int c = 0; c < 6; c++) out[c * stride] = w[c];
+    if (nt < 2) return CWO_OK;
+    double dt0 = t[1] - t[0];
+    for (int64_t j = 1; j < nt; j++) {
+        int res = cwo_dop853(P, t[j - 1], w, t[j], rtol, atol, dt0, nmax, st);
+        if (res < 0) return res;
+        if (out) for (int c = 0; c < 6; c++) out[c * stride + j] = w[c];
+    }
+    return CWO_OK;
+}
+
+/* ------------------------------------------------------------------ the kicks.py driver */
+
+/* potential.integrate_orbit(w, t=T[first..last]) in galactic units */
+static int integrate_segment(const cwo_potential *P, int integrator, double rtol, double atol,
+                             int64_t nmax, double *w, const double *tmyr, int64_t nt,
+                             double *out, int64_t stride, cwo_stats *st)
+{
+    if (integrator == CWO_LEAPFROG) { cwo_leapfrog(P, w, tmyr, nt, out, stride); return CWO_OK; }
+    return cwo_dop853_segment(P, w, tmyr, nt, rtol, atol, nmax, out, stride, st);
+}
+
+/*
+ * One orbit of integrate_orbit_with_events (kicks.py:97-209), one attempt (the retry loop
+ * kicks.py:113,193-199 is host logic in the caller).
+ *
+ *   t1,t2,dt,ev_time : in the orbit's GRID unit  (seconds on the events branch kicks.py:118,
+ *                      Myr on the no-events branch kicks.py:100-104, where gala builds the grid)
+ *   to_myr           : grid unit -> Myr factor (astropy multiplies by 1/3.15576e13; 1.0 for Myr)
+ *   flags & 1        : append t2 as the last node (kicks.py:121-122)
+ *   ev_dv            : n_ev x 3, already rotated (get_kick_differential) and in kpc/Myr
+ *   n_nodes_expected : trajectory capacity when store_all (samples written to
+ *                      traj[c*stride + j], times to traj_t[j]); ignored otherwise
+ * Outputs: w_final[6]; ev_step[e] = grid node at which kick e is applied; *n_nodes.
+ */
+int cwo_integrate_orbit(const cwo_potential *P, int integrator, double rtol, double atol, int64_t nmax,
+                        const double *w0, double t1, double t2, double dt, double to_myr, int flags,
+                        int64_t n_ev, const double *ev_time, const double *ev_dv,
+                        int store_all, double *traj, int64_t stride, double *traj_t, int64_t cap,
+                        double *w_final, int32_t *ev_step, int64_t *n_nodes, cwo_stats *st)
+{
+    int64_t n = cwo_time_grid(t1, t2, dt, flags & CWO_FLAG_APPEND_T2, NULL, 0);
+    if (n_nodes) *n_nodes = n;
+    if (n <= 0) return CWO_E_INCONSISTENT;
+    if (store_all && cap < n) return CWO_E_CAPACITY;
+    double *T = (double *)malloc(sizeof(double) * (size_t)n * 2);
+    if (!T) return CWO_E_CAPACITY;
+    double *Tm = T + n;
+    cwo_time_grid(t1, t2, dt, flags & CWO_FLAG_APPEND_T2, T, n);
+    for (int64_t j = 0; j < n; j++) Tm[j] = T[j] * to_myr;     /* Quantity.decompose(galactic) */
+
+    double w[6];
+    memcpy(w, w0, sizeof w);
+    int status = CWO_OK;
+    int64_t n_written = 0;             /* samples appended to orbit_data so far */
+    double cursor = T[0];              /* kicks.py:125 */
+
+    for (int64_t e = 0; e < n_ev && status == CWO_OK; e++) {
+        /* timestep_mask = (timesteps >= time_cursor) & (timesteps < t1 + tphys)   kicks.py:134 */
+        int64_t first = -1, last = -1;
+        for (int64_t j = 0; j < n; j++) {
+            if (T[j] >= cursor && T[j] < ev_time[e]) { if (first < 0) first = j; last = j; }
+        }
+        if (first >= 0) {
+            int64_t nt = last - first + 1;
+            double *out = NULL;
+            if (store_all) out = traj + n_written;   /* writes nt samples; only nt-1 are kept */
+            status = integrate_segment(P, integrator, rtol, atol, nmax, w, Tm + first, nt,
+                                       out, stride, st);
+            n_written += nt - 1;                 /* orbit.data[:-1]          kicks.py:148 */
+            cursor = T[last];                    /* kicks.py:154 */
+            if (ev_step) ev_step[e] = (int32_t)last;
+        } else {
+            cursor = ev_time[e];                 /* kicks.py:157 */
+            /* the kick lands on the node the state currently sits at */
+            if (ev_step) ev_step[e] = (int32_t)n_written;
+        }
+        /* current_w0.vel + kick_differential     kicks.py:160-172 */
+        w[3] += ev_dv[3 * e + 0];
+        w[4] += ev_dv[3 * e + 1];
+        w[5] += ev_dv[3 * e + 2];
+    }
+    if (status == CWO_OK && (n_ev == 0 || cursor < T[n - 1])) {       /* kicks.py:175 / :102 */
+        int64_t first = -1;
+        for (int64_t j = 0; j < n; j++) if (T[j] >= cursor) { first = j; break; }
+        if (first >= 0) {
+            int64_t nt = n - first;
+            double *out = NULL;
+            if (store_all) out = traj + n_written;
+            status = integrate_segment(P, integrator, rtol, atol, nmax, w, Tm + first, nt,
+                                       out, stride, st);
+            n_written += nt;
+        }
+    } else if (status == CWO_OK && store_all) {
+        /* no tail: the state after the last kick is never stored by the reference */
+    }
+    /* Orbit(pos, vel, t=timesteps) requires len(data) == len(timesteps)   kicks.py:187-189 */
+    if (status == CWO_OK && n_written != n) status = CWO_E_INCONSISTENT;
+    if (status == CWO_OK && store_all && traj_t) for (int64_t j = 0; j < n; j++) traj_t[j] = Tm[j];
+    memcpy(w_final, w, sizeof w);
+    free(T);
+    return status;
+}
+
+/*
+ * Batch driver = the work Population.perform_galactic_evolution fans out over its pool
+ * (pop.py:1240-1266), here a pthread pool pulling chunks of orbits from an atomic counter.
+ * SoA layouts identical to the C-ABI of the product (include/cogsworth_b200.h) so the parity
+ * tests feed both the same buffers.
+ *   w0 / w_final : 6 x n (component-major);  ev_off : n+1 CSR offsets into ev_time / ev_dv(K x 3)
+ *   traj_off     : n+1 offsets, traj_pos/vel : 3 x total, traj_t : total   (store_all only)
+ */
+typedef struct {
+    const cwo_potential *P;
+    int integrator; double rtol, atol; int64_t nmax;
+    int64_t n_orbits;
+    const double *w0, *t1, *t2, *dt, *to_myr; const int32_t *flags;
+    const int64_t *ev_off; const double *ev_time, *ev_dv;
+    double *w_final; int32_t *status, *n_nodes_out, *ev_step;
+    const int64_t *traj_off; double *traj_pos, *traj_vel, *traj_t;
+    int64_t next;                  /* work counter (atomic) */
+    int64_t acc, rej, nf;          /* stats (atomic adds) */
+} batch_job;
+
+static void batch_one(batch_job *J, int64_t i, cwo_stats *tot)
+{
+    const int64_t n_orbits = J->n_orbits;
+    int store_all = J->traj_off != NULL;
+    int64_t total = store_all ? J->traj_off[n_orbits] : 0;
+    double w[6], wf[6];
+    for (int c = 0; c < 6; c++) w[c] = J->w0[c * n_orbits + i];
+    int64_t e0 = J->ev_off ? J->ev_off[i] : 0, e1 = J->ev_off ? J->ev_off[i + 1] : 0;
+    int64_t nn = 0;
+    cwo_stats st = {0, 0, 0};
+    double *tmp = NULL;
+    int64_t cap = 0;
+    if (store_all) {
+        cap = J->traj_off[i + 1] - J->traj_off[i];
+        tmp = (double *)malloc(sizeof(double) * 6 * (size_t)(cap + 1));
+    }
+    int s = cwo_integrate_orbit(J->P, J->integrator, J->rtol, J->atol, J->nmax, w, J->t1[i], J->t2[i],
+                                J->dt[i], J->to_myr[i], J->flags[i], e1 - e0,
+                                J->ev_time ? J->ev_time + e0 : NULL, J->ev_dv ? J->ev_dv + 3 * e0 : NULL,
+                                store_all, tmp, cap + 1,
+                                (store_all && J->traj_t) ? J->traj_t + J->traj_off[i] : NULL, cap,
+                                wf, J->ev_step ? J->ev_step + e0 : NULL, &nn, &st);
+    if (store_all && tmp) {
+        if (s == CWO_OK) {
+            for (int c = 0; c < 3; c++)
+                for (int64_t j = 0; j < nn; j++) {
+                    J->traj_pos[c * total + J->traj_off[i] + j] = tmp[c * (cap + 1) + j];
+                    J->traj_vel[c * total + J->traj_off[i] + j] = tmp[(3 + c) * (cap + 1) + j];
+                }
+        }
+        free(tmp);
+    }
+    for (int c = 0; c < 6; c++) J->w_final[c * n_orbits + i] = wf[c];
+    if (J->status) J->status[i] = s;
+    if (J->n_nodes_out) J->n_nodes_out[i] = (int32_t)nn;
+    tot->n_accepted += st.n_accepted; tot->n_rejected += st.n_rejected; tot->n_fcn += st.n_fcn;
+}
+
+static void *batch_worker(void *arg)
+{
+    batch_job *J = (batch_job *)arg;
+    cwo_stats tot = {0, 0, 0};
+    const int64_t chunk = 16;
+    for (;;) {
+        int64_t b = __atomic_fetch_add(&J->next, chunk, __ATOMIC_RELAXED);
+        if (b >= J->n_orbits) break;
+        int64_t e = b + chunk < J->n_orbits ? b + chunk : J->n_orbits;
+        for (int64_t i = b; i < e; i++) batch_one(J, i, &tot);
+    }
+    __atomic_fetch_add(&J->acc, tot.n_accepted, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&J->rej, tot.n_rejected, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&J->nf, tot.n_fcn, __ATOMIC_RELAXED);
+    return NULL;
+}
+
+int cwo_max_threads(void)
+{
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n > 0 ? (int)n : 1;
+}
+
+int cwo_integrate_batch(const cwo_potential *P, int integrator, double rtol, double atol, int64_t nmax,
+                        int64_t n_orbits, const double *w0, const double *t1, const double *t2,
+                        const double *dt, const double *to_myr, const int32_t *flags,
+                        const int64_t *ev_off, const double *ev_time, const double *ev_dv,
+                        double *w_final, int32_t *status, int32_t *n_nodes_out, int32_t *ev_step,
+                        const int64_t *traj_off, double *traj_pos, double *traj_vel, double *traj_t,
+                        int64_t *stats3, int n_threads)
+{
+    batch_job J = {P, integrator, rtol, atol, nmax, n_orbits, w0, t1, t2, dt, to_myr, flags,
+                   ev_off, ev_time, ev_dv, w_final, status, n_nodes_out, ev_step,
+                   traj_off, traj_pos, traj_vel, traj_t, 0, 0, 0, 0};
+    if (n_threads <= 0) n_threads = cwo_max_threads();
+    if (n_threads > 256) n_threads = 256;
+    if (n_threads == 1) {
+        batch_worker(&J);
+    } else {
+        pthread_t th[256];
+        int started = 0;
+        for (int k = 0; k < n_threads; k++)
+            if (pthread_create(&th[started], NULL, batch_worker, &J) == 0) started++;
+        if (started == 0) batch_worker(&J);
+        for (int k = 0; k < started; k++) pthread_join(th[k], NULL);
+    }
+    if (stats3) { stats3[0] = J.acc; stats3[1] = J.rej; stats3[2] = J.nf; }
+    return 0;
+}
