@@ -1,0 +1,614 @@
+// cw_api.cu -- the C ABI (include/cogsworth_b200.h): context, device memory, sharding of a batch
+// over the context's devices, kernel sequencing.  This is the B200 replacement for the
+// multiprocessing boundary of the reference (cogsworth pop.py:917-939 _ensure_pool,
+// :1240-1266 pool.starmap(_orbit_worker), :2187-2201 _init_pool/_orbit_worker).
+//
+// There is NO CPU fallback anywhere in this file: without a CUDA device cw_create fails with
+// CW_E_NO_DEVICE.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "cw_kernels.cuh"
+
+using namespace cw;
+
+namespace {
+
+struct Arena {
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        used = 0;
+        if (bytes <= cap) return cudaSuccess;
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = 0;
+        size_t want = bytes + (bytes >> 3) + (1u << 20);
+        cudaError_t e = cudaMalloc((void **)&base, want);
+        if (e != cudaSuccess) return e;
+        cap = want;
+        return cudaSuccess;
+    }
+    template <class T> T *take(size_t count)
+    {
+        size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+        if (used + bytes > cap) return nullptr;
+        T *p = reinterpret_cast<T *>(base + used);
+        used += bytes;
+        return p;
+    }
+    static size_t padded(size_t count, size_t elt) { return (count * elt + 255) & ~size_t(255); }
+    void release()
+    {
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = used = 0;
+    }
+};
+
+struct Slot {
+    int dev = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    Arena arena;
+    double last_kernel_ms = 0.0, last_total_ms = 0.0;
+    bool timed = false;
+};
+
+} // namespace
+
+struct cw_ctx {
+    std::vector<Slot> slots;
+    PotParams pot;
+    bool has_pot = false;
+    std::string last_error;
+    int64_t last_launches = 0;
+};
+
+#define CW_CK(ctx, call)                                                                          \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            char _b[512];                                                                         \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            (ctx)->last_error = _b;                                                               \
+            return CW_E_CUDA;                                                                     \
+        }                                                                                         \
+    } while (0)
+
+static int fail(cw_ctx *ctx, int code, const char *msg)
+{
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+
+extern "C" int cw_abi_version(void) { return CW_ABI_VERSION; }
+
+extern "C" const char *cw_strerror(int code)
+{
+    switch (code) {
+    case CW_OK: return "ok";
+    case CW_E_INVALID: return "invalid argument";
+    case CW_E_CUDA: return "CUDA runtime error";
+    case CW_E_NO_POTENTIAL: return "no potential set (call cw_set_potential)";
+    case CW_E_NO_DEVICE: return "no CUDA device available (this library has no CPU fallback)";
+    case CW_E_UNSUPPORTED: return "unsupported";
+    default: return "unknown error";
+    }
+}
+
+extern "C" const char *cw_last_error(const cw_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+extern "C" int cw_create(cw_ctx **out, int n_devices, const int *device_ids)
+{
+    if (!out) return CW_E_INVALID;
+    *out = nullptr;
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible <= 0) {
+        cudaGetLastError();
+        return CW_E_NO_DEVICE;
+    }
+    cw_ctx *ctx = new (std::nothrow) cw_ctx();
+    if (!ctx) return CW_E_INVALID;
+    memset(&ctx->pot, 0, sizeof ctx->pot);
+    std::vector<int> ids;
+    if (n_devices <= 0) {
+        for (int d = 0; d < visible; d++) ids.push_back(d);
+    } else {
+        for (int k = 0; k < n_devices; k++) {
+            int d = device_ids ? device_ids[k] : k;
+            if (d < 0 || d >= visible) {
+                delete ctx;
+                return CW_E_INVALID;
+            }
+            ids.push_back(d);
+        }
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (int d : ids) {
+        Slot s;
+        s.dev = d;
+        cudaError_t e = cudaSetDevice(d);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s.sm_count, cudaDevAttrMultiProcessorCount, d);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreate(&s.ev_t0);
+        if (e == cudaSuccess) e = cudaEventCreate(&s.ev_k0);
+        if (e == cudaSuccess) e = cudaEventCreate(&s.ev_k1);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaSetDevice(prev);
+            delete ctx;
+            return CW_E_CUDA;
+        }
+        ctx->slots.push_back(s);
+    }
+    cudaSetDevice(prev);
+    *out = ctx;
+    return CW_OK;
+}
+
+extern "C" void cw_destroy(cw_ctx *ctx)
+{
+    if (!ctx) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (Slot &s : ctx->slots) {
+        cudaSetDevice(s.dev);
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        s.arena.release();
+        if (s.ev_t0) cudaEventDestroy(s.ev_t0);
+        if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+        if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    cudaSetDevice(prev);
+    delete ctx;
+}
+
+extern "C" int cw_device_count(const cw_ctx *ctx) { return ctx ? (int)ctx->slots.size() : 0; }
+
+extern "C" int cw_set_potential(cw_ctx *ctx, double G, int n_comp, const int32_t *types, const double *params)
+{
+    if (!ctx || !types || !params || n_comp <= 0 || n_comp > CW_MAX_COMPONENTS)
+        return fail(ctx, CW_E_INVALID, "cw_set_potential: bad arguments");
+    PotParams P;
+    memset(&P, 0, sizeof P);
+    P.n_comp = n_comp;
+    P.G = G;
+    for (int i = 0; i < n_comp; i++) {
+        const int t = types[i];
+        if (t != CW_COMP_MIYAMOTO_NAGAI && t != CW_COMP_HERNQUIST && t != CW_COMP_NFW_SPHERICAL)
+            return fail(ctx, CW_E_UNSUPPORTED, "cw_set_potential: unknown component type");
+        P.type[i] = t;
+        P.GM[i] = G * params[3 * i + 0];
+        P.p1[i] = params[3 * i + 1];
+        P.p2[i] = (t == CW_COMP_NFW_SPHERICAL) ? 1.0 / params[3 * i + 1] : params[3 * i + 2];
+    }
+    // recognise the two Milky Way shapes that have specialised kernels
+    auto is = [&](int i, int t) { return i < n_comp && types[i] == t; };
+    P.kind = POT_GENERIC;
+    int nmn = 0;
+    while (nmn < n_comp && types[nmn] == CW_COMP_MIYAMOTO_NAGAI) nmn++;
+    if ((nmn == 1 || nmn == 3) && n_comp == nmn + 3 && is(nmn, CW_COMP_HERNQUIST) &&
+        is(nmn + 1, CW_COMP_HERNQUIST) && is(nmn + 2, CW_COMP_NFW_SPHERICAL)) {
+        bool shared_b = true;
+        for (int i = 1; i < nmn; i++) shared_b = shared_b && (params[3 * i + 2] == params[2]);
+        if (nmn == 1) P.kind = POT_MW_V1;
+        else if (shared_b) P.kind = POT_MW_V2;
+        if (P.kind != POT_GENERIC) {
+            for (int i = 0; i < nmn; i++) {
+                P.mn_GM[i] = P.GM[i];
+                P.mn_a[i] = params[3 * i + 1];
+                P.mn_b2[i] = params[3 * i + 2] * params[3 * i + 2];
+            }
+            for (int k = 0; k < 2; k++) {
+                P.h_GM[k] = P.GM[nmn + k];
+                P.h_c[k] = params[3 * (nmn + k) + 1];
+            }
+            P.nfw_GM = P.GM[nmn + 2];
+            P.nfw_rs = params[3 * (nmn + 2) + 1];
+            P.nfw_inv_rs = 1.0 / P.nfw_rs;
+        }
+    }
+    ctx->pot = P;
+    ctx->has_pot = true;
+    return CW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+
+namespace {
+
+struct Shard {
+    int64_t a = 0, b = 0;   // orbit range
+    int64_t ea = 0, eb = 0; // event range
+    int64_t ta = 0, tb = 0; // trajectory column range
+};
+
+// size of the CUB temp storage for sorting m (key, value) pairs
+size_t sort_temp_bytes(int64_t m)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const int32_t *)nullptr, (int32_t *)nullptr,
+                                              (const int32_t *)nullptr, (int32_t *)nullptr, (int)m);
+    return bytes;
+}
+
+constexpr int64_t SORT_THRESHOLD = 4096;
+
+struct Plan {
+    IntegArgs A;
+    int32_t *iota = nullptr, *keys_out = nullptr;
+    void *sort_tmp = nullptr;
+    size_t sort_bytes = 0;
+    bool sort = false;
+};
+
+} // namespace
+
+// Allocate (host mode: everything; device mode: scratch only) and fill the IntegArgs of one shard.
+static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B, const cw_result *R,
+                      const Shard &sh, bool integrate, Plan &pl)
+{
+    const bool dev_mode = o->mem_space == CW_MEM_DEVICE;
+    const int64_t m = sh.b - sh.a, K = sh.eb - sh.ea, Lt = sh.tb - sh.ta;
+    const bool store_all = integrate && R && R->traj_off;
+    pl.sort = integrate && m >= SORT_THRESHOLD;
+    pl.sort_bytes = pl.sort ? sort_temp_bytes(m) : 0;
+
+    size_t need = 0;
+    auto add = [&](size_t count, size_t elt) { need += Arena::padded(count, elt); };
+    // scratch common to both modes
+    add(K + 1, sizeof(double));          // ev_tk
+    add(1, 64);                          // queue + stats
+    if (pl.sort) { add(m, 4); add(m, 4); add(m, 4); add(pl.sort_bytes, 1); }
+    if (!dev_mode) {
+        add(6 * m, 8); add(4 * m, 8); add(m, 4); add(m + 1, 8); add(K + 1, 8); add(3 * K + 3, 8);
+        add(m, 4); add(K + 1, 4);               // n_nodes, ev_step
+        add(6 * m, 8); add(m, 4);               // w_final, status
+        if (store_all) { add(m + 1, 8); add(6 * Lt + 6, 8); add(Lt + 1, 8); }
+    } else {
+        add(m, 4); add(K + 1, 4); add(m, 4);    // n_nodes / ev_step / status if the caller passed NULL
+    }
+    CW_CK(ctx, s.arena.reserve(need + 4096));
+
+    IntegArgs &A = pl.A;
+    memset(&A, 0, sizeof A);
+    A.n = m;
+    A.atol = o->atol > 0 ? o->atol : 1e-10;
+    A.rtol = o->rtol > 0 ? o->rtol : 1e-10;
+    A.nmax = o->nmax;
+    A.ev_tk = s.arena.take<double>(K + 1);
+    unsigned long long *qs = s.arena.take<unsigned long long>(8);
+    A.queue = qs;
+    A.stats = qs + 1;
+    if (pl.sort) {
+        pl.iota = s.arena.take<int32_t>(m);
+        pl.keys_out = s.arena.take<int32_t>(m);
+        A.order = s.arena.take<int32_t>(m);
+        pl.sort_tmp = s.arena.take<char>(pl.sort_bytes);
+    }
+    if (!dev_mode) {
+        double *w0 = s.arena.take<double>(6 * m);
+        double *tt = s.arena.take<double>(4 * m);
+        int32_t *fl = s.arena.take<int32_t>(m);
+        int64_t *eo = s.arena.take<int64_t>(m + 1);
+        double *et = s.arena.take<double>(K + 1);
+        double *ed = s.arena.take<double>(3 * K + 3);
+        A.n_nodes = s.arena.take<int32_t>(m);
+        A.ev_step = s.arena.take<int32_t>(K + 1);
+        A.w_final = s.arena.take<double>(6 * m);
+        A.status = s.arena.take<int32_t>(m);
+        A.w0 = w0; A.t1 = tt; A.t2 = tt + m; A.dt = tt + 2 * m; A.to_myr = tt + 3 * m; A.flags = fl;
+        for (int c = 0; c < 6; c++)
+            CW_CK(ctx, cudaMemcpyAsync(w0 + c * m, B->w0 + c * B->n_orbits + sh.a, m * 8, cudaMemcpyHostToDevice, s.stream));
+        CW_CK(ctx, cudaMemcpyAsync(tt, B->t1 + sh.a, m * 8, cudaMemcpyHostToDevice, s.stream));
+        CW_CK(ctx, cudaMemcpyAsync(tt + m, B->t2 + sh.a, m * 8, cudaMemcpyHostToDevice, s.stream));
+        CW_CK(ctx, cudaMemcpyAsync(tt + 2 * m, B->dt + sh.a, m * 8, cudaMemcpyHostToDevice, s.stream));
+        CW_CK(ctx, cudaMemcpyAsync(tt + 3 * m, B->to_myr + sh.a, m * 8, cudaMemcpyHostToDevice, s.stream));
+        CW_CK(ctx, cudaMemcpyAsync(fl, B->grid_flags + sh.a, m * 4, cudaMemcpyHostToDevice, s.stream));
+        if (B->ev_off && K > 0) {
+            CW_CK(ctx, cudaMemcpyAsync(eo, B->ev_off + sh.a, (m + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+            CW_CK(ctx, cudaMemcpyAsync(et, B->ev_time + sh.ea, K * 8, cudaMemcpyHostToDevice, s.stream));
+            CW_CK(ctx, cudaMemcpyAsync(ed, B->ev_dv + 3 * sh.ea, 3 * K * 8, cudaMemcpyHostToDevice, s.stream));
+            A.ev_off = eo; A.ev_base = sh.ea; A.ev_time = et; A.ev_dv = ed;
+        }
+        if (store_all) {
+            int64_t *to = s.arena.take<int64_t>(m + 1);
+            double *tp = s.arena.take<double>(6 * Lt + 6);
+            double *ttm = s.arena.take<double>(Lt + 1);
+            CW_CK(ctx, cudaMemcpyAsync(to, R->traj_off + sh.a, (m + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+            A.traj_off = to; A.traj_base = sh.ta; A.traj_total = Lt;
+            A.traj_pos = tp; A.traj_vel = tp + 3 * Lt; A.traj_t = R->traj_t ? ttm : nullptr;
+        }
+    } else {
+        A.w0 = B->w0; A.t1 = B->t1; A.t2 = B->t2; A.dt = B->dt; A.to_myr = B->to_myr; A.flags = B->grid_flags;
+        if (B->ev_off && K > 0) { A.ev_off = B->ev_off; A.ev_base = 0; A.ev_time = B->ev_time; A.ev_dv = B->ev_dv; }
+        int32_t *nn = s.arena.take<int32_t>(m), *es = s.arena.take<int32_t>(K + 1), *st = s.arena.take<int32_t>(m);
+        A.n_nodes = (R && R->n_nodes) ? R->n_nodes : nn;
+        A.ev_step = (R && R->ev_step) ? R->ev_step : es;
+        A.status = (R && R->status) ? R->status : st;
+        A.w_final = R ? R->w_final : nullptr;
+        if (store_all) {
+            A.traj_off = R->traj_off; A.traj_base = 0; A.traj_total = Lt;
+            A.traj_pos = R->traj_pos; A.traj_vel = R->traj_vel; A.traj_t = R->traj_t;
+        }
+    }
+    if (!A.ev_tk || !A.queue || !A.n_nodes || !A.ev_step || !A.status)
+        return fail(ctx, CW_E_CUDA, "device arena exhausted (internal sizing error)");
+    return CW_OK;
+}
+
+static int run_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, Plan &pl, bool integrate, bool store_all,
+                     cudaStream_t stream)
+{
+    LaunchCfg cfg{s.sm_count, stream};
+    IntegArgs &A = pl.A;
+    CW_CK(ctx, cudaMemsetAsync(A.queue, 0, 64, stream));
+    CW_CK(ctx, cudaEventRecord(s.ev_t0, stream));
+    CW_CK(ctx, launch_grid_prepass(A, pl.sort ? pl.iota : nullptr, cfg));
+    ctx->last_launches += 1;
+    if (integrate) {
+        if (pl.sort) {
+            // longest orbits first: keys = node counts, values = orbit ids
+            CW_CK(ctx, cub::DeviceRadixSort::SortPairsDescending(pl.sort_tmp, pl.sort_bytes, (const int32_t *)A.n_nodes,
+                                                                 pl.keys_out, (const int32_t *)pl.iota, A.order,
+                                                                 (int)A.n, 0, 32, stream));
+        }
+        CW_CK(ctx, cudaEventRecord(s.ev_k0, stream));
+        if (o->integrator == CW_LEAPFROG) CW_CK(ctx, launch_leapfrog(ctx->pot, A, store_all, cfg));
+        else CW_CK(ctx, launch_dop853(ctx->pot, A, store_all, cfg));
+        ctx->last_launches += 1;
+        CW_CK(ctx, cudaEventRecord(s.ev_k1, stream));
+        s.timed = true;
+    }
+    return CW_OK;
+}
+
+static int validate(cw_ctx *ctx, const cw_opts *o, const cw_batch *B)
+{
+    if (!ctx || !o || !B) return CW_E_INVALID;
+    if (B->n_orbits < 0 || B->n_orbits > (int64_t)1 << 31) return fail(ctx, CW_E_INVALID, "n_orbits out of range");
+    if (B->n_orbits > 0 && (!B->w0 || !B->t1 || !B->t2 || !B->dt || !B->to_myr || !B->grid_flags))
+        return fail(ctx, CW_E_INVALID, "null input array");
+    if (o->mem_space != CW_MEM_HOST && o->mem_space != CW_MEM_DEVICE) return fail(ctx, CW_E_INVALID, "bad mem_space");
+    if (o->integrator != CW_LEAPFROG && o->integrator != CW_DOP853) return fail(ctx, CW_E_UNSUPPORTED, "unknown integrator");
+    if (ctx->slots.empty()) return fail(ctx, CW_E_NO_DEVICE, "context has no device");
+    return CW_OK;
+}
+
+// read one int64 that may live on the device
+static int fetch_i64(cw_ctx *ctx, const int64_t *p, bool on_device, int64_t *out)
+{
+    if (!on_device) { *out = *p; return CW_OK; }
+    CW_CK(ctx, cudaMemcpy(out, p, 8, cudaMemcpyDeviceToHost));
+    return CW_OK;
+}
+
+static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, const cw_result *R, bool integrate,
+                          int32_t *n_nodes_out, int32_t *ev_step_out)
+{
+    int rc = validate(ctx, o, B);
+    if (rc != CW_OK) return rc;
+    if (integrate && !ctx->has_pot) return fail(ctx, CW_E_NO_POTENTIAL, "cw_set_potential has not been called");
+    if (integrate && (!R || !R->w_final || !R->status)) return fail(ctx, CW_E_INVALID, "w_final and status are required");
+    ctx->last_launches = 0;
+    for (Slot &s : ctx->slots) { s.timed = false; s.last_kernel_ms = s.last_total_ms = 0.0; }
+    const int64_t n = B->n_orbits;
+    if (n == 0) return CW_OK;
+    const bool dev_mode = o->mem_space == CW_MEM_DEVICE;
+    const bool store_all = integrate && R->traj_off;
+    if (store_all && (!R->traj_pos || !R->traj_vel)) return fail(ctx, CW_E_INVALID, "traj_pos / traj_vel missing");
+
+    int prev = 0;
+    cudaGetDevice(&prev);
+    const int nslots = dev_mode ? 1 : (int)std::min<int64_t>((int64_t)ctx->slots.size(), std::max<int64_t>(1, n));
+    std::vector<Shard> shards(nslots);
+    std::vector<Plan> plans(nslots);
+    for (int d = 0; d < nslots; d++) {
+        Shard &sh = shards[d];
+        sh.a = n * d / nslots;
+        sh.b = n * (d + 1) / nslots;
+        if (B->ev_off) {
+            if ((rc = fetch_i64(ctx, B->ev_off + sh.a, dev_mode, &sh.ea)) != CW_OK) return rc;
+            if ((rc = fetch_i64(ctx, B->ev_off + sh.b, dev_mode, &sh.eb)) != CW_OK) return rc;
+        }
+        if (store_all) {
+            if ((rc = fetch_i64(ctx, R->traj_off + sh.a, dev_mode, &sh.ta)) != CW_OK) return rc;
+            if ((rc = fetch_i64(ctx, R->traj_off + sh.b, dev_mode, &sh.tb)) != CW_OK) return rc;
+        }
+        if (sh.eb < sh.ea || sh.tb < sh.ta) return fail(ctx, CW_E_INVALID, "offsets must be non-decreasing");
+    }
+    // phase 1: enqueue everything on every device (async), phase 2: copy back + sync
+    for (int d = 0; d < nslots; d++) {
+        Slot &s = ctx->slots[d];
+        cudaSetDevice(s.dev);
+        cudaStream_t stream = (dev_mode && o->stream) ? (cudaStream_t)o->stream : s.stream;
+        cw_result Rl;
+        memset(&Rl, 0, sizeof Rl);
+        if (R) Rl = *R;
+        if (!integrate) { Rl.n_nodes = n_nodes_out; Rl.ev_step = ev_step_out; }
+        rc = plan_shard(ctx, s, o, B, &Rl, shards[d], integrate, plans[d]);
+        if (rc == CW_OK) rc = run_shard(ctx, s, o, plans[d], integrate, store_all, stream);
+        if (rc != CW_OK) { cudaSetDevice(prev); return rc; }
+        if (!dev_mode) {
+            const Shard &sh = shards[d];
+            const IntegArgs &A = plans[d].A;
+            const int64_t m = sh.b - sh.a, K = sh.eb - sh.ea, Lt = sh.tb - sh.ta;
+            int32_t *nn = integrate ? R->n_nodes : n_nodes_out;
+            int32_t *es = integrate ? R->ev_step : ev_step_out;
+            if (nn) CW_CK(ctx, cudaMemcpyAsync(nn + sh.a, A.n_nodes, m * 4, cudaMemcpyDeviceToHost, stream));
+            if (es && K > 0) CW_CK(ctx, cudaMemcpyAsync(es + sh.ea, A.ev_step, K * 4, cudaMemcpyDeviceToHost, stream));
+            if (integrate) {
+                for (int c = 0; c < 6; c++)
+                    CW_CK(ctx, cudaMemcpyAsync(R->w_final + c * n + sh.a, A.w_final + c * m, m * 8, cudaMemcpyDeviceToHost, stream));
+                CW_CK(ctx, cudaMemcpyAsync(R->status + sh.a, A.status, m * 4, cudaMemcpyDeviceToHost, stream));
+                if (store_all && Lt > 0) {
+                    int64_t total = 0;
+                    total = R->traj_off[n];
+                    for (int c = 0; c < 3; c++) {
+                        CW_CK(ctx, cudaMemcpyAsync(R->traj_pos + c * total + sh.ta, A.traj_pos + c * Lt, Lt * 8, cudaMemcpyDeviceToHost, stream));
+                        CW_CK(ctx, cudaMemcpyAsync(R->traj_vel + c * total + sh.ta, A.traj_vel + c * Lt, Lt * 8, cudaMemcpyDeviceToHost, stream));
+                    }
+                    if (R->traj_t) CW_CK(ctx, cudaMemcpyAsync(R->traj_t + sh.ta, A.traj_t, Lt * 8, cudaMemcpyDeviceToHost, stream));
+                }
+            }
+        }
+    }
+    if (dev_mode && o->no_sync) { cudaSetDevice(prev); return CW_OK; }
+    int64_t stats[4] = {0, 0, 0, 0};
+    for (int d = 0; d < nslots; d++) {
+        Slot &s = ctx->slots[d];
+        cudaSetDevice(s.dev);
+        cudaStream_t stream = (dev_mode && o->stream) ? (cudaStream_t)o->stream : s.stream;
+        unsigned long long hs[4] = {0, 0, 0, 0};
+        if (integrate && R->stats)
+            CW_CK(ctx, cudaMemcpyAsync(hs, plans[d].A.stats, sizeof hs, cudaMemcpyDeviceToHost, stream));
+        CW_CK(ctx, cudaStreamSynchronize(stream));
+        for (int k = 0; k < 4; k++) stats[k] += (int64_t)hs[k];
+        if (s.timed) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) s.last_kernel_ms = ms;
+            if (cudaEventElapsedTime(&ms, s.ev_t0, s.ev_k1) == cudaSuccess) s.last_total_ms = ms;
+        }
+    }
+    if (integrate && R->stats) {
+        if (dev_mode) CW_CK(ctx, cudaMemcpy(R->stats, stats, sizeof stats, cudaMemcpyHostToDevice));
+        else memcpy(R->stats, stats, sizeof stats);
+    }
+    cudaSetDevice(prev);
+    return CW_OK;
+}
+
+extern "C" int cw_count_nodes(cw_ctx *ctx, const cw_opts *opts, const cw_batch *batch, int32_t *n_nodes, int32_t *ev_step)
+{
+    if (!n_nodes) return fail(ctx, CW_E_INVALID, "n_nodes is required");
+    return integrate_impl(ctx, opts, batch, nullptr, false, n_nodes, ev_step);
+}
+
+extern "C" int cw_integrate(cw_ctx *ctx, const cw_opts *opts, const cw_batch *batch, const cw_result *result)
+{
+    return integrate_impl(ctx, opts, batch, result, true, nullptr, nullptr);
+}
+
+extern "C" int64_t cw_last_launch_count(const cw_ctx *ctx) { return ctx ? ctx->last_launches : 0; }
+
+extern "C" double cw_last_kernel_ms(const cw_ctx *ctx, int dev)
+{
+    if (!ctx || dev < 0 || dev >= (int)ctx->slots.size()) return 0.0;
+    return ctx->slots[dev].last_kernel_ms;
+}
+
+extern "C" double cw_last_total_kernel_ms(const cw_ctx *ctx, int dev)
+{
+    if (!ctx || dev < 0 || dev >= (int)ctx->slots.size()) return 0.0;
+    return ctx->slots[dev].last_total_ms;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pointwise potential entry points
+
+static int pointwise(cw_ctx *ctx, int mode, int mem_space, int64_t n, const double *q, double *out)
+{
+    if (!ctx || !q || !out || n < 0) return fail(ctx, CW_E_INVALID, "bad arguments");
+    if (!ctx->has_pot) return fail(ctx, CW_E_NO_POTENTIAL, "cw_set_potential has not been called");
+    if (ctx->slots.empty()) return CW_E_NO_DEVICE;
+    if (n == 0) return CW_OK;
+    Slot &s = ctx->slots[0];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s.dev);
+    LaunchCfg cfg{s.sm_count, s.stream};
+    const int64_t n_out = (mode == 0) ? 3 * n : n;
+    ctx->last_launches = 1;
+    if (mem_space == CW_MEM_DEVICE) {
+        CW_CK(ctx, launch_pointwise(ctx->pot, mode, n, q, out, cfg));
+    } else {
+        CW_CK(ctx, s.arena.reserve(Arena::padded(3 * n, 8) + Arena::padded(n_out, 8) + 4096));
+        double *dq = s.arena.take<double>(3 * n), *dout = s.arena.take<double>(n_out);
+        CW_CK(ctx, cudaMemcpyAsync(dq, q, 3 * n * 8, cudaMemcpyHostToDevice, s.stream));
+        CW_CK(ctx, launch_pointwise(ctx->pot, mode, n, dq, dout, cfg));
+        CW_CK(ctx, cudaMemcpyAsync(out, dout, n_out * 8, cudaMemcpyDeviceToHost, s.stream));
+    }
+    CW_CK(ctx, cudaStreamSynchronize(s.stream));
+    cudaSetDevice(prev);
+    return CW_OK;
+}
+
+extern "C" int cw_gradient(cw_ctx *ctx, int mem_space, int64_t n, const double *q, double *grad)
+{
+    return pointwise(ctx, 0, mem_space, n, q, grad);
+}
+extern "C" int cw_potential_value(cw_ctx *ctx, int mem_space, int64_t n, const double *q, double *phi)
+{
+    return pointwise(ctx, 1, mem_space, n, q, phi);
+}
+extern "C" int cw_circular_velocity(cw_ctx *ctx, int mem_space, int64_t n, const double *q, double *vcirc)
+{
+    return pointwise(ctx, 2, mem_space, n, q, vcirc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagnostics
+
+extern "C" double cw_measure_fp64_peak(cw_ctx *ctx, int dev, double ms_target)
+{
+    if (!ctx || dev < 0 || dev >= (int)ctx->slots.size()) return -1.0;
+    Slot &s = ctx->slots[dev];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s.dev);
+    LaunchCfg cfg{s.sm_count, s.stream};
+    double result = -1.0;
+    do {
+        if (s.arena.reserve(4096) != cudaSuccess) break;
+        double *sink = s.arena.take<double>(8);
+        int blocks = 0, threads = 0, iters = 20000;
+        float ms = 0.f;
+        // warm-up + calibration pass, then the timed pass sized for ~ms_target
+        for (int pass = 0; pass < 2; pass++) {
+            if (cudaEventRecord(s.ev_k0, s.stream) != cudaSuccess) break;
+            if (launch_dfma_peak(sink, iters, cfg, &blocks, &threads) != cudaSuccess) break;
+            if (cudaEventRecord(s.ev_k1, s.stream) != cudaSuccess) break;
+            if (cudaStreamSynchronize(s.stream) != cudaSuccess) break;
+            if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) != cudaSuccess) break;
+            if (pass == 0 && ms > 0.f) {
+                double scale = (ms_target > 0 ? ms_target : 50.0) / ms;
+                if (scale > 200.0) scale = 200.0;
+                if (scale < 0.05) scale = 0.05;
+                iters = (int)(iters * scale);
+                if (iters < 1000) iters = 1000;
+            }
+        }
+        if (ms > 0.f) result = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads / (ms * 1e-3) / 1e12;
+    } while (0);
+    cudaGetLastError();
+    cudaSetDevice(prev);
+    return result;
+}
+
+extern "C" int cw_selftest_math(cw_ctx *ctx, int64_t n, double *out)
+{
+    if (!ctx || !out || ctx->slots.empty()) return CW_E_INVALID;
+    Slot &s = ctx->slots[0];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s.dev);
+    LaunchCfg cfg{s.sm_count, s.stream};
+    CW_CK(ctx, s.arena.reserve(4096));
+    double *d = s.arena.take<double>(4);
+    CW_CK(ctx, launch_math_selftest(n, d, cfg));
+    CW_CK(ctx, cudaMemcpyAsync(out, d, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CW_CK(ctx, cudaStreamSynchronize(s.stream));
+    cudaSetDevice(prev);
+    return CW_OK;
+}

@@ -1,0 +1,241 @@
+// cw_device.cuh -- device-side building blocks shared by every kernel of the path:
+// FP64 special functions built for the DFMA pipe, the potential parameter block and the
+// analytic composite gradient (the B200 replacement for gala's builtin_potentials.c +
+// cpotential.c c_gradient; algorithm restated in oracle/cw_oracle.c).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/cogsworth_b200.h"
+
+namespace cw {
+
+// ------------------------------------------------------------------------------------------
+// FP64 special functions.  B200 has no FP64 SFU: sqrt / divide / log are DFMA sequences seeded
+// by MUFU.RSQ64H / MUFU.RCP64H (the only FP64-related ops that run OFF the FP64 pipe).  The CUDA
+// library versions carry special-case branches (denormals, inf, negative) that orbits never hit;
+// these versions are branch-free and cost 5 / 3 / ~12 FP64-pipe instructions.
+// ------------------------------------------------------------------------------------------
+
+// 1/sqrt(x), x normal and positive.  Seed (~2^-22 rel. error) + one third-order step:
+// y(1 + e/2 + 3e^2/8), e = 1 - x y^2  -> error O(e^3) plus rounding (<= ~1 ulp).
+__device__ __forceinline__ double rsqrt_fast(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double t = x * y;
+    double e = fma(-t, y, 1.0);
+    double p = fma(0.375, e, 0.5);
+    double q = y * e;
+    return fma(q, p, y);
+}
+
+// 1/x, x normal.  Seed + one third-order step y(1 + e + e^2), e = 1 - x y.
+__device__ __forceinline__ double rcp_fast(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    double t = fma(e, e, e);
+    return fma(y, t, y);
+}
+
+// ln(x) for normal positive x (here x = 1 + r/r_s >= 1).  Classic reduction x = 2^k m,
+// m in [sqrt(1/2), sqrt(2)), s = (m-1)/(m+1), ln m = 2s + s R(s^2) with the degree-7 minimax
+// polynomial of fdlibm's e_log.c (|s| <= 0.1716, error < 2^-58.45).  Exponent handling is integer
+// work on the ALU pipe, k -> double by the 2^52 bias trick (no I2F): 1 MUFU + 16 FP64-pipe
+// instructions, no branches, no special cases.
+__device__ __forceinline__ double log_fast(double x)
+{
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int k = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;        // m in [1, 2)
+    const int big = (hi >= 0x3ff6a09f);          // m >= ~sqrt(2): halve it
+    hi -= big << 20;
+    k += big;
+    const double m = __hiloint2double(hi, lo);
+    const double kd = __hiloint2double(0x43300000, k ^ 0x80000000) - 4503601774854144.0; // 2^52 + 2^31
+    const double s = (m - 1.0) * rcp_fast(m + 1.0);
+    const double z = s * s;
+    double R = 1.479819860511658591e-01;
+    R = fma(R, z, 1.531383769920937332e-01);
+    R = fma(R, z, 1.818357216161805012e-01);
+    R = fma(R, z, 2.222219843214978396e-01);
+    R = fma(R, z, 2.857142874366239149e-01);
+    R = fma(R, z, 3.999999999940941908e-01);
+    R = fma(R, z, 6.666666666666735130e-01);
+    const double r = fma(s, R * z, s + s);       // 2s + s z R
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    return fma(kd, LN2_HI, fma(kd, LN2_LO, r));
+}
+
+// ------------------------------------------------------------------------------------------
+// Potential parameter block.  Passed by value as a __grid_constant__ kernel parameter, i.e. it
+// lives in the constant bank (c[0x0][...]) and every access is a uniform broadcast -- the
+// per-launch equivalent of a __constant__ symbol, but safe with several devices/streams per
+// process.
+// ------------------------------------------------------------------------------------------
+enum PotKind : int {
+    POT_GENERIC = 0, // any ordered list of components (loop + switch)
+    POT_MW_V1 = 1,   // MiyamotoNagai + Hernquist + Hernquist + spherical NFW
+    POT_MW_V2 = 2    // 3 x MiyamotoNagai sharing b (MN3 disk) + Hernquist + Hernquist + NFW
+};
+
+struct PotParams {
+    int32_t kind;
+    int32_t n_comp;
+    double G;
+    int32_t type[CW_MAX_COMPONENTS];
+    double GM[CW_MAX_COMPONENTS]; // fl(G * m), the same product gala forms on every call
+    double p1[CW_MAX_COMPONENTS]; // a | c | r_s
+    double p2[CW_MAX_COMPONENTS]; // b | - | 1/r_s
+    // pre-digested copies for the specialised kinds (MN terms first, then the spherical ones)
+    double mn_GM[3], mn_a[3], mn_b2[3];
+    double h_GM[2], h_c[2];
+    double nfw_GM, nfw_rs, nfw_inv_rs;
+};
+
+// Specialised composite: NMN Miyamoto-Nagai terms (+ optionally one shared b), two Hernquist
+// spheres and one spherical NFW halo.  FP64-pipe instruction budget (v2): ~105 per gradient.
+//   MN(m,a,b):   sz = sqrt(z^2+b^2); zd = a+sz; f = GM (R^2+zd^2)^-3/2;  g += (f x, f y, f z (1 + a/sz))
+//   Hernquist:   f = GM / ((r+c)^2 r);                                    g += f q
+//   NFW:         f = GM (ln(1+r/rs) - r/(r+rs)) / r^3;                    g += f q
+template <int NMN, bool SHARED_B>
+__device__ __forceinline__ void gradient_mw(const PotParams &P, double x, double y, double z,
+                                            double &gx, double &gy, double &gz)
+{
+    const double R2 = fma(y, y, x * x);
+    const double z2 = z * z;
+    const double r2 = R2 + z2;
+
+    double fxy = 0.0, fz = 0.0;
+    double isz_shared = 0.0, sz_shared = 0.0;
+    if (SHARED_B) {
+        const double q = z2 + P.mn_b2[0];
+        isz_shared = rsqrt_fast(q);
+        sz_shared = q * isz_shared;
+    }
+#pragma unroll
+    for (int i = 0; i < NMN; i++) {
+        double isz, sz;
+        if (SHARED_B) {
+            isz = isz_shared;
+            sz = sz_shared;
+        } else {
+            const double q = z2 + P.mn_b2[i];
+            isz = rsqrt_fast(q);
+            sz = q * isz;
+        }
+        const double zd = P.mn_a[i] + sz;
+        const double s = fma(zd, zd, R2);
+        const double rs = rsqrt_fast(s);
+        const double f = (rs * rs) * (P.mn_GM[i] * rs);
+        fxy += f;
+        fz = fma(f, fma(P.mn_a[i], isz, 1.0), fz);
+    }
+
+    const double ir = rsqrt_fast(r2);
+    const double r = r2 * ir;
+    // two Hernquist spheres
+    const double rc0 = r + P.h_c[0], rc1 = r + P.h_c[1];
+    double h = P.h_GM[0] * rcp_fast(rc0 * rc0);
+    h = fma(P.h_GM[1], rcp_fast(rc1 * rc1), h);
+    // NFW
+    const double u = r * P.nfw_inv_rs;
+    const double w = 1.0 + u;
+    const double bracket = log_fast(w) - u * rcp_fast(w);
+    const double ir3 = (ir * ir) * ir;
+    double fs = h * ir;
+    fs = fma(P.nfw_GM * ir3, bracket, fs);
+
+    gx = (fxy + fs) * x;
+    gy = (fxy + fs) * y;
+    gz = (fz + fs) * z;
+}
+
+// Generic composite: components in the caller's order.
+__device__ __forceinline__ void gradient_generic(const PotParams &P, double x, double y, double z,
+                                                 double &gx, double &gy, double &gz)
+{
+    const double R2 = fma(y, y, x * x);
+    const double z2 = z * z;
+    const double r2 = R2 + z2;
+    double fxy = 0.0, fz = 0.0;
+    double ir = 0.0, r = 0.0;
+    bool have_r = false;
+    for (int i = 0; i < P.n_comp; i++) {
+        const int t = P.type[i];
+        if (t == CW_COMP_MIYAMOTO_NAGAI) {
+            const double q = fma(P.p2[i], P.p2[i], z2);
+            const double isz = rsqrt_fast(q);
+            const double zd = P.p1[i] + q * isz;
+            const double rs = rsqrt_fast(fma(zd, zd, R2));
+            const double f = (rs * rs) * (P.GM[i] * rs);
+            fxy += f;
+            fz = fma(f, fma(P.p1[i], isz, 1.0), fz);
+        } else {
+            if (!have_r) {
+                ir = rsqrt_fast(r2);
+                r = r2 * ir;
+                have_r = true;
+            }
+            double f;
+            if (t == CW_COMP_HERNQUIST) {
+                const double rc = r + P.p1[i];
+                f = P.GM[i] * rcp_fast(rc * rc) * ir;
+            } else { // CW_COMP_NFW_SPHERICAL
+                const double u = r * P.p2[i];               // p2 = 1/r_s for NFW
+                const double w = 1.0 + u;
+                const double bracket = log_fast(w) - u * rcp_fast(w);
+                f = P.GM[i] * ((ir * ir) * ir) * bracket;
+            }
+            fxy += f;
+            fz += f;
+        }
+    }
+    gx = fxy * x;
+    gy = fxy * y;
+    gz = fz * z;
+}
+
+template <int KIND>
+__device__ __forceinline__ void gradient(const PotParams &P, double x, double y, double z,
+                                         double &gx, double &gy, double &gz)
+{
+    if (KIND == POT_MW_V1) gradient_mw<1, false>(P, x, y, z, gx, gy, gz);
+    else if (KIND == POT_MW_V2) gradient_mw<3, true>(P, x, y, z, gx, gy, gz);
+    else gradient_generic(P, x, y, z, gx, gy, gz);
+}
+
+// dt of a segment = t[1] - t[0] with both nodes converted to Myr first (gala converts the whole
+// time array, then differences it).  The orbit is sensitive to the last bit of dt (a 2e-12
+// relative change moves a 1 Gyr leapfrog orbit by ~1e-10), so the two products and the difference
+// are rounded separately -- no FMA contraction.
+__device__ __forceinline__ double seg_dt_myr(double t0, double t1, double to_myr)
+{
+    return __dsub_rn(__dmul_rn(t1, to_myr), __dmul_rn(t0, to_myr));
+}
+
+// Phi of the same components (gala *_value functions) -- for the N3 rows, not the hot loop.
+__device__ __forceinline__ double potential_value(const PotParams &P, double x, double y, double z)
+{
+    const double R2 = fma(y, y, x * x);
+    const double z2 = z * z;
+    const double r = sqrt(R2 + z2);
+    double v = 0.0;
+    for (int i = 0; i < P.n_comp; i++) {
+        const int t = P.type[i];
+        if (t == CW_COMP_MIYAMOTO_NAGAI) {
+            const double zd = P.p1[i] + sqrt(fma(P.p2[i], P.p2[i], z2));
+            v -= P.GM[i] / sqrt(fma(zd, zd, R2));
+        } else if (t == CW_COMP_HERNQUIST) {
+            v -= P.GM[i] / (r + P.p1[i]);
+        } else {
+            const double u = r / P.p1[i];
+            v -= (P.GM[i] / P.p1[i]) * log(1.0 + u) / u;
+        }
+    }
+    return v;
+}
+
+} // namespace cw

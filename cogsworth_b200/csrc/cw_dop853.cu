@@ -1,0 +1,353 @@
+// cw_dop853.cu -- adaptive Dormand-Prince 8(5,3) kernel (sm_100a).
+//
+// Reference semantics (restated in oracle/cw_oracle.c: cwo_dop853 / cwo_dop853_segment):
+//   gala dop853.pyx dop853_integrate_hamiltonian: for every grid interval [t[j-1], t[j]] a fresh
+//   Hairer dop853() with h = dt0 = t[1]-t[0] of the segment, itoler = 0, atol = rtol = 1e-10 by
+//   default, safe = 0.9, fac1 = 0.333, fac2 = 6, beta = 0, hmax = xend - x, nmax = 100000,
+//   nstiff = 1, uround = 2.3e-16; the error norm runs over the 6 components of the one orbit.
+//   cogsworth restarts the integrator at every kick node (kicks.py:132-183).
+//
+// Execution model: persistent lanes, as in cw_leapfrog.cu, but the unit of work inside the loop is
+// ONE RK STEP ATTEMPT of the lane's own current interval.  Lanes of a warp are not held at
+// interval boundaries: a lane that needs sub-steps near the nucleus simply falls behind in ITS
+// orbit while its neighbours keep advancing theirs (warp-level early exit: the warp leaves the
+// loop when a ballot shows no lane has work and the queue is empty).  Divergence therefore costs
+// only the difference in total attempts per orbit, not per interval.
+//
+// The first stage of every interval, k1 = f(t_j, y_j), is bit-identical to the derivative Hairer
+// evaluates at the end of the previous accepted step (same y), so it is carried over instead of
+// being recomputed: 12 gradient evaluations per accepted step instead of gala's 13.
+#include <cooperative_groups.h>
+#include <climits>
+#include "cw_kernels.cuh"
+#include "../../include/cw_dop853_coeffs.h"
+
+namespace cg = cooperative_groups;
+
+namespace cw {
+
+constexpr int DP_BLOCK = 128;
+
+struct DpLane {
+    double y[6];      // state at time x
+    double k1[6];     // f(x, y) = (v, -grad)
+    double x, xend;   // current time / end of the current interval (Myr)
+    double h;         // trial step
+    double hmax, facold, hlamb;
+    double dt0;       // h0 of every interval of the current segment
+    double tgrid;     // grid time of node j (grid unit, FP64-accumulated)
+    double hgrid, t2, smyr;
+    int64_t e, e1, oid;
+    int j, L;
+    int nstep, naccpt, iasti, nonsti;
+    bool last, reject, append;
+};
+
+__device__ __forceinline__ int64_t dp_queue_pop(unsigned long long *queue)
+{
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(queue, (unsigned long long)g.size());
+    base = g.shfl(base, 0);
+    return (int64_t)(base + g.thread_rank());
+}
+
+template <int KIND>
+__device__ __forceinline__ void fcn(const PotParams &P, const double *y, double *f)
+{
+    double gx, gy, gz;
+    gradient<KIND>(P, y[0], y[1], y[2], gx, gy, gz);
+    f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
+    f[3] = -gx; f[4] = -gy; f[5] = -gz;
+}
+
+template <bool STORE>
+__device__ __forceinline__ void dp_store_sample(const IntegArgs &A, const DpLane &s)
+{
+    if (STORE) {
+        const int64_t col = A.traj_off[s.oid] - A.traj_base + s.j;
+        A.traj_pos[col] = s.y[0];
+        A.traj_pos[A.traj_total + col] = s.y[1];
+        A.traj_pos[2 * A.traj_total + col] = s.y[2];
+        A.traj_vel[col] = s.y[3];
+        A.traj_vel[A.traj_total + col] = s.y[4];
+        A.traj_vel[2 * A.traj_total + col] = s.y[5];
+        if (A.traj_t) A.traj_t[col] = s.tgrid * s.smyr;
+    }
+}
+
+__device__ __forceinline__ void dp_write_final(const IntegArgs &A, const DpLane &s, int status)
+{
+    const int64_t n = A.n;
+#pragma unroll
+    for (int c = 0; c < 6; c++) A.w_final[c * n + s.oid] = s.y[c];
+    if (status != CW_ORBIT_OK) A.status[s.oid] = status;
+}
+
+// kicks on node s.j: v += dv, the velocity half of k1 follows, the segment restarts with a new dt0
+__device__ __forceinline__ void dp_apply_kicks(const IntegArgs &A, DpLane &s)
+{
+    while (s.e < s.e1 && A.ev_step[s.e] == s.j) {
+        s.y[3] += A.ev_dv[3 * s.e + 0];
+        s.y[4] += A.ev_dv[3 * s.e + 1];
+        s.y[5] += A.ev_dv[3 * s.e + 2];
+        const double tk = A.ev_tk[s.e];
+        const double tn = (s.append && s.j + 1 == s.L) ? s.t2 : tk + s.hgrid;
+        s.dt0 = seg_dt_myr(tk, tn, s.smyr);
+        s.e++;
+    }
+    s.k1[0] = s.y[3]; s.k1[1] = s.y[4]; s.k1[2] = s.y[5];
+}
+
+// open the interval [node j, node j+1] = the argument set of one dop853() call
+__device__ __forceinline__ void dp_begin_interval(DpLane &s)
+{
+    const double tn = (s.append && s.j + 1 == s.L) ? s.t2 : s.tgrid + s.hgrid;
+    s.x = s.tgrid * s.smyr;
+    s.xend = tn * s.smyr;
+    s.h = s.dt0;
+    s.hmax = fabs(s.xend - s.x);
+    s.facold = 1.0e-4;
+    s.hlamb = 0.0;
+    s.nstep = 0; s.naccpt = 0; s.iasti = 0; s.nonsti = 0;
+    s.last = false; s.reject = false;
+}
+
+template <int KIND, bool STORE>
+__global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant__ PotParams P,
+                                                          const __grid_constant__ IntegArgs A)
+{
+    const unsigned FULL = 0xffffffffu;
+    DpLane s;
+#pragma unroll
+    for (int c = 0; c < 6; c++) { s.y[c] = (c == 0) ? 8.0 : 0.0; s.k1[c] = 0.0; }
+    s.x = 0.0; s.xend = 1.0; s.h = 1.0; s.hmax = 1.0; s.facold = 1e-4; s.hlamb = 0.0; s.dt0 = 1.0;
+    s.tgrid = 0.0; s.hgrid = 1.0; s.t2 = 0.0; s.smyr = 1.0;
+    s.e = s.e1 = 0; s.oid = -1; s.j = 0; s.L = 0;
+    s.nstep = s.naccpt = s.iasti = s.nonsti = 0;
+    s.last = s.reject = s.append = false;
+    bool active = false, exhausted = false, interval_done = false;
+    unsigned long long n_acc = 0, n_rej = 0, n_fcn = 0, n_int = 0;
+    const int64_t nmax = (A.nmax > 0) ? A.nmax : 100000;
+    const double atol = A.atol, rtol = A.rtol;
+
+    for (;;) {
+        // ---- phase A: lanes that completed an interval stand on node j+1
+        if (active && interval_done) {
+            interval_done = false;
+            s.j += 1;
+            s.tgrid = (s.append && s.j == s.L) ? s.t2 : s.tgrid + s.hgrid;
+            n_int++;
+            dp_apply_kicks(A, s);
+            dp_store_sample<STORE>(A, s);
+            if (s.j == s.L) {
+                dp_write_final(A, s, CW_ORBIT_OK);
+                active = false;
+            } else {
+                dp_begin_interval(s);
+            }
+        }
+        // ---- phase B: idle lanes pull the next orbit
+        while (!active && !exhausted) {
+            const int64_t p = dp_queue_pop(A.queue);
+            if (p >= A.n) { exhausted = true; break; }
+            const int64_t o = A.order ? (int64_t)A.order[p] : p;
+            const int64_t n = A.n;
+            s.oid = o;
+#pragma unroll
+            for (int c = 0; c < 6; c++) s.y[c] = A.w0[c * n + o];
+            s.j = 0;
+            s.L = A.n_nodes[o] - 1;
+            if (A.status[o] != CW_ORBIT_OK || s.L < 0) {
+                dp_write_final(A, s, CW_ORBIT_OK); // status already set by the pre-pass
+                continue;
+            }
+            s.hgrid = A.dt[o]; s.t2 = A.t2[o]; s.smyr = A.to_myr[o];
+            s.append = (A.flags[o] & CW_GRID_APPEND_T2) != 0;
+            s.tgrid = A.t1[o];
+            s.e = s.e1 = 0;
+            if (A.ev_off) { s.e = A.ev_off[o] - A.ev_base; s.e1 = A.ev_off[o + 1] - A.ev_base; }
+            {
+                const double tn = (s.append && s.L == 1) ? s.t2 : s.tgrid + s.hgrid;
+                s.dt0 = seg_dt_myr(s.tgrid, tn, s.smyr);
+            }
+            dp_apply_kicks(A, s);
+            dp_store_sample<STORE>(A, s);
+            if (s.L == 0) { dp_write_final(A, s, CW_ORBIT_OK); continue; }
+            fcn<KIND>(P, s.y, s.k1);
+            n_fcn++;
+            dp_begin_interval(s);
+            active = true;
+        }
+        if (!__any_sync(FULL, active)) break;   // warp-level early exit
+
+        // ---- phase C: one step attempt of dopcor() for every lane that has an open interval
+        if (active) {
+            int fail = 0;
+            if (s.nstep > nmax) fail = CW_ORBIT_NMAX;
+            else if (0.1 * fabs(s.h) <= fabs(s.x) * 2.3e-16) fail = CW_ORBIT_STEP_TOO_SMALL;
+            if (fail) {
+                dp_write_final(A, s, fail);
+                active = false;
+                continue;
+            }
+            const double posneg = (s.xend - s.x > 0.0) ? 1.0 : -1.0;
+            if (__dmul_rn(__dsub_rn(__dadd_rn(s.x, __dmul_rn(1.01, s.h)), s.xend), posneg) > 0.0) { s.h = __dsub_rn(s.xend, s.x); s.last = true; }
+            s.nstep++;
+            const double h = s.h;
+            const double *y = s.y, *k1 = s.k1;
+            double k2[6], k3[6], k4[6], k5[6], k6[6], k7[6], k8[6], k9[6], k10[6], yy1[6];
+
+#define CW_STAGE(EXPR) _Pragma("unroll") for (int i = 0; i < 6; i++) yy1[i] = fma(h, (EXPR), y[i]);
+            CW_STAGE(CW_A0201 * k1[i])
+            fcn<KIND>(P, yy1, k2);
+            CW_STAGE(fma(CW_A0302, k2[i], CW_A0301 * k1[i]))
+            fcn<KIND>(P, yy1, k3);
+            CW_STAGE(fma(CW_A0403, k3[i], CW_A0401 * k1[i]))
+            fcn<KIND>(P, yy1, k4);
+            CW_STAGE(fma(CW_A0504, k4[i], fma(CW_A0503, k3[i], CW_A0501 * k1[i])))
+            fcn<KIND>(P, yy1, k5);
+            CW_STAGE(fma(CW_A0605, k5[i], fma(CW_A0604, k4[i], CW_A0601 * k1[i])))
+            fcn<KIND>(P, yy1, k6);
+            CW_STAGE(fma(CW_A0706, k6[i], fma(CW_A0705, k5[i], fma(CW_A0704, k4[i], CW_A0701 * k1[i]))))
+            fcn<KIND>(P, yy1, k7);
+            CW_STAGE(fma(CW_A0807, k7[i], fma(CW_A0806, k6[i], fma(CW_A0805, k5[i], fma(CW_A0804, k4[i], CW_A0801 * k1[i])))))
+            fcn<KIND>(P, yy1, k8);
+            CW_STAGE(fma(CW_A0908, k8[i], fma(CW_A0907, k7[i], fma(CW_A0906, k6[i], fma(CW_A0905, k5[i], fma(CW_A0904, k4[i], CW_A0901 * k1[i]))))))
+            fcn<KIND>(P, yy1, k9);
+            CW_STAGE(fma(CW_A1009, k9[i], fma(CW_A1008, k8[i], fma(CW_A1007, k7[i], fma(CW_A1006, k6[i], fma(CW_A1005, k5[i], fma(CW_A1004, k4[i], CW_A1001 * k1[i])))))))
+            fcn<KIND>(P, yy1, k10);
+            CW_STAGE(fma(CW_A1110, k10[i], fma(CW_A1109, k9[i], fma(CW_A1108, k8[i], fma(CW_A1107, k7[i], fma(CW_A1106, k6[i], fma(CW_A1105, k5[i], fma(CW_A1104, k4[i], CW_A1101 * k1[i]))))))))
+            fcn<KIND>(P, yy1, k2);
+            const double xph = __dadd_rn(s.x, h);
+            CW_STAGE(fma(CW_A1211, k2[i], fma(CW_A1210, k10[i], fma(CW_A1209, k9[i], fma(CW_A1208, k8[i], fma(CW_A1207, k7[i], fma(CW_A1206, k6[i], fma(CW_A1205, k5[i], fma(CW_A1204, k4[i], CW_A1201 * k1[i])))))))))
+            fcn<KIND>(P, yy1, k3);
+#undef CW_STAGE
+            n_fcn += 11;
+
+            double err = 0.0, err2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                k4[i] = fma(CW_B12, k3[i], fma(CW_B11, k2[i], fma(CW_B10, k10[i], fma(CW_B09, k9[i],
+                        fma(CW_B08, k8[i], fma(CW_B07, k7[i], fma(CW_B06, k6[i], CW_B01 * k1[i])))))));
+                k5[i] = fma(h, k4[i], y[i]);
+                const double sk = fma(rtol, fmax(fabs(y[i]), fabs(k5[i])), atol);
+                const double isk = rcp_fast(sk);
+                double erri = k4[i] - CW_BHH1 * k1[i] - CW_BHH2 * k9[i] - CW_BHH3 * k3[i];
+                double sq = erri * isk;
+                err2 = fma(sq, sq, err2);
+                erri = fma(CW_ER12, k3[i], fma(CW_ER11, k2[i], fma(CW_ER10, k10[i], fma(CW_ER09, k9[i],
+                       fma(CW_ER08, k8[i], fma(CW_ER07, k7[i], fma(CW_ER06, k6[i], CW_ER01 * k1[i])))))));
+                sq = erri * isk;
+                err = fma(sq, sq, err);
+            }
+            double deno = fma(0.01, err2, err);
+            if (deno <= 0.0) deno = 1.0;
+            err = fabs(h) * err * sqrt(1.0 / (deno * 6.0));
+            if (!(err <= 1.79769313486231571e+308)) {   // NaN or inf: Hairer would spin to nmax
+                dp_write_final(A, s, CW_ORBIT_NONFINITE);
+                active = false;
+                continue;
+            }
+            const double fac11 = sqrt(sqrt(sqrt(err)));            // err^(1/8), beta = 0
+            const double facc1 = 1.0 / 0.333, facc2 = 1.0 / 6.0, safe = 0.9;
+            const double fac = fmax(facc2, fmin(facc1, fac11 / safe));
+            double hnew = h / fac;
+            if (err <= 1.0) {
+                // ---- step accepted
+                s.facold = fmax(err, 1.0e-4);
+                s.naccpt++;
+                n_acc++;
+                fcn<KIND>(P, k5, k4);       // first stage of the next step
+                n_fcn++;
+                // stiffness detection (nstiff = 1: every accepted step)
+                double stnum = 0.0, stden = 0.0;
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    const double a = k4[i] - k3[i];
+                    stnum = fma(a, a, stnum);
+                    const double b = k5[i] - yy1[i];
+                    stden = fma(b, b, stden);
+                }
+                if (stden > 0.0) s.hlamb = h * sqrt(stnum / stden);
+                bool stiff = false;
+                if (s.hlamb > 6.1) {
+                    s.nonsti = 0;
+                    s.iasti++;
+                    if (s.iasti == 15) stiff = true;
+                } else {
+                    s.nonsti++;
+                    if (s.nonsti == 6) s.iasti = 0;
+                }
+#pragma unroll
+                for (int i = 0; i < 6; i++) { s.k1[i] = k4[i]; s.y[i] = k5[i]; }
+                s.x = xph;
+                if (stiff) {
+                    dp_write_final(A, s, CW_ORBIT_STIFF);
+                    active = false;
+                    continue;
+                }
+                if (s.last) {
+                    interval_done = true;
+                } else {
+                    if (fabs(hnew) > s.hmax) hnew = posneg * s.hmax;
+                    if (s.reject) hnew = posneg * fmin(fabs(hnew), fabs(h));
+                    s.reject = false;
+                    s.h = hnew;
+                }
+            } else {
+                // ---- step rejected
+                hnew = h / fmin(facc1, fac11 / safe);
+                s.reject = true;
+                if (s.naccpt >= 1) n_rej++;
+                s.last = false;
+                s.h = hnew;
+            }
+        }
+    }
+    if (A.stats) {
+        for (int off = 16; off > 0; off >>= 1) {
+            n_acc += __shfl_down_sync(FULL, n_acc, off);
+            n_rej += __shfl_down_sync(FULL, n_rej, off);
+            n_fcn += __shfl_down_sync(FULL, n_fcn, off);
+            n_int += __shfl_down_sync(FULL, n_int, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (n_acc) atomicAdd(A.stats + 0, n_acc);
+            if (n_rej) atomicAdd(A.stats + 1, n_rej);
+            if (n_fcn) atomicAdd(A.stats + 2, n_fcn);
+            if (n_int) atomicAdd(A.stats + 3, n_int);
+        }
+    }
+}
+
+template <int KIND, bool STORE>
+static cudaError_t launch_dp(const PotParams &P, const IntegArgs &A, const LaunchCfg &cfg)
+{
+    int per_sm = 0;
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dop853_kernel<KIND, STORE>,
+                                                                    DP_BLOCK, 0);
+    if (err != cudaSuccess) return err;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)cfg.sm_count * per_sm;
+    const int64_t need = (A.n + DP_BLOCK - 1) / DP_BLOCK;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    dop853_kernel<KIND, STORE><<<(unsigned)grid, DP_BLOCK, 0, cfg.stream>>>(P, A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dop853(const PotParams &P, const IntegArgs &A, bool store_all, const LaunchCfg &cfg)
+{
+    if (A.n <= 0) return cudaSuccess;
+    switch (P.kind) {
+    case POT_MW_V1:
+        return store_all ? launch_dp<POT_MW_V1, true>(P, A, cfg) : launch_dp<POT_MW_V1, false>(P, A, cfg);
+    case POT_MW_V2:
+        return store_all ? launch_dp<POT_MW_V2, true>(P, A, cfg) : launch_dp<POT_MW_V2, false>(P, A, cfg);
+    default:
+        return store_all ? launch_dp<POT_GENERIC, true>(P, A, cfg) : launch_dp<POT_GENERIC, false>(P, A, cfg);
+    }
+}
+
+} // namespace cw

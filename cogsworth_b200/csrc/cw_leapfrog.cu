@@ -1,0 +1,302 @@
+// cw_leapfrog.cu -- grid pre-pass and the fixed-step leapfrog kernel (sm_100a).
+//
+// Reference semantics (restated in oracle/cw_oracle.c):
+//   time grid + kick node      cogsworth kicks.py:97,118-122,134; gala timespec.py
+//   leapfrog                   gala leapfrog.pyx c_init_velocity / c_leapfrog_step
+//   segment restart at kicks   cogsworth kicks.py:132-183
+//
+// Execution model: PERSISTENT LANES.  The grid is sized to fill the 148 SMs exactly once; every
+// lane (thread) owns one orbit at a time and pulls the next one from a global queue (longest
+// orbits first) the moment its own finishes, so divergent step counts never leave lanes idle
+// behind a warp-wide barrier and there is no wave-quantisation tail.  Inside a warp the hot loop
+// runs a warp-uniform number of branch-free steps (the minimum over lanes of the distance to the
+// lane's next kick / last node), then the lanes that reached such a node handle it.
+#include <cooperative_groups.h>
+#include <climits>
+#include "cw_kernels.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace cw {
+
+// ------------------------------------------------------------------------------------------
+// Grid pre-pass: one thread per orbit walks T_{j+1} = T_j + dt in FP64 exactly as
+// parse_time_specification does and resolves, for every event, k = max(cursor, last j with
+// T_j < t_event) -- the bit-exact kick timing the reference defines at kicks.py:134.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grid_prepass_kernel(const __grid_constant__ IntegArgs A, int32_t *iota)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    const double a = A.t1[i], b = A.t2[i], h = A.dt[i];
+    const bool append = (A.flags[i] & CW_GRID_APPEND_T2) != 0;
+    int64_t e = 0, e1 = 0;
+    if (A.ev_off) {
+        e = A.ev_off[i] - A.ev_base;
+        e1 = A.ev_off[i + 1] - A.ev_base;
+    }
+    int st = CW_ORBIT_OK;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double te = (e < e1) ? A.ev_time[e] : INF;
+    double te_prev = -INF;
+    int j = 0, cursor = 0;
+    double T = a, Tprev = a;
+    while (T < b && j < 1000000) {
+        // node j exists at time T; every pending event with t_event <= T lands before it
+        while (!(T < te)) {
+            const int k = max(cursor, j - 1);
+            A.ev_step[e] = k;
+            A.ev_tk[e] = Tprev;
+            cursor = k;
+            if (te < te_prev) st = CW_ORBIT_INCONSISTENT; // events must be chronological
+            te_prev = te;
+            e++;
+            te = (e < e1) ? A.ev_time[e] : INF;
+        }
+        Tprev = T;
+        j++;
+        T += h;
+    }
+    const int n_acc = j;
+    const int n_nodes = n_acc + ((append && n_acc > 0) ? 1 : 0);
+    // events not before any accumulated node boundary: after the last accumulated node
+    while (e < e1) {
+        int k;
+        if (append && te > b) k = n_nodes - 1;        // later than t2 itself: lands on the final node
+        else k = max(cursor, n_acc - 1);
+        A.ev_step[e] = k;
+        A.ev_tk[e] = Tprev;
+        cursor = k;
+        if (te < te_prev) st = CW_ORBIT_INCONSISTENT;
+        te_prev = te;
+        e++;
+        te = (e < e1) ? A.ev_time[e] : INF;
+    }
+    // a kick on the final node leaves no tail segment: the reference cannot stitch such an orbit
+    if (n_nodes <= 0 || (cursor >= n_nodes - 1 && (e1 > (A.ev_off ? A.ev_off[i] - A.ev_base : 0))))
+        st = CW_ORBIT_INCONSISTENT;
+    A.n_nodes[i] = n_nodes;
+    A.status[i] = st;
+    if (iota) iota[i] = (int32_t)i;
+}
+
+cudaError_t launch_grid_prepass(const IntegArgs &A, int32_t *iota_out, const LaunchCfg &cfg)
+{
+    if (A.n <= 0) return cudaSuccess;
+    const int block = 256;
+    const int64_t grid = (A.n + block - 1) / block;
+    grid_prepass_kernel<<<(unsigned)grid, block, 0, cfg.stream>>>(A, iota_out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Leapfrog
+// ------------------------------------------------------------------------------------------
+constexpr int LF_BLOCK = 256;
+
+struct Lane {
+    double x, y, z, vx, vy, vz;     // state at node j (v synchronised only at sync nodes)
+    double vhx, vhy, vhz;           // half-step velocity
+    double gx, gy, gz;              // gradient at node j
+    double dt;                      // leapfrog dt of the current segment (Myr)
+    double hgrid, t2, smyr;         // grid step, end time (grid unit), grid unit -> Myr
+    double tcur;                    // STORE only: grid time of node j
+    int64_t e, e1;                  // pending events
+    int64_t oid;                    // orbit id within the shard
+    int j, next, L;                 // current node, next sync node, last node
+    bool append;
+};
+
+// pull one queue position per calling lane (called from divergent code: aggregate over the
+// lanes that are here together, one atomic per group)
+__device__ __forceinline__ int64_t queue_pop(unsigned long long *queue)
+{
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(queue, (unsigned long long)g.size());
+    base = g.shfl(base, 0);
+    return (int64_t)(base + g.thread_rank());
+}
+
+template <bool STORE>
+__device__ __forceinline__ void store_sample(const IntegArgs &A, const Lane &s)
+{
+    if (STORE) {
+        const int64_t col = A.traj_off[s.oid] - A.traj_base + s.j;
+        A.traj_pos[col] = s.x;
+        A.traj_pos[A.traj_total + col] = s.y;
+        A.traj_pos[2 * A.traj_total + col] = s.z;
+        A.traj_vel[col] = s.vx;
+        A.traj_vel[A.traj_total + col] = s.vy;
+        A.traj_vel[2 * A.traj_total + col] = s.vz;
+        if (A.traj_t) A.traj_t[col] = s.tcur * s.smyr;
+    }
+}
+
+// apply every kick scheduled on node s.j (kicks.py:160-172); returns true if the segment restarts
+__device__ __forceinline__ bool apply_kicks(const IntegArgs &A, Lane &s)
+{
+    bool kicked = false;
+    while (s.e < s.e1 && A.ev_step[s.e] == s.j) {
+        s.vx += A.ev_dv[3 * s.e + 0];
+        s.vy += A.ev_dv[3 * s.e + 1];
+        s.vz += A.ev_dv[3 * s.e + 2];
+        // gala restarts with dt = t[1] - t[0] of the new segment, both converted to Myr
+        const double tk = A.ev_tk[s.e];
+        const double tn = (s.append && s.j + 1 == s.L) ? s.t2 : tk + s.hgrid;
+        s.dt = seg_dt_myr(tk, tn, s.smyr);
+        kicked = true;
+        s.e++;
+    }
+    return kicked;
+}
+
+__device__ __forceinline__ void write_final(const IntegArgs &A, const Lane &s)
+{
+    const int64_t n = A.n;
+    A.w_final[s.oid] = s.x;
+    A.w_final[n + s.oid] = s.y;
+    A.w_final[2 * n + s.oid] = s.z;
+    A.w_final[3 * n + s.oid] = s.vx;
+    A.w_final[4 * n + s.oid] = s.vy;
+    A.w_final[5 * n + s.oid] = s.vz;
+}
+
+template <int KIND, bool STORE>
+__global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constant__ PotParams P,
+                                                            const __grid_constant__ IntegArgs A)
+{
+    const unsigned FULL = 0xffffffffu;
+    Lane s;
+    s.x = 8.0; s.y = 0.0; s.z = 0.0; s.vx = s.vy = s.vz = 0.0;
+    s.vhx = s.vhy = s.vhz = 0.0; s.gx = s.gy = s.gz = 0.0;
+    s.dt = 0.0; s.hgrid = 0.0; s.t2 = 0.0; s.smyr = 1.0; s.tcur = 0.0;
+    s.e = s.e1 = 0; s.oid = -1; s.j = 0; s.next = 0; s.L = 0; s.append = false;
+    bool active = false, exhausted = false;
+    unsigned long long steps_done = 0;
+
+    for (;;) {
+        // ---- phase A: lanes standing on a sync node (kick node / last node / every node when STORE)
+        if (active && s.j == s.next) {
+            const bool kicked = apply_kicks(A, s);
+            store_sample<STORE>(A, s);
+            if (s.j == s.L) {
+                write_final(A, s);
+                active = false;
+            } else {
+                if (kicked) { // c_init_velocity of the new segment; gradient at this node is already known
+                    const double hdt = s.dt * 0.5;
+                    s.vhx = fma(-s.gx, hdt, s.vx);
+                    s.vhy = fma(-s.gy, hdt, s.vy);
+                    s.vhz = fma(-s.gz, hdt, s.vz);
+                }
+                s.next = STORE ? s.j + 1 : ((s.e < s.e1) ? A.ev_step[s.e] : s.L);
+            }
+        }
+        // ---- phase B: idle lanes pull the next orbit from the queue
+        while (!active && !exhausted) {
+            const int64_t p = queue_pop(A.queue);
+            if (p >= A.n) { exhausted = true; break; }
+            const int64_t o = A.order ? (int64_t)A.order[p] : p;
+            const int64_t n = A.n;
+            s.oid = o;
+            s.x = A.w0[o]; s.y = A.w0[n + o]; s.z = A.w0[2 * n + o];
+            s.vx = A.w0[3 * n + o]; s.vy = A.w0[4 * n + o]; s.vz = A.w0[5 * n + o];
+            s.j = 0;
+            s.L = A.n_nodes[o] - 1;
+            if (A.status[o] != CW_ORBIT_OK || s.L < 0) { // rejected by the pre-pass: hand back w0
+                write_final(A, s);
+                continue;
+            }
+            s.hgrid = A.dt[o]; s.t2 = A.t2[o]; s.smyr = A.to_myr[o];
+            s.append = (A.flags[o] & CW_GRID_APPEND_T2) != 0;
+            s.tcur = A.t1[o];
+            s.e = s.e1 = 0;
+            if (A.ev_off) { s.e = A.ev_off[o] - A.ev_base; s.e1 = A.ev_off[o + 1] - A.ev_base; }
+            {   // dt = t[1] - t[0] in Myr (leapfrog.pyx); node 1 is t2 itself when it was appended
+                const double t0 = s.tcur;
+                const double tn = (s.append && s.L == 1) ? s.t2 : t0 + s.hgrid;
+                s.dt = seg_dt_myr(t0, tn, s.smyr);
+            }
+            apply_kicks(A, s);          // events at (or before) the first node: kicks.py:155-157
+            store_sample<STORE>(A, s);
+            if (s.L == 0) { write_final(A, s); continue; }
+            gradient<KIND>(P, s.x, s.y, s.z, s.gx, s.gy, s.gz);
+            const double hdt = s.dt * 0.5;
+            s.vhx = fma(-s.gx, hdt, s.vx);
+            s.vhy = fma(-s.gy, hdt, s.vy);
+            s.vhz = fma(-s.gz, hdt, s.vz);
+            s.next = STORE ? 1 : ((s.e < s.e1) ? A.ev_step[s.e] : s.L);
+            active = true;
+        }
+        if (!__any_sync(FULL, active)) break;
+
+        // ---- phase C: a warp-uniform run of steps up to the nearest sync node of any lane
+        const int r = active ? (s.next - s.j) : INT_MAX;
+        const int m = __reduce_min_sync(FULL, r);
+        const double dt = s.dt;
+        for (int q = 1; q < m; q++) {   // c_leapfrog_step without the synchronised velocity
+            s.x = fma(s.vhx, dt, s.x);
+            s.y = fma(s.vhy, dt, s.y);
+            s.z = fma(s.vhz, dt, s.z);
+            gradient<KIND>(P, s.x, s.y, s.z, s.gx, s.gy, s.gz);
+            s.vhx = fma(-s.gx, dt, s.vhx);
+            s.vhy = fma(-s.gy, dt, s.vhy);
+            s.vhz = fma(-s.gz, dt, s.vhz);
+        }
+        {   // full c_leapfrog_step: v = vh - g dt/2 ; vh = vh - g dt
+            s.x = fma(s.vhx, dt, s.x);
+            s.y = fma(s.vhy, dt, s.y);
+            s.z = fma(s.vhz, dt, s.z);
+            gradient<KIND>(P, s.x, s.y, s.z, s.gx, s.gy, s.gz);
+            const double hdt = dt * 0.5;
+            s.vx = fma(-s.gx, hdt, s.vhx);
+            s.vy = fma(-s.gy, hdt, s.vhy);
+            s.vz = fma(-s.gz, hdt, s.vhz);
+            s.vhx = fma(-s.gx, dt, s.vhx);
+            s.vhy = fma(-s.gy, dt, s.vhy);
+            s.vhz = fma(-s.gz, dt, s.vhz);
+        }
+        if (active) {
+            s.j += m;
+            steps_done += (unsigned long long)m;
+            if (STORE) s.tcur = (s.append && s.j == s.L) ? s.t2 : s.tcur + s.hgrid;
+        }
+    }
+    if (A.stats) {
+        // orbit-steps actually integrated (the bench's unit of work), one atomic per warp
+        for (int off = 16; off > 0; off >>= 1) steps_done += __shfl_down_sync(FULL, steps_done, off);
+        if ((threadIdx.x & 31) == 0 && steps_done) atomicAdd(A.stats + 3, steps_done);
+    }
+}
+
+template <int KIND, bool STORE>
+static cudaError_t launch_lf(const PotParams &P, const IntegArgs &A, const LaunchCfg &cfg)
+{
+    int per_sm = 0;
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, leapfrog_kernel<KIND, STORE>,
+                                                                    LF_BLOCK, 0);
+    if (err != cudaSuccess) return err;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)cfg.sm_count * per_sm;
+    const int64_t need = (A.n + LF_BLOCK - 1) / LF_BLOCK;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    leapfrog_kernel<KIND, STORE><<<(unsigned)grid, LF_BLOCK, 0, cfg.stream>>>(P, A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_leapfrog(const PotParams &P, const IntegArgs &A, bool store_all, const LaunchCfg &cfg)
+{
+    if (A.n <= 0) return cudaSuccess;
+    switch (P.kind) {
+    case POT_MW_V1:
+        return store_all ? launch_lf<POT_MW_V1, true>(P, A, cfg) : launch_lf<POT_MW_V1, false>(P, A, cfg);
+    case POT_MW_V2:
+        return store_all ? launch_lf<POT_MW_V2, true>(P, A, cfg) : launch_lf<POT_MW_V2, false>(P, A, cfg);
+    default:
+        return store_all ? launch_lf<POT_GENERIC, true>(P, A, cfg) : launch_lf<POT_GENERIC, false>(P, A, cfg);
+    }
+}
+
+} // namespace cw

@@ -1,0 +1,153 @@
+"""Supernova event tables: host-side mirror of ``cogsworth.events.identify_events``
+(reference ``src/cogsworth/events.py:6-72``).
+
+The reference joins three pandas tables per call; here the join is done once on integer keys
+with numpy (``bin_num * 4 + star``) so it scales to 10^7 systems, and the result is available
+both as the reference's DataFrames (index = ``bin_num``; columns ``tphys, delta_vsys_x,
+delta_vsys_y, delta_vsys_z, inc, phase``) and as the flat :class:`~cogsworth_b200.batch.EventTable`
+the kernels consume.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .batch import EventTable
+
+__all__ = ["identify_events", "identify_event_tables", "draw_sn_angles"]
+
+_COLS = ["tphys", "delta_vsys_x", "delta_vsys_y", "delta_vsys_z", "inc", "phase"]
+
+
+def draw_sn_angles(initC, rng=None):
+    """Draw and persist per-SN phase / inclination if absent (pop.py:1229-1234, events.py:21-26).
+
+    Uses the global ``np.random`` state like the reference unless ``rng`` is given."""
+    n = len(initC)
+    for col in ("phase_sn_1", "phase_sn_2"):
+        if col not in initC:
+            initC[col] = np.random.uniform(0, 2 * np.pi, n) if rng is None else rng.uniform(0, 2 * np.pi, n)
+    for col in ("inc_sn_1", "inc_sn_2"):
+        if col not in initC:
+            u01 = np.random.rand(n) if rng is None else rng.random(n)
+            initC[col] = np.arccos(2 * u01 - 1.0)
+    return initC
+
+
+def _sn_rows(p):
+    """All supernova rows joined with their kicks and angles, in bpp order.
+
+    Returns a dict of equal-length arrays."""
+    kick = p.kick_info
+    bpp = p.bpp
+    initC = p.initC if hasattr(p, "initC") else p.initial_binaries
+    draw_sn_angles(initC)
+
+    k_star = np.asarray(kick["star"].values)
+    k_keep = k_star > 0.0
+    k_bin = np.asarray(kick["bin_num"].values)[k_keep].astype(np.int64)
+    k_key = k_bin * 4 + k_star[k_keep].astype(np.int64)
+
+    et = np.asarray(bpp["evol_type"].values)
+    b_keep = (et == 15) | (et == 16)
+    b_bin = np.asarray(bpp["bin_num"].values)[b_keep].astype(np.int64)
+    b_star = np.where(et[b_keep] == 15, 1, 2).astype(np.int64)
+    b_key = b_bin * 4 + b_star
+    b_tphys = np.asarray(bpp["tphys"].values, dtype=np.float64)[b_keep]
+
+    # inner join bpp SN rows with kick rows on (bin_num, star); keys are unique on the kick side
+    order = np.argsort(k_key, kind="stable")
+    pos = np.searchsorted(k_key[order], b_key)
+    pos_c = np.minimum(pos, max(len(order) - 1, 0))
+    hit = (len(order) > 0) & (pos < len(order))
+    if len(order):
+        hit = hit & (k_key[order][pos_c] == b_key)
+    else:
+        hit = np.zeros(len(b_key), dtype=bool)
+    krow = order[pos_c[hit]] if len(order) else np.zeros(0, dtype=np.int64)
+
+    def kcol(name):
+        return np.asarray(kick[name].values, dtype=np.float64)[k_keep][krow]
+
+    bins = b_bin[hit]
+    star = b_star[hit]
+    # angles: row of initC for each bin_num (initC is indexed by bin_num)
+    ic_bins = np.asarray(initC["bin_num"].values if "bin_num" in initC else initC.index.values).astype(np.int64)
+    ic_order = np.argsort(ic_bins, kind="stable")
+    ic_row = ic_order[np.searchsorted(ic_bins[ic_order], bins)]
+    inc1, inc2 = np.asarray(initC["inc_sn_1"].values), np.asarray(initC["inc_sn_2"].values)
+    ph1, ph2 = np.asarray(initC["phase_sn_1"].values), np.asarray(initC["phase_sn_2"].values)
+    return dict(
+        bin_num=bins, star=star, tphys=b_tphys[hit], disrupted=kcol("disrupted"),
+        dv1=np.stack([kcol("delta_vsysx_1"), kcol("delta_vsysy_1"), kcol("delta_vsysz_1")], axis=1)
+        if len(bins) else np.zeros((0, 3)),
+        dv2=np.stack([kcol("delta_vsysx_2"), kcol("delta_vsysy_2"), kcol("delta_vsysz_2")], axis=1)
+        if len(bins) else np.zeros((0, 3)),
+        inc=np.where(star == 1, inc1[ic_row], inc2[ic_row]).astype(np.float64),
+        phase=np.where(star == 1, ph1[ic_row], ph2[ic_row]).astype(np.float64))
+
+
+def _select(rows, mask, dv):
+    return dict(bin_num=rows["bin_num"][mask], tphys=rows["tphys"][mask], dv=dv[mask],
+                inc=rows["inc"][mask], phase=rows["phase"][mask])
+
+
+def _primary_secondary(p):
+    rows = _sn_rows(p)
+    # primaries: delta_vsys*_1 at every supernova                              (events.py:47-53)
+    prim = _select(rows, np.ones(len(rows["bin_num"]), dtype=bool), rows["dv1"])
+    # secondaries: *_2, except *_1 while the binary is still bound             (events.py:56-67)
+    dv_sec = np.where((rows["disrupted"] == 0)[:, None], rows["dv1"], rows["dv2"])
+    # ... and only for disrupted binaries, in bin_nums[disrupted] order         (events.py:70)
+    bin_nums = np.asarray(p.bin_nums).astype(np.int64)
+    dis_bins = bin_nums[np.asarray(p.disrupted, dtype=bool)]
+    sec_rows = []
+    if len(dis_bins) and len(rows["bin_num"]):
+        o = np.argsort(rows["bin_num"], kind="stable")
+        sb = rows["bin_num"][o]
+        lo, hi = np.searchsorted(sb, dis_bins, "left"), np.searchsorted(sb, dis_bins, "right")
+        sec_rows = [o[a:b] for a, b in zip(lo, hi)]
+    sec_idx = np.concatenate(sec_rows) if len(sec_rows) else np.zeros(0, dtype=np.int64)
+    m = np.zeros(len(rows["bin_num"]), dtype=bool)
+    sec = _select(rows, sec_idx, dv_sec) if len(sec_idx) else _select(rows, m, dv_sec)
+    return prim, sec, bin_nums
+
+
+def _frame(t):
+    import pandas as pd
+    df = pd.DataFrame({"tphys": t["tphys"], "delta_vsys_x": t["dv"][:, 0], "delta_vsys_y": t["dv"][:, 1],
+                       "delta_vsys_z": t["dv"][:, 2], "inc": t["inc"], "phase": t["phase"]}, columns=_COLS)
+    df.index = t["bin_num"]
+    return df
+
+
+def identify_events(p):
+    """Drop-in for ``cogsworth.events.identify_events(p)``: (primary_event_rows, secondary_event_rows)."""
+    prim, sec, _ = _primary_secondary(p)
+    return _frame(prim), _frame(sec)
+
+
+def _table(t, bin_nums):
+    """EventTable whose owners are positions in ``bin_nums``, grouped by owner, time order kept."""
+    order_b = np.argsort(bin_nums, kind="stable")
+    owner = order_b[np.searchsorted(bin_nums[order_b], t["bin_num"])] if len(t["bin_num"]) else \
+        np.zeros(0, dtype=np.int64)
+    o = np.argsort(owner, kind="stable")      # stable: keeps the chronological bpp order per system
+    return EventTable(owner[o].astype(np.int64), t["tphys"][o], t["dv"][o], t["phase"][o], t["inc"][o])
+
+
+def identify_event_tables(p):
+    """Same content as :func:`identify_events` as flat :class:`EventTable` s (owners = positions in
+    ``p.bin_nums``), ready for :func:`cogsworth_b200.batch.build_orbit_batch`."""
+    prim, sec, bin_nums = _primary_secondary(p)
+    return _table(prim, bin_nums), _table(sec, bin_nums)
+
+
+def event_table_from_frame(df, bin_nums):
+    """Convert a reference-style events DataFrame (index = bin_num) to an EventTable."""
+    t = dict(bin_num=np.asarray(df.index.values).astype(np.int64),
+             tphys=np.asarray(df["tphys"].values, dtype=np.float64),
+             dv=np.stack([np.asarray(df[c].values, dtype=np.float64) for c in _COLS[1:4]], axis=1)
+             if len(df) else np.zeros((0, 3)),
+             inc=np.asarray(df["inc"].values, dtype=np.float64),
+             phase=np.asarray(df["phase"].values, dtype=np.float64))
+    return _table(t, np.asarray(bin_nums).astype(np.int64))

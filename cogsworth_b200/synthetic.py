@@ -1,0 +1,172 @@
+"""Synthetic populations of the BASELINE.json configs: INPUT GENERATION ONLY.
+
+Stands in for the two host stages that sit upstream of the hot path and are outside its scope:
+the Wagg2022 star-formation-history sampler (reference ``src/cogsworth/sfh.py:1026-1165``; birth
+time, position) with the birth-velocity rule of ``Population.sample_initial_galaxy``
+(``src/cogsworth/pop.py:1001-1013``), and COSMIC's ``bpp`` / ``kick_info`` supernova rows
+(drawn from simple distributions; COSMIC is Fortran and excluded by the north star).
+Everything is seeded: ``numpy.random.default_rng(20221101 + cfg_id)``; draws happen in the order
+ICs, then events.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+from scipy.integrate import quad
+from scipy.special import lambertw
+from scipy.stats import beta as beta_dist
+
+from . import constants as K
+from .batch import EventTable, OrbitBatch, build_orbit_batch
+from .potential import CompositePotential, MilkyWayPotential
+
+SEED0 = 20221101
+
+
+def _host_circular_velocity(pot: CompositePotential, x, y, z):
+    """v_circ = sqrt(r |dPhi/dr|) in kpc/Myr, vectorised numpy -- used ONLY to draw birth velocities
+    for synthetic inputs (upstream of the hot path; the product's own version is cw_circular_velocity)."""
+    r = np.sqrt(x * x + y * y + z * z)
+    qdotg = np.zeros_like(r)
+    for t, (m, a, b) in zip(pot.types, pot.params):
+        GM = pot.G * m
+        if t == 1:
+            sz = np.sqrt(z * z + b * b)
+            zd = a + sz
+            f = GM * (x * x + y * y + zd * zd) ** -1.5
+            qdotg += f * (x * x + y * y) + f * z * z * (1.0 + a / sz)
+        elif t == 2:
+            qdotg += GM / ((r + a) ** 2 * r) * r * r
+        else:
+            u = r / a
+            qdotg += GM / a / (u ** 3) / (a * a) * (np.log(1 + u) - u / (1 + u)) * r * r
+    return np.sqrt(np.abs(qdotg))
+
+
+def wagg2022_initial_conditions(n, rng, potential=None, galaxy_age=12.0, tsfr=6.8, alpha=0.3,
+                                v_dispersion_kms=5.0):
+    """Birth (tau [Gyr], pos (3,n) [kpc], vel (3,n) [km/s]) of ``n`` systems, Wagg+2022-like."""
+    potential = MilkyWayPotential("v2") if potential is None else potential
+    comp = rng.choice(3, size=n, p=np.array([2.585, 2.585, 0.91]) / (2 * 2.585 + 0.91))
+    U = rng.random(n)
+    tau = np.empty(n)
+    # low-alpha disc: 0-8 Gyr (sfh.py:1050-1052); high-alpha: 8-12 Gyr (sfh.py:1083-1086)
+    norm_lo = 1 / quad(lambda x: np.exp(-(galaxy_age - x) / tsfr), 0, 8)[0]
+    norm_hi = 1 / quad(lambda x: np.exp(-(galaxy_age - x) / tsfr), 8, 12)[0]
+    lo, hi, bu = comp == 0, comp == 1, comp == 2
+    tau[lo] = tsfr * np.log(U[lo] * np.exp(galaxy_age / tsfr) / (norm_lo * tsfr) + 1)
+    tau[hi] = tsfr * np.log(U[hi] * np.exp(galaxy_age / tsfr) / (norm_hi * tsfr) + np.exp(8 / tsfr))
+    tau[bu] = beta_dist.rvs(a=2, b=3, loc=6, scale=6, size=int(bu.sum()), random_state=rng)  # sfh.py:1115
+    # radii: inverse CDF of an exponential disc (sfh.py:1003); scale lengths sfh.py:1055,1065,1096
+    R_d = np.where(lo, 4.0 * (1 - alpha * tau / 8.0), np.where(hi, 1 / 0.43, 1.5))
+    rho = -R_d * (lambertw((rng.random(n) - 1) / np.e, k=-1).real + 1)
+    h_z = np.where(lo, 0.3, np.where(hi, 0.95, 0.2))
+    z = h_z * np.log(1 - rng.random(n)) * rng.choice([-1.0, 1.0], size=n)
+    phi = rng.uniform(0, 2 * np.pi, n)
+    x, y = rho * np.sin(phi), rho * np.cos(phi)                  # sfh.py:425-426
+    # velocities (pop.py:1001-1013): N((0, v_circ, 0), sigma/sqrt(3)) in (v_R, v_T, v_z)
+    v_circ = _host_circular_velocity(potential, x, y, z) * K.KMS_PER_KPC_MYR
+    sig = v_dispersion_kms / np.sqrt(3)
+    v_R, v_T, v_zz = rng.normal(0, sig, n), rng.normal(v_circ, sig), rng.normal(0, sig, n)
+    ang = np.arctan2(y, x)
+    v_x = v_R * np.cos(ang) - v_T * np.sin(ang)                  # sfh.py:327-345
+    v_y = v_R * np.sin(ang) + v_T * np.cos(ang)
+    return tau, np.stack([x, y, z]), np.stack([v_x, v_y, v_zz])
+
+
+def synthetic_supernovae(n, tau_gyr, rng, f_sn=1.0, p_second=0.3, p_disrupt=0.8, sigma1=50.0, sigma2=150.0,
+                         tphys_range=(3.0, 50.0)):
+    """Stand-in for COSMIC's SN rows: returns (primary EventTable, secondary EventTable, disrupted mask)
+    built with exactly the rules of ``events.identify_events`` (events.py:47-70)."""
+    kicked = rng.random(n) < f_sn
+    t_sn1 = rng.uniform(*tphys_range, n)
+    has2 = kicked & (rng.random(n) < p_second)
+    t_sn2 = t_sn1 + rng.uniform(0.1, 20.0, n)
+    horizon = tau_gyr * 1000.0
+    ok1 = kicked & (t_sn1 < horizon)                 # events later than the evolution time are discarded
+    ok2 = has2 & ok1 & (t_sn2 < horizon)
+    n_sn = ok1.astype(int) + ok2.astype(int)
+    disrupt_draw = rng.random(n) < p_disrupt
+    disrupted = (n_sn > 0) & disrupt_draw            # disruption happens at the LAST supernova
+    dv1_a, dv1_b = rng.normal(0, sigma1, (n, 3)), rng.normal(0, sigma1, (n, 3))
+    dv2_a, dv2_b = rng.normal(0, sigma2, (n, 3)), rng.normal(0, sigma2, (n, 3))
+    phase = rng.uniform(0, 2 * np.pi, (n, 2))
+    inc = np.arccos(2 * rng.random((n, 2)) - 1.0)
+
+    i1, i2 = np.flatnonzero(ok1), np.flatnonzero(ok2)
+    owner = np.concatenate([i1, i2])
+    order = np.lexsort((np.concatenate([np.zeros(len(i1)), np.ones(len(i2))]), owner))
+    owner = owner[order]
+    which = np.concatenate([np.zeros(len(i1), dtype=int), np.ones(len(i2), dtype=int)])[order]
+    tphys = np.where(which == 0, t_sn1[owner], t_sn2[owner])
+    dv1 = np.where((which == 0)[:, None], dv1_a[owner], dv1_b[owner])
+    dv2 = np.where((which == 0)[:, None], dv2_a[owner], dv2_b[owner])
+    ph, ic = phase[owner, which], inc[owner, which]
+    is_last = which == (n_sn[owner] - 1)
+    row_disrupted = disrupted[owner] & is_last       # kick_info.disrupted of that SN row
+    prim = EventTable(owner, tphys, dv1, ph, ic)
+    keep = disrupted[owner]
+    dv_sec = np.where(row_disrupted[:, None], dv2, dv1)
+    sec = EventTable(owner[keep], tphys[keep], dv_sec[keep], ph[keep], ic[keep])
+    return prim, sec, disrupted
+
+
+@dataclass
+class SyntheticPopulation:
+    batch: OrbitBatch
+    tau_gyr: np.ndarray
+    pos_kpc: np.ndarray
+    vel_kms: np.ndarray
+    disrupted: np.ndarray
+    primary_events: EventTable
+    secondary_events: EventTable
+    potential: CompositePotential
+    max_ev_time_gyr: float
+    timestep_myr: float
+
+
+def make_population(n_binaries, cfg_id=0, potential=None, f_sn=1.0, horizon_gyr=None, max_ev_time_gyr=12.0,
+                    timestep_myr=1.0, plunging_fraction=0.0, seed=None) -> SyntheticPopulation:
+    """A seeded synthetic population + its flattened OrbitBatch.
+
+    horizon_gyr : None -> every system keeps its Wagg2022 birth time (variable step counts);
+    a number -> every orbit is integrated for exactly that long (configs 1, 3, 4, 5).
+    plunging_fraction : share of systems put on nearly radial orbits (|L_z| < 50 kpc km/s), config 5.
+    """
+    potential = MilkyWayPotential("v2") if potential is None else potential
+    rng = np.random.default_rng(SEED0 + cfg_id if seed is None else seed)
+    tau, pos, vel = wagg2022_initial_conditions(n_binaries, rng, potential, galaxy_age=max_ev_time_gyr)
+    if horizon_gyr is not None:
+        tau = np.full(n_binaries, float(horizon_gyr))
+    if plunging_fraction > 0:
+        k = rng.random(n_binaries) < plunging_fraction
+        R = np.sqrt(pos[0] ** 2 + pos[1] ** 2)
+        lz_target = rng.uniform(-50.0, 50.0, n_binaries)            # kpc km/s
+        vT = lz_target / np.maximum(R, 1e-3)
+        ang = np.arctan2(pos[1], pos[0])
+        vR = rng.normal(0, 30.0, n_binaries)
+        vel[0] = np.where(k, vR * np.cos(ang) - vT * np.sin(ang), vel[0])
+        vel[1] = np.where(k, vR * np.sin(ang) + vT * np.cos(ang), vel[1])
+    if f_sn > 0:
+        prim, sec, disrupted = synthetic_supernovae(n_binaries, tau, rng, f_sn=f_sn)
+    else:
+        prim, sec, disrupted = EventTable.empty(), EventTable.empty(), np.zeros(n_binaries, dtype=bool)
+    batch = build_orbit_batch(pos, vel, tau, max_ev_time_gyr, timestep_myr, disrupted, prim, sec)
+    return SyntheticPopulation(batch, tau, pos, vel, disrupted, prim, sec, potential, max_ev_time_gyr, timestep_myr)
+
+
+def population_with_n_orbits(n_orbits, **kw) -> SyntheticPopulation:
+    """Config 4 / 5 are specified in ORBITS (primaries + disrupted secondaries): pick the number of
+    binaries whose expected orbit count matches, then trim the disrupted tail to hit it exactly."""
+    f_sn = kw.get("f_sn", 1.0)
+    exp_per_binary = 1.0 + 0.8 * f_sn
+    nb = int(np.ceil(n_orbits / exp_per_binary * 1.002)) + 16
+    pop = make_population(nb, **kw)
+    while pop.batch.n_orbits < n_orbits:
+        nb = int(nb * 1.01) + 16
+        pop = make_population(nb, **kw)
+    if pop.batch.n_orbits > n_orbits:
+        pop.batch = pop.batch.take(np.arange(n_orbits))
+        pop.batch.n_primary = min(nb, n_orbits)
+    return pop

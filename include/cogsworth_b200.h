@@ -1,0 +1,187 @@
+/*
+ * cogsworth_b200.h -- C ABI of the B200-native galactic-orbit integrator.
+ *
+ * The reference (TomWagg/cogsworth) has no FFI seam on this path: the seam is Python,
+ *     cogsworth.kicks.integrate_orbit_with_events(w0, t1, t2, dt, potential, events, store_all,
+ *         integrator, integrator_kwargs, max_retries, timestep_multiplier)   src/cogsworth/kicks.py:52-56
+ *     cogsworth.pop.Population.perform_galactic_evolution(progress_bar)      src/cogsworth/pop.py:1195
+ *     cogsworth.pop._init_pool / _orbit_worker  (the multiprocessing boundary) src/cogsworth/pop.py:2187-2201
+ * and underneath them gala's Cython operators
+ *     leapfrog_integrate_hamiltonian(H, w0[norb,6], t[ntimes], store_all)
+ *     dop853_integrate_hamiltonian(H, w0, t, atol, rtol, nmax, ...)
+ * The entry points below are the BATCH form of that per-orbit call: one call integrates every
+ * orbit that perform_galactic_evolution would fan out over its process pool.  The ctypes
+ * binding a cogsworth maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes; no torch / CUDA types (streams travel as void*).
+ *   - all arrays are caller-owned; the library keeps no reference after a call returns.
+ *   - phase-space arrays are structure-of-arrays, component-major:  w[c*n + i],
+ *     c = 0..5 = (x, y, z [kpc], vx, vy, vz [kpc/Myr])   (gala's galactic unit system).
+ *   - every entry point returns 0 or a negative CW_E_* code; per-orbit failures are reported in
+ *     status[] with Hairer's DOP853 codes, which the Python layer maps to `None` orbits exactly
+ *     as kicks.py:105-106,193-203 does.
+ */
+#ifndef COGSWORTH_B200_H
+#define COGSWORTH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CW_ABI_VERSION 1
+#define CW_MAX_COMPONENTS 16
+
+/* potential components = gala builtin potentials reachable from MilkyWayPotential v1 / v2
+ * (gala/potential/potential/builtin/builtin_potentials.c); params are 3 doubles per component */
+enum {
+    CW_COMP_MIYAMOTO_NAGAI = 1, /* (m [Msun], a [kpc], b [kpc])  -- MN3ExponentialDisk = three of these */
+    CW_COMP_HERNQUIST = 2,      /* (m, c, unused) */
+    CW_COMP_NFW_SPHERICAL = 3   /* (m, r_s, unused) */
+};
+
+/* integrators = the two gala Integrator classes cogsworth passes (pop.py:130, kicks.py:54) */
+enum {
+    CW_LEAPFROG = 0, /* gi.LeapfrogIntegrator : fixed-step KDK, 1 gradient per grid interval */
+    CW_DOP853 = 1    /* gi.DOPRI853Integrator : Hairer dop853 restarted on every grid interval */
+};
+
+/* per-orbit grid flags */
+enum {
+    CW_GRID_APPEND_T2 = 1 /* kicks.py:121-122: append t2 as the final node (events branch) */
+};
+
+/* buffer placement */
+enum {
+    CW_MEM_HOST = 0,  /* every pointer in cw_batch / cw_result is host memory (pinned or pageable) */
+    CW_MEM_DEVICE = 1 /* every pointer is device memory on the context's FIRST device */
+};
+
+/* call-level error codes */
+enum {
+    CW_OK = 0,
+    CW_E_INVALID = -1,      /* bad argument */
+    CW_E_CUDA = -2,         /* CUDA runtime error (see cw_last_error) */
+    CW_E_NO_POTENTIAL = -3, /* cw_set_potential not called */
+    CW_E_NO_DEVICE = -4,    /* no usable sm_100 device: there is no CPU fallback */
+    CW_E_UNSUPPORTED = -5
+};
+
+/* per-orbit status (Hairer dop853 codes; -5 and -6 are ours) */
+enum {
+    CW_ORBIT_OK = 0,
+    CW_ORBIT_INCONSISTENT = -1,    /* empty grid, unsorted events, or an event after t2 (the reference
+                                      raises ValueError when stitching, kicks.py:187-189) */
+    CW_ORBIT_NMAX = -2,            /* "Larger nmax is needed" */
+    CW_ORBIT_STEP_TOO_SMALL = -3,  /* "Step size becomes too small" */
+    CW_ORBIT_STIFF = -4,           /* "The problem is probably stiff" */
+    CW_ORBIT_NONFINITE = -5,       /* error norm became NaN/inf (Hairer would spin to nmax) */
+    CW_ORBIT_CAPACITY = -6         /* trajectory slot smaller than the orbit's node count */
+};
+
+typedef struct cw_ctx cw_ctx;
+
+/* Options of one integrate call = the static arguments of pop._init_pool (pop.py:2187-2194). */
+typedef struct cw_opts {
+    int32_t integrator; /* CW_LEAPFROG | CW_DOP853 */
+    int32_t mem_space;  /* CW_MEM_HOST | CW_MEM_DEVICE */
+    double atol;        /* integrator_kwargs["atol"], gala default 1e-10 (DOP853 only) */
+    double rtol;        /* integrator_kwargs["rtol"], gala default 1e-10 */
+    int64_t nmax;       /* integrator_kwargs["nmax"], <= 0 -> 100000 */
+    void *stream;       /* CW_MEM_DEVICE only: cudaStream_t to launch on (NULL = the context's own) */
+    int32_t no_sync;    /* CW_MEM_DEVICE only: return without synchronising the stream */
+    int32_t reserved;
+} cw_opts;
+
+/*
+ * The orbits of one call = what pop._iter_orbit_args yields (pop.py:1156-1193), flattened.
+ *
+ * Time grid of orbit i (kicks.py:97,118-122 and gala.integrate.parse_time_specification):
+ *     T_0 = t1[i];  T_{j+1} = T_j + dt[i]  while T_j < t2[i]  (FP64 accumulation, <= 1e6 nodes);
+ *     if (grid_flags[i] & CW_GRID_APPEND_T2) and T_last < t2[i]:  append t2[i].
+ * t1/t2/dt/ev_time are in the orbit's own GRID UNIT and to_myr[i] converts it to Myr by
+ * multiplication (cogsworth builds the grid in seconds on the events branch -- to_myr =
+ * 1/3.15576e13 -- and gala builds it in Myr on the no-events branch -- to_myr = 1).  The caller
+ * must already have applied dt = min(dt, t2 - t1) (kicks.py:97).
+ *
+ * Events of orbit i are rows ev_off[i] .. ev_off[i+1]-1, chronological.  Event e is applied at
+ * the last node k >= cursor with T_k < ev_time[e] (kicks.py:134); the velocity change ev_dv[e]
+ * is get_kick_differential(...) (kicks.py:12-49) already rotated and converted to kpc/Myr.
+ */
+typedef struct cw_batch {
+    int64_t n_orbits;
+    const double *w0;          /* 6 x n_orbits */
+    const double *t1;          /* n_orbits */
+    const double *t2;          /* n_orbits */
+    const double *dt;          /* n_orbits */
+    const double *to_myr;      /* n_orbits */
+    const int32_t *grid_flags; /* n_orbits */
+    const int64_t *ev_off;     /* n_orbits + 1, or NULL when no orbit has events */
+    const double *ev_time;     /* K = ev_off[n_orbits] */
+    const double *ev_dv;       /* K x 3 (row-major: dvx, dvy, dvz per event) */
+} cw_batch;
+
+/* Outputs.  Any pointer except w_final and status may be NULL. */
+typedef struct cw_result {
+    double *w_final;   /* 6 x n_orbits : state at the last grid node = orbit[-1] (kicks.py:108-110,206-207) */
+    int32_t *status;   /* n_orbits     : CW_ORBIT_* */
+    int32_t *n_nodes;  /* n_orbits     : number of grid nodes = len(orbit.t) */
+    int32_t *ev_step;  /* K            : node index at which each kick was applied (bit-exact check) */
+    /* full trajectories (store_all=True), in the layout Population.save writes (pop.py:1853-1876):
+       sample j of orbit i lives at column traj_off[i] + j */
+    const int64_t *traj_off; /* n_orbits + 1, or NULL for final-state-only runs */
+    double *traj_pos;        /* 3 x traj_off[n_orbits]  kpc */
+    double *traj_vel;        /* 3 x traj_off[n_orbits]  kpc/Myr */
+    double *traj_t;          /* traj_off[n_orbits]      Myr (may be NULL) */
+    int64_t *stats;          /* 4 : DOP853 accepted steps, rejected steps, gradient evaluations, orbit-steps */
+} cw_result;
+
+/* Context: owns streams and scratch on each device.  n_devices <= 0 -> every visible device.
+ * Replaces Population._ensure_pool / _close_pool (pop.py:917-939). */
+int cw_create(cw_ctx **ctx, int n_devices, const int *device_ids);
+void cw_destroy(cw_ctx *ctx);
+int cw_device_count(const cw_ctx *ctx);
+
+/* Replaces the `potential` static argument of _init_pool (pop.py:2188): an ordered list of
+ * analytic components in galactic units; G in kpc^3 / Msun / Myr^2. */
+int cw_set_potential(cw_ctx *ctx, double G, int n_components, const int32_t *types, const double *params);
+
+/* The grid pre-pass alone: node count per orbit and the node index of every event.  Lets the
+ * host size trajectory buffers (traj_off) before cw_integrate, and is the bit-exact
+ * kick-timing check on its own. */
+int cw_count_nodes(cw_ctx *ctx, const cw_opts *opts, const cw_batch *batch, int32_t *n_nodes, int32_t *ev_step);
+
+/* The hot path: replaces pool.starmap(_orbit_worker, ...) (pop.py:1245-1266).  Orbits are sharded
+ * by index over the context's devices; there is no collective. */
+int cw_integrate(cw_ctx *ctx, const cw_opts *opts, const cw_batch *batch, const cw_result *result);
+
+/* "Next" rows either side of the path: potential gradient / value / circular
+ * velocity for n points, q is 3 x n SoA.  Replaces potential.gradient / .energy /
+ * .circular_velocity as used at pop.py:886-895,1001-1013. */
+int cw_gradient(cw_ctx *ctx, int mem_space, int64_t n, const double *q, double *grad /* 3 x n */);
+int cw_potential_value(cw_ctx *ctx, int mem_space, int64_t n, const double *q, double *phi /* n */);
+int cw_circular_velocity(cw_ctx *ctx, int mem_space, int64_t n, const double *q, double *vcirc /* n, kpc/Myr */);
+
+/* Diagnostics */
+const char *cw_strerror(int code);
+const char *cw_last_error(const cw_ctx *ctx);
+int cw_abi_version(void);
+/* kernels launched by the last cw_integrate / cw_count_nodes call, over all devices */
+int64_t cw_last_launch_count(const cw_ctx *ctx);
+/* device time (ms, CUDA events on the launching stream) of the integrator kernel / of all kernels
+ * of the last call on device slot `dev` */
+double cw_last_kernel_ms(const cw_ctx *ctx, int dev);
+double cw_last_total_kernel_ms(const cw_ctx *ctx, int dev);
+/* DFMA micro-benchmark on device slot `dev`: returns sustained FP64 TFLOP/s (2 flop per FMA) over
+ * about `ms_target` milliseconds -- the roofline denominator for this path. */
+double cw_measure_fp64_peak(cw_ctx *ctx, int dev, double ms_target);
+/* max relative error of the kernels' own rsqrt / reciprocal / log against the CUDA math library
+ * over n samples; out[3] */
+int cw_selftest_math(cw_ctx *ctx, int64_t n, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COGSWORTH_B200_H */
