@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- FP64 orbit-steps/s of the galactic-orbit hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...     (one rank per GPU)
+
+A "step" is one pass of the hot path over the whole batch of synthetic orbits.
+
+Workloads (synthetic inputs seeded with numpy default_rng(20221101 + cfg_id)):
+  config4 (default)  10^7 orbits (primaries + disrupted secondaries), MilkyWayPotential2022, leapfrog,
+                     1 Gyr at dt = 1 Myr (1000 steps each), supernova kicks on, final state only.
+                     N GPUs: the 10^7 orbits are sharded by index over the ranks (strong scaling; no
+                     collective on the data path); --scaling weak gives every rank its own 10^7.
+  config2            10^5 binaries with Wagg2022 horizons (<= 12000 steps), final state, kicks
+  config3            10^6 orbits x 1000 stored steps (store_all, HBM-write bound), no kicks
+  config5            10^6 orbits DOPRI853 rtol = atol = 1e-8, kicks, 1 % plunging orbits
+
+Output: ONE JSON line on rank 0 (see README / task contract): value = device-resident throughput,
+e2e = through the C-ABI with pinned HOST buffers (H2D + D2H inside the timed region), roofline
+(FP64 pipe, measured DFMA peak), cpu_baseline (the C oracle on the host cores, bounded sample).
+--impl reference times the CPU implementation only (the gala-equivalent C oracle: gala itself is not
+installable in this image) with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_STEP = {"leapfrog_v2": 114.0, "leapfrog_v1": 78.0, "dop853_v2": 2152.0}
+BYTES_PER_STORED_STEP = 48.0
+
+WORKLOADS = {
+    "config4": dict(cfg_id=4, n_orbits=10_000_000, horizon_gyr=1.0, integrator="leapfrog", store_all=False,
+                    f_sn=1.0, desc="1e7 orbits, MilkyWayPotential2022, leapfrog 1 Gyr dt=1 Myr, kicks, final state"),
+    "config2": dict(cfg_id=2, n_binaries=100_000, horizon_gyr=None, integrator="leapfrog", store_all=False,
+                    f_sn=1.0, desc="1e5 binaries, Wagg2022 horizons, MilkyWayPotential2022, leapfrog, kicks, final state"),
+    "config2_dop853": dict(cfg_id=2, n_binaries=100_000, horizon_gyr=None, integrator="dop853", store_all=False,
+                           f_sn=1.0, desc="1e5 binaries, Wagg2022 horizons, MilkyWayPotential2022, DOPRI853 1e-10, kicks"),
+    "config3": dict(cfg_id=3, n_orbits=1_000_000, horizon_gyr=1.0, integrator="leapfrog", store_all=True,
+                    f_sn=0.0, desc="1e6 orbits x 1000 stored steps (48 GB), MilkyWayPotential2022, leapfrog, no kicks"),
+    "config5": dict(cfg_id=5, n_orbits=1_000_000, horizon_gyr=1.0, integrator="dop853", store_all=False,
+                    f_sn=1.0, plunging_fraction=0.01, rtol=1e-8, atol=1e-8,
+                    desc="1e6 orbits DOPRI853 rtol=atol=1e-8, 1 Gyr, kicks, 1% plunging"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config4", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; marks the line)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-orbits", type=int, default=100_000)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def build_shard(wl, rank, world, scaling, scale):
+    """This rank's orbits.  Strong scaling: rank r generates 1/world of the population with its own
+    seed (the union over ranks is the workload); weak: every rank generates the full size."""
+    from cogsworth_b200.synthetic import make_population, population_with_n_orbits
+    share = 1.0 if scaling == "weak" else 1.0 / world
+    seed = 20221101 + wl["cfg_id"] + 1000 * world + rank if world > 1 else None
+    kw = dict(cfg_id=wl["cfg_id"], horizon_gyr=wl["horizon_gyr"], f_sn=wl["f_sn"],
+              plunging_fraction=wl.get("plunging_fraction", 0.0), seed=seed)
+    if "n_orbits" in wl:
+        n = max(int(round(wl["n_orbits"] * share * scale)), 64)
+        return population_with_n_orbits(n, **kw)
+    n = max(int(round(wl["n_binaries"] * share * scale)), 64)
+    return make_population(n, **kw)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] if pw else sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(pop, wl, n_sample, threads=0, repeats=1):
+    """The gala-equivalent C oracle on the host cores over a bounded sample of the same workload."""
+    import oracle as O
+    b = pop.batch.take(np.arange(min(n_sample, pop.batch.n_orbits)))
+    integ = O.LEAPFROG if wl["integrator"] == "leapfrog" else O.DOP853
+    threads = threads or O.max_threads()
+    best, steps = None, 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        r = O.integrate_batch(pop.potential, b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv,
+                              integrator=integ, rtol=wl.get("rtol", 1e-10), atol=wl.get("atol", 1e-10), n_threads=threads)
+        dt = time.perf_counter() - t0
+        steps = int((r["n_nodes"].astype(np.int64) - 1).clip(min=0).sum())
+        best = dt if best is None else min(best, dt)
+    return {"value": steps / best, "unit": "orbit-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{b.n_orbits} orbits of the workload ({steps} orbit-steps, {best:.2f} s wall, "
+                      "gala-equivalent C oracle -- not gala)"}, steps, best
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, wl, rank, world):
+    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    size = wl.get("n_orbits", int(1.8 * wl.get("n_binaries", 0)))
+    pop = build_shard(wl, 0, 1, "strong", min(args.scale, 1.0, 2.0 * args.cpu_sample_orbits / size))
+    import oracle as O
+    threads = O.max_threads()
+    n_sample = min(args.cpu_sample_orbits, pop.batch.n_orbits)
+    for _ in range(args.warmup):
+        cpu_baseline(pop, wl, max(n_sample // 8, 64), threads)
+    tot_steps, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        cb, steps, dt = cpu_baseline(pop, wl, n_sample, threads)
+        tot_steps += steps
+        tot_t += dt
+    value = tot_steps / tot_t
+    cb["value"] = value
+    line = {"impl": "reference", "metric": "FP64 orbit-steps/sec", "value": value, "unit": "orbit-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}",
+                       "reference_arm": "CPU oracle port of gala leapfrog/DOP853 + cogsworth kicks driver "
+                                        "(gala/astropy/COSMIC are not installable offline), all host threads, "
+                                        f"each step = {n_sample} orbits of the workload"},
+            "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": "orbit-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import cogsworth_b200 as cb
+    from cogsworth_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    pop = build_shard(wl, rank, world, args.scaling, args.scale)
+    b = pop.batch
+    n, K = b.n_orbits, b.n_events
+    integ = _lib.LEAPFROG if wl["integrator"] == "leapfrog" else _lib.DOP853
+    tol = dict(atol=wl.get("atol", 1e-10), rtol=wl.get("rtol", 1e-10))
+    ctx = cb.Context(devices=[local_rank])
+    ctx.set_potential(pop.potential)
+
+    # ---- host (pinned) and device copies of the inputs -------------------------------------------
+    def pinned(a, dtype):
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+        return t.pin_memory()
+
+    f64, i32, i64 = torch.float64, torch.int32, torch.int64
+    H = dict(w0=pinned(b.w0, f64), t1=pinned(b.t1, f64), t2=pinned(b.t2, f64), dt=pinned(b.dt, f64),
+             to_myr=pinned(b.to_myr, f64), flags=pinned(b.flags, i32))
+    if K:
+        H.update(ev_off=pinned(b.ev_off, i64), ev_time=pinned(b.ev_time, f64), ev_dv=pinned(b.ev_dv, f64))
+    else:
+        H.update(ev_off=None, ev_time=None, ev_dv=None)
+    D = {k: (v.to(dev) if v is not None else None) for k, v in H.items()}
+    traj_off_h = traj_off_d = traj_pos_d = traj_vel_d = None
+    total_cols = 0
+    if wl["store_all"]:
+        nn, _ = ctx.count_nodes(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv)
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(nn, out=off[1:])
+        total_cols = int(off[-1])
+        traj_off_h = pinned(off, i64)
+        traj_off_d = traj_off_h.to(dev)
+        traj_pos_d = torch.empty((3, total_cols), dtype=f64, device=dev)
+        traj_vel_d = torch.empty((3, total_cols), dtype=f64, device=dev)
+    wf_d = torch.empty((6, n), dtype=f64, device=dev)
+    st_d = torch.empty(n, dtype=i32, device=dev)
+    stats_d = torch.zeros(4, dtype=i64, device=dev)
+    wf_h = torch.empty((6, n), dtype=f64).pin_memory()
+    st_h = torch.empty(n, dtype=i32).pin_memory()
+    stats_h = np.zeros(4, dtype=np.int64)
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        ctx.integrate_raw(n, D["w0"], D["t1"], D["t2"], D["dt"], D["to_myr"], D["flags"], D["ev_off"], D["ev_time"],
+                          D["ev_dv"], wf_d, st_d, None, None, traj_off_d, traj_pos_d, traj_vel_d, None, stats_d,
+                          integrator=integ, mem_space=_lib.MEM_DEVICE, stream=stream.cuda_stream, **tol)
+
+    def step_host():
+        ctx.integrate_raw(n, H["w0"], H["t1"], H["t2"], H["dt"], H["to_myr"], H["flags"], H["ev_off"], H["ev_time"],
+                          H["ev_dv"], wf_h, st_h, None, None, None, None, None, None, stats_h,
+                          integrator=integ, mem_space=_lib.MEM_HOST, **tol)
+
+    # ---- device-resident throughput ("value") ------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    steps_per_pass = int(stats_d.cpu()[3])
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, total_kernel_ms, launches = [], [], 0
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+        kernel_ms.append(ctx.last_kernel_ms(0))
+        total_kernel_ms.append(ctx.last_total_kernel_ms(0))
+        launches += ctx.last_launch_count
+    e1.record(stream)
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    stats_run = stats_d.cpu().numpy().copy()
+    total_steps = sum_over_ranks(float(steps_per_pass))
+    value = total_steps * args.steps / (dev_ms * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers -------------------------------------
+    e2e = None
+    if not wl["store_all"]:
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        assert np.array_equal(wf_h.numpy(), wf_d.cpu().numpy()), "host-buffer path and device path disagree"
+        h2d = sum(v.numel() * v.element_size() for v in H.values() if v is not None)
+        d2h = wf_h.numel() * 8 + st_h.numel() * 4 + 32
+        e2e = {"value": total_steps * args.steps / e2e_s, "unit": "orbit-steps/s",
+               "h2d_bytes_per_step": int(sum_over_ranks(float(h2d))), "d2h_bytes_per_step": int(sum_over_ranks(float(d2h))),
+               "ms_per_step": 1e3 * e2e_s / args.steps,
+               "how": "cw_integrate(CW_MEM_HOST) on pinned host arrays: H2D of w0/t1/t2/dt/to_myr/flags/events, grid "
+                      "pre-pass + integrator kernels, D2H of w_final/status, host wall clock, max over ranks"}
+    n_failed = int((st_d != 0).sum().item())
+    n_total = int(sum_over_ranks(float(n)))
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------------
+    k_ms = float(np.mean(kernel_ms))
+    hbm_peak, hbm_src = measured_peaks()
+    if wl["store_all"]:
+        ach = BYTES_PER_STORED_STEP * steps_per_pass / (k_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": None, "peak_source": hbm_src, "kernel": "leapfrog_kernel<MW_V2,STORE>",
+                "kernel_ms": k_ms, "algorithmic_bytes_per_orbit_step": BYTES_PER_STORED_STEP}
+    else:
+        peak = ctx.measure_fp64_peak(0, 200.0)
+        if integ == _lib.LEAPFROG:
+            flops = FLOP_PER_STEP["leapfrog_v2"] * steps_per_pass
+            kname, per = "leapfrog_kernel<MW_V2>", FLOP_PER_STEP["leapfrog_v2"]
+        else:
+            # 12 gradients + 1000 flop of stage algebra per accepted step, per launch
+            flops = FLOP_PER_STEP["dop853_v2"] * float(stats_run[0])
+            kname, per = "dop853_kernel<MW_V2>", FLOP_PER_STEP["dop853_v2"]
+        ach = flops / (k_ms * 1e-3) / 1e12
+        roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": "measured live: DFMA micro-benchmark cw_measure_fp64_peak (MEASURED_PEAKS.json has no "
+                               "FP64 entry; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
+                "kernel": kname, "kernel_ms": k_ms, "algorithmic_flop_per_unit": per,
+                "kernel_share_of_step": k_ms / (dev_ms / args.steps)}
+
+    cbase = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cbase, _, _ = cpu_baseline(pop, wl, args.cpu_sample_orbits)
+
+    if rank == 0:
+        line = {"metric": "FP64 orbit-steps/sec", "value": value, "unit": "orbit-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {wl['desc']}" + ("" if args.scale == 1.0 else f" [SCALED x{args.scale}: not a valid bench line]"),
+                           "n_orbits_total": n_total,
+                           "n_kick_events_rank0": K, "orbit_steps_per_step": int(total_steps),
+                           "integrator": wl["integrator"], "potential": "MilkyWayPotential2022 (MN3 disk + 2 Hernquist + NFW)",
+                           "parallelism": f"orbits sharded by index over {world} GPU(s), no collective",
+                           "cache": "inputs + outputs (>= 1 GB per pass) exceed the 126 MB L2; nothing is reused between steps",
+                           "failed_orbits_rank0": n_failed},
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cbase}
+        if integ == _lib.DOP853:
+            line["config"]["dop853"] = {"accepted_steps": int(stats_run[0]), "rejected_steps": int(stats_run[1]),
+                                        "gradient_evals": int(stats_run[2]), "intervals": int(stats_run[3]),
+                                        "gradient_evals_per_s": float(stats_run[2]) / (k_ms * 1e-3)}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

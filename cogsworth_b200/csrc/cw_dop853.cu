@@ -1,6 +1,6 @@
 // cw_dop853.cu -- adaptive Dormand-Prince 8(5,3) kernel (sm_100a).
 //
-// Reference semantics (restated in oracle/cw_oracle.c: cwo_dop853 / cwo_dop853_segment):
+// Reference semantics (the test oracle restates the same algorithm on the CPU):
 //   gala dop853.pyx dop853_integrate_hamiltonian: for every grid interval [t[j-1], t[j]] a fresh
 //   Hairer dop853() with h = dt0 = t[1]-t[0] of the segment, itoler = 0, atol = rtol = 1e-10 by
 //   default, safe = 0.9, fac1 = 0.333, fac2 = 6, beta = 0, hmax = xend - x, nmax = 100000,

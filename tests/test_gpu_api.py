@@ -1,0 +1,147 @@
+"""GPU tests of the reference-facing API (per-orbit call, Population stage, retry logic, device
+pointers) and size-independent properties at BASELINE sizes."""
+import numpy as np
+import pytest
+
+import cogsworth_b200 as cb
+from cogsworth_b200 import _lib
+from cogsworth_b200 import constants as K
+from cogsworth_b200.potential import MilkyWayPotential
+from cogsworth_b200.synthetic import make_population, population_with_n_orbits
+
+pytestmark = pytest.mark.gpu
+
+
+def test_per_orbit_api_matches_batch_and_oracle(ctx, oracle):
+    """integrate_orbit_with_events(w0, t1, t2, dt, potential, events, ...) -- reference signature."""
+    import pandas as pd
+    pot = MilkyWayPotential("v2")
+    w0 = [8.0, 0.3, 0.05, 5.0, 215.0, 3.0]                       # kpc, km/s
+    events = pd.DataFrame({"tphys": [12.3, 40.1], "delta_vsys_x": [30., -80.], "delta_vsys_y": [10., 50.],
+                           "delta_vsys_z": [-5., 120.], "phase": [0.3, 2.0], "inc": [1.1, 0.4]})
+    for integ, O_int in (("leapfrog", oracle.LEAPFROG), (None, oracle.DOP853)):
+        orb = cb.integrate_orbit_with_events(w0, 11.8, 12.0, 1.0, potential=pot, events=events, store_all=True,
+                                             integrator=integ, context=ctx)
+        assert orb.shape[0] in (201, 202) and orb.t[-1] == 12000.0
+        dv = cb.batch.rotate_kicks(events[["delta_vsys_x", "delta_vsys_y", "delta_vsys_z"]].values,
+                                   events["phase"].values, events["inc"].values) * K.KPC_MYR_PER_KMS
+        w_gal = np.array(w0[:3] + [v * K.KPC_MYR_PER_KMS for v in w0[3:]])
+        te = (11.8 + events["tphys"].values * K.GYR_PER_MYR) * K.SEC_PER_GYR
+        ref = oracle.integrate_orbit(pot, w_gal, 11.8 * K.SEC_PER_GYR, 12.0 * K.SEC_PER_GYR, K.SEC_PER_MYR,
+                                     K.MYR_PER_SEC, 1, te, dv, integrator=O_int, store_all=True)
+        assert orb.shape[0] == ref["n_nodes"] and np.array_equal(orb.t, ref["t"])
+        assert np.abs(orb.pos.xyz - ref["traj"][:3]).max() < 1e-9
+        last = cb.integrate_orbit_with_events(w0, 11.8, 12.0, 1.0, potential=pot, events=events, store_all=False,
+                                              integrator=integ, context=ctx)
+        assert last.shape == (1,) and np.array_equal(last.pos.xyz[:, 0], orb.pos.xyz[:, -1])
+    # no events: gala's own grid, which stops at the last node < t2 (quirk Q1)
+    orb = cb.integrate_orbit_with_events(w0, 11.8, 12.0, 1.0, potential=pot, events=None, integrator="leapfrog",
+                                         context=ctx)
+    assert orb.shape == (200,) and abs(orb.t[-1] - 11999.0) < 1e-9
+    # dt larger than the span is clipped: dt = min(dt, t2 - t1)  (kicks.py:97)
+    orb = cb.integrate_orbit_with_events(w0, 11.9995, 12.0, 1.0, potential=pot, events=events.iloc[:0],
+                                         integrator="leapfrog", context=ctx)
+    assert orb.shape[0] in (2, 3) and orb.t[-1] == 12000.0
+
+
+def test_population_stage_end_to_end(ctx):
+    """B200Population.perform_galactic_evolution with COSMIC-style tables (reference tests/test_pop.py
+    :232-247 store_entire_orbits, :841-864 primary/secondary views, tests/test_kicks.py:40-52 rerun)."""
+    from test_host import fake_population
+    p = fake_population()
+    p._cw_context = ctx
+    np.random.seed(11)
+    p.perform_galactic_evolution(progress_bar=False)
+    n, nd = len(p), int(p.disrupted.sum())
+    assert len(p.orbits) == n + nd == 6
+    assert all(o.shape[0] == 1 for o in p.orbits)               # store_entire_orbits=False
+    assert p.final_pos.shape == (6, 3) and p.final_vel.shape == (6, 3)
+    assert p.final_primary_pos.shape == (4, 3) and p.final_secondary_pos.shape == (4, 3)
+    # bound systems: secondary == primary; disrupted: the extra orbits
+    assert np.array_equal(p.final_secondary_pos[:2], p.final_primary_pos[:2])
+    assert np.array_equal(p.final_secondary_pos[2:], p.final_pos[4:])
+    first = np.array(p.final_pos).copy()
+    p.perform_galactic_evolution(progress_bar=False)            # angles persisted -> reproducible
+    assert np.array_equal(np.array(p.final_pos), first)
+    # full orbits + DOPRI853 default
+    p.store_entire_orbits, p.integrator = True, None
+    p.perform_galactic_evolution()
+    lens = [o.shape[0] for o in p.orbits]
+    assert lens[0] == 1000 and lens[1] == 2001 and lens[3] == 4001 and lens[5] == 4001
+    assert np.array_equal(np.array(p.primary_orbits[1].pos.xyz)[:, -1], np.array(p.final_pos)[1])
+
+
+def test_retry_with_smaller_timestep(ctx, oracle):
+    """kicks.py:113,193-203: failed kicked orbits are retried with dt * timestep_multiplier,
+    max_retries attempts in total; un-kicked ones are not retried; exhausted -> None."""
+    pop = make_population(200, cfg_id=21, horizon_gyr=0.1, plunging_fraction=0.5)
+    b = pop.batch
+    kw = dict(potential=pop.potential, store_all=False, integrator="dopri853", context=ctx)
+    orbits0, info0 = cb.integrate_orbits(b, integrator_kwargs={"nmax": 1}, max_retries=1, **kw)
+    failed0 = np.flatnonzero(info0["status"] != 0)
+    assert len(failed0) > 0 and (info0["status"][failed0] == -2).all()      # "Larger nmax is needed"
+    assert all(orbits0[int(i)] is None for i in failed0[:5])
+    orbits1, info1 = cb.integrate_orbits(b, integrator_kwargs={"nmax": 1}, max_retries=2, timestep_multiplier=0.1, **kw)
+    recovered = failed0[info1["status"][failed0] == 0]
+    assert len(recovered) > 0
+    i = int(recovered[0])
+    e0, e1 = b.ev_off[i], b.ev_off[i + 1]
+    ref = oracle.integrate_orbit(pop.potential, b.w0[:, i], b.t1[i], b.t2[i], b.dt[i] * 0.1, b.to_myr[i],
+                                 int(b.flags[i]), b.ev_time[e0:e1], b.ev_dv[e0:e1], integrator=oracle.DOP853, nmax=1)
+    assert ref["status"] == 0 and info1["n_nodes"][i] == ref["n_nodes"]
+    assert np.abs(info1["w_final"][:, i] - ref["w_final"]).max() < 1e-7
+    fp, fv = orbits1.final_coords()
+    still = np.flatnonzero(info1["status"] != 0)
+    assert np.isinf(fp[still]).all() and np.isfinite(fp[info1["status"] == 0]).all()
+
+
+def test_device_pointer_mode_matches_host_mode(ctx):
+    import torch
+    pop = make_population(3000, cfg_id=31, horizon_gyr=0.15)
+    b = pop.batch
+    ctx.set_potential(pop.potential)
+    host = ctx.integrate(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv, integrator=_lib.LEAPFROG)
+    dev = torch.device("cuda:0")
+    tt = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dtype=dt)
+    d = dict(w0=tt(b.w0), t1=tt(b.t1), t2=tt(b.t2), dt=tt(b.dt), to_myr=tt(b.to_myr), flags=tt(b.flags, torch.int32),
+             ev_off=tt(b.ev_off, torch.int64), ev_time=tt(b.ev_time), ev_dv=tt(b.ev_dv))
+    n = b.n_orbits
+    wf = torch.empty((6, n), dtype=torch.float64, device=dev)
+    st = torch.empty(n, dtype=torch.int32, device=dev)
+    es = torch.empty(b.n_events, dtype=torch.int32, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    ctx.integrate_raw(n, d["w0"], d["t1"], d["t2"], d["dt"], d["to_myr"], d["flags"], d["ev_off"], d["ev_time"],
+                      d["ev_dv"], wf, st, None, es, stats=stats, integrator=_lib.LEAPFROG, mem_space=_lib.MEM_DEVICE)
+    assert np.array_equal(wf.cpu().numpy(), host["w_final"])
+    assert np.array_equal(es.cpu().numpy(), host["ev_step"]) and int(stats[3]) == int(host["stats"][3])
+    assert ctx.last_kernel_ms(0) > 0
+
+
+def test_properties_at_full_size(ctx):
+    """10^6 orbits x 1000 steps (a tenth of configs[3]): determinism, exact step accounting, time
+    reversibility of the leapfrog map, bounded energy error -- no oracle needed."""
+    pop = population_with_n_orbits(1_000_000, cfg_id=4, horizon_gyr=1.0)
+    b = pop.batch
+    ctx.set_potential(pop.potential)
+    run = lambda w0, ev=True: ctx.integrate(w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off if ev else None,
+                                            b.ev_time if ev else None, b.ev_dv if ev else None, integrator=_lib.LEAPFROG)
+    r1, r2 = run(b.w0), run(b.w0)
+    assert np.array_equal(r1["w_final"], r2["w_final"])                      # deterministic
+    assert (r1["status"] == 0).all() and (r1["n_nodes"] == 1001).all()
+    assert int(r1["stats"][3]) == 1000 * b.n_orbits                          # every orbit-step accounted for
+    nn, es = ctx.count_nodes(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv)
+    assert np.array_equal(nn, r1["n_nodes"]) and np.array_equal(es, r1["ev_step"])
+    assert es.min() >= 3 and es.max() <= 70                                   # SN at 3..70 Myr after birth
+    assert np.isfinite(r1["w_final"]).all()
+    # reversibility (no kicks): forward, flip v, forward again, flip -> back at the start
+    fwd = run(b.w0, ev=False)["w_final"]
+    fwd[3:] *= -1
+    back = run(fwd, ev=False)["w_final"]
+    back[3:] *= -1
+    err = np.abs(back - b.w0).max(axis=0) / np.maximum(np.linalg.norm(b.w0[:3], axis=0), 1e-2)
+    assert np.median(err) < 1e-12 and np.quantile(err, 0.9) < 1e-9, np.quantile(err, [0.5, 0.9, 0.99])
+    # energy: symplectic, so bounded for resolved orbits
+    E0 = 0.5 * (b.w0[3:] ** 2).sum(axis=0) + ctx.potential_value(np.ascontiguousarray(b.w0[:3]))
+    E1 = 0.5 * (fwd[3:] ** 2).sum(axis=0) + ctx.potential_value(np.ascontiguousarray(fwd[:3]))
+    assert np.median(np.abs(E1 / E0 - 1)) < 1e-5

@@ -1,0 +1,149 @@
+"""CPU tests of the oracle (oracle/cw_oracle.c) against every known answer the reference holds for
+this path: the executed-notebook values in tests/golden/gala_notebook_kats.json
+(extracted by tools/extract_notebook_kats.py) and scipy's compiled Hairer DOP853."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cogsworth_b200 import constants as K
+from cogsworth_b200.potential import MilkyWayPotential, mn3_exponential_disk
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KATS = json.load(open(os.path.join(HERE, "golden", "gala_notebook_kats.json")))
+
+
+def test_kat1_circular_velocity(oracle):
+    v2 = MilkyWayPotential("v2")
+    vc = oracle.circular_velocity(v2, [8.5, 0.0, 0.0]) * K.KMS_PER_KPC_MYR
+    # all 11 printed digits of the notebook value
+    assert abs(vc - KATS["KAT1_vcirc_kms_at_8p5kpc_v2"]) < 5e-9
+    # the KAT discriminates the parameter set: v1 is 230.75 km/s
+    v1 = oracle.circular_velocity(MilkyWayPotential("v1"), [8.5, 0.0, 0.0]) * K.KMS_PER_KPC_MYR
+    assert abs(v1 - 230.748) < 1e-2 and abs(v1 - vc) > 1.0
+
+
+def test_kat2_structure():
+    v2 = MilkyWayPotential("v2")
+    assert KATS["KAT2_component_order"] == ["disk", "bulge", "nucleus", "halo"]
+    assert [n.split(".")[0] for n in v2.names] == ["disk"] * 3 + ["bulge", "nucleus", "halo"]
+    assert "m=4.77e+10" in KATS["KAT2_disk_repr"] and "h_R=2.60" in KATS["KAT2_disk_repr"]
+    terms = mn3_exponential_disk(4.7717e10, 2.6, 0.3)
+    assert np.allclose([t[0] for t in terms], [7.8723070e9, -2.7562522e11, 3.2061842e11], rtol=1e-7)
+    assert np.allclose([t[1] for t in terms], [1.5259432, 6.7827644, 5.8947996], rtol=1e-7)
+    assert all(abs(t[2] - 0.2066374) < 1e-7 for t in terms)
+    # nominal component masses sum to the 6.09e11 printed at docs/tutorials/pop_settings/potentials.ipynb:132
+    assert abs((4.7717e10 + sum(p[0] for p in v2.params[3:])) / 6.09e11 - 1) < 1e-3
+
+
+def test_kat4_time_grid(oracle):
+    """Kicked-orbit grid: accumulate dt in seconds, append t2 (kicks.py:118-122)."""
+    t_first, t_last = KATS["KAT4_t_first3_myr"], KATS["KAT4_t_last3_myr"]
+    T = oracle.time_grid(t_first[0] * 1e-3 * K.SEC_PER_GYR, 12.0 * K.SEC_PER_GYR,
+                         KATS["KAT4_timestep_myr"] * K.SEC_PER_MYR, append_t2=True)
+    assert len(T) == KATS["KAT4_n_samples"] == 77554
+    tm = T * K.MYR_PER_SEC
+    assert np.allclose(tm[:3], t_first, atol=1e-8, rtol=0)
+    assert np.allclose(tm[-3:], t_last, atol=2e-8, rtol=0)
+    assert tm[-1] == 12000.0
+    # without the append the grid stops at the last node < t2 (gala's own rule, reference quirk Q1)
+    T2 = oracle.time_grid(t_first[0], 12000.0, 0.1, append_t2=False)
+    assert len(T2) == 77553 and T2[-1] < 12000.0
+
+
+def test_kat5_dop853_samples(oracle):
+    """Six printed phase-space samples of a real gala DOPRI853 orbit in MilkyWayPotential2022."""
+    v2 = MilkyWayPotential("v2")
+    for pos, vel, t in ((KATS["KAT5_pos_first3_kpc"], KATS["KAT5_vel_first3_kpc_per_myr"], KATS["KAT4_t_first3_myr"]),
+                        (KATS["KAT5_pos_last3_kpc"], KATS["KAT5_vel_last3_kpc_per_myr"], KATS["KAT4_t_last3_myr"])):
+        w = np.array(pos[0] + vel[0])
+        import ctypes as C
+        P = oracle.make_potential(v2)
+        tt = np.array(t)
+        out = np.empty((6, 3))
+        dp = C.POINTER(C.c_double)
+        rc = oracle.lib().cwo_dop853_segment(C.byref(P), w.ctypes.data_as(dp), tt.ctypes.data_as(dp), 3, 1e-10,
+                                             1e-10, 0, out.ctypes.data_as(dp), 3, None)
+        assert rc == 0
+        got = out.T[1:]
+        exp = np.array([pos[1] + vel[1], pos[2] + vel[2]])
+        # the start sample is itself rounded to 8 decimals; positions move by v*dt with dt <= 0.2 Myr
+        assert np.abs(got - exp).max() < 2.5e-8, np.abs(got - exp).max()
+    # the last interval is the short appended one (0.0588 Myr): the position increment shrinks with it
+    d1 = np.array(KATS["KAT5_pos_last3_kpc"][1]) - np.array(KATS["KAT5_pos_last3_kpc"][0])
+    d2 = np.array(KATS["KAT5_pos_last3_kpc"][2]) - np.array(KATS["KAT5_pos_last3_kpc"][1])
+    frac = (KATS["KAT4_t_last3_myr"][2] - KATS["KAT4_t_last3_myr"][1]) / 0.1
+    assert abs(d2[0] / d1[0] - frac) < 1e-3
+
+
+def test_dop853_matches_scipy_hairer(oracle):
+    """scipy.integrate.ode('dop853') is the compiled Hairer code with the same controller: identical
+    step sequences, results equal to rounding."""
+    from scipy.integrate import ode
+    v2 = MilkyWayPotential("v2")
+
+    def f(t, y):
+        g = oracle.gradient(v2, y[:3])
+        return np.concatenate([y[3:], -g])
+
+    rng = np.random.default_rng(5)
+    for trial in range(6):
+        y0 = np.array([rng.uniform(0.3, 12), rng.uniform(-3, 3), rng.uniform(-1, 1),
+                       rng.uniform(-0.1, 0.1), rng.uniform(0.05, 0.25), rng.uniform(-0.05, 0.05)])
+        y_or = y0.copy()
+        y_sp = y0.copy()
+        n_steps_total = 0
+        for j in range(40):
+            t0, t1 = 100.0 + j * 1.0, 101.0 + j * 1.0
+            res, y_or, st = oracle.dop853(v2, t0, y_or, t1, rtol=1e-10, atol=1e-10, h=1.0)
+            assert res == 1
+            n_steps_total += st[0]
+            r = ode(f).set_integrator("dop853", rtol=1e-10, atol=1e-10, first_step=1.0, nsteps=100000,
+                                      safety=0.9, ifactor=6.0, dfactor=0.333, beta=0.0)
+            r.set_initial_value(y_sp, t0)
+            y_sp = r.integrate(t1)
+            assert r.successful()
+        rel = np.abs(y_or - y_sp) / np.maximum(np.abs(y_sp), 1e-3)
+        assert rel.max() < 1e-11, (trial, rel.max(), n_steps_total)
+
+
+def test_dop853_tableau_consistency():
+    """The generated header reproduces scipy's tableau: row sums = c_i, sum b = 1, error weights sum to 0."""
+    import re
+    txt = open(os.path.join(HERE, "..", "include", "cw_dop853_coeffs.h")).read()
+    vals = {m.group(1): float(m.group(2)) for m in re.finditer(r"#define CW_(\w+) ([-\d.e+]+)", txt)}
+    for i in range(2, 13):
+        row = sum(v for k, v in vals.items() if re.fullmatch(rf"A{i:02d}\d\d", k))
+        assert abs(row - vals[f"C{i:02d}"]) < 1e-14, i
+    assert abs(sum(v for k, v in vals.items() if re.fullmatch(r"B\d\d", k)) - 1) < 1e-14
+    assert abs(sum(v for k, v in vals.items() if re.fullmatch(r"ER\d\d", k))) < 1e-14
+    assert abs(vals["BHH1"] + vals["BHH2"] + vals["BHH3"] - 1) < 1e-14
+
+
+def test_gradient_against_numpy_and_finite_difference(oracle):
+    rng = np.random.default_rng(1)
+    for ver in ("v1", "v2"):
+        pot = MilkyWayPotential(ver)
+        for _ in range(50):
+            q = rng.normal(0, 6, 3)
+            g = oracle.gradient(pot, q)
+            # central differences of the potential value
+            h = 1e-5
+            fd = np.array([(oracle.value(pot, q + h * e) - oracle.value(pot, q - h * e)) / (2 * h) for e in np.eye(3)])
+            assert np.allclose(g, fd, rtol=2e-6, atol=1e-12)
+
+
+def test_leapfrog_reversible_and_energy(oracle):
+    v2 = MilkyWayPotential("v2")
+    w0 = np.array([8.0, 0.5, 0.1, 0.01, 0.22, 0.02])
+    t = np.arange(0.0, 1001.0, 1.0)
+    traj = oracle.leapfrog(v2, w0, t)
+    E = 0.5 * (traj[3:] ** 2).sum(axis=0) + np.array([oracle.value(v2, traj[:3, j]) for j in range(traj.shape[1])])
+    assert np.abs(E / E[0] - 1).max() < 1e-4          # symplectic: bounded energy error at dt = 1 Myr
+    # reverse: flip the velocity of the synchronised end state and integrate the same grid
+    wf = traj[:, -1].copy()
+    wf[3:] *= -1
+    back = oracle.leapfrog(v2, wf, t, store_all=False)
+    back[3:] *= -1
+    assert np.abs(back - w0).max() < 1e-10
