@@ -288,9 +288,9 @@ class Context:
         return float(self._L.cw_measure_fp64_peak(self._h, dev, ms_target))
 
     def selftest_math(self, n=1 << 22):
-        out = (C.c_double * 3)()
+        out = (C.c_double * 4)()
         self._check(self._L.cw_selftest_math(self._h, n, out), "cw_selftest_math")
-        return dict(rsqrt=out[0], rcp=out[1], log=out[2])
+        return dict(rsqrt=out[0], rcp=out[1], log=out[2], log_table=out[3])
 
 
 _DEFAULT: Optional[Context] = None

@@ -54,13 +54,25 @@ struct Arena {
 };
 
 struct Slot {
+    static constexpr int N_LANES = 3;
     int dev = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev_t0 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaStream_t stream = nullptr;          // = lanes[0]
+    cudaStream_t lanes[N_LANES] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_t0 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;   // diagnostics entry points
+    std::vector<cudaEvent_t> events;        // per-shard timing events (grow-only pool)
     Arena arena;
     double last_kernel_ms = 0.0, last_total_ms = 0.0;
-    bool timed = false;
+    cudaError_t ensure_events(size_t n)
+    {
+        while (events.size() < n) {
+            cudaEvent_t e;
+            cudaError_t err = cudaEventCreate(&e);
+            if (err != cudaSuccess) return err;
+            events.push_back(e);
+        }
+        return cudaSuccess;
+    }
 };
 
 } // namespace
@@ -139,7 +151,9 @@ extern "C" int cw_create(cw_ctx **out, int n_devices, const int *device_ids)
         s.dev = d;
         cudaError_t e = cudaSetDevice(d);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s.sm_count, cudaDevAttrMultiProcessorCount, d);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        for (int l = 0; l < Slot::N_LANES && e == cudaSuccess; l++)
+            e = cudaStreamCreateWithFlags(&s.lanes[l], cudaStreamNonBlocking);
+        s.stream = s.lanes[0];
         if (e == cudaSuccess) e = cudaEventCreate(&s.ev_t0);
         if (e == cudaSuccess) e = cudaEventCreate(&s.ev_k0);
         if (e == cudaSuccess) e = cudaEventCreate(&s.ev_k1);
@@ -163,12 +177,15 @@ extern "C" void cw_destroy(cw_ctx *ctx)
     cudaGetDevice(&prev);
     for (Slot &s : ctx->slots) {
         cudaSetDevice(s.dev);
-        if (s.stream) cudaStreamSynchronize(s.stream);
+        for (int l = 0; l < Slot::N_LANES; l++)
+            if (s.lanes[l]) cudaStreamSynchronize(s.lanes[l]);
         s.arena.release();
+        for (cudaEvent_t e : s.events) cudaEventDestroy(e);
         if (s.ev_t0) cudaEventDestroy(s.ev_t0);
         if (s.ev_k0) cudaEventDestroy(s.ev_k0);
         if (s.ev_k1) cudaEventDestroy(s.ev_k1);
-        if (s.stream) cudaStreamDestroy(s.stream);
+        for (int l = 0; l < Slot::N_LANES; l++)
+            if (s.lanes[l]) cudaStreamDestroy(s.lanes[l]);
     }
     cudaSetDevice(prev);
     delete ctx;
@@ -228,7 +245,9 @@ extern "C" int cw_set_potential(cw_ctx *ctx, double G, int n_comp, const int32_t
 
 namespace {
 
+// One unit of work: a contiguous range of orbits on one device slot, on one of its streams.
 struct Shard {
+    int slot = 0, lane = 0; // device slot, stream lane within the slot
     int64_t a = 0, b = 0;   // orbit range
     int64_t ea = 0, eb = 0; // event range
     int64_t ta = 0, tb = 0; // trajectory column range
@@ -244,6 +263,9 @@ size_t sort_temp_bytes(int64_t m)
 }
 
 constexpr int64_t SORT_THRESHOLD = 4096;
+// Host-buffer calls are cut into chunks of this many orbits that rotate over N_LANES streams, so the
+// H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the kernels of chunk c.
+constexpr int64_t HOST_CHUNK = 1 << 20;
 
 struct Plan {
     IntegArgs A;
@@ -251,23 +273,23 @@ struct Plan {
     void *sort_tmp = nullptr;
     size_t sort_bytes = 0;
     bool sort = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    bool timed = false;
 };
 
 } // namespace
 
-// Allocate (host mode: everything; device mode: scratch only) and fill the IntegArgs of one shard.
-static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B, const cw_result *R,
-                      const Shard &sh, bool integrate, Plan &pl)
+// bytes of device scratch one shard needs (host mode: everything; device mode: scratch only)
+static size_t shard_bytes(const cw_opts *o, const cw_result *R, const Shard &sh, bool integrate, Plan &pl)
 {
     const bool dev_mode = o->mem_space == CW_MEM_DEVICE;
     const int64_t m = sh.b - sh.a, K = sh.eb - sh.ea, Lt = sh.tb - sh.ta;
     const bool store_all = integrate && R && R->traj_off;
     pl.sort = integrate && m >= SORT_THRESHOLD;
     pl.sort_bytes = pl.sort ? sort_temp_bytes(m) : 0;
-
     size_t need = 0;
     auto add = [&](size_t count, size_t elt) { need += Arena::padded(count, elt); };
-    // scratch common to both modes
     add(K + 1, sizeof(double));          // ev_tk
     add(1, 64);                          // queue + stats
     if (pl.sort) { add(m, 4); add(m, 4); add(m, 4); add(pl.sort_bytes, 1); }
@@ -279,7 +301,17 @@ static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B,
     } else {
         add(m, 4); add(K + 1, 4); add(m, 4);    // n_nodes / ev_step / status if the caller passed NULL
     }
-    CW_CK(ctx, s.arena.reserve(need + 4096));
+    return need + 1024;
+}
+
+// Carve the shard's buffers out of the slot arena, fill its IntegArgs and enqueue the H2D copies.
+static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B, const cw_result *R,
+                      const Shard &sh, bool integrate, Plan &pl)
+{
+    const bool dev_mode = o->mem_space == CW_MEM_DEVICE;
+    const int64_t m = sh.b - sh.a, K = sh.eb - sh.ea, Lt = sh.tb - sh.ta;
+    const bool store_all = integrate && R && R->traj_off;
+    cudaStream_t stream = pl.stream;
 
     IntegArgs &A = pl.A;
     memset(&A, 0, sizeof A);
@@ -308,25 +340,28 @@ static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B,
         A.ev_step = s.arena.take<int32_t>(K + 1);
         A.w_final = s.arena.take<double>(6 * m);
         A.status = s.arena.take<int32_t>(m);
+        if (!w0 || !tt || !fl || !eo || !et || !ed || !A.w_final || !A.status)
+            return fail(ctx, CW_E_CUDA, "device arena exhausted (internal sizing error)");
         A.w0 = w0; A.t1 = tt; A.t2 = tt + m; A.dt = tt + 2 * m; A.to_myr = tt + 3 * m; A.flags = fl;
         for (int c = 0; c < 6; c++)
-            CW_CK(ctx, cudaMemcpyAsync(w0 + c * m, B->w0 + c * B->n_orbits + sh.a, m * 8, cudaMemcpyHostToDevice, s.stream));
-        CW_CK(ctx, cudaMemcpyAsync(tt, B->t1 + sh.a, m * 8, cudaMemcpyHostToDevice, s.stream));
-        CW_CK(ctx, cudaMemcpyAsync(tt + m, B->t2 + sh.a, m * 8, cudaMemcpyHostToDevice, s.stream));
-        CW_CK(ctx, cudaMemcpyAsync(tt + 2 * m, B->dt + sh.a, m * 8, cudaMemcpyHostToDevice, s.stream));
-        CW_CK(ctx, cudaMemcpyAsync(tt + 3 * m, B->to_myr + sh.a, m * 8, cudaMemcpyHostToDevice, s.stream));
-        CW_CK(ctx, cudaMemcpyAsync(fl, B->grid_flags + sh.a, m * 4, cudaMemcpyHostToDevice, s.stream));
+            CW_CK(ctx, cudaMemcpyAsync(w0 + c * m, B->w0 + c * B->n_orbits + sh.a, m * 8, cudaMemcpyHostToDevice, stream));
+        CW_CK(ctx, cudaMemcpyAsync(tt, B->t1 + sh.a, m * 8, cudaMemcpyHostToDevice, stream));
+        CW_CK(ctx, cudaMemcpyAsync(tt + m, B->t2 + sh.a, m * 8, cudaMemcpyHostToDevice, stream));
+        CW_CK(ctx, cudaMemcpyAsync(tt + 2 * m, B->dt + sh.a, m * 8, cudaMemcpyHostToDevice, stream));
+        CW_CK(ctx, cudaMemcpyAsync(tt + 3 * m, B->to_myr + sh.a, m * 8, cudaMemcpyHostToDevice, stream));
+        CW_CK(ctx, cudaMemcpyAsync(fl, B->grid_flags + sh.a, m * 4, cudaMemcpyHostToDevice, stream));
         if (B->ev_off && K > 0) {
-            CW_CK(ctx, cudaMemcpyAsync(eo, B->ev_off + sh.a, (m + 1) * 8, cudaMemcpyHostToDevice, s.stream));
-            CW_CK(ctx, cudaMemcpyAsync(et, B->ev_time + sh.ea, K * 8, cudaMemcpyHostToDevice, s.stream));
-            CW_CK(ctx, cudaMemcpyAsync(ed, B->ev_dv + 3 * sh.ea, 3 * K * 8, cudaMemcpyHostToDevice, s.stream));
+            CW_CK(ctx, cudaMemcpyAsync(eo, B->ev_off + sh.a, (m + 1) * 8, cudaMemcpyHostToDevice, stream));
+            CW_CK(ctx, cudaMemcpyAsync(et, B->ev_time + sh.ea, K * 8, cudaMemcpyHostToDevice, stream));
+            CW_CK(ctx, cudaMemcpyAsync(ed, B->ev_dv + 3 * sh.ea, 3 * K * 8, cudaMemcpyHostToDevice, stream));
             A.ev_off = eo; A.ev_base = sh.ea; A.ev_time = et; A.ev_dv = ed;
         }
         if (store_all) {
             int64_t *to = s.arena.take<int64_t>(m + 1);
             double *tp = s.arena.take<double>(6 * Lt + 6);
             double *ttm = s.arena.take<double>(Lt + 1);
-            CW_CK(ctx, cudaMemcpyAsync(to, R->traj_off + sh.a, (m + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+            if (!to || !tp || !ttm) return fail(ctx, CW_E_CUDA, "device arena exhausted (internal sizing error)");
+            CW_CK(ctx, cudaMemcpyAsync(to, R->traj_off + sh.a, (m + 1) * 8, cudaMemcpyHostToDevice, stream));
             A.traj_off = to; A.traj_base = sh.ta; A.traj_total = Lt;
             A.traj_pos = tp; A.traj_vel = tp + 3 * Lt; A.traj_t = R->traj_t ? ttm : nullptr;
         }
@@ -348,13 +383,13 @@ static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B,
     return CW_OK;
 }
 
-static int run_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, Plan &pl, bool integrate, bool store_all,
-                     cudaStream_t stream)
+static int run_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, Plan &pl, bool integrate, bool store_all)
 {
+    cudaStream_t stream = pl.stream;
     LaunchCfg cfg{s.sm_count, stream};
     IntegArgs &A = pl.A;
     CW_CK(ctx, cudaMemsetAsync(A.queue, 0, 64, stream));
-    CW_CK(ctx, cudaEventRecord(s.ev_t0, stream));
+    CW_CK(ctx, cudaEventRecord(pl.ev_t0, stream));
     CW_CK(ctx, launch_grid_prepass(A, pl.sort ? pl.iota : nullptr, cfg));
     ctx->last_launches += 1;
     if (integrate) {
@@ -364,12 +399,12 @@ static int run_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, Plan &pl, bool inte
                                                                  pl.keys_out, (const int32_t *)pl.iota, A.order,
                                                                  (int)A.n, 0, 32, stream));
         }
-        CW_CK(ctx, cudaEventRecord(s.ev_k0, stream));
+        CW_CK(ctx, cudaEventRecord(pl.ev_k0, stream));
         if (o->integrator == CW_LEAPFROG) CW_CK(ctx, launch_leapfrog(ctx->pot, A, store_all, cfg));
         else CW_CK(ctx, launch_dop853(ctx->pot, A, store_all, cfg));
         ctx->last_launches += 1;
-        CW_CK(ctx, cudaEventRecord(s.ev_k1, stream));
-        s.timed = true;
+        CW_CK(ctx, cudaEventRecord(pl.ev_k1, stream));
+        pl.timed = true;
     }
     return CW_OK;
 }
@@ -402,7 +437,7 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
     if (integrate && !ctx->has_pot) return fail(ctx, CW_E_NO_POTENTIAL, "cw_set_potential has not been called");
     if (integrate && (!R || !R->w_final || !R->status)) return fail(ctx, CW_E_INVALID, "w_final and status are required");
     ctx->last_launches = 0;
-    for (Slot &s : ctx->slots) { s.timed = false; s.last_kernel_ms = s.last_total_ms = 0.0; }
+    for (Slot &s : ctx->slots) { s.last_kernel_ms = s.last_total_ms = 0.0; }
     const int64_t n = B->n_orbits;
     if (n == 0) return CW_OK;
     const bool dev_mode = o->mem_space == CW_MEM_DEVICE;
@@ -411,13 +446,23 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
 
     int prev = 0;
     cudaGetDevice(&prev);
+    // ---- cut the batch: by index over the device slots, then (host buffers) into pipelined chunks
     const int nslots = dev_mode ? 1 : (int)std::min<int64_t>((int64_t)ctx->slots.size(), std::max<int64_t>(1, n));
-    std::vector<Shard> shards(nslots);
-    std::vector<Plan> plans(nslots);
+    std::vector<Shard> shards;
     for (int d = 0; d < nslots; d++) {
-        Shard &sh = shards[d];
-        sh.a = n * d / nslots;
-        sh.b = n * (d + 1) / nslots;
+        const int64_t a = n * d / nslots, b = n * (d + 1) / nslots;
+        const int64_t chunk = dev_mode ? (b - a) : HOST_CHUNK;
+        int lane = 0;
+        for (int64_t c = a; c < b; c += chunk) {
+            Shard sh;
+            sh.slot = d;
+            sh.lane = dev_mode ? 0 : (lane++ % Slot::N_LANES);
+            sh.a = c;
+            sh.b = std::min(b, c + chunk);
+            shards.push_back(sh);
+        }
+    }
+    for (Shard &sh : shards) {
         if (B->ev_off) {
             if ((rc = fetch_i64(ctx, B->ev_off + sh.a, dev_mode, &sh.ea)) != CW_OK) return rc;
             if ((rc = fetch_i64(ctx, B->ev_off + sh.b, dev_mode, &sh.eb)) != CW_OK) return rc;
@@ -428,21 +473,43 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
         }
         if (sh.eb < sh.ea || sh.tb < sh.ta) return fail(ctx, CW_E_INVALID, "offsets must be non-decreasing");
     }
-    // phase 1: enqueue everything on every device (async), phase 2: copy back + sync
+    cw_result Rl;
+    memset(&Rl, 0, sizeof Rl);
+    if (R) Rl = *R;
+    if (!integrate) { Rl.n_nodes = n_nodes_out; Rl.ev_step = ev_step_out; }
+
+    // ---- size and reserve each slot's arena once, for all of its shards
+    std::vector<Plan> plans(shards.size());
+    std::vector<size_t> need(nslots, 0);
+    for (size_t k = 0; k < shards.size(); k++) need[shards[k].slot] += shard_bytes(o, &Rl, shards[k], integrate, plans[k]);
     for (int d = 0; d < nslots; d++) {
         Slot &s = ctx->slots[d];
         cudaSetDevice(s.dev);
-        cudaStream_t stream = (dev_mode && o->stream) ? (cudaStream_t)o->stream : s.stream;
-        cw_result Rl;
-        memset(&Rl, 0, sizeof Rl);
-        if (R) Rl = *R;
-        if (!integrate) { Rl.n_nodes = n_nodes_out; Rl.ev_step = ev_step_out; }
-        rc = plan_shard(ctx, s, o, B, &Rl, shards[d], integrate, plans[d]);
-        if (rc == CW_OK) rc = run_shard(ctx, s, o, plans[d], integrate, store_all, stream);
+        size_t n_sh = 0;
+        for (const Shard &sh : shards) n_sh += (sh.slot == d);
+        // streams still running a previous no_sync call must not see their buffers move
+        if (need[d] + 4096 > s.arena.cap) for (int l = 0; l < Slot::N_LANES; l++) cudaStreamSynchronize(s.lanes[l]);
+        CW_CK(ctx, s.arena.reserve(need[d] + 4096));
+        CW_CK(ctx, s.ensure_events(3 * n_sh));
+    }
+    // ---- phase 1: enqueue everything (H2D, kernels, D2H) on every device, all asynchronous
+    std::vector<size_t> ev_used(nslots, 0);
+    const int64_t total_cols = (store_all && !dev_mode) ? R->traj_off[n] : 0;
+    for (size_t k = 0; k < shards.size(); k++) {
+        const Shard &sh = shards[k];
+        Slot &s = ctx->slots[sh.slot];
+        Plan &pl = plans[k];
+        cudaSetDevice(s.dev);
+        pl.stream = (dev_mode && o->stream) ? (cudaStream_t)o->stream : s.lanes[sh.lane];
+        pl.ev_t0 = s.events[ev_used[sh.slot]++];
+        pl.ev_k0 = s.events[ev_used[sh.slot]++];
+        pl.ev_k1 = s.events[ev_used[sh.slot]++];
+        rc = plan_shard(ctx, s, o, B, &Rl, sh, integrate, pl);
+        if (rc == CW_OK) rc = run_shard(ctx, s, o, pl, integrate, store_all);
         if (rc != CW_OK) { cudaSetDevice(prev); return rc; }
         if (!dev_mode) {
-            const Shard &sh = shards[d];
-            const IntegArgs &A = plans[d].A;
+            cudaStream_t stream = pl.stream;
+            const IntegArgs &A = pl.A;
             const int64_t m = sh.b - sh.a, K = sh.eb - sh.ea, Lt = sh.tb - sh.ta;
             int32_t *nn = integrate ? R->n_nodes : n_nodes_out;
             int32_t *es = integrate ? R->ev_step : ev_step_out;
@@ -453,11 +520,9 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
                     CW_CK(ctx, cudaMemcpyAsync(R->w_final + c * n + sh.a, A.w_final + c * m, m * 8, cudaMemcpyDeviceToHost, stream));
                 CW_CK(ctx, cudaMemcpyAsync(R->status + sh.a, A.status, m * 4, cudaMemcpyDeviceToHost, stream));
                 if (store_all && Lt > 0) {
-                    int64_t total = 0;
-                    total = R->traj_off[n];
                     for (int c = 0; c < 3; c++) {
-                        CW_CK(ctx, cudaMemcpyAsync(R->traj_pos + c * total + sh.ta, A.traj_pos + c * Lt, Lt * 8, cudaMemcpyDeviceToHost, stream));
-                        CW_CK(ctx, cudaMemcpyAsync(R->traj_vel + c * total + sh.ta, A.traj_vel + c * Lt, Lt * 8, cudaMemcpyDeviceToHost, stream));
+                        CW_CK(ctx, cudaMemcpyAsync(R->traj_pos + c * total_cols + sh.ta, A.traj_pos + c * Lt, Lt * 8, cudaMemcpyDeviceToHost, stream));
+                        CW_CK(ctx, cudaMemcpyAsync(R->traj_vel + c * total_cols + sh.ta, A.traj_vel + c * Lt, Lt * 8, cudaMemcpyDeviceToHost, stream));
                     }
                     if (R->traj_t) CW_CK(ctx, cudaMemcpyAsync(R->traj_t + sh.ta, A.traj_t, Lt * 8, cudaMemcpyDeviceToHost, stream));
                 }
@@ -465,20 +530,24 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
         }
     }
     if (dev_mode && o->no_sync) { cudaSetDevice(prev); return CW_OK; }
+    // ---- phase 2: wait, gather statistics and kernel times
     int64_t stats[4] = {0, 0, 0, 0};
-    for (int d = 0; d < nslots; d++) {
-        Slot &s = ctx->slots[d];
+    std::vector<unsigned long long> hs(4 * shards.size(), 0);
+    for (size_t k = 0; k < shards.size(); k++) {
+        Slot &s = ctx->slots[shards[k].slot];
         cudaSetDevice(s.dev);
-        cudaStream_t stream = (dev_mode && o->stream) ? (cudaStream_t)o->stream : s.stream;
-        unsigned long long hs[4] = {0, 0, 0, 0};
         if (integrate && R->stats)
-            CW_CK(ctx, cudaMemcpyAsync(hs, plans[d].A.stats, sizeof hs, cudaMemcpyDeviceToHost, stream));
-        CW_CK(ctx, cudaStreamSynchronize(stream));
-        for (int k = 0; k < 4; k++) stats[k] += (int64_t)hs[k];
-        if (s.timed) {
+            CW_CK(ctx, cudaMemcpyAsync(&hs[4 * k], plans[k].A.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, plans[k].stream));
+    }
+    for (size_t k = 0; k < shards.size(); k++) {
+        Slot &s = ctx->slots[shards[k].slot];
+        cudaSetDevice(s.dev);
+        CW_CK(ctx, cudaStreamSynchronize(plans[k].stream));
+        for (int q = 0; q < 4; q++) stats[q] += (int64_t)hs[4 * k + q];
+        if (plans[k].timed) {
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) s.last_kernel_ms = ms;
-            if (cudaEventElapsedTime(&ms, s.ev_t0, s.ev_k1) == cudaSuccess) s.last_total_ms = ms;
+            if (cudaEventElapsedTime(&ms, plans[k].ev_k0, plans[k].ev_k1) == cudaSuccess) s.last_kernel_ms += ms;
+            if (cudaEventElapsedTime(&ms, plans[k].ev_t0, plans[k].ev_k1) == cudaSuccess) s.last_total_ms += ms;
         }
     }
     if (integrate && R->stats) {
@@ -607,7 +676,7 @@ extern "C" int cw_selftest_math(cw_ctx *ctx, int64_t n, double *out)
     CW_CK(ctx, s.arena.reserve(4096));
     double *d = s.arena.take<double>(4);
     CW_CK(ctx, launch_math_selftest(n, d, cfg));
-    CW_CK(ctx, cudaMemcpyAsync(out, d, 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CW_CK(ctx, cudaMemcpyAsync(out, d, 4 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     CW_CK(ctx, cudaStreamSynchronize(s.stream));
     cudaSetDevice(prev);
     return CW_OK;

@@ -13,7 +13,7 @@ namespace cw {
 // FP64 special functions.  B200 has no FP64 SFU: sqrt / divide / log are DFMA sequences seeded
 // by MUFU.RSQ64H / MUFU.RCP64H (the only FP64-related ops that run OFF the FP64 pipe).  The CUDA
 // library versions carry special-case branches (denormals, inf, negative) that orbits never hit;
-// these versions are branch-free and cost 5 / 3 / ~12 FP64-pipe instructions.
+// these versions are branch-free and cost 5 / 3 / 12-19 FP64-pipe instructions.
 // ------------------------------------------------------------------------------------------
 
 // 1/sqrt(x), x normal and positive.  Seed (~2^-22 rel. error) + one third-order step:
@@ -69,6 +69,44 @@ __device__ __forceinline__ double log_fast(double x)
     return fma(kd, LN2_HI, fma(kd, LN2_LO, r));
 }
 
+// Table-driven ln(x), x >= 1 (Tang-style): x = 2^k m, m in [1,2); c_j = 1 + j/128 is the table node
+// nearest to m (j = 0..128), r = m/c_j - 1 (one FMA with the tabulated 1/c_j, |r| <= 2^-8) and
+// ln m = ln c_j + log1p(r), log1p by its degree-7 Taylor polynomial (remainder < 2^-67).
+// The 129 x {1/c_j, -ln(1/c_j)} table (2 KB) sits in shared memory and is filled once per CTA by
+// log_table_init; the look-up is one LDS.128 on the otherwise idle LSU pipe.  1 DADD for k plus
+// 11 FP64-pipe instructions, no MUFU: 7 fewer FP64 instructions than log_fast.
+constexpr int LOG_TABLE_N = 129;
+
+__device__ __forceinline__ void log_table_init(double2 *tab)
+{
+    for (int j = threadIdx.x; j < LOG_TABLE_N; j += blockDim.x) {
+        const double invc = 1.0 / (1.0 + (double)j * 0.0078125);
+        tab[j] = make_double2(invc, -log(invc));      // ln of the c actually used (1/invc)
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double log_tab(double x, const double2 *__restrict__ tab)
+{
+    const int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    const int k = (hi >> 20) - 1023;
+    const int j = (((hi >> 12) & 0xff) + 1) >> 1;                    // nearest of 128 mantissa nodes
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double kd = __hiloint2double(0x43300000, k ^ 0x80000000) - 4503601774854144.0; // 2^52 + 2^31
+    const double2 t = tab[j];
+    const double r = fma(m, t.x, -1.0);
+    double q = 1.0 / 7.0;
+    q = fma(q, r, -1.0 / 6.0);
+    q = fma(q, r, 0.2);
+    q = fma(q, r, -0.25);
+    q = fma(q, r, 1.0 / 3.0);
+    q = fma(q, r, -0.5);
+    const double lp = fma(r * r, q, r);                              // log1p(r)
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    return fma(kd, LN2_HI, t.y + fma(kd, LN2_LO, lp));
+}
+
 // ------------------------------------------------------------------------------------------
 // Potential parameter block.  Passed by value as a __grid_constant__ kernel parameter, i.e. it
 // lives in the constant bank (c[0x0][...]) and every access is a uniform broadcast -- the
@@ -101,7 +139,8 @@ struct PotParams {
 //   Hernquist:   f = GM / ((r+c)^2 r);                                    g += f q
 //   NFW:         f = GM (ln(1+r/rs) - r/(r+rs)) / r^3;                    g += f q
 template <int NMN, bool SHARED_B>
-__device__ __forceinline__ void gradient_mw(const PotParams &P, double x, double y, double z,
+__device__ __forceinline__ void gradient_mw(const PotParams &P, const double2 *__restrict__ ltab,
+                                            double x, double y, double z,
                                             double &gx, double &gy, double &gz)
 {
     const double R2 = fma(y, y, x * x);
@@ -109,41 +148,45 @@ __device__ __forceinline__ void gradient_mw(const PotParams &P, double x, double
     const double r2 = R2 + z2;
 
     double fxy = 0.0, fz = 0.0;
-    double isz_shared = 0.0, sz_shared = 0.0;
     if (SHARED_B) {
+        // all terms share sqrt(z^2 + b^2): fz = sum f_i (1 + a_i/sz) = fxy + (sum a_i f_i) / sz
         const double q = z2 + P.mn_b2[0];
-        isz_shared = rsqrt_fast(q);
-        sz_shared = q * isz_shared;
-    }
+        const double isz = rsqrt_fast(q);
+        const double sz = q * isz;
+        double fa = 0.0;
 #pragma unroll
-    for (int i = 0; i < NMN; i++) {
-        double isz, sz;
-        if (SHARED_B) {
-            isz = isz_shared;
-            sz = sz_shared;
-        } else {
-            const double q = z2 + P.mn_b2[i];
-            isz = rsqrt_fast(q);
-            sz = q * isz;
+        for (int i = 0; i < NMN; i++) {
+            const double zd = P.mn_a[i] + sz;
+            const double rs = rsqrt_fast(fma(zd, zd, R2));
+            const double f = (rs * rs) * (P.mn_GM[i] * rs);
+            fxy += f;
+            fa = fma(P.mn_a[i], f, fa);
         }
-        const double zd = P.mn_a[i] + sz;
-        const double s = fma(zd, zd, R2);
-        const double rs = rsqrt_fast(s);
-        const double f = (rs * rs) * (P.mn_GM[i] * rs);
-        fxy += f;
-        fz = fma(f, fma(P.mn_a[i], isz, 1.0), fz);
+        fz = fma(isz, fa, fxy);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NMN; i++) {
+            const double q = z2 + P.mn_b2[i];
+            const double isz = rsqrt_fast(q);
+            const double zd = fma(q, isz, P.mn_a[i]);
+            const double rs = rsqrt_fast(fma(zd, zd, R2));
+            const double f = (rs * rs) * (P.mn_GM[i] * rs);
+            fxy += f;
+            fz = fma(f, fma(P.mn_a[i], isz, 1.0), fz);
+        }
     }
 
     const double ir = rsqrt_fast(r2);
     const double r = r2 * ir;
-    // two Hernquist spheres
+    // two Hernquist spheres over one reciprocal: GM0/rc0^2 + GM1/rc1^2 = (GM0 rc1^2 + GM1 rc0^2) / (rc0 rc1)^2
     const double rc0 = r + P.h_c[0], rc1 = r + P.h_c[1];
-    double h = P.h_GM[0] * rcp_fast(rc0 * rc0);
-    h = fma(P.h_GM[1], rcp_fast(rc1 * rc1), h);
+    const double s0 = rc0 * rc0, s1 = rc1 * rc1;
+    const double h = fma(P.h_GM[1], s0, P.h_GM[0] * s1) * rcp_fast(s0 * s1);
     // NFW
     const double u = r * P.nfw_inv_rs;
     const double w = 1.0 + u;
-    const double bracket = log_fast(w) - u * rcp_fast(w);
+    const double lw = ltab ? log_tab(w, ltab) : log_fast(w);
+    const double bracket = lw - u * rcp_fast(w);
     const double ir3 = (ir * ir) * ir;
     double fs = h * ir;
     fs = fma(P.nfw_GM * ir3, bracket, fs);
@@ -154,7 +197,8 @@ __device__ __forceinline__ void gradient_mw(const PotParams &P, double x, double
 }
 
 // Generic composite: components in the caller's order.
-__device__ __forceinline__ void gradient_generic(const PotParams &P, double x, double y, double z,
+__device__ __forceinline__ void gradient_generic(const PotParams &P, const double2 *__restrict__ ltab,
+                                                 double x, double y, double z,
                                                  double &gx, double &gy, double &gz)
 {
     const double R2 = fma(y, y, x * x);
@@ -186,7 +230,7 @@ __device__ __forceinline__ void gradient_generic(const PotParams &P, double x, d
             } else { // CW_COMP_NFW_SPHERICAL
                 const double u = r * P.p2[i];               // p2 = 1/r_s for NFW
                 const double w = 1.0 + u;
-                const double bracket = log_fast(w) - u * rcp_fast(w);
+                const double bracket = (ltab ? log_tab(w, ltab) : log_fast(w)) - u * rcp_fast(w);
                 f = P.GM[i] * ((ir * ir) * ir) * bracket;
             }
             fxy += f;
@@ -198,13 +242,15 @@ __device__ __forceinline__ void gradient_generic(const PotParams &P, double x, d
     gz = fz * z;
 }
 
+// ltab: the CTA's shared-memory log table (log_table_init), or nullptr to use the table-free log.
 template <int KIND>
-__device__ __forceinline__ void gradient(const PotParams &P, double x, double y, double z,
+__device__ __forceinline__ void gradient(const PotParams &P, const double2 *__restrict__ ltab,
+                                         double x, double y, double z,
                                          double &gx, double &gy, double &gz)
 {
-    if (KIND == POT_MW_V1) gradient_mw<1, false>(P, x, y, z, gx, gy, gz);
-    else if (KIND == POT_MW_V2) gradient_mw<3, true>(P, x, y, z, gx, gy, gz);
-    else gradient_generic(P, x, y, z, gx, gy, gz);
+    if (KIND == POT_MW_V1) gradient_mw<1, false>(P, ltab, x, y, z, gx, gy, gz);
+    else if (KIND == POT_MW_V2) gradient_mw<3, true>(P, ltab, x, y, z, gx, gy, gz);
+    else gradient_generic(P, ltab, x, y, z, gx, gy, gz);
 }
 
 // dt of a segment = t[1] - t[0] with both nodes converted to Myr first (gala converts the whole

@@ -12,6 +12,8 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const __grid_constant__ 
                                                         int64_t n, const double *__restrict__ q,
                                                         double *__restrict__ out)
 {
+    __shared__ double2 ltab[LOG_TABLE_N];
+    log_table_init(ltab);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double x = q[i], y = q[n + i], z = q[2 * n + i];
@@ -20,7 +22,7 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const __grid_constant__ 
             continue;
         }
         double gx, gy, gz;
-        gradient<KIND>(P, x, y, z, gx, gy, gz);
+        gradient<KIND>(P, ltab, x, y, z, gx, gy, gz);
         if (mode == 0) {
             out[i] = gx; out[n + i] = gy; out[2 * n + i] = gz;
         } else {
@@ -80,7 +82,9 @@ cudaError_t launch_dfma_peak(double *sink, int iters, const LaunchCfg &cfg, int 
 // log-uniform sample of the arguments orbits produce (1e-8 .. 1e8; log argument 1 .. 1e4)
 __global__ void __launch_bounds__(256) math_selftest_kernel(int64_t n, double *out3)
 {
-    double e0 = 0.0, e1 = 0.0, e2 = 0.0;
+    __shared__ double2 ltab[LOG_TABLE_N];
+    log_table_init(ltab);
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         // golden-ratio low-discrepancy sequence in [0,1)
@@ -94,16 +98,18 @@ __global__ void __launch_bounds__(256) math_selftest_kernel(int64_t n, double *o
         e1 = fmax(e1, fabs(rcp_fast(x) - r1) / r1);
         const double r2 = log(w);
         if (r2 > 1e-3) e2 = fmax(e2, fabs(log_fast(w) - r2) / r2);
+        if (r2 > 1e-3) e3 = fmax(e3, fabs(log_tab(w, ltab) - r2) / r2);
     }
     // orders are preserved for non-negative doubles reinterpreted as integers
     atomicMax((unsigned long long *)&out3[0], (unsigned long long)__double_as_longlong(e0));
     atomicMax((unsigned long long *)&out3[1], (unsigned long long)__double_as_longlong(e1));
     atomicMax((unsigned long long *)&out3[2], (unsigned long long)__double_as_longlong(e2));
+    atomicMax((unsigned long long *)&out3[3], (unsigned long long)__double_as_longlong(e3));
 }
 
 cudaError_t launch_math_selftest(int64_t n, double *out3, const LaunchCfg &cfg)
 {
-    cudaError_t err = cudaMemsetAsync(out3, 0, 3 * sizeof(double), cfg.stream);
+    cudaError_t err = cudaMemsetAsync(out3, 0, 4 * sizeof(double), cfg.stream);
     if (err != cudaSuccess) return err;
     math_selftest_kernel<<<cfg.sm_count * 4, 256, 0, cfg.stream>>>(n, out3);
     return cudaGetLastError();

@@ -53,10 +53,10 @@ __device__ __forceinline__ int64_t dp_queue_pop(unsigned long long *queue)
 }
 
 template <int KIND>
-__device__ __forceinline__ void fcn(const PotParams &P, const double *y, double *f)
+__device__ __forceinline__ void fcn(const PotParams &P, const double2 *__restrict__ ltab, const double *y, double *f)
 {
     double gx, gy, gz;
-    gradient<KIND>(P, y[0], y[1], y[2], gx, gy, gz);
+    gradient<KIND>(P, ltab, y[0], y[1], y[2], gx, gy, gz);
     f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
     f[3] = -gx; f[4] = -gy; f[5] = -gz;
 }
@@ -118,6 +118,8 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
                                                           const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
+    __shared__ double2 ltab[LOG_TABLE_N];
+    log_table_init(ltab);
     DpLane s;
 #pragma unroll
     for (int c = 0; c < 6; c++) { s.y[c] = (c == 0) ? 8.0 : 0.0; s.k1[c] = 0.0; }
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
             dp_apply_kicks(A, s);
             dp_store_sample<STORE>(A, s);
             if (s.L == 0) { dp_write_final(A, s, CW_ORBIT_OK); continue; }
-            fcn<KIND>(P, s.y, s.k1);
+            fcn<KIND>(P, ltab, s.y, s.k1);
             n_fcn++;
             dp_begin_interval(s);
             active = true;
@@ -200,28 +202,28 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
 
 #define CW_STAGE(EXPR) _Pragma("unroll") for (int i = 0; i < 6; i++) yy1[i] = fma(h, (EXPR), y[i]);
             CW_STAGE(CW_A0201 * k1[i])
-            fcn<KIND>(P, yy1, k2);
+            fcn<KIND>(P, ltab, yy1, k2);
             CW_STAGE(fma(CW_A0302, k2[i], CW_A0301 * k1[i]))
-            fcn<KIND>(P, yy1, k3);
+            fcn<KIND>(P, ltab, yy1, k3);
             CW_STAGE(fma(CW_A0403, k3[i], CW_A0401 * k1[i]))
-            fcn<KIND>(P, yy1, k4);
+            fcn<KIND>(P, ltab, yy1, k4);
             CW_STAGE(fma(CW_A0504, k4[i], fma(CW_A0503, k3[i], CW_A0501 * k1[i])))
-            fcn<KIND>(P, yy1, k5);
+            fcn<KIND>(P, ltab, yy1, k5);
             CW_STAGE(fma(CW_A0605, k5[i], fma(CW_A0604, k4[i], CW_A0601 * k1[i])))
-            fcn<KIND>(P, yy1, k6);
+            fcn<KIND>(P, ltab, yy1, k6);
             CW_STAGE(fma(CW_A0706, k6[i], fma(CW_A0705, k5[i], fma(CW_A0704, k4[i], CW_A0701 * k1[i]))))
-            fcn<KIND>(P, yy1, k7);
+            fcn<KIND>(P, ltab, yy1, k7);
             CW_STAGE(fma(CW_A0807, k7[i], fma(CW_A0806, k6[i], fma(CW_A0805, k5[i], fma(CW_A0804, k4[i], CW_A0801 * k1[i])))))
-            fcn<KIND>(P, yy1, k8);
+            fcn<KIND>(P, ltab, yy1, k8);
             CW_STAGE(fma(CW_A0908, k8[i], fma(CW_A0907, k7[i], fma(CW_A0906, k6[i], fma(CW_A0905, k5[i], fma(CW_A0904, k4[i], CW_A0901 * k1[i]))))))
-            fcn<KIND>(P, yy1, k9);
+            fcn<KIND>(P, ltab, yy1, k9);
             CW_STAGE(fma(CW_A1009, k9[i], fma(CW_A1008, k8[i], fma(CW_A1007, k7[i], fma(CW_A1006, k6[i], fma(CW_A1005, k5[i], fma(CW_A1004, k4[i], CW_A1001 * k1[i])))))))
-            fcn<KIND>(P, yy1, k10);
+            fcn<KIND>(P, ltab, yy1, k10);
             CW_STAGE(fma(CW_A1110, k10[i], fma(CW_A1109, k9[i], fma(CW_A1108, k8[i], fma(CW_A1107, k7[i], fma(CW_A1106, k6[i], fma(CW_A1105, k5[i], fma(CW_A1104, k4[i], CW_A1101 * k1[i]))))))))
-            fcn<KIND>(P, yy1, k2);
+            fcn<KIND>(P, ltab, yy1, k2);
             const double xph = __dadd_rn(s.x, h);
             CW_STAGE(fma(CW_A1211, k2[i], fma(CW_A1210, k10[i], fma(CW_A1209, k9[i], fma(CW_A1208, k8[i], fma(CW_A1207, k7[i], fma(CW_A1206, k6[i], fma(CW_A1205, k5[i], fma(CW_A1204, k4[i], CW_A1201 * k1[i])))))))))
-            fcn<KIND>(P, yy1, k3);
+            fcn<KIND>(P, ltab, yy1, k3);
 #undef CW_STAGE
             n_fcn += 11;
 
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
                 s.facold = fmax(err, 1.0e-4);
                 s.naccpt++;
                 n_acc++;
-                fcn<KIND>(P, k5, k4);       // first stage of the next step
+                fcn<KIND>(P, ltab, k5, k4);       // first stage of the next step
                 n_fcn++;
                 // stiffness detection (nstiff = 1: every accepted step)
                 double stnum = 0.0, stden = 0.0;

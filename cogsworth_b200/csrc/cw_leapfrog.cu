@@ -41,17 +41,26 @@ __global__ void __launch_bounds__(256) grid_prepass_kernel(const __grid_constant
     double te_prev = -INF;
     int j = 0, cursor = 0;
     double T = a, Tprev = a;
-    while (T < b && j < 1000000) {
-        // node j exists at time T; every pending event with t_event <= T lands before it
-        while (!(T < te)) {
-            const int k = max(cursor, j - 1);
-            A.ev_step[e] = k;
-            A.ev_tk[e] = Tprev;
-            cursor = k;
-            if (te < te_prev) st = CW_ORBIT_INCONSISTENT; // events must be chronological
-            te_prev = te;
-            e++;
-            te = (e < e1) ? A.ev_time[e] : INF;
+    if (te != te) st = CW_ORBIT_INCONSISTENT;      // NaN event time
+    // One loop, one FP64 compare + one DADD per node on the fast path; the rare branch (an event
+    // lands, or the grid ends) sits INSIDE the loop body so the warp reconverges every iteration.
+    double lim = fmin(b, te);
+    for (;;) {
+        if (!(T < lim) || j >= 1000000) {
+            if (!(T < b) || j >= 1000000) break;   // the grid ends here
+            // node j exists at time T and every pending event with t_event <= T lands before it
+            while (!(T < te)) {
+                const int k = max(cursor, j - 1);
+                A.ev_step[e] = k;
+                A.ev_tk[e] = Tprev;
+                cursor = k;
+                if (te < te_prev) st = CW_ORBIT_INCONSISTENT; // events must be chronological
+                te_prev = te;
+                e++;
+                te = (e < e1) ? A.ev_time[e] : INF;
+                if (te != te) st = CW_ORBIT_INCONSISTENT;
+            }
+            lim = fmin(b, te);
         }
         Tprev = T;
         j++;
@@ -167,6 +176,8 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
                                                             const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
+    __shared__ double2 ltab[LOG_TABLE_N];
+    log_table_init(ltab);
     Lane s;
     s.x = 8.0; s.y = 0.0; s.z = 0.0; s.vx = s.vy = s.vz = 0.0;
     s.vhx = s.vhy = s.vhz = 0.0; s.gx = s.gy = s.gz = 0.0;
@@ -221,7 +232,7 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
             apply_kicks(A, s);          // events at (or before) the first node: kicks.py:155-157
             store_sample<STORE>(A, s);
             if (s.L == 0) { write_final(A, s); continue; }
-            gradient<KIND>(P, s.x, s.y, s.z, s.gx, s.gy, s.gz);
+            gradient<KIND>(P, ltab, s.x, s.y, s.z, s.gx, s.gy, s.gz);
             const double hdt = s.dt * 0.5;
             s.vhx = fma(-s.gx, hdt, s.vx);
             s.vhy = fma(-s.gy, hdt, s.vy);
@@ -239,7 +250,7 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
             s.x = fma(s.vhx, dt, s.x);
             s.y = fma(s.vhy, dt, s.y);
             s.z = fma(s.vhz, dt, s.z);
-            gradient<KIND>(P, s.x, s.y, s.z, s.gx, s.gy, s.gz);
+            gradient<KIND>(P, ltab, s.x, s.y, s.z, s.gx, s.gy, s.gz);
             s.vhx = fma(-s.gx, dt, s.vhx);
             s.vhy = fma(-s.gy, dt, s.vhy);
             s.vhz = fma(-s.gz, dt, s.vhz);
@@ -248,7 +259,7 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
             s.x = fma(s.vhx, dt, s.x);
             s.y = fma(s.vhy, dt, s.y);
             s.z = fma(s.vhz, dt, s.z);
-            gradient<KIND>(P, s.x, s.y, s.z, s.gx, s.gy, s.gz);
+            gradient<KIND>(P, ltab, s.x, s.y, s.z, s.gx, s.gy, s.gz);
             const double hdt = dt * 0.5;
             s.vx = fma(-s.gx, hdt, s.vhx);
             s.vy = fma(-s.gy, hdt, s.vhy);

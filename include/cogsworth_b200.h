@@ -177,8 +177,8 @@ double cw_last_total_kernel_ms(const cw_ctx *ctx, int dev);
 /* DFMA micro-benchmark on device slot `dev`: returns sustained FP64 TFLOP/s (2 flop per FMA) over
  * about `ms_target` milliseconds -- the roofline denominator for this path. */
 double cw_measure_fp64_peak(cw_ctx *ctx, int dev, double ms_target);
-/* max relative error of the kernels' own rsqrt / reciprocal / log against the CUDA math library
- * over n samples; out[3] */
+/* max relative error of the kernels' own rsqrt / reciprocal / log (table-free) / log (table)
+ * against the CUDA math library over n samples; out[4] */
 int cw_selftest_math(cw_ctx *ctx, int64_t n, double *out);
 
 #ifdef __cplusplus
