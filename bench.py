@@ -352,7 +352,8 @@ def main():
         roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": "measured live: DFMA micro-benchmark cw_measure_fp64_peak (MEASURED_PEAKS.json has no "
                                "FP64 entry; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
-                "kernel": kname, "kernel_ms": k_ms, "algorithmic_flop_per_unit": per,
+                "kernel": kname, "kernel_ms": k_ms, "prepass_sort_pilot_ms": float(np.mean(total_kernel_ms)) - k_ms,
+                "algorithmic_flop_per_unit": per,
                 "kernel_share_of_step": k_ms / (dev_ms / args.steps)}
 
     cbase = None

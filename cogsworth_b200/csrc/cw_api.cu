@@ -269,7 +269,7 @@ constexpr int64_t HOST_CHUNK = 1 << 20;
 
 struct Plan {
     IntegArgs A;
-    int32_t *iota = nullptr, *keys_out = nullptr;
+    int32_t *iota = nullptr, *keys_out = nullptr, *keys_in = nullptr, *order = nullptr;
     void *sort_tmp = nullptr;
     size_t sort_bytes = 0;
     bool sort = false;
@@ -292,12 +292,12 @@ static size_t shard_bytes(const cw_opts *o, const cw_result *R, const Shard &sh,
     auto add = [&](size_t count, size_t elt) { need += Arena::padded(count, elt); };
     add(K + 1, sizeof(double));          // ev_tk
     add(1, 64);                          // queue + stats
-    if (pl.sort) { add(m, 4); add(m, 4); add(m, 4); add(pl.sort_bytes, 1); }
+    if (pl.sort) { add(m, 4); add(m, 4); add(m, 4); add(m, 4); add(pl.sort_bytes, 1); }
     if (!dev_mode) {
         add(6 * m, 8); add(4 * m, 8); add(m, 4); add(m + 1, 8); add(K + 1, 8); add(3 * K + 3, 8);
         add(m, 4); add(K + 1, 4);               // n_nodes, ev_step
         add(6 * m, 8); add(m, 4);               // w_final, status
-        if (store_all) { add(m + 1, 8); add(6 * Lt + 6, 8); add(Lt + 1, 8); }
+        if (store_all) { add(m + 1, 8); add(6 * (Lt + 16), 8); add(Lt + 1, 8); }
     } else {
         add(m, 4); add(K + 1, 4); add(m, 4);    // n_nodes / ev_step / status if the caller passed NULL
     }
@@ -326,7 +326,9 @@ static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B,
     if (pl.sort) {
         pl.iota = s.arena.take<int32_t>(m);
         pl.keys_out = s.arena.take<int32_t>(m);
-        A.order = s.arena.take<int32_t>(m);
+        pl.keys_in = s.arena.take<int32_t>(m);
+        pl.order = s.arena.take<int32_t>(m);
+        A.order = pl.order;
         pl.sort_tmp = s.arena.take<char>(pl.sort_bytes);
     }
     if (!dev_mode) {
@@ -357,13 +359,16 @@ static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B,
             A.ev_off = eo; A.ev_base = sh.ea; A.ev_time = et; A.ev_dv = ed;
         }
         if (store_all) {
+            // device rows are padded to a multiple of 16 columns so every row starts 128-byte aligned
+            // (the trajectory writer's bulk stores need 16-byte aligned destinations)
+            const int64_t Ltp = (Lt + 15) & ~int64_t(15);
             int64_t *to = s.arena.take<int64_t>(m + 1);
-            double *tp = s.arena.take<double>(6 * Lt + 6);
+            double *tp = s.arena.take<double>(6 * Ltp);
             double *ttm = s.arena.take<double>(Lt + 1);
             if (!to || !tp || !ttm) return fail(ctx, CW_E_CUDA, "device arena exhausted (internal sizing error)");
             CW_CK(ctx, cudaMemcpyAsync(to, R->traj_off + sh.a, (m + 1) * 8, cudaMemcpyHostToDevice, stream));
-            A.traj_off = to; A.traj_base = sh.ta; A.traj_total = Lt;
-            A.traj_pos = tp; A.traj_vel = tp + 3 * Lt; A.traj_t = R->traj_t ? ttm : nullptr;
+            A.traj_off = to; A.traj_base = sh.ta; A.traj_total = Ltp;
+            A.traj_pos = tp; A.traj_vel = tp + 3 * Ltp; A.traj_t = R->traj_t ? ttm : nullptr;
         }
     } else {
         A.w0 = B->w0; A.t1 = B->t1; A.t2 = B->t2; A.dt = B->dt; A.to_myr = B->to_myr; A.flags = B->grid_flags;
@@ -394,8 +399,21 @@ static int run_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, Plan &pl, bool inte
     ctx->last_launches += 1;
     if (integrate) {
         if (pl.sort) {
-            // longest orbits first: keys = node counts, values = orbit ids
-            CW_CK(ctx, cub::DeviceRadixSort::SortPairsDescending(pl.sort_tmp, pl.sort_bytes, (const int32_t *)A.n_nodes,
+            // Longest-processing-time-first queue.  Leapfrog: cost = node count.  DOP853: cost = node
+            // count x step attempts per interval, measured by a short pilot integration (the persistent
+            // short-period orbits near the nucleus need 10-50x the attempts of a disc orbit).
+            const int32_t *keys = (const int32_t *)A.n_nodes;
+            if (o->integrator == CW_DOP853) {
+                A.cost_key = pl.keys_in;
+                A.pilot_intervals = 16;
+                A.order = nullptr;
+                CW_CK(ctx, launch_dop853_pilot(ctx->pot, A, cfg));
+                ctx->last_launches += 1;
+                CW_CK(ctx, cudaMemsetAsync(A.queue, 0, 8, stream));
+                A.order = pl.order;
+                keys = pl.keys_in;
+            }
+            CW_CK(ctx, cub::DeviceRadixSort::SortPairsDescending(pl.sort_tmp, pl.sort_bytes, keys,
                                                                  pl.keys_out, (const int32_t *)pl.iota, A.order,
                                                                  (int)A.n, 0, 32, stream));
         }
@@ -405,6 +423,10 @@ static int run_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, Plan &pl, bool inte
         ctx->last_launches += 1;
         CW_CK(ctx, cudaEventRecord(pl.ev_k1, stream));
         pl.timed = true;
+        if (store_all && A.traj_t) {
+            CW_CK(ctx, launch_traj_times(A, cfg));
+            ctx->last_launches += 1;
+        }
     }
     return CW_OK;
 }
@@ -521,8 +543,8 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
                 CW_CK(ctx, cudaMemcpyAsync(R->status + sh.a, A.status, m * 4, cudaMemcpyDeviceToHost, stream));
                 if (store_all && Lt > 0) {
                     for (int c = 0; c < 3; c++) {
-                        CW_CK(ctx, cudaMemcpyAsync(R->traj_pos + c * total_cols + sh.ta, A.traj_pos + c * Lt, Lt * 8, cudaMemcpyDeviceToHost, stream));
-                        CW_CK(ctx, cudaMemcpyAsync(R->traj_vel + c * total_cols + sh.ta, A.traj_vel + c * Lt, Lt * 8, cudaMemcpyDeviceToHost, stream));
+                        CW_CK(ctx, cudaMemcpyAsync(R->traj_pos + c * total_cols + sh.ta, A.traj_pos + c * A.traj_total, Lt * 8, cudaMemcpyDeviceToHost, stream));
+                        CW_CK(ctx, cudaMemcpyAsync(R->traj_vel + c * total_cols + sh.ta, A.traj_vel + c * A.traj_total, Lt * 8, cudaMemcpyDeviceToHost, stream));
                     }
                     if (R->traj_t) CW_CK(ctx, cudaMemcpyAsync(R->traj_t + sh.ta, A.traj_t, Lt * 8, cudaMemcpyDeviceToHost, stream));
                 }

@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 #include <climits>
 #include "cw_kernels.cuh"
+#include "cw_traj.cuh"
 #include "../../include/cw_dop853_coeffs.h"
 
 namespace cg = cooperative_groups;
@@ -61,21 +62,6 @@ __device__ __forceinline__ void fcn(const PotParams &P, const double2 *__restric
     f[3] = -gx; f[4] = -gy; f[5] = -gz;
 }
 
-template <bool STORE>
-__device__ __forceinline__ void dp_store_sample(const IntegArgs &A, const DpLane &s)
-{
-    if (STORE) {
-        const int64_t col = A.traj_off[s.oid] - A.traj_base + s.j;
-        A.traj_pos[col] = s.y[0];
-        A.traj_pos[A.traj_total + col] = s.y[1];
-        A.traj_pos[2 * A.traj_total + col] = s.y[2];
-        A.traj_vel[col] = s.y[3];
-        A.traj_vel[A.traj_total + col] = s.y[4];
-        A.traj_vel[2 * A.traj_total + col] = s.y[5];
-        if (A.traj_t) A.traj_t[col] = s.tgrid * s.smyr;
-    }
-}
-
 __device__ __forceinline__ void dp_write_final(const IntegArgs &A, const DpLane &s, int status)
 {
     const int64_t n = A.n;
@@ -113,13 +99,22 @@ __device__ __forceinline__ void dp_begin_interval(DpLane &s)
     s.last = false; s.reject = false;
 }
 
-template <int KIND, bool STORE>
+// PILOT = true: integrate only the first A.pilot_intervals intervals of every orbit and write a cost
+// estimate (attempts per interval x number of intervals) to A.cost_key, nothing else.  The host
+// sorts the queue by that key so the expensive (short-period, sub-stepping) orbits start first:
+// with one sequential orbit per lane the makespan is max(longest orbit, total work / lanes), and a
+// long orbit started late would leave the whole GPU waiting for a single lane.
+template <int KIND, bool STORE, bool PILOT>
 __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant__ PotParams P,
                                                           const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
     __shared__ double2 ltab[LOG_TABLE_N];
+    extern __shared__ __align__(16) unsigned char traj_smem[];
     log_table_init(ltab);
+    TrajWriter tw;
+    if (STORE && !PILOT) tw.init(traj_smem, A);
+    int64_t col_base = 0;
     DpLane s;
 #pragma unroll
     for (int c = 0; c < 6; c++) { s.y[c] = (c == 0) ? 8.0 : 0.0; s.k1[c] = 0.0; }
@@ -129,6 +124,7 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
     s.nstep = s.naccpt = s.iasti = s.nonsti = 0;
     s.last = s.reject = s.append = false;
     bool active = false, exhausted = false, interval_done = false;
+    int attempts = 0, Lstop = 0;       // PILOT bookkeeping
     unsigned long long n_acc = 0, n_rej = 0, n_fcn = 0, n_int = 0;
     const int64_t nmax = (A.nmax > 0) ? A.nmax : 100000;
     const double atol = A.atol, rtol = A.rtol;
@@ -141,14 +137,19 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
             s.tgrid = (s.append && s.j == s.L) ? s.t2 : s.tgrid + s.hgrid;
             n_int++;
             dp_apply_kicks(A, s);
-            dp_store_sample<STORE>(A, s);
-            if (s.j == s.L) {
+            if (STORE && !PILOT)
+                tw.put(col_base + s.j, s.y[0], s.y[1], s.y[2], s.y[3], s.y[4], s.y[5], s.j == s.L);
+            if (PILOT && s.j == Lstop) {
+                A.cost_key[s.oid] = __float_as_int((float)attempts * ((float)s.L / (float)Lstop));
+                active = false;
+            } else if (s.j == s.L) {
                 dp_write_final(A, s, CW_ORBIT_OK);
                 active = false;
             } else {
                 dp_begin_interval(s);
             }
         }
+        if (STORE && !PILOT) tw.flush_warp();
         // ---- phase B: idle lanes pull the next orbit
         while (!active && !exhausted) {
             const int64_t p = dp_queue_pop(A.queue);
@@ -161,9 +162,12 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
             s.j = 0;
             s.L = A.n_nodes[o] - 1;
             if (A.status[o] != CW_ORBIT_OK || s.L < 0) {
-                dp_write_final(A, s, CW_ORBIT_OK); // status already set by the pre-pass
+                if (PILOT) A.cost_key[o] = 0;
+                else dp_write_final(A, s, CW_ORBIT_OK); // status already set by the pre-pass
                 continue;
             }
+            attempts = 0;
+            Lstop = min(s.L, A.pilot_intervals);
             s.hgrid = A.dt[o]; s.t2 = A.t2[o]; s.smyr = A.to_myr[o];
             s.append = (A.flags[o] & CW_GRID_APPEND_T2) != 0;
             s.tgrid = A.t1[o];
@@ -174,13 +178,22 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
                 s.dt0 = seg_dt_myr(s.tgrid, tn, s.smyr);
             }
             dp_apply_kicks(A, s);
-            dp_store_sample<STORE>(A, s);
-            if (s.L == 0) { dp_write_final(A, s, CW_ORBIT_OK); continue; }
+            if (STORE && !PILOT) {
+                col_base = A.traj_off[o] - A.traj_base;
+                if (s.L == 0) traj_store_direct(A, col_base, s.y[0], s.y[1], s.y[2], s.y[3], s.y[4], s.y[5]);
+                else tw.put(col_base, s.y[0], s.y[1], s.y[2], s.y[3], s.y[4], s.y[5], false);
+            }
+            if (s.L == 0) {
+                if (PILOT) A.cost_key[o] = 0;
+                else dp_write_final(A, s, CW_ORBIT_OK);
+                continue;
+            }
             fcn<KIND>(P, ltab, s.y, s.k1);
             n_fcn++;
             dp_begin_interval(s);
             active = true;
         }
+        if (STORE && !PILOT) tw.flush_warp();
         if (!__any_sync(FULL, active)) break;   // warp-level early exit
 
         // ---- phase C: one step attempt of dopcor() for every lane that has an open interval
@@ -189,10 +202,12 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
             if (s.nstep > nmax) fail = CW_ORBIT_NMAX;
             else if (0.1 * fabs(s.h) <= fabs(s.x) * 2.3e-16) fail = CW_ORBIT_STEP_TOO_SMALL;
             if (fail) {
-                dp_write_final(A, s, fail);
+                if (PILOT) A.cost_key[s.oid] = 0x7f000000;   // failing orbits are the most expensive: first
+                else dp_write_final(A, s, fail);
                 active = false;
                 continue;
             }
+            attempts++;
             const double posneg = (s.xend - s.x > 0.0) ? 1.0 : -1.0;
             if (__dmul_rn(__dsub_rn(__dadd_rn(s.x, __dmul_rn(1.01, s.h)), s.xend), posneg) > 0.0) { s.h = __dsub_rn(s.xend, s.x); s.last = true; }
             s.nstep++;
@@ -247,7 +262,8 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
             if (deno <= 0.0) deno = 1.0;
             err = fabs(h) * err * sqrt(1.0 / (deno * 6.0));
             if (!(err <= 1.79769313486231571e+308)) {   // NaN or inf: Hairer would spin to nmax
-                dp_write_final(A, s, CW_ORBIT_NONFINITE);
+                if (PILOT) A.cost_key[s.oid] = 0;
+                else dp_write_final(A, s, CW_ORBIT_NONFINITE);
                 active = false;
                 continue;
             }
@@ -285,7 +301,8 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
                 for (int i = 0; i < 6; i++) { s.k1[i] = k4[i]; s.y[i] = k5[i]; }
                 s.x = xph;
                 if (stiff) {
-                    dp_write_final(A, s, CW_ORBIT_STIFF);
+                    if (PILOT) A.cost_key[s.oid] = 0;
+                    else dp_write_final(A, s, CW_ORBIT_STIFF);
                     active = false;
                     continue;
                 }
@@ -307,7 +324,7 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
             }
         }
     }
-    if (A.stats) {
+    if (A.stats && !PILOT) {
         for (int off = 16; off > 0; off >>= 1) {
             n_acc += __shfl_down_sync(FULL, n_acc, off);
             n_rej += __shfl_down_sync(FULL, n_rej, off);
@@ -323,19 +340,24 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
     }
 }
 
-template <int KIND, bool STORE>
+template <int KIND, bool STORE, bool PILOT>
 static cudaError_t launch_dp(const PotParams &P, const IntegArgs &A, const LaunchCfg &cfg)
 {
     int per_sm = 0;
-    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dop853_kernel<KIND, STORE>,
-                                                                    DP_BLOCK, 0);
+    const size_t dyn = (STORE && !PILOT) ? (size_t)DP_BLOCK * TRAJ_LANE_BYTES : 0;
+    cudaError_t err = cudaSuccess;
+    if (dyn) {
+        err = cudaFuncSetAttribute(dop853_kernel<KIND, STORE, PILOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (err != cudaSuccess) return err;
+    }
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dop853_kernel<KIND, STORE, PILOT>, DP_BLOCK, dyn);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)cfg.sm_count * per_sm;
     const int64_t need = (A.n + DP_BLOCK - 1) / DP_BLOCK;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    dop853_kernel<KIND, STORE><<<(unsigned)grid, DP_BLOCK, 0, cfg.stream>>>(P, A);
+    dop853_kernel<KIND, STORE, PILOT><<<(unsigned)grid, DP_BLOCK, dyn, cfg.stream>>>(P, A);
     return cudaGetLastError();
 }
 
@@ -344,11 +366,21 @@ cudaError_t launch_dop853(const PotParams &P, const IntegArgs &A, bool store_all
     if (A.n <= 0) return cudaSuccess;
     switch (P.kind) {
     case POT_MW_V1:
-        return store_all ? launch_dp<POT_MW_V1, true>(P, A, cfg) : launch_dp<POT_MW_V1, false>(P, A, cfg);
+        return store_all ? launch_dp<POT_MW_V1, true, false>(P, A, cfg) : launch_dp<POT_MW_V1, false, false>(P, A, cfg);
     case POT_MW_V2:
-        return store_all ? launch_dp<POT_MW_V2, true>(P, A, cfg) : launch_dp<POT_MW_V2, false>(P, A, cfg);
+        return store_all ? launch_dp<POT_MW_V2, true, false>(P, A, cfg) : launch_dp<POT_MW_V2, false, false>(P, A, cfg);
     default:
-        return store_all ? launch_dp<POT_GENERIC, true>(P, A, cfg) : launch_dp<POT_GENERIC, false>(P, A, cfg);
+        return store_all ? launch_dp<POT_GENERIC, true, false>(P, A, cfg) : launch_dp<POT_GENERIC, false, false>(P, A, cfg);
+    }
+}
+
+cudaError_t launch_dop853_pilot(const PotParams &P, const IntegArgs &A, const LaunchCfg &cfg)
+{
+    if (A.n <= 0) return cudaSuccess;
+    switch (P.kind) {
+    case POT_MW_V1: return launch_dp<POT_MW_V1, false, true>(P, A, cfg);
+    case POT_MW_V2: return launch_dp<POT_MW_V2, false, true>(P, A, cfg);
+    default: return launch_dp<POT_GENERIC, false, true>(P, A, cfg);
     }
 }
 

@@ -36,6 +36,8 @@ struct IntegArgs {
     double atol, rtol;
     int64_t nmax;
     unsigned long long *stats; // 4: accepted, rejected, gradient evaluations, orbit-steps
+    int32_t *cost_key;         // n   DOP853 pilot: float bits of the estimated step attempts per orbit
+    int32_t pilot_intervals;   // intervals the pilot integrates
 };
 
 struct LaunchCfg {
@@ -49,6 +51,10 @@ cudaError_t launch_grid_prepass(const IntegArgs &A, int32_t *iota_out, const Lau
 cudaError_t launch_leapfrog(const PotParams &P, const IntegArgs &A, bool store_all, const LaunchCfg &cfg);
 // adaptive DOP853 restarted per grid interval (gala dop853_integrate_hamiltonian semantics)
 cudaError_t launch_dop853(const PotParams &P, const IntegArgs &A, bool store_all, const LaunchCfg &cfg);
+// DOP853 pilot: first A.pilot_intervals intervals of every orbit -> A.cost_key (queue ordering)
+cudaError_t launch_dop853_pilot(const PotParams &P, const IntegArgs &A, const LaunchCfg &cfg);
+// Orbit.t of stored trajectories (only when traj_t was requested)
+cudaError_t launch_traj_times(const IntegArgs &A, const LaunchCfg &cfg);
 // pointwise potential kernels (N3 rows); mode 0 gradient (3 x n), 1 value (n), 2 v_circ (n)
 cudaError_t launch_pointwise(const PotParams &P, int mode, int64_t n, const double *q, double *out,
                              const LaunchCfg &cfg);

@@ -14,6 +14,7 @@
 #include <cooperative_groups.h>
 #include <climits>
 #include "cw_kernels.cuh"
+#include "cw_traj.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -45,26 +46,44 @@ __global__ void __launch_bounds__(256) grid_prepass_kernel(const __grid_constant
     // One loop, one FP64 compare + one DADD per node on the fast path; the rare branch (an event
     // lands, or the grid ends) sits INSIDE the loop body so the warp reconverges every iteration.
     double lim = fmin(b, te);
-    for (;;) {
-        if (!(T < lim) || j >= 1000000) {
-            if (!(T < b) || j >= 1000000) break;   // the grid ends here
-            // node j exists at time T and every pending event with t_event <= T lands before it
-            while (!(T < te)) {
-                const int k = max(cursor, j - 1);
-                A.ev_step[e] = k;
-                A.ev_tk[e] = Tprev;
-                cursor = k;
-                if (te < te_prev) st = CW_ORBIT_INCONSISTENT; // events must be chronological
-                te_prev = te;
-                e++;
-                te = (e < e1) ? A.ev_time[e] : INF;
-                if (te != te) st = CW_ORBIT_INCONSISTENT;
+    if (!(h > 0.0)) st = CW_ORBIT_INCONSISTENT;    // gala raises for dt <= 0 with t2 > t1
+    bool done = false;
+    while (!done) {
+        // 8 nodes per trip while none of them reaches `lim`: the same sequential FP64 additions, but
+        // one compare and one branch for eight of them (the add chain is latency-, not pipe-bound).
+        // Both arms sit inside one if/else so the warp reconverges at the bottom of every trip.
+        const double a1 = T + h, a2 = a1 + h, a3 = a2 + h, a4 = a3 + h;
+        const double a5 = a4 + h, a6 = a5 + h, a7 = a6 + h, a8 = a7 + h;
+        if (a7 < lim && j + 8 <= 1000000 && h > 0.0) {
+            Tprev = a7;
+            T = a8;
+            j += 8;
+        } else {
+            if (!(T < lim) || j >= 1000000) {
+                if (!(T < b) || j >= 1000000) {
+                    done = true;                   // the grid ends here
+                } else {
+                    // node j exists at time T and every pending event with t_event <= T lands before it
+                    while (!(T < te)) {
+                        const int k = max(cursor, j - 1);
+                        A.ev_step[e] = k;
+                        A.ev_tk[e] = Tprev;
+                        cursor = k;
+                        if (te < te_prev) st = CW_ORBIT_INCONSISTENT; // events must be chronological
+                        te_prev = te;
+                        e++;
+                        te = (e < e1) ? A.ev_time[e] : INF;
+                        if (te != te) st = CW_ORBIT_INCONSISTENT;
+                    }
+                    lim = fmin(b, te);
+                }
             }
-            lim = fmin(b, te);
+            if (!done) {
+                Tprev = T;
+                j++;
+                T += h;
+            }
         }
-        Tprev = T;
-        j++;
-        T += h;
     }
     const int n_acc = j;
     const int n_nodes = n_acc + ((append && n_acc > 0) ? 1 : 0);
@@ -98,6 +117,32 @@ cudaError_t launch_grid_prepass(const IntegArgs &A, int32_t *iota_out, const Lau
     return cudaGetLastError();
 }
 
+// Orbit.t of stored trajectories: the grid itself, converted to Myr (kicks.py:188).  t is a pure
+// function of (t1, dt, t2, flags), so it is written by this side kernel (thread per orbit, same FP64
+// accumulation as the pre-pass) instead of riding through the integrator kernels.
+__global__ void __launch_bounds__(256) traj_times_kernel(const __grid_constant__ IntegArgs A)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n || A.status[i] != CW_ORBIT_OK) return;
+    const double b = A.t2[i], h = A.dt[i], sm = A.to_myr[i];
+    const int n = A.n_nodes[i];
+    const bool append = (A.flags[i] & CW_GRID_APPEND_T2) != 0;
+    double *out = A.traj_t + (A.traj_off[i] - A.traj_base);
+    double T = A.t1[i];
+    for (int j = 0; j < n; j++) {
+        out[j] = ((append && j == n - 1) ? b : T) * sm;
+        T += h;
+    }
+}
+
+cudaError_t launch_traj_times(const IntegArgs &A, const LaunchCfg &cfg)
+{
+    if (A.n <= 0 || !A.traj_t || !A.traj_off) return cudaSuccess;
+    const int block = 256;
+    traj_times_kernel<<<(unsigned)((A.n + block - 1) / block), block, 0, cfg.stream>>>(A);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // Leapfrog
 // ------------------------------------------------------------------------------------------
@@ -125,21 +170,6 @@ __device__ __forceinline__ int64_t queue_pop(unsigned long long *queue)
     if (g.thread_rank() == 0) base = atomicAdd(queue, (unsigned long long)g.size());
     base = g.shfl(base, 0);
     return (int64_t)(base + g.thread_rank());
-}
-
-template <bool STORE>
-__device__ __forceinline__ void store_sample(const IntegArgs &A, const Lane &s)
-{
-    if (STORE) {
-        const int64_t col = A.traj_off[s.oid] - A.traj_base + s.j;
-        A.traj_pos[col] = s.x;
-        A.traj_pos[A.traj_total + col] = s.y;
-        A.traj_pos[2 * A.traj_total + col] = s.z;
-        A.traj_vel[col] = s.vx;
-        A.traj_vel[A.traj_total + col] = s.vy;
-        A.traj_vel[2 * A.traj_total + col] = s.vz;
-        if (A.traj_t) A.traj_t[col] = s.tcur * s.smyr;
-    }
 }
 
 // apply every kick scheduled on node s.j (kicks.py:160-172); returns true if the segment restarts
@@ -177,7 +207,11 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
 {
     const unsigned FULL = 0xffffffffu;
     __shared__ double2 ltab[LOG_TABLE_N];
+    extern __shared__ __align__(16) unsigned char traj_smem[];
     log_table_init(ltab);
+    TrajWriter tw;
+    if (STORE) tw.init(traj_smem, A);
+    int64_t col_base = 0;          // STORE: column of sample 0 of the current orbit
     Lane s;
     s.x = 8.0; s.y = 0.0; s.z = 0.0; s.vx = s.vy = s.vz = 0.0;
     s.vhx = s.vhy = s.vhz = 0.0; s.gx = s.gy = s.gz = 0.0;
@@ -190,7 +224,7 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
         // ---- phase A: lanes standing on a sync node (kick node / last node / every node when STORE)
         if (active && s.j == s.next) {
             const bool kicked = apply_kicks(A, s);
-            store_sample<STORE>(A, s);
+            if (STORE) tw.put(col_base + s.j, s.x, s.y, s.z, s.vx, s.vy, s.vz, s.j == s.L);
             if (s.j == s.L) {
                 write_final(A, s);
                 active = false;
@@ -204,6 +238,7 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
                 s.next = STORE ? s.j + 1 : ((s.e < s.e1) ? A.ev_step[s.e] : s.L);
             }
         }
+        if (STORE) tw.flush_warp();   // windows completed on this node (incl. the last one of an orbit)
         // ---- phase B: idle lanes pull the next orbit from the queue
         while (!active && !exhausted) {
             const int64_t p = queue_pop(A.queue);
@@ -230,7 +265,11 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
                 s.dt = seg_dt_myr(t0, tn, s.smyr);
             }
             apply_kicks(A, s);          // events at (or before) the first node: kicks.py:155-157
-            store_sample<STORE>(A, s);
+            if (STORE) {
+                col_base = A.traj_off[o] - A.traj_base;
+                if (s.L == 0) traj_store_direct(A, col_base, s.x, s.y, s.z, s.vx, s.vy, s.vz);
+                else tw.put(col_base, s.x, s.y, s.z, s.vx, s.vy, s.vz, false);
+            }
             if (s.L == 0) { write_final(A, s); continue; }
             gradient<KIND>(P, ltab, s.x, s.y, s.z, s.gx, s.gy, s.gz);
             const double hdt = s.dt * 0.5;
@@ -240,6 +279,7 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
             s.next = STORE ? 1 : ((s.e < s.e1) ? A.ev_step[s.e] : s.L);
             active = true;
         }
+        if (STORE) tw.flush_warp();   // a first sample can complete a window (column = 7 mod 8)
         if (!__any_sync(FULL, active)) break;
 
         // ---- phase C: a warp-uniform run of steps up to the nearest sync node of any lane
@@ -271,7 +311,6 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
         if (active) {
             s.j += m;
             steps_done += (unsigned long long)m;
-            if (STORE) s.tcur = (s.append && s.j == s.L) ? s.t2 : s.tcur + s.hgrid;
         }
     }
     if (A.stats) {
@@ -285,15 +324,20 @@ template <int KIND, bool STORE>
 static cudaError_t launch_lf(const PotParams &P, const IntegArgs &A, const LaunchCfg &cfg)
 {
     int per_sm = 0;
-    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, leapfrog_kernel<KIND, STORE>,
-                                                                    LF_BLOCK, 0);
+    const size_t dyn = STORE ? (size_t)LF_BLOCK * TRAJ_LANE_BYTES : 0;
+    cudaError_t err = cudaSuccess;
+    if (STORE) {
+        err = cudaFuncSetAttribute(leapfrog_kernel<KIND, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (err != cudaSuccess) return err;
+    }
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, leapfrog_kernel<KIND, STORE>, LF_BLOCK, dyn);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)cfg.sm_count * per_sm;
     const int64_t need = (A.n + LF_BLOCK - 1) / LF_BLOCK;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    leapfrog_kernel<KIND, STORE><<<(unsigned)grid, LF_BLOCK, 0, cfg.stream>>>(P, A);
+    leapfrog_kernel<KIND, STORE><<<(unsigned)grid, LF_BLOCK, dyn, cfg.stream>>>(P, A);
     return cudaGetLastError();
 }
 

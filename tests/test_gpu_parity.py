@@ -153,6 +153,31 @@ def test_config5_dop853_plunging(ctx, oracle):
     assert acc_g > ni_g          # sub-stepping happened (divergent step counts)
 
 
+@pytest.mark.parametrize("integ", [_lib.LEAPFROG, _lib.DOP853])
+def test_results_independent_of_queue_order_and_chunking(ctx, oracle, integ):
+    """Large batches are reordered (longest / most expensive orbit first; DOP853 runs a pilot to
+    estimate the cost) and host-buffer calls are cut into pipelined chunks: neither may change a bit
+    of any orbit's result."""
+    pop = make_population(3400, cfg_id=41, horizon_gyr=0.12, plunging_fraction=0.05)
+    b = pop.batch
+    assert b.n_orbits > 4096                       # above the sort threshold
+    ctx.set_potential(pop.potential)
+    big = ctx.integrate(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv, integrator=integ)
+    idx = np.arange(500, 1500)
+    sub = b.take(idx)
+    small = ctx.integrate(sub.w0, sub.t1, sub.t2, sub.dt, sub.to_myr, sub.flags, sub.ev_off, sub.ev_time, sub.ev_dv,
+                          integrator=integ)
+    assert np.array_equal(big["w_final"][:, idx], small["w_final"])
+    assert np.array_equal(big["status"][idx], small["status"])
+    o = oracle.integrate_batch(pop.potential, b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv,
+                               integrator=integ)
+    check_bit_exact_bookkeeping(big, o)
+    d = rel_diff(big["w_final"], o["w_final"])
+    assert np.quantile(d, 0.9) < (1e-10 if integ == _lib.LEAPFROG else 1e-7)
+    if integ == _lib.DOP853:
+        assert abs(int(big["stats"][0]) - o["stats"][0]) <= 5e-3 * o["stats"][0]
+
+
 def test_generic_composite_kernel(ctx, oracle):
     """A component list that is neither MW shape runs through the generic kernel."""
     pot = CompositePotential(names=["bulge", "disk", "halo", "disk2"], types=[2, 1, 3, 1],
