@@ -26,7 +26,7 @@ ORBIT_STATUS = {0: "ok", -1: "inconsistent input", -2: "larger nmax is needed",
 EXPORTS = ["cw_create", "cw_destroy", "cw_device_count", "cw_set_potential", "cw_count_nodes",
            "cw_integrate", "cw_gradient", "cw_potential_value", "cw_circular_velocity", "cw_strerror",
            "cw_last_error", "cw_abi_version", "cw_last_launch_count", "cw_last_kernel_ms",
-           "cw_last_total_kernel_ms", "cw_measure_fp64_peak", "cw_selftest_math"]
+           "cw_last_total_kernel_ms", "cw_measure_fp64_peak", "cw_measure_scatter_write", "cw_selftest_math"]
 
 
 class CwOpts(C.Structure):
@@ -94,6 +94,8 @@ def load():
     L.cw_last_total_kernel_ms.restype = C.c_double
     L.cw_measure_fp64_peak.argtypes = [vp, C.c_int, C.c_double]
     L.cw_measure_fp64_peak.restype = C.c_double
+    L.cw_measure_scatter_write.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int]
+    L.cw_measure_scatter_write.restype = C.c_double
     L.cw_selftest_math.argtypes = [vp, C.c_int64, C.POINTER(C.c_double)]
     L.cw_selftest_math.restype = C.c_int
     _LIB = L
@@ -287,10 +289,15 @@ class Context:
     def measure_fp64_peak(self, dev=0, ms_target=50.0) -> float:
         return float(self._L.cw_measure_fp64_peak(self._h, dev, ms_target))
 
+    def measure_scatter_write(self, streams, stream_bytes, run_bytes, resident_threads_per_sm=2048, dev=0) -> float:
+        return float(self._L.cw_measure_scatter_write(self._h, dev, streams, stream_bytes, run_bytes,
+                                                      resident_threads_per_sm))
+
     def selftest_math(self, n=1 << 22):
-        out = (C.c_double * 4)()
+        out = (C.c_double * 8)()
         self._check(self._L.cw_selftest_math(self._h, n, out), "cw_selftest_math")
-        return dict(rsqrt=out[0], rcp=out[1], log=out[2], log_table=out[3])
+        return dict(rsqrt=out[0], rcp=out[1], log=out[2], log_table=out[3], dfma_latency_cycles=out[4],
+                    rsqrt_dadd_latency_cycles=out[5], dmul_latency_cycles=out[6])
 
 
 _DEFAULT: Optional[Context] = None

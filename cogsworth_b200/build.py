@@ -32,7 +32,10 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return OUT
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    extra = []
+    if os.environ.get("CW_TRAJ_S"):          # experiment knob: staging window of the trajectory writer
+        extra.append("-DCW_TRAJ_S=" + os.environ["CW_TRAJ_S"])
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
     env = dict(os.environ)
     env.pop("CC", None)      # the image exports a CC without libgomp specs; nvcc wants the system g++
     env.pop("CXX", None)

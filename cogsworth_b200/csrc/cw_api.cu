@@ -687,6 +687,40 @@ extern "C" double cw_measure_fp64_peak(cw_ctx *ctx, int dev, double ms_target)
     return result;
 }
 
+extern "C" double cw_measure_scatter_write(cw_ctx *ctx, int dev, int64_t streams, int64_t stream_bytes, int run_bytes,
+                                           int resident_threads_per_sm)
+{
+    if (!ctx || dev < 0 || dev >= (int)ctx->slots.size() || run_bytes < 16 || run_bytes > 512 || (run_bytes & 15) ||
+        stream_bytes % run_bytes)
+        return -1.0;
+    Slot &s = ctx->slots[dev];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s.dev);
+    LaunchCfg cfg{s.sm_count, s.stream};
+    double result = -1.0;
+    do {
+        const size_t bytes = (size_t)streams * (size_t)stream_bytes;
+        if (s.arena.reserve(bytes + 4096) != cudaSuccess) break;
+        double2 *base = s.arena.take<double2>(bytes / 16);
+        if (!base) break;
+        int blocks = s.sm_count * std::max(1, resident_threads_per_sm / 256);
+        float ms = 0.f;
+        bool ok = true;
+        for (int pass = 0; pass < 2 && ok; pass++) {
+            ok = ok && cudaEventRecord(s.ev_k0, s.stream) == cudaSuccess;
+            ok = ok && launch_scatter_write(base, streams, stream_bytes, run_bytes, blocks, cfg) == cudaSuccess;
+            ok = ok && cudaEventRecord(s.ev_k1, s.stream) == cudaSuccess;
+            ok = ok && cudaStreamSynchronize(s.stream) == cudaSuccess;
+            ok = ok && cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess;
+        }
+        if (ok && ms > 0.f) result = (double)bytes / (ms * 1e-3) / 1e9;
+    } while (0);
+    cudaGetLastError();
+    cudaSetDevice(prev);
+    return result;
+}
+
 extern "C" int cw_selftest_math(cw_ctx *ctx, int64_t n, double *out)
 {
     if (!ctx || !out || ctx->slots.empty()) return CW_E_INVALID;
@@ -696,9 +730,9 @@ extern "C" int cw_selftest_math(cw_ctx *ctx, int64_t n, double *out)
     cudaSetDevice(s.dev);
     LaunchCfg cfg{s.sm_count, s.stream};
     CW_CK(ctx, s.arena.reserve(4096));
-    double *d = s.arena.take<double>(4);
+    double *d = s.arena.take<double>(8);
     CW_CK(ctx, launch_math_selftest(n, d, cfg));
-    CW_CK(ctx, cudaMemcpyAsync(out, d, 4 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CW_CK(ctx, cudaMemcpyAsync(out, d, 7 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     CW_CK(ctx, cudaStreamSynchronize(s.stream));
     cudaSetDevice(prev);
     return CW_OK;

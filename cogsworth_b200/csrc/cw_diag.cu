@@ -107,11 +107,64 @@ __global__ void __launch_bounds__(256) math_selftest_kernel(int64_t n, double *o
     atomicMax((unsigned long long *)&out3[3], (unsigned long long)__double_as_longlong(e3));
 }
 
+// Scatter-write micro-benchmark: the HBM write pattern of store_all, without the arithmetic.  `streams`
+// independent sequential streams (one per orbit coordinate), each `stream_bytes` long and far apart;
+// every visit appends one run of `run_bytes` (16-byte chunks by run_bytes/16 adjacent lanes, one
+// STG.128 per lane), all streams advance in lock-step.  Gives the ceiling of the access pattern.
+__global__ void __launch_bounds__(256) scatter_write_kernel(double2 *base, long long streams, long long stream_bytes,
+                                                            int run_bytes)
+{
+    const int g = run_bytes / 16;                  // lanes per run
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / g; // global run-slot id
+    const long long nslots = (long long)gridDim.x * blockDim.x / g;
+    const int c = threadIdx.x % g;
+    const long long visits = stream_bytes / run_bytes;
+    const double2 v = make_double2((double)gw, (double)c);
+    for (long long s0 = gw; s0 < streams; s0 += nslots) {
+        // this slot owns stream s0 (streams beyond the resident set are taken in later passes)
+        double2 *p = base + (s0 * stream_bytes) / 16 + c;
+        for (long long k = 0; k < visits; k++) p[k * g] = v;
+    }
+}
+
+cudaError_t launch_scatter_write(double2 *base, long long streams, long long stream_bytes, int run_bytes,
+                                 int blocks, const LaunchCfg &cfg)
+{
+    scatter_write_kernel<<<blocks, 256, 0, cfg.stream>>>(base, streams, stream_bytes, run_bytes);
+    return cudaGetLastError();
+}
+
+// dependent-issue latency (cycles) of DFMA, MUFU.RSQ64H+DFMA and the whole rsqrt_fast, one warp alone
+__global__ void latency_probe_kernel(double *out)
+{
+    double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-9;
+    const int N = 4096;
+    long long t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; i++) a = fma(a, 1.0000001, b);
+    long long t1 = clock64();
+    double c = 2.0 + a * 1e-30;
+#pragma unroll 16
+    for (int i = 0; i < N; i++) c = rsqrt_fast(c) + 1.5;
+    long long t2 = clock64();
+    double d = 2.0 + c * 1e-30;
+#pragma unroll 16
+    for (int i = 0; i < N; i++) d = d * 1.0000001;
+    long long t3 = clock64();
+    if (threadIdx.x == 0) {
+        out[4] = (double)(t1 - t0) / N;
+        out[5] = (double)(t2 - t1) / N;
+        out[6] = (double)(t3 - t2) / N;
+        out[7] = a + c + d;
+    }
+}
+
 cudaError_t launch_math_selftest(int64_t n, double *out3, const LaunchCfg &cfg)
 {
-    cudaError_t err = cudaMemsetAsync(out3, 0, 4 * sizeof(double), cfg.stream);
+    cudaError_t err = cudaMemsetAsync(out3, 0, 8 * sizeof(double), cfg.stream);
     if (err != cudaSuccess) return err;
     math_selftest_kernel<<<cfg.sm_count * 4, 256, 0, cfg.stream>>>(n, out3);
+    latency_probe_kernel<<<1, 32, 0, cfg.stream>>>(out3);
     return cudaGetLastError();
 }
 

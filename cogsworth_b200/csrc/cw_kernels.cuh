@@ -60,6 +60,8 @@ cudaError_t launch_pointwise(const PotParams &P, int mode, int64_t n, const doub
                              const LaunchCfg &cfg);
 // diagnostics
 cudaError_t launch_dfma_peak(double *sink, int iters, const LaunchCfg &cfg, int *blocks, int *threads);
+cudaError_t launch_scatter_write(double2 *base, long long streams, long long stream_bytes, int run_bytes,
+                                 int blocks, const LaunchCfg &cfg);
 cudaError_t launch_math_selftest(int64_t n, double *out3, const LaunchCfg &cfg);
 
 } // namespace cw

@@ -217,25 +217,42 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
     s.vhx = s.vhy = s.vhz = 0.0; s.gx = s.gy = s.gz = 0.0;
     s.dt = 0.0; s.hgrid = 0.0; s.t2 = 0.0; s.smyr = 1.0; s.tcur = 0.0;
     s.e = s.e1 = 0; s.oid = -1; s.j = 0; s.next = 0; s.L = 0; s.append = false;
-    bool active = false, exhausted = false;
+    bool active = false, exhausted = false, staged = false;
     unsigned long long steps_done = 0;
+    if (STORE) {
+        // De-phase the warps.  With equal-length orbits every warp of the GPU would complete its staging
+        // windows on the same step and the whole chip would alternate between an FP64-only phase and a
+        // store burst that overruns the LSU queues (ncu: 28 % of warp time stalled in the flush).  One
+        // step takes about a microsecond per warp at this occupancy; spreading the start of the warps
+        // over one window period lets the stores of one warp overlap the arithmetic of the others.
+        const unsigned gw = (blockIdx.x * (LF_BLOCK / 32) + (threadIdx.x >> 5));
+        __nanosleep((gw % TRAJ_S) * 1000u);
+    }
 
     for (;;) {
-        // ---- phase A: lanes standing on a sync node (kick node / last node / every node when STORE)
-        if (active && s.j == s.next) {
-            const bool kicked = apply_kicks(A, s);
-            if (STORE) tw.put(col_base + s.j, s.x, s.y, s.z, s.vx, s.vy, s.vz, s.j == s.L);
-            if (s.j == s.L) {
-                write_final(A, s);
-                active = false;
-            } else {
-                if (kicked) { // c_init_velocity of the new segment; gradient at this node is already known
-                    const double hdt = s.dt * 0.5;
-                    s.vhx = fma(-s.gx, hdt, s.vx);
-                    s.vhy = fma(-s.gy, hdt, s.vy);
-                    s.vhz = fma(-s.gz, hdt, s.vz);
+        // ---- phase A: lanes standing on a sync node (kick node / last node).  When STORE, the sample of
+        // the node every active lane stands on has not been staged yet (it must carry the post-kick
+        // velocity): stage it here, sync node or not.
+        if (active && (s.j == s.next || (STORE && !staged))) {
+            const bool at_sync = (s.j == s.next);
+            const bool kicked = at_sync ? apply_kicks(A, s) : false;
+            if (STORE) {
+                tw.put(col_base + s.j, s.x, s.y, s.z, s.vx, s.vy, s.vz, s.j == s.L);
+                staged = true;
+            }
+            if (at_sync) {
+                if (s.j == s.L) {
+                    write_final(A, s);
+                    active = false;
+                } else {
+                    if (kicked) { // c_init_velocity of the new segment; gradient at this node is already known
+                        const double hdt = s.dt * 0.5;
+                        s.vhx = fma(-s.gx, hdt, s.vx);
+                        s.vhy = fma(-s.gy, hdt, s.vy);
+                        s.vhz = fma(-s.gz, hdt, s.vz);
+                    }
+                    s.next = (s.e < s.e1) ? A.ev_step[s.e] : s.L;
                 }
-                s.next = STORE ? s.j + 1 : ((s.e < s.e1) ? A.ev_step[s.e] : s.L);
             }
         }
         if (STORE) tw.flush_warp();   // windows completed on this node (incl. the last one of an orbit)
@@ -269,6 +286,7 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
                 col_base = A.traj_off[o] - A.traj_base;
                 if (s.L == 0) traj_store_direct(A, col_base, s.x, s.y, s.z, s.vx, s.vy, s.vz);
                 else tw.put(col_base, s.x, s.y, s.z, s.vx, s.vy, s.vz, false);
+                staged = true;
             }
             if (s.L == 0) { write_final(A, s); continue; }
             gradient<KIND>(P, ltab, s.x, s.y, s.z, s.gx, s.gy, s.gz);
@@ -276,24 +294,47 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
             s.vhx = fma(-s.gx, hdt, s.vx);
             s.vhy = fma(-s.gy, hdt, s.vy);
             s.vhz = fma(-s.gz, hdt, s.vz);
-            s.next = STORE ? 1 : ((s.e < s.e1) ? A.ev_step[s.e] : s.L);
+            s.next = (s.e < s.e1) ? A.ev_step[s.e] : s.L;
             active = true;
         }
         if (STORE) tw.flush_warp();   // a first sample can complete a window (column = 7 mod 8)
         if (!__any_sync(FULL, active)) break;
 
         // ---- phase C: a warp-uniform run of steps up to the nearest sync node of any lane
-        const int r = active ? (s.next - s.j) : INT_MAX;
+        int r = active ? (s.next - s.j) : INT_MAX;
+        if (STORE && active) {
+            // ... and not past the node that completes this lane's staging window (column = 7 mod 8):
+            // inside the run samples are staged without any vote, the completing one at the next phase A
+            const int c7 = (int)((col_base + s.j) & (TRAJ_S - 1));
+            r = min(r, ((TRAJ_S - 2 - c7) & (TRAJ_S - 1)) + 1);
+        }
         const int m = __reduce_min_sync(FULL, r);
         const double dt = s.dt;
-        for (int q = 1; q < m; q++) {   // c_leapfrog_step without the synchronised velocity
-            s.x = fma(s.vhx, dt, s.x);
-            s.y = fma(s.vhy, dt, s.y);
-            s.z = fma(s.vhz, dt, s.z);
-            gradient<KIND>(P, ltab, s.x, s.y, s.z, s.gx, s.gy, s.gz);
-            s.vhx = fma(-s.gx, dt, s.vhx);
-            s.vhy = fma(-s.gy, dt, s.vhy);
-            s.vhz = fma(-s.gz, dt, s.vhz);
+        if (!STORE) {
+            for (int q = 1; q < m; q++) {   // c_leapfrog_step without the synchronised velocity
+                s.x = fma(s.vhx, dt, s.x);
+                s.y = fma(s.vhy, dt, s.y);
+                s.z = fma(s.vhz, dt, s.z);
+                gradient<KIND>(P, ltab, s.x, s.y, s.z, s.gx, s.gy, s.gz);
+                s.vhx = fma(-s.gx, dt, s.vhx);
+                s.vhy = fma(-s.gy, dt, s.vhy);
+                s.vhz = fma(-s.gz, dt, s.vhz);
+            }
+        } else {
+            const double hdt = dt * 0.5;
+            for (int q = 1; q < m; q++) {   // full steps, every sample staged
+                s.x = fma(s.vhx, dt, s.x);
+                s.y = fma(s.vhy, dt, s.y);
+                s.z = fma(s.vhz, dt, s.z);
+                gradient<KIND>(P, ltab, s.x, s.y, s.z, s.gx, s.gy, s.gz);
+                s.vx = fma(-s.gx, hdt, s.vhx);
+                s.vy = fma(-s.gy, hdt, s.vhy);
+                s.vz = fma(-s.gz, hdt, s.vhz);
+                s.vhx = fma(-s.gx, dt, s.vhx);
+                s.vhy = fma(-s.gy, dt, s.vhy);
+                s.vhz = fma(-s.gz, dt, s.vhz);
+                if (active) tw.stage(col_base + s.j + q, s.x, s.y, s.z, s.vx, s.vy, s.vz);
+            }
         }
         {   // full c_leapfrog_step: v = vh - g dt/2 ; vh = vh - g dt
             s.x = fma(s.vhx, dt, s.x);
@@ -308,6 +349,7 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
             s.vhy = fma(-s.gy, dt, s.vhy);
             s.vhz = fma(-s.gz, dt, s.vhz);
         }
+        staged = false;
         if (active) {
             s.j += m;
             steps_done += (unsigned long long)m;

@@ -4,7 +4,7 @@
 //
 // One lane integrates one orbit, so consecutive samples of a lane are consecutive in memory but the
 // 32 lanes of a warp write 32 far-apart columns: a plain st.global.f64 per sample would cost a whole
-// 32-byte L2 sector transaction for 8 useful bytes.  Instead every lane stages TRAJ_S = 8 consecutive
+// 32-byte L2 sector transaction for 8 useful bytes.  Instead every lane stages TRAJ_S (8) consecutive
 // samples of its six coordinates in its own shared-memory rows.  Windows are aligned to ABSOLUTE
 // columns (slot = column & 7), so a complete window is six 64-byte, 64-byte-aligned runs whatever the
 // orbit's offset.  At the two warp-convergent points of the integrator loop the warp votes which lanes
@@ -22,7 +22,13 @@
 
 namespace cw {
 
-constexpr int TRAJ_S = 8;                                    // samples per window
+#ifndef CW_TRAJ_S
+#define CW_TRAJ_S 8
+#endif
+constexpr int TRAJ_S = CW_TRAJ_S;                            // samples per window (4 or 8)
+constexpr int TRAJ_CPR = TRAJ_S / 2;                         // 16-byte chunks per row
+constexpr int TRAJ_LPS = 6 * TRAJ_CPR;                       // flush lanes per source lane (24 | 12)
+constexpr int TRAJ_SPI = 32 / TRAJ_LPS;                      // source lanes per store instruction (1 | 2)
 constexpr int TRAJ_ROWS = 6;                                 // x y z vx vy vz
 constexpr int TRAJ_DATA_BYTES = TRAJ_ROWS * TRAJ_S * 8;      // 384
 constexpr int TRAJ_LANE_BYTES = TRAJ_DATA_BYTES + 16;        // + header {col0, n}; also de-phases the banks
@@ -47,9 +53,8 @@ struct TrajWriter {
         const int lane = threadIdx.x & 31;
         warp_base = smem + (size_t)(threadIdx.x - lane) * TRAJ_LANE_BYTES;
         buf = reinterpret_cast<double *>(warp_base + (size_t)lane * TRAJ_LANE_BYTES);
-        const int r = lane >> 2;
-        my_row = (r < 3) ? A.traj_pos + (int64_t)r * A.traj_total
-                         : A.traj_vel + (int64_t)((r < 6 ? r : 5) - 3) * A.traj_total;
+        const int r = min((lane % TRAJ_LPS) / TRAJ_CPR, TRAJ_ROWS - 1);
+        my_row = (r < 3) ? A.traj_pos + (int64_t)r * A.traj_total : A.traj_vel + (int64_t)(r - 3) * A.traj_total;
         col0 = 0;
         n = 0;
         want = false;
@@ -79,6 +84,20 @@ struct TrajWriter {
         }
     }
 
+    // stage a sample that is known NOT to complete the window (the integrator bounds its runs so)
+    __device__ __forceinline__ void stage(int64_t col, double x, double y, double z, double vx, double vy, double vz)
+    {
+        const int slot = (int)(col & (TRAJ_S - 1));
+        if (n == 0) col0 = col;
+        buf[0 * TRAJ_S + slot] = x;
+        buf[1 * TRAJ_S + slot] = y;
+        buf[2 * TRAJ_S + slot] = z;
+        buf[3 * TRAJ_S + slot] = vx;
+        buf[4 * TRAJ_S + slot] = vy;
+        buf[5 * TRAJ_S + slot] = vz;
+        n++;
+    }
+
     // Warp-convergent: every lane of the warp must call this together.
     __device__ __forceinline__ void flush_warp()
     {
@@ -86,23 +105,41 @@ struct TrajWriter {
         if (m == 0) return;
         __syncwarp();                       // the staged samples / headers of the other lanes are visible
         const int lane = threadIdx.x & 31;
-        const int r = lane >> 2, c = lane & 3;
-        while (m) {
-            const int l = __ffs(m) - 1;
-            m &= m - 1;
-            const unsigned char *src = warp_base + (size_t)l * TRAJ_LANE_BYTES;
-            const TrajHeader h = *reinterpret_cast<const TrajHeader *>(src + TRAJ_DATA_BYTES);
-            if (lane < 4 * TRAJ_ROWS) {
-                if (h.n == TRAJ_S && wide_ok) {
-                    const double2 v = *reinterpret_cast<const double2 *>(src + r * (TRAJ_S * 8) + c * 16);
-                    *reinterpret_cast<double2 *>(my_row + h.col0 + 2 * c) = v;
-                } else {
-                    const int s0 = (int)(h.col0 & (TRAJ_S - 1));
-                    const double *rowbuf = reinterpret_cast<const double *>(src + r * (TRAJ_S * 8));
+        const int sub = lane / TRAJ_LPS;                       // which source lane of a store instruction
+        const int r = (lane % TRAJ_LPS) / TRAJ_CPR, c = lane % TRAJ_CPR;
+        const bool role = lane < TRAJ_SPI * TRAJ_LPS;
+        if (m == 0xffffffffu && wide_ok && __all_sync(0xffffffffu, n == TRAJ_S)) {
+            // lockstep case (equal-length orbits): all 32 windows are complete -- fully unrolled, every
+            // shared-memory offset an immediate: LDS.64 column, LDS.128 data, address, STG.128
+            if (role) {
+                const unsigned char *src = warp_base + sub * TRAJ_LANE_BYTES + r * (TRAJ_S * 8) + c * 16;
+                const unsigned char *hdr = warp_base + sub * TRAJ_LANE_BYTES + TRAJ_DATA_BYTES;
+                double *dst = my_row + 2 * c;
 #pragma unroll
-                    for (int q = 0; q < 2; q++) {
-                        const int e = 2 * c + q;
-                        if (e >= s0 && e < s0 + h.n) my_row[h.col0 - s0 + e] = rowbuf[e];
+                for (int l = 0; l < 32; l += TRAJ_SPI) {
+                    const long long c0 = *reinterpret_cast<const long long *>(hdr + l * TRAJ_LANE_BYTES);
+                    const double2 v = *reinterpret_cast<const double2 *>(src + l * TRAJ_LANE_BYTES);
+                    *reinterpret_cast<double2 *>(dst + c0) = v;
+                }
+            }
+        } else {
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const unsigned char *src = warp_base + (size_t)l * TRAJ_LANE_BYTES;
+                const TrajHeader h = *reinterpret_cast<const TrajHeader *>(src + TRAJ_DATA_BYTES);
+                if (role && sub == 0) {
+                    if (h.n == TRAJ_S && wide_ok) {
+                        const double2 v = *reinterpret_cast<const double2 *>(src + r * (TRAJ_S * 8) + c * 16);
+                        *reinterpret_cast<double2 *>(my_row + h.col0 + 2 * c) = v;
+                    } else {
+                        const int s0 = (int)(h.col0 & (TRAJ_S - 1));
+                        const double *rowbuf = reinterpret_cast<const double *>(src + r * (TRAJ_S * 8));
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            const int e = 2 * c + q;
+                            if (e >= s0 && e < s0 + h.n) my_row[h.col0 - s0 + e] = rowbuf[e];
+                        }
                     }
                 }
             }

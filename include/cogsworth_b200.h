@@ -177,8 +177,14 @@ double cw_last_total_kernel_ms(const cw_ctx *ctx, int dev);
 /* DFMA micro-benchmark on device slot `dev`: returns sustained FP64 TFLOP/s (2 flop per FMA) over
  * about `ms_target` milliseconds -- the roofline denominator for this path. */
 double cw_measure_fp64_peak(cw_ctx *ctx, int dev, double ms_target);
+/* Scatter-write micro-benchmark = the HBM access pattern of store_all without the arithmetic: `streams`
+ * far-apart sequential streams of `stream_bytes`, appended `run_bytes` (16..512) at a time in lock-step by
+ * `resident_threads_per_sm` threads per SM.  Returns GB/s written (the pattern's ceiling). */
+double cw_measure_scatter_write(cw_ctx *ctx, int dev, int64_t streams, int64_t stream_bytes, int run_bytes,
+                                int resident_threads_per_sm);
 /* max relative error of the kernels' own rsqrt / reciprocal / log (table-free) / log (table)
- * against the CUDA math library over n samples; out[4] */
+ * against the CUDA math library over n samples (out[0..3]), then the dependent-issue latency in cycles of
+ * DFMA, rsqrt_fast + DADD and DMUL measured by one warp alone (out[4..6]); out[7] */
 int cw_selftest_math(cw_ctx *ctx, int64_t n, double *out);
 
 #ifdef __cplusplus
