@@ -222,19 +222,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from cogsworth_b200 import dist as cwdist
+
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return cwdist.reduce_scalar(x, "max", device=dev)
 
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return cwdist.reduce_scalar(x, "sum", device=dev)
 
     pop = build_shard(wl, rank, world, args.scaling, args.scale)
     b = pop.batch
