@@ -13,7 +13,8 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcogsworth_b200.so")
+# COGSWORTH_B200_LIB selects another build of the same ABI (A/B experiments); default = the in-tree build
+LIB_PATH = os.environ.get("COGSWORTH_B200_LIB") or os.path.join(_HERE, "libcogsworth_b200.so")
 
 LEAPFROG, DOP853 = 0, 1
 GRID_APPEND_T2 = 1

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["cw_api.cu", "cw_leapfrog.cu", "cw_dop853.cu", "cw_diag.cu"]
 HEADERS = ["cw_device.cuh", "cw_kernels.cuh", "../../include/cogsworth_b200.h", "../../include/cw_dop853_coeffs.h"]
-OUT = os.path.join(HERE, "libcogsworth_b200.so")
+OUT = os.environ.get("CW_BUILD_OUT") or os.path.join(HERE, "libcogsworth_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -33,8 +33,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return OUT
     extra = []
-    if os.environ.get("CW_TRAJ_S"):          # experiment knob: staging window of the trajectory writer
-        extra.append("-DCW_TRAJ_S=" + os.environ["CW_TRAJ_S"])
+    for knob in ("CW_TRAJ_S", "CW_LF_MINB"):      # experiment knobs (see cw_traj.cuh / cw_leapfrog.cu)
+        if os.environ.get(knob):
+            extra.append(f"-D{knob}=" + os.environ[knob])
     cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
     env = dict(os.environ)
     env.pop("CC", None)      # the image exports a CC without libgomp specs; nvcc wants the system g++

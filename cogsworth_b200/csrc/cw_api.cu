@@ -236,6 +236,7 @@ extern "C" int cw_set_potential(cw_ctx *ctx, double G, int n_comp, const int32_t
             P.nfw_inv_rs = 1.0 / P.nfw_rs;
         }
     }
+    pot_fill_constants(P);
     ctx->pot = P;
     ctx->has_pot = true;
     return CW_OK;

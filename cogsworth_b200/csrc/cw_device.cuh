@@ -69,44 +69,6 @@ __device__ __forceinline__ double log_fast(double x)
     return fma(kd, LN2_HI, fma(kd, LN2_LO, r));
 }
 
-// Table-driven ln(x), x >= 1 (Tang-style): x = 2^k m, m in [1,2); c_j = 1 + j/128 is the table node
-// nearest to m (j = 0..128), r = m/c_j - 1 (one FMA with the tabulated 1/c_j, |r| <= 2^-8) and
-// ln m = ln c_j + log1p(r), log1p by its degree-7 Taylor polynomial (remainder < 2^-67).
-// The 129 x {1/c_j, -ln(1/c_j)} table (2 KB) sits in shared memory and is filled once per CTA by
-// log_table_init; the look-up is one LDS.128 on the otherwise idle LSU pipe.  1 DADD for k plus
-// 11 FP64-pipe instructions, no MUFU: 7 fewer FP64 instructions than log_fast.
-constexpr int LOG_TABLE_N = 129;
-
-__device__ __forceinline__ void log_table_init(double2 *tab)
-{
-    for (int j = threadIdx.x; j < LOG_TABLE_N; j += blockDim.x) {
-        const double invc = 1.0 / (1.0 + (double)j * 0.0078125);
-        tab[j] = make_double2(invc, -log(invc));      // ln of the c actually used (1/invc)
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ double log_tab(double x, const double2 *__restrict__ tab)
-{
-    const int hi = __double2hiint(x);
-    const int lo = __double2loint(x);
-    const int k = (hi >> 20) - 1023;
-    const int j = (((hi >> 12) & 0xff) + 1) >> 1;                    // nearest of 128 mantissa nodes
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    const double kd = __hiloint2double(0x43300000, k ^ 0x80000000) - 4503601774854144.0; // 2^52 + 2^31
-    const double2 t = tab[j];
-    const double r = fma(m, t.x, -1.0);
-    double q = 1.0 / 7.0;
-    q = fma(q, r, -1.0 / 6.0);
-    q = fma(q, r, 0.2);
-    q = fma(q, r, -0.25);
-    q = fma(q, r, 1.0 / 3.0);
-    q = fma(q, r, -0.5);
-    const double lp = fma(r * r, q, r);                              // log1p(r)
-    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
-    return fma(kd, LN2_HI, t.y + fma(kd, LN2_LO, lp));
-}
-
 // ------------------------------------------------------------------------------------------
 // Potential parameter block.  Passed by value as a __grid_constant__ kernel parameter, i.e. it
 // lives in the constant bank (c[0x0][...]) and every access is a uniform broadcast -- the
@@ -131,7 +93,59 @@ struct PotParams {
     double mn_GM[3], mn_a[3], mn_b2[3];
     double h_GM[2], h_c[2];
     double nfw_GM, nfw_rs, nfw_inv_rs;
+    // Full 64-bit numeric constants of log_tab.  As kernel parameters they are constant-bank operands
+    // of the DFMA that uses them; as literals ptxas rebuilds each with two UMOVs inside the hot loop,
+    // and on sm_100 every non-FP64 instruction costs half an FP64 issue slot (an FP64 warp instruction
+    // holds the dispatch port for 2 cycles; measured, tools/exp/pipe_mix2.cu).
+    double k_ln2_hi, k_ln2_lo, k_2p52, k_c7, k_c6, k_c5, k_c3;
 };
+
+__host__ __device__ inline void pot_fill_constants(PotParams &P)
+{
+    P.k_ln2_hi = 6.93147180369123816490e-01;
+    P.k_ln2_lo = 1.90821492927058770002e-10;
+    P.k_2p52 = 4503601774854144.0;      // 2^52 + 2^31
+    P.k_c7 = 1.0 / 7.0;
+    P.k_c6 = -1.0 / 6.0;
+    P.k_c5 = 0.2;
+    P.k_c3 = 1.0 / 3.0;
+}
+
+// Table-driven ln(x), x >= 1 (Tang-style): x = 2^k m, m in [1,2); c_j = 1 + j/128 is the table node
+// nearest to m (j = 0..128), r = m/c_j - 1 (one FMA with the tabulated 1/c_j, |r| <= 2^-8) and
+// ln m = ln c_j + log1p(r), log1p by its degree-7 Taylor polynomial (remainder < 2^-67).
+// The 129 x {1/c_j, -ln(1/c_j)} table (2 KB) sits in shared memory and is filled once per CTA by
+// log_table_init; the look-up is one LDS.128 on the otherwise idle LSU pipe.  1 DADD for k plus
+// 11 FP64-pipe instructions, no MUFU: 7 fewer FP64 instructions than log_fast.
+constexpr int LOG_TABLE_N = 129;
+
+__device__ __forceinline__ void log_table_init(double2 *tab)
+{
+    for (int j = threadIdx.x; j < LOG_TABLE_N; j += blockDim.x) {
+        const double invc = 1.0 / (1.0 + (double)j * 0.0078125);
+        tab[j] = make_double2(invc, -log(invc));      // ln of the c actually used (1/invc)
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double log_tab(const PotParams &P, double x, const double2 *__restrict__ tab)
+{
+    const int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    const int k = (hi >> 20) - 1023;
+    const int j = (((hi >> 12) & 0xff) + 1) >> 1;                    // nearest of 128 mantissa nodes
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double kd = __hiloint2double(0x43300000, k ^ 0x80000000) - P.k_2p52;
+    const double2 t = tab[j];
+    const double r = fma(m, t.x, -1.0);
+    double q = fma(P.k_c7, r, P.k_c6);
+    q = fma(q, r, P.k_c5);
+    q = fma(q, r, -0.25);
+    q = fma(q, r, P.k_c3);
+    q = fma(q, r, -0.5);
+    const double lp = fma(r * r, q, r);                              // log1p(r)
+    return fma(kd, P.k_ln2_hi, t.y + fma(kd, P.k_ln2_lo, lp));
+}
 
 // Specialised composite: NMN Miyamoto-Nagai terms (+ optionally one shared b), two Hernquist
 // spheres and one spherical NFW halo.  FP64-pipe instruction budget (v2): ~105 per gradient.
@@ -139,9 +153,8 @@ struct PotParams {
 //   Hernquist:   f = GM / ((r+c)^2 r);                                    g += f q
 //   NFW:         f = GM (ln(1+r/rs) - r/(r+rs)) / r^3;                    g += f q
 template <int NMN, bool SHARED_B>
-__device__ __forceinline__ void gradient_mw(const PotParams &P, const double2 *__restrict__ ltab,
-                                            double x, double y, double z,
-                                            double &gx, double &gy, double &gz)
+__device__ __forceinline__ void force_mw(const PotParams &P, const double2 *__restrict__ ltab,
+                                         double x, double y, double z, double &Fxy, double &Fz)
 {
     const double R2 = fma(y, y, x * x);
     const double z2 = z * z;
@@ -185,21 +198,19 @@ __device__ __forceinline__ void gradient_mw(const PotParams &P, const double2 *_
     // NFW
     const double u = r * P.nfw_inv_rs;
     const double w = 1.0 + u;
-    const double lw = ltab ? log_tab(w, ltab) : log_fast(w);
+    const double lw = ltab ? log_tab(P, w, ltab) : log_fast(w);
     const double bracket = lw - u * rcp_fast(w);
     const double ir3 = (ir * ir) * ir;
     double fs = h * ir;
     fs = fma(P.nfw_GM * ir3, bracket, fs);
 
-    gx = (fxy + fs) * x;
-    gy = (fxy + fs) * y;
-    gz = (fz + fs) * z;
+    Fxy = fxy + fs;     // grad = (Fxy x, Fxy y, Fz z)
+    Fz = fz + fs;
 }
 
 // Generic composite: components in the caller's order.
-__device__ __forceinline__ void gradient_generic(const PotParams &P, const double2 *__restrict__ ltab,
-                                                 double x, double y, double z,
-                                                 double &gx, double &gy, double &gz)
+__device__ __forceinline__ void force_generic(const PotParams &P, const double2 *__restrict__ ltab,
+                                              double x, double y, double z, double &Fxy, double &Fz)
 {
     const double R2 = fma(y, y, x * x);
     const double z2 = z * z;
@@ -230,27 +241,38 @@ __device__ __forceinline__ void gradient_generic(const PotParams &P, const doubl
             } else { // CW_COMP_NFW_SPHERICAL
                 const double u = r * P.p2[i];               // p2 = 1/r_s for NFW
                 const double w = 1.0 + u;
-                const double bracket = (ltab ? log_tab(w, ltab) : log_fast(w)) - u * rcp_fast(w);
+                const double bracket = (ltab ? log_tab(P, w, ltab) : log_fast(w)) - u * rcp_fast(w);
                 f = P.GM[i] * ((ir * ir) * ir) * bracket;
             }
             fxy += f;
             fz += f;
         }
     }
-    gx = fxy * x;
-    gy = fxy * y;
-    gz = fz * z;
+    Fxy = fxy;
+    Fz = fz;
 }
 
 // ltab: the CTA's shared-memory log table (log_table_init), or nullptr to use the table-free log.
+// force<KIND> returns the two scalar factors of the axisymmetric composite: grad = (Fxy x, Fxy y, Fz z).
+template <int KIND>
+__device__ __forceinline__ void force(const PotParams &P, const double2 *__restrict__ ltab,
+                                      double x, double y, double z, double &Fxy, double &Fz)
+{
+    if (KIND == POT_MW_V1) force_mw<1, false>(P, ltab, x, y, z, Fxy, Fz);
+    else if (KIND == POT_MW_V2) force_mw<3, true>(P, ltab, x, y, z, Fxy, Fz);
+    else force_generic(P, ltab, x, y, z, Fxy, Fz);
+}
+
 template <int KIND>
 __device__ __forceinline__ void gradient(const PotParams &P, const double2 *__restrict__ ltab,
                                          double x, double y, double z,
                                          double &gx, double &gy, double &gz)
 {
-    if (KIND == POT_MW_V1) gradient_mw<1, false>(P, ltab, x, y, z, gx, gy, gz);
-    else if (KIND == POT_MW_V2) gradient_mw<3, true>(P, ltab, x, y, z, gx, gy, gz);
-    else gradient_generic(P, ltab, x, y, z, gx, gy, gz);
+    double Fxy, Fz;
+    force<KIND>(P, ltab, x, y, z, Fxy, Fz);
+    gx = Fxy * x;
+    gy = Fxy * y;
+    gz = Fz * z;
 }
 
 // dt of a segment = t[1] - t[0] with both nodes converted to Myr first (gala converts the whole

@@ -147,11 +147,15 @@ cudaError_t launch_traj_times(const IntegArgs &A, const LaunchCfg &cfg)
 // Leapfrog
 // ------------------------------------------------------------------------------------------
 constexpr int LF_BLOCK = 256;
+// resident CTAs per SM the final-state kernel is compiled for (register budget = 65536 / (256 * N))
+#ifndef CW_LF_MINB
+#define CW_LF_MINB 4
+#endif
 
 struct Lane {
     double x, y, z, vx, vy, vz;     // state at node j (v synchronised only at sync nodes)
     double vhx, vhy, vhz;           // half-step velocity
-    double gx, gy, gz;              // gradient at node j
+    double Fxy, Fz;                 // force factors at node j: grad = (Fxy x, Fxy y, Fz z)
     double dt;                      // leapfrog dt of the current segment (Myr)
     double hgrid, t2, smyr;         // grid step, end time (grid unit), grid unit -> Myr
     double tcur;                    // STORE only: grid time of node j
@@ -202,7 +206,7 @@ __device__ __forceinline__ void write_final(const IntegArgs &A, const Lane &s)
 }
 
 template <int KIND, bool STORE>
-__global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constant__ PotParams P,
+__global__ void __launch_bounds__(LF_BLOCK, STORE ? 2 : CW_LF_MINB) leapfrog_kernel(const __grid_constant__ PotParams P,
                                                             const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
     int64_t col_base = 0;          // STORE: column of sample 0 of the current orbit
     Lane s;
     s.x = 8.0; s.y = 0.0; s.z = 0.0; s.vx = s.vy = s.vz = 0.0;
-    s.vhx = s.vhy = s.vhz = 0.0; s.gx = s.gy = s.gz = 0.0;
+    s.vhx = s.vhy = s.vhz = 0.0; s.Fxy = s.Fz = 0.0;
     s.dt = 0.0; s.hgrid = 0.0; s.t2 = 0.0; s.smyr = 1.0; s.tcur = 0.0;
     s.e = s.e1 = 0; s.oid = -1; s.j = 0; s.next = 0; s.L = 0; s.append = false;
     bool active = false, exhausted = false, staged = false;
@@ -245,11 +249,11 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
                     write_final(A, s);
                     active = false;
                 } else {
-                    if (kicked) { // c_init_velocity of the new segment; gradient at this node is already known
-                        const double hdt = s.dt * 0.5;
-                        s.vhx = fma(-s.gx, hdt, s.vx);
-                        s.vhy = fma(-s.gy, hdt, s.vy);
-                        s.vhz = fma(-s.gz, hdt, s.vz);
+                    if (kicked) { // c_init_velocity of the new segment; the force at this node is already known
+                        const double nhdt = -0.5 * s.dt;
+                        s.vhx = fma(s.Fxy * nhdt, s.x, s.vx);
+                        s.vhy = fma(s.Fxy * nhdt, s.y, s.vy);
+                        s.vhz = fma(s.Fz * nhdt, s.z, s.vz);
                     }
                     s.next = (s.e < s.e1) ? A.ev_step[s.e] : s.L;
                 }
@@ -289,11 +293,11 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
                 staged = true;
             }
             if (s.L == 0) { write_final(A, s); continue; }
-            gradient<KIND>(P, ltab, s.x, s.y, s.z, s.gx, s.gy, s.gz);
-            const double hdt = s.dt * 0.5;
-            s.vhx = fma(-s.gx, hdt, s.vx);
-            s.vhy = fma(-s.gy, hdt, s.vy);
-            s.vhz = fma(-s.gz, hdt, s.vz);
+            force<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fz);
+            const double nhdt = -0.5 * s.dt;
+            s.vhx = fma(s.Fxy * nhdt, s.x, s.vx);
+            s.vhy = fma(s.Fxy * nhdt, s.y, s.vy);
+            s.vhz = fma(s.Fz * nhdt, s.z, s.vz);
             s.next = (s.e < s.e1) ? A.ev_step[s.e] : s.L;
             active = true;
         }
@@ -309,30 +313,36 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
             r = min(r, ((TRAJ_S - 2 - c7) & (TRAJ_S - 1)) + 1);
         }
         const int m = __reduce_min_sync(FULL, r);
-        const double dt = s.dt;
+        // One formula for every step of both modes (so a final-state run equals the last sample of a
+        // store_all run bit for bit):  x += vh dt;  F = force(x);  v = vh - grad dt/2;  vh -= grad dt,
+        // with grad = (Fxy x, Fxy y, Fz z) folded into the FMAs: vh = fma(Fxy * (-dt), x, vh).
+        const double dt = s.dt, ndt = -s.dt, nhdt = -0.5 * s.dt;
         if (!STORE) {
+#pragma unroll 2
             for (int q = 1; q < m; q++) {   // c_leapfrog_step without the synchronised velocity
                 s.x = fma(s.vhx, dt, s.x);
                 s.y = fma(s.vhy, dt, s.y);
                 s.z = fma(s.vhz, dt, s.z);
-                gradient<KIND>(P, ltab, s.x, s.y, s.z, s.gx, s.gy, s.gz);
-                s.vhx = fma(-s.gx, dt, s.vhx);
-                s.vhy = fma(-s.gy, dt, s.vhy);
-                s.vhz = fma(-s.gz, dt, s.vhz);
+                force<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fz);
+                const double a = s.Fxy * ndt, b = s.Fz * ndt;
+                s.vhx = fma(a, s.x, s.vhx);
+                s.vhy = fma(a, s.y, s.vhy);
+                s.vhz = fma(b, s.z, s.vhz);
             }
         } else {
-            const double hdt = dt * 0.5;
             for (int q = 1; q < m; q++) {   // full steps, every sample staged
                 s.x = fma(s.vhx, dt, s.x);
                 s.y = fma(s.vhy, dt, s.y);
                 s.z = fma(s.vhz, dt, s.z);
-                gradient<KIND>(P, ltab, s.x, s.y, s.z, s.gx, s.gy, s.gz);
-                s.vx = fma(-s.gx, hdt, s.vhx);
-                s.vy = fma(-s.gy, hdt, s.vhy);
-                s.vz = fma(-s.gz, hdt, s.vhz);
-                s.vhx = fma(-s.gx, dt, s.vhx);
-                s.vhy = fma(-s.gy, dt, s.vhy);
-                s.vhz = fma(-s.gz, dt, s.vhz);
+                force<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fz);
+                const double ah = s.Fxy * nhdt, bh = s.Fz * nhdt;
+                s.vx = fma(ah, s.x, s.vhx);
+                s.vy = fma(ah, s.y, s.vhy);
+                s.vz = fma(bh, s.z, s.vhz);
+                const double a = s.Fxy * ndt, b = s.Fz * ndt;
+                s.vhx = fma(a, s.x, s.vhx);
+                s.vhy = fma(a, s.y, s.vhy);
+                s.vhz = fma(b, s.z, s.vhz);
                 if (active) tw.stage(col_base + s.j + q, s.x, s.y, s.z, s.vx, s.vy, s.vz);
             }
         }
@@ -340,14 +350,15 @@ __global__ void __launch_bounds__(LF_BLOCK) leapfrog_kernel(const __grid_constan
             s.x = fma(s.vhx, dt, s.x);
             s.y = fma(s.vhy, dt, s.y);
             s.z = fma(s.vhz, dt, s.z);
-            gradient<KIND>(P, ltab, s.x, s.y, s.z, s.gx, s.gy, s.gz);
-            const double hdt = dt * 0.5;
-            s.vx = fma(-s.gx, hdt, s.vhx);
-            s.vy = fma(-s.gy, hdt, s.vhy);
-            s.vz = fma(-s.gz, hdt, s.vhz);
-            s.vhx = fma(-s.gx, dt, s.vhx);
-            s.vhy = fma(-s.gy, dt, s.vhy);
-            s.vhz = fma(-s.gz, dt, s.vhz);
+            force<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fz);
+            const double ah = s.Fxy * nhdt, bh = s.Fz * nhdt;
+            s.vx = fma(ah, s.x, s.vhx);
+            s.vy = fma(ah, s.y, s.vhy);
+            s.vz = fma(bh, s.z, s.vhz);
+            const double a = s.Fxy * ndt, b = s.Fz * ndt;
+            s.vhx = fma(a, s.x, s.vhx);
+            s.vhy = fma(a, s.y, s.vhy);
+            s.vhz = fma(b, s.z, s.vhz);
         }
         staged = false;
         if (active) {
