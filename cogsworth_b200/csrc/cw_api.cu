@@ -264,9 +264,16 @@ size_t sort_temp_bytes(int64_t m)
 }
 
 constexpr int64_t SORT_THRESHOLD = 4096;
-// Host-buffer calls are cut into chunks of this many orbits that rotate over N_LANES streams, so the
-// H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap the kernels of chunk c.
-constexpr int64_t HOST_CHUNK = 1 << 20;
+// Host-buffer calls are cut into chunks that rotate over N_LANES streams, so the H2D copy of chunk c+1
+// and the D2H copy of chunk c-1 overlap the kernels of chunk c: about 8 chunks per device, between
+// 2^16 orbits (below that launch overheads show) and 2^20 (bounds the exposed first copy).
+constexpr int64_t HOST_CHUNK_MAX = 1 << 20, HOST_CHUNK_MIN = 1 << 16;
+static int64_t host_chunk(int64_t n_on_device)
+{
+    int64_t c = (n_on_device + 7) / 8;
+    c = (c + 4095) & ~int64_t(4095);
+    return std::min(HOST_CHUNK_MAX, std::max(HOST_CHUNK_MIN, c));
+}
 
 struct Plan {
     IntegArgs A;
@@ -474,7 +481,7 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
     std::vector<Shard> shards;
     for (int d = 0; d < nslots; d++) {
         const int64_t a = n * d / nslots, b = n * (d + 1) / nslots;
-        const int64_t chunk = dev_mode ? (b - a) : HOST_CHUNK;
+        const int64_t chunk = dev_mode ? (b - a) : host_chunk(b - a);
         int lane = 0;
         for (int64_t c = a; c < b; c += chunk) {
             Shard sh;

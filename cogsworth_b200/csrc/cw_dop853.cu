@@ -17,6 +17,14 @@
 // The first stage of every interval, k1 = f(t_j, y_j), is bit-identical to the derivative Hairer
 // evaluates at the end of the previous accepted step (same y), so it is carried over instead of
 // being recomputed: 12 gradient evaluations per accepted step instead of gala's 13.
+//
+// Stage algebra is kept in Hairer's first-order form (10 x 6 stage doubles, ~220 registers, 8 warps
+// per SM) on purpose.  A Nystrom (second-order) folding that stores only the 3-vector accelerations
+// was built and measured in round 1: 168 registers and 12 warps per SM, parity green, but 10-25 %
+// SLOWER on every DOPRI853 workload.  These runs are bound by the single most expensive orbit
+// (sequential by nature: 10^5 step attempts for a star orbiting inside 50 pc), i.e. by the latency
+// of ONE lane, and six independent component chains per stage give that lane twice the
+// instruction-level parallelism of three.
 #include <cooperative_groups.h>
 #include <climits>
 #include "cw_kernels.cuh"
