@@ -49,6 +49,8 @@ WORKLOADS = {
                            f_sn=1.0, desc="1e5 binaries, Wagg2022 horizons, MilkyWayPotential2022, DOPRI853 1e-10, kicks"),
     "config3": dict(cfg_id=3, n_orbits=1_000_000, horizon_gyr=1.0, integrator="leapfrog", store_all=True,
                     f_sn=0.0, desc="1e6 orbits x 1000 stored steps (48 GB), MilkyWayPotential2022, leapfrog, no kicks"),
+    "config3k": dict(cfg_id=3, n_orbits=1_000_000, horizon_gyr=1.0, integrator="leapfrog", store_all=True,
+                     f_sn=1.0, desc="1e6 orbits x 1001 stored steps (48 GB), MilkyWayPotential2022, leapfrog, kicks on"),
     "config5": dict(cfg_id=5, n_orbits=1_000_000, horizon_gyr=1.0, integrator="dop853", store_all=False,
                     f_sn=1.0, plunging_fraction=0.01, rtol=1e-8, atol=1e-8,
                     desc="1e6 orbits DOPRI853 rtol=atol=1e-8, 1 Gyr, kicks, 1% plunging"),

@@ -698,8 +698,8 @@ extern "C" double cw_measure_fp64_peak(cw_ctx *ctx, int dev, double ms_target)
 extern "C" double cw_measure_scatter_write(cw_ctx *ctx, int dev, int64_t streams, int64_t stream_bytes, int run_bytes,
                                            int resident_threads_per_sm)
 {
-    if (!ctx || dev < 0 || dev >= (int)ctx->slots.size() || run_bytes < 16 || run_bytes > 512 || (run_bytes & 15) ||
-        stream_bytes % run_bytes)
+    const int rb = run_bytes < 0 ? -run_bytes : run_bytes;      // negative: with L2 eviction-priority hints
+    if (!ctx || dev < 0 || dev >= (int)ctx->slots.size() || rb < 16 || rb > 512 || (rb & 15) || stream_bytes % rb)
         return -1.0;
     Slot &s = ctx->slots[dev];
     int prev = 0;

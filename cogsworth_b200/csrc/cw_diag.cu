@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256) math_selftest_kernel(int64_t n, double *o
 // independent sequential streams (one per orbit coordinate), each `stream_bytes` long and far apart;
 // every visit appends one run of `run_bytes` (16-byte chunks by run_bytes/16 adjacent lanes, one
 // STG.128 per lane), all streams advance in lock-step.  Gives the ceiling of the access pattern.
+template <int HINT>
 __global__ void __launch_bounds__(256) scatter_write_kernel(double2 *base, long long streams, long long stream_bytes,
                                                             int run_bytes)
 {
@@ -122,17 +123,33 @@ __global__ void __launch_bounds__(256) scatter_write_kernel(double2 *base, long 
     const int c = threadIdx.x % g;
     const long long visits = stream_bytes / run_bytes;
     const double2 v = make_double2((double)gw, (double)c);
-    for (long long s0 = gw; s0 < streams; s0 += nslots) {
-        // this slot owns stream s0 (streams beyond the resident set are taken in later passes)
-        double2 *p = base + (s0 * stream_bytes) / 16 + c;
-        for (long long k = 0; k < visits; k++) p[k * g] = v;
+    unsigned long long pol_keep = 0, pol_drop = 0;
+    if (HINT) {
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_drop));
     }
+    // visit-major order: every stream receives its k-th run before any stream receives its (k+1)-th,
+    // exactly like orbits advancing in lock-step (consecutive runs of one stream are a whole sweep apart)
+    for (long long k = 0; k < visits; k++)
+        for (long long s0 = gw; s0 < streams; s0 += nslots) {
+            double2 *p = base + (s0 * stream_bytes) / 16 + k * g + c;
+            if (HINT) {
+                // first run of a 128-byte line: keep it in L2 until the second run completes the line
+                const bool first_half = (((reinterpret_cast<uintptr_t>(p) / run_bytes) & 1) == 0) && run_bytes == 64;
+                const unsigned long long pol = first_half ? pol_keep : pol_drop;
+                asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol)
+                             : "memory");
+            } else {
+                *p = v;
+            }
+        }
 }
 
 cudaError_t launch_scatter_write(double2 *base, long long streams, long long stream_bytes, int run_bytes,
                                  int blocks, const LaunchCfg &cfg)
 {
-    scatter_write_kernel<<<blocks, 256, 0, cfg.stream>>>(base, streams, stream_bytes, run_bytes);
+    if (run_bytes < 0) scatter_write_kernel<1><<<blocks, 256, 0, cfg.stream>>>(base, streams, stream_bytes, -run_bytes);
+    else scatter_write_kernel<0><<<blocks, 256, 0, cfg.stream>>>(base, streams, stream_bytes, run_bytes);
     return cudaGetLastError();
 }
 

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
                 dp_begin_interval(s);
             }
         }
-        if (STORE && !PILOT) tw.flush_warp();
+        if (STORE && !PILOT) tw.flush_warp(A);
         // ---- phase B: idle lanes pull the next orbit
         while (!active && !exhausted) {
             const int64_t p = dp_queue_pop(A.queue);
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
             dp_begin_interval(s);
             active = true;
         }
-        if (STORE && !PILOT) tw.flush_warp();
+        if (STORE && !PILOT) tw.flush_warp(A);
         if (!__any_sync(FULL, active)) break;   // warp-level early exit
 
         // ---- phase C: one step attempt of dopcor() for every lane that has an open interval

@@ -146,7 +146,10 @@ cudaError_t launch_traj_times(const IntegArgs &A, const LaunchCfg &cfg)
 // ------------------------------------------------------------------------------------------
 // Leapfrog
 // ------------------------------------------------------------------------------------------
-constexpr int LF_BLOCK = 256;
+constexpr int LF_BLOCK = 256;        // final-state kernel: 4 CTAs x 256 threads per SM (64 registers)
+// store_all kernel: the staging windows cap the orbits in flight; 3 CTAs x 192 threads x 392 B fill the
+// 228 KB of shared memory (18 warps per SM), which is why this variant uses the table-free logarithm.
+constexpr int LF_BLOCK_STORE = 192;
 // resident CTAs per SM the final-state kernel is compiled for (register budget = 65536 / (256 * N))
 #ifndef CW_LF_MINB
 #define CW_LF_MINB 4
@@ -206,13 +209,14 @@ __device__ __forceinline__ void write_final(const IntegArgs &A, const Lane &s)
 }
 
 template <int KIND, bool STORE>
-__global__ void __launch_bounds__(LF_BLOCK, STORE ? 2 : CW_LF_MINB) leapfrog_kernel(const __grid_constant__ PotParams P,
+__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK, STORE ? 3 : CW_LF_MINB) leapfrog_kernel(const __grid_constant__ PotParams P,
                                                             const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
-    __shared__ double2 ltab[LOG_TABLE_N];
+    __shared__ double2 ltab_s[STORE ? 1 : LOG_TABLE_N];
     extern __shared__ __align__(16) unsigned char traj_smem[];
-    log_table_init(ltab);
+    const double2 *ltab = STORE ? nullptr : ltab_s;
+    if (!STORE) log_table_init(ltab_s);
     TrajWriter tw;
     if (STORE) tw.init(traj_smem, A);
     int64_t col_base = 0;          // STORE: column of sample 0 of the current orbit
@@ -223,15 +227,15 @@ __global__ void __launch_bounds__(LF_BLOCK, STORE ? 2 : CW_LF_MINB) leapfrog_ker
     s.e = s.e1 = 0; s.oid = -1; s.j = 0; s.next = 0; s.L = 0; s.append = false;
     bool active = false, exhausted = false, staged = false;
     unsigned long long steps_done = 0;
-    if (STORE) {
-        // De-phase the warps.  With equal-length orbits every warp of the GPU would complete its staging
-        // windows on the same step and the whole chip would alternate between an FP64-only phase and a
-        // store burst that overruns the LSU queues (ncu: 28 % of warp time stalled in the flush).  One
-        // step takes about a microsecond per warp at this occupancy; spreading the start of the warps
-        // over one window period lets the stores of one warp overlap the arithmetic of the others.
-        const unsigned gw = (blockIdx.x * (LF_BLOCK / 32) + (threadIdx.x >> 5));
-        __nanosleep((gw % TRAJ_S) * 1000u);
-    }
+    // De-phasing of the store bursts (STORE only).  With equal-length orbits every warp of the GPU
+    // completes its staging windows on the same step, so the whole chip alternates between an FP64-only
+    // phase (HBM idle) and a store burst (FP64 idle): measured 8.3 ms of arithmetic + 6.3 ms of stores
+    // per 10^9 samples, strictly serialised.  Each warp therefore times its own first window period and
+    // then waits once for (warp id mod 8) / 8 of it: from then on one eighth of the warps is flushing at
+    // any moment while the others compute, and since all warps advance at the same rate the offsets stay.
+    const unsigned gw = STORE ? (blockIdx.x * (LF_BLOCK_STORE / 32) + (threadIdx.x >> 5)) : 0u;
+    long long t_first = STORE ? clock64() : 0;
+    int dephase = STORE ? 2 : 0;       // 2: first flush not seen yet, 1: second flush pending, 0: done
 
     for (;;) {
         // ---- phase A: lanes standing on a sync node (kick node / last node).  When STORE, the sample of
@@ -259,7 +263,20 @@ __global__ void __launch_bounds__(LF_BLOCK, STORE ? 2 : CW_LF_MINB) leapfrog_ker
                 }
             }
         }
-        if (STORE) tw.flush_warp();   // windows completed on this node (incl. the last one of an orbit)
+        if (STORE) {
+            const bool flushed = tw.flush_warp(A);   // windows completed on this node (incl. the last of an orbit)
+            if (dephase && flushed) {
+                const long long now = clock64();
+                if (dephase == 2) {
+                    t_first = now;                   // start of the first full window period
+                    dephase = 1;
+                } else {
+                    const long long wait = (now - t_first) * (long long)(gw % TRAJ_S) / TRAJ_S;
+                    while (clock64() - now < wait) { }
+                    dephase = 0;
+                }
+            }
+        }
         // ---- phase B: idle lanes pull the next orbit from the queue
         while (!active && !exhausted) {
             const int64_t p = queue_pop(A.queue);
@@ -301,7 +318,7 @@ __global__ void __launch_bounds__(LF_BLOCK, STORE ? 2 : CW_LF_MINB) leapfrog_ker
             s.next = (s.e < s.e1) ? A.ev_step[s.e] : s.L;
             active = true;
         }
-        if (STORE) tw.flush_warp();   // a first sample can complete a window (column = 7 mod 8)
+        if (STORE) tw.flush_warp(A);   // a first sample can complete a window (column = 7 mod 8)
         if (!__any_sync(FULL, active)) break;
 
         // ---- phase C: a warp-uniform run of steps up to the nearest sync node of any lane
@@ -377,20 +394,21 @@ template <int KIND, bool STORE>
 static cudaError_t launch_lf(const PotParams &P, const IntegArgs &A, const LaunchCfg &cfg)
 {
     int per_sm = 0;
-    const size_t dyn = STORE ? (size_t)LF_BLOCK * TRAJ_LANE_BYTES : 0;
+    const int block = STORE ? LF_BLOCK_STORE : LF_BLOCK;
+    const size_t dyn = STORE ? (size_t)block * TRAJ_LANE_BYTES : 0;
     cudaError_t err = cudaSuccess;
     if (STORE) {
         err = cudaFuncSetAttribute(leapfrog_kernel<KIND, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (err != cudaSuccess) return err;
     }
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, leapfrog_kernel<KIND, STORE>, LF_BLOCK, dyn);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, leapfrog_kernel<KIND, STORE>, block, dyn);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)cfg.sm_count * per_sm;
-    const int64_t need = (A.n + LF_BLOCK - 1) / LF_BLOCK;
+    const int64_t need = (A.n + block - 1) / block;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    leapfrog_kernel<KIND, STORE><<<(unsigned)grid, LF_BLOCK, dyn, cfg.stream>>>(P, A);
+    leapfrog_kernel<KIND, STORE><<<(unsigned)grid, block, dyn, cfg.stream>>>(P, A);
     return cudaGetLastError();
 }
 

@@ -8,9 +8,9 @@
 // samples of its six coordinates in its own shared-memory rows.  Windows are aligned to ABSOLUTE
 // columns (slot = column & 7), so a complete window is six 64-byte, 64-byte-aligned runs whatever the
 // orbit's offset.  At the two warp-convergent points of the integrator loop the warp votes which lanes
-// completed a window and writes each of them cooperatively: 24 lanes x LDS.128 -> STG.128 = the six
-// runs of one lane in ONE store instruction (12 full sectors, no partial-sector traffic).  The ragged
-// first / last window of an orbit goes out as predicated 8-byte stores.
+// completed a window and writes them cooperatively: 8 adjacent lanes move one 64-byte run (LDS.64 ->
+// STG.64), so every store instruction writes four full runs = eight full sectors, no partial-sector
+// traffic.  The ragged first / last window of an orbit goes out through the same path, predicated.
 //
 // (Round-1 note: the first version issued per-lane cp.async.bulk (TMA) stores.  UBLKCP is a
 // uniform-datapath instruction, so ptxas serialised the 32 lanes with an R2UR/PLOP3/BRA loop -- 466
@@ -22,66 +22,38 @@
 
 namespace cw {
 
-#ifndef CW_TRAJ_S
-#define CW_TRAJ_S 8
-#endif
-constexpr int TRAJ_S = CW_TRAJ_S;                            // samples per window (4 or 8)
-constexpr int TRAJ_CPR = TRAJ_S / 2;                         // 16-byte chunks per row
-constexpr int TRAJ_LPS = 6 * TRAJ_CPR;                       // flush lanes per source lane (24 | 12)
-constexpr int TRAJ_SPI = 32 / TRAJ_LPS;                      // source lanes per store instruction (1 | 2)
+constexpr int TRAJ_S = 8;                                    // samples per window
 constexpr int TRAJ_ROWS = 6;                                 // x y z vx vy vz
-constexpr int TRAJ_DATA_BYTES = TRAJ_ROWS * TRAJ_S * 8;      // 384
-constexpr int TRAJ_LANE_BYTES = TRAJ_DATA_BYTES + 16;        // + header {col0, n}; also de-phases the banks
-
-struct TrajHeader {
-    long long col0; // absolute column of the first staged sample
-    int n;          // staged samples
-    int pad;
-};
+constexpr int TRAJ_DATA_BYTES = TRAJ_ROWS * TRAJ_S * 8;      // 384: rows of one lane, [row][slot]
+// + 8-byte header {column << 4 | count}.  392 bytes = 98 words = 2 (mod 32): the 8-byte staging stores
+// of the 32 lanes fall into 32 distinct bank pairs (conflict-free), which a 16-byte-aligned stride
+// cannot give -- so the flush moves 8-byte words (LDS.64 -> STG.64), 8 adjacent lanes per 64-byte run.
+constexpr int TRAJ_LANE_BYTES = TRAJ_DATA_BYTES + 8;
 
 struct TrajWriter {
     unsigned char *warp_base; // the 32 lane regions of this warp
     double *buf;              // this lane's rows: buf[row * TRAJ_S + slot]
-    double *my_row;           // flush role of this lane: destination row (lane >> 2), lanes 0..23
+    double *dst_pos, *dst_vel; // flush role of this lane: row 0 of pos / vel, offset by its slot (lane & 7)
+    int64_t row_stride;        // columns per row
     int64_t col0;
     int n;
     bool want;                // my window is complete and waits for the next cooperative flush
-    bool wide_ok;             // destination rows are 16-byte aligned -> 128-bit stores
+    bool ok8;                 // destination rows are 8-byte aligned (always) -- kept for symmetry
 
     __device__ __forceinline__ void init(unsigned char *smem, const IntegArgs &A)
     {
         const int lane = threadIdx.x & 31;
         warp_base = smem + (size_t)(threadIdx.x - lane) * TRAJ_LANE_BYTES;
         buf = reinterpret_cast<double *>(warp_base + (size_t)lane * TRAJ_LANE_BYTES);
-        const int r = min((lane % TRAJ_LPS) / TRAJ_CPR, TRAJ_ROWS - 1);
-        my_row = (r < 3) ? A.traj_pos + (int64_t)r * A.traj_total : A.traj_vel + (int64_t)(r - 3) * A.traj_total;
+        // flush role: lanes 8q..8q+7 move the 64-byte run of source lane 4g + q (slot = lane & 7), one
+        // row per instruction -- every store instruction writes four full runs
+        dst_pos = A.traj_pos + (lane & 7);
+        dst_vel = A.traj_vel + (lane & 7);
+        row_stride = A.traj_total;
         col0 = 0;
         n = 0;
         want = false;
-        wide_ok = ((A.traj_total & 1) == 0) &&
-                  (((reinterpret_cast<uintptr_t>(A.traj_pos) | reinterpret_cast<uintptr_t>(A.traj_vel)) & 15) == 0);
-    }
-
-    // stage one sample for absolute column `col`; `last` = final sample of the orbit.
-    // At most one window may complete between two flush_warp() calls.
-    __device__ __forceinline__ void put(int64_t col, double x, double y, double z, double vx, double vy, double vz,
-                                        bool last)
-    {
-        const int slot = (int)(col & (TRAJ_S - 1));
-        if (n == 0) col0 = col;
-        buf[0 * TRAJ_S + slot] = x;
-        buf[1 * TRAJ_S + slot] = y;
-        buf[2 * TRAJ_S + slot] = z;
-        buf[3 * TRAJ_S + slot] = vx;
-        buf[4 * TRAJ_S + slot] = vy;
-        buf[5 * TRAJ_S + slot] = vz;
-        n++;
-        if (slot == TRAJ_S - 1 || last) {
-            TrajHeader *h = reinterpret_cast<TrajHeader *>(reinterpret_cast<unsigned char *>(buf) + TRAJ_DATA_BYTES);
-            h->col0 = col0;
-            h->n = n;
-            want = true;
-        }
+        ok8 = true;
     }
 
     // stage a sample that is known NOT to complete the window (the integrator bounds its runs so)
@@ -98,47 +70,79 @@ struct TrajWriter {
         n++;
     }
 
-    // Warp-convergent: every lane of the warp must call this together.
-    __device__ __forceinline__ void flush_warp()
+    // stage one sample for absolute column `col`; `last` = final sample of the orbit.
+    // At most one window may complete between two flush_warp() calls.
+    __device__ __forceinline__ void put(int64_t col, double x, double y, double z, double vx, double vy, double vz,
+                                        bool last)
+    {
+        stage(col, x, y, z, vx, vy, vz);
+        if ((col & (TRAJ_S - 1)) == TRAJ_S - 1 || last) {
+            *reinterpret_cast<long long *>(reinterpret_cast<unsigned char *>(buf) + TRAJ_DATA_BYTES) =
+                (long long)(col0 << 4) | (long long)n;
+            want = true;
+        }
+    }
+
+    // Warp-convergent: every lane of the warp must call this together.  Returns true if anything was
+    // written (warp-uniform).
+    __device__ __forceinline__ bool flush_warp(const IntegArgs &A)
     {
         unsigned m = __ballot_sync(0xffffffffu, want);
-        if (m == 0) return;
+        if (m == 0) return false;
         __syncwarp();                       // the staged samples / headers of the other lanes are visible
         const int lane = threadIdx.x & 31;
-        const int sub = lane / TRAJ_LPS;                       // which source lane of a store instruction
-        const int r = (lane % TRAJ_LPS) / TRAJ_CPR, c = lane % TRAJ_CPR;
-        const bool role = lane < TRAJ_SPI * TRAJ_LPS;
-        if (m == 0xffffffffu && wide_ok && __all_sync(0xffffffffu, n == TRAJ_S)) {
-            // lockstep case (equal-length orbits): all 32 windows are complete -- fully unrolled, every
-            // shared-memory offset an immediate: LDS.64 column, LDS.128 data, address, STG.128
-            if (role) {
-                const unsigned char *src = warp_base + sub * TRAJ_LANE_BYTES + r * (TRAJ_S * 8) + c * 16;
-                const unsigned char *hdr = warp_base + sub * TRAJ_LANE_BYTES + TRAJ_DATA_BYTES;
-                double *dst = my_row + 2 * c;
+        const int q = lane >> 3, slot = lane & 7;
+        if (m == 0xffffffffu && __all_sync(0xffffffffu, n == TRAJ_S)) {
+            // lockstep case (equal-length orbits): all 32 windows complete.  Fully unrolled, immediate
+            // shared-memory offsets; per group of 4 source lanes ONE header load, then six independent
+            // (LDS.64 -> STG.64) pairs, each writing four full 64-byte runs.
+            const unsigned char *src = warp_base + q * TRAJ_LANE_BYTES + slot * 8;
 #pragma unroll
-                for (int l = 0; l < 32; l += TRAJ_SPI) {
-                    const long long c0 = *reinterpret_cast<const long long *>(hdr + l * TRAJ_LANE_BYTES);
-                    const double2 v = *reinterpret_cast<const double2 *>(src + l * TRAJ_LANE_BYTES);
-                    *reinterpret_cast<double2 *>(dst + c0) = v;
-                }
+            for (int g = 0; g < 8; g++) {
+                const unsigned char *sg = src + g * 4 * TRAJ_LANE_BYTES;
+                const long long c0 = *reinterpret_cast<const long long *>(sg - slot * 8 + TRAJ_DATA_BYTES) >> 4;
+                double *dp = dst_pos + c0, *dv = dst_vel + c0;
+                const double w0 = *reinterpret_cast<const double *>(sg + 0 * TRAJ_S * 8);
+                const double w1 = *reinterpret_cast<const double *>(sg + 1 * TRAJ_S * 8);
+                const double w2 = *reinterpret_cast<const double *>(sg + 2 * TRAJ_S * 8);
+                const double w3 = *reinterpret_cast<const double *>(sg + 3 * TRAJ_S * 8);
+                const double w4 = *reinterpret_cast<const double *>(sg + 4 * TRAJ_S * 8);
+                const double w5 = *reinterpret_cast<const double *>(sg + 5 * TRAJ_S * 8);
+#ifndef CW_TRAJ_NOSTORE
+                dp[0] = w0;
+                dp[row_stride] = w1;
+                dp[2 * row_stride] = w2;
+                dv[0] = w3;
+                dv[row_stride] = w4;
+                dv[2 * row_stride] = w5;
+#else
+                if (c0 == -12345) dp[0] = w0 + w1 + w2 + w3 + w4 + w5;
+#endif
             }
         } else {
             while (m) {
-                const int l = __ffs(m) - 1;
-                m &= m - 1;
-                const unsigned char *src = warp_base + (size_t)l * TRAJ_LANE_BYTES;
-                const TrajHeader h = *reinterpret_cast<const TrajHeader *>(src + TRAJ_DATA_BYTES);
-                if (role && sub == 0) {
-                    if (h.n == TRAJ_S && wide_ok) {
-                        const double2 v = *reinterpret_cast<const double2 *>(src + r * (TRAJ_S * 8) + c * 16);
-                        *reinterpret_cast<double2 *>(my_row + h.col0 + 2 * c) = v;
-                    } else {
-                        const int s0 = (int)(h.col0 & (TRAJ_S - 1));
-                        const double *rowbuf = reinterpret_cast<const double *>(src + r * (TRAJ_S * 8));
+                // up to four flushing source lanes per trip, one per 8-lane group
+                int l = -1;
+                unsigned mm = m;
+                for (int k = 0; k < 4; k++) {
+                    const int cand = mm ? (__ffs(mm) - 1) : -1;
+                    if (mm) mm &= mm - 1;
+                    if (k == q) l = cand;
+                }
+                m = mm;
+                if (l >= 0) {
+                    const unsigned char *sl = warp_base + (size_t)l * TRAJ_LANE_BYTES;
+                    const long long h = *reinterpret_cast<const long long *>(sl + TRAJ_DATA_BYTES);
+                    const long long c0 = h >> 4;
+                    const int cnt = (int)(h & 15);
+                    const int s0 = (int)(c0 & (TRAJ_S - 1));
+                    if (slot >= s0 && slot < s0 + cnt) {
+                        const double *rowbuf = reinterpret_cast<const double *>(sl) + slot;
+                        double *dp = dst_pos + (c0 - s0), *dv = dst_vel + (c0 - s0);
 #pragma unroll
-                        for (int q = 0; q < 2; q++) {
-                            const int e = 2 * c + q;
-                            if (e >= s0 && e < s0 + h.n) my_row[h.col0 - s0 + e] = rowbuf[e];
+                        for (int r = 0; r < 3; r++) {
+                            dp[r * row_stride] = rowbuf[r * TRAJ_S];
+                            dv[r * row_stride] = rowbuf[(3 + r) * TRAJ_S];
                         }
                     }
                 }
@@ -149,6 +153,7 @@ struct TrajWriter {
             want = false;
             n = 0;
         }
+        return true;
     }
 };
 

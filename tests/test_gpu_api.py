@@ -145,3 +145,27 @@ def test_properties_at_full_size(ctx):
     E0 = 0.5 * (b.w0[3:] ** 2).sum(axis=0) + ctx.potential_value(np.ascontiguousarray(b.w0[:3]))
     E1 = 0.5 * (fwd[3:] ** 2).sum(axis=0) + ctx.potential_value(np.ascontiguousarray(fwd[:3]))
     assert np.median(np.abs(E1 / E0 - 1)) < 1e-5
+
+
+def test_in_process_multi_device_sharding(built):
+    """cw_create over every visible GPU: orbits are sharded by index across the devices inside one call
+    (no collective); the result equals the single-device run bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    pop = make_population(5000, cfg_id=51, horizon_gyr=0.1)
+    b = pop.batch
+    one = cb.Context(devices=[0])
+    many = cb.Context()                       # all devices
+    assert many.n_devices == torch.cuda.device_count()
+    outs = []
+    for c in (one, many):
+        c.set_potential(pop.potential)
+        outs.append(c.integrate(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv,
+                                integrator=_lib.LEAPFROG, store_all=True))
+    assert np.array_equal(outs[0]["w_final"], outs[1]["w_final"])
+    assert np.array_equal(outs[0]["ev_step"], outs[1]["ev_step"])
+    assert np.array_equal(outs[0]["traj_pos"], outs[1]["traj_pos"])
+    assert np.array_equal(outs[0]["traj_t"], outs[1]["traj_t"])
+    assert int(outs[1]["stats"][3]) == int(outs[0]["stats"][3])
+    one.close(); many.close()
