@@ -147,9 +147,11 @@ cudaError_t launch_traj_times(const IntegArgs &A, const LaunchCfg &cfg)
 // Leapfrog
 // ------------------------------------------------------------------------------------------
 constexpr int LF_BLOCK = 256;        // final-state kernel: 4 CTAs x 256 threads per SM (64 registers)
-// store_all kernel: the staging windows cap the orbits in flight; 3 CTAs x 192 threads x 392 B fill the
-// 228 KB of shared memory (18 warps per SM), which is why this variant uses the table-free logarithm.
-constexpr int LF_BLOCK_STORE = 192;
+// store_all kernel: the staging windows cap the orbits in flight at 2 CTAs x 256 threads x 392 B per SM.
+// (3 x 192 threads with the table-free logarithm fit too, but the kernel is bound by the DRAM efficiency
+// of 64-byte runs, not by occupancy -- measured identical -- and sharing log_tab keeps a final-state run
+// bit-identical to the last sample of a store_all run.)
+constexpr int LF_BLOCK_STORE = 256;
 // resident CTAs per SM the final-state kernel is compiled for (register budget = 65536 / (256 * N))
 #ifndef CW_LF_MINB
 #define CW_LF_MINB 4
@@ -209,14 +211,13 @@ __device__ __forceinline__ void write_final(const IntegArgs &A, const Lane &s)
 }
 
 template <int KIND, bool STORE>
-__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK, STORE ? 3 : CW_LF_MINB) leapfrog_kernel(const __grid_constant__ PotParams P,
+__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK, STORE ? 2 : CW_LF_MINB) leapfrog_kernel(const __grid_constant__ PotParams P,
                                                             const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
-    __shared__ double2 ltab_s[STORE ? 1 : LOG_TABLE_N];
+    __shared__ double2 ltab[LOG_TABLE_N];
     extern __shared__ __align__(16) unsigned char traj_smem[];
-    const double2 *ltab = STORE ? nullptr : ltab_s;
-    if (!STORE) log_table_init(ltab_s);
+    log_table_init(ltab);
     TrajWriter tw;
     if (STORE) tw.init(traj_smem, A);
     int64_t col_base = 0;          // STORE: column of sample 0 of the current orbit
