@@ -403,14 +403,14 @@ static int run_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, Plan &pl, bool inte
     IntegArgs &A = pl.A;
     CW_CK(ctx, cudaMemsetAsync(A.queue, 0, 64, stream));
     CW_CK(ctx, cudaEventRecord(pl.ev_t0, stream));
-    CW_CK(ctx, launch_grid_prepass(A, pl.sort ? pl.iota : nullptr, cfg));
+    CW_CK(ctx, launch_grid_prepass(A, pl.sort ? pl.iota : nullptr, pl.sort ? pl.keys_in : nullptr, cfg));
     ctx->last_launches += 1;
     if (integrate) {
         if (pl.sort) {
             // Longest-processing-time-first queue.  Leapfrog: cost = node count.  DOP853: cost = node
             // count x step attempts per interval, measured by a short pilot integration (the persistent
             // short-period orbits near the nucleus need 10-50x the attempts of a disc orbit).
-            const int32_t *keys = (const int32_t *)A.n_nodes;
+            const int32_t *keys = pl.keys_in;      // node count << 4 | trajectory column phase
             if (o->integrator == CW_DOP853) {
                 A.cost_key = pl.keys_in;
                 A.pilot_intervals = 16;

@@ -46,7 +46,7 @@ struct LaunchCfg {
 };
 
 // grid pre-pass: node counts, kick node indices (bit-exact FP64 accumulation of the grid)
-cudaError_t launch_grid_prepass(const IntegArgs &A, int32_t *iota_out, const LaunchCfg &cfg);
+cudaError_t launch_grid_prepass(const IntegArgs &A, int32_t *iota_out, int32_t *sort_key_out, const LaunchCfg &cfg);
 // fixed-step leapfrog (gala leapfrog_integrate_hamiltonian semantics)
 cudaError_t launch_leapfrog(const PotParams &P, const IntegArgs &A, bool store_all, const LaunchCfg &cfg);
 // adaptive DOP853 restarted per grid interval (gala dop853_integrate_hamiltonian semantics)

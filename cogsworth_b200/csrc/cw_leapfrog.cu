@@ -25,7 +25,8 @@ namespace cw {
 // parse_time_specification does and resolves, for every event, k = max(cursor, last j with
 // T_j < t_event) -- the bit-exact kick timing the reference defines at kicks.py:134.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) grid_prepass_kernel(const __grid_constant__ IntegArgs A, int32_t *iota)
+__global__ void __launch_bounds__(256) grid_prepass_kernel(const __grid_constant__ IntegArgs A, int32_t *iota,
+                                                           int32_t *sort_key)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n) return;
@@ -106,14 +107,22 @@ __global__ void __launch_bounds__(256) grid_prepass_kernel(const __grid_constant
     A.n_nodes[i] = n_nodes;
     A.status[i] = st;
     if (iota) iota[i] = (int32_t)i;
+    if (sort_key) {
+        // queue order: longest orbit first; among equal lengths, orbits whose trajectories start at the
+        // same column phase (mod 16) are adjacent, so the 32 lanes of a warp fill -- and flush -- their
+        // staging windows on the same step (the trajectory writer's lock-step fast path)
+        int key = min(max(n_nodes, 0), (1 << 27) - 1) << 4;
+        if (A.traj_off) key |= 15 - (int)((A.traj_off[i] - A.traj_base) & 15);
+        sort_key[i] = key;
+    }
 }
 
-cudaError_t launch_grid_prepass(const IntegArgs &A, int32_t *iota_out, const LaunchCfg &cfg)
+cudaError_t launch_grid_prepass(const IntegArgs &A, int32_t *iota_out, int32_t *sort_key_out, const LaunchCfg &cfg)
 {
     if (A.n <= 0) return cudaSuccess;
     const int block = 256;
     const int64_t grid = (A.n + block - 1) / block;
-    grid_prepass_kernel<<<(unsigned)grid, block, 0, cfg.stream>>>(A, iota_out);
+    grid_prepass_kernel<<<(unsigned)grid, block, 0, cfg.stream>>>(A, iota_out, sort_key_out);
     return cudaGetLastError();
 }
 
@@ -218,8 +227,15 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK, STORE ? 2 :
     __shared__ double2 ltab[LOG_TABLE_N];
     extern __shared__ __align__(16) unsigned char traj_smem[];
     log_table_init(ltab);
+    __shared__ uint32_t tmem_slot;
+    uint32_t tmem_base = 0;
     TrajWriter tw;
-    if (STORE) tw.init(traj_smem, A);
+    if (STORE) {
+        tw.init(traj_smem, A);
+        // 8 warps x 96 columns of tensor memory: second staging level of the trajectory writer
+        tmem_base = traj_tmem_alloc(&tmem_slot);
+        tw.enable_tmem(tmem_base);
+    }
     int64_t col_base = 0;          // STORE: column of sample 0 of the current orbit
     Lane s;
     s.x = 8.0; s.y = 0.0; s.z = 0.0; s.vx = s.vy = s.vz = 0.0;
@@ -384,6 +400,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK, STORE ? 2 :
             steps_done += (unsigned long long)m;
         }
     }
+    if (STORE) traj_tmem_free(tmem_base);
     if (A.stats) {
         // orbit-steps actually integrated (the bench's unit of work), one atomic per warp
         for (int off = 16; off > 0; off >>= 1) steps_done += __shfl_down_sync(FULL, steps_done, off);

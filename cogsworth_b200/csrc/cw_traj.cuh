@@ -30,6 +30,59 @@ constexpr int TRAJ_DATA_BYTES = TRAJ_ROWS * TRAJ_S * 8;      // 384: rows of one
 // cannot give -- so the flush moves 8-byte words (LDS.64 -> STG.64), 8 adjacent lanes per 64-byte run.
 constexpr int TRAJ_LANE_BYTES = TRAJ_DATA_BYTES + 8;
 
+// ---- tensor memory as a second staging level ---------------------------------------------------------
+// Shared memory caps the staging windows at 8 samples = 64-byte runs, and lock-step 64-byte appends to
+// millions of streams reach only 2.6-4.0 TB/s of HBM (cw_measure_scatter_write): by the time the second
+// half of a 128-byte line arrives, a whole sweep later, the first half has long been evicted from L2 and
+// DRAM sees half-line writes.  The 256 KB of TMEM per SM are idle in this kernel, so a completed LOWER
+// half-line window (columns 0..7 mod 16) is parked there (tcgen05.st, 96 columns per lane) instead of
+// being written, and is written right after the UPPER half 8 steps later: the two halves reach L2 within
+// a microsecond of each other, merge, and leave as full 128-byte lines.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+                 "%13, %14, %15, %16};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+                 "%14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+constexpr int TRAJ_TMEM_COLS_PER_WARP = TRAJ_ROWS * TRAJ_S * 2;   // 96 32-bit columns per lane
+constexpr int TRAJ_TMEM_COLS_PER_CTA = 256;                        // 8 warps: 2 per lane quadrant x 96 -> 256
+
+// one warp of the CTA allocates; returns the TMEM base address to every thread (0 = not allocated)
+__device__ __forceinline__ uint32_t traj_tmem_alloc(uint32_t *slot)
+{
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(slot)), "n"(TRAJ_TMEM_COLS_PER_CTA) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return *slot;
+}
+
+__device__ __forceinline__ void traj_tmem_free(uint32_t base)
+{
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(base), "n"(TRAJ_TMEM_COLS_PER_CTA)
+                     : "memory");
+}
+
 struct TrajWriter {
     unsigned char *warp_base; // the 32 lane regions of this warp
     double *buf;              // this lane's rows: buf[row * TRAJ_S + slot]
@@ -38,7 +91,11 @@ struct TrajWriter {
     int64_t col0;
     int n;
     bool want;                // my window is complete and waits for the next cooperative flush
-    bool ok8;                 // destination rows are 8-byte aligned (always) -- kept for symmetry
+    bool want_last;           // ... and it is the last window of the orbit
+    bool parked;              // warp-uniform: a lower half-line window of every lane sits in TMEM
+    int64_t park_col0;        // its first column
+    uint32_t taddr;           // this warp's TMEM block (lane quadrant << 16 | first column)
+    bool tmem_on;             // TMEM parking enabled
 
     __device__ __forceinline__ void init(unsigned char *smem, const IntegArgs &A)
     {
@@ -52,8 +109,19 @@ struct TrajWriter {
         row_stride = A.traj_total;
         col0 = 0;
         n = 0;
-        want = false;
-        ok8 = true;
+        want = want_last = parked = false;
+        park_col0 = 0;
+        taddr = 0;
+        tmem_on = false;
+    }
+
+    // tmem_base: value returned by traj_tmem_alloc.  Warp w owns TMEM lanes 32 (w % 4) .. +31 (the only ones
+    // it can address) and, of those, columns 96 (w / 4) .. +95.
+    __device__ __forceinline__ void enable_tmem(uint32_t tmem_base)
+    {
+        const int warp = threadIdx.x >> 5;
+        taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TRAJ_TMEM_COLS_PER_WARP);
+        tmem_on = true;
     }
 
     // stage a sample that is known NOT to complete the window (the integrator bounds its runs so)
@@ -80,11 +148,88 @@ struct TrajWriter {
             *reinterpret_cast<long long *>(reinterpret_cast<unsigned char *>(buf) + TRAJ_DATA_BYTES) =
                 (long long)(col0 << 4) | (long long)n;
             want = true;
+            want_last = last;
         }
     }
 
-    // Warp-convergent: every lane of the warp must call this together.  Returns true if anything was
-    // written (warp-uniform).
+    // own rows -> TMEM (warp-convergent)
+    __device__ __forceinline__ void park()
+    {
+#pragma unroll
+        for (int r = 0; r < TRAJ_ROWS; r++) {
+            uint32_t v[16];
+#pragma unroll
+            for (int k = 0; k < TRAJ_S; k++) {
+                const double d = buf[r * TRAJ_S + k];
+                v[2 * k] = (uint32_t)__double2loint(d);
+                v[2 * k + 1] = (uint32_t)__double2hiint(d);
+            }
+            tmem_st16(taddr + 16 * r, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        park_col0 = col0;
+        parked = true;
+    }
+
+    // TMEM -> own rows + header (warp-convergent); the caller then flushes them like a fresh window
+    __device__ __forceinline__ void unpark_to_smem()
+    {
+#pragma unroll
+        for (int r = 0; r < TRAJ_ROWS; r++) {
+            uint32_t v[16];
+            tmem_ld16(taddr + 16 * r, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < TRAJ_S; k++) buf[r * TRAJ_S + k] = __hiloint2double((int)v[2 * k + 1], (int)v[2 * k]);
+        }
+        *reinterpret_cast<long long *>(reinterpret_cast<unsigned char *>(buf) + TRAJ_DATA_BYTES) =
+            (long long)(park_col0 << 4) | (long long)TRAJ_S;
+        parked = false;
+    }
+
+    // TMEM -> global with this lane's own 8-byte stores (rare: the warp fell out of lock-step while parked)
+    __device__ __forceinline__ void unpark_direct()
+    {
+#pragma unroll
+        for (int r = 0; r < TRAJ_ROWS; r++) {
+            uint32_t v[16];
+            tmem_ld16(taddr + 16 * r, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            double *dst = (r < 3 ? dst_pos - (threadIdx.x & 7) + (int64_t)r * row_stride
+                                 : dst_vel - (threadIdx.x & 7) + (int64_t)(r - 3) * row_stride) + park_col0;
+#pragma unroll
+            for (int k = 0; k < TRAJ_S; k++) dst[k] = __hiloint2double((int)v[2 * k + 1], (int)v[2 * k]);
+        }
+        parked = false;
+    }
+
+    // the lock-step store loop: all 32 lanes hold a complete window + header in shared memory
+    __device__ __forceinline__ void store_all_windows(int lane)
+    {
+        const int q = lane >> 3, slot = lane & 7;
+        const unsigned char *src = warp_base + q * TRAJ_LANE_BYTES + slot * 8;
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const unsigned char *sg = src + g * 4 * TRAJ_LANE_BYTES;
+            const long long c0 = *reinterpret_cast<const long long *>(sg - slot * 8 + TRAJ_DATA_BYTES) >> 4;
+            double *dp = dst_pos + c0, *dv = dst_vel + c0;
+            const double w0 = *reinterpret_cast<const double *>(sg + 0 * TRAJ_S * 8);
+            const double w1 = *reinterpret_cast<const double *>(sg + 1 * TRAJ_S * 8);
+            const double w2 = *reinterpret_cast<const double *>(sg + 2 * TRAJ_S * 8);
+            const double w3 = *reinterpret_cast<const double *>(sg + 3 * TRAJ_S * 8);
+            const double w4 = *reinterpret_cast<const double *>(sg + 4 * TRAJ_S * 8);
+            const double w5 = *reinterpret_cast<const double *>(sg + 5 * TRAJ_S * 8);
+            dp[0] = w0;
+            dp[row_stride] = w1;
+            dp[2 * row_stride] = w2;
+            dv[0] = w3;
+            dv[row_stride] = w4;
+            dv[2 * row_stride] = w5;
+        }
+    }
+
+    // Warp-convergent: every lane of the warp must call this together.  Returns true if any window was
+    // completed (warp-uniform).
     __device__ __forceinline__ bool flush_warp(const IntegArgs &A)
     {
         unsigned m = __ballot_sync(0xffffffffu, want);
@@ -92,59 +237,52 @@ struct TrajWriter {
         __syncwarp();                       // the staged samples / headers of the other lanes are visible
         const int lane = threadIdx.x & 31;
         const int q = lane >> 3, slot = lane & 7;
-        if (m == 0xffffffffu && __all_sync(0xffffffffu, n == TRAJ_S)) {
-            // lockstep case (equal-length orbits): all 32 windows complete.  Fully unrolled, immediate
-            // shared-memory offsets; per group of 4 source lanes ONE header load, then six independent
-            // (LDS.64 -> STG.64) pairs, each writing four full 64-byte runs.
-            const unsigned char *src = warp_base + q * TRAJ_LANE_BYTES + slot * 8;
-#pragma unroll
-            for (int g = 0; g < 8; g++) {
-                const unsigned char *sg = src + g * 4 * TRAJ_LANE_BYTES;
-                const long long c0 = *reinterpret_cast<const long long *>(sg - slot * 8 + TRAJ_DATA_BYTES) >> 4;
-                double *dp = dst_pos + c0, *dv = dst_vel + c0;
-                const double w0 = *reinterpret_cast<const double *>(sg + 0 * TRAJ_S * 8);
-                const double w1 = *reinterpret_cast<const double *>(sg + 1 * TRAJ_S * 8);
-                const double w2 = *reinterpret_cast<const double *>(sg + 2 * TRAJ_S * 8);
-                const double w3 = *reinterpret_cast<const double *>(sg + 3 * TRAJ_S * 8);
-                const double w4 = *reinterpret_cast<const double *>(sg + 4 * TRAJ_S * 8);
-                const double w5 = *reinterpret_cast<const double *>(sg + 5 * TRAJ_S * 8);
-#ifndef CW_TRAJ_NOSTORE
-                dp[0] = w0;
-                dp[row_stride] = w1;
-                dp[2 * row_stride] = w2;
-                dv[0] = w3;
-                dv[row_stride] = w4;
-                dv[2 * row_stride] = w5;
-#else
-                if (c0 == -12345) dp[0] = w0 + w1 + w2 + w3 + w4 + w5;
-#endif
-            }
+        const bool lockstep = (m == 0xffffffffu) && __all_sync(0xffffffffu, n == TRAJ_S);
+        if (lockstep && tmem_on && !parked &&
+            __all_sync(0xffffffffu, (col0 & (2 * TRAJ_S - 1)) == 0 && !want_last)) {
+            // lower half of a 128-byte line everywhere and no orbit ends here: park it, write nothing
+            park();
         } else {
-            while (m) {
-                // up to four flushing source lanes per trip, one per 8-lane group
-                int l = -1;
-                unsigned mm = m;
-                for (int k = 0; k < 4; k++) {
-                    const int cand = mm ? (__ffs(mm) - 1) : -1;
-                    if (mm) mm &= mm - 1;
-                    if (k == q) l = cand;
-                }
-                m = mm;
-                if (l >= 0) {
-                    const unsigned char *sl = warp_base + (size_t)l * TRAJ_LANE_BYTES;
-                    const long long h = *reinterpret_cast<const long long *>(sl + TRAJ_DATA_BYTES);
-                    const long long c0 = h >> 4;
-                    const int cnt = (int)(h & 15);
-                    const int s0 = (int)(c0 & (TRAJ_S - 1));
-                    if (slot >= s0 && slot < s0 + cnt) {
-                        const double *rowbuf = reinterpret_cast<const double *>(sl) + slot;
-                        double *dp = dst_pos + (c0 - s0), *dv = dst_vel + (c0 - s0);
+            if (lockstep) {
+                store_all_windows(lane);
+            } else {
+                while (m) {
+                    // up to four flushing source lanes per trip, one per 8-lane group
+                    int l = -1;
+                    unsigned mm = m;
+                    for (int k = 0; k < 4; k++) {
+                        const int cand = mm ? (__ffs(mm) - 1) : -1;
+                        if (mm) mm &= mm - 1;
+                        if (k == q) l = cand;
+                    }
+                    m = mm;
+                    if (l >= 0) {
+                        const unsigned char *sl = warp_base + (size_t)l * TRAJ_LANE_BYTES;
+                        const long long h = *reinterpret_cast<const long long *>(sl + TRAJ_DATA_BYTES);
+                        const long long c0 = h >> 4;
+                        const int cnt = (int)(h & 15);
+                        const int s0 = (int)(c0 & (TRAJ_S - 1));
+                        if (slot >= s0 && slot < s0 + cnt) {
+                            const double *rowbuf = reinterpret_cast<const double *>(sl) + slot;
+                            double *dp = dst_pos + (c0 - s0), *dv = dst_vel + (c0 - s0);
 #pragma unroll
-                        for (int r = 0; r < 3; r++) {
-                            dp[r * row_stride] = rowbuf[r * TRAJ_S];
-                            dv[r * row_stride] = rowbuf[(3 + r) * TRAJ_S];
+                            for (int r = 0; r < 3; r++) {
+                                dp[r * row_stride] = rowbuf[r * TRAJ_S];
+                                dv[r * row_stride] = rowbuf[(3 + r) * TRAJ_S];
+                            }
                         }
                     }
+                }
+            }
+            if (parked) {
+                // the parked lower halves follow immediately, so both halves of every line meet in L2
+                if (lockstep) {
+                    __syncwarp();           // the rows just written out are free again
+                    unpark_to_smem();
+                    __syncwarp();
+                    store_all_windows(lane);
+                } else {
+                    unpark_direct();
                 }
             }
         }
