@@ -13,6 +13,8 @@
 // lane's next kick / last node), then the lanes that reached such a node handle it.
 #include <cooperative_groups.h>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include "cw_kernels.cuh"
 #include "cw_traj.cuh"
 
@@ -156,11 +158,11 @@ cudaError_t launch_traj_times(const IntegArgs &A, const LaunchCfg &cfg)
 // Leapfrog
 // ------------------------------------------------------------------------------------------
 constexpr int LF_BLOCK = 256;        // final-state kernel: 4 CTAs x 256 threads per SM (64 registers)
-// store_all kernel: the staging windows cap the orbits in flight at 2 CTAs x 256 threads x 392 B per SM.
-// (3 x 192 threads with the table-free logarithm fit too, but the kernel is bound by the DRAM efficiency
-// of 64-byte runs, not by occupancy -- measured identical -- and sharing log_tab keeps a final-state run
-// bit-identical to the last sample of a store_all run.)
-constexpr int LF_BLOCK_STORE = 256;
+// store_all kernel: ONE CTA of 512 threads per SM.  The staging windows (392 B per lane = 196 KB) cap the
+// orbits in flight at 512 per SM, and a kernel that allocates tensor memory is given one CTA per SM by the
+// occupancy calculator whatever it asks for, so the 16 warps live in one CTA that owns all 512 TMEM columns
+// (measured 4.13 TB/s vs 4.00 TB/s for 2 x 256 threads with 256 columns each; 112 registers per thread).
+constexpr int LF_BLOCK_STORE = 512;
 // resident CTAs per SM the final-state kernel is compiled for (register budget = 65536 / (256 * N))
 #ifndef CW_LF_MINB
 #define CW_LF_MINB 4
@@ -220,7 +222,7 @@ __device__ __forceinline__ void write_final(const IntegArgs &A, const Lane &s)
 }
 
 template <int KIND, bool STORE>
-__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK, STORE ? 2 : CW_LF_MINB) leapfrog_kernel(const __grid_constant__ PotParams P,
+__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? 112 : 64) leapfrog_kernel(const __grid_constant__ PotParams P,
                                                             const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK, STORE ? 2 :
     TrajWriter tw;
     if (STORE) {
         tw.init(traj_smem, A);
-        // 8 warps x 96 columns of tensor memory: second staging level of the trajectory writer
+        // 16 warps x 96 columns of tensor memory: second staging level of the trajectory writer
         tmem_base = traj_tmem_alloc(&tmem_slot);
         tw.enable_tmem(tmem_base);
     }
@@ -426,6 +428,9 @@ static cudaError_t launch_lf(const PotParams &P, const IntegArgs &A, const Launc
     const int64_t need = (A.n + block - 1) / block;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    if (getenv("CW_DEBUG"))
+        fprintf(stderr, "[cw] leapfrog_kernel<%d,%d>: %d CTAs/SM x %d SMs, grid %lld, block %d, dyn smem %zu\n", KIND,
+                (int)STORE, per_sm, cfg.sm_count, (long long)grid, block, dyn);
     leapfrog_kernel<KIND, STORE><<<(unsigned)grid, block, dyn, cfg.stream>>>(P, A);
     return cudaGetLastError();
 }

@@ -58,7 +58,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v)
 }
 
 constexpr int TRAJ_TMEM_COLS_PER_WARP = TRAJ_ROWS * TRAJ_S * 2;   // 96 32-bit columns per lane
-constexpr int TRAJ_TMEM_COLS_PER_CTA = 256;                        // 8 warps: 2 per lane quadrant x 96 -> 256
+constexpr int TRAJ_TMEM_COLS_PER_CTA = 512;                        // 16 warps: 4 per lane quadrant x 96 = 384 -> 512
 
 // one warp of the CTA allocates; returns the TMEM base address to every thread (0 = not allocated)
 __device__ __forceinline__ uint32_t traj_tmem_alloc(uint32_t *slot)
@@ -242,7 +242,13 @@ struct TrajWriter {
             __all_sync(0xffffffffu, (col0 & (2 * TRAJ_S - 1)) == 0 && !want_last)) {
             // lower half of a 128-byte line everywhere and no orbit ends here: park it, write nothing
             park();
+#ifdef CW_TRAJ_DEBUG
+            if (lane == 0) atomicAdd(A.stats + 0, 1ull);
+#endif
         } else {
+#ifdef CW_TRAJ_DEBUG
+            if (lane == 0) atomicAdd(A.stats + (lockstep ? 2 : 1), lockstep ? 1ull : (unsigned long long)(__popc(m) + 1000000ull));
+#endif
             if (lockstep) {
                 store_all_windows(lane);
             } else {
