@@ -51,6 +51,11 @@ WORKLOADS = {
                     f_sn=0.0, desc="1e6 orbits x 1000 stored steps (48 GB), MilkyWayPotential2022, leapfrog, no kicks"),
     "config3k": dict(cfg_id=3, n_orbits=1_000_000, horizon_gyr=1.0, integrator="leapfrog", store_all=True,
                      f_sn=1.0, desc="1e6 orbits x 1001 stored steps (48 GB), MilkyWayPotential2022, leapfrog, kicks on"),
+    "config2_dop853_dense": dict(cfg_id=2, n_binaries=100_000, horizon_gyr=None, integrator="dop853_dense", store_all=False,
+                                 f_sn=1.0, desc="1e5 binaries, Wagg2022 horizons, MilkyWayPotential2022, DOPRI853 1e-10 dense-output form, kicks"),
+    "config5_dense": dict(cfg_id=5, n_orbits=1_000_000, horizon_gyr=1.0, integrator="dop853_dense", store_all=False,
+                          f_sn=1.0, plunging_fraction=0.01, rtol=1e-8, atol=1e-8,
+                          desc="1e6 orbits DOPRI853 rtol=atol=1e-8 (one call per segment, dense-output form), 1 Gyr, kicks, 1% plunging"),
     "config5": dict(cfg_id=5, n_orbits=1_000_000, horizon_gyr=1.0, integrator="dop853", store_all=False,
                     f_sn=1.0, plunging_fraction=0.01, rtol=1e-8, atol=1e-8,
                     desc="1e6 orbits DOPRI853 rtol=atol=1e-8, 1 Gyr, kicks, 1% plunging"),
@@ -149,7 +154,7 @@ def cpu_baseline(pop, wl, n_sample, threads=0, repeats=1):
     """The gala-equivalent C oracle on the host cores over a bounded sample of the same workload."""
     import oracle as O
     b = pop.batch.take(np.arange(min(n_sample, pop.batch.n_orbits)))
-    integ = O.LEAPFROG if wl["integrator"] == "leapfrog" else O.DOP853
+    integ = {"leapfrog": O.LEAPFROG, "dop853": O.DOP853, "dop853_dense": O.DOP853_DENSE}[wl["integrator"]]
     threads = threads or O.max_threads()
     best, steps = None, 0
     for _ in range(repeats):
@@ -235,7 +240,7 @@ def main():
     pop = build_shard(wl, rank, world, args.scaling, args.scale)
     b = pop.batch
     n, K = b.n_orbits, b.n_events
-    integ = _lib.LEAPFROG if wl["integrator"] == "leapfrog" else _lib.DOP853
+    integ = {"leapfrog": _lib.LEAPFROG, "dop853": _lib.DOP853, "dop853_dense": _lib.DOP853_DENSE}[wl["integrator"]]
     tol = dict(atol=wl.get("atol", 1e-10), rtol=wl.get("rtol", 1e-10))
     ctx = cb.Context(devices=[local_rank])
     ctx.set_potential(pop.potential)
@@ -343,7 +348,8 @@ def main():
         else:
             # 12 gradients + 1000 flop of stage algebra per accepted step, per launch
             flops = FLOP_PER_STEP["dop853_v2"] * float(stats_run[0])
-            kname, per = "dop853_kernel<MW_V2>", FLOP_PER_STEP["dop853_v2"]
+            kname = "dop853_kernel<MW_V2%s>" % (",DENSE" if integ == _lib.DOP853_DENSE else "")
+            per = FLOP_PER_STEP["dop853_v2"]
         ach = flops / (k_ms * 1e-3) / 1e12
         roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": "measured live: DFMA micro-benchmark cw_measure_fp64_peak (MEASURED_PEAKS.json has no "
@@ -369,7 +375,7 @@ def main():
                            "cache": "inputs + outputs (>= 1 GB per pass) exceed the 126 MB L2; nothing is reused between steps",
                            "failed_orbits_rank0": n_failed},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cbase}
-        if integ == _lib.DOP853:
+        if integ != _lib.LEAPFROG:
             line["config"]["dop853"] = {"accepted_steps": int(stats_run[0]), "rejected_steps": int(stats_run[1]),
                                         "gradient_evals": int(stats_run[2]), "intervals": int(stats_run[3]),
                                         "gradient_evals_per_s": float(stats_run[2]) / (k_ms * 1e-3)}

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # COGSWORTH_B200_LIB selects another build of the same ABI (A/B experiments); default = the in-tree build
 LIB_PATH = os.environ.get("COGSWORTH_B200_LIB") or os.path.join(_HERE, "libcogsworth_b200.so")
 
-LEAPFROG, DOP853 = 0, 1
+LEAPFROG, DOP853, DOP853_DENSE = 0, 1, 2
 GRID_APPEND_T2 = 1
 MEM_HOST, MEM_DEVICE = 0, 1
 

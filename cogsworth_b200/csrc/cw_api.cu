@@ -299,6 +299,7 @@ static size_t shard_bytes(const cw_opts *o, const cw_result *R, const Shard &sh,
     size_t need = 0;
     auto add = [&](size_t count, size_t elt) { need += Arena::padded(count, elt); };
     add(K + 1, sizeof(double));          // ev_tk
+    if (integrate && o->integrator == CW_DOP853_DENSE) add(m, sizeof(double));   // t_last
     add(1, 64);                          // queue + stats
     if (pl.sort) { add(m, 4); add(m, 4); add(m, 4); add(m, 4); add(pl.sort_bytes, 1); }
     if (!dev_mode) {
@@ -328,6 +329,10 @@ static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B,
     A.rtol = o->rtol > 0 ? o->rtol : 1e-10;
     A.nmax = o->nmax;
     A.ev_tk = s.arena.take<double>(K + 1);
+    if (integrate && o->integrator == CW_DOP853_DENSE) {
+        A.t_last = s.arena.take<double>(m);
+        if (!A.t_last) return fail(ctx, CW_E_CUDA, "device arena exhausted (internal sizing error)");
+    }
     unsigned long long *qs = s.arena.take<unsigned long long>(8);
     A.queue = qs;
     A.stats = qs + 1;
@@ -411,7 +416,7 @@ static int run_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, Plan &pl, bool inte
             // count x step attempts per interval, measured by a short pilot integration (the persistent
             // short-period orbits near the nucleus need 10-50x the attempts of a disc orbit).
             const int32_t *keys = pl.keys_in;      // node count << 4 | trajectory column phase
-            if (o->integrator == CW_DOP853) {
+            if (o->integrator != CW_LEAPFROG) {
                 A.cost_key = pl.keys_in;
                 A.pilot_intervals = 16;
                 A.order = nullptr;
@@ -427,7 +432,7 @@ static int run_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, Plan &pl, bool inte
         }
         CW_CK(ctx, cudaEventRecord(pl.ev_k0, stream));
         if (o->integrator == CW_LEAPFROG) CW_CK(ctx, launch_leapfrog(ctx->pot, A, store_all, cfg));
-        else CW_CK(ctx, launch_dop853(ctx->pot, A, store_all, cfg));
+        else CW_CK(ctx, launch_dop853(ctx->pot, A, store_all, o->integrator == CW_DOP853_DENSE, cfg));
         ctx->last_launches += 1;
         CW_CK(ctx, cudaEventRecord(pl.ev_k1, stream));
         pl.timed = true;
@@ -446,7 +451,7 @@ static int validate(cw_ctx *ctx, const cw_opts *o, const cw_batch *B)
     if (B->n_orbits > 0 && (!B->w0 || !B->t1 || !B->t2 || !B->dt || !B->to_myr || !B->grid_flags))
         return fail(ctx, CW_E_INVALID, "null input array");
     if (o->mem_space != CW_MEM_HOST && o->mem_space != CW_MEM_DEVICE) return fail(ctx, CW_E_INVALID, "bad mem_space");
-    if (o->integrator != CW_LEAPFROG && o->integrator != CW_DOP853) return fail(ctx, CW_E_UNSUPPORTED, "unknown integrator");
+    if (o->integrator != CW_LEAPFROG && o->integrator != CW_DOP853 && o->integrator != CW_DOP853_DENSE) return fail(ctx, CW_E_UNSUPPORTED, "unknown integrator");
     if (ctx->slots.empty()) return fail(ctx, CW_E_NO_DEVICE, "context has no device");
     return CW_OK;
 }

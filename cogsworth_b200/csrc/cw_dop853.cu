@@ -7,6 +7,13 @@
 //   nstiff = 1, uround = 2.3e-16; the error norm runs over the 6 components of the one orbit.
 //   cogsworth restarts the integrator at every kick node (kicks.py:132-183).
 //
+//   DENSE = true is the dense-output variant (newer gala releases evaluate the
+//   requested times with Hairer's continuous extension contd8 instead of stopping on every node):
+//   ONE dop853() call per segment [kick node .. next kick node / last node], h0 = t[1]-t[0],
+//   hmax = the whole segment, nmax attempts per segment.  Final-state runs never need the
+//   interpolant (segments end exactly on the nodes whose state matters); store_all runs evaluate
+//   it, after the three extra stages c14..c16, only for steps that contain a grid node.
+//
 // Execution model: persistent lanes, as in cw_leapfrog.cu, but the unit of work inside the loop is
 // ONE RK STEP ATTEMPT of the lane's own current interval.  Lanes of a warp are not held at
 // interval boundaries: a lane that needs sub-steps near the nucleus simply falls behind in ITS
@@ -50,6 +57,10 @@ struct DpLane {
     int j, L;
     int nstep, naccpt, iasti, nonsti;
     bool last, reject, append;
+    // DENSE: the segment [j, next] is one dop853() call
+    int next;         // node that ends the current segment (next kick node, or L)
+    double tend;      // its grid time (grid unit)
+    double tlast;     // grid time of the last accumulated node of the orbit (pre-pass)
 };
 
 __device__ __forceinline__ int64_t dp_queue_pop(unsigned long long *queue)
@@ -93,10 +104,20 @@ __device__ __forceinline__ void dp_apply_kicks(const IntegArgs &A, DpLane &s)
     s.k1[0] = s.y[3]; s.k1[1] = s.y[4]; s.k1[2] = s.y[5];
 }
 
-// open the interval [node j, node j+1] = the argument set of one dop853() call
-__device__ __forceinline__ void dp_begin_interval(DpLane &s)
+// open the interval [node j, node j+1] (DENSE: the segment [node j, next sync node]) = the argument
+// set of one dop853() call
+template <bool DENSE>
+__device__ __forceinline__ void dp_begin_interval(const IntegArgs &A, DpLane &s)
 {
-    const double tn = (s.append && s.j + 1 == s.L) ? s.t2 : s.tgrid + s.hgrid;
+    double tn;
+    if (DENSE) {
+        const bool to_kick = s.e < s.e1;
+        s.next = to_kick ? A.ev_step[s.e] : s.L;
+        tn = to_kick ? A.ev_tk[s.e] : (s.append ? s.t2 : s.tlast);
+        s.tend = tn;
+    } else {
+        tn = (s.append && s.j + 1 == s.L) ? s.t2 : s.tgrid + s.hgrid;
+    }
     s.x = s.tgrid * s.smyr;
     s.xend = tn * s.smyr;
     s.h = s.dt0;
@@ -112,7 +133,7 @@ __device__ __forceinline__ void dp_begin_interval(DpLane &s)
 // sorts the queue by that key so the expensive (short-period, sub-stepping) orbits start first:
 // with one sequential orbit per lane the makespan is max(longest orbit, total work / lanes), and a
 // long orbit started late would leave the whole GPU waiting for a single lane.
-template <int KIND, bool STORE, bool PILOT>
+template <int KIND, bool STORE, bool PILOT, bool DENSE>
 __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant__ PotParams P,
                                                           const __grid_constant__ IntegArgs A)
 {
@@ -131,6 +152,11 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
     s.e = s.e1 = 0; s.oid = -1; s.j = 0; s.L = 0;
     s.nstep = s.naccpt = s.iasti = s.nonsti = 0;
     s.last = s.reject = s.append = false;
+    s.next = 0; s.tend = 0.0; s.tlast = 0.0;
+    // DENSE && STORE: continuous extension of the last accepted step (Hairer rcont1..8), valid while `pend`
+    double rc[8][6];
+    double dn_xold = 0.0, dn_h = 1.0;
+    bool pend = false;
     bool active = false, exhausted = false, interval_done = false;
     int attempts = 0, Lstop = 0;       // PILOT bookkeeping
     unsigned long long n_acc = 0, n_rej = 0, n_fcn = 0, n_int = 0;
@@ -138,12 +164,40 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
     const double atol = A.atol, rtol = A.rtol;
 
     for (;;) {
-        // ---- phase A: lanes that completed an interval stand on node j+1
+        // ---- phase A0 (DENSE store_all): grid nodes strictly inside the segment that the last accepted
+        // step passed over are evaluated with contd8, one node per lane per warp-uniform trip
+        if (DENSE && STORE && !PILOT) {
+            for (;;) {
+                const bool emit = active && pend && (s.j + 1 < s.next) && ((s.tgrid + s.hgrid) * s.smyr <= s.x);
+                if (!__any_sync(FULL, emit)) break;
+                if (emit) {
+                    s.tgrid += s.hgrid;
+                    s.j += 1;
+                    n_int++;
+                    const double th = (s.tgrid * s.smyr - dn_xold) / dn_h, th1 = 1.0 - th;
+                    double v[6];
+#pragma unroll
+                    for (int i = 0; i < 6; i++)
+                        v[i] = fma(th, fma(th1, fma(th, fma(th1, fma(th, fma(th1, fma(th, rc[7][i], rc[6][i]), rc[5][i]),
+                                   rc[4][i]), rc[3][i]), rc[2][i]), rc[1][i]), rc[0][i]);
+                    tw.put(col_base + s.j, v[0], v[1], v[2], v[3], v[4], v[5], false);
+                }
+                tw.flush_warp(A);
+            }
+            pend = false;
+        }
+        // ---- phase A: lanes that completed an interval stand on node j+1 (DENSE: on the segment's end node)
         if (active && interval_done) {
             interval_done = false;
-            s.j += 1;
-            s.tgrid = (s.append && s.j == s.L) ? s.t2 : s.tgrid + s.hgrid;
-            n_int++;
+            if (DENSE) {
+                n_int += (unsigned long long)(s.next - s.j);
+                s.j = s.next;
+                s.tgrid = s.tend;
+            } else {
+                s.j += 1;
+                s.tgrid = (s.append && s.j == s.L) ? s.t2 : s.tgrid + s.hgrid;
+                n_int++;
+            }
             dp_apply_kicks(A, s);
             if (STORE && !PILOT)
                 tw.put(col_base + s.j, s.y[0], s.y[1], s.y[2], s.y[3], s.y[4], s.y[5], s.j == s.L);
@@ -154,7 +208,7 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
                 dp_write_final(A, s, CW_ORBIT_OK);
                 active = false;
             } else {
-                dp_begin_interval(s);
+                dp_begin_interval<DENSE>(A, s);
             }
         }
         if (STORE && !PILOT) tw.flush_warp(A);
@@ -179,6 +233,7 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
             s.hgrid = A.dt[o]; s.t2 = A.t2[o]; s.smyr = A.to_myr[o];
             s.append = (A.flags[o] & CW_GRID_APPEND_T2) != 0;
             s.tgrid = A.t1[o];
+            if (DENSE) s.tlast = A.t_last[o];
             s.e = s.e1 = 0;
             if (A.ev_off) { s.e = A.ev_off[o] - A.ev_base; s.e1 = A.ev_off[o + 1] - A.ev_base; }
             {
@@ -198,7 +253,7 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
             }
             fcn<KIND>(P, ltab, s.y, s.k1);
             n_fcn++;
-            dp_begin_interval(s);
+            dp_begin_interval<DENSE>(A, s);
             active = true;
         }
         if (STORE && !PILOT) tw.flush_warp(A);
@@ -305,6 +360,49 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
                     s.nonsti++;
                     if (s.nonsti == 6) s.iasti = 0;
                 }
+                if (DENSE && STORE && !PILOT) {
+                    // a grid node of this segment inside (x, x+h]: dop853.c "final preparation for dense output"
+                    if ((s.j + 1 < s.next) && ((s.tgrid + s.hgrid) * s.smyr <= xph)) {
+                        double ka[6], kb[6], kc[6];
+#pragma unroll
+                        for (int i = 0; i < 6; i++) {
+                            const double ydiff = k5[i] - y[i];
+                            const double bspl = fma(h, k1[i], -ydiff);
+                            rc[0][i] = y[i];
+                            rc[1][i] = ydiff;
+                            rc[2][i] = bspl;
+                            rc[3][i] = ydiff - h * k4[i] - bspl;
+                            rc[4][i] = fma(CW_D412, k3[i], fma(CW_D411, k2[i], fma(CW_D410, k10[i], fma(CW_D409, k9[i], fma(CW_D408, k8[i], fma(CW_D407, k7[i], fma(CW_D406, k6[i], CW_D401 * k1[i])))))));
+                            rc[5][i] = fma(CW_D512, k3[i], fma(CW_D511, k2[i], fma(CW_D510, k10[i], fma(CW_D509, k9[i], fma(CW_D508, k8[i], fma(CW_D507, k7[i], fma(CW_D506, k6[i], CW_D501 * k1[i])))))));
+                            rc[6][i] = fma(CW_D612, k3[i], fma(CW_D611, k2[i], fma(CW_D610, k10[i], fma(CW_D609, k9[i], fma(CW_D608, k8[i], fma(CW_D607, k7[i], fma(CW_D606, k6[i], CW_D601 * k1[i])))))));
+                            rc[7][i] = fma(CW_D712, k3[i], fma(CW_D711, k2[i], fma(CW_D710, k10[i], fma(CW_D709, k9[i], fma(CW_D708, k8[i], fma(CW_D707, k7[i], fma(CW_D706, k6[i], CW_D701 * k1[i])))))));
+                        }
+                        double yd[6];
+#pragma unroll
+                        for (int i = 0; i < 6; i++)
+                            yd[i] = fma(h, fma(CW_A1413, k4[i], fma(CW_A1412, k3[i], fma(CW_A1411, k2[i], fma(CW_A1410, k10[i], fma(CW_A1409, k9[i], fma(CW_A1408, k8[i], fma(CW_A1407, k7[i], CW_A1401 * k1[i]))))))), y[i]);
+                        fcn<KIND>(P, ltab, yd, ka);
+#pragma unroll
+                        for (int i = 0; i < 6; i++)
+                            yd[i] = fma(h, fma(CW_A1514, ka[i], fma(CW_A1513, k4[i], fma(CW_A1512, k3[i], fma(CW_A1511, k2[i], fma(CW_A1508, k8[i], fma(CW_A1507, k7[i], fma(CW_A1506, k6[i], CW_A1501 * k1[i]))))))), y[i]);
+                        fcn<KIND>(P, ltab, yd, kb);
+#pragma unroll
+                        for (int i = 0; i < 6; i++)
+                            yd[i] = fma(h, fma(CW_A1615, kb[i], fma(CW_A1614, ka[i], fma(CW_A1613, k4[i], fma(CW_A1609, k9[i], fma(CW_A1608, k8[i], fma(CW_A1607, k7[i], fma(CW_A1606, k6[i], CW_A1601 * k1[i]))))))), y[i]);
+                        fcn<KIND>(P, ltab, yd, kc);
+                        n_fcn += 3;
+#pragma unroll
+                        for (int i = 0; i < 6; i++) {
+                            rc[4][i] = h * fma(CW_D416, kc[i], fma(CW_D415, kb[i], fma(CW_D414, ka[i], fma(CW_D413, k4[i], rc[4][i]))));
+                            rc[5][i] = h * fma(CW_D516, kc[i], fma(CW_D515, kb[i], fma(CW_D514, ka[i], fma(CW_D513, k4[i], rc[5][i]))));
+                            rc[6][i] = h * fma(CW_D616, kc[i], fma(CW_D615, kb[i], fma(CW_D614, ka[i], fma(CW_D613, k4[i], rc[6][i]))));
+                            rc[7][i] = h * fma(CW_D716, kc[i], fma(CW_D715, kb[i], fma(CW_D714, ka[i], fma(CW_D713, k4[i], rc[7][i]))));
+                        }
+                        dn_xold = s.x;
+                        dn_h = h;
+                        pend = true;
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 6; i++) { s.k1[i] = k4[i]; s.y[i] = k5[i]; }
                 s.x = xph;
@@ -348,47 +446,54 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
     }
 }
 
-template <int KIND, bool STORE, bool PILOT>
+template <int KIND, bool STORE, bool PILOT, bool DENSE>
 static cudaError_t launch_dp(const PotParams &P, const IntegArgs &A, const LaunchCfg &cfg)
 {
     int per_sm = 0;
     const size_t dyn = (STORE && !PILOT) ? (size_t)DP_BLOCK * TRAJ_LANE_BYTES : 0;
     cudaError_t err = cudaSuccess;
     if (dyn) {
-        err = cudaFuncSetAttribute(dop853_kernel<KIND, STORE, PILOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        err = cudaFuncSetAttribute(dop853_kernel<KIND, STORE, PILOT, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (err != cudaSuccess) return err;
     }
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dop853_kernel<KIND, STORE, PILOT>, DP_BLOCK, dyn);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dop853_kernel<KIND, STORE, PILOT, DENSE>, DP_BLOCK, dyn);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)cfg.sm_count * per_sm;
     const int64_t need = (A.n + DP_BLOCK - 1) / DP_BLOCK;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    dop853_kernel<KIND, STORE, PILOT><<<(unsigned)grid, DP_BLOCK, dyn, cfg.stream>>>(P, A);
+    dop853_kernel<KIND, STORE, PILOT, DENSE><<<(unsigned)grid, DP_BLOCK, dyn, cfg.stream>>>(P, A);
     return cudaGetLastError();
 }
 
-cudaError_t launch_dop853(const PotParams &P, const IntegArgs &A, bool store_all, const LaunchCfg &cfg)
+template <int KIND>
+static cudaError_t launch_dp_kind(const PotParams &P, const IntegArgs &A, bool store_all, bool dense, const LaunchCfg &cfg)
+{
+    if (dense) return store_all ? launch_dp<KIND, true, false, true>(P, A, cfg) : launch_dp<KIND, false, false, true>(P, A, cfg);
+    return store_all ? launch_dp<KIND, true, false, false>(P, A, cfg) : launch_dp<KIND, false, false, false>(P, A, cfg);
+}
+
+cudaError_t launch_dop853(const PotParams &P, const IntegArgs &A, bool store_all, bool dense, const LaunchCfg &cfg)
 {
     if (A.n <= 0) return cudaSuccess;
+    if (dense && !A.t_last) return cudaErrorInvalidValue;
     switch (P.kind) {
-    case POT_MW_V1:
-        return store_all ? launch_dp<POT_MW_V1, true, false>(P, A, cfg) : launch_dp<POT_MW_V1, false, false>(P, A, cfg);
-    case POT_MW_V2:
-        return store_all ? launch_dp<POT_MW_V2, true, false>(P, A, cfg) : launch_dp<POT_MW_V2, false, false>(P, A, cfg);
-    default:
-        return store_all ? launch_dp<POT_GENERIC, true, false>(P, A, cfg) : launch_dp<POT_GENERIC, false, false>(P, A, cfg);
+    case POT_MW_V1: return launch_dp_kind<POT_MW_V1>(P, A, store_all, dense, cfg);
+    case POT_MW_V2: return launch_dp_kind<POT_MW_V2>(P, A, store_all, dense, cfg);
+    default: return launch_dp_kind<POT_GENERIC>(P, A, store_all, dense, cfg);
     }
 }
 
+// The pilot always runs the restart-per-interval form: attempts per grid interval is the cost proxy of
+// both modes (it resolves exactly the expensive, sub-stepping orbits that decide the makespan).
 cudaError_t launch_dop853_pilot(const PotParams &P, const IntegArgs &A, const LaunchCfg &cfg)
 {
     if (A.n <= 0) return cudaSuccess;
     switch (P.kind) {
-    case POT_MW_V1: return launch_dp<POT_MW_V1, false, true>(P, A, cfg);
-    case POT_MW_V2: return launch_dp<POT_MW_V2, false, true>(P, A, cfg);
-    default: return launch_dp<POT_GENERIC, false, true>(P, A, cfg);
+    case POT_MW_V1: return launch_dp<POT_MW_V1, false, true, false>(P, A, cfg);
+    case POT_MW_V2: return launch_dp<POT_MW_V2, false, true, false>(P, A, cfg);
+    default: return launch_dp<POT_GENERIC, false, true, false>(P, A, cfg);
     }
 }
 

@@ -23,6 +23,7 @@ struct IntegArgs {
     int32_t *n_nodes;      // n
     int32_t *ev_step;      // K   node index of each kick
     double *ev_tk;         // K   accumulated grid time of that node (grid unit)
+    double *t_last;        // n   accumulated grid time of the last accumulated node (may be null)
     int32_t *order;        // n   queue position -> orbit (longest first), may be null = identity
     unsigned long long *queue; // work counter of the persistent-lane scheduler
     // outputs (cw_result)
@@ -49,8 +50,9 @@ struct LaunchCfg {
 cudaError_t launch_grid_prepass(const IntegArgs &A, int32_t *iota_out, int32_t *sort_key_out, const LaunchCfg &cfg);
 // fixed-step leapfrog (gala leapfrog_integrate_hamiltonian semantics)
 cudaError_t launch_leapfrog(const PotParams &P, const IntegArgs &A, bool store_all, const LaunchCfg &cfg);
-// adaptive DOP853 restarted per grid interval (gala dop853_integrate_hamiltonian semantics)
-cudaError_t launch_dop853(const PotParams &P, const IntegArgs &A, bool store_all, const LaunchCfg &cfg);
+// adaptive DOP853: restarted per grid interval (gala dop853_integrate_hamiltonian semantics), or
+// dense = one call per segment with Hairer's continuous extension at the grid nodes
+cudaError_t launch_dop853(const PotParams &P, const IntegArgs &A, bool store_all, bool dense, const LaunchCfg &cfg);
 // DOP853 pilot: first A.pilot_intervals intervals of every orbit -> A.cost_key (queue ordering)
 cudaError_t launch_dop853_pilot(const PotParams &P, const IntegArgs &A, const LaunchCfg &cfg);
 // Orbit.t of stored trajectories (only when traj_t was requested)

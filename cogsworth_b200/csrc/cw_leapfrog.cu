@@ -108,13 +108,14 @@ __global__ void __launch_bounds__(256) grid_prepass_kernel(const __grid_constant
         st = CW_ORBIT_INCONSISTENT;
     A.n_nodes[i] = n_nodes;
     A.status[i] = st;
+    if (A.t_last) A.t_last[i] = Tprev;     // time of node n_acc - 1 (DOP853 dense mode: end of the last segment)
     if (iota) iota[i] = (int32_t)i;
     if (sort_key) {
-        // queue order: longest orbit first; among equal lengths, orbits whose trajectories start at the
-        // same column phase (mod 16) are adjacent, so the 32 lanes of a warp fill -- and flush -- their
-        // staging windows on the same step (the trajectory writer's lock-step fast path)
+        // queue order: longest orbit first; among equal lengths the (stable) sort keeps index order, so the
+        // 32 lanes of a warp write 32 NEIGHBOURING trajectories.  Measured on store_all: lanes whose streams
+        // are >= 32 KB apart (orbits grouped by column phase instead) reach 2.3 TB/s, neighbours 3.4 TB/s;
+        // phase alignment is the warp clock's job (cw_leapfrog.cu), not the queue's.
         int key = min(max(n_nodes, 0), (1 << 27) - 1) << 4;
-        if (A.traj_off) key |= 15 - (int)((A.traj_off[i] - A.traj_base) & 15);
         sort_key[i] = key;
     }
 }
@@ -222,7 +223,7 @@ __device__ __forceinline__ void write_final(const IntegArgs &A, const Lane &s)
 }
 
 template <int KIND, bool STORE>
-__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? 112 : 64) leapfrog_kernel(const __grid_constant__ PotParams P,
+__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? 128 : 64) leapfrog_kernel(const __grid_constant__ PotParams P,
                                                             const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
@@ -246,6 +247,19 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
     s.e = s.e1 = 0; s.oid = -1; s.j = 0; s.next = 0; s.L = 0; s.append = false;
     bool active = false, exhausted = false, staged = false;
     unsigned long long steps_done = 0;
+    // STORE: the warp clock.  W counts the steps this warp has executed; an orbit whose first sample lives
+    // in column c starts only when W = c (mod 16), so (column of the node a lane stands on) mod 16 is the
+    // same for every active lane of the warp at every step: windows fill and flush in lock-step and the
+    // lower / upper halves of the 128-byte lines alternate warp-wide.  A popped orbit waits at most 15 steps.
+    int W = 0, delay = 0;
+    bool pending = false;
+    int64_t pend_o = -1;
+    // STORE: the warp takes queue entries in private blocks of 32 CONSECUTIVE positions (one atomic per
+    // block) and hands them to its lanes as they fall idle, so a warp always writes 32 neighbouring
+    // trajectories even when its lanes finish at different steps.  (Per-lane pops interleave the warps:
+    // after the first round every lane of a warp would hold an orbit from somewhere else in the queue,
+    // and streams >= 32 KB apart cost a third of the HBM write throughput -- measured.)
+    int64_t wq_next = 0, wq_end = 0;
     // De-phasing of the store bursts (STORE only).  With equal-length orbits every warp of the GPU
     // completes its staging windows on the same step, so the whole chip alternates between an FP64-only
     // phase (HBM idle) and a store burst (FP64 idle): measured 8.3 ms of arithmetic + 6.3 ms of stores
@@ -297,10 +311,48 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
             }
         }
         // ---- phase B: idle lanes pull the next orbit from the queue
+        do {
+        if (STORE) {
+            // warp-uniform hand-out from the warp's private block of queue positions
+            for (;;) {
+                const bool need = !active && !exhausted && !pending;
+                const unsigned nm = __ballot_sync(FULL, need);
+                if (nm == 0) break;
+                if (wq_next >= wq_end) {
+                    unsigned long long base = 0;
+                    if ((threadIdx.x & 31) == 0) base = atomicAdd(A.queue, 32ull);
+                    base = __shfl_sync(FULL, base, 0);
+                    wq_next = min((int64_t)base, A.n);
+                    wq_end = min((int64_t)base + 32, A.n);
+                }
+                const int avail = (int)(wq_end - wq_next);
+                const int rank = __popc(nm & ((1u << (threadIdx.x & 31)) - 1u));
+                if (need) {
+                    if (avail == 0) {
+                        exhausted = true;
+                    } else if (rank < avail) {
+                        const int64_t p = wq_next + rank;
+                        pend_o = A.order ? (int64_t)A.order[p] : p;
+                        pending = true;
+                        delay = 0;
+                        if (A.status[pend_o] == CW_ORBIT_OK && A.n_nodes[pend_o] > 1)
+                            delay = (int)((A.traj_off[pend_o] - A.traj_base - (int64_t)W) & (2 * TRAJ_S - 1));
+                    }
+                }
+                wq_next += min(__popc(nm), avail);
+            }
+        }
         while (!active && !exhausted) {
-            const int64_t p = queue_pop(A.queue);
-            if (p >= A.n) { exhausted = true; break; }
-            const int64_t o = A.order ? (int64_t)A.order[p] : p;
+            int64_t o;
+            if (STORE) {
+                if (!pending || delay > 0) break;   // nothing handed out yet / not this orbit's start slot yet
+                o = pend_o;
+                pending = false;
+            } else {
+                const int64_t p = queue_pop(A.queue);
+                if (p >= A.n) { exhausted = true; break; }
+                o = A.order ? (int64_t)A.order[p] : p;
+            }
             const int64_t n = A.n;
             s.oid = o;
             s.x = A.w0[o]; s.y = A.w0[n + o]; s.z = A.w0[2 * n + o];
@@ -337,11 +389,12 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
             s.next = (s.e < s.e1) ? A.ev_step[s.e] : s.L;
             active = true;
         }
+        } while (STORE && __any_sync(FULL, !active && !pending && !exhausted));   // rejected orbits: hand out again
         if (STORE) tw.flush_warp(A);   // a first sample can complete a window (column = 7 mod 8)
-        if (!__any_sync(FULL, active)) break;
+        if (!__any_sync(FULL, active || (STORE && pending))) break;
 
         // ---- phase C: a warp-uniform run of steps up to the nearest sync node of any lane
-        int r = active ? (s.next - s.j) : INT_MAX;
+        int r = active ? (s.next - s.j) : ((STORE && pending) ? delay : INT_MAX);
         if (STORE && active) {
             // ... and not past the node that completes this lane's staging window (column = 7 mod 8):
             // inside the run samples are staged without any vote, the completing one at the next phase A
@@ -400,6 +453,10 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
         if (active) {
             s.j += m;
             steps_done += (unsigned long long)m;
+        }
+        if (STORE) {
+            W += m;
+            if (pending) delay -= m;
         }
     }
     if (STORE) traj_tmem_free(tmem_base);

@@ -12,6 +12,10 @@
 // STG.64), so every store instruction writes four full runs = eight full sectors, no partial-sector
 // traffic.  The ragged first / last window of an orbit goes out through the same path, predicated.
 //
+// Lock-step is kept by construction, not by luck: the integrator starts an orbit only on a step of its
+// warp clock W with W = (first column of the orbit) mod 16, so every active lane of a warp always stands
+// on the same column phase, whatever the queue order and however different the orbit lengths are.
+//
 // (Round-1 note: the first version issued per-lane cp.async.bulk (TMA) stores.  UBLKCP is a
 // uniform-datapath instruction, so ptxas serialised the 32 lanes with an R2UR/PLOP3/BRA loop -- 466
 // warp instructions per orbit-step, 2.2 TB/s.  See profiles/r1_ncu_store_all_tma_per_lane_summary.md.)
@@ -92,8 +96,9 @@ struct TrajWriter {
     int n;
     bool want;                // my window is complete and waits for the next cooperative flush
     bool want_last;           // ... and it is the last window of the orbit
-    bool parked;              // warp-uniform: a lower half-line window of every lane sits in TMEM
-    int64_t park_col0;        // its first column
+    bool parked;              // warp-uniform: lower half-line windows of some lanes sit in TMEM
+    bool lane_parked;         // ... and this lane is one of them
+    int64_t park_col0;        // first column of this lane's parked window
     uint32_t taddr;           // this warp's TMEM block (lane quadrant << 16 | first column)
     bool tmem_on;             // TMEM parking enabled
 
@@ -109,7 +114,7 @@ struct TrajWriter {
         row_stride = A.traj_total;
         col0 = 0;
         n = 0;
-        want = want_last = parked = false;
+        want = want_last = parked = lane_parked = false;
         park_col0 = 0;
         taddr = 0;
         tmem_on = false;
@@ -168,6 +173,7 @@ struct TrajWriter {
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         park_col0 = col0;
+        lane_parked = want;     // lanes that had nothing to flush parked garbage: never written back
         parked = true;
     }
 
@@ -183,23 +189,7 @@ struct TrajWriter {
             for (int k = 0; k < TRAJ_S; k++) buf[r * TRAJ_S + k] = __hiloint2double((int)v[2 * k + 1], (int)v[2 * k]);
         }
         *reinterpret_cast<long long *>(reinterpret_cast<unsigned char *>(buf) + TRAJ_DATA_BYTES) =
-            (long long)(park_col0 << 4) | (long long)TRAJ_S;
-        parked = false;
-    }
-
-    // TMEM -> global with this lane's own 8-byte stores (rare: the warp fell out of lock-step while parked)
-    __device__ __forceinline__ void unpark_direct()
-    {
-#pragma unroll
-        for (int r = 0; r < TRAJ_ROWS; r++) {
-            uint32_t v[16];
-            tmem_ld16(taddr + 16 * r, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            double *dst = (r < 3 ? dst_pos - (threadIdx.x & 7) + (int64_t)r * row_stride
-                                 : dst_vel - (threadIdx.x & 7) + (int64_t)(r - 3) * row_stride) + park_col0;
-#pragma unroll
-            for (int k = 0; k < TRAJ_S; k++) dst[k] = __hiloint2double((int)v[2 * k + 1], (int)v[2 * k]);
-        }
+            (long long)(park_col0 << 4) | (long long)(lane_parked ? TRAJ_S : 0);
         parked = false;
     }
 
@@ -228,68 +218,66 @@ struct TrajWriter {
         }
     }
 
+    // The same sweep for ANY subset of lanes and ragged windows (first / last window of an orbit, lanes
+    // that are idle or waiting for their start slot): `mask` = source lanes that flush, each window's
+    // extent comes from its header.  Eight trips whatever the mask, four 64-byte runs per store instruction.
+    __device__ __forceinline__ void store_windows_masked(int lane, unsigned mask)
+    {
+        const int q = lane >> 3, slot = lane & 7;
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const int l = 4 * g + q;
+            if ((mask >> l) & 1u) {
+                const unsigned char *sl = warp_base + (size_t)l * TRAJ_LANE_BYTES;
+                const long long h = *reinterpret_cast<const long long *>(sl + TRAJ_DATA_BYTES);
+                const long long c0 = h >> 4;
+                const int cnt = (int)(h & 15);
+                const int s0 = (int)(c0 & (TRAJ_S - 1));
+                if (slot >= s0 && slot < s0 + cnt) {
+                    const double *rowbuf = reinterpret_cast<const double *>(sl) + slot;
+                    double *dp = dst_pos + (c0 - s0), *dv = dst_vel + (c0 - s0);
+#pragma unroll
+                    for (int r = 0; r < 3; r++) {
+                        dp[r * row_stride] = rowbuf[r * TRAJ_S];
+                        dv[r * row_stride] = rowbuf[(3 + r) * TRAJ_S];
+                    }
+                }
+            }
+        }
+    }
+
     // Warp-convergent: every lane of the warp must call this together.  Returns true if any window was
     // completed (warp-uniform).
     __device__ __forceinline__ bool flush_warp(const IntegArgs &A)
     {
-        unsigned m = __ballot_sync(0xffffffffu, want);
+        const unsigned FULL = 0xffffffffu;
+        const unsigned m = __ballot_sync(FULL, want);
         if (m == 0) return false;
         __syncwarp();                       // the staged samples / headers of the other lanes are visible
         const int lane = threadIdx.x & 31;
-        const int q = lane >> 3, slot = lane & 7;
-        const bool lockstep = (m == 0xffffffffu) && __all_sync(0xffffffffu, n == TRAJ_S);
-        if (lockstep && tmem_on && !parked &&
-            __all_sync(0xffffffffu, (col0 & (2 * TRAJ_S - 1)) == 0 && !want_last)) {
-            // lower half of a 128-byte line everywhere and no orbit ends here: park it, write nothing
-            park();
+        // a complete window on the lower half of a 128-byte line, not the last of its orbit, can wait in TMEM
+        const bool parkable = want && n == TRAJ_S && (col0 & (2 * TRAJ_S - 1)) == 0 && !want_last;
+        if (tmem_on && !parked && __ballot_sync(FULL, parkable) == m) {
+            park();                         // every flushing lane parks; nothing is written
 #ifdef CW_TRAJ_DEBUG
             if (lane == 0) atomicAdd(A.stats + 0, 1ull);
 #endif
         } else {
+            const bool lockstep = (m == FULL) && __all_sync(FULL, n == TRAJ_S);
 #ifdef CW_TRAJ_DEBUG
             if (lane == 0) atomicAdd(A.stats + (lockstep ? 2 : 1), lockstep ? 1ull : (unsigned long long)(__popc(m) + 1000000ull));
 #endif
-            if (lockstep) {
-                store_all_windows(lane);
-            } else {
-                while (m) {
-                    // up to four flushing source lanes per trip, one per 8-lane group
-                    int l = -1;
-                    unsigned mm = m;
-                    for (int k = 0; k < 4; k++) {
-                        const int cand = mm ? (__ffs(mm) - 1) : -1;
-                        if (mm) mm &= mm - 1;
-                        if (k == q) l = cand;
-                    }
-                    m = mm;
-                    if (l >= 0) {
-                        const unsigned char *sl = warp_base + (size_t)l * TRAJ_LANE_BYTES;
-                        const long long h = *reinterpret_cast<const long long *>(sl + TRAJ_DATA_BYTES);
-                        const long long c0 = h >> 4;
-                        const int cnt = (int)(h & 15);
-                        const int s0 = (int)(c0 & (TRAJ_S - 1));
-                        if (slot >= s0 && slot < s0 + cnt) {
-                            const double *rowbuf = reinterpret_cast<const double *>(sl) + slot;
-                            double *dp = dst_pos + (c0 - s0), *dv = dst_vel + (c0 - s0);
-#pragma unroll
-                            for (int r = 0; r < 3; r++) {
-                                dp[r * row_stride] = rowbuf[r * TRAJ_S];
-                                dv[r * row_stride] = rowbuf[(3 + r) * TRAJ_S];
-                            }
-                        }
-                    }
-                }
-            }
+            if (lockstep) store_all_windows(lane);
+            else store_windows_masked(lane, m);
             if (parked) {
                 // the parked lower halves follow immediately, so both halves of every line meet in L2
-                if (lockstep) {
-                    __syncwarp();           // the rows just written out are free again
-                    unpark_to_smem();
-                    __syncwarp();
-                    store_all_windows(lane);
-                } else {
-                    unpark_direct();
-                }
+                const unsigned pm = __ballot_sync(FULL, lane_parked);
+                __syncwarp();               // the rows just written out are free again
+                unpark_to_smem();
+                __syncwarp();
+                if (pm == FULL) store_all_windows(lane);
+                else store_windows_masked(lane, pm);
+                lane_parked = false;
             }
         }
         __syncwarp();                       // rows may be overwritten by their owners from here on

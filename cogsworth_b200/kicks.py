@@ -57,10 +57,21 @@ def get_kick_differential(delta_v_sys_x, delta_v_sys_y, delta_v_sys_z, phase=Non
     return np.array([v_X, v_Y, v_Z], dtype=np.float64)
 
 
-def resolve_integrator(integrator):
+#: How ``gi.DOPRI853Integrator`` is executed when the caller does not say: "restart" = a fresh
+#: dop853() on every grid interval (gala's classic dop853_integrate_hamiltonian), "dense" = one call
+#: per segment with Hairer's continuous extension at the grid nodes.  Per call:
+#: ``integrator="dop853_dense"`` or ``integrator_kwargs={"dense_output": True}``.
+DOP853_MODE = "restart"
+
+
+def resolve_integrator(integrator, integrator_kwargs=None):
     """Map a gala Integrator class / instance / name onto the kernel id (pop.py:130, kicks.py:54)."""
+    dense = (integrator_kwargs or {}).get("dense_output")
+    if dense is None:
+        dense = DOP853_MODE == "dense"
+    dop = _lib.DOP853_DENSE if dense else _lib.DOP853
     if integrator is None:
-        return _lib.DOP853
+        return dop
     if isinstance(integrator, (int, np.integer)):
         return int(integrator)
     name = integrator if isinstance(integrator, str) else getattr(integrator, "__name__", type(integrator).__name__)
@@ -68,7 +79,11 @@ def resolve_integrator(integrator):
     if "leapfrog" in name:
         return _lib.LEAPFROG
     if "dop" in name or "853" in name:
-        return _lib.DOP853
+        if "dense" in name:
+            return _lib.DOP853_DENSE
+        if "restart" in name:
+            return _lib.DOP853
+        return dop
     raise NotImplementedError(f"integrator {integrator!r} has no sm_100a kernel (Leapfrog, DOPRI853 only)")
 
 
@@ -106,7 +121,7 @@ def integrate_orbits(batch: OrbitBatch, potential=None, store_all=True, integrat
     potential = MilkyWayPotential("v2") if potential is None else potential
     ctx = _context(potential, context)
     kw = dict(integrator_kwargs or {})
-    integ = resolve_integrator(integrator)
+    integ = resolve_integrator(integrator, kw)
     common = dict(integrator=integ, atol=kw.get("atol", 1e-10), rtol=kw.get("rtol", 1e-10),
                   nmax=kw.get("nmax", 0) or 0)
 

@@ -45,7 +45,10 @@ enum {
 /* integrators = the two gala Integrator classes cogsworth passes (pop.py:130, kicks.py:54) */
 enum {
     CW_LEAPFROG = 0, /* gi.LeapfrogIntegrator : fixed-step KDK, 1 gradient per grid interval */
-    CW_DOP853 = 1    /* gi.DOPRI853Integrator : Hairer dop853 restarted on every grid interval */
+    CW_DOP853 = 1,   /* gi.DOPRI853Integrator : Hairer dop853 restarted on every grid interval */
+    CW_DOP853_DENSE = 2 /* gi.DOPRI853Integrator, dense-output form: ONE dop853 call per segment between
+                           kicks (h0 = t[1]-t[0], hmax = the segment), grid nodes inside a step evaluated with
+                           Hairer's continuous extension contd8; the segment's end state is the integrator's own */
 };
 
 /* per-orbit grid flags */
@@ -85,7 +88,7 @@ typedef struct cw_ctx cw_ctx;
 
 /* Options of one integrate call = the static arguments of pop._init_pool (pop.py:2187-2194). */
 typedef struct cw_opts {
-    int32_t integrator; /* CW_LEAPFROG | CW_DOP853 */
+    int32_t integrator; /* CW_LEAPFROG | CW_DOP853 | CW_DOP853_DENSE */
     int32_t mem_space;  /* CW_MEM_HOST | CW_MEM_DEVICE */
     double atol;        /* integrator_kwargs["atol"], gala default 1e-10 (DOP853 only) */
     double rtol;        /* integrator_kwargs["rtol"], gala default 1e-10 */

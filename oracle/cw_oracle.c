@@ -49,7 +49,8 @@
 #define CWO_COMP_NFW 3
 
 #define CWO_LEAPFROG 0
-#define CWO_DOP853 1
+#define CWO_DOP853 1        /* restarted on every grid interval */
+#define CWO_DOP853_DENSE 2  /* one call per segment, dense output at the grid nodes */
 
 #define CWO_FLAG_APPEND_T2 1
 
@@ -225,10 +226,17 @@ static double max_d(double a, double b) { return (a > b) ? a : b; }
  * itoler=0 (scalar tolerances), iout=0, uround/safe/fac1/fac2/beta/hmax = 0 -> defaults,
  * h = dt0 (non-zero so hinit is skipped), meth=0 -> 1, nstiff=1, no dense output.
  * Integrates y from x to xend in place.  Returns 1 on success or a negative Hairer code. */
-int cwo_dop853(const cwo_potential *P, double x, double *y, double xend, double rtol, double atol,
-               double h, int64_t nmax, cwo_stats *st)
+/* Dense output (iout = 2, contd8): when nout > 0, the solution at every requested time
+ * tout[j] (ascending in the direction of integration, all inside (x, xend)) is evaluated with
+ * Hairer's 7th-order continuous extension of the step that contains it and written to
+ * out[c * stride + j].  The three extra stages (c14, c15, c16) do not feed back into y, so they
+ * are only evaluated for steps that contain an output time. */
+static int dop853_core(const cwo_potential *P, double x, double *y, double xend, double rtol, double atol,
+                       double h, int64_t nmax, cwo_stats *st,
+                       const double *tout, int64_t nout, double *out, int64_t stride)
 {
     const int n = NEQ;
+    int64_t jout = 0;
     double k1[NEQ], k2[NEQ], k3[NEQ], k4[NEQ], k5[NEQ], k6[NEQ], k7[NEQ], k8[NEQ], k9[NEQ], k10[NEQ];
     double yy1[NEQ];
     /* dop853(): defaults */
@@ -333,6 +341,43 @@ int cwo_dop853(const cwo_potential *P, double x, double *y, double xend, double 
                     if (nonsti == 6) iasti = 0;
                 }
             }
+            /* dense output: dop853.c "final preparation for dense output" + contd8 */
+            if (jout < nout && (tout[jout] - xph) * posneg <= 0.0) {
+                double rc[8][NEQ], ka[NEQ], kb[NEQ], kc[NEQ];
+                for (i = 0; i < n; i++) {
+                    double ydiff = k5[i] - y[i];
+                    double bspl = h * k1[i] - ydiff;
+                    rc[0][i] = y[i];
+                    rc[1][i] = ydiff;
+                    rc[2][i] = bspl;
+                    rc[3][i] = ydiff - h * k4[i] - bspl;
+                    rc[4][i] = CW_D401 * k1[i] + CW_D406 * k6[i] + CW_D407 * k7[i] + CW_D408 * k8[i] + CW_D409 * k9[i] + CW_D410 * k10[i] + CW_D411 * k2[i] + CW_D412 * k3[i];
+                    rc[5][i] = CW_D501 * k1[i] + CW_D506 * k6[i] + CW_D507 * k7[i] + CW_D508 * k8[i] + CW_D509 * k9[i] + CW_D510 * k10[i] + CW_D511 * k2[i] + CW_D512 * k3[i];
+                    rc[6][i] = CW_D601 * k1[i] + CW_D606 * k6[i] + CW_D607 * k7[i] + CW_D608 * k8[i] + CW_D609 * k9[i] + CW_D610 * k10[i] + CW_D611 * k2[i] + CW_D612 * k3[i];
+                    rc[7][i] = CW_D701 * k1[i] + CW_D706 * k6[i] + CW_D707 * k7[i] + CW_D708 * k8[i] + CW_D709 * k9[i] + CW_D710 * k10[i] + CW_D711 * k2[i] + CW_D712 * k3[i];
+                }
+                /* the next three function evaluations (k4 = f(x+h, y_new) is stage 13) */
+                for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A1401 * k1[i] + CW_A1407 * k7[i] + CW_A1408 * k8[i] + CW_A1409 * k9[i] + CW_A1410 * k10[i] + CW_A1411 * k2[i] + CW_A1412 * k3[i] + CW_A1413 * k4[i]);
+                fcn(P, yy1, ka);
+                for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A1501 * k1[i] + CW_A1506 * k6[i] + CW_A1507 * k7[i] + CW_A1508 * k8[i] + CW_A1511 * k2[i] + CW_A1512 * k3[i] + CW_A1513 * k4[i] + CW_A1514 * ka[i]);
+                fcn(P, yy1, kb);
+                for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A1601 * k1[i] + CW_A1606 * k6[i] + CW_A1607 * k7[i] + CW_A1608 * k8[i] + CW_A1609 * k9[i] + CW_A1613 * k4[i] + CW_A1614 * ka[i] + CW_A1615 * kb[i]);
+                fcn(P, yy1, kc);
+                nfcn += 3;
+                for (i = 0; i < n; i++) {
+                    rc[4][i] = h * (rc[4][i] + CW_D413 * k4[i] + CW_D414 * ka[i] + CW_D415 * kb[i] + CW_D416 * kc[i]);
+                    rc[5][i] = h * (rc[5][i] + CW_D513 * k4[i] + CW_D514 * ka[i] + CW_D515 * kb[i] + CW_D516 * kc[i]);
+                    rc[6][i] = h * (rc[6][i] + CW_D613 * k4[i] + CW_D614 * ka[i] + CW_D615 * kb[i] + CW_D616 * kc[i]);
+                    rc[7][i] = h * (rc[7][i] + CW_D713 * k4[i] + CW_D714 * ka[i] + CW_D715 * kb[i] + CW_D716 * kc[i]);
+                }
+                /* solout: every requested time inside (xold, x], contd8 */
+                while (jout < nout && (tout[jout] - xph) * posneg <= 0.0) {
+                    double s = (tout[jout] - x) / h, s1 = 1.0 - s;
+                    for (i = 0; i < n; i++)
+                        out[i * stride + jout] = rc[0][i] + s * (rc[1][i] + s1 * (rc[2][i] + s * (rc[3][i] + s1 * (rc[4][i] + s * (rc[5][i] + s1 * (rc[6][i] + s * rc[7][i]))))));
+                    jout++;
+                }
+            }
             memcpy(k1, k4, n * sizeof(double));
             memcpy(y, k5, n * sizeof(double));
             x = xph;
@@ -352,6 +397,38 @@ int cwo_dop853(const cwo_potential *P, double x, double *y, double xend, double 
         }
         h = hnew;
     }
+}
+
+int cwo_dop853(const cwo_potential *P, double x, double *y, double xend, double rtol, double atol,
+               double h, int64_t nmax, cwo_stats *st)
+{
+    return dop853_core(P, x, y, xend, rtol, atol, h, nmax, st, NULL, 0, NULL, 0);
+}
+
+/* one dop853() call with dense output at tout[0..nout-1] (exposed for the interpolant tests) */
+int cwo_dop853_dense(const cwo_potential *P, double x, double *y, double xend, double rtol, double atol,
+                     double h, int64_t nmax, cwo_stats *st, const double *tout, int64_t nout, double *out,
+                     int64_t stride)
+{
+    return dop853_core(P, x, y, xend, rtol, atol, h, nmax, st, tout, nout, out, stride);
+}
+
+/* DENSE-OUTPUT variant of dop853_integrate_hamiltonian (newer gala releases
+ * evaluate the requested times with Hairer's continuous extension instead of stopping the
+ * integrator on every one): ONE dop853() call from t[0] to t[nt-1], h = t[1]-t[0],
+ * hmax = t[nt-1]-t[0], nmax steps for the whole segment; interior samples by contd8, the last
+ * sample is the integrator's own end state. */
+int cwo_dop853_dense_segment(const cwo_potential *P, double *w, const double *t, int64_t nt,
+                             double rtol, double atol, int64_t nmax, double *out, int64_t stride,
+                             cwo_stats *st)
+{
+    if (out) for (int c = 0; c < 6; c++) out[c * stride] = w[c];
+    if (nt < 2) return CWO_OK;
+    int res = dop853_core(P, t[0], w, t[nt - 1], rtol, atol, t[1] - t[0], nmax, st,
+                          out ? t + 1 : NULL, out ? nt - 2 : 0, out ? out + 1 : NULL, stride);
+    if (res < 0) return res;
+    if (out) for (int c = 0; c < 6; c++) out[c * stride + nt - 1] = w[c];
+    return CWO_OK;
 }
 
 /* dop853.pyx dop853_integrate_hamiltonian for one orbit over t[0..nt-1] (Myr):
@@ -379,6 +456,7 @@ static int integrate_segment(const cwo_potential *P, int integrator, double rtol
                              double *out, int64_t stride, cwo_stats *st)
 {
     if (integrator == CWO_LEAPFROG) { cwo_leapfrog(P, w, tmyr, nt, out, stride); return CWO_OK; }
+    if (integrator == CWO_DOP853_DENSE) return cwo_dop853_dense_segment(P, w, tmyr, nt, rtol, atol, nmax, out, stride, st);
     return cwo_dop853_segment(P, w, tmyr, nt, rtol, atol, nmax, out, stride, st);
 }
 

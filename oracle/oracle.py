@@ -14,12 +14,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 MAX_COMP = 16
-LEAPFROG, DOP853 = 0, 1
+LEAPFROG, DOP853, DOP853_DENSE = 0, 1, 2
 FLAG_APPEND_T2 = 1
 
 __all__ = ["build", "lib", "make_potential", "gradient", "value", "circular_velocity", "time_grid",
-           "leapfrog", "dop853", "integrate_orbit", "integrate_batch", "max_threads",
-           "LEAPFROG", "DOP853", "FLAG_APPEND_T2"]
+           "leapfrog", "dop853", "dop853_dense", "integrate_orbit", "integrate_batch", "max_threads",
+           "LEAPFROG", "DOP853", "DOP853_DENSE", "FLAG_APPEND_T2"]
 
 
 class _Pot(C.Structure):
@@ -58,9 +58,14 @@ def lib():
         L.cwo_dop853.argtypes = [C.POINTER(_Pot), C.c_double, dp, C.c_double, C.c_double, C.c_double,
                                  C.c_double, C.c_int64, C.POINTER(_Stats)]
         L.cwo_dop853.restype = C.c_int
+        L.cwo_dop853_dense.argtypes = [C.POINTER(_Pot), C.c_double, dp, C.c_double, C.c_double, C.c_double,
+                                       C.c_double, C.c_int64, C.POINTER(_Stats), dp, C.c_int64, dp, C.c_int64]
+        L.cwo_dop853_dense.restype = C.c_int
         L.cwo_dop853_segment.argtypes = [C.POINTER(_Pot), dp, dp, C.c_int64, C.c_double, C.c_double,
                                          C.c_int64, dp, C.c_int64, C.POINTER(_Stats)]
         L.cwo_dop853_segment.restype = C.c_int
+        L.cwo_dop853_dense_segment.argtypes = L.cwo_dop853_segment.argtypes
+        L.cwo_dop853_dense_segment.restype = C.c_int
         L.cwo_integrate_orbit.argtypes = [
             C.POINTER(_Pot), C.c_int, C.c_double, C.c_double, C.c_int64,
             dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
@@ -148,6 +153,19 @@ def dop853(pot, x, y, xend, rtol=1e-10, atol=1e-10, h=None, nmax=0):
     res = lib().cwo_dop853(C.byref(P), x, _dp(y), xend, rtol, atol, (xend - x) if h is None else h,
                            nmax, C.byref(st))
     return res, y, (st.n_accepted, st.n_rejected, st.n_fcn)
+
+
+def dop853_dense(pot, x, y, xend, tout, rtol=1e-10, atol=1e-10, h=None, nmax=0):
+    """One dop853() call with dense output (contd8) at ``tout`` (inside (x, xend), ascending).
+    Returns (res, y_end, out (6, len(tout)), (accepted, rejected, nfcn))."""
+    P = _as_pot(pot)
+    y = np.array(y, dtype=np.float64)
+    tout = np.ascontiguousarray(tout, dtype=np.float64)
+    out = np.full((6, max(len(tout), 1)), np.nan)
+    st = _Stats()
+    res = lib().cwo_dop853_dense(C.byref(P), x, _dp(y), xend, rtol, atol, (xend - x) if h is None else h,
+                                 nmax, C.byref(st), _dp(tout), len(tout), _dp(out), out.shape[1])
+    return res, y, out[:, :len(tout)], (st.n_accepted, st.n_rejected, st.n_fcn)
 
 
 def integrate_orbit(pot, w0, t1, t2, dt, to_myr=1.0, flags=0, ev_time=None, ev_dv=None,

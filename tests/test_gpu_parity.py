@@ -231,3 +231,55 @@ def test_math_selftest_and_peak(ctx):
     assert st["rsqrt"] < 4e-16 and st["rcp"] < 4e-16 and st["log"] < 1e-15, st
     peak = ctx.measure_fp64_peak(0, 20.0)
     assert 10.0 < peak < 60.0, peak            # B200 FP64: ~37 TFLOP/s
+
+
+def test_dop853_dense_mode(ctx, oracle):
+    """CW_DOP853_DENSE (one dop853 call per segment, contd8 at the grid nodes) against the
+    oracle's dense restatement: bookkeeping bit-exact, same controller (step counts), states within the
+    DOPRI853 tolerance; the final-state run equals the last sample of the store_all run bit for bit; and
+    the dense and restart modes agree with each other to the north_star tolerance."""
+    pop = make_population(300, cfg_id=8, horizon_gyr=0.4)
+    g, o = run_both(ctx, oracle, pop, _lib.DOP853_DENSE)
+    check_bit_exact_bookkeeping(g, o)
+    assert (g["status"] == 0).mean() > 0.98
+    ok = (g["status"] == 0) & (o["status"] == 0)
+    d = rel_diff(g["w_final"][:, ok], o["w_final"][:, ok])
+    assert np.median(d) < 1e-10 and np.quantile(d, 0.9) < 1e-7, np.quantile(d, [0.5, 0.9, 0.99, 1])
+    assert abs(g["stats"][0] - o["stats"][0]) <= 5e-3 * o["stats"][0]
+    if (g["status"] == 0).all():
+        assert g["stats"][3] == int((g["n_nodes"] - 1).sum())
+    # trajectories
+    gs, os_ = run_both(ctx, oracle, pop, _lib.DOP853_DENSE, store_all=True)
+    check_bit_exact_bookkeeping(gs, os_)
+    off = gs["traj_off"]
+    assert np.array_equal(gs["traj_t"], os_["traj_t"]) and not np.isnan(gs["traj_pos"][:, : off[-1]]).any()
+    assert np.array_equal(gs["w_final"], g["w_final"])
+    assert np.array_equal(gs["traj_pos"][:, off[1:] - 1][:, ok], gs["w_final"][:3][:, ok])
+    assert np.array_equal(gs["traj_pos"][:, off[:-1]], pop.batch.w0[:3])
+    dp = np.abs(gs["traj_pos"] - os_["traj_pos"]).max(axis=0)
+    assert np.median(dp) < 1e-9 and np.quantile(dp, 0.95) < 1e-7, np.quantile(dp, [0.5, 0.95, 1])
+    # the two DOPRI853 modes against each other
+    r, _ = run_both(ctx, oracle, pop, _lib.DOP853)
+    both = ok & (r["status"] == 0)
+    dm = rel_diff(g["w_final"][:, both], r["w_final"][:, both])
+    # (the dense form takes steps of several Myr: its global error after 0.4 Gyr at tol 1e-10 is ~1e-8..1e-6,
+    # the restart form's forced 1 Myr steps are far more accurate than the tolerance asks)
+    assert np.median(dm) < 1e-7 and np.quantile(dm, 0.9) < 2e-6, np.quantile(dm, [0.5, 0.9, 1])
+    # dense needs far fewer gradient evaluations for the same tolerance
+    assert g["stats"][2] < 0.6 * r["stats"][2]
+
+
+def test_dop853_dense_large_batch_sorted_queue(ctx, oracle):
+    """Dense mode through the sorted queue (pilot + LPT order) equals the small-batch results bit for bit."""
+    pop = make_population(3000, cfg_id=9, horizon_gyr=0.2)
+    b = pop.batch
+    ctx.set_potential(pop.potential)
+    full = ctx.integrate(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv,
+                         integrator=_lib.DOP853_DENSE, atol=1e-8, rtol=1e-8)
+    assert b.n_orbits >= 4096
+    idx = np.arange(0, b.n_orbits, 37)
+    sub = b.take(idx)
+    part = ctx.integrate(sub.w0, sub.t1, sub.t2, sub.dt, sub.to_myr, sub.flags, sub.ev_off, sub.ev_time, sub.ev_dv,
+                         integrator=_lib.DOP853_DENSE, atol=1e-8, rtol=1e-8)
+    assert np.array_equal(full["w_final"][:, idx], part["w_final"])
+    assert np.array_equal(full["status"][idx], part["status"])

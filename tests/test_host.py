@@ -124,6 +124,17 @@ def test_resolve_integrator():
     assert resolve_integrator(DOPRI853Integrator) == _lib.DOP853
     assert resolve_integrator(None) == _lib.DOP853          # cogsworth default (pop.py:130)
     assert resolve_integrator("leapfrog") == _lib.LEAPFROG
+    # the dense-output form of DOPRI853 is opt-in per call or per process
+    assert resolve_integrator("dop853_dense") == _lib.DOP853_DENSE
+    assert resolve_integrator(DOPRI853Integrator, {"dense_output": True}) == _lib.DOP853_DENSE
+    assert resolve_integrator(LeapfrogIntegrator, {"dense_output": True}) == _lib.LEAPFROG
+    import cogsworth_b200.kicks as kk
+    kk.DOP853_MODE = "dense"
+    try:
+        assert resolve_integrator(None) == _lib.DOP853_DENSE
+        assert resolve_integrator(DOPRI853Integrator, {"dense_output": False}) == _lib.DOP853
+    finally:
+        kk.DOP853_MODE = "restart"
     with pytest.raises(NotImplementedError):
         resolve_integrator(Ruth4Integrator)
 

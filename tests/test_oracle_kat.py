@@ -147,3 +147,107 @@ def test_leapfrog_reversible_and_energy(oracle):
     back = oracle.leapfrog(v2, wf, t, store_all=False)
     back[3:] *= -1
     assert np.abs(back - w0).max() < 1e-10
+
+
+# ---- dense-output DOP853 ("implement both modes") ---------------------------------
+
+def test_dop853_dense_interpolant_matches_scipy(oracle):
+    """Hairer's contd8 (oracle, dop853.c iout = 2) against scipy's independent DOP853 dense output of
+    the SAME step: same tableau rows 14-16 and d4..d7, so the two polynomials agree to rounding."""
+    from scipy.integrate import DOP853
+    v2 = MilkyWayPotential("v2")
+
+    def f(t, y):
+        g = oracle.gradient(v2, y[:3])
+        return np.concatenate([y[3:], -g])
+
+    rng = np.random.default_rng(11)
+    for trial in range(5):
+        y0 = np.array([rng.uniform(2, 12), rng.uniform(-3, 3), rng.uniform(-1, 1),
+                       rng.uniform(-0.1, 0.1), rng.uniform(0.1, 0.25), rng.uniform(-0.05, 0.05)])
+        h = rng.uniform(0.5, 3.0)
+        s = DOP853(f, 10.0, y0, 10.0 + 2 * h, first_step=h, rtol=1e-6, atol=1e-6)
+        s.step()
+        assert s.t == 10.0 + h            # one accepted step of h
+        sol = s.dense_output()
+        th = 10.0 + np.linspace(0.03, 0.97, 12) * h
+        res, y, out, st = oracle.dop853_dense(v2, 10.0, y0, s.t, th, rtol=1e-6, atol=1e-6, h=h)
+        assert res == 1 and st[0] == 1 and st[2] == 2 + 11 + 1 + 3     # 3 extra stages for the interpolant
+        assert np.abs(y - s.y).max() < 1e-14
+        assert np.abs(out - sol(th)).max() < 5e-15 * np.abs(out).max()
+
+
+def test_dop853_dense_tableau_rows():
+    """Rows 14-16 of the extended tableau sum to c14..c16 (0.1, 0.2, 7/9)."""
+    import re
+    txt = open(os.path.join(HERE, "..", "include", "cw_dop853_coeffs.h")).read()
+    vals = {m.group(1): float(m.group(2)) for m in re.finditer(r"#define CW_(\w+) ([-\d.e+]+)", txt)}
+    for i, c in ((14, 0.1), (15, 0.2), (16, 7.0 / 9.0)):
+        row = sum(v for k, v in vals.items() if re.fullmatch(rf"A{i:02d}\d\d", k))
+        assert abs(row - c) < 1e-14 and abs(vals[f"C{i}"] - c) < 1e-15
+    assert sum(1 for k in vals if re.fullmatch(r"D[4-7]\d\d", k)) == 48
+
+
+def test_dop853_dense_vs_restart_and_kat5(oracle):
+    """The two DOPRI853 modes solve the same problem to the same tolerance: trajectories agree to
+    ~1e-8 relative over 0.5 Gyr at rtol = atol = 1e-10 (north_star allows 1e-7), the dense mode needs
+    several times fewer gradient evaluations, and it also reproduces the notebook's printed samples."""
+    v2 = MilkyWayPotential("v2")
+    y0 = np.array([8.0, 0.3, 0.1, 0.01, 0.22, 0.02])
+    r1 = oracle.integrate_orbit(v2, y0, 0.0, 500.0, 1.0, integrator=oracle.DOP853, store_all=True)
+    r2 = oracle.integrate_orbit(v2, y0, 0.0, 500.0, 1.0, integrator=oracle.DOP853_DENSE, store_all=True)
+    assert r1["status"] == 0 and r2["status"] == 0 and r1["n_nodes"] == r2["n_nodes"] == 500
+    assert np.array_equal(r1["t"], r2["t"])
+    # relative to the orbit's own size (|pos|, |vel|), as in the GPU parity tests
+    sp, sv = np.linalg.norm(r1["traj"][:3], axis=0), np.linalg.norm(r1["traj"][3:], axis=0)
+    d = max((np.abs(r1["traj"][:3] - r2["traj"][:3]).max(axis=0) / sp).max(),
+            (np.abs(r1["traj"][3:] - r2["traj"][3:]).max(axis=0) / sv).max())
+    assert d < 1e-7, d
+    assert np.array_equal(r2["traj"][:, -1], r2["w_final"]) and np.array_equal(r2["traj"][:, 0], y0)
+    assert r2["stats"][2] < 0.5 * r1["stats"][2]
+    # final state only == last sample of the stored trajectory, bit for bit (the interpolant never feeds back)
+    r3 = oracle.integrate_orbit(v2, y0, 0.0, 500.0, 1.0, integrator=oracle.DOP853_DENSE, store_all=False)
+    assert np.array_equal(r3["w_final"], r2["w_final"])
+    # KAT-5 through the dense path
+    import ctypes as C
+    P = oracle.make_potential(v2)
+    dp = C.POINTER(C.c_double)
+    for pos, vel, t in ((KATS["KAT5_pos_first3_kpc"], KATS["KAT5_vel_first3_kpc_per_myr"], KATS["KAT4_t_first3_myr"]),
+                        (KATS["KAT5_pos_last3_kpc"], KATS["KAT5_vel_last3_kpc_per_myr"], KATS["KAT4_t_last3_myr"])):
+        w = np.array(pos[0] + vel[0])
+        tt = np.array(t)
+        out = np.empty((6, 3))
+        rc = oracle.lib().cwo_dop853_dense_segment(C.byref(P), w.ctypes.data_as(dp), tt.ctypes.data_as(dp), 3, 1e-10,
+                                                   1e-10, 0, out.ctypes.data_as(dp), 3, None)
+        assert rc == 0
+        exp = np.array([pos[1] + vel[1], pos[2] + vel[2]])
+        assert np.abs(out.T[1:] - exp).max() < 2.5e-8
+
+
+def test_dop853_dense_driver_with_kicks(oracle):
+    """Kick nodes, node counts and the stitched trajectory layout do not depend on the DOPRI853 mode."""
+    from cogsworth_b200.synthetic import make_population
+    pop = make_population(40, cfg_id=7, horizon_gyr=0.15)
+    b = pop.batch
+    kw = dict(ev_off=b.ev_off, ev_time=b.ev_time, ev_dv=b.ev_dv)
+    r0 = oracle.integrate_batch(pop.potential, b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, integrator=oracle.DOP853, **kw)
+    off = np.concatenate([[0], np.cumsum(r0["n_nodes"])]).astype(np.int64)
+    r1 = oracle.integrate_batch(pop.potential, b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, integrator=oracle.DOP853,
+                                traj_off=off, **kw)
+    r2 = oracle.integrate_batch(pop.potential, b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, integrator=oracle.DOP853_DENSE,
+                                traj_off=off, **kw)
+    assert (r1["status"] == 0).all() and (r2["status"] == 0).all()
+    assert np.array_equal(r1["ev_step"], r2["ev_step"]) and np.array_equal(r1["n_nodes"], r2["n_nodes"])
+    assert np.array_equal(r1["traj_t"], r2["traj_t"]) and not np.isnan(r2["traj_pos"]).any()
+    scale = np.abs(r1["traj_pos"]).max()
+    assert np.abs(r1["traj_pos"] - r2["traj_pos"]).max() / scale < 1e-7
+    assert np.array_equal(r2["traj_pos"][:, off[1:] - 1], r2["w_final"][:3])
+    # the sample stored on a kick node carries the kicked velocity in both modes
+    for i in np.flatnonzero(b.ev_off[1:] > b.ev_off[:-1])[:10]:
+        e = b.ev_off[i]
+        k = r2["ev_step"][e]
+        if k == 0:
+            continue
+        j1 = r1["traj_vel"][:, off[i] + k] - r1["traj_vel"][:, off[i] + k - 1]
+        j2 = r2["traj_vel"][:, off[i] + k] - r2["traj_vel"][:, off[i] + k - 1]
+        assert np.abs(j1 - j2).max() < 1e-8 and np.abs(j2).max() > 0
