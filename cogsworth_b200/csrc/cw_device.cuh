@@ -97,7 +97,7 @@ struct PotParams {
     // of the DFMA that uses them; as literals ptxas rebuilds each with two UMOVs inside the hot loop,
     // and on sm_100 every non-FP64 instruction costs half an FP64 issue slot (an FP64 warp instruction
     // holds the dispatch port for 2 cycles; measured, tools/exp/pipe_mix2.cu).
-    double k_ln2_hi, k_ln2_lo, k_2p52, k_c7, k_c6, k_c5, k_c3;
+    double k_ln2_hi, k_ln2_lo, k_2p52, k_c5, k_c3, k_c158;
 };
 
 __host__ __device__ inline void pot_fill_constants(PotParams &P)
@@ -105,46 +105,59 @@ __host__ __device__ inline void pot_fill_constants(PotParams &P)
     P.k_ln2_hi = 6.93147180369123816490e-01;
     P.k_ln2_lo = 1.90821492927058770002e-10;
     P.k_2p52 = 4503601774854144.0;      // 2^52 + 2^31
-    P.k_c7 = 1.0 / 7.0;
-    P.k_c6 = -1.0 / 6.0;
     P.k_c5 = 0.2;
     P.k_c3 = 1.0 / 3.0;
+    P.k_c158 = 1.875;                   // 15/8: second-order coefficient of (1 - e)^-3/2
 }
 
-// Table-driven ln(x), x >= 1 (Tang-style): x = 2^k m, m in [1,2); c_j = 1 + j/128 is the table node
-// nearest to m (j = 0..128), r = m/c_j - 1 (one FMA with the tabulated 1/c_j, |r| <= 2^-8) and
-// ln m = ln c_j + log1p(r), log1p by its degree-7 Taylor polynomial (remainder < 2^-67).
-// The 129 x {1/c_j, -ln(1/c_j)} table (2 KB) sits in shared memory and is filled once per CTA by
-// log_table_init; the look-up is one LDS.128 on the otherwise idle LSU pipe.  1 DADD for k plus
-// 11 FP64-pipe instructions, no MUFU: 7 fewer FP64 instructions than log_fast.
-constexpr int LOG_TABLE_N = 129;
+// Table-driven ln(x), x >= 1 (Tang-style): x = 2^k m, m in [1,2); c_j = 1 + j/1024 is the table node
+// nearest to m (j = 0..1024), r = m/c_j - 1 (one FMA with the tabulated 1/c_j, |r| <= 2^-11) and
+// ln m = ln c_j + log1p(r), log1p by its degree-5 Taylor polynomial (remainder r^6/6 < 2^-57 |r|).
+// The 1025 x {1/c_j, -ln(1/c_j)} table (16 KB) sits in shared memory and is filled once per CTA by
+// log_table_init; the look-up is one LDS.128 on the otherwise idle LSU pipe, addressed through the
+// CTA's 32-bit shared window address (no uniform-register address arithmetic inside the hot loop).
+// 1 DADD for k plus 9 FP64-pipe instructions, no MUFU: 9 fewer FP64 instructions than log_fast.
+// (Round 1 used 128 nodes and degree 7: two more DFMA and two more 64-bit constants per call; every
+// instruction of the leapfrog loop costs issue slots -- FP64 two, anything else one -- and the kernel
+// is exactly issue-bound, so both the DFMAs and the constant loads showed.)
+constexpr int LOG_TABLE_BITS = 10;
+constexpr int LOG_TABLE_N = (1 << LOG_TABLE_BITS) + 1;
 
-__device__ __forceinline__ void log_table_init(double2 *tab)
+struct LogTab {
+    uint32_t s;      // shared-window byte address of the table, 0xffffffff = no table (use log_fast)
+    __device__ __forceinline__ bool on() const { return s != 0xffffffffu; }
+};
+__device__ __forceinline__ LogTab no_log_table() { LogTab t; t.s = 0xffffffffu; return t; }
+
+__device__ __forceinline__ LogTab log_table_init(double2 *tab)
 {
     for (int j = threadIdx.x; j < LOG_TABLE_N; j += blockDim.x) {
-        const double invc = 1.0 / (1.0 + (double)j * 0.0078125);
+        const double invc = 1.0 / (1.0 + (double)j * (1.0 / (double)(1 << LOG_TABLE_BITS)));
         tab[j] = make_double2(invc, -log(invc));      // ln of the c actually used (1/invc)
     }
     __syncthreads();
+    LogTab t;
+    t.s = (uint32_t)__cvta_generic_to_shared(tab);
+    return t;
 }
 
-__device__ __forceinline__ double log_tab(const PotParams &P, double x, const double2 *__restrict__ tab)
+__device__ __forceinline__ double log_tab(const PotParams &P, double x, LogTab tab)
 {
     const int hi = __double2hiint(x);
     const int lo = __double2loint(x);
     const int k = (hi >> 20) - 1023;
-    const int j = (((hi >> 12) & 0xff) + 1) >> 1;                    // nearest of 128 mantissa nodes
+    // byte offset 16 j of node j = round(top LOG_TABLE_BITS+1 mantissa bits / 2): (((hi >> 6) & 0x3ff8) + 8) & ~15
+    const uint32_t addr = ((((uint32_t)hi >> (16 - LOG_TABLE_BITS)) & ((2u << (LOG_TABLE_BITS + 3)) - 8u)) + 8u + tab.s) & ~15u;
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double kd = __hiloint2double(0x43300000, k ^ 0x80000000) - P.k_2p52;
-    const double2 t = tab[j];
-    const double r = fma(m, t.x, -1.0);
-    double q = fma(P.k_c7, r, P.k_c6);
-    q = fma(q, r, P.k_c5);
-    q = fma(q, r, -0.25);
+    double tx, ty;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(addr));
+    const double r = fma(m, tx, -1.0);
+    double q = fma(P.k_c5, r, -0.25);
     q = fma(q, r, P.k_c3);
     q = fma(q, r, -0.5);
     const double lp = fma(r * r, q, r);                              // log1p(r)
-    return fma(kd, P.k_ln2_hi, t.y + fma(kd, P.k_ln2_lo, lp));
+    return fma(kd, P.k_ln2_hi, ty + fma(kd, P.k_ln2_lo, lp));
 }
 
 // Specialised composite: NMN Miyamoto-Nagai terms (+ optionally one shared b), two Hernquist
@@ -153,30 +166,47 @@ __device__ __forceinline__ double log_tab(const PotParams &P, double x, const do
 //   Hernquist:   f = GM / ((r+c)^2 r);                                    g += f q
 //   NFW:         f = GM (ln(1+r/rs) - r/(r+rs)) / r^3;                    g += f q
 template <int NMN, bool SHARED_B>
-__device__ __forceinline__ void force_mw(const PotParams &P, const double2 *__restrict__ ltab,
+__device__ __forceinline__ void force_mw(const PotParams &P, LogTab ltab,
                                          double x, double y, double z, double &Fxy, double &Fz)
 {
     const double R2 = fma(y, y, x * x);
     const double z2 = z * z;
     const double r2 = R2 + z2;
 
-    double fxy = 0.0, fz = 0.0;
+    // One Miyamoto-Nagai term needs f = GM D^-3/2, not D^-1/2 itself, so the third-order correction is
+    // applied to the cube directly: with the seed y ~ D^-1/2 and e = 1 - D y^2,
+    //     D^-3/2 = y^3 (1 - e)^-3/2 = y^3 (1 + e (3/2 + 15/8 e) + O(e^3)),   |e| < 2^-21,
+    // and y^2 serves both e and y^3: 7 FP64 instructions per term instead of 5 (rsqrt) + 3.
+    double fxy, fz;
     if (SHARED_B) {
         // all terms share sqrt(z^2 + b^2): fz = sum f_i (1 + a_i/sz) = fxy + (sum a_i f_i) / sz
         const double q = z2 + P.mn_b2[0];
         const double isz = rsqrt_fast(q);
         const double sz = q * isz;
-        double fa = 0.0;
+        double f[NMN];
 #pragma unroll
         for (int i = 0; i < NMN; i++) {
             const double zd = P.mn_a[i] + sz;
-            const double rs = rsqrt_fast(fma(zd, zd, R2));
-            const double f = (rs * rs) * (P.mn_GM[i] * rs);
-            fxy += f;
-            fa = fma(P.mn_a[i], f, fa);
+            const double D = fma(zd, zd, R2);
+            double y;
+            asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(D));
+            const double y2 = y * y;
+            const double e = fma(-D, y2, 1.0);
+            const double p = fma(P.k_c158, e, 1.5);
+            const double g = y2 * (P.mn_GM[i] * y);
+            f[i] = fma(g * e, p, g);
+        }
+        fxy = f[0];
+        double fa = P.mn_a[0] * f[0];
+#pragma unroll
+        for (int i = 1; i < NMN; i++) {
+            fxy += f[i];
+            fa = fma(P.mn_a[i], f[i], fa);
         }
         fz = fma(isz, fa, fxy);
     } else {
+        fxy = 0.0;
+        fz = 0.0;
 #pragma unroll
         for (int i = 0; i < NMN; i++) {
             const double q = z2 + P.mn_b2[i];
@@ -184,8 +214,9 @@ __device__ __forceinline__ void force_mw(const PotParams &P, const double2 *__re
             const double zd = fma(q, isz, P.mn_a[i]);
             const double rs = rsqrt_fast(fma(zd, zd, R2));
             const double f = (rs * rs) * (P.mn_GM[i] * rs);
-            fxy += f;
-            fz = fma(f, fma(P.mn_a[i], isz, 1.0), fz);
+            fxy = (i == 0) ? f : fxy + f;
+            const double w = fma(P.mn_a[i], isz, 1.0);
+            fz = (i == 0) ? f * w : fma(f, w, fz);
         }
     }
 
@@ -198,7 +229,7 @@ __device__ __forceinline__ void force_mw(const PotParams &P, const double2 *__re
     // NFW
     const double u = r * P.nfw_inv_rs;
     const double w = 1.0 + u;
-    const double lw = ltab ? log_tab(P, w, ltab) : log_fast(w);
+    const double lw = ltab.on() ? log_tab(P, w, ltab) : log_fast(w);
     const double bracket = lw - u * rcp_fast(w);
     const double ir3 = (ir * ir) * ir;
     double fs = h * ir;
@@ -209,7 +240,7 @@ __device__ __forceinline__ void force_mw(const PotParams &P, const double2 *__re
 }
 
 // Generic composite: components in the caller's order.
-__device__ __forceinline__ void force_generic(const PotParams &P, const double2 *__restrict__ ltab,
+__device__ __forceinline__ void force_generic(const PotParams &P, LogTab ltab,
                                               double x, double y, double z, double &Fxy, double &Fz)
 {
     const double R2 = fma(y, y, x * x);
@@ -241,7 +272,7 @@ __device__ __forceinline__ void force_generic(const PotParams &P, const double2 
             } else { // CW_COMP_NFW_SPHERICAL
                 const double u = r * P.p2[i];               // p2 = 1/r_s for NFW
                 const double w = 1.0 + u;
-                const double bracket = (ltab ? log_tab(P, w, ltab) : log_fast(w)) - u * rcp_fast(w);
+                const double bracket = (ltab.on() ? log_tab(P, w, ltab) : log_fast(w)) - u * rcp_fast(w);
                 f = P.GM[i] * ((ir * ir) * ir) * bracket;
             }
             fxy += f;
@@ -255,7 +286,7 @@ __device__ __forceinline__ void force_generic(const PotParams &P, const double2 
 // ltab: the CTA's shared-memory log table (log_table_init), or nullptr to use the table-free log.
 // force<KIND> returns the two scalar factors of the axisymmetric composite: grad = (Fxy x, Fxy y, Fz z).
 template <int KIND>
-__device__ __forceinline__ void force(const PotParams &P, const double2 *__restrict__ ltab,
+__device__ __forceinline__ void force(const PotParams &P, LogTab ltab,
                                       double x, double y, double z, double &Fxy, double &Fz)
 {
     if (KIND == POT_MW_V1) force_mw<1, false>(P, ltab, x, y, z, Fxy, Fz);
@@ -264,7 +295,7 @@ __device__ __forceinline__ void force(const PotParams &P, const double2 *__restr
 }
 
 template <int KIND>
-__device__ __forceinline__ void gradient(const PotParams &P, const double2 *__restrict__ ltab,
+__device__ __forceinline__ void gradient(const PotParams &P, LogTab ltab,
                                          double x, double y, double z,
                                          double &gx, double &gy, double &gz)
 {

@@ -12,8 +12,8 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const __grid_constant__ 
                                                         int64_t n, const double *__restrict__ q,
                                                         double *__restrict__ out)
 {
-    __shared__ double2 ltab[LOG_TABLE_N];
-    log_table_init(ltab);
+    __shared__ double2 ltab_mem[LOG_TABLE_N];
+    const LogTab ltab = log_table_init(ltab_mem);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double x = q[i], y = q[n + i], z = q[2 * n + i];
@@ -82,8 +82,8 @@ cudaError_t launch_dfma_peak(double *sink, int iters, const LaunchCfg &cfg, int 
 // log-uniform sample of the arguments orbits produce (1e-8 .. 1e8; log argument 1 .. 1e4)
 __global__ void __launch_bounds__(256) math_selftest_kernel(int64_t n, double *out3)
 {
-    __shared__ double2 ltab[LOG_TABLE_N];
-    log_table_init(ltab);
+    __shared__ double2 ltab_mem[LOG_TABLE_N];
+    const LogTab ltab = log_table_init(ltab_mem);
     PotParams P;
     pot_fill_constants(P);
     double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;

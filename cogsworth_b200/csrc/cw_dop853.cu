@@ -73,7 +73,7 @@ __device__ __forceinline__ int64_t dp_queue_pop(unsigned long long *queue)
 }
 
 template <int KIND>
-__device__ __forceinline__ void fcn(const PotParams &P, const double2 *__restrict__ ltab, const double *y, double *f)
+__device__ __forceinline__ void fcn(const PotParams &P, LogTab ltab, const double *y, double *f)
 {
     double gx, gy, gz;
     gradient<KIND>(P, ltab, y[0], y[1], y[2], gx, gy, gz);
@@ -138,9 +138,9 @@ __global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant_
                                                           const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
-    __shared__ double2 ltab[LOG_TABLE_N];
+    __shared__ double2 ltab_mem[LOG_TABLE_N];
     extern __shared__ __align__(16) unsigned char traj_smem[];
-    log_table_init(ltab);
+    const LogTab ltab = log_table_init(ltab_mem);
     TrajWriter tw;
     if (STORE && !PILOT) tw.init(traj_smem, A);
     int64_t col_base = 0;

@@ -227,9 +227,9 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                                                             const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
-    __shared__ double2 ltab[LOG_TABLE_N];
+    __shared__ double2 ltab_mem[LOG_TABLE_N];
     extern __shared__ __align__(16) unsigned char traj_smem[];
-    log_table_init(ltab);
+    const LogTab ltab = log_table_init(ltab_mem);
     __shared__ uint32_t tmem_slot;
     uint32_t tmem_base = 0;
     TrajWriter tw;
