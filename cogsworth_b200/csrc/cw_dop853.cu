@@ -43,6 +43,9 @@ namespace cg = cooperative_groups;
 namespace cw {
 
 constexpr int DP_BLOCK = 128;
+#ifndef CW_DP_MINB
+#define CW_DP_MINB 1       // resident CTAs per SM the kernel is compiled for (experiment knob; 1 = no register cap)
+#endif
 
 struct DpLane {
     double y[6];      // state at time x
@@ -134,7 +137,7 @@ __device__ __forceinline__ void dp_begin_interval(const IntegArgs &A, DpLane &s)
 // with one sequential orbit per lane the makespan is max(longest orbit, total work / lanes), and a
 // long orbit started late would leave the whole GPU waiting for a single lane.
 template <int KIND, bool STORE, bool PILOT, bool DENSE>
-__global__ void __launch_bounds__(DP_BLOCK) dop853_kernel(const __grid_constant__ PotParams P,
+__global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __grid_constant__ PotParams P,
                                                           const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
