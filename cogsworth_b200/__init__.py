@@ -10,6 +10,7 @@ from . import constants, potential  # noqa: F401
 from .potential import CompositePotential, MilkyWayPotential, MilkyWayPotential2022  # noqa: F401
 from .batch import EventTable, OrbitBatch, build_orbit_batch  # noqa: F401
 from .orbits import Orbit, OrbitArray  # noqa: F401
+from .orbit_io import load_orbits, save_orbits  # noqa: F401
 from .events import identify_events, identify_event_tables  # noqa: F401
 from .kicks import get_kick_differential, integrate_orbit_with_events, integrate_orbits  # noqa: F401
 from .pop import B200Population, GalacticStageB200, InitialGalaxy, TablePopulation  # noqa: F401

@@ -203,12 +203,19 @@ extern "C" int cw_set_potential(cw_ctx *ctx, double G, int n_comp, const int32_t
     P.G = G;
     for (int i = 0; i < n_comp; i++) {
         const int t = types[i];
-        if (t != CW_COMP_MIYAMOTO_NAGAI && t != CW_COMP_HERNQUIST && t != CW_COMP_NFW_SPHERICAL)
+        if (t < CW_COMP_MIYAMOTO_NAGAI || t > CW_COMP_LOGARITHMIC)
             return fail(ctx, CW_E_UNSUPPORTED, "cw_set_potential: unknown component type");
         P.type[i] = t;
         P.GM[i] = G * params[3 * i + 0];
         P.p1[i] = params[3 * i + 1];
         P.p2[i] = (t == CW_COMP_NFW_SPHERICAL) ? 1.0 / params[3 * i + 1] : params[3 * i + 2];
+        if (t == CW_COMP_PLUMMER || t == CW_COMP_ISOCHRONE) P.p2[i] = params[3 * i + 1] * params[3 * i + 1];  // b^2
+        if (t == CW_COMP_LOGARITHMIC) {
+            if (!(params[3 * i + 2] > 0.0)) return fail(ctx, CW_E_INVALID, "cw_set_potential: logarithmic q3 must be > 0");
+            P.GM[i] = params[3 * i + 0] * params[3 * i + 0];                 // v_c^2
+            P.p1[i] = params[3 * i + 1] * params[3 * i + 1];                 // r_h^2
+            P.p2[i] = 1.0 / (params[3 * i + 2] * params[3 * i + 2]);         // 1 / q3^2
+        }
     }
     // recognise the two Milky Way shapes that have specialised kernels
     auto is = [&](int i, int t) { return i < n_comp && types[i] == t; };

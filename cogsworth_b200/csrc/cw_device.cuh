@@ -266,9 +266,27 @@ __device__ __forceinline__ void force_generic(const PotParams &P, LogTab ltab,
                 have_r = true;
             }
             double f;
+            if (t == CW_COMP_LOGARITHMIC) {                 // GM = v_c^2, p1 = r_h^2, p2 = 1/q3^2
+                const double inv = P.GM[i] * rcp_fast(fma(z2, P.p2[i], R2 + P.p1[i]));
+                fxy += inv;
+                fz = fma(inv, P.p2[i], fz);
+                continue;
+            }
             if (t == CW_COMP_HERNQUIST) {
                 const double rc = r + P.p1[i];
                 f = P.GM[i] * rcp_fast(rc * rc) * ir;
+            } else if (t == CW_COMP_KEPLER) {
+                f = P.GM[i] * ((ir * ir) * ir);
+            } else if (t == CW_COMP_PLUMMER) {              // p2 = b^2
+                const double is = rsqrt_fast(r2 + P.p2[i]);
+                f = P.GM[i] * ((is * is) * is);
+            } else if (t == CW_COMP_ISOCHRONE) {            // p1 = b, p2 = b^2
+                const double s2 = r2 + P.p2[i];
+                const double is = rsqrt_fast(s2);
+                const double sb = fma(s2, is, P.p1[i]);
+                f = P.GM[i] * is * rcp_fast(sb * sb);
+            } else if (t == CW_COMP_JAFFE) {
+                f = P.GM[i] * (ir * ir) * rcp_fast(r + P.p1[i]);
             } else { // CW_COMP_NFW_SPHERICAL
                 const double u = r * P.p2[i];               // p2 = 1/r_s for NFW
                 const double w = 1.0 + u;
@@ -329,6 +347,16 @@ __device__ __forceinline__ double potential_value(const PotParams &P, double x, 
             v -= P.GM[i] / sqrt(fma(zd, zd, R2));
         } else if (t == CW_COMP_HERNQUIST) {
             v -= P.GM[i] / (r + P.p1[i]);
+        } else if (t == CW_COMP_KEPLER) {
+            v -= P.GM[i] / r;
+        } else if (t == CW_COMP_PLUMMER) {
+            v -= P.GM[i] / sqrt(R2 + z2 + P.p2[i]);
+        } else if (t == CW_COMP_ISOCHRONE) {
+            v -= P.GM[i] / (sqrt(R2 + z2 + P.p2[i]) + P.p1[i]);
+        } else if (t == CW_COMP_JAFFE) {
+            v += P.GM[i] / P.p1[i] * log(r / (r + P.p1[i]));
+        } else if (t == CW_COMP_LOGARITHMIC) {
+            v += 0.5 * P.GM[i] * log(fma(z2, P.p2[i], R2 + P.p1[i]));
         } else {
             const double u = r / P.p1[i];
             v -= (P.GM[i] / P.p1[i]) * log(1.0 + u) / u;

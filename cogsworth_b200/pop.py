@@ -142,6 +142,21 @@ class GalacticStageB200:
         self._final_pos, self._final_vel = fp, fv
         return fp, fv
 
+    def save_orbits(self, file_name):
+        """The ``orbits`` group of ``Population.save`` (pop.py:1853-1876), straight from the SoA buffers."""
+        from .orbit_io import save_orbits
+        orbits = self.orbits
+        if not isinstance(orbits, OrbitArray):
+            raise TypeError("save_orbits writes the OrbitArray produced by perform_galactic_evolution")
+        save_orbits(file_name, orbits)
+
+    def load_orbits(self, file_name):
+        """Lazy counterpart of the ``orbits`` property's load branch (pop.py:696-719)."""
+        from .orbit_io import final_coords_from_file, load_orbits
+        self._orbits = load_orbits(file_name)
+        self._final_pos, self._final_vel = final_coords_from_file(file_name)
+        return self._orbits
+
     @property
     def primary_orbits(self):
         return self.orbits[:len(self)]

@@ -22,9 +22,17 @@ from .constants import G_GALACTIC
 COMP_MIYAMOTO_NAGAI = 1   # params (m, a, b)
 COMP_HERNQUIST = 2        # params (m, c, -)
 COMP_NFW_SPHERICAL = 3    # params (m, r_s, -)
+# further gala builtins a user can put into a CompositePotential (generic kernel; SURVEY 8f N4,
+# reference online-interface/potentials.py:93-131)
+COMP_KEPLER = 4           # params (m, -, -)
+COMP_PLUMMER = 5          # params (m, b, -)
+COMP_ISOCHRONE = 6        # params (m, b, -)
+COMP_JAFFE = 7            # params (m, c, -)
+COMP_LOGARITHMIC = 8      # params (v_c [kpc/Myr], r_h, q3), q1 = q2 = 1
 
 _COMP_NAMES = {COMP_MIYAMOTO_NAGAI: "MiyamotoNagai", COMP_HERNQUIST: "Hernquist",
-               COMP_NFW_SPHERICAL: "NFW"}
+               COMP_NFW_SPHERICAL: "NFW", COMP_KEPLER: "Kepler", COMP_PLUMMER: "Plummer",
+               COMP_ISOCHRONE: "Isochrone", COMP_JAFFE: "Jaffe", COMP_LOGARITHMIC: "Logarithmic"}
 
 # Smith+2015 three-Miyamoto-Nagai fit to an exponential disk, positive-density variant
 # (the table gala's MN3ExponentialDiskPotential uses with positive_density=True).
@@ -126,8 +134,20 @@ def from_gala(potential) -> CompositePotential:
             names.append(name); types.append(COMP_HERNQUIST); params.append((p["m"], p["c"], 0.0))
         elif cls == "NFWPotential" and all(abs(p.get(k, 1.0) - 1.0) < 1e-12 for k in ("a", "b", "c")):
             names.append(name); types.append(COMP_NFW_SPHERICAL); params.append((p["m"], p["r_s"], 0.0))
+        elif cls == "KeplerPotential":
+            names.append(name); types.append(COMP_KEPLER); params.append((p["m"], 0.0, 0.0))
+        elif cls == "PlummerPotential":
+            names.append(name); types.append(COMP_PLUMMER); params.append((p["m"], p["b"], 0.0))
+        elif cls == "IsochronePotential":
+            names.append(name); types.append(COMP_ISOCHRONE); params.append((p["m"], p["b"], 0.0))
+        elif cls == "JaffePotential":
+            names.append(name); types.append(COMP_JAFFE); params.append((p["m"], p["c"], 0.0))
+        elif (cls == "LogarithmicPotential" and abs(p.get("q1", 1.0) - 1.0) < 1e-12
+              and abs(p.get("q2", 1.0) - 1.0) < 1e-12):
+            names.append(name); types.append(COMP_LOGARITHMIC); params.append((p["v_c"], p["r_h"], p.get("q3", 1.0)))
         else:
             raise NotImplementedError(
                 f"component {name!r} ({cls}) has no sm_100a kernel; supported: MiyamotoNagai, "
-                "MN3ExponentialDisk, Hernquist, spherical NFW")
+                "MN3ExponentialDisk, Hernquist, spherical NFW, Kepler, Plummer, Isochrone, Jaffe, "
+                "axisymmetric Logarithmic")
     return CompositePotential(names=names, types=types, params=params, G=G, label=type(potential).__name__)

@@ -38,6 +38,18 @@ def _host_circular_velocity(pot: CompositePotential, x, y, z):
             qdotg += f * (x * x + y * y) + f * z * z * (1.0 + a / sz)
         elif t == 2:
             qdotg += GM / ((r + a) ** 2 * r) * r * r
+        elif t == 4:
+            qdotg += GM / r
+        elif t == 5:
+            qdotg += GM * (r * r + a * a) ** -1.5 * r * r
+        elif t == 6:
+            s = np.sqrt(r * r + a * a)
+            qdotg += GM / (s * (s + a) ** 2) * r * r
+        elif t == 7:
+            qdotg += GM / (r + a)
+        elif t == 8:                                     # (v_c, r_h, q3)
+            fac = m * m / (a * a + x * x + y * y + z * z / (b * b))
+            qdotg += fac * (x * x + y * y) + fac * z * z / (b * b)
         else:
             u = r / a
             qdotg += GM / a / (u ** 3) / (a * a) * (np.log(1 + u) - u / (1 + u)) * r * r

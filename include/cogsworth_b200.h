@@ -39,7 +39,13 @@ extern "C" {
 enum {
     CW_COMP_MIYAMOTO_NAGAI = 1, /* (m [Msun], a [kpc], b [kpc])  -- MN3ExponentialDisk = three of these */
     CW_COMP_HERNQUIST = 2,      /* (m, c, unused) */
-    CW_COMP_NFW_SPHERICAL = 3   /* (m, r_s, unused) */
+    CW_COMP_NFW_SPHERICAL = 3,  /* (m, r_s, unused) */
+    /* further spherical / axisymmetric gala builtins for user-supplied CompositePotentials (generic kernel) */
+    CW_COMP_KEPLER = 4,         /* (m, unused, unused) */
+    CW_COMP_PLUMMER = 5,        /* (m, b, unused) */
+    CW_COMP_ISOCHRONE = 6,      /* (m, b, unused) */
+    CW_COMP_JAFFE = 7,          /* (m, c, unused) */
+    CW_COMP_LOGARITHMIC = 8     /* (v_c [kpc/Myr], r_h, q3) with q1 = q2 = 1 */
 };
 
 /* integrators = the two gala Integrator classes cogsworth passes (pop.py:130, kicks.py:54) */

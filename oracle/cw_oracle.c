@@ -47,6 +47,11 @@
 #define CWO_COMP_MN 1
 #define CWO_COMP_HERNQUIST 2
 #define CWO_COMP_NFW 3
+#define CWO_COMP_KEPLER 4       /* (m, -, -) */
+#define CWO_COMP_PLUMMER 5      /* (m, b, -) */
+#define CWO_COMP_ISOCHRONE 6    /* (m, b, -) */
+#define CWO_COMP_JAFFE 7        /* (m, c, -) */
+#define CWO_COMP_LOGARITHMIC 8  /* (v_c, r_h, q3) with q1 = q2 = 1 (axisymmetric) */
 
 #define CWO_LEAPFROG 0
 #define CWO_DOP853 1        /* restarted on every grid interval */
@@ -108,6 +113,39 @@ static void nfw_gradient(double G, const double *p, const double *q, double *gra
     grad[2] = grad[2] + fac * q[2];
 }
 
+/* The remaining spherical / axisymmetric builtins a cogsworth user can put into a CompositePotential
+ * (online-interface/potentials.py:93-131), restated from builtin_potentials.c [gala-recall]:
+ *   kepler_gradient      fac = G m / r^3
+ *   plummer_gradient     fac = G m / (r^2 + b^2)^1.5
+ *   isochrone_gradient   fac = G m / (s (s + b)^2),  s = sqrt(r^2 + b^2)
+ *   jaffe_gradient       fac = G m / (r^2 (r + c))          [Phi = G m / c ln(r / (r + c))]
+ *   logarithmic_gradient fac = v_c^2 / (r_h^2 + x^2/q1^2 + y^2/q2^2 + z^2/q3^2), grad_i = fac q_i / q_i^2
+ *                        (only q1 = q2 = 1: the kernels factor the gradient as (Fxy x, Fxy y, Fz z)) */
+static void extra_gradient(int type, double G, const double *p, const double *q, double *grad)
+{
+    double r2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+    double fxy, fz;
+    if (type == CWO_COMP_KEPLER) {
+        double R = sqrt(r2);
+        fxy = fz = G * p[0] / (R * R * R);
+    } else if (type == CWO_COMP_PLUMMER) {
+        fxy = fz = G * p[0] / pow(r2 + p[1] * p[1], 1.5);
+    } else if (type == CWO_COMP_ISOCHRONE) {
+        double s = sqrt(r2 + p[1] * p[1]);
+        fxy = fz = G * p[0] / (s * (s + p[1]) * (s + p[1]));
+    } else if (type == CWO_COMP_JAFFE) {
+        double R = sqrt(r2);
+        fxy = fz = G * p[0] / (R * R * (R + p[1]));
+    } else { /* CWO_COMP_LOGARITHMIC */
+        double fac = p[0] * p[0] / (p[1] * p[1] + q[0] * q[0] + q[1] * q[1] + q[2] * q[2] / (p[2] * p[2]));
+        fxy = fac;
+        fz = fac / (p[2] * p[2]);
+    }
+    grad[0] = grad[0] + fxy * q[0];
+    grad[1] = grad[1] + fxy * q[1];
+    grad[2] = grad[2] + fz * q[2];
+}
+
 /* cpotential.c: c_gradient -- zero, then accumulate components in order */
 void cwo_gradient(const cwo_potential *P, const double *q, double *grad)
 {
@@ -117,6 +155,8 @@ void cwo_gradient(const cwo_potential *P, const double *q, double *grad)
         case CWO_COMP_MN: mn_gradient(P->G, P->p[i], q, grad); break;
         case CWO_COMP_HERNQUIST: hernquist_gradient(P->G, P->p[i], q, grad); break;
         case CWO_COMP_NFW: nfw_gradient(P->G, P->p[i], q, grad); break;
+        case CWO_COMP_KEPLER: case CWO_COMP_PLUMMER: case CWO_COMP_ISOCHRONE: case CWO_COMP_JAFFE:
+        case CWO_COMP_LOGARITHMIC: extra_gradient(P->type[i], P->G, P->p[i], q, grad); break;
         default: grad[0] = grad[1] = grad[2] = NAN;
         }
     }
@@ -138,6 +178,15 @@ double cwo_value(const cwo_potential *P, const double *q)
             double u = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]) / p[1];
             double v_h2 = -P->G * p[0] / p[1];
             v += v_h2 * log(1 + u) / u;
+        } else if (P->type[i] >= CWO_COMP_KEPLER && P->type[i] <= CWO_COMP_LOGARITHMIC) {
+            double r2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2], R = sqrt(r2);
+            switch (P->type[i]) {
+            case CWO_COMP_KEPLER: v += -P->G * p[0] / R; break;
+            case CWO_COMP_PLUMMER: v += -P->G * p[0] / sqrt(r2 + p[1] * p[1]); break;
+            case CWO_COMP_ISOCHRONE: v += -P->G * p[0] / (sqrt(r2 + p[1] * p[1]) + p[1]); break;
+            case CWO_COMP_JAFFE: v += P->G * p[0] / p[1] * log(R / (R + p[1])); break;
+            default: v += 0.5 * p[0] * p[0] * log(p[1] * p[1] + q[0] * q[0] + q[1] * q[1] + q[2] * q[2] / (p[2] * p[2]));
+            }
         } else v = NAN;
     }
     return v;

@@ -190,6 +190,31 @@ def test_generic_composite_kernel(ctx, oracle):
         assert np.quantile(d, 0.95) < tol, np.quantile(d, [0.5, 0.95, 1])
 
 
+def test_generic_kernel_extra_components(ctx, oracle):
+    """Kepler, Plummer, Isochrone, Jaffe and the axisymmetric Logarithmic halo through the generic kernel
+    (gradient, value, v_circ pointwise; leapfrog and both DOPRI853 forms with kicks)."""
+    pot = CompositePotential(names=["disk", "bh", "bulge", "iso", "jaffe", "halo"], types=[1, 4, 5, 6, 7, 8],
+                             params=[(5e10, 3.0, 0.28), (4e6, 0.0, 0.0), (6e9, 0.6, 0.0), (8e9, 1.5, 0.0),
+                                     (2e10, 4.0, 0.0), (0.19, 8.0, 0.85)])
+    ctx.set_potential(pot)
+    rng = np.random.default_rng(12)
+    q = rng.normal(0, 7, (3, 2048))
+    g = ctx.gradient(q)
+    phi = ctx.potential_value(q)
+    vc = ctx.circular_velocity(q)
+    for i in range(0, 2048, 16):
+        go = oracle.gradient(pot, q[:, i].copy())
+        assert np.allclose(g[:, i], go, rtol=1e-13, atol=1e-18)
+        assert abs(phi[i] - oracle.value(pot, q[:, i].copy())) < 1e-13 * abs(phi[i])
+        assert abs(vc[i] - oracle.circular_velocity(pot, q[:, i].copy())) < 1e-13 * vc[i]
+    pop = make_population(200, cfg_id=13, potential=pot, horizon_gyr=0.25)
+    for integ, tol in ((_lib.LEAPFROG, 1e-10), (_lib.DOP853, 1e-7), (_lib.DOP853_DENSE, 1e-7)):
+        g_, o_ = run_both(ctx, oracle, pop, integ)
+        check_bit_exact_bookkeeping(g_, o_)
+        d = rel_diff(g_["w_final"], o_["w_final"])
+        assert np.quantile(d, 0.9) < tol, (integ, np.quantile(d, [0.5, 0.9, 1]))
+
+
 def test_pointwise_potential_and_kat1(ctx, oracle):
     v2 = MilkyWayPotential("v2")
     ctx.set_potential(v2)

@@ -209,3 +209,45 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle", txt, flags=re.M), f
                 assert "libcw_oracle" not in txt and "cwo_" not in txt, f
+
+
+def test_orbit_wire_format_roundtrip(tmp_path):
+    """orbits/{offsets,pos,vel,t} (pop.py:1853-1876): pos kpc, vel km/s, t Myr; load is lazy and the final
+    coordinates come from the last column of every orbit (pop.py:715-718)."""
+    from cogsworth_b200 import constants as K
+    from cogsworth_b200.orbit_io import final_coords_from_file, load_orbits, save_orbits
+    from cogsworth_b200.orbits import OrbitArray
+    rng = np.random.default_rng(0)
+    lens = np.array([5, 1, 9, 3])
+    off = np.concatenate([[0], np.cumsum(lens)])
+    pos, vel, t = rng.normal(size=(3, off[-1])), rng.normal(size=(3, off[-1])) * 0.2, np.arange(off[-1], dtype=float)
+    oa = OrbitArray(off, pos, vel, t)
+    f = str(tmp_path / "pop.npz")
+    np.savez(f, numeric_params=np.arange(3))            # an existing population file keeps its other keys
+    save_orbits(f, oa)
+    with np.load(f) as z:
+        assert set(z.files) == {"numeric_params", "orbits/offsets", "orbits/pos", "orbits/vel", "orbits/t"}
+        assert np.array_equal(z["orbits/offsets"], off) and z["orbits/pos"].shape == (3, off[-1])
+        assert np.allclose(z["orbits/vel"], vel * K.KMS_PER_KPC_MYR, rtol=1e-15)
+    back = load_orbits(f)
+    assert len(back) == 4 and np.array_equal(back.lengths(), lens)
+    assert np.array_equal(back.pos, pos) and np.allclose(back.vel, vel, rtol=1e-15) and np.array_equal(back.t, t)
+    o2 = back[2]
+    assert o2.shape == (9,) and np.array_equal(o2.pos.xyz, pos[:, off[2]:off[3]])
+    fp, fv = final_coords_from_file(f)
+    fp2, fv2 = oa.final_coords()
+    assert np.array_equal(fp, fp2) and np.allclose(fv, fv2, rtol=1e-15)
+    # a masked selection is written compacted, in order (primary_orbits / secondary_orbits style slicing)
+    save_orbits(f, oa[np.array([True, False, True, False])])
+    assert np.array_equal(load_orbits(f).lengths(), [5, 9])
+    # failed orbits cannot be represented (the reference drops them before saving)
+    bad = OrbitArray(off, pos, vel, t, ok=np.array([True, False, True, True]))
+    with pytest.raises(ValueError):
+        save_orbits(f, bad)
+    with pytest.raises(ValueError):
+        load_orbits(str(tmp_path / "pop.npz").replace("pop", "other")) if False else save_orbits(str(tmp_path / "x.bin"), oa)
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            save_orbits(str(tmp_path / "pop.h5"), oa)

@@ -134,6 +134,30 @@ def test_gradient_against_numpy_and_finite_difference(oracle):
             assert np.allclose(g, fd, rtol=2e-6, atol=1e-12)
 
 
+def test_extra_components_gradient_is_derivative_of_value(oracle):
+    """Kepler / Plummer / Isochrone / Jaffe / axisymmetric Logarithmic: the restated gradients
+    are the derivatives of the restated potential values, alone and inside a composite."""
+    from cogsworth_b200.potential import CompositePotential
+    singles = [(4, (3e10, 0.0, 0.0)), (5, (2e10, 1.3, 0.0)), (6, (5e10, 2.1, 0.0)), (7, (4e10, 3.0, 0.0)),
+               (8, (0.2, 1.5, 0.8))]
+    pots = [CompositePotential(names=["c"], types=[t], params=[p]) for t, p in singles]
+    pots.append(CompositePotential(names=list("abcdefg"), types=[1, 4, 5, 6, 7, 8, 3],
+                                   params=[(5e10, 3.0, 0.3)] + [p for _, p in singles] + [(5e11, 16.0, 0.0)]))
+    rng = np.random.default_rng(3)
+    for pot in pots:
+        for _ in range(30):
+            q = rng.normal(0, 5, 3)
+            g = oracle.gradient(pot, q)
+            h = 1e-5
+            fd = np.array([(oracle.value(pot, q + h * e) - oracle.value(pot, q - h * e)) / (2 * h) for e in np.eye(3)])
+            assert np.allclose(g, fd, rtol=5e-6, atol=1e-12), (pot.types, q, g, fd)
+    # closed forms: Kepler circular speed, Plummer at r = 0 scale, logarithmic flat rotation curve
+    vk = oracle.circular_velocity(pots[0], [4.0, 0.0, 0.0])
+    assert abs(vk - np.sqrt(pots[0].G * 3e10 / 4.0)) < 1e-15
+    vl = oracle.circular_velocity(pots[4], [400.0, 0.0, 0.0])
+    assert abs(vl - 0.2) < 1e-5
+
+
 def test_leapfrog_reversible_and_energy(oracle):
     v2 = MilkyWayPotential("v2")
     w0 = np.array([8.0, 0.5, 0.1, 0.01, 0.22, 0.02])
