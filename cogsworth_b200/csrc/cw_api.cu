@@ -494,13 +494,30 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
     for (int d = 0; d < nslots; d++) {
         const int64_t a = n * d / nslots, b = n * (d + 1) / nslots;
         const int64_t chunk = dev_mode ? (b - a) : host_chunk(b - a);
+        // The first H2D copy and the last D2H copy have nothing to hide behind: ramp the chunk size up from
+        // chunk/8 at the start and back down at the end (the kernels in between keep the full size).
+        std::vector<int64_t> sizes;
+        if (dev_mode || b - a < 4 * chunk) {
+            for (int64_t c = a; c < b; c += chunk) sizes.push_back(std::min(chunk, b - c));
+        } else {
+            std::vector<int64_t> head, tail;
+            int64_t used = 0;
+            for (int64_t sz = std::max<int64_t>(chunk / 8, HOST_CHUNK_MIN / 2); sz < chunk; sz *= 2) { head.push_back(sz); used += sz; }
+            for (int64_t sz = std::max<int64_t>(chunk / 4, HOST_CHUNK_MIN / 2); sz < chunk; sz *= 2) { tail.push_back(sz); used += sz; }
+            int64_t mid = (b - a) - used;
+            sizes = head;
+            while (mid > 0) { const int64_t sz = std::min(chunk, mid); sizes.push_back(sz); mid -= sz; }
+            for (size_t k = tail.size(); k-- > 0;) sizes.push_back(tail[k]);
+        }
         int lane = 0;
-        for (int64_t c = a; c < b; c += chunk) {
+        int64_t c = a;
+        for (int64_t sz : sizes) {
             Shard sh;
             sh.slot = d;
             sh.lane = dev_mode ? 0 : (lane++ % Slot::N_LANES);
             sh.a = c;
-            sh.b = std::min(b, c + chunk);
+            sh.b = c + sz;
+            c += sz;
             shards.push_back(sh);
         }
     }

@@ -251,7 +251,8 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
     // in column c starts only when W = c (mod 16), so (column of the node a lane stands on) mod 16 is the
     // same for every active lane of the warp at every step: windows fill and flush in lock-step and the
     // lower / upper halves of the 128-byte lines alternate warp-wide.  A popped orbit waits at most 15 steps.
-    int W = 0, delay = 0;
+    unsigned W = 0;        // wraps modulo 2^32, a multiple of 16
+    int delay = 0;
     bool pending = false;
     int64_t pend_o = -1;
     // STORE: the warp takes queue entries in private blocks of 32 CONSECUTIVE positions (one atomic per
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                         pending = true;
                         delay = 0;
                         if (A.status[pend_o] == CW_ORBIT_OK && A.n_nodes[pend_o] > 1)
-                            delay = (int)((A.traj_off[pend_o] - A.traj_base - (int64_t)W) & (2 * TRAJ_S - 1));
+                            delay = (int)((unsigned)(A.traj_off[pend_o] - A.traj_base) - W) & (2 * TRAJ_S - 1);
                     }
                 }
                 wq_next += min(__popc(nm), avail);
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
             steps_done += (unsigned long long)m;
         }
         if (STORE) {
-            W += m;
+            W += (unsigned)m;
             if (pending) delay -= m;
         }
     }
