@@ -150,6 +150,21 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload, scale, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    ncu --set full capture (profiles/ncu_traffic.json).  The capture of a store_all workload was taken at a
+    reduced size (ncu replays need the 48 GB output twice); both kernels' traffic is linear in the number
+    of orbits, so it is scaled to this run's size and the scaling is stated."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))[workload]
+    except Exception:
+        return None, None
+    f = (scale / world) / d["scale"]
+    note = d["source"] + ("" if f == 1.0 else f"; captured at x{d['scale']} of the workload, scaled x{f:g} (traffic is linear in orbits)")
+    return d["dram_bytes_per_launch"] * f, note
+
+
 def cpu_baseline(pop, wl, n_sample, threads=0, repeats=1):
     """The gala-equivalent C oracle on the host cores over a bounded sample of the same workload."""
     import oracle as O
@@ -335,11 +350,14 @@ def main():
     # ---- roofline of the dominant kernel -------------------------------------------------------------
     k_ms = float(np.mean(kernel_ms))
     hbm_peak, hbm_src = measured_peaks()
+    traffic, traffic_src = ncu_traffic(args.workload, args.scale, world if args.scaling == "strong" else 1)
     if wl["store_all"]:
         ach = BYTES_PER_STORED_STEP * steps_per_pass / (k_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "peak_source": hbm_src, "kernel": "leapfrog_kernel<MW_V2,STORE>",
-                "kernel_ms": k_ms, "algorithmic_bytes_per_orbit_step": BYTES_PER_STORED_STEP}
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,
+                "kernel": "leapfrog_kernel<MW_V2,STORE>",
+                "kernel_ms": k_ms, "algorithmic_bytes_per_orbit_step": BYTES_PER_STORED_STEP,
+                "algorithmic_bytes_per_launch": BYTES_PER_STORED_STEP * steps_per_pass}
     else:
         peak = ctx.measure_fp64_peak(0, 200.0)
         if integ == _lib.LEAPFROG:
@@ -351,7 +369,9 @@ def main():
             kname = "dop853_kernel<MW_V2%s>" % (",DENSE" if integ == _lib.DOP853_DENSE else "")
             per = FLOP_PER_STEP["dop853_v2"]
         ach = flops / (k_ms * 1e-3) / 1e12
-        roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+        roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": traffic if integ == _lib.LEAPFROG else None, "traffic_source": traffic_src if integ == _lib.LEAPFROG else None,
+                "algorithmic_bytes_per_launch": float(108 * n + 28 * K),
                 "peak_source": "measured live: DFMA micro-benchmark cw_measure_fp64_peak (MEASURED_PEAKS.json has no "
                                "FP64 entry; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
                 "kernel": kname, "kernel_ms": k_ms, "prepass_sort_pilot_ms": float(np.mean(total_kernel_ms)) - k_ms,
