@@ -308,3 +308,66 @@ def test_dop853_dense_large_batch_sorted_queue(ctx, oracle):
                          integrator=_lib.DOP853_DENSE, atol=1e-8, rtol=1e-8)
     assert np.array_equal(full["w_final"][:, idx], part["w_final"])
     assert np.array_equal(full["status"][idx], part["status"])
+
+
+def test_store_all_ragged_lengths_and_edge_orbits(ctx, oracle):
+    """store_all with every orbit a different length (Wagg2022 horizons: lanes finish at different steps, every
+    column phase occurs, the warp clock delays each start by up to 15 steps) plus degenerate orbits: one- and
+    two-node grids, a kick before the first node, an orbit the pre-pass rejects.  Trajectory layout, time stamps
+    and kick nodes bit-exact against the oracle; samples within the leapfrog tolerance."""
+    pop = make_population(160, cfg_id=21)                      # horizons 0.1 .. 12 Gyr
+    b = pop.batch
+    n0 = b.n_orbits
+    # append hand-made edge orbits (events branch: grid in seconds, t2 appended)
+    S, M = K.SEC_PER_GYR, K.SEC_PER_MYR
+    w = np.array([8.0, 0.1, 0.05, 0.0, 0.22, 0.01])
+    extra = [
+        dict(t1=11.9999 * S, t2=12.0 * S, dt=0.1 * M, ev=[]),                         # 2 nodes (dt == span)
+        dict(t1=11.9 * S, t2=12.0 * S, dt=1.0 * M, ev=[(11.8 * S, (0.01, 0.0, 0.0))]),   # kick before t1 -> node 0
+        dict(t1=11.99 * S, t2=12.0 * S, dt=1.0 * M, ev=[(12.5 * S, (0.01, 0.0, 0.0))]),  # kick after t2 -> rejected
+        dict(t1=12.0 * S, t2=12.0 * S, dt=1.0 * M, ev=[]),                            # empty span -> rejected
+        dict(t1=11.95 * S, t2=12.0 * S, dt=1.0 * M, ev=[(11.96 * S, (0.0, 0.02, 0.0)), (11.96 * S, (0.0, 0.0, 0.02))]),
+    ]
+    ne = len(extra)
+    w0 = np.concatenate([b.w0, np.tile(w[:, None], (1, ne))], axis=1)
+    t1 = np.concatenate([b.t1, [e["t1"] for e in extra]])
+    t2 = np.concatenate([b.t2, [e["t2"] for e in extra]])
+    dt = np.concatenate([b.dt, [e["dt"] for e in extra]])
+    to_myr = np.concatenate([b.to_myr, np.full(ne, K.MYR_PER_SEC)])
+    flags = np.concatenate([b.flags, np.ones(ne, dtype=np.int32)])
+    ev_off = list(b.ev_off)
+    ev_time, ev_dv = list(b.ev_time), [tuple(x) for x in b.ev_dv.reshape(-1, 3)]
+    for e in extra:
+        for te, dv in e["ev"]:
+            ev_time.append(te); ev_dv.append(dv)
+        ev_off.append(len(ev_time))
+    ev_off, ev_time, ev_dv = np.array(ev_off, dtype=np.int64), np.array(ev_time), np.array(ev_dv).reshape(-1, 3)
+    ctx.set_potential(pop.potential)
+    for integ, tol in ((_lib.LEAPFROG, 1e-9), (_lib.DOP853_DENSE, 1e-6)):
+        g = ctx.integrate(w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv, integrator=integ, store_all=True)
+        o = oracle.integrate_batch(pop.potential, w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv,
+                                   integrator=integ, traj_off=g["traj_off"])
+        assert np.array_equal(g["n_nodes"], o["n_nodes"]) and np.array_equal(g["status"], o["status"])
+        assert list(g["status"][n0:]) == [0, 0, -1, -1, 0] and list(g["n_nodes"][n0:n0 + 2]) == [2, 101]
+        ok = g["status"] == 0
+        assert np.array_equal(g["ev_step"][: b.n_events], o["ev_step"][: b.n_events])
+        assert g["ev_step"][b.n_events] == 0                     # the kick before t1 lands on node 0
+        off = g["traj_off"]
+        cols = np.concatenate([np.arange(off[i], off[i + 1]) for i in np.flatnonzero(ok)])
+        assert np.array_equal(g["traj_t"][cols], o["traj_t"][cols])
+        assert not np.isnan(g["traj_pos"][:, cols]).any()
+        dpos = np.abs(g["traj_pos"][:, cols] - o["traj_pos"][:, cols]).max(axis=0)
+        assert np.median(dpos) < 1e-11 if integ == _lib.LEAPFROG else np.median(dpos) < 1e-8
+        assert np.quantile(dpos, 0.9) < tol * 30, np.quantile(dpos, [0.5, 0.9, 0.99, 1])
+        # first sample = (kicked) initial state, last sample = w_final, for every accepted orbit
+        first, last = off[:-1][ok], (off[1:] - 1)[ok]
+        assert np.array_equal(g["traj_pos"][:, first], w0[:3][:, ok])
+        assert np.array_equal(g["traj_pos"][:, last], g["w_final"][:3][:, ok])
+        assert np.array_equal(g["traj_vel"][:, last], g["w_final"][3:][:, ok])
+        # the node-0 kick is in the first stored velocity
+        i = n0 + 1
+        assert abs(g["traj_vel"][0, off[i]] - (w[3] + 0.01)) < 1e-15
+    # an empty batch is a no-op
+    e = ctx.integrate(np.zeros((6, 0)), np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0, dtype=np.int32),
+                      integrator=_lib.LEAPFROG)
+    assert e["w_final"].shape == (6, 0)
