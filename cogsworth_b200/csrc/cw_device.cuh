@@ -16,6 +16,47 @@ namespace cw {
 // these versions are branch-free and cost 5 / 3 / 12-19 FP64-pipe instructions.
 // ------------------------------------------------------------------------------------------
 
+// MUFU.RSQ64H produces only the HIGH word of the seed; `rsqrt.approx.f64` therefore costs a second
+// instruction that zeroes the low word.  The refinement does not care what the low word is (any value
+// perturbs the seed by < 2^-20, and the third-order steps below leave (2^-19)^3 << 2^-53), so the seed is
+// assembled from the MUFU result and the low word of `donor`, a value that dies here: ptxas can then keep
+// the seed in the donor's register pair and the zeroing move disappears (one issue slot per seed).
+__device__ __forceinline__ double rsqrt_seed(double x, double donor)
+{
+#ifdef CW_NO_SEED_DONOR
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+#else
+    double y;
+    asm("{\n\t.reg .b32 dl, dh, yl, yh;\n\t.reg .f64 s;\n\t"
+        "rsqrt.approx.ftz.f64 s, %1;\n\t"
+        "mov.b64 {yl, yh}, s;\n\t"
+        "mov.b64 {dl, dh}, %2;\n\t"
+        "mov.b64 %0, {dl, yh};\n\t}"
+        : "=d"(y) : "d"(x), "d"(donor));
+    return y;
+#endif
+}
+
+__device__ __forceinline__ double rcp_seed(double x, double donor)
+{
+#ifdef CW_NO_SEED_DONOR
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+#else
+    double y;
+    asm("{\n\t.reg .b32 dl, dh, yl, yh;\n\t.reg .f64 s;\n\t"
+        "rcp.approx.ftz.f64 s, %1;\n\t"
+        "mov.b64 {yl, yh}, s;\n\t"
+        "mov.b64 {dl, dh}, %2;\n\t"
+        "mov.b64 %0, {dl, yh};\n\t}"
+        : "=d"(y) : "d"(x), "d"(donor));
+    return y;
+#endif
+}
+
 // 1/sqrt(x), x normal and positive.  Seed (~2^-22 rel. error) + one third-order step:
 // y(1 + e/2 + 3e^2/8), e = 1 - x y^2  -> error O(e^3) plus rounding (<= ~1 ulp).
 __device__ __forceinline__ double rsqrt_fast(double x)
@@ -27,6 +68,25 @@ __device__ __forceinline__ double rsqrt_fast(double x)
     double p = fma(0.375, e, 0.5);
     double q = y * e;
     return fma(q, p, y);
+}
+
+// the same with the seed's low word taken from `donor` (a value that is dead after this call)
+__device__ __forceinline__ double rsqrt_fast(double x, double donor)
+{
+    const double y = rsqrt_seed(x, donor);
+    double t = x * y;
+    double e = fma(-t, y, 1.0);
+    double p = fma(0.375, e, 0.5);
+    double q = y * e;
+    return fma(q, p, y);
+}
+
+__device__ __forceinline__ double rcp_fast(double x, double donor)
+{
+    const double y = rcp_seed(x, donor);
+    double e = fma(-x, y, 1.0);
+    double t = fma(e, e, e);
+    return fma(y, t, y);
 }
 
 // 1/x, x normal.  Seed + one third-order step y(1 + e + e^2), e = 1 - x y.
@@ -188,8 +248,7 @@ __device__ __forceinline__ void force_mw(const PotParams &P, LogTab ltab,
         for (int i = 0; i < NMN; i++) {
             const double zd = P.mn_a[i] + sz;
             const double D = fma(zd, zd, R2);
-            double y;
-            asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(D));
+            const double y = rsqrt_seed(D, zd);            // zd dies here
             const double y2 = y * y;
             const double e = fma(-D, y2, 1.0);
             const double p = fma(P.k_c158, e, 1.5);
@@ -220,17 +279,17 @@ __device__ __forceinline__ void force_mw(const PotParams &P, LogTab ltab,
         }
     }
 
-    const double ir = rsqrt_fast(r2);
+    const double ir = rsqrt_fast(r2, R2);                  // seed donors: values whose last use is here
     const double r = r2 * ir;
     // two Hernquist spheres over one reciprocal: GM0/rc0^2 + GM1/rc1^2 = (GM0 rc1^2 + GM1 rc0^2) / (rc0 rc1)^2
     const double rc0 = r + P.h_c[0], rc1 = r + P.h_c[1];
     const double s0 = rc0 * rc0, s1 = rc1 * rc1;
-    const double h = fma(P.h_GM[1], s0, P.h_GM[0] * s1) * rcp_fast(s0 * s1);
+    const double h = fma(P.h_GM[1], s0, P.h_GM[0] * s1) * rcp_fast(s0 * s1, rc0);
     // NFW
     const double u = r * P.nfw_inv_rs;
     const double w = 1.0 + u;
     const double lw = ltab.on() ? log_tab(P, w, ltab) : log_fast(w);
-    const double bracket = lw - u * rcp_fast(w);
+    const double bracket = lw - u * rcp_fast(w, rc1);
     const double ir3 = (ir * ir) * ir;
     double fs = h * ir;
     fs = fma(P.nfw_GM * ir3, bracket, fs);
