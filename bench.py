@@ -72,7 +72,7 @@ def parse_args():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; marks the line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-orbits", type=int, default=100_000)
+    ap.add_argument("--cpu-sample-orbits", type=int, default=200_000)
     return ap.parse_args()
 
 

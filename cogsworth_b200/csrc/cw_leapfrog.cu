@@ -420,6 +420,11 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 s.vhz = fma(b, s.z, s.vhz);
             }
         } else {
+#ifdef CW_STORE_UNROLL
+#define CW_PRAGMA_(x) _Pragma(#x)
+#define CW_PRAGMA(x) CW_PRAGMA_(x)
+            CW_PRAGMA(unroll CW_STORE_UNROLL)
+#endif
             for (int q = 1; q < m; q++) {   // full steps, every sample staged
                 s.x = fma(s.vhx, dt, s.x);
                 s.y = fma(s.vhy, dt, s.y);
