@@ -7,6 +7,7 @@
 // CW_E_NO_DEVICE.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -607,6 +608,18 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, plans[k].ev_k0, plans[k].ev_k1) == cudaSuccess) s.last_kernel_ms += ms;
             if (cudaEventElapsedTime(&ms, plans[k].ev_t0, plans[k].ev_k1) == cudaSuccess) s.last_total_ms += ms;
+        }
+    }
+    if (getenv("CW_DEBUG") && !shards.empty() && plans[0].timed) {
+        // shard timeline relative to the first shard's first kernel: pre-pass start, integrator start / end
+        for (size_t k = 0; k < shards.size(); k++) {
+            if (shards[k].slot != 0 || !plans[k].timed) continue;
+            float a = 0.f, b = 0.f, c = 0.f;
+            cudaEventElapsedTime(&a, plans[0].ev_t0, plans[k].ev_t0);
+            cudaEventElapsedTime(&b, plans[0].ev_t0, plans[k].ev_k0);
+            cudaEventElapsedTime(&c, plans[0].ev_t0, plans[k].ev_k1);
+            fprintf(stderr, "[cw] shard %2zu lane %d orbits %8lld: prepass %8.3f  kernel %8.3f .. %8.3f ms\n", k,
+                    shards[k].lane, (long long)(shards[k].b - shards[k].a), a, b, c);
         }
     }
     if (integrate && R->stats) {
