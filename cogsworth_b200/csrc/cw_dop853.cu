@@ -42,6 +42,150 @@ namespace cg = cooperative_groups;
 
 namespace cw {
 
+// The tableau lives in constant bank 3: a 64-bit literal costs two UMOVs at every use inside the unrolled
+// stage algebra (220 of them), a constant-bank operand one uniform load.
+__constant__ double k_A0201 = CW_A0201;
+__constant__ double k_A0301 = CW_A0301;
+__constant__ double k_A0302 = CW_A0302;
+__constant__ double k_A0401 = CW_A0401;
+__constant__ double k_A0403 = CW_A0403;
+__constant__ double k_A0501 = CW_A0501;
+__constant__ double k_A0503 = CW_A0503;
+__constant__ double k_A0504 = CW_A0504;
+__constant__ double k_A0601 = CW_A0601;
+__constant__ double k_A0604 = CW_A0604;
+__constant__ double k_A0605 = CW_A0605;
+__constant__ double k_A0701 = CW_A0701;
+__constant__ double k_A0704 = CW_A0704;
+__constant__ double k_A0705 = CW_A0705;
+__constant__ double k_A0706 = CW_A0706;
+__constant__ double k_A0801 = CW_A0801;
+__constant__ double k_A0804 = CW_A0804;
+__constant__ double k_A0805 = CW_A0805;
+__constant__ double k_A0806 = CW_A0806;
+__constant__ double k_A0807 = CW_A0807;
+__constant__ double k_A0901 = CW_A0901;
+__constant__ double k_A0904 = CW_A0904;
+__constant__ double k_A0905 = CW_A0905;
+__constant__ double k_A0906 = CW_A0906;
+__constant__ double k_A0907 = CW_A0907;
+__constant__ double k_A0908 = CW_A0908;
+__constant__ double k_A1001 = CW_A1001;
+__constant__ double k_A1004 = CW_A1004;
+__constant__ double k_A1005 = CW_A1005;
+__constant__ double k_A1006 = CW_A1006;
+__constant__ double k_A1007 = CW_A1007;
+__constant__ double k_A1008 = CW_A1008;
+__constant__ double k_A1009 = CW_A1009;
+__constant__ double k_A1101 = CW_A1101;
+__constant__ double k_A1104 = CW_A1104;
+__constant__ double k_A1105 = CW_A1105;
+__constant__ double k_A1106 = CW_A1106;
+__constant__ double k_A1107 = CW_A1107;
+__constant__ double k_A1108 = CW_A1108;
+__constant__ double k_A1109 = CW_A1109;
+__constant__ double k_A1110 = CW_A1110;
+__constant__ double k_A1201 = CW_A1201;
+__constant__ double k_A1204 = CW_A1204;
+__constant__ double k_A1205 = CW_A1205;
+__constant__ double k_A1206 = CW_A1206;
+__constant__ double k_A1207 = CW_A1207;
+__constant__ double k_A1208 = CW_A1208;
+__constant__ double k_A1209 = CW_A1209;
+__constant__ double k_A1210 = CW_A1210;
+__constant__ double k_A1211 = CW_A1211;
+__constant__ double k_B01 = CW_B01;
+__constant__ double k_B06 = CW_B06;
+__constant__ double k_B07 = CW_B07;
+__constant__ double k_B08 = CW_B08;
+__constant__ double k_B09 = CW_B09;
+__constant__ double k_B10 = CW_B10;
+__constant__ double k_B11 = CW_B11;
+__constant__ double k_B12 = CW_B12;
+__constant__ double k_BHH1 = CW_BHH1;
+__constant__ double k_BHH2 = CW_BHH2;
+__constant__ double k_BHH3 = CW_BHH3;
+__constant__ double k_ER01 = CW_ER01;
+__constant__ double k_ER06 = CW_ER06;
+__constant__ double k_ER07 = CW_ER07;
+__constant__ double k_ER08 = CW_ER08;
+__constant__ double k_ER09 = CW_ER09;
+__constant__ double k_ER10 = CW_ER10;
+__constant__ double k_ER11 = CW_ER11;
+__constant__ double k_ER12 = CW_ER12;
+__constant__ double k_A1401 = CW_A1401;
+__constant__ double k_A1407 = CW_A1407;
+__constant__ double k_A1408 = CW_A1408;
+__constant__ double k_A1409 = CW_A1409;
+__constant__ double k_A1410 = CW_A1410;
+__constant__ double k_A1411 = CW_A1411;
+__constant__ double k_A1412 = CW_A1412;
+__constant__ double k_A1413 = CW_A1413;
+__constant__ double k_A1501 = CW_A1501;
+__constant__ double k_A1506 = CW_A1506;
+__constant__ double k_A1507 = CW_A1507;
+__constant__ double k_A1508 = CW_A1508;
+__constant__ double k_A1511 = CW_A1511;
+__constant__ double k_A1512 = CW_A1512;
+__constant__ double k_A1513 = CW_A1513;
+__constant__ double k_A1514 = CW_A1514;
+__constant__ double k_A1601 = CW_A1601;
+__constant__ double k_A1606 = CW_A1606;
+__constant__ double k_A1607 = CW_A1607;
+__constant__ double k_A1608 = CW_A1608;
+__constant__ double k_A1609 = CW_A1609;
+__constant__ double k_A1613 = CW_A1613;
+__constant__ double k_A1614 = CW_A1614;
+__constant__ double k_A1615 = CW_A1615;
+__constant__ double k_D401 = CW_D401;
+__constant__ double k_D406 = CW_D406;
+__constant__ double k_D407 = CW_D407;
+__constant__ double k_D408 = CW_D408;
+__constant__ double k_D409 = CW_D409;
+__constant__ double k_D410 = CW_D410;
+__constant__ double k_D411 = CW_D411;
+__constant__ double k_D412 = CW_D412;
+__constant__ double k_D413 = CW_D413;
+__constant__ double k_D414 = CW_D414;
+__constant__ double k_D415 = CW_D415;
+__constant__ double k_D416 = CW_D416;
+__constant__ double k_D501 = CW_D501;
+__constant__ double k_D506 = CW_D506;
+__constant__ double k_D507 = CW_D507;
+__constant__ double k_D508 = CW_D508;
+__constant__ double k_D509 = CW_D509;
+__constant__ double k_D510 = CW_D510;
+__constant__ double k_D511 = CW_D511;
+__constant__ double k_D512 = CW_D512;
+__constant__ double k_D513 = CW_D513;
+__constant__ double k_D514 = CW_D514;
+__constant__ double k_D515 = CW_D515;
+__constant__ double k_D516 = CW_D516;
+__constant__ double k_D601 = CW_D601;
+__constant__ double k_D606 = CW_D606;
+__constant__ double k_D607 = CW_D607;
+__constant__ double k_D608 = CW_D608;
+__constant__ double k_D609 = CW_D609;
+__constant__ double k_D610 = CW_D610;
+__constant__ double k_D611 = CW_D611;
+__constant__ double k_D612 = CW_D612;
+__constant__ double k_D613 = CW_D613;
+__constant__ double k_D614 = CW_D614;
+__constant__ double k_D615 = CW_D615;
+__constant__ double k_D616 = CW_D616;
+__constant__ double k_D701 = CW_D701;
+__constant__ double k_D706 = CW_D706;
+__constant__ double k_D707 = CW_D707;
+__constant__ double k_D708 = CW_D708;
+__constant__ double k_D709 = CW_D709;
+__constant__ double k_D710 = CW_D710;
+__constant__ double k_D711 = CW_D711;
+__constant__ double k_D712 = CW_D712;
+__constant__ double k_D713 = CW_D713;
+__constant__ double k_D714 = CW_D714;
+__constant__ double k_D715 = CW_D715;
+__constant__ double k_D716 = CW_D716;
+
 constexpr int DP_BLOCK = 128;
 #ifndef CW_DP_MINB
 #define CW_DP_MINB 1       // resident CTAs per SM the kernel is compiled for (experiment knob; 1 = no register cap)
@@ -282,28 +426,28 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
             double k2[6], k3[6], k4[6], k5[6], k6[6], k7[6], k8[6], k9[6], k10[6], yy1[6];
 
 #define CW_STAGE(EXPR) _Pragma("unroll") for (int i = 0; i < 6; i++) yy1[i] = fma(h, (EXPR), y[i]);
-            CW_STAGE(CW_A0201 * k1[i])
+            CW_STAGE(k_A0201 * k1[i])
             fcn<KIND>(P, ltab, yy1, k2);
-            CW_STAGE(fma(CW_A0302, k2[i], CW_A0301 * k1[i]))
+            CW_STAGE(fma(k_A0302, k2[i], k_A0301 * k1[i]))
             fcn<KIND>(P, ltab, yy1, k3);
-            CW_STAGE(fma(CW_A0403, k3[i], CW_A0401 * k1[i]))
+            CW_STAGE(fma(k_A0403, k3[i], k_A0401 * k1[i]))
             fcn<KIND>(P, ltab, yy1, k4);
-            CW_STAGE(fma(CW_A0504, k4[i], fma(CW_A0503, k3[i], CW_A0501 * k1[i])))
+            CW_STAGE(fma(k_A0504, k4[i], fma(k_A0503, k3[i], k_A0501 * k1[i])))
             fcn<KIND>(P, ltab, yy1, k5);
-            CW_STAGE(fma(CW_A0605, k5[i], fma(CW_A0604, k4[i], CW_A0601 * k1[i])))
+            CW_STAGE(fma(k_A0605, k5[i], fma(k_A0604, k4[i], k_A0601 * k1[i])))
             fcn<KIND>(P, ltab, yy1, k6);
-            CW_STAGE(fma(CW_A0706, k6[i], fma(CW_A0705, k5[i], fma(CW_A0704, k4[i], CW_A0701 * k1[i]))))
+            CW_STAGE(fma(k_A0706, k6[i], fma(k_A0705, k5[i], fma(k_A0704, k4[i], k_A0701 * k1[i]))))
             fcn<KIND>(P, ltab, yy1, k7);
-            CW_STAGE(fma(CW_A0807, k7[i], fma(CW_A0806, k6[i], fma(CW_A0805, k5[i], fma(CW_A0804, k4[i], CW_A0801 * k1[i])))))
+            CW_STAGE(fma(k_A0807, k7[i], fma(k_A0806, k6[i], fma(k_A0805, k5[i], fma(k_A0804, k4[i], k_A0801 * k1[i])))))
             fcn<KIND>(P, ltab, yy1, k8);
-            CW_STAGE(fma(CW_A0908, k8[i], fma(CW_A0907, k7[i], fma(CW_A0906, k6[i], fma(CW_A0905, k5[i], fma(CW_A0904, k4[i], CW_A0901 * k1[i]))))))
+            CW_STAGE(fma(k_A0908, k8[i], fma(k_A0907, k7[i], fma(k_A0906, k6[i], fma(k_A0905, k5[i], fma(k_A0904, k4[i], k_A0901 * k1[i]))))))
             fcn<KIND>(P, ltab, yy1, k9);
-            CW_STAGE(fma(CW_A1009, k9[i], fma(CW_A1008, k8[i], fma(CW_A1007, k7[i], fma(CW_A1006, k6[i], fma(CW_A1005, k5[i], fma(CW_A1004, k4[i], CW_A1001 * k1[i])))))))
+            CW_STAGE(fma(k_A1009, k9[i], fma(k_A1008, k8[i], fma(k_A1007, k7[i], fma(k_A1006, k6[i], fma(k_A1005, k5[i], fma(k_A1004, k4[i], k_A1001 * k1[i])))))))
             fcn<KIND>(P, ltab, yy1, k10);
-            CW_STAGE(fma(CW_A1110, k10[i], fma(CW_A1109, k9[i], fma(CW_A1108, k8[i], fma(CW_A1107, k7[i], fma(CW_A1106, k6[i], fma(CW_A1105, k5[i], fma(CW_A1104, k4[i], CW_A1101 * k1[i]))))))))
+            CW_STAGE(fma(k_A1110, k10[i], fma(k_A1109, k9[i], fma(k_A1108, k8[i], fma(k_A1107, k7[i], fma(k_A1106, k6[i], fma(k_A1105, k5[i], fma(k_A1104, k4[i], k_A1101 * k1[i]))))))))
             fcn<KIND>(P, ltab, yy1, k2);
             const double xph = __dadd_rn(s.x, h);
-            CW_STAGE(fma(CW_A1211, k2[i], fma(CW_A1210, k10[i], fma(CW_A1209, k9[i], fma(CW_A1208, k8[i], fma(CW_A1207, k7[i], fma(CW_A1206, k6[i], fma(CW_A1205, k5[i], fma(CW_A1204, k4[i], CW_A1201 * k1[i])))))))))
+            CW_STAGE(fma(k_A1211, k2[i], fma(k_A1210, k10[i], fma(k_A1209, k9[i], fma(k_A1208, k8[i], fma(k_A1207, k7[i], fma(k_A1206, k6[i], fma(k_A1205, k5[i], fma(k_A1204, k4[i], k_A1201 * k1[i])))))))))
             fcn<KIND>(P, ltab, yy1, k3);
 #undef CW_STAGE
             n_fcn += 11;
@@ -311,32 +455,39 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
             double err = 0.0, err2 = 0.0;
 #pragma unroll
             for (int i = 0; i < 6; i++) {
-                k4[i] = fma(CW_B12, k3[i], fma(CW_B11, k2[i], fma(CW_B10, k10[i], fma(CW_B09, k9[i],
-                        fma(CW_B08, k8[i], fma(CW_B07, k7[i], fma(CW_B06, k6[i], CW_B01 * k1[i])))))));
+                k4[i] = fma(k_B12, k3[i], fma(k_B11, k2[i], fma(k_B10, k10[i], fma(k_B09, k9[i],
+                        fma(k_B08, k8[i], fma(k_B07, k7[i], fma(k_B06, k6[i], k_B01 * k1[i])))))));
                 k5[i] = fma(h, k4[i], y[i]);
                 const double sk = fma(rtol, fmax(fabs(y[i]), fabs(k5[i])), atol);
                 const double isk = rcp_fast(sk);
-                double erri = k4[i] - CW_BHH1 * k1[i] - CW_BHH2 * k9[i] - CW_BHH3 * k3[i];
+                double erri = k4[i] - k_BHH1 * k1[i] - k_BHH2 * k9[i] - k_BHH3 * k3[i];
                 double sq = erri * isk;
                 err2 = fma(sq, sq, err2);
-                erri = fma(CW_ER12, k3[i], fma(CW_ER11, k2[i], fma(CW_ER10, k10[i], fma(CW_ER09, k9[i],
-                       fma(CW_ER08, k8[i], fma(CW_ER07, k7[i], fma(CW_ER06, k6[i], CW_ER01 * k1[i])))))));
+                erri = fma(k_ER12, k3[i], fma(k_ER11, k2[i], fma(k_ER10, k10[i], fma(k_ER09, k9[i],
+                       fma(k_ER08, k8[i], fma(k_ER07, k7[i], fma(k_ER06, k6[i], k_ER01 * k1[i])))))));
                 sq = erri * isk;
                 err = fma(sq, sq, err);
             }
+            // Controller arithmetic on the DFMA pipe with the kernels' own branch-free rsqrt / reciprocal (the
+            // library sqrt / divide carry slow-path branches and ~4x the instructions; a lane's step attempts
+            // are strictly sequential, so every instruction here is on the critical path of the slowest orbit).
             double deno = fma(0.01, err2, err);
-            if (deno <= 0.0) deno = 1.0;
-            err = fabs(h) * err * sqrt(1.0 / (deno * 6.0));
+            if (!(deno > 1.0e-290)) deno = 1.0;            // Hairer: deno <= 0 -> 1 (and keeps the rsqrt seed normal)
+            err = fabs(h) * err * rsqrt_fast(deno * 6.0);
             if (!(err <= 1.79769313486231571e+308)) {   // NaN or inf: Hairer would spin to nmax
                 if (PILOT) A.cost_key[s.oid] = 0;
                 else dp_write_final(A, s, CW_ORBIT_NONFINITE);
                 active = false;
                 continue;
             }
-            const double fac11 = sqrt(sqrt(sqrt(err)));            // err^(1/8), beta = 0
-            const double facc1 = 1.0 / 0.333, facc2 = 1.0 / 6.0, safe = 0.9;
-            const double fac = fmax(facc2, fmin(facc1, fac11 / safe));
-            double hnew = h / fac;
+            // err^(1/8) (beta = 0) by three square roots; below 1e-280 the factor is clamped to facc2 anyway
+            const double e0 = fmax(err, 1.0e-280);
+            const double e1 = e0 * rsqrt_fast(e0);
+            const double e2 = e1 * rsqrt_fast(e1);
+            const double fac11 = e2 * rsqrt_fast(e2);
+            const double facc1 = 1.0 / 0.333, facc2 = 1.0 / 6.0, inv_safe = 1.0 / 0.9;
+            const double fac = fmax(facc2, fmin(facc1, fac11 * inv_safe));
+            double hnew = h * rcp_fast(fac);
             if (err <= 1.0) {
                 // ---- step accepted
                 s.facold = fmax(err, 1.0e-4);
@@ -353,7 +504,9 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
                     const double b = k5[i] - yy1[i];
                     stden = fma(b, b, stden);
                 }
-                if (stden > 0.0) s.hlamb = h * sqrt(stnum / stden);
+                // hlamb = h sqrt(stnum / stden) > 6.1  <=>  h^2 stnum > 37.21 stden  (no root, no divide); hlamb
+                // keeps its previous verdict when stden == 0, as in dopcor
+                if (stden > 0.0) s.hlamb = (h * h * stnum > 37.21 * stden) ? 7.0 : 0.0;
                 bool stiff = false;
                 if (s.hlamb > 6.1) {
                     s.nonsti = 0;
@@ -375,31 +528,31 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
                             rc[1][i] = ydiff;
                             rc[2][i] = bspl;
                             rc[3][i] = ydiff - h * k4[i] - bspl;
-                            rc[4][i] = fma(CW_D412, k3[i], fma(CW_D411, k2[i], fma(CW_D410, k10[i], fma(CW_D409, k9[i], fma(CW_D408, k8[i], fma(CW_D407, k7[i], fma(CW_D406, k6[i], CW_D401 * k1[i])))))));
-                            rc[5][i] = fma(CW_D512, k3[i], fma(CW_D511, k2[i], fma(CW_D510, k10[i], fma(CW_D509, k9[i], fma(CW_D508, k8[i], fma(CW_D507, k7[i], fma(CW_D506, k6[i], CW_D501 * k1[i])))))));
-                            rc[6][i] = fma(CW_D612, k3[i], fma(CW_D611, k2[i], fma(CW_D610, k10[i], fma(CW_D609, k9[i], fma(CW_D608, k8[i], fma(CW_D607, k7[i], fma(CW_D606, k6[i], CW_D601 * k1[i])))))));
-                            rc[7][i] = fma(CW_D712, k3[i], fma(CW_D711, k2[i], fma(CW_D710, k10[i], fma(CW_D709, k9[i], fma(CW_D708, k8[i], fma(CW_D707, k7[i], fma(CW_D706, k6[i], CW_D701 * k1[i])))))));
+                            rc[4][i] = fma(k_D412, k3[i], fma(k_D411, k2[i], fma(k_D410, k10[i], fma(k_D409, k9[i], fma(k_D408, k8[i], fma(k_D407, k7[i], fma(k_D406, k6[i], k_D401 * k1[i])))))));
+                            rc[5][i] = fma(k_D512, k3[i], fma(k_D511, k2[i], fma(k_D510, k10[i], fma(k_D509, k9[i], fma(k_D508, k8[i], fma(k_D507, k7[i], fma(k_D506, k6[i], k_D501 * k1[i])))))));
+                            rc[6][i] = fma(k_D612, k3[i], fma(k_D611, k2[i], fma(k_D610, k10[i], fma(k_D609, k9[i], fma(k_D608, k8[i], fma(k_D607, k7[i], fma(k_D606, k6[i], k_D601 * k1[i])))))));
+                            rc[7][i] = fma(k_D712, k3[i], fma(k_D711, k2[i], fma(k_D710, k10[i], fma(k_D709, k9[i], fma(k_D708, k8[i], fma(k_D707, k7[i], fma(k_D706, k6[i], k_D701 * k1[i])))))));
                         }
                         double yd[6];
 #pragma unroll
                         for (int i = 0; i < 6; i++)
-                            yd[i] = fma(h, fma(CW_A1413, k4[i], fma(CW_A1412, k3[i], fma(CW_A1411, k2[i], fma(CW_A1410, k10[i], fma(CW_A1409, k9[i], fma(CW_A1408, k8[i], fma(CW_A1407, k7[i], CW_A1401 * k1[i]))))))), y[i]);
+                            yd[i] = fma(h, fma(k_A1413, k4[i], fma(k_A1412, k3[i], fma(k_A1411, k2[i], fma(k_A1410, k10[i], fma(k_A1409, k9[i], fma(k_A1408, k8[i], fma(k_A1407, k7[i], k_A1401 * k1[i]))))))), y[i]);
                         fcn<KIND>(P, ltab, yd, ka);
 #pragma unroll
                         for (int i = 0; i < 6; i++)
-                            yd[i] = fma(h, fma(CW_A1514, ka[i], fma(CW_A1513, k4[i], fma(CW_A1512, k3[i], fma(CW_A1511, k2[i], fma(CW_A1508, k8[i], fma(CW_A1507, k7[i], fma(CW_A1506, k6[i], CW_A1501 * k1[i]))))))), y[i]);
+                            yd[i] = fma(h, fma(k_A1514, ka[i], fma(k_A1513, k4[i], fma(k_A1512, k3[i], fma(k_A1511, k2[i], fma(k_A1508, k8[i], fma(k_A1507, k7[i], fma(k_A1506, k6[i], k_A1501 * k1[i]))))))), y[i]);
                         fcn<KIND>(P, ltab, yd, kb);
 #pragma unroll
                         for (int i = 0; i < 6; i++)
-                            yd[i] = fma(h, fma(CW_A1615, kb[i], fma(CW_A1614, ka[i], fma(CW_A1613, k4[i], fma(CW_A1609, k9[i], fma(CW_A1608, k8[i], fma(CW_A1607, k7[i], fma(CW_A1606, k6[i], CW_A1601 * k1[i]))))))), y[i]);
+                            yd[i] = fma(h, fma(k_A1615, kb[i], fma(k_A1614, ka[i], fma(k_A1613, k4[i], fma(k_A1609, k9[i], fma(k_A1608, k8[i], fma(k_A1607, k7[i], fma(k_A1606, k6[i], k_A1601 * k1[i]))))))), y[i]);
                         fcn<KIND>(P, ltab, yd, kc);
                         n_fcn += 3;
 #pragma unroll
                         for (int i = 0; i < 6; i++) {
-                            rc[4][i] = h * fma(CW_D416, kc[i], fma(CW_D415, kb[i], fma(CW_D414, ka[i], fma(CW_D413, k4[i], rc[4][i]))));
-                            rc[5][i] = h * fma(CW_D516, kc[i], fma(CW_D515, kb[i], fma(CW_D514, ka[i], fma(CW_D513, k4[i], rc[5][i]))));
-                            rc[6][i] = h * fma(CW_D616, kc[i], fma(CW_D615, kb[i], fma(CW_D614, ka[i], fma(CW_D613, k4[i], rc[6][i]))));
-                            rc[7][i] = h * fma(CW_D716, kc[i], fma(CW_D715, kb[i], fma(CW_D714, ka[i], fma(CW_D713, k4[i], rc[7][i]))));
+                            rc[4][i] = h * fma(k_D416, kc[i], fma(k_D415, kb[i], fma(k_D414, ka[i], fma(k_D413, k4[i], rc[4][i]))));
+                            rc[5][i] = h * fma(k_D516, kc[i], fma(k_D515, kb[i], fma(k_D514, ka[i], fma(k_D513, k4[i], rc[5][i]))));
+                            rc[6][i] = h * fma(k_D616, kc[i], fma(k_D615, kb[i], fma(k_D614, ka[i], fma(k_D613, k4[i], rc[6][i]))));
+                            rc[7][i] = h * fma(k_D716, kc[i], fma(k_D715, kb[i], fma(k_D714, ka[i], fma(k_D713, k4[i], rc[7][i]))));
                         }
                         dn_xold = s.x;
                         dn_h = h;
@@ -425,7 +578,7 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
                 }
             } else {
                 // ---- step rejected
-                hnew = h / fmin(facc1, fac11 / safe);
+                hnew = h * rcp_fast(fmin(facc1, fac11 * inv_safe));
                 s.reject = true;
                 if (s.naccpt >= 1) n_rej++;
                 s.last = false;
