@@ -157,14 +157,13 @@ struct PotParams {
     // of the DFMA that uses them; as literals ptxas rebuilds each with two UMOVs inside the hot loop,
     // and on sm_100 every non-FP64 instruction costs half an FP64 issue slot (an FP64 warp instruction
     // holds the dispatch port for 2 cycles; measured, tools/exp/pipe_mix2.cu).
-    double k_ln2_hi, k_ln2_lo, k_2p52, k_c5, k_c3, k_c158;
+    double k_ln2_hi, k_ln2_lo, k_c5, k_c3, k_c158;
 };
 
 __host__ __device__ inline void pot_fill_constants(PotParams &P)
 {
     P.k_ln2_hi = 6.93147180369123816490e-01;
     P.k_ln2_lo = 1.90821492927058770002e-10;
-    P.k_2p52 = 4503601774854144.0;      // 2^52 + 2^31
     P.k_c5 = 0.2;
     P.k_c3 = 1.0 / 3.0;
     P.k_c158 = 1.875;                   // 15/8: second-order coefficient of (1 - e)^-3/2
@@ -204,15 +203,16 @@ __device__ __forceinline__ LogTab log_table_init(double2 *tab)
 __device__ __forceinline__ double log_tab(const PotParams &P, double x, LogTab tab)
 {
     const int hi = __double2hiint(x);
-    const int lo = __double2loint(x);
     const int k = (hi >> 20) - 1023;
     // byte offset 16 j of node j = round(top LOG_TABLE_BITS+1 mantissa bits / 2): (((hi >> 6) & 0x3ff8) + 8) & ~15
     const uint32_t addr = ((((uint32_t)hi >> (16 - LOG_TABLE_BITS)) & ((2u << (LOG_TABLE_BITS + 3)) - 8u)) + 8u + tab.s) & ~15u;
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    const double kd = __hiloint2double(0x43300000, k ^ 0x80000000) - P.k_2p52;
+    const double kd = (double)k;                                     // I2F on the XU pipe: one issue slot
     double tx, ty;
     asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tx), "=d"(ty) : "r"(addr));
-    const double r = fma(m, tx, -1.0);
+    // r = m / c_j - 1 with m = x 2^-k: the power of two goes into the exponent of the tabulated 1/c_j (exact),
+    // so the mantissa of x never has to be re-assembled into a register pair of its own
+    const double txs = __hiloint2double(__double2hiint(tx) - (hi & 0x7ff00000) + 0x3ff00000, __double2loint(tx));
+    const double r = fma(x, txs, -1.0);
     double q = fma(P.k_c5, r, -0.25);
     q = fma(q, r, P.k_c3);
     q = fma(q, r, -0.5);
