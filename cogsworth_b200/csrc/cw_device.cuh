@@ -157,13 +157,12 @@ struct PotParams {
     // of the DFMA that uses them; as literals ptxas rebuilds each with two UMOVs inside the hot loop,
     // and on sm_100 every non-FP64 instruction costs half an FP64 issue slot (an FP64 warp instruction
     // holds the dispatch port for 2 cycles; measured, tools/exp/pipe_mix2.cu).
-    double k_ln2_hi, k_ln2_lo, k_c5, k_c3, k_c158;
+    double k_ln2, k_c5, k_c3, k_c158;
 };
 
 __host__ __device__ inline void pot_fill_constants(PotParams &P)
 {
-    P.k_ln2_hi = 6.93147180369123816490e-01;
-    P.k_ln2_lo = 1.90821492927058770002e-10;
+    P.k_ln2 = 6.931471805599453094e-01;
     P.k_c5 = 0.2;
     P.k_c3 = 1.0 / 3.0;
     P.k_c158 = 1.875;                   // 15/8: second-order coefficient of (1 - e)^-3/2
@@ -217,7 +216,9 @@ __device__ __forceinline__ double log_tab(const PotParams &P, double x, LogTab t
     q = fma(q, r, P.k_c3);
     q = fma(q, r, -0.5);
     const double lp = fma(r * r, q, r);                              // log1p(r)
-    return fma(kd, P.k_ln2_hi, ty + fma(kd, P.k_ln2_lo, lp));
+    // k <= 1023 and the result is compared with u / (1 + u) right away: one correctly rounded ln 2 is enough
+    // (k (LN2 - ln 2) < 6e-17 k, relative to k ln 2 + ... below 1e-16); measured by cw_selftest_math
+    return fma(kd, P.k_ln2, ty + lp);
 }
 
 // Specialised composite: NMN Miyamoto-Nagai terms (+ optionally one shared b), two Hernquist
@@ -237,7 +238,8 @@ __device__ __forceinline__ void force_mw(const PotParams &P, LogTab ltab,
     // applied to the cube directly: with the seed y ~ D^-1/2 and e = 1 - D y^2,
     //     D^-3/2 = y^3 (1 - e)^-3/2 = y^3 (1 + e (3/2 + 15/8 e) + O(e^3)),   |e| < 2^-21,
     // and y^2 serves both e and y^3: 7 FP64 instructions per term instead of 5 (rsqrt) + 3.
-    double fxy, fz;
+    // both branches leave fxy and (za, zb) with fz = fxy + za zb, so that Fz = fma(za, zb, Fxy) below
+    double fxy, za, zb;
     if (SHARED_B) {
         // all terms share sqrt(z^2 + b^2): fz = sum f_i (1 + a_i/sz) = fxy + (sum a_i f_i) / sz
         const double q = z2 + P.mn_b2[0];
@@ -262,10 +264,12 @@ __device__ __forceinline__ void force_mw(const PotParams &P, LogTab ltab,
             fxy += f[i];
             fa = fma(P.mn_a[i], f[i], fa);
         }
-        fz = fma(isz, fa, fxy);
+        za = isz;
+        zb = fa;
     } else {
         fxy = 0.0;
-        fz = 0.0;
+        za = 0.0;
+        zb = 1.0;
 #pragma unroll
         for (int i = 0; i < NMN; i++) {
             const double q = z2 + P.mn_b2[i];
@@ -274,8 +278,8 @@ __device__ __forceinline__ void force_mw(const PotParams &P, LogTab ltab,
             const double rs = rsqrt_fast(fma(zd, zd, R2));
             const double f = (rs * rs) * (P.mn_GM[i] * rs);
             fxy = (i == 0) ? f : fxy + f;
-            const double w = fma(P.mn_a[i], isz, 1.0);
-            fz = (i == 0) ? f * w : fma(f, w, fz);
+            const double fa = P.mn_a[i] * f;                 // f_i a_i / sz_i accumulates in za (zb = 1)
+            za = (i == 0) ? fa * isz : fma(fa, isz, za);
         }
     }
 
@@ -290,12 +294,11 @@ __device__ __forceinline__ void force_mw(const PotParams &P, LogTab ltab,
     const double w = 1.0 + u;
     const double lw = ltab.on() ? log_tab(P, w, ltab) : log_fast(w);
     const double bracket = lw - u * rcp_fast(w, rc1);
-    const double ir3 = (ir * ir) * ir;
-    double fs = h * ir;
-    fs = fma(P.nfw_GM * ir3, bracket, fs);
+    // fs = h / r + GM_nfw bracket / r^3 = (h + (GM_nfw / r^2) bracket) / r
+    const double fs = ir * fma(P.nfw_GM * (ir * ir), bracket, h);
 
     Fxy = fxy + fs;     // grad = (Fxy x, Fxy y, Fz z)
-    Fz = fz + fs;
+    Fz = fma(za, zb, Fxy);
 }
 
 // Generic composite: components in the caller's order.
