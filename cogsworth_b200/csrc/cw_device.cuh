@@ -288,12 +288,15 @@ __device__ __forceinline__ void force_mw(const PotParams &P, LogTab ltab,
     // two Hernquist spheres over one reciprocal: GM0/rc0^2 + GM1/rc1^2 = (GM0 rc1^2 + GM1 rc0^2) / (rc0 rc1)^2
     const double rc0 = r + P.h_c[0], rc1 = r + P.h_c[1];
     const double s0 = rc0 * rc0, s1 = rc1 * rc1;
-    const double h = fma(P.h_GM[1], s0, P.h_GM[0] * s1) * rcp_fast(s0 * s1, rc0);
     // NFW
     const double u = r * P.nfw_inv_rs;
     const double w = 1.0 + u;
+    // ... and over the same reciprocal 1 / (s0 s1 w): 1/(s0 s1) = inv w, 1/w = inv s0 s1
+    const double s01 = s0 * s1;
+    const double inv = rcp_fast(s01 * w, rc0);
+    const double h = fma(P.h_GM[1], s0, P.h_GM[0] * s1) * (inv * w);
     const double lw = ltab.on() ? log_tab(P, w, ltab) : log_fast(w);
-    const double bracket = lw - u * rcp_fast(w, rc1);
+    const double bracket = lw - u * (inv * s01);
     // fs = h / r + GM_nfw bracket / r^3 = (h + (GM_nfw / r^2) bracket) / r
     const double fs = ir * fma(P.nfw_GM * (ir * ir), bracket, h);
 
