@@ -79,6 +79,13 @@ def test_config1_leapfrog_v1(ctx, oracle):
     assert np.array_equal(g96["ev_step"], G["cfg1_leapfrog_v1_ev_step"])
     d96 = rel_diff(g96["w_final"], G["cfg1_leapfrog_v1_w_final"])
     assert np.median(d96) < 1e-13 and np.quantile(d96, 0.9) < 1e-10
+    # the frozen DOPRI853 cases (MW v2, same generator), both forms
+    pop96v2 = make_population(96, cfg_id=1, potential=MilkyWayPotential("v2"), horizon_gyr=0.2)
+    for name, integ in (("cfg1_dop853_v2", _lib.DOP853), ("cfg1_dop853dense_v2", _lib.DOP853_DENSE)):
+        gd, _ = run_both(ctx, oracle, pop96v2, integ)
+        assert np.array_equal(gd["ev_step"], G[name + "_ev_step"]) and np.array_equal(gd["n_nodes"], G[name + "_n_nodes"])
+        dd = rel_diff(gd["w_final"], G[name + "_w_final"])
+        assert np.quantile(dd, 0.9) < 1e-7, (name, np.quantile(dd, [0.5, 0.9, 1]))
 
 
 @pytest.mark.parametrize("integ,tol", [(_lib.LEAPFROG, 1e-10), (_lib.DOP853, 1e-7)])

@@ -11,7 +11,8 @@ from cogsworth_b200.synthetic import make_population
 G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_cases.npz"))
 
 
-@pytest.mark.parametrize("name,ver,integ", [("cfg1_leapfrog_v1", "v1", 0), ("cfg1_dop853_v2", "v2", 1)])
+@pytest.mark.parametrize("name,ver,integ", [("cfg1_leapfrog_v1", "v1", 0), ("cfg1_dop853_v2", "v2", 1),
+                                           ("cfg1_dop853dense_v2", "v2", 2)])
 def test_oracle_reproduces_golden(oracle, name, ver, integ):
     pot = MilkyWayPotential(ver)
     b = make_population(96, cfg_id=1, potential=pot, horizon_gyr=0.2).batch

@@ -4,7 +4,8 @@
 These are NOT reference (gala) outputs -- gala cannot run here -- they pin the oracle itself (and
 through it the CUDA path) against drift: tests/test_oracle_golden.py re-runs the oracle against
 them on the CPU, tests/test_gpu_parity.py compares the CUDA path with them on the B200.
-Cases: config 1 (MW v1, leapfrog, 200 x 1 Myr, kicks) and a DOPRI853 / MW v2 variant, 96 binaries.
+Cases: config 1 (MW v1, leapfrog, 200 x 1 Myr, kicks) and DOPRI853 / MW v2 variants in both forms (restart per
+interval, dense output), 96 binaries.
 """
 import os
 import sys
@@ -18,7 +19,8 @@ from cogsworth_b200.potential import MilkyWayPotential  # noqa: E402
 from cogsworth_b200.synthetic import make_population  # noqa: E402
 
 out = {}
-for name, ver, integ in (("cfg1_leapfrog_v1", "v1", O.LEAPFROG), ("cfg1_dop853_v2", "v2", O.DOP853)):
+for name, ver, integ in (("cfg1_leapfrog_v1", "v1", O.LEAPFROG), ("cfg1_dop853_v2", "v2", O.DOP853),
+                         ("cfg1_dop853dense_v2", "v2", O.DOP853_DENSE)):
     pot = MilkyWayPotential(ver)
     pop = make_population(96, cfg_id=1, potential=pot, horizon_gyr=0.2)
     b = pop.batch
