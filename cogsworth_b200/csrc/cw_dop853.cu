@@ -315,7 +315,8 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
         // step passed over are evaluated with contd8, one node per lane per warp-uniform trip
         if (DENSE && STORE && !PILOT) {
             for (;;) {
-                const bool emit = active && pend && (s.j + 1 < s.next) && ((s.tgrid + s.hgrid) * s.smyr <= s.x);
+                const double tnx = (s.tgrid + s.hgrid) * s.smyr;   // next grid node; the grid may run backward in time
+                const bool emit = active && pend && (s.j + 1 < s.next) && ((s.hgrid > 0.0) ? (tnx <= s.x) : (tnx >= s.x));
                 if (!__any_sync(FULL, emit)) break;
                 if (emit) {
                     s.tgrid += s.hgrid;
@@ -518,7 +519,8 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
                 }
                 if (DENSE && STORE && !PILOT) {
                     // a grid node of this segment inside (x, x+h]: dop853.c "final preparation for dense output"
-                    if ((s.j + 1 < s.next) && ((s.tgrid + s.hgrid) * s.smyr <= xph)) {
+                    const double tnx = (s.tgrid + s.hgrid) * s.smyr;
+                    if ((s.j + 1 < s.next) && ((s.hgrid > 0.0) ? (tnx <= xph) : (tnx >= xph))) {
                         double ka[6], kb[6], kc[6];
 #pragma unroll
                         for (int i = 0; i < 6; i++) {

@@ -49,8 +49,20 @@ __global__ void __launch_bounds__(256) grid_prepass_kernel(const __grid_constant
     // One loop, one FP64 compare + one DADD per node on the fast path; the rare branch (an event
     // lands, or the grid ends) sits INSIDE the loop body so the warp reconverges every iteration.
     double lim = fmin(b, te);
-    if (!(h > 0.0)) st = CW_ORBIT_INCONSISTENT;    // gala raises for dt <= 0 with t2 > t1
+    const bool backward = (h < 0.0) && (b < a);    // rewind (cogsworth hydro/rewind.py:16-19): t2 < t1, dt < 0
+    if (!(h > 0.0) && !backward) st = CW_ORBIT_INCONSISTENT;    // gala raises for dt <= 0 with t2 > t1
     bool done = false;
+    if (backward) {
+        // gala's backward grid: nodes while T > t2 (same sequential FP64 accumulation); events never occur on
+        // this branch (kicks.py only integrates forward)
+        while (T > b && j < 1000000) {
+            Tprev = T;
+            j++;
+            T += h;
+        }
+        if (e < e1) st = CW_ORBIT_INCONSISTENT;
+        done = true;
+    }
     while (!done) {
         // 8 nodes per trip while none of them reaches `lim`: the same sequential FP64 additions, but
         // one compare and one branch for eight of them (the add chain is latency-, not pipe-bound).
@@ -89,7 +101,8 @@ __global__ void __launch_bounds__(256) grid_prepass_kernel(const __grid_constant
         }
     }
     const int n_acc = j;
-    const int n_nodes = n_acc + ((append && n_acc > 0) ? 1 : 0);
+    // forward: t2 is appended after the last node < t2; backward: gala appends it unless the last node IS t2
+    const int n_nodes = n_acc + ((append && n_acc > 0 && !(backward && Tprev == b)) ? 1 : 0);
     // events not before any accumulated node boundary: after the last accumulated node
     while (e < e1) {
         int k;

@@ -212,6 +212,26 @@ int64_t cwo_time_grid(double t1, double t2, double dt, int append_t2, double *T,
 {
     int64_t n = 0;
     double t_i = t1, last = t1;
+    if (dt < 0.0 && t2 < t1) {
+        /* backward branch of parse_time_specification [gala-recall]:
+         *     while (t_i > t2) and (ii < 1e6): times.append(t_i); t_i += dt
+         *     if times[-1] != t2: times.append(t2)
+         * gala appends t2 itself here (it does not on the forward branch); the caller asks for it with
+         * `append_t2`, as cogsworth.hydro.rewind._tohspans implies (hydro/rewind.py:16-19). */
+        while (t_i > t2 && n < 1000000) {
+            if (T && n < cap) T[n] = t_i;
+            last = t_i;
+            n++;
+            t_i += dt;
+        }
+        if (n == 0) return 0;
+        if (append_t2 && last != t2) {
+            if (T && n < cap) T[n] = t2;
+            n++;
+        }
+        return n;
+    }
+    if (!(dt > 0.0)) return 0;      /* dt <= 0 with t2 >= t1: gala raises ValueError */
     while (t_i < t2 && n < 1000000) {
         if (T && n < cap) T[n] = t_i;
         last = t_i;
@@ -531,6 +551,7 @@ int cwo_integrate_orbit(const cwo_potential *P, int integrator, double rtol, dou
     int64_t n = cwo_time_grid(t1, t2, dt, flags & CWO_FLAG_APPEND_T2, NULL, 0);
     if (n_nodes) *n_nodes = n;
     if (n <= 0) return CWO_E_INCONSISTENT;
+    if (dt < 0.0 && n_ev > 0) return CWO_E_INCONSISTENT;   /* kicks.py only ever integrates forward */
     if (store_all && cap < n) return CWO_E_CAPACITY;
     double *T = (double *)malloc(sizeof(double) * (size_t)n * 2);
     if (!T) return CWO_E_CAPACITY;

@@ -169,3 +169,36 @@ def test_in_process_multi_device_sharding(built):
     assert np.array_equal(outs[0]["traj_t"], outs[1]["traj_t"])
     assert int(outs[1]["stats"][3]) == int(outs[0]["stats"][3])
     one.close(); many.close()
+
+
+def test_rewind_backward_integration(ctx, oracle):
+    """cogsworth_b200.rewind.rewind_orbits = the batch form of hydro/rewind.py's _tohspans fan-out: every particle
+    integrated from the snapshot time back to its own formation time (dt = -1 Myr, DOPRI853, final state)."""
+    from cogsworth_b200.rewind import rewind_orbits
+    pop = make_population(400, cfg_id=61, f_sn=0.0, horizon_gyr=0.3)
+    b = pop.batch
+    n = b.n_orbits
+    rng = np.random.default_rng(5)
+    t_form = 13000.0 - rng.uniform(5.0, 400.0, n)                       # Myr, ragged spans incl. non-integer ones
+    pos, vel_kms = b.w0[:3], b.w0[3:] * K.KMS_PER_KPC_MYR
+    for integ, o_int, tol in (("dopri853", oracle.DOP853, 1e-7), ("leapfrog", oracle.LEAPFROG, 1e-10),
+                              ("dop853_dense", oracle.DOP853_DENSE, 1e-7)):
+        p0, v0, ok = rewind_orbits(pos, vel_kms, 13000.0, t_form, -1.0, potential=pop.potential, integrator=integ, context=ctx)
+        assert ok.all() and p0.shape == (n, 3)
+        ref = oracle.integrate_batch(pop.potential, b.w0, np.full(n, 13000.0), t_form, np.full(n, -1.0), 1.0, 1,
+                                     integrator=o_int)
+        assert (ref["status"] == 0).all()
+        d = np.maximum(np.abs(p0.T - ref["w_final"][:3]).max(axis=0) / np.linalg.norm(ref["w_final"][:3], axis=0),
+                       np.abs(v0.T / K.KMS_PER_KPC_MYR - ref["w_final"][3:]).max(axis=0) / np.linalg.norm(ref["w_final"][3:], axis=0))
+        assert np.quantile(d, 0.95) < tol, (integ, np.quantile(d, [0.5, 0.95, 1]))
+    # node counts follow gala's backward grid: ceil(span) nodes above t2, plus t2 itself
+    nn, _ = ctx.count_nodes(b.w0, np.full(n, 13000.0), t_form, np.full(n, -1.0), np.ones(n), np.ones(n, dtype=np.int32))
+    assert np.array_equal(nn, np.ceil(13000.0 - t_form).astype(np.int32) + 1)
+    # forward then backward returns to the start (leapfrog is time-reversible)
+    fwd = ctx.integrate(b.w0, np.zeros(n), np.full(n, 200.0), np.ones(n), np.ones(n), np.zeros(n, dtype=np.int32),
+                        integrator=_lib.LEAPFROG)["w_final"]            # gala's own grid: ends on node 199
+    p1, v1, ok = rewind_orbits(fwd[:3], fwd[3:] * K.KMS_PER_KPC_MYR, 199.0, np.zeros(n), -1.0, potential=pop.potential,
+                               integrator="leapfrog", context=ctx)
+    assert np.abs(p1.T - b.w0[:3]).max() < 1e-10
+    with pytest.raises(ValueError):
+        rewind_orbits(pos, vel_kms, 100.0, np.full(n, 200.0), -1.0, potential=pop.potential, context=ctx)

@@ -137,3 +137,26 @@ def test_batch_equals_single_and_threads(oracle):
                                    b.ev_time[e0:e1], b.ev_dv[e0:e1], integrator=oracle.LEAPFROG)
         assert np.array_equal(s["w_final"], r1["w_final"][:, i])
         assert list(s["ev_step"]) == list(r1["ev_step"][e0:e1])
+
+
+def test_backward_grid_and_rewind_roundtrip(oracle):
+    """Backward integration (cogsworth hydro/rewind.py:16-19): gala's backward grid -- nodes
+    while T > t2, then t2 itself -- and forward-then-backward round trips with both integrators."""
+    from cogsworth_b200.potential import MilkyWayPotential
+    T = oracle.time_grid(1000.0, 990.5, -1.0, True)
+    assert len(T) == 11 and T[0] == 1000.0 and T[-2] == 991.0 and T[-1] == 990.5
+    T = oracle.time_grid(1000.0, 990.0, -1.0, True)
+    assert len(T) == 11 and T[-1] == 990.0 and T[-2] == 991.0       # t2 is appended, never duplicated
+    assert len(oracle.time_grid(1000.0, 990.0, -1.0, False)) == 10
+    assert len(oracle.time_grid(0.0, 10.0, -1.0, True)) == 0         # dt < 0 with t2 > t1: gala raises
+    assert len(oracle.time_grid(10.0, 0.0, 1.0, True)) == 0          # dt > 0 with t2 < t1: gala raises
+    v2 = MilkyWayPotential("v2")
+    w = np.array([8.0, 0.3, 0.1, 0.01, 0.22, 0.02])
+    for integ, tol in ((oracle.LEAPFROG, 1e-13), (oracle.DOP853, 1e-11), (oracle.DOP853_DENSE, 1e-6)):   # dense: global error of the larger steps
+        f = oracle.integrate_orbit(v2, w, 0.0, 300.0, 1.0, integrator=integ)          # ends on node 299
+        b = oracle.integrate_orbit(v2, f["w_final"], 299.0, 0.0, -1.0, flags=1, integrator=integ)
+        assert b["status"] == 0 and b["n_nodes"] == 300
+        assert np.abs(b["w_final"] - w).max() < tol, (integ, np.abs(b["w_final"] - w).max())
+    # events never occur on a backward grid
+    r = oracle.integrate_orbit(v2, w, 299.0, 0.0, -1.0, flags=1, ev_time=[100.0], ev_dv=[[0.01, 0.0, 0.0]])
+    assert r["status"] == -1
