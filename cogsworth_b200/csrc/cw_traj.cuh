@@ -177,20 +177,25 @@ struct TrajWriter {
         parked = true;
     }
 
-    // TMEM -> own rows + header (warp-convergent); the caller then flushes them like a fresh window
-    __device__ __forceinline__ void unpark_to_smem()
+    // TMEM -> own rows + header, for the lanes with `mine` set; the caller then flushes them like a fresh
+    // window.  Warp-convergent (tcgen05.ld is .sync.aligned: every lane loads), but ONLY the selected lanes
+    // touch their shared-memory rows: a lane that is not flushing may hold the staged samples of its
+    // current window there.
+    __device__ __forceinline__ void unpark_to_smem(bool mine)
     {
 #pragma unroll
         for (int r = 0; r < TRAJ_ROWS; r++) {
             uint32_t v[16];
             tmem_ld16(taddr + 16 * r, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (mine) {
 #pragma unroll
-            for (int k = 0; k < TRAJ_S; k++) buf[r * TRAJ_S + k] = __hiloint2double((int)v[2 * k + 1], (int)v[2 * k]);
+                for (int k = 0; k < TRAJ_S; k++) buf[r * TRAJ_S + k] = __hiloint2double((int)v[2 * k + 1], (int)v[2 * k]);
+            }
         }
-        *reinterpret_cast<long long *>(reinterpret_cast<unsigned char *>(buf) + TRAJ_DATA_BYTES) =
-            (long long)(park_col0 << 4) | (long long)(lane_parked ? TRAJ_S : 0);
-        parked = false;
+        if (mine)
+            *reinterpret_cast<long long *>(reinterpret_cast<unsigned char *>(buf) + TRAJ_DATA_BYTES) =
+                (long long)(park_col0 << 4) | (long long)TRAJ_S;
     }
 
     // the lock-step store loop: all 32 lanes hold a complete window + header in shared memory
@@ -270,14 +275,22 @@ struct TrajWriter {
             if (lockstep) store_all_windows(lane);
             else store_windows_masked(lane, m);
             if (parked) {
-                // the parked lower halves follow immediately, so both halves of every line meet in L2
+                // The parked lower halves of the lanes that just flushed follow immediately, so both halves of
+                // every line meet in L2.  Lanes that are NOT flushing now (their upper window is still filling:
+                // another lane's orbit ended mid-window) keep theirs in TMEM -- their shared-memory rows hold
+                // live samples -- and write it when their own window completes.
                 const unsigned pm = __ballot_sync(FULL, lane_parked);
-                __syncwarp();               // the rows just written out are free again
-                unpark_to_smem();
-                __syncwarp();
-                if (pm == FULL) store_all_windows(lane);
-                else store_windows_masked(lane, pm);
-                lane_parked = false;
+                const unsigned um = pm & m;
+                if (um) {
+                    const bool mine = (um >> lane) & 1u;
+                    __syncwarp();           // the rows just written out are free again
+                    unpark_to_smem(mine);
+                    __syncwarp();
+                    if (um == FULL) store_all_windows(lane);
+                    else store_windows_masked(lane, um);
+                    if (mine) lane_parked = false;
+                }
+                parked = (pm & ~um) != 0u;
             }
         }
         __syncwarp();                       // rows may be overwritten by their owners from here on

@@ -378,3 +378,55 @@ def test_store_all_ragged_lengths_and_edge_orbits(ctx, oracle):
     e = ctx.integrate(np.zeros((6, 0)), np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0, dtype=np.int32),
                       integrator=_lib.LEAPFROG)
     assert e["w_final"].shape == (6, 0)
+
+
+def _local_step_check(ctx, oracle, pop, label):
+    """EVERY stored leapfrog sample against the CPU oracle, locally: sample j+1 must be one oracle KDK step
+    from sample j (no chaotic amplification, so the bound is tight and a single misplaced or stale column
+    shows).  Transitions into a kick node (the stored velocity is post-kick) and into an appended t2 node
+    (gala's leapfrog keeps the segment's dt there, quirk Q2) are checked by position / skipped."""
+    b = pop.batch
+    ctx.set_potential(pop.potential)
+    g = ctx.integrate(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv,
+                      integrator=_lib.LEAPFROG, store_all=True)
+    assert (g["status"] == 0).all()
+    off, t = g["traj_off"], g["traj_t"]
+    n = b.n_orbits
+    lens = off[1:] - off[:-1]
+    col = np.arange(off[-1])
+    orbit_of = np.repeat(np.arange(n), lens)
+    j = col - off[orbit_of]
+    is_last = j == lens[orbit_of] - 1
+    # kick nodes as absolute columns
+    ev_orbit = np.repeat(np.arange(n), b.ev_off[1:] - b.ev_off[:-1])
+    kick_cols = off[ev_orbit] + g["ev_step"]
+    to_kick = np.zeros(off[-1] + 1, dtype=bool)
+    to_kick[kick_cols] = True
+    appended = (b.flags[orbit_of] & 1) == 1
+    src = col[~is_last]
+    dst = src + 1
+    skip = appended[src] & is_last[dst]                     # the short appended interval
+    src, dst = src[~skip], dst[~skip]
+    w_src = np.vstack([g["traj_pos"][:, src], g["traj_vel"][:, src]])
+    dt = t[dst] - t[src]
+    # the segment's own dt: the first interval after the last kick node (or the orbit start) before src
+    o = oracle.integrate_batch(pop.potential, w_src, t[src], t[src] + 1.5 * dt, dt, 1.0, 0, integrator=oracle.LEAPFROG)
+    assert (o["n_nodes"] == 2).all()
+    dp = np.abs(o["w_final"][:3] - g["traj_pos"][:, dst]).max(axis=0)
+    dv = np.abs(o["w_final"][3:] - g["traj_vel"][:, dst]).max(axis=0)
+    r = np.maximum(np.linalg.norm(g["traj_pos"][:, dst], axis=0), 1e-3)
+    smooth = ~to_kick[dst]
+    # positions everywhere; velocities except into kick nodes.  A step through the nucleus (r << 1 kpc) amplifies the
+    # 1e-13 difference between the interval and the segment's dt, hence the relative bound with a floor on r
+    assert (dp / r).max() < 1e-9, (label, float((dp / r).max()), int(np.argmax(dp / r)))
+    assert (dv[smooth]).max() < 1e-9, (label, float(dv[smooth].max()))
+    assert np.median(dp) < 1e-13
+    return off[-1]
+
+
+def test_store_all_every_sample_locally_exact(ctx, oracle):
+    cols = 0
+    cols += _local_step_check(ctx, oracle, make_population(200, cfg_id=21), "ragged horizons")
+    cols += _local_step_check(ctx, oracle, make_population(5000, cfg_id=3, horizon_gyr=0.25), "mixed 250/251 nodes, sorted queue")
+    cols += _local_step_check(ctx, oracle, make_population(400, cfg_id=4, horizon_gyr=1.0), "kicked 1001 nodes")
+    assert cols > 3_000_000
