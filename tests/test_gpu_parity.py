@@ -380,18 +380,24 @@ def test_store_all_ragged_lengths_and_edge_orbits(ctx, oracle):
     assert e["w_final"].shape == (6, 0)
 
 
-def _local_step_check(ctx, oracle, pop, label):
+def _local_step_check(ctx, oracle, pop, label, integ=None, tol_p=1e-9, tol_v=1e-9, tol_med=1e-13):
     """EVERY stored leapfrog sample against the CPU oracle, locally: sample j+1 must be one oracle KDK step
     from sample j (no chaotic amplification, so the bound is tight and a single misplaced or stale column
     shows).  Transitions into a kick node (the stored velocity is post-kick) and into an appended t2 node
     (gala's leapfrog keeps the segment's dt there, quirk Q2) are checked by position / skipped."""
     b = pop.batch
     ctx.set_potential(pop.potential)
+    integ = _lib.LEAPFROG if integ is None else integ
     g = ctx.integrate(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv,
-                      integrator=_lib.LEAPFROG, store_all=True)
+                      integrator=integ, store_all=True)
     assert (g["status"] == 0).all()
     off, t = g["traj_off"], g["traj_t"]
     n = b.n_orbits
+    # the final-state kernel (another template instance, another queue consumption pattern) gives the same bits
+    f = ctx.integrate(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv, integrator=integ)
+    assert np.array_equal(f["w_final"], g["w_final"]) and np.array_equal(f["ev_step"], g["ev_step"])
+    assert np.array_equal(g["traj_pos"][:, off[1:] - 1], g["w_final"][:3])
+    assert np.array_equal(g["traj_vel"][:, off[1:] - 1], g["w_final"][3:])
     lens = off[1:] - off[:-1]
     col = np.arange(off[-1])
     orbit_of = np.repeat(np.arange(n), lens)
@@ -405,22 +411,25 @@ def _local_step_check(ctx, oracle, pop, label):
     appended = (b.flags[orbit_of] & 1) == 1
     src = col[~is_last]
     dst = src + 1
-    skip = appended[src] & is_last[dst]                     # the short appended interval
+    skip = appended[src] & is_last[dst] & (integ == _lib.LEAPFROG)   # the short appended interval (leapfrog only)
     src, dst = src[~skip], dst[~skip]
     w_src = np.vstack([g["traj_pos"][:, src], g["traj_vel"][:, src]])
     dt = t[dst] - t[src]
     # the segment's own dt: the first interval after the last kick node (or the orbit start) before src
-    o = oracle.integrate_batch(pop.potential, w_src, t[src], t[src] + 1.5 * dt, dt, 1.0, 0, integrator=oracle.LEAPFROG)
-    assert (o["n_nodes"] == 2).all()
+    # DOPRI853 (either form): one accurate restart-form interval from sample j; the dense form's interpolated
+    # samples carry its tolerance-level interpolation error, hence the looser bounds passed in
+    o = oracle.integrate_batch(pop.potential, w_src, t[src], t[src] + 1.5 * dt, dt, 1.0, 0,
+                               integrator=oracle.LEAPFROG if integ == _lib.LEAPFROG else oracle.DOP853)
+    assert (o["n_nodes"] == 2).all() and (o["status"] == 0).all()
     dp = np.abs(o["w_final"][:3] - g["traj_pos"][:, dst]).max(axis=0)
     dv = np.abs(o["w_final"][3:] - g["traj_vel"][:, dst]).max(axis=0)
     r = np.maximum(np.linalg.norm(g["traj_pos"][:, dst], axis=0), 1e-3)
     smooth = ~to_kick[dst]
     # positions everywhere; velocities except into kick nodes.  A step through the nucleus (r << 1 kpc) amplifies the
     # 1e-13 difference between the interval and the segment's dt, hence the relative bound with a floor on r
-    assert (dp / r).max() < 1e-9, (label, float((dp / r).max()), int(np.argmax(dp / r)))
-    assert (dv[smooth]).max() < 1e-9, (label, float(dv[smooth].max()))
-    assert np.median(dp) < 1e-13
+    assert (dp / r).max() < tol_p, (label, float((dp / r).max()), int(np.argmax(dp / r)))
+    assert (dv[smooth]).max() < tol_v, (label, float(dv[smooth].max()))
+    assert np.median(dp) < tol_med
     return off[-1]
 
 
@@ -430,3 +439,13 @@ def test_store_all_every_sample_locally_exact(ctx, oracle):
     cols += _local_step_check(ctx, oracle, make_population(5000, cfg_id=3, horizon_gyr=0.25), "mixed 250/251 nodes, sorted queue")
     cols += _local_step_check(ctx, oracle, make_population(400, cfg_id=4, horizon_gyr=1.0), "kicked 1001 nodes")
     assert cols > 3_000_000
+
+
+def test_store_all_dop853_every_sample_locally_exact(ctx, oracle):
+    """The same per-sample check for the DOPRI853 trajectories: restart form (the identical algorithm, so tight)
+    and dense form (interior samples are contd8 values: bounded by the interpolation error at tol 1e-10)."""
+    pop = make_population(300, cfg_id=23, horizon_gyr=0.3)
+    _local_step_check(ctx, oracle, pop, "dop853 restart", integ=_lib.DOP853, tol_p=1e-10, tol_v=1e-10, tol_med=1e-13)
+    _local_step_check(ctx, oracle, pop, "dop853 dense", integ=_lib.DOP853_DENSE, tol_p=3e-8, tol_v=3e-8, tol_med=1e-9)
+    ragged = make_population(60, cfg_id=24)
+    _local_step_check(ctx, oracle, ragged, "dop853 dense ragged", integ=_lib.DOP853_DENSE, tol_p=3e-7, tol_v=3e-7, tol_med=1e-9)
