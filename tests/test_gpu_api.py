@@ -202,3 +202,35 @@ def test_rewind_backward_integration(ctx, oracle):
     assert np.abs(p1.T - b.w0[:3]).max() < 1e-10
     with pytest.raises(ValueError):
         rewind_orbits(pos, vel_kms, 100.0, np.full(n, 200.0), -1.0, potential=pop.potential, context=ctx)
+
+
+def test_chunked_host_store_all_matches_device_mode(ctx):
+    """Host-buffer store_all calls large enough to be cut into pipelined chunks (per-chunk event and trajectory
+    column bases) return exactly the bits of one device-resident launch."""
+    import torch
+    pop = population_with_n_orbits(300_000, cfg_id=33, horizon_gyr=0.012)       # 13 nodes per orbit
+    b = pop.batch
+    n = b.n_orbits
+    ctx.set_potential(pop.potential)
+    host = ctx.integrate(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv,
+                         integrator=_lib.LEAPFROG, store_all=True)
+    assert ctx.last_launch_count > 6                                           # several shards
+    off = host["traj_off"]
+    dev = torch.device("cuda:0")
+    tt = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dtype=dt)
+    d = dict(w0=tt(b.w0), t1=tt(b.t1), t2=tt(b.t2), dt=tt(b.dt), to_myr=tt(b.to_myr), flags=tt(b.flags, torch.int32),
+             ev_off=tt(b.ev_off, torch.int64), ev_time=tt(b.ev_time), ev_dv=tt(b.ev_dv))
+    wf = torch.empty((6, n), dtype=torch.float64, device=dev)
+    st = torch.empty(n, dtype=torch.int32, device=dev)
+    toff = tt(off, torch.int64)
+    tp = torch.full((3, int(off[-1])), float("nan"), dtype=torch.float64, device=dev)
+    tv = torch.full((3, int(off[-1])), float("nan"), dtype=torch.float64, device=dev)
+    tm = torch.empty(int(off[-1]), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    ctx.integrate_raw(n, d["w0"], d["t1"], d["t2"], d["dt"], d["to_myr"], d["flags"], d["ev_off"], d["ev_time"],
+                      d["ev_dv"], wf, st, None, None, toff, tp, tv, tm, None, integrator=_lib.LEAPFROG,
+                      mem_space=_lib.MEM_DEVICE)
+    assert np.array_equal(tp.cpu().numpy(), host["traj_pos"])
+    assert np.array_equal(tv.cpu().numpy(), host["traj_vel"])
+    assert np.array_equal(tm.cpu().numpy(), host["traj_t"])
+    assert np.array_equal(wf.cpu().numpy(), host["w_final"])
