@@ -175,12 +175,10 @@ constexpr int LF_BLOCK = 256;        // final-state kernel: 4 CTAs x 256 threads
 // store_all kernel: ONE CTA of 512 threads per SM.  The staging windows (392 B per lane = 196 KB) cap the
 // orbits in flight at 512 per SM, and a kernel that allocates tensor memory is given one CTA per SM by the
 // occupancy calculator whatever it asks for, so the 16 warps live in one CTA that owns all 512 TMEM columns
-// (measured 4.13 TB/s vs 4.00 TB/s for 2 x 256 threads with 256 columns each; 112 registers per thread).
+// (measured 4.13 TB/s vs 4.00 TB/s for 2 x 256 threads with 256 columns each; 128 registers per thread).
 constexpr int LF_BLOCK_STORE = 512;
-// resident CTAs per SM the final-state kernel is compiled for (register budget = 65536 / (256 * N))
-#ifndef CW_LF_MINB
-#define CW_LF_MINB 4
-#endif
+// Register budgets (__maxnreg__ on the kernel): 64 for the final-state kernel = 4 resident CTAs of 256 threads,
+// 128 for the store_all kernel = its single 512-thread CTA.
 
 struct Lane {
     double x, y, z, vx, vy, vz;     // state at node j (v synchronised only at sync nodes)
