@@ -177,6 +177,9 @@ constexpr int LF_BLOCK = 256;        // final-state kernel: 4 CTAs x 256 threads
 // occupancy calculator whatever it asks for, so the 16 warps live in one CTA that owns all 512 TMEM columns
 // (measured 4.13 TB/s vs 4.00 TB/s for 2 x 256 threads with 256 columns each; 128 registers per thread).
 constexpr int LF_BLOCK_STORE = 512;
+#ifndef CW_LF_REGS
+#define CW_LF_REGS 64      // experiment knob: 80 -> 3 resident CTAs (measured: see DESIGN.md)
+#endif
 // Register budgets (__maxnreg__ on the kernel): 64 for the final-state kernel = 4 resident CTAs of 256 threads,
 // 128 for the store_all kernel = its single 512-thread CTA.
 
@@ -234,7 +237,7 @@ __device__ __forceinline__ void write_final(const IntegArgs &A, const Lane &s)
 }
 
 template <int KIND, bool STORE>
-__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? 128 : 64) leapfrog_kernel(const __grid_constant__ PotParams P,
+__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? 128 : CW_LF_REGS) leapfrog_kernel(const __grid_constant__ PotParams P,
                                                             const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
