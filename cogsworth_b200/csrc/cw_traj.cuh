@@ -42,6 +42,9 @@ constexpr int TRAJ_LANE_BYTES = TRAJ_DATA_BYTES + 8;
 // half-line window (columns 0..7 mod 16) is parked there (tcgen05.st, 96 columns per lane) instead of
 // being written, and is written right after the UPPER half 8 steps later: the two halves reach L2 within
 // a microsecond of each other, merge, and leave as full 128-byte lines.
+// Parking is decided warp-wide (tcgen05.st is .sync.aligned) but released PER LANE: when one lane's orbit ends
+// in the middle of a window, only that lane's parked half is written; the others stay in TMEM until their own
+// upper window completes, because their shared-memory rows hold the samples of the window still filling.
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
