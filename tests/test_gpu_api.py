@@ -234,3 +234,60 @@ def test_chunked_host_store_all_matches_device_mode(ctx):
     assert np.array_equal(tv.cpu().numpy(), host["traj_vel"])
     assert np.array_equal(tm.cpu().numpy(), host["traj_t"])
     assert np.array_equal(wf.cpu().numpy(), host["w_final"])
+
+
+def test_store_all_full_size_properties(ctx, oracle):
+    """configs[2] at FULL size on one B200: 10^6 orbits x 1000 stored steps = 48 GB of trajectories, device
+    resident.  Size-independent properties checked where the data lives: no unwritten column, first sample = w0,
+    last sample = w_final, the final-state kernel returns the same bits, and 200 000 randomly chosen samples are
+    one oracle KDK step from their predecessors."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2**30:
+        pytest.skip("needs ~55 GB of free device memory")
+    pop = population_with_n_orbits(1_000_000, cfg_id=3, horizon_gyr=1.0, f_sn=0.0)
+    b = pop.batch
+    n = b.n_orbits
+    ctx.set_potential(pop.potential)
+    nn, _ = ctx.count_nodes(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, None, None, None)
+    assert (nn == 1000).all()
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(nn, out=off[1:])
+    dev = torch.device("cuda:0")
+    tt = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dtype=dt)
+    d = dict(w0=tt(b.w0), t1=tt(b.t1), t2=tt(b.t2), dt=tt(b.dt), to_myr=tt(b.to_myr), flags=tt(b.flags, torch.int32))
+    toff = tt(off, torch.int64)
+    total = int(off[-1])
+    tp = torch.full((3, total), float("nan"), dtype=torch.float64, device=dev)
+    tv = torch.full((3, total), float("nan"), dtype=torch.float64, device=dev)
+    wf = torch.empty((6, n), dtype=torch.float64, device=dev)
+    wf2 = torch.empty((6, n), dtype=torch.float64, device=dev)
+    st = torch.empty(n, dtype=torch.int32, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    ctx.integrate_raw(n, d["w0"], d["t1"], d["t2"], d["dt"], d["to_myr"], d["flags"], None, None, None, wf, st, None, None,
+                      toff, tp, tv, None, stats, integrator=_lib.LEAPFROG, mem_space=_lib.MEM_DEVICE)
+    k_ms = ctx.last_kernel_ms(0)
+    assert int(stats[3]) == 999 * n and int((st != 0).sum()) == 0
+    assert not bool(torch.isnan(tp).any()) and not bool(torch.isnan(tv).any())       # every column written
+    first, last = toff[:-1], toff[1:] - 1
+    assert bool((tp[:, first] == d["w0"][:3]).all()) and bool((tv[:, first] == d["w0"][3:]).all())
+    assert bool((tp[:, last] == wf[:3]).all()) and bool((tv[:, last] == wf[3:]).all())
+    ctx.integrate_raw(n, d["w0"], d["t1"], d["t2"], d["dt"], d["to_myr"], d["flags"], None, None, None, wf2, st, None, None,
+                      None, None, None, None, stats, integrator=_lib.LEAPFROG, mem_space=_lib.MEM_DEVICE)
+    assert bool((wf2 == wf).all())                                                   # final-state kernel: same bits
+    # random local-step check against the oracle (columns that are not the last of their orbit)
+    rng = np.random.default_rng(1)
+    src = rng.integers(0, total, 200_000)
+    src = src[(src % 1000) != 999]
+    src_d = torch.from_numpy(src).to(dev)
+    w_src = torch.cat([tp[:, src_d], tv[:, src_d]]).cpu().numpy()
+    w_dst = torch.cat([tp[:, src_d + 1], tv[:, src_d + 1]]).cpu().numpy()
+    m = len(src)
+    o = oracle.integrate_batch(pop.potential, w_src, np.zeros(m), np.full(m, 1.5), np.ones(m), 1.0, 0, integrator=oracle.LEAPFROG)
+    r = np.maximum(np.linalg.norm(w_dst[:3], axis=0), 1e-3)
+    assert (np.abs(o["w_final"][:3] - w_dst[:3]).max(axis=0) / r).max() < 1e-9
+    assert np.abs(o["w_final"][3:] - w_dst[3:]).max() < 1e-9
+    assert 48.0 * total / (k_ms * 1e-3) / 1e9 > 2000.0                               # and it ran at HBM-class speed
+    del tp, tv
+    torch.cuda.empty_cache()
