@@ -491,7 +491,11 @@ template <int KIND, bool STORE>
 static cudaError_t launch_lf(const PotParams &P, const IntegArgs &A, const LaunchCfg &cfg)
 {
     int per_sm = 0;
-    const int block = STORE ? LF_BLOCK_STORE : LF_BLOCK;
+    int block = STORE ? LF_BLOCK_STORE : LF_BLOCK;
+    // Batches too small to give every SM two full CTAs are cut into smaller CTAs (down to 64 threads), so the
+    // orbits spread evenly over the 148 SMs instead of filling a few of them (results do not depend on it).
+    if (!STORE)
+        while (block > 64 && (A.n + block - 1) / block < 2 * (int64_t)cfg.sm_count) block >>= 1;
     const size_t dyn = STORE ? (size_t)block * TRAJ_LANE_BYTES : 0;
     cudaError_t err = cudaSuccess;
     if (STORE) {
