@@ -62,7 +62,12 @@ struct Slot {
     cudaStream_t lanes[N_LANES] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_t0 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;   // diagnostics entry points
     std::vector<cudaEvent_t> events;        // per-shard timing events (grow-only pool)
-    Arena arena;
+    Arena arena;                            // diagnostics / pointwise entry points
+    // Integration scratch, ONE ARENA PER STREAM LANE: the shards of a lane run one after another on the lane's
+    // stream, so each of them re-uses the lane's buffers (stream order is the only synchronisation needed).
+    // Device memory of a host-buffer call is therefore bounded by N_LANES chunks, not by the size of the batch:
+    // trajectories larger than HBM stream through.
+    Arena lane_arena[N_LANES];
     double last_kernel_ms = 0.0, last_total_ms = 0.0;
     cudaError_t ensure_events(size_t n)
     {
@@ -181,6 +186,7 @@ extern "C" void cw_destroy(cw_ctx *ctx)
         for (int l = 0; l < Slot::N_LANES; l++)
             if (s.lanes[l]) cudaStreamSynchronize(s.lanes[l]);
         s.arena.release();
+        for (int l = 0; l < Slot::N_LANES; l++) s.lane_arena[l].release();
         for (cudaEvent_t e : s.events) cudaEventDestroy(e);
         if (s.ev_t0) cudaEventDestroy(s.ev_t0);
         if (s.ev_k0) cudaEventDestroy(s.ev_k0);
@@ -276,6 +282,13 @@ constexpr int64_t SORT_THRESHOLD = 4096;
 // and the D2H copy of chunk c-1 overlap the kernels of chunk c: about 8 chunks per device, between
 // 2^16 orbits (below that launch overheads show) and 2^20 (bounds the exposed first copy).
 constexpr int64_t HOST_CHUNK_MAX = 1 << 20, HOST_CHUNK_MIN = 1 << 16;
+constexpr int64_t TRAJ_SHARD_COLS = (int64_t)1 << 26;   // trajectory columns per host-mode shard (store_all)
+static int64_t traj_shard_cols()
+{
+    const char *e = getenv("CW_TRAJ_SHARD_COLS");       // test hook: force many small shards
+    const long long v = e ? atoll(e) : 0;
+    return v > 0 ? (int64_t)v : TRAJ_SHARD_COLS;
+}
 static int64_t host_chunk(int64_t n_on_device)
 {
     int64_t c = (n_on_device + 7) / 8;
@@ -329,6 +342,8 @@ static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B,
     const int64_t m = sh.b - sh.a, K = sh.eb - sh.ea, Lt = sh.tb - sh.ta;
     const bool store_all = integrate && R && R->traj_off;
     cudaStream_t stream = pl.stream;
+    Arena &ar = s.lane_arena[sh.lane];
+    ar.used = 0;                            // the previous shard of this lane precedes us in stream order
 
     IntegArgs &A = pl.A;
     memset(&A, 0, sizeof A);
@@ -336,33 +351,33 @@ static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B,
     A.atol = o->atol > 0 ? o->atol : 1e-10;
     A.rtol = o->rtol > 0 ? o->rtol : 1e-10;
     A.nmax = o->nmax;
-    A.ev_tk = s.arena.take<double>(K + 1);
+    A.ev_tk = ar.take<double>(K + 1);
     if (integrate && o->integrator == CW_DOP853_DENSE) {
-        A.t_last = s.arena.take<double>(m);
+        A.t_last = ar.take<double>(m);
         if (!A.t_last) return fail(ctx, CW_E_CUDA, "device arena exhausted (internal sizing error)");
     }
-    unsigned long long *qs = s.arena.take<unsigned long long>(8);
+    unsigned long long *qs = ar.take<unsigned long long>(8);
     A.queue = qs;
     A.stats = qs + 1;
     if (pl.sort) {
-        pl.iota = s.arena.take<int32_t>(m);
-        pl.keys_out = s.arena.take<int32_t>(m);
-        pl.keys_in = s.arena.take<int32_t>(m);
-        pl.order = s.arena.take<int32_t>(m);
+        pl.iota = ar.take<int32_t>(m);
+        pl.keys_out = ar.take<int32_t>(m);
+        pl.keys_in = ar.take<int32_t>(m);
+        pl.order = ar.take<int32_t>(m);
         A.order = pl.order;
-        pl.sort_tmp = s.arena.take<char>(pl.sort_bytes);
+        pl.sort_tmp = ar.take<char>(pl.sort_bytes);
     }
     if (!dev_mode) {
-        double *w0 = s.arena.take<double>(6 * m);
-        double *tt = s.arena.take<double>(4 * m);
-        int32_t *fl = s.arena.take<int32_t>(m);
-        int64_t *eo = s.arena.take<int64_t>(m + 1);
-        double *et = s.arena.take<double>(K + 1);
-        double *ed = s.arena.take<double>(3 * K + 3);
-        A.n_nodes = s.arena.take<int32_t>(m);
-        A.ev_step = s.arena.take<int32_t>(K + 1);
-        A.w_final = s.arena.take<double>(6 * m);
-        A.status = s.arena.take<int32_t>(m);
+        double *w0 = ar.take<double>(6 * m);
+        double *tt = ar.take<double>(4 * m);
+        int32_t *fl = ar.take<int32_t>(m);
+        int64_t *eo = ar.take<int64_t>(m + 1);
+        double *et = ar.take<double>(K + 1);
+        double *ed = ar.take<double>(3 * K + 3);
+        A.n_nodes = ar.take<int32_t>(m);
+        A.ev_step = ar.take<int32_t>(K + 1);
+        A.w_final = ar.take<double>(6 * m);
+        A.status = ar.take<int32_t>(m);
         if (!w0 || !tt || !fl || !eo || !et || !ed || !A.w_final || !A.status)
             return fail(ctx, CW_E_CUDA, "device arena exhausted (internal sizing error)");
         A.w0 = w0; A.t1 = tt; A.t2 = tt + m; A.dt = tt + 2 * m; A.to_myr = tt + 3 * m; A.flags = fl;
@@ -383,9 +398,9 @@ static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B,
             // device rows are padded to a multiple of 16 columns so every row starts 128-byte aligned
             // (the trajectory writer's bulk stores need 16-byte aligned destinations)
             const int64_t Ltp = (Lt + 15) & ~int64_t(15);
-            int64_t *to = s.arena.take<int64_t>(m + 1);
-            double *tp = s.arena.take<double>(6 * Ltp);
-            double *ttm = s.arena.take<double>(Lt + 1);
+            int64_t *to = ar.take<int64_t>(m + 1);
+            double *tp = ar.take<double>(6 * Ltp);
+            double *ttm = ar.take<double>(Lt + 1);
             if (!to || !tp || !ttm) return fail(ctx, CW_E_CUDA, "device arena exhausted (internal sizing error)");
             CW_CK(ctx, cudaMemcpyAsync(to, R->traj_off + sh.a, (m + 1) * 8, cudaMemcpyHostToDevice, stream));
             A.traj_off = to; A.traj_base = sh.ta; A.traj_total = Ltp;
@@ -394,7 +409,7 @@ static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B,
     } else {
         A.w0 = B->w0; A.t1 = B->t1; A.t2 = B->t2; A.dt = B->dt; A.to_myr = B->to_myr; A.flags = B->grid_flags;
         if (B->ev_off && K > 0) { A.ev_off = B->ev_off; A.ev_base = 0; A.ev_time = B->ev_time; A.ev_dv = B->ev_dv; }
-        int32_t *nn = s.arena.take<int32_t>(m), *es = s.arena.take<int32_t>(K + 1), *st = s.arena.take<int32_t>(m);
+        int32_t *nn = ar.take<int32_t>(m), *es = ar.take<int32_t>(K + 1), *st = ar.take<int32_t>(m);
         A.n_nodes = (R && R->n_nodes) ? R->n_nodes : nn;
         A.ev_step = (R && R->ev_step) ? R->ev_step : es;
         A.status = (R && R->status) ? R->status : st;
@@ -517,13 +532,27 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
         int lane = 0;
         int64_t c = a;
         for (int64_t sz : sizes) {
-            Shard sh;
-            sh.slot = d;
-            sh.lane = dev_mode ? 0 : (lane++ % Slot::N_LANES);
-            sh.a = c;
-            sh.b = c + sz;
-            c += sz;
-            shards.push_back(sh);
+            // store_all from host buffers: a shard's trajectories live in its lane's buffer, so shards are also
+            // cut by trajectory COLUMNS (<= 2^26 = 3.2 GB of pos + vel); with the lane buffers re-used this
+            // bounds device memory however long the orbits are
+            int64_t s0 = c;
+            const int64_t e0 = c + sz;
+            while (s0 < e0) {
+                int64_t e1 = e0;
+                if (store_all && !dev_mode) {
+                    const int64_t lim = R->traj_off[s0] + traj_shard_cols();
+                    const int64_t *ub = std::upper_bound(R->traj_off + s0 + 1, R->traj_off + e0 + 1, lim);
+                    e1 = std::min(e0, std::max<int64_t>(s0 + 1, (int64_t)(ub - R->traj_off) - 1));
+                }
+                Shard sh;
+                sh.slot = d;
+                sh.lane = dev_mode ? 0 : (lane++ % Slot::N_LANES);
+                sh.a = s0;
+                sh.b = e1;
+                shards.push_back(sh);
+                s0 = e1;
+            }
+            c = e0;
         }
     }
     for (Shard &sh : shards) {
@@ -544,20 +573,28 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
 
     // ---- size and reserve each slot's arena once, for all of its shards
     std::vector<Plan> plans(shards.size());
-    std::vector<size_t> need(nslots, 0);
-    for (size_t k = 0; k < shards.size(); k++) need[shards[k].slot] += shard_bytes(o, &Rl, shards[k], integrate, plans[k]);
+    std::vector<size_t> need((size_t)nslots * Slot::N_LANES, 0);
+    for (size_t k = 0; k < shards.size(); k++) {
+        size_t &nd = need[(size_t)shards[k].slot * Slot::N_LANES + shards[k].lane];
+        nd = std::max(nd, shard_bytes(o, &Rl, shards[k], integrate, plans[k]));
+    }
     for (int d = 0; d < nslots; d++) {
         Slot &s = ctx->slots[d];
         cudaSetDevice(s.dev);
         size_t n_sh = 0;
         for (const Shard &sh : shards) n_sh += (sh.slot == d);
-        // streams still running a previous no_sync call must not see their buffers move
-        if (need[d] + 4096 > s.arena.cap) for (int l = 0; l < Slot::N_LANES; l++) cudaStreamSynchronize(s.lanes[l]);
-        CW_CK(ctx, s.arena.reserve(need[d] + 4096));
+        for (int l = 0; l < Slot::N_LANES; l++) {
+            const size_t nd = need[(size_t)d * Slot::N_LANES + l];
+            if (nd == 0) continue;
+            // a stream still running a previous no_sync call must not see its buffers move
+            if (nd + 4096 > s.lane_arena[l].cap) cudaStreamSynchronize(s.lanes[l]);
+            CW_CK(ctx, s.lane_arena[l].reserve(nd + 4096));
+        }
         CW_CK(ctx, s.ensure_events(3 * n_sh));
     }
     // ---- phase 1: enqueue everything (H2D, kernels, D2H) on every device, all asynchronous
     std::vector<size_t> ev_used(nslots, 0);
+    std::vector<unsigned long long> hs(4 * shards.size(), 0);
     const int64_t total_cols = (store_all && !dev_mode) ? R->traj_off[n] : 0;
     for (size_t k = 0; k < shards.size(); k++) {
         const Shard &sh = shards[k];
@@ -571,6 +608,8 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
         rc = plan_shard(ctx, s, o, B, &Rl, sh, integrate, pl);
         if (rc == CW_OK) rc = run_shard(ctx, s, o, pl, integrate, store_all);
         if (rc != CW_OK) { cudaSetDevice(prev); return rc; }
+        if (integrate && R->stats && !(dev_mode && o->no_sync))
+            CW_CK(ctx, cudaMemcpyAsync(&hs[4 * k], pl.A.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, pl.stream));
         if (!dev_mode) {
             cudaStream_t stream = pl.stream;
             const IntegArgs &A = pl.A;
@@ -596,13 +635,6 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
     if (dev_mode && o->no_sync) { cudaSetDevice(prev); return CW_OK; }
     // ---- phase 2: wait, gather statistics and kernel times
     int64_t stats[4] = {0, 0, 0, 0};
-    std::vector<unsigned long long> hs(4 * shards.size(), 0);
-    for (size_t k = 0; k < shards.size(); k++) {
-        Slot &s = ctx->slots[shards[k].slot];
-        cudaSetDevice(s.dev);
-        if (integrate && R->stats)
-            CW_CK(ctx, cudaMemcpyAsync(&hs[4 * k], plans[k].A.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, plans[k].stream));
-    }
     for (size_t k = 0; k < shards.size(); k++) {
         Slot &s = ctx->slots[shards[k].slot];
         cudaSetDevice(s.dev);

@@ -291,3 +291,25 @@ def test_store_all_full_size_properties(ctx, oracle):
     assert 48.0 * total / (k_ms * 1e-3) / 1e9 > 2000.0                               # and it ran at HBM-class speed
     del tp, tv
     torch.cuda.empty_cache()
+
+
+def test_host_store_all_streams_through_bounded_buffers(ctx, monkeypatch):
+    """Host-buffer store_all calls are cut by trajectory columns and every stream lane re-uses its own device
+    buffers shard after shard (device memory bounded by three shards, not by the batch): forcing hundreds of
+    tiny shards must not change a bit, for ragged orbit lengths and with kicks."""
+    pop = make_population(700, cfg_id=35)                                       # Wagg horizons: 10^2 .. 1.2x10^4 nodes
+    b = pop.batch
+    ctx.set_potential(pop.potential)
+    args = (b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv)
+    ref = ctx.integrate(*args, integrator=_lib.LEAPFROG, store_all=True)
+    n_ref = ctx.last_launch_count
+    monkeypatch.setenv("CW_TRAJ_SHARD_COLS", "60000")
+    cut = ctx.integrate(*args, integrator=_lib.LEAPFROG, store_all=True)
+    assert ctx.last_launch_count > 20 * n_ref                                   # hundreds of shards
+    for k in ("traj_pos", "traj_vel", "traj_t", "w_final", "status", "n_nodes", "ev_step"):
+        assert np.array_equal(ref[k], cut[k]), k
+    assert int(cut["stats"][3]) == int(ref["stats"][3])
+    cut2 = ctx.integrate(*args, integrator=_lib.DOP853_DENSE, store_all=True)   # single shard by design, same API
+    monkeypatch.delenv("CW_TRAJ_SHARD_COLS")
+    ref2 = ctx.integrate(*args, integrator=_lib.DOP853_DENSE, store_all=True)
+    assert np.array_equal(ref2["traj_pos"], cut2["traj_pos"])
