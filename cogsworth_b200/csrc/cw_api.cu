@@ -68,6 +68,8 @@ struct Slot {
     // Device memory of a host-buffer call is therefore bounded by N_LANES chunks, not by the size of the batch:
     // trajectories larger than HBM stream through.
     Arena lane_arena[N_LANES];
+    Arena meta;                             // queue counter + statistics of every shard of a call (64 B each): NOT
+                                            // re-used within a call, so they can be read back after the last shard
     double last_kernel_ms = 0.0, last_total_ms = 0.0;
     cudaError_t ensure_events(size_t n)
     {
@@ -187,6 +189,7 @@ extern "C" void cw_destroy(cw_ctx *ctx)
             if (s.lanes[l]) cudaStreamSynchronize(s.lanes[l]);
         s.arena.release();
         for (int l = 0; l < Slot::N_LANES; l++) s.lane_arena[l].release();
+        s.meta.release();
         for (cudaEvent_t e : s.events) cudaEventDestroy(e);
         if (s.ev_t0) cudaEventDestroy(s.ev_t0);
         if (s.ev_k0) cudaEventDestroy(s.ev_k0);
@@ -356,7 +359,7 @@ static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B,
         A.t_last = ar.take<double>(m);
         if (!A.t_last) return fail(ctx, CW_E_CUDA, "device arena exhausted (internal sizing error)");
     }
-    unsigned long long *qs = ar.take<unsigned long long>(8);
+    unsigned long long *qs = s.meta.take<unsigned long long>(8);
     A.queue = qs;
     A.stats = qs + 1;
     if (pl.sort) {
@@ -590,6 +593,9 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
             if (nd + 4096 > s.lane_arena[l].cap) cudaStreamSynchronize(s.lanes[l]);
             CW_CK(ctx, s.lane_arena[l].reserve(nd + 4096));
         }
+        if (Arena::padded(8, 8) * n_sh + 4096 > s.meta.cap)
+            for (int l = 0; l < Slot::N_LANES; l++) cudaStreamSynchronize(s.lanes[l]);
+        CW_CK(ctx, s.meta.reserve(Arena::padded(8, 8) * n_sh + 4096));
         CW_CK(ctx, s.ensure_events(3 * n_sh));
     }
     // ---- phase 1: enqueue everything (H2D, kernels, D2H) on every device, all asynchronous
@@ -608,8 +614,6 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
         rc = plan_shard(ctx, s, o, B, &Rl, sh, integrate, pl);
         if (rc == CW_OK) rc = run_shard(ctx, s, o, pl, integrate, store_all);
         if (rc != CW_OK) { cudaSetDevice(prev); return rc; }
-        if (integrate && R->stats && !(dev_mode && o->no_sync))
-            CW_CK(ctx, cudaMemcpyAsync(&hs[4 * k], pl.A.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, pl.stream));
         if (!dev_mode) {
             cudaStream_t stream = pl.stream;
             const IntegArgs &A = pl.A;
@@ -635,6 +639,12 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
     if (dev_mode && o->no_sync) { cudaSetDevice(prev); return CW_OK; }
     // ---- phase 2: wait, gather statistics and kernel times
     int64_t stats[4] = {0, 0, 0, 0};
+    for (size_t k = 0; k < shards.size(); k++) {
+        Slot &s = ctx->slots[shards[k].slot];
+        cudaSetDevice(s.dev);
+        if (integrate && R->stats)      // (pageable destination: this copy blocks the host, so it comes after every enqueue)
+            CW_CK(ctx, cudaMemcpyAsync(&hs[4 * k], plans[k].A.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, plans[k].stream));
+    }
     for (size_t k = 0; k < shards.size(); k++) {
         Slot &s = ctx->slots[shards[k].slot];
         cudaSetDevice(s.dev);
