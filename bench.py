@@ -139,6 +139,30 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads (and therefore its pinned buffers, first-touch) to the NUMA node its GPU hangs
+    off: with 8 ranks on a two-socket box the H2D/D2H legs of the end-to-end figure otherwise cross the socket link.
+    Best effort: silently does nothing when the topology cannot be read."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -236,6 +260,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -391,7 +416,8 @@ def main():
                            "n_orbits_total": n_total,
                            "n_kick_events_rank0": K, "orbit_steps_per_step": int(total_steps),
                            "integrator": wl["integrator"], "potential": "MilkyWayPotential2022 (MN3 disk + 2 Hernquist + NFW)",
-                           "parallelism": f"orbits sharded by index over {world} GPU(s), no collective",
+                           "parallelism": f"orbits sharded by index over {world} GPU(s), no collective"
+                                          + (f"; ranks bound to their GPU's NUMA node (rank 0: node {numa_node})" if numa_node is not None else ""),
                            "cache": "inputs + outputs (>= 1 GB per pass) exceed the 126 MB L2; nothing is reused between steps",
                            "failed_orbits_rank0": n_failed},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cbase}
