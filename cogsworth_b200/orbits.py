@@ -92,6 +92,28 @@ class Orbit:
     def w(self):
         return np.vstack([self._pos, self._vel])
 
+    # the slice of gala's representation API the reference touches (classify.py:137-153, plot.py:541-577)
+    class _Cyl:
+        def __init__(self, pos):
+            self.rho = np.hypot(pos[0], pos[1])
+            self.phi = np.arctan2(pos[1], pos[0])
+            self.z = pos[2]
+
+    @property
+    def cylindrical(self):
+        return Orbit._Cyl(self._pos)
+
+    def represent_as(self, name):
+        if str(name).lower().startswith("cyl"):
+            return self.cylindrical
+        if str(name).lower().startswith("cart"):
+            return self
+        raise NotImplementedError(f"representation {name!r} needs gala (install it to get real gala Orbit objects)")
+
+    @property
+    def data(self):
+        return self.pos
+
     def __repr__(self):
         return f"<Orbit cartesian, dim=3, shape={self.shape}>"
 

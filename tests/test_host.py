@@ -211,6 +211,20 @@ def test_product_never_imports_oracle():
                 assert "libcw_oracle" not in txt and "cwo_" not in txt, f
 
 
+def test_light_orbit_surface():
+    """Attribute surface of the gala-less Orbit stand-in."""
+    from cogsworth_b200.orbits import Orbit
+    pos = np.array([[3.0, 0.0, -1.0], [4.0, 2.0, 0.0], [0.5, -0.5, 0.1]])
+    o = Orbit(pos, pos / 10, np.arange(3.0))
+    assert np.allclose(o.cylindrical.rho, [5.0, 2.0, 1.0]) and np.array_equal(o.cylindrical.z, pos[2])
+    assert np.allclose(o.represent_as("cylindrical").phi, np.arctan2(pos[1], pos[0]))
+    assert o[-1].shape == (1,) and o[-1:].shape == (1,) and o[np.array([True, False, True])].shape == (2,)
+    assert len(o.pos) == 3 and np.array_equal(o.data.xyz, pos) and np.array_equal(o.vel.d_xyz, pos / 10)
+    assert np.array_equal(o.x, pos[0]) and o.ndim == 3
+    with pytest.raises(NotImplementedError):
+        o.represent_as("spherical")
+
+
 def test_orbit_wire_format_roundtrip(tmp_path):
     """orbits/{offsets,pos,vel,t} (pop.py:1853-1876): pos kpc, vel km/s, t Myr; load is lazy and the final
     coordinates come from the last column of every orbit (pop.py:715-718)."""
