@@ -59,7 +59,7 @@ enum {
 
 /* per-orbit grid flags */
 enum {
-    CW_GRID_APPEND_T2 = 1 /* kicks.py:121-122: append t2 as the final node (events branch) */
+    CW_GRID_APPEND_T2 = 1 /* kicks.py:121-122: append t2 as the final node (events branch; backward grids) */
 };
 
 /* buffer placement */
@@ -110,6 +110,8 @@ typedef struct cw_opts {
  * Time grid of orbit i (kicks.py:97,118-122 and gala.integrate.parse_time_specification):
  *     T_0 = t1[i];  T_{j+1} = T_j + dt[i]  while T_j < t2[i]  (FP64 accumulation, <= 1e6 nodes);
  *     if (grid_flags[i] & CW_GRID_APPEND_T2) and T_last < t2[i]:  append t2[i].
+ * Backward grids (t2 < t1 with dt < 0; cogsworth hydro/rewind.py:16-19): T_{j+1} = T_j + dt while T_j > t2, then t2
+ * itself when CW_GRID_APPEND_T2 is set (gala's backward branch); such orbits must not carry events.
  * t1/t2/dt/ev_time are in the orbit's own GRID UNIT and to_myr[i] converts it to Myr by
  * multiplication (cogsworth builds the grid in seconds on the events branch -- to_myr =
  * 1/3.15576e13 -- and gala builds it in Myr on the no-events branch -- to_myr = 1).  The caller
