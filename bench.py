@@ -183,10 +183,10 @@ def ncu_traffic(workload, scale, world):
     try:
         d = json.load(open(p))[workload]
     except Exception:
-        return None, None
+        return None, None, None
     f = (scale / world) / d["scale"]
     note = d["source"] + ("" if f == 1.0 else f"; captured at x{d['scale']} of the workload, scaled x{f:g} (traffic is linear in orbits)")
-    return d["dram_bytes_per_launch"] * f, note
+    return d["dram_bytes_per_launch"] * f, note, d.get("fp64_pipe_busy_pct")
 
 
 def cpu_baseline(pop, wl, n_sample, threads=0, repeats=1):
@@ -375,7 +375,7 @@ def main():
     # ---- roofline of the dominant kernel -------------------------------------------------------------
     k_ms = float(np.mean(kernel_ms))
     hbm_peak, hbm_src = measured_peaks()
-    traffic, traffic_src = ncu_traffic(args.workload, args.scale, world if args.scaling == "strong" else 1)
+    traffic, traffic_src, pipe_pct = ncu_traffic(args.workload, args.scale, world if args.scaling == "strong" else 1)
     if wl["store_all"]:
         ach = BYTES_PER_STORED_STEP * steps_per_pass / (k_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
@@ -397,6 +397,7 @@ def main():
         roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "traffic": traffic if integ == _lib.LEAPFROG else None, "traffic_source": traffic_src if integ == _lib.LEAPFROG else None,
                 "algorithmic_bytes_per_launch": float(108 * n + 28 * K),
+                "fp64_pipe_busy_ncu": (pipe_pct / 100.0) if (pipe_pct is not None and integ == _lib.LEAPFROG) else None,
                 "peak_source": "measured live: DFMA micro-benchmark cw_measure_fp64_peak (MEASURED_PEAKS.json has no "
                                "FP64 entry; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
                 "kernel": kname, "kernel_ms": k_ms, "prepass_sort_pilot_ms": float(np.mean(total_kernel_ms)) - k_ms,
