@@ -205,7 +205,7 @@ extern "C" int cw_device_count(const cw_ctx *ctx) { return ctx ? (int)ctx->slots
 
 extern "C" int cw_set_potential(cw_ctx *ctx, double G, int n_comp, const int32_t *types, const double *params)
 {
-    if (!ctx || !types || !params || n_comp <= 0 || n_comp > CW_MAX_COMPONENTS)
+    if (!ctx || n_comp < 0 || n_comp > CW_MAX_COMPONENTS || (n_comp > 0 && (!types || !params)))
         return fail(ctx, CW_E_INVALID, "cw_set_potential: bad arguments");
     PotParams P;
     memset(&P, 0, sizeof P);
@@ -213,13 +213,17 @@ extern "C" int cw_set_potential(cw_ctx *ctx, double G, int n_comp, const int32_t
     P.G = G;
     for (int i = 0; i < n_comp; i++) {
         const int t = types[i];
-        if (t < CW_COMP_MIYAMOTO_NAGAI || t > CW_COMP_LOGARITHMIC)
+        if (t < CW_COMP_MIYAMOTO_NAGAI || t > CW_COMP_BURKERT)
             return fail(ctx, CW_E_UNSUPPORTED, "cw_set_potential: unknown component type");
         P.type[i] = t;
         P.GM[i] = G * params[3 * i + 0];
         P.p1[i] = params[3 * i + 1];
         P.p2[i] = (t == CW_COMP_NFW_SPHERICAL) ? 1.0 / params[3 * i + 1] : params[3 * i + 2];
         if (t == CW_COMP_PLUMMER || t == CW_COMP_ISOCHRONE) P.p2[i] = params[3 * i + 1] * params[3 * i + 1];  // b^2
+        if (t == CW_COMP_BURKERT) {
+            P.GM[i] = 3.14159265358979323846 * G * params[3 * i + 0] * params[3 * i + 1];   // pi G rho r0
+            P.p2[i] = 1.0 / params[3 * i + 1];                                               // 1 / r0
+        }
         if (t == CW_COMP_LOGARITHMIC) {
             if (!(params[3 * i + 2] > 0.0)) return fail(ctx, CW_E_INVALID, "cw_set_potential: logarithmic q3 must be > 0");
             P.GM[i] = params[3 * i + 0] * params[3 * i + 0];                 // v_c^2

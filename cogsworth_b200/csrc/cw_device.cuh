@@ -337,9 +337,21 @@ __device__ __forceinline__ void force_generic(const PotParams &P, LogTab ltab,
                 fz = fma(inv, P.p2[i], fz);
                 continue;
             }
+            if (t == CW_COMP_KUZMIN) {                      // p1 = a; gz = f (a + |z|) sign z
+                const double az = P.p1[i] + fabs(z);
+                const double is = rsqrt_fast(fma(az, az, R2));
+                const double fk = P.GM[i] * ((is * is) * is);
+                fxy += fk;
+                if (z != 0.0) fz = fma(fk, az * rcp_fast(fabs(z)), fz);
+                continue;
+            }
             if (t == CW_COMP_HERNQUIST) {
                 const double rc = r + P.p1[i];
                 f = P.GM[i] * rcp_fast(rc * rc) * ir;
+            } else if (t == CW_COMP_BURKERT) {              // GM = pi G rho r0, p1 = r0, p2 = 1 / r0
+                const double xb = r * P.p2[i];
+                const double br = log(fma(xb, xb, 1.0)) + 2.0 * log(1.0 + xb) - 2.0 * atan(xb);
+                f = P.GM[i] * br * rcp_fast(xb * xb) * ir;
             } else if (t == CW_COMP_KEPLER) {
                 f = P.GM[i] * ((ir * ir) * ir);
             } else if (t == CW_COMP_PLUMMER) {              // p2 = b^2
@@ -412,6 +424,13 @@ __device__ __forceinline__ double potential_value(const PotParams &P, double x, 
             v -= P.GM[i] / sqrt(fma(zd, zd, R2));
         } else if (t == CW_COMP_HERNQUIST) {
             v -= P.GM[i] / (r + P.p1[i]);
+        } else if (t == CW_COMP_KUZMIN) {
+            const double az = P.p1[i] + fabs(z);
+            v -= P.GM[i] / sqrt(fma(az, az, R2));
+        } else if (t == CW_COMP_BURKERT) {
+            const double xb = r * P.p2[i], ix = 1.0 / xb;
+            v -= P.GM[i] * P.p1[i] * (3.14159265358979323846 - 2.0 * (1.0 + ix) * atan(xb) + 2.0 * (1.0 + ix) * log(1.0 + xb)
+                                      - (1.0 - ix) * log(fma(xb, xb, 1.0)));
         } else if (t == CW_COMP_KEPLER) {
             v -= P.GM[i] / r;
         } else if (t == CW_COMP_PLUMMER) {

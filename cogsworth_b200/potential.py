@@ -29,10 +29,13 @@ COMP_PLUMMER = 5          # params (m, b, -)
 COMP_ISOCHRONE = 6        # params (m, b, -)
 COMP_JAFFE = 7            # params (m, c, -)
 COMP_LOGARITHMIC = 8      # params (v_c [kpc/Myr], r_h, q3), q1 = q2 = 1
+COMP_KUZMIN = 9           # params (m, a, -)
+COMP_BURKERT = 10         # params (rho [Msun/kpc^3], r0, -)
 
 _COMP_NAMES = {COMP_MIYAMOTO_NAGAI: "MiyamotoNagai", COMP_HERNQUIST: "Hernquist",
                COMP_NFW_SPHERICAL: "NFW", COMP_KEPLER: "Kepler", COMP_PLUMMER: "Plummer",
-               COMP_ISOCHRONE: "Isochrone", COMP_JAFFE: "Jaffe", COMP_LOGARITHMIC: "Logarithmic"}
+               COMP_ISOCHRONE: "Isochrone", COMP_JAFFE: "Jaffe", COMP_LOGARITHMIC: "Logarithmic",
+               COMP_KUZMIN: "Kuzmin", COMP_BURKERT: "Burkert"}
 
 # Smith+2015 three-Miyamoto-Nagai fit to an exponential disk, positive-density variant
 # (the table gala's MN3ExponentialDiskPotential uses with positive_density=True).
@@ -140,6 +143,12 @@ def from_gala(potential) -> CompositePotential:
             names.append(name); types.append(COMP_PLUMMER); params.append((p["m"], p["b"], 0.0))
         elif cls == "IsochronePotential":
             names.append(name); types.append(COMP_ISOCHRONE); params.append((p["m"], p["b"], 0.0))
+        elif cls == "KuzminPotential":
+            names.append(name); types.append(COMP_KUZMIN); params.append((p["m"], p["a"], 0.0))
+        elif cls == "BurkertPotential":
+            names.append(name); types.append(COMP_BURKERT); params.append((p["rho"], p["r0"], 0.0))
+        elif cls == "NullPotential":
+            continue                                   # free motion: contributes nothing
         elif cls == "JaffePotential":
             names.append(name); types.append(COMP_JAFFE); params.append((p["m"], p["c"], 0.0))
         elif (cls == "LogarithmicPotential" and abs(p.get("q1", 1.0) - 1.0) < 1e-12
@@ -148,6 +157,6 @@ def from_gala(potential) -> CompositePotential:
         else:
             raise NotImplementedError(
                 f"component {name!r} ({cls}) has no sm_100a kernel; supported: MiyamotoNagai, "
-                "MN3ExponentialDisk, Hernquist, spherical NFW, Kepler, Plummer, Isochrone, Jaffe, "
-                "axisymmetric Logarithmic")
+                "MN3ExponentialDisk, Hernquist, spherical NFW, Kepler, Plummer, Isochrone, Jaffe, Kuzmin, "
+                "Burkert, Null, axisymmetric Logarithmic")
     return CompositePotential(names=names, types=types, params=params, G=G, label=type(potential).__name__)

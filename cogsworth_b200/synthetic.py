@@ -47,6 +47,13 @@ def _host_circular_velocity(pot: CompositePotential, x, y, z):
             qdotg += GM / (s * (s + a) ** 2) * r * r
         elif t == 7:
             qdotg += GM / (r + a)
+        elif t == 9:
+            az = a + np.abs(z)
+            f = GM * (x * x + y * y + az * az) ** -1.5
+            qdotg += f * (x * x + y * y) + f * az * np.abs(z)
+        elif t == 10:                                    # Burkert (rho, r0)
+            xb = r / a
+            qdotg += np.pi * pot.G * m * a / xb ** 2 * (np.log(1 + xb * xb) + 2 * np.log(1 + xb) - 2 * np.arctan(xb)) * r
         elif t == 8:                                     # (v_c, r_h, q3)
             fac = m * m / (a * a + x * x + y * y + z * z / (b * b))
             qdotg += fac * (x * x + y * y) + fac * z * z / (b * b)

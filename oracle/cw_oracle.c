@@ -52,6 +52,8 @@
 #define CWO_COMP_ISOCHRONE 6    /* (m, b, -) */
 #define CWO_COMP_JAFFE 7        /* (m, c, -) */
 #define CWO_COMP_LOGARITHMIC 8  /* (v_c, r_h, q3) with q1 = q2 = 1 (axisymmetric) */
+#define CWO_COMP_KUZMIN 9       /* (m, a, -) */
+#define CWO_COMP_BURKERT 10     /* (rho, r0, -) */
 
 #define CWO_LEAPFROG 0
 #define CWO_DOP853 1        /* restarted on every grid interval */
@@ -120,7 +122,9 @@ static void nfw_gradient(double G, const double *p, const double *q, double *gra
  *   isochrone_gradient   fac = G m / (s (s + b)^2),  s = sqrt(r^2 + b^2)
  *   jaffe_gradient       fac = G m / (r^2 (r + c))          [Phi = G m / c ln(r / (r + c))]
  *   logarithmic_gradient fac = v_c^2 / (r_h^2 + x^2/q1^2 + y^2/q2^2 + z^2/q3^2), grad_i = fac q_i / q_i^2
- *                        (only q1 = q2 = 1: the kernels factor the gradient as (Fxy x, Fxy y, Fz z)) */
+ *                        (only q1 = q2 = 1: the kernels factor the gradient as (Fxy x, Fxy y, Fz z))
+ *   kuzmin_gradient      fac = G m / (R^2 + (a + |z|)^2)^1.5, grad = (fac x, fac y, fac (a + |z|) sign z)
+ *   burkert_gradient     dPhi/dr = pi G rho r0 (ln(1 + x^2) + 2 ln(1 + x) - 2 atan x) / x^2,  x = r / r0 */
 static void extra_gradient(int type, double G, const double *p, const double *q, double *grad)
 {
     double r2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
@@ -136,6 +140,15 @@ static void extra_gradient(int type, double G, const double *p, const double *q,
     } else if (type == CWO_COMP_JAFFE) {
         double R = sqrt(r2);
         fxy = fz = G * p[0] / (R * R * (R + p[1]));
+    } else if (type == CWO_COMP_KUZMIN) {
+        double az = p[1] + fabs(q[2]);
+        double fac = G * p[0] / pow(q[0] * q[0] + q[1] * q[1] + az * az, 1.5);
+        fxy = fac;
+        fz = (q[2] != 0.0) ? fac * az / fabs(q[2]) : 0.0;    /* fz z = fac (a + |z|) sign z */
+    } else if (type == CWO_COMP_BURKERT) {
+        double R = sqrt(r2), x = R / p[1];
+        double dphi_dr = M_PI * G * p[0] * p[1] / (x * x) * (log(1. + x * x) + 2. * log(1. + x) - 2. * atan(x));
+        fxy = fz = dphi_dr / R;
     } else { /* CWO_COMP_LOGARITHMIC */
         double fac = p[0] * p[0] / (p[1] * p[1] + q[0] * q[0] + q[1] * q[1] + q[2] * q[2] / (p[2] * p[2]));
         fxy = fac;
@@ -156,7 +169,8 @@ void cwo_gradient(const cwo_potential *P, const double *q, double *grad)
         case CWO_COMP_HERNQUIST: hernquist_gradient(P->G, P->p[i], q, grad); break;
         case CWO_COMP_NFW: nfw_gradient(P->G, P->p[i], q, grad); break;
         case CWO_COMP_KEPLER: case CWO_COMP_PLUMMER: case CWO_COMP_ISOCHRONE: case CWO_COMP_JAFFE:
-        case CWO_COMP_LOGARITHMIC: extra_gradient(P->type[i], P->G, P->p[i], q, grad); break;
+        case CWO_COMP_LOGARITHMIC: case CWO_COMP_KUZMIN: case CWO_COMP_BURKERT:
+            extra_gradient(P->type[i], P->G, P->p[i], q, grad); break;
         default: grad[0] = grad[1] = grad[2] = NAN;
         }
     }
@@ -178,6 +192,14 @@ double cwo_value(const cwo_potential *P, const double *q)
             double u = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]) / p[1];
             double v_h2 = -P->G * p[0] / p[1];
             v += v_h2 * log(1 + u) / u;
+        } else if (P->type[i] == CWO_COMP_KUZMIN) {
+            double az = p[1] + fabs(q[2]);
+            v += -P->G * p[0] / sqrt(q[0] * q[0] + q[1] * q[1] + az * az);
+        } else if (P->type[i] == CWO_COMP_BURKERT) {
+            /* Mori & Burkert 2000, as gala's burkert_value */
+            double x = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]) / p[1];
+            v += -M_PI * P->G * p[0] * p[1] * p[1] * (M_PI - 2. * (1. + 1. / x) * atan(x) + 2. * (1. + 1. / x) * log(1. + x)
+                                                     - (1. - 1. / x) * log(1. + x * x));
         } else if (P->type[i] >= CWO_COMP_KEPLER && P->type[i] <= CWO_COMP_LOGARITHMIC) {
             double r2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2], R = sqrt(r2);
             switch (P->type[i]) {

@@ -139,9 +139,9 @@ def test_extra_components_gradient_is_derivative_of_value(oracle):
     are the derivatives of the restated potential values, alone and inside a composite."""
     from cogsworth_b200.potential import CompositePotential
     singles = [(4, (3e10, 0.0, 0.0)), (5, (2e10, 1.3, 0.0)), (6, (5e10, 2.1, 0.0)), (7, (4e10, 3.0, 0.0)),
-               (8, (0.2, 1.5, 0.8))]
+               (8, (0.2, 1.5, 0.8)), (9, (3e10, 2.5, 0.0)), (10, (2e7, 9.0, 0.0))]
     pots = [CompositePotential(names=["c"], types=[t], params=[p]) for t, p in singles]
-    pots.append(CompositePotential(names=list("abcdefg"), types=[1, 4, 5, 6, 7, 8, 3],
+    pots.append(CompositePotential(names=list("abcdefghi"), types=[1, 4, 5, 6, 7, 8, 9, 10, 3],
                                    params=[(5e10, 3.0, 0.3)] + [p for _, p in singles] + [(5e11, 16.0, 0.0)]))
     rng = np.random.default_rng(3)
     for pot in pots:
@@ -156,6 +156,13 @@ def test_extra_components_gradient_is_derivative_of_value(oracle):
     assert abs(vk - np.sqrt(pots[0].G * 3e10 / 4.0)) < 1e-15
     vl = oracle.circular_velocity(pots[4], [400.0, 0.0, 0.0])
     assert abs(vl - 0.2) < 1e-5
+    # Burkert: enclosed mass pi rho r0^3 (ln(1+x^2) + 2 ln(1+x) - 2 atan x) at x = 1; Kuzmin is even in z
+    rho, r0 = 2e7, 9.0
+    m_enc = np.pi * rho * r0 ** 3 * (np.log(2.0) + 2 * np.log(2.0) - 2 * np.arctan(1.0))
+    vb = oracle.circular_velocity(pots[6], [r0, 0.0, 0.0])
+    assert abs(vb - np.sqrt(pots[6].G * m_enc / r0)) < 1e-15
+    gk_up, gk_dn = oracle.gradient(pots[5], [3.0, 1.0, 0.7]), oracle.gradient(pots[5], [3.0, 1.0, -0.7])
+    assert gk_up[2] == -gk_dn[2] and gk_up[0] == gk_dn[0]
 
 
 def test_leapfrog_reversible_and_energy(oracle):
