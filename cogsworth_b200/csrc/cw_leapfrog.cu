@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(256) grid_prepass_kernel(const __grid_constant
     // a kick on the final node leaves no tail segment: the reference cannot stitch such an orbit
     if (n_nodes <= 0 || (cursor >= n_nodes - 1 && (e1 > (A.ev_off ? A.ev_off[i] - A.ev_base : 0))))
         st = CW_ORBIT_INCONSISTENT;
+    // store_all: the caller's trajectory slot must hold every node (a too-small slot would overwrite the next orbit)
+    if (A.traj_off && st == CW_ORBIT_OK && A.traj_off[i + 1] - A.traj_off[i] < (int64_t)n_nodes) st = CW_ORBIT_CAPACITY;
     A.n_nodes[i] = n_nodes;
     A.status[i] = st;
     if (A.t_last) A.t_last[i] = Tprev;     // time of node n_acc - 1 (DOP853 dense mode: end of the last segment)

@@ -313,3 +313,30 @@ def test_host_store_all_streams_through_bounded_buffers(ctx, monkeypatch):
     monkeypatch.delenv("CW_TRAJ_SHARD_COLS")
     ref2 = ctx.integrate(*args, integrator=_lib.DOP853_DENSE, store_all=True)
     assert np.array_equal(ref2["traj_pos"], cut2["traj_pos"])
+
+
+def test_trajectory_slot_too_small_is_reported_not_overrun(ctx):
+    """A caller-supplied traj_off whose slot is smaller than an orbit's node count: that orbit is rejected with
+    CW_ORBIT_CAPACITY (-6) and every other orbit's slot holds exactly its trajectory (no overrun into a neighbour)."""
+    pop = make_population(40, cfg_id=71, f_sn=0.0, horizon_gyr=0.05)            # 50 nodes each
+    b = pop.batch
+    n = b.n_orbits
+    ctx.set_potential(pop.potential)
+    good = ctx.integrate(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, integrator=_lib.LEAPFROG, store_all=True)
+    lens = good["n_nodes"].astype(np.int64).copy()
+    lens[3] -= 7                                                                 # too small
+    lens[5] += 4                                                                 # larger than needed: fine
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    tp = np.full((3, off[-1]), np.nan); tv = np.full((3, off[-1]), np.nan); tt = np.full(off[-1], np.nan)
+    wf = np.empty((6, n)); st = np.empty(n, dtype=np.int32); nn = np.empty(n, dtype=np.int32)
+    ctx.integrate_raw(n, b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, None, None, None, wf, st, nn, None, off, tp, tv, tt, None,
+                      integrator=_lib.LEAPFROG, mem_space=_lib.MEM_HOST)
+    assert st[3] == -6 and (np.delete(st, 3) == 0).all()
+    # (the columns of a rejected orbit, and the slack of an over-sized slot, are unspecified: host-buffer calls
+    # copy the device buffer of the whole shard back)
+    goff = good["traj_off"]
+    for i in (0, 2, 4, 5, n - 1):
+        m = good["n_nodes"][i]
+        assert np.array_equal(tp[:, off[i]:off[i] + m], good["traj_pos"][:, goff[i]:goff[i] + m])
+    assert np.array_equal(wf[:, 5], good["w_final"][:, 5]) and np.array_equal(nn, good["n_nodes"])
