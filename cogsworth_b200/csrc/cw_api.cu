@@ -572,6 +572,7 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
             if ((rc = fetch_i64(ctx, R->traj_off + sh.b, dev_mode, &sh.tb)) != CW_OK) return rc;
         }
         if (sh.eb < sh.ea || sh.tb < sh.ta) return fail(ctx, CW_E_INVALID, "offsets must be non-decreasing");
+        if (sh.eb > sh.ea && (!B->ev_time || !B->ev_dv)) return fail(ctx, CW_E_INVALID, "ev_off lists events but ev_time / ev_dv is null");
     }
     cw_result Rl;
     memset(&Rl, 0, sizeof Rl);
