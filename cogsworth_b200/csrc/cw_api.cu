@@ -21,6 +21,13 @@ using namespace cw;
 
 namespace {
 
+// restores the caller's current device on every exit path (the CW_CK macro returns early on CUDA errors)
+struct DeviceGuard {
+    int prev = 0;
+    DeviceGuard() { cudaGetDevice(&prev); }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
 struct Arena {
     char *base = nullptr;
     size_t cap = 0, used = 0;
@@ -509,8 +516,8 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
     const bool store_all = integrate && R->traj_off;
     if (store_all && (!R->traj_pos || !R->traj_vel)) return fail(ctx, CW_E_INVALID, "traj_pos / traj_vel missing");
 
-    int prev = 0;
-    cudaGetDevice(&prev);
+    DeviceGuard guard;
+    const int prev = guard.prev;
     // ---- cut the batch: by index over the device slots, then (host buffers) into pipelined chunks
     const int nslots = dev_mode ? 1 : (int)std::min<int64_t>((int64_t)ctx->slots.size(), std::max<int64_t>(1, n));
     std::vector<Shard> shards;
