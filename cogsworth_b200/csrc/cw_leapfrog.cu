@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
         // with grad = (Fxy x, Fxy y, Fz z) folded into the FMAs: vh = fma(Fxy * (-dt), x, vh).
         const double dt = s.dt, ndt = -s.dt, nhdt = -0.5 * s.dt;
         if (!STORE) {
-#pragma unroll 2
+#pragma unroll 4
             for (int q = 1; q < m; q++) {   // c_leapfrog_step without the synchronised velocity
                 s.x = fma(s.vhx, dt, s.x);
                 s.y = fma(s.vhy, dt, s.y);
