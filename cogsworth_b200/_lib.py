@@ -24,7 +24,7 @@ ORBIT_STATUS = {0: "ok", -1: "inconsistent input", -2: "larger nmax is needed",
                 -3: "step size becomes too small", -4: "problem is probably stiff",
                 -5: "non-finite error norm", -6: "trajectory slot too small"}
 
-EXPORTS = ["cw_create", "cw_destroy", "cw_device_count", "cw_set_potential", "cw_count_nodes",
+EXPORTS = ["cw_create", "cw_destroy", "cw_device_count", "cw_set_potential", "cw_set_potential_ex", "cw_count_nodes",
            "cw_integrate", "cw_gradient", "cw_potential_value", "cw_circular_velocity", "cw_strerror",
            "cw_last_error", "cw_abi_version", "cw_last_launch_count", "cw_last_kernel_ms",
            "cw_last_total_kernel_ms", "cw_measure_fp64_peak", "cw_measure_scatter_write", "cw_selftest_math"]
@@ -74,6 +74,8 @@ def load():
     L.cw_device_count.restype = C.c_int
     L.cw_set_potential.argtypes = [vp, C.c_double, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     L.cw_set_potential.restype = C.c_int
+    L.cw_set_potential_ex.argtypes = [vp, C.c_double, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_int]
+    L.cw_set_potential_ex.restype = C.c_int
     L.cw_count_nodes.argtypes = [vp, C.POINTER(CwOpts), C.POINTER(CwBatch), vp, vp]
     L.cw_count_nodes.restype = C.c_int
     L.cw_integrate.argtypes = [vp, C.POINTER(CwOpts), C.POINTER(CwBatch), C.POINTER(CwResult)]
@@ -166,10 +168,11 @@ class Context:
     def set_potential(self, pot):
         types = np.ascontiguousarray(pot.type_array(), dtype=np.int32)
         params = np.ascontiguousarray(pot.param_array(), dtype=np.float64)
-        rc = self._L.cw_set_potential(self._h, float(pot.G), len(types),
-                                      types.ctypes.data_as(C.POINTER(C.c_int32)),
-                                      params.ctypes.data_as(C.POINTER(C.c_double)))
-        self._check(rc, "cw_set_potential")
+        stride = params.shape[1] if params.ndim == 2 and params.shape[0] else 3
+        rc = self._L.cw_set_potential_ex(self._h, float(pot.G), len(types),
+                                         types.ctypes.data_as(C.POINTER(C.c_int32)),
+                                         params.ctypes.data_as(C.POINTER(C.c_double)), int(stride))
+        self._check(rc, "cw_set_potential_ex")
         self.potential = pot
 
     # -- raw entry points (host or device pointers) ------------------------------------------

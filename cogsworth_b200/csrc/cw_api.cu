@@ -210,9 +210,22 @@ extern "C" void cw_destroy(cw_ctx *ctx)
 
 extern "C" int cw_device_count(const cw_ctx *ctx) { return ctx ? (int)ctx->slots.size() : 0; }
 
+extern "C" int cw_set_potential_ex(cw_ctx *ctx, double G, int n_comp, const int32_t *types, const double *params_in, int stride);
+
 extern "C" int cw_set_potential(cw_ctx *ctx, double G, int n_comp, const int32_t *types, const double *params)
 {
-    if (!ctx || n_comp < 0 || n_comp > CW_MAX_COMPONENTS || (n_comp > 0 && (!types || !params)))
+    return cw_set_potential_ex(ctx, G, n_comp, types, params, 3);
+}
+
+extern "C" int cw_set_potential_ex(cw_ctx *ctx, double G, int n_comp, const int32_t *types, const double *params_in, int stride)
+{
+    if (stride < 3 || stride > 6) return fail(ctx, CW_E_INVALID, "cw_set_potential_ex: stride must be 3..6");
+    // the three leading parameters in the layout the rest of this function reads
+    double params[3 * CW_MAX_COMPONENTS] = {0};
+    if (n_comp > 0 && n_comp <= CW_MAX_COMPONENTS && params_in)
+        for (int i = 0; i < n_comp; i++)
+            for (int k = 0; k < 3; k++) params[3 * i + k] = params_in[(size_t)stride * i + k];
+    if (!ctx || n_comp < 0 || n_comp > CW_MAX_COMPONENTS || (n_comp > 0 && (!types || !params_in)))
         return fail(ctx, CW_E_INVALID, "cw_set_potential: bad arguments");
     PotParams P;
     memset(&P, 0, sizeof P);
@@ -220,13 +233,22 @@ extern "C" int cw_set_potential(cw_ctx *ctx, double G, int n_comp, const int32_t
     P.G = G;
     for (int i = 0; i < n_comp; i++) {
         const int t = types[i];
-        if (t < CW_COMP_MIYAMOTO_NAGAI || t > CW_COMP_BURKERT)
+        if (t < CW_COMP_MIYAMOTO_NAGAI || t > CW_COMP_NFW_TRIAXIAL)
             return fail(ctx, CW_E_UNSUPPORTED, "cw_set_potential: unknown component type");
         P.type[i] = t;
         P.GM[i] = G * params[3 * i + 0];
         P.p1[i] = params[3 * i + 1];
         P.p2[i] = (t == CW_COMP_NFW_SPHERICAL) ? 1.0 / params[3 * i + 1] : params[3 * i + 2];
         if (t == CW_COMP_PLUMMER || t == CW_COMP_ISOCHRONE) P.p2[i] = params[3 * i + 1] * params[3 * i + 1];  // b^2
+        if (t == CW_COMP_NFW_TRIAXIAL) {
+            if (stride < 5) return fail(ctx, CW_E_INVALID, "cw_set_potential_ex: a triaxial NFW needs 5 parameters (m, r_s, a, b, c)");
+            const double *pp = params_in + (size_t)stride * i;
+            if (!(pp[2] > 0.0 && pp[3] > 0.0 && pp[4] > 0.0)) return fail(ctx, CW_E_INVALID, "cw_set_potential_ex: a, b, c must be > 0");
+            P.p2[i] = 1.0 / pp[1];                       // 1 / r_s
+            P.q2[i][0] = 1.0 / (pp[2] * pp[2]);          // 1 / a^2, 1 / b^2, 1 / c^2
+            P.q2[i][1] = 1.0 / (pp[3] * pp[3]);
+            P.q2[i][2] = 1.0 / (pp[4] * pp[4]);
+        }
         if (t == CW_COMP_BURKERT) {
             P.GM[i] = 3.14159265358979323846 * G * params[3 * i + 0] * params[3 * i + 1];   // pi G rho r0
             P.p2[i] = 1.0 / params[3 * i + 1];                                               // 1 / r0

@@ -149,6 +149,7 @@ struct PotParams {
     double GM[CW_MAX_COMPONENTS]; // fl(G * m), the same product gala forms on every call
     double p1[CW_MAX_COMPONENTS]; // a | c | r_s
     double p2[CW_MAX_COMPONENTS]; // b | - | 1/r_s
+    double q2[CW_MAX_COMPONENTS][3]; // triaxial NFW: 1/a^2, 1/b^2, 1/c^2
     // pre-digested copies for the specialised kinds (MN terms first, then the spherical ones)
     double mn_GM[3], mn_a[3], mn_b2[3];
     double h_GM[2], h_c[2];
@@ -306,12 +307,13 @@ __device__ __forceinline__ void force_mw(const PotParams &P, LogTab ltab,
 
 // Generic composite: components in the caller's order.
 __device__ __forceinline__ void force_generic(const PotParams &P, LogTab ltab,
-                                              double x, double y, double z, double &Fxy, double &Fz)
+                                              double x, double y, double z, double &Fxy, double &Fy, double &Fz)
 {
     const double R2 = fma(y, y, x * x);
     const double z2 = z * z;
     const double r2 = R2 + z2;
     double fxy = 0.0, fz = 0.0;
+    double fyx = 0.0;             // Fy - Fxy: non-zero only for components flattened differently in x and y
     double ir = 0.0, r = 0.0;
     bool have_r = false;
     for (int i = 0; i < P.n_comp; i++) {
@@ -335,6 +337,18 @@ __device__ __forceinline__ void force_generic(const PotParams &P, LogTab ltab,
                 const double inv = P.GM[i] * rcp_fast(fma(z2, P.p2[i], R2 + P.p1[i]));
                 fxy += inv;
                 fz = fma(inv, P.p2[i], fz);
+                continue;
+            }
+            if (t == CW_COMP_NFW_TRIAXIAL) {                // gradient = fac (x / a^2, y / b^2, z / c^2), flattened radius
+                const double m2 = fma(z2, P.q2[i][2], fma(y * y, P.q2[i][1], (x * x) * P.q2[i][0]));
+                const double im = rsqrt_fast(m2);
+                const double u = (m2 * im) * P.p2[i];
+                const double w = 1.0 + u;
+                const double bracket = (ltab.on() ? log_tab(P, w, ltab) : log_fast(w)) - u * rcp_fast(w);
+                const double fac = P.GM[i] * ((im * im) * im) * bracket;
+                fxy = fma(fac, P.q2[i][0], fxy);
+                fyx = fma(fac, P.q2[i][1] - P.q2[i][0], fyx);
+                fz = fma(fac, P.q2[i][2], fz);
                 continue;
             }
             if (t == CW_COMP_KUZMIN) {                      // p1 = a; gz = f (a + |z|) sign z
@@ -375,6 +389,7 @@ __device__ __forceinline__ void force_generic(const PotParams &P, LogTab ltab,
         }
     }
     Fxy = fxy;
+    Fy = fxy + fyx;
     Fz = fz;
 }
 
@@ -386,7 +401,17 @@ __device__ __forceinline__ void force(const PotParams &P, LogTab ltab,
 {
     if (KIND == POT_MW_V1) force_mw<1, false>(P, ltab, x, y, z, Fxy, Fz);
     else if (KIND == POT_MW_V2) force_mw<3, true>(P, ltab, x, y, z, Fxy, Fz);
-    else force_generic(P, ltab, x, y, z, Fxy, Fz);
+    else { double Fy; force_generic(P, ltab, x, y, z, Fxy, Fy, Fz); }
+}
+
+// The same with the y factor separate: grad = (Fx x, Fy y, Fz z).  Fy = Fx for the axisymmetric Milky Way kinds; the
+// generic composite may contain components flattened along x or y (triaxial NFW).
+template <int KIND>
+__device__ __forceinline__ void force3(const PotParams &P, LogTab ltab,
+                                       double x, double y, double z, double &Fx, double &Fy, double &Fz)
+{
+    if (KIND == POT_GENERIC) force_generic(P, ltab, x, y, z, Fx, Fy, Fz);
+    else { force<KIND>(P, ltab, x, y, z, Fx, Fz); Fy = Fx; }
 }
 
 template <int KIND>
@@ -394,10 +419,10 @@ __device__ __forceinline__ void gradient(const PotParams &P, LogTab ltab,
                                          double x, double y, double z,
                                          double &gx, double &gy, double &gz)
 {
-    double Fxy, Fz;
-    force<KIND>(P, ltab, x, y, z, Fxy, Fz);
-    gx = Fxy * x;
-    gy = Fxy * y;
+    double Fx, Fy, Fz;
+    force3<KIND>(P, ltab, x, y, z, Fx, Fy, Fz);
+    gx = Fx * x;
+    gy = Fy * y;
     gz = Fz * z;
 }
 
@@ -424,6 +449,9 @@ __device__ __forceinline__ double potential_value(const PotParams &P, double x, 
             v -= P.GM[i] / sqrt(fma(zd, zd, R2));
         } else if (t == CW_COMP_HERNQUIST) {
             v -= P.GM[i] / (r + P.p1[i]);
+        } else if (t == CW_COMP_NFW_TRIAXIAL) {
+            const double u = sqrt(fma(z2, P.q2[i][2], fma(y * y, P.q2[i][1], (x * x) * P.q2[i][0]))) * P.p2[i];
+            v -= (P.GM[i] * P.p2[i]) * log(1.0 + u) / u;
         } else if (t == CW_COMP_KUZMIN) {
             const double az = P.p1[i] + fabs(z);
             v -= P.GM[i] / sqrt(fma(az, az, R2));

@@ -188,7 +188,8 @@ constexpr int LF_BLOCK_STORE = 512;
 struct Lane {
     double x, y, z, vx, vy, vz;     // state at node j (v synchronised only at sync nodes)
     double vhx, vhy, vhz;           // half-step velocity
-    double Fxy, Fz;                 // force factors at node j: grad = (Fxy x, Fxy y, Fz z)
+    double Fxy, Fy, Fz;             // force factors at node j: grad = (Fxy x, Fy y, Fz z); Fy = Fxy unless the generic
+                                    // composite holds a component flattened along x or y
     double dt;                      // leapfrog dt of the current segment (Myr)
     double hgrid, t2, smyr;         // grid step, end time (grid unit), grid unit -> Myr
     double tcur;                    // STORE only: grid time of node j
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
     int64_t col_base = 0;          // STORE: column of sample 0 of the current orbit
     Lane s;
     s.x = 8.0; s.y = 0.0; s.z = 0.0; s.vx = s.vy = s.vz = 0.0;
-    s.vhx = s.vhy = s.vhz = 0.0; s.Fxy = s.Fz = 0.0;
+    s.vhx = s.vhy = s.vhz = 0.0; s.Fxy = s.Fy = s.Fz = 0.0;
     s.dt = 0.0; s.hgrid = 0.0; s.t2 = 0.0; s.smyr = 1.0; s.tcur = 0.0;
     s.e = s.e1 = 0; s.oid = -1; s.j = 0; s.next = 0; s.L = 0; s.append = false;
     bool active = false, exhausted = false, staged = false;
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                     if (kicked) { // c_init_velocity of the new segment; the force at this node is already known
                         const double nhdt = -0.5 * s.dt;
                         s.vhx = fma(s.Fxy * nhdt, s.x, s.vx);
-                        s.vhy = fma(s.Fxy * nhdt, s.y, s.vy);
+                        s.vhy = fma(s.Fy * nhdt, s.y, s.vy);
                         s.vhz = fma(s.Fz * nhdt, s.z, s.vz);
                     }
                     s.next = (s.e < s.e1) ? A.ev_step[s.e] : s.L;
@@ -399,10 +400,10 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 staged = true;
             }
             if (s.L == 0) { write_final(A, s); continue; }
-            force<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fz);
+            force3<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
             const double nhdt = -0.5 * s.dt;
             s.vhx = fma(s.Fxy * nhdt, s.x, s.vx);
-            s.vhy = fma(s.Fxy * nhdt, s.y, s.vy);
+            s.vhy = fma(s.Fy * nhdt, s.y, s.vy);
             s.vhz = fma(s.Fz * nhdt, s.z, s.vz);
             s.next = (s.e < s.e1) ? A.ev_step[s.e] : s.L;
             active = true;
@@ -424,16 +425,18 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
         // store_all run bit for bit):  x += vh dt;  F = force(x);  v = vh - grad dt/2;  vh -= grad dt,
         // with grad = (Fxy x, Fxy y, Fz z) folded into the FMAs: vh = fma(Fxy * (-dt), x, vh).
         const double dt = s.dt, ndt = -s.dt, nhdt = -0.5 * s.dt;
+        constexpr bool TRI = (KIND == POT_GENERIC);    // only the generic composite can have Fy != Fx
         if (!STORE) {
 #pragma unroll 4
             for (int q = 1; q < m; q++) {   // c_leapfrog_step without the synchronised velocity
                 s.x = fma(s.vhx, dt, s.x);
                 s.y = fma(s.vhy, dt, s.y);
                 s.z = fma(s.vhz, dt, s.z);
-                force<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fz);
+                force3<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
                 const double a = s.Fxy * ndt, b = s.Fz * ndt;
+                const double ay = TRI ? s.Fy * ndt : a;
                 s.vhx = fma(a, s.x, s.vhx);
-                s.vhy = fma(a, s.y, s.vhy);
+                s.vhy = fma(ay, s.y, s.vhy);
                 s.vhz = fma(b, s.z, s.vhz);
             }
         } else {
@@ -446,14 +449,16 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 s.x = fma(s.vhx, dt, s.x);
                 s.y = fma(s.vhy, dt, s.y);
                 s.z = fma(s.vhz, dt, s.z);
-                force<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fz);
+                force3<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
                 const double ah = s.Fxy * nhdt, bh = s.Fz * nhdt;
+                const double ahy = TRI ? s.Fy * nhdt : ah;
                 s.vx = fma(ah, s.x, s.vhx);
-                s.vy = fma(ah, s.y, s.vhy);
+                s.vy = fma(ahy, s.y, s.vhy);
                 s.vz = fma(bh, s.z, s.vhz);
                 const double a = s.Fxy * ndt, b = s.Fz * ndt;
+                const double ay = TRI ? s.Fy * ndt : a;
                 s.vhx = fma(a, s.x, s.vhx);
-                s.vhy = fma(a, s.y, s.vhy);
+                s.vhy = fma(ay, s.y, s.vhy);
                 s.vhz = fma(b, s.z, s.vhz);
                 if (active) tw.stage(col_base + s.j + q, s.x, s.y, s.z, s.vx, s.vy, s.vz);
             }
@@ -462,14 +467,16 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
             s.x = fma(s.vhx, dt, s.x);
             s.y = fma(s.vhy, dt, s.y);
             s.z = fma(s.vhz, dt, s.z);
-            force<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fz);
+            force3<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
             const double ah = s.Fxy * nhdt, bh = s.Fz * nhdt;
+            const double ahy = TRI ? s.Fy * nhdt : ah;
             s.vx = fma(ah, s.x, s.vhx);
-            s.vy = fma(ah, s.y, s.vhy);
+            s.vy = fma(ahy, s.y, s.vhy);
             s.vz = fma(bh, s.z, s.vhz);
             const double a = s.Fxy * ndt, b = s.Fz * ndt;
+            const double ay = TRI ? s.Fy * ndt : a;
             s.vhx = fma(a, s.x, s.vhx);
-            s.vhy = fma(a, s.y, s.vhy);
+            s.vhy = fma(ay, s.y, s.vhy);
             s.vhz = fma(b, s.z, s.vhz);
         }
         staged = false;

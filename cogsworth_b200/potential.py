@@ -31,11 +31,13 @@ COMP_JAFFE = 7            # params (m, c, -)
 COMP_LOGARITHMIC = 8      # params (v_c [kpc/Myr], r_h, q3), q1 = q2 = 1
 COMP_KUZMIN = 9           # params (m, a, -)
 COMP_BURKERT = 10         # params (rho [Msun/kpc^3], r0, -)
+COMP_NFW_TRIAXIAL = 11    # params (m, r_s, a, b, c): gp.NFWPotential with flattening
+PARAM_STRIDE = 6          # doubles per component handed to cw_set_potential_ex
 
 _COMP_NAMES = {COMP_MIYAMOTO_NAGAI: "MiyamotoNagai", COMP_HERNQUIST: "Hernquist",
                COMP_NFW_SPHERICAL: "NFW", COMP_KEPLER: "Kepler", COMP_PLUMMER: "Plummer",
                COMP_ISOCHRONE: "Isochrone", COMP_JAFFE: "Jaffe", COMP_LOGARITHMIC: "Logarithmic",
-               COMP_KUZMIN: "Kuzmin", COMP_BURKERT: "Burkert"}
+               COMP_KUZMIN: "Kuzmin", COMP_BURKERT: "Burkert", COMP_NFW_TRIAXIAL: "TriaxialNFW"}
 
 # Smith+2015 three-Miyamoto-Nagai fit to an exponential disk, positive-density variant
 # (the table gala's MN3ExponentialDiskPotential uses with positive_density=True).
@@ -79,7 +81,11 @@ class CompositePotential:
         return np.asarray(self.types, dtype=np.int32)
 
     def param_array(self) -> np.ndarray:
-        return np.ascontiguousarray(np.asarray(self.params, dtype=np.float64).reshape(-1, 3))
+        """(n, PARAM_STRIDE) table, rows zero-padded (most components have three parameters or fewer)."""
+        out = np.zeros((len(self.params), PARAM_STRIDE), dtype=np.float64)
+        for i, p in enumerate(self.params):
+            out[i, :len(p)] = p
+        return out
 
     def describe(self) -> str:
         return ",".join(self.names)
@@ -137,6 +143,9 @@ def from_gala(potential) -> CompositePotential:
             names.append(name); types.append(COMP_HERNQUIST); params.append((p["m"], p["c"], 0.0))
         elif cls == "NFWPotential" and all(abs(p.get(k, 1.0) - 1.0) < 1e-12 for k in ("a", "b", "c")):
             names.append(name); types.append(COMP_NFW_SPHERICAL); params.append((p["m"], p["r_s"], 0.0))
+        elif cls == "NFWPotential":                     # flattened: the spherical formula in the flattened radius
+            names.append(name); types.append(COMP_NFW_TRIAXIAL)
+            params.append((p["m"], p["r_s"], p.get("a", 1.0), p.get("b", 1.0), p.get("c", 1.0)))
         elif cls == "KeplerPotential":
             names.append(name); types.append(COMP_KEPLER); params.append((p["m"], 0.0, 0.0))
         elif cls == "PlummerPotential":
@@ -158,5 +167,5 @@ def from_gala(potential) -> CompositePotential:
             raise NotImplementedError(
                 f"component {name!r} ({cls}) has no sm_100a kernel; supported: MiyamotoNagai, "
                 "MN3ExponentialDisk, Hernquist, spherical NFW, Kepler, Plummer, Isochrone, Jaffe, Kuzmin, "
-                "Burkert, Null, axisymmetric Logarithmic")
+                "Burkert, Null, axisymmetric Logarithmic, flattened NFW")
     return CompositePotential(names=names, types=types, params=params, G=G, label=type(potential).__name__)

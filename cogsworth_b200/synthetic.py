@@ -29,7 +29,8 @@ def _host_circular_velocity(pot: CompositePotential, x, y, z):
     for synthetic inputs (upstream of the hot path; the product's own version is cw_circular_velocity)."""
     r = np.sqrt(x * x + y * y + z * z)
     qdotg = np.zeros_like(r)
-    for t, (m, a, b) in zip(pot.types, pot.params):
+    for t, prm in zip(pot.types, pot.params):
+        m, a, b = (tuple(prm) + (0.0, 0.0))[:3]
         GM = pot.G * m
         if t == 1:
             sz = np.sqrt(z * z + b * b)
@@ -47,6 +48,11 @@ def _host_circular_velocity(pot: CompositePotential, x, y, z):
             qdotg += GM / (s * (s + a) ** 2) * r * r
         elif t == 7:
             qdotg += GM / (r + a)
+        elif t == 11:                                    # flattened NFW (m, r_s, a, b, c)
+            qa, qb, qc = prm[2], prm[3], prm[4]
+            u = np.sqrt(x * x / qa ** 2 + y * y / qb ** 2 + z * z / qc ** 2) / a
+            fac = GM / a / u ** 3 / (a * a) * (np.log(1 + u) - u / (1 + u))
+            qdotg += fac * (x * x / qa ** 2 + y * y / qb ** 2 + z * z / qc ** 2)
         elif t == 9:
             az = a + np.abs(z)
             f = GM * (x * x + y * y + az * az) ** -1.5

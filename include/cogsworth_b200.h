@@ -47,7 +47,8 @@ enum {
     CW_COMP_JAFFE = 7,          /* (m, c, unused) */
     CW_COMP_LOGARITHMIC = 8,    /* (v_c [kpc/Myr], r_h, q3) with q1 = q2 = 1 */
     CW_COMP_KUZMIN = 9,         /* (m, a, unused) */
-    CW_COMP_BURKERT = 10        /* (rho [Msun/kpc^3], r0, unused) */
+    CW_COMP_BURKERT = 10,       /* (rho [Msun/kpc^3], r0, unused) */
+    CW_COMP_NFW_TRIAXIAL = 11   /* (m, r_s, a, b, c): gp.NFWPotential with flattening; cw_set_potential_ex only */
 };
 
 /* integrators = the two gala Integrator classes cogsworth passes (pop.py:130, kicks.py:54) */
@@ -161,6 +162,8 @@ int cw_device_count(const cw_ctx *ctx);
  * analytic components in galactic units; G in kpc^3 / Msun / Myr^2. */
 int cw_set_potential(cw_ctx *ctx, double G, int n_components, const int32_t *types, const double *params);
 /* n_components = 0 is gala's NullPotential (free motion). */
+/* The same with `stride` (3..6) doubles per component, for components with more than three parameters. */
+int cw_set_potential_ex(cw_ctx *ctx, double G, int n_components, const int32_t *types, const double *params, int stride);
 
 /* The grid pre-pass alone: node count per orbit and the node index of every event.  Lets the
  * host size trajectory buffers (traj_off) before cw_integrate, and is the bit-exact

@@ -54,6 +54,7 @@
 #define CWO_COMP_LOGARITHMIC 8  /* (v_c, r_h, q3) with q1 = q2 = 1 (axisymmetric) */
 #define CWO_COMP_KUZMIN 9       /* (m, a, -) */
 #define CWO_COMP_BURKERT 10     /* (rho, r0, -) */
+#define CWO_COMP_NFW_TRIAXIAL 11 /* (m, r_s, a, b, c): NFWPotential with flattening (docs/tutorials/pop_settings/potentials.ipynb:141) */
 
 #define CWO_LEAPFROG 0
 #define CWO_DOP853 1        /* restarted on every grid interval */
@@ -74,7 +75,7 @@ typedef struct {
     double G;
     int32_t n;
     int32_t type[CWO_MAX_COMP];
-    double p[CWO_MAX_COMP][3];
+    double p[CWO_MAX_COMP][6];
 } cwo_potential;
 
 typedef struct {
@@ -159,6 +160,19 @@ static void extra_gradient(int type, double G, const double *p, const double *q,
     grad[2] = grad[2] + fz * q[2];
 }
 
+/* builtin_potentials.c: triaxialnfw_gradient, pars = (G, m, r_s, a, b, c) [gala-recall]:
+ * the spherical formula in the flattened radius u = sqrt(x^2/a^2 + y^2/b^2 + z^2/c^2) / r_s,
+ * gradient components divided by a^2, b^2, c^2 */
+static void triaxial_nfw_gradient(double G, const double *p, const double *q, double *grad)
+{
+    double v_h2 = G * p[0] / p[1];
+    double u = sqrt(q[0] * q[0] / (p[2] * p[2]) + q[1] * q[1] / (p[3] * p[3]) + q[2] * q[2] / (p[4] * p[4])) / p[1];
+    double fac = v_h2 / (u * u * u) / (p[1] * p[1]) * (log(1 + u) - u / (1 + u));
+    grad[0] = grad[0] + fac * q[0] / (p[2] * p[2]);
+    grad[1] = grad[1] + fac * q[1] / (p[3] * p[3]);
+    grad[2] = grad[2] + fac * q[2] / (p[4] * p[4]);
+}
+
 /* cpotential.c: c_gradient -- zero, then accumulate components in order */
 void cwo_gradient(const cwo_potential *P, const double *q, double *grad)
 {
@@ -168,6 +182,7 @@ void cwo_gradient(const cwo_potential *P, const double *q, double *grad)
         case CWO_COMP_MN: mn_gradient(P->G, P->p[i], q, grad); break;
         case CWO_COMP_HERNQUIST: hernquist_gradient(P->G, P->p[i], q, grad); break;
         case CWO_COMP_NFW: nfw_gradient(P->G, P->p[i], q, grad); break;
+        case CWO_COMP_NFW_TRIAXIAL: triaxial_nfw_gradient(P->G, P->p[i], q, grad); break;
         case CWO_COMP_KEPLER: case CWO_COMP_PLUMMER: case CWO_COMP_ISOCHRONE: case CWO_COMP_JAFFE:
         case CWO_COMP_LOGARITHMIC: case CWO_COMP_KUZMIN: case CWO_COMP_BURKERT:
             extra_gradient(P->type[i], P->G, P->p[i], q, grad); break;
@@ -192,6 +207,9 @@ double cwo_value(const cwo_potential *P, const double *q)
             double u = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]) / p[1];
             double v_h2 = -P->G * p[0] / p[1];
             v += v_h2 * log(1 + u) / u;
+        } else if (P->type[i] == CWO_COMP_NFW_TRIAXIAL) {
+            double u = sqrt(q[0] * q[0] / (p[2] * p[2]) + q[1] * q[1] / (p[3] * p[3]) + q[2] * q[2] / (p[4] * p[4])) / p[1];
+            v += -P->G * p[0] / p[1] * log(1 + u) / u;
         } else if (P->type[i] == CWO_COMP_KUZMIN) {
             double az = p[1] + fabs(q[2]);
             v += -P->G * p[0] / sqrt(q[0] * q[0] + q[1] * q[1] + az * az);

@@ -24,7 +24,7 @@ __all__ = ["build", "lib", "make_potential", "gradient", "value", "circular_velo
 
 class _Pot(C.Structure):
     _fields_ = [("G", C.c_double), ("n", C.c_int32), ("type", C.c_int32 * MAX_COMP),
-                ("p", (C.c_double * 3) * MAX_COMP)]
+                ("p", (C.c_double * 6) * MAX_COMP)]
 
 
 class _Stats(C.Structure):
@@ -100,8 +100,8 @@ def make_potential(pot) -> _Pot:
     assert P.n <= MAX_COMP
     for i, (t, p) in enumerate(zip(pot.types, pot.params)):
         P.type[i] = int(t)
-        for k in range(3):
-            P.p[i][k] = float(p[k])
+        for k in range(6):
+            P.p[i][k] = float(p[k]) if k < len(p) else 0.0
     return P
 
 

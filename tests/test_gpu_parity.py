@@ -228,6 +228,35 @@ def test_generic_kernel_extra_components(ctx, oracle):
         assert np.quantile(d, 0.9) < tol, (integ, np.quantile(d, [0.5, 0.9, 1]))
 
 
+def test_flattened_nfw_from_the_reference_tutorial(ctx, oracle):
+    """docs/tutorials/pop_settings/potentials.ipynb:141 swaps the Milky Way for gp.NFWPotential(m=6.09e11, r_s=10,
+    a=0.25): a halo flattened along x, i.e. grad = (Fx x, Fy y, Fz z) with Fx != Fy.  Pointwise and integrated
+    parity against the oracle, alone and inside a composite."""
+    tut = CompositePotential(names=["nfw"], types=[11], params=[(6.09e11, 10.0, 0.25, 1.0, 1.0)])
+    mix = CompositePotential(names=["disk", "bulge", "halo"], types=[1, 2, 11],
+                             params=[(6e10, 3.0, 0.28), (5e9, 1.0, 0.0), (5e11, 16.0, 1.0, 0.85, 0.7)])
+    rng = np.random.default_rng(3)
+    q = rng.normal(0, 7, (3, 1024))
+    for pot in (tut, mix):
+        ctx.set_potential(pot)
+        g, phi = ctx.gradient(q), ctx.potential_value(q)
+        for i in range(0, 1024, 16):
+            assert np.allclose(g[:, i], oracle.gradient(pot, q[:, i].copy()), rtol=1e-13, atol=1e-18)
+            assert abs(phi[i] - oracle.value(pot, q[:, i].copy())) < 1e-13 * abs(phi[i])
+        pop = make_population(200, cfg_id=15, potential=pot, horizon_gyr=0.3)
+        for integ, tol in ((_lib.LEAPFROG, 1e-10), (_lib.DOP853, 1e-7), (_lib.DOP853_DENSE, 1e-7)):
+            g_, o_ = run_both(ctx, oracle, pop, integ)
+            check_bit_exact_bookkeeping(g_, o_)
+            d = rel_diff(g_["w_final"], o_["w_final"])
+            assert np.quantile(d, 0.9) < tol, (pot.names, integ, np.quantile(d, [0.5, 0.9, 1]))
+        _local_step_check(ctx, oracle, pop, "flattened NFW")
+    # the three-parameter entry point still refuses it (it cannot carry a, b, c)
+    with pytest.raises(RuntimeError):
+        bad = CompositePotential(names=["nfw"], types=[11], params=[(6.09e11, 10.0, 0.25)])
+        bad.param_array = lambda: np.array([[6.09e11, 10.0, 0.25]])
+        ctx.set_potential(bad)
+
+
 def test_null_potential_is_free_motion(ctx):
     """gala's NullPotential (online-interface/potentials.py:103): zero components, straight lines."""
     pot = CompositePotential(names=[], types=[], params=[])

@@ -141,6 +141,8 @@ def test_extra_components_gradient_is_derivative_of_value(oracle):
     singles = [(4, (3e10, 0.0, 0.0)), (5, (2e10, 1.3, 0.0)), (6, (5e10, 2.1, 0.0)), (7, (4e10, 3.0, 0.0)),
                (8, (0.2, 1.5, 0.8)), (9, (3e10, 2.5, 0.0)), (10, (2e7, 9.0, 0.0))]
     pots = [CompositePotential(names=["c"], types=[t], params=[p]) for t, p in singles]
+    pots.append(CompositePotential(names=["tnfw"], types=[11], params=[(6.09e11, 10.0, 0.25, 1.0, 1.0)]))   # the tutorial's NFW
+    pots.append(CompositePotential(names=["tnfw2"], types=[11], params=[(5e11, 15.0, 1.0, 0.8, 0.6)]))
     pots.append(CompositePotential(names=list("abcdefghi"), types=[1, 4, 5, 6, 7, 8, 9, 10, 3],
                                    params=[(5e10, 3.0, 0.3)] + [p for _, p in singles] + [(5e11, 16.0, 0.0)]))
     rng = np.random.default_rng(3)
@@ -161,6 +163,11 @@ def test_extra_components_gradient_is_derivative_of_value(oracle):
     m_enc = np.pi * rho * r0 ** 3 * (np.log(2.0) + 2 * np.log(2.0) - 2 * np.arctan(1.0))
     vb = oracle.circular_velocity(pots[6], [r0, 0.0, 0.0])
     assert abs(vb - np.sqrt(pots[6].G * m_enc / r0)) < 1e-15
+    # a flattened NFW with a = b = c = 1 is the spherical one, bit for bit
+    sph = CompositePotential(names=["h"], types=[3], params=[(5e11, 15.0, 0.0)])
+    tri = CompositePotential(names=["h"], types=[11], params=[(5e11, 15.0, 1.0, 1.0, 1.0)])
+    qq = [3.0, -4.0, 1.5]
+    assert np.array_equal(oracle.gradient(sph, qq), oracle.gradient(tri, qq)) and oracle.value(sph, qq) == oracle.value(tri, qq)
     gk_up, gk_dn = oracle.gradient(pots[5], [3.0, 1.0, 0.7]), oracle.gradient(pots[5], [3.0, 1.0, -0.7])
     assert gk_up[2] == -gk_dn[2] and gk_up[0] == gk_dn[0]
 
