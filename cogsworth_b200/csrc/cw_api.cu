@@ -233,7 +233,7 @@ extern "C" int cw_set_potential_ex(cw_ctx *ctx, double G, int n_comp, const int3
     P.G = G;
     for (int i = 0; i < n_comp; i++) {
         const int t = types[i];
-        if (t < CW_COMP_MIYAMOTO_NAGAI || t > CW_COMP_NFW_TRIAXIAL)
+        if (t < CW_COMP_MIYAMOTO_NAGAI || t > CW_COMP_LOG_TRIAXIAL)
             return fail(ctx, CW_E_UNSUPPORTED, "cw_set_potential: unknown component type");
         P.type[i] = t;
         P.GM[i] = G * params[3 * i + 0];
@@ -246,6 +246,16 @@ extern "C" int cw_set_potential_ex(cw_ctx *ctx, double G, int n_comp, const int3
             if (!(pp[2] > 0.0 && pp[3] > 0.0 && pp[4] > 0.0)) return fail(ctx, CW_E_INVALID, "cw_set_potential_ex: a, b, c must be > 0");
             P.p2[i] = 1.0 / pp[1];                       // 1 / r_s
             P.q2[i][0] = 1.0 / (pp[2] * pp[2]);          // 1 / a^2, 1 / b^2, 1 / c^2
+            P.q2[i][1] = 1.0 / (pp[3] * pp[3]);
+            P.q2[i][2] = 1.0 / (pp[4] * pp[4]);
+        }
+        if (t == CW_COMP_LOG_TRIAXIAL) {
+            if (stride < 5) return fail(ctx, CW_E_INVALID, "cw_set_potential_ex: a triaxial logarithmic halo needs 5 parameters");
+            const double *pp = params_in + (size_t)stride * i;
+            if (!(pp[2] > 0.0 && pp[3] > 0.0 && pp[4] > 0.0)) return fail(ctx, CW_E_INVALID, "cw_set_potential_ex: q1, q2, q3 must be > 0");
+            P.GM[i] = pp[0] * pp[0];                     // v_c^2
+            P.p1[i] = pp[1] * pp[1];                     // r_h^2
+            P.q2[i][0] = 1.0 / (pp[2] * pp[2]);
             P.q2[i][1] = 1.0 / (pp[3] * pp[3]);
             P.q2[i][2] = 1.0 / (pp[4] * pp[4]);
         }

@@ -351,6 +351,14 @@ __device__ __forceinline__ void force_generic(const PotParams &P, LogTab ltab,
                 fz = fma(fac, P.q2[i][2], fz);
                 continue;
             }
+            if (t == CW_COMP_LOG_TRIAXIAL) {                // GM = v_c^2, p1 = r_h^2, q2 = 1 / q_i^2
+                const double S = fma(z2, P.q2[i][2], fma(y * y, P.q2[i][1], fma(x * x, P.q2[i][0], P.p1[i])));
+                const double fac = P.GM[i] * rcp_fast(S);
+                fxy = fma(fac, P.q2[i][0], fxy);
+                fyx = fma(fac, P.q2[i][1] - P.q2[i][0], fyx);
+                fz = fma(fac, P.q2[i][2], fz);
+                continue;
+            }
             if (t == CW_COMP_KUZMIN) {                      // p1 = a; gz = f (a + |z|) sign z
                 const double az = P.p1[i] + fabs(z);
                 const double is = rsqrt_fast(fma(az, az, R2));
@@ -449,6 +457,8 @@ __device__ __forceinline__ double potential_value(const PotParams &P, double x, 
             v -= P.GM[i] / sqrt(fma(zd, zd, R2));
         } else if (t == CW_COMP_HERNQUIST) {
             v -= P.GM[i] / (r + P.p1[i]);
+        } else if (t == CW_COMP_LOG_TRIAXIAL) {
+            v += 0.5 * P.GM[i] * log(fma(z2, P.q2[i][2], fma(y * y, P.q2[i][1], fma(x * x, P.q2[i][0], P.p1[i]))));
         } else if (t == CW_COMP_NFW_TRIAXIAL) {
             const double u = sqrt(fma(z2, P.q2[i][2], fma(y * y, P.q2[i][1], (x * x) * P.q2[i][0]))) * P.p2[i];
             v -= (P.GM[i] * P.p2[i]) * log(1.0 + u) / u;

@@ -32,12 +32,13 @@ COMP_LOGARITHMIC = 8      # params (v_c [kpc/Myr], r_h, q3), q1 = q2 = 1
 COMP_KUZMIN = 9           # params (m, a, -)
 COMP_BURKERT = 10         # params (rho [Msun/kpc^3], r0, -)
 COMP_NFW_TRIAXIAL = 11    # params (m, r_s, a, b, c): gp.NFWPotential with flattening
+COMP_LOG_TRIAXIAL = 12    # params (v_c, r_h, q1, q2, q3), phi = 0
 PARAM_STRIDE = 6          # doubles per component handed to cw_set_potential_ex
 
 _COMP_NAMES = {COMP_MIYAMOTO_NAGAI: "MiyamotoNagai", COMP_HERNQUIST: "Hernquist",
                COMP_NFW_SPHERICAL: "NFW", COMP_KEPLER: "Kepler", COMP_PLUMMER: "Plummer",
                COMP_ISOCHRONE: "Isochrone", COMP_JAFFE: "Jaffe", COMP_LOGARITHMIC: "Logarithmic",
-               COMP_KUZMIN: "Kuzmin", COMP_BURKERT: "Burkert", COMP_NFW_TRIAXIAL: "TriaxialNFW"}
+               COMP_KUZMIN: "Kuzmin", COMP_BURKERT: "Burkert", COMP_NFW_TRIAXIAL: "TriaxialNFW", COMP_LOG_TRIAXIAL: "TriaxialLogarithmic"}
 
 # Smith+2015 three-Miyamoto-Nagai fit to an exponential disk, positive-density variant
 # (the table gala's MN3ExponentialDiskPotential uses with positive_density=True).
@@ -163,6 +164,9 @@ def from_gala(potential) -> CompositePotential:
         elif (cls == "LogarithmicPotential" and abs(p.get("q1", 1.0) - 1.0) < 1e-12
               and abs(p.get("q2", 1.0) - 1.0) < 1e-12):
             names.append(name); types.append(COMP_LOGARITHMIC); params.append((p["v_c"], p["r_h"], p.get("q3", 1.0)))
+        elif cls == "LogarithmicPotential" and abs(p.get("phi", 0.0)) < 1e-15:
+            names.append(name); types.append(COMP_LOG_TRIAXIAL)
+            params.append((p["v_c"], p["r_h"], p.get("q1", 1.0), p.get("q2", 1.0), p.get("q3", 1.0)))
         else:
             raise NotImplementedError(
                 f"component {name!r} ({cls}) has no sm_100a kernel; supported: MiyamotoNagai, "

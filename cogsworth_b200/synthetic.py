@@ -53,6 +53,9 @@ def _host_circular_velocity(pot: CompositePotential, x, y, z):
             u = np.sqrt(x * x / qa ** 2 + y * y / qb ** 2 + z * z / qc ** 2) / a
             fac = GM / a / u ** 3 / (a * a) * (np.log(1 + u) - u / (1 + u))
             qdotg += fac * (x * x / qa ** 2 + y * y / qb ** 2 + z * z / qc ** 2)
+        elif t == 12:                                    # triaxial logarithmic (v_c, r_h, q1, q2, q3)
+            s2 = x * x / prm[2] ** 2 + y * y / prm[3] ** 2 + z * z / prm[4] ** 2
+            qdotg += m * m * s2 / (a * a + s2)
         elif t == 9:
             az = a + np.abs(z)
             f = GM * (x * x + y * y + az * az) ** -1.5

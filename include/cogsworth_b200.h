@@ -48,7 +48,8 @@ enum {
     CW_COMP_LOGARITHMIC = 8,    /* (v_c [kpc/Myr], r_h, q3) with q1 = q2 = 1 */
     CW_COMP_KUZMIN = 9,         /* (m, a, unused) */
     CW_COMP_BURKERT = 10,       /* (rho [Msun/kpc^3], r0, unused) */
-    CW_COMP_NFW_TRIAXIAL = 11   /* (m, r_s, a, b, c): gp.NFWPotential with flattening; cw_set_potential_ex only */
+    CW_COMP_NFW_TRIAXIAL = 11,  /* (m, r_s, a, b, c): gp.NFWPotential with flattening; cw_set_potential_ex only */
+    CW_COMP_LOG_TRIAXIAL = 12   /* (v_c, r_h, q1, q2, q3): LogarithmicPotential with axis ratios, phi = 0; _ex only */
 };
 
 /* integrators = the two gala Integrator classes cogsworth passes (pop.py:130, kicks.py:54) */

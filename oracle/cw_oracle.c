@@ -54,6 +54,7 @@
 #define CWO_COMP_LOGARITHMIC 8  /* (v_c, r_h, q3) with q1 = q2 = 1 (axisymmetric) */
 #define CWO_COMP_KUZMIN 9       /* (m, a, -) */
 #define CWO_COMP_BURKERT 10     /* (rho, r0, -) */
+#define CWO_COMP_LOG_TRIAXIAL 12 /* (v_c, r_h, q1, q2, q3), phi = 0: LogarithmicPotential with axis ratios */
 #define CWO_COMP_NFW_TRIAXIAL 11 /* (m, r_s, a, b, c): NFWPotential with flattening (docs/tutorials/pop_settings/potentials.ipynb:141) */
 
 #define CWO_LEAPFROG 0
@@ -173,6 +174,16 @@ static void triaxial_nfw_gradient(double G, const double *p, const double *q, do
     grad[2] = grad[2] + fac * q[2] / (p[4] * p[4]);
 }
 
+/* logarithmic_gradient with q1, q2, q3 and no rotation (phi = 0) [gala-recall]:
+ * fac = v_c^2 / (r_h^2 + x^2/q1^2 + y^2/q2^2 + z^2/q3^2), grad_i = fac q_i / q_i^2 */
+static void triaxial_log_gradient(const double *p, const double *q, double *grad)
+{
+    double fac = p[0] * p[0] / (p[1] * p[1] + q[0] * q[0] / (p[2] * p[2]) + q[1] * q[1] / (p[3] * p[3]) + q[2] * q[2] / (p[4] * p[4]));
+    grad[0] = grad[0] + fac * q[0] / (p[2] * p[2]);
+    grad[1] = grad[1] + fac * q[1] / (p[3] * p[3]);
+    grad[2] = grad[2] + fac * q[2] / (p[4] * p[4]);
+}
+
 /* cpotential.c: c_gradient -- zero, then accumulate components in order */
 void cwo_gradient(const cwo_potential *P, const double *q, double *grad)
 {
@@ -183,6 +194,7 @@ void cwo_gradient(const cwo_potential *P, const double *q, double *grad)
         case CWO_COMP_HERNQUIST: hernquist_gradient(P->G, P->p[i], q, grad); break;
         case CWO_COMP_NFW: nfw_gradient(P->G, P->p[i], q, grad); break;
         case CWO_COMP_NFW_TRIAXIAL: triaxial_nfw_gradient(P->G, P->p[i], q, grad); break;
+        case CWO_COMP_LOG_TRIAXIAL: triaxial_log_gradient(P->p[i], q, grad); break;
         case CWO_COMP_KEPLER: case CWO_COMP_PLUMMER: case CWO_COMP_ISOCHRONE: case CWO_COMP_JAFFE:
         case CWO_COMP_LOGARITHMIC: case CWO_COMP_KUZMIN: case CWO_COMP_BURKERT:
             extra_gradient(P->type[i], P->G, P->p[i], q, grad); break;
@@ -210,6 +222,8 @@ double cwo_value(const cwo_potential *P, const double *q)
         } else if (P->type[i] == CWO_COMP_NFW_TRIAXIAL) {
             double u = sqrt(q[0] * q[0] / (p[2] * p[2]) + q[1] * q[1] / (p[3] * p[3]) + q[2] * q[2] / (p[4] * p[4])) / p[1];
             v += -P->G * p[0] / p[1] * log(1 + u) / u;
+        } else if (P->type[i] == CWO_COMP_LOG_TRIAXIAL) {
+            v += 0.5 * p[0] * p[0] * log(p[1] * p[1] + q[0] * q[0] / (p[2] * p[2]) + q[1] * q[1] / (p[3] * p[3]) + q[2] * q[2] / (p[4] * p[4]));
         } else if (P->type[i] == CWO_COMP_KUZMIN) {
             double az = p[1] + fabs(q[2]);
             v += -P->G * p[0] / sqrt(q[0] * q[0] + q[1] * q[1] + az * az);

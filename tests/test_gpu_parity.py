@@ -233,8 +233,9 @@ def test_flattened_nfw_from_the_reference_tutorial(ctx, oracle):
     a=0.25): a halo flattened along x, i.e. grad = (Fx x, Fy y, Fz z) with Fx != Fy.  Pointwise and integrated
     parity against the oracle, alone and inside a composite."""
     tut = CompositePotential(names=["nfw"], types=[11], params=[(6.09e11, 10.0, 0.25, 1.0, 1.0)])
-    mix = CompositePotential(names=["disk", "bulge", "halo"], types=[1, 2, 11],
-                             params=[(6e10, 3.0, 0.28), (5e9, 1.0, 0.0), (5e11, 16.0, 1.0, 0.85, 0.7)])
+    mix = CompositePotential(names=["disk", "bulge", "halo", "loghalo"], types=[1, 2, 11, 12],
+                             params=[(6e10, 3.0, 0.28), (5e9, 1.0, 0.0), (3e11, 16.0, 1.0, 0.85, 0.7),
+                                     (0.12, 12.0, 1.38, 1.0, 1.36)])
     rng = np.random.default_rng(3)
     q = rng.normal(0, 7, (3, 1024))
     for pot in (tut, mix):

@@ -143,6 +143,7 @@ def test_extra_components_gradient_is_derivative_of_value(oracle):
     pots = [CompositePotential(names=["c"], types=[t], params=[p]) for t, p in singles]
     pots.append(CompositePotential(names=["tnfw"], types=[11], params=[(6.09e11, 10.0, 0.25, 1.0, 1.0)]))   # the tutorial's NFW
     pots.append(CompositePotential(names=["tnfw2"], types=[11], params=[(5e11, 15.0, 1.0, 0.8, 0.6)]))
+    pots.append(CompositePotential(names=["tlog"], types=[12], params=[(0.18, 12.0, 1.38, 1.0, 1.36)]))     # LM10-like axis ratios
     pots.append(CompositePotential(names=list("abcdefghi"), types=[1, 4, 5, 6, 7, 8, 9, 10, 3],
                                    params=[(5e10, 3.0, 0.3)] + [p for _, p in singles] + [(5e11, 16.0, 0.0)]))
     rng = np.random.default_rng(3)
