@@ -24,7 +24,8 @@ ORBIT_STATUS = {0: "ok", -1: "inconsistent input", -2: "larger nmax is needed",
                 -3: "step size becomes too small", -4: "problem is probably stiff",
                 -5: "non-finite error norm", -6: "trajectory slot too small"}
 
-EXPORTS = ["cw_create", "cw_destroy", "cw_device_count", "cw_set_potential", "cw_set_potential_ex", "cw_count_nodes",
+EXPORTS = ["cw_create", "cw_destroy", "cw_device_count", "cw_set_potential", "cw_set_potential_ex", "cw_set_potential_general",
+           "cw_set_potential_time", "cw_count_nodes",
            "cw_integrate", "cw_gradient", "cw_potential_value", "cw_circular_velocity", "cw_strerror",
            "cw_last_error", "cw_abi_version", "cw_last_launch_count", "cw_last_kernel_ms",
            "cw_last_total_kernel_ms", "cw_measure_fp64_peak", "cw_measure_scatter_write", "cw_selftest_math"]
@@ -76,6 +77,12 @@ def load():
     L.cw_set_potential.restype = C.c_int
     L.cw_set_potential_ex.argtypes = [vp, C.c_double, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_int]
     L.cw_set_potential_ex.restype = C.c_int
+    L.cw_set_potential_general.argtypes = [vp, C.c_double, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_int,
+                                           C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                                           C.POINTER(C.c_double), C.c_int]
+    L.cw_set_potential_general.restype = C.c_int
+    L.cw_set_potential_time.argtypes = [vp, C.c_double]
+    L.cw_set_potential_time.restype = C.c_int
     L.cw_count_nodes.argtypes = [vp, C.POINTER(CwOpts), C.POINTER(CwBatch), vp, vp]
     L.cw_count_nodes.restype = C.c_int
     L.cw_integrate.argtypes = [vp, C.POINTER(CwOpts), C.POINTER(CwBatch), C.POINTER(CwResult)]
@@ -169,10 +176,24 @@ class Context:
         types = np.ascontiguousarray(pot.type_array(), dtype=np.int32)
         params = np.ascontiguousarray(pot.param_array(), dtype=np.float64)
         stride = params.shape[1] if params.ndim == 2 and params.shape[0] else 3
-        rc = self._L.cw_set_potential_ex(self._h, float(pot.G), len(types),
-                                         types.ctypes.data_as(C.POINTER(C.c_int32)),
-                                         params.ctypes.data_as(C.POINTER(C.c_double)), int(stride))
-        self._check(rc, "cw_set_potential_ex")
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        rot = pot.rotation_array() if hasattr(pot, "rotation_array") else None
+        knots = pot.knot_arrays() if hasattr(pot, "knot_arrays") else None
+        if rot is None and knots is None:
+            rc = self._L.cw_set_potential_ex(self._h, float(pot.G), len(types), types.ctypes.data_as(ip),
+                                             params.ctypes.data_as(dp), int(stride))
+            self._check(rc, "cw_set_potential_ex")
+        else:       # rotated components / gp.TimeInterpolatedPotential: the general kernels
+            k_off, k_t, k_amp = knots if knots is not None else (None, None, None)
+            rc = self._L.cw_set_potential_general(
+                self._h, float(pot.G), len(types), types.ctypes.data_as(ip), params.ctypes.data_as(dp), int(stride),
+                None if rot is None else rot.ctypes.data_as(dp),
+                None if k_off is None else k_off.ctypes.data_as(ip),
+                None if k_t is None else k_t.ctypes.data_as(dp),
+                None if k_amp is None else k_amp.ctypes.data_as(dp),
+                1 if getattr(pot, "interp", "cubic") == "cubic" else 0)
+            self._check(rc, "cw_set_potential_general")
+        self._check(self._L.cw_set_potential_time(self._h, float(getattr(pot, "t_eval", 0.0))), "cw_set_potential_time")
         self.potential = pot
 
     # -- raw entry points (host or device pointers) ------------------------------------------

@@ -6,6 +6,7 @@
 // There is NO CPU fallback anywhere in this file: without a CUDA device cw_create fails with
 // CW_E_NO_DEVICE.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -217,7 +218,61 @@ extern "C" int cw_set_potential(cw_ctx *ctx, double G, int n_comp, const int32_t
     return cw_set_potential_ex(ctx, G, n_comp, types, params, 3);
 }
 
+static int set_potential_impl(cw_ctx *ctx, double G, int n_comp, const int32_t *types, const double *params_in, int stride,
+                              const double *rotations, const int32_t *knot_off, const double *knot_t,
+                              const double *knot_amp, int interp);
+
 extern "C" int cw_set_potential_ex(cw_ctx *ctx, double G, int n_comp, const int32_t *types, const double *params_in, int stride)
+{
+    return set_potential_impl(ctx, G, n_comp, types, params_in, stride, nullptr, nullptr, nullptr, nullptr, 0);
+}
+
+extern "C" int cw_set_potential_general(cw_ctx *ctx, double G, int n_comp, const int32_t *types, const double *params_in,
+                                        int stride, const double *rotations, const int32_t *knot_off,
+                                        const double *knot_t, const double *knot_amp, int interp)
+{
+    return set_potential_impl(ctx, G, n_comp, types, params_in, stride, rotations, knot_off, knot_t, knot_amp, interp);
+}
+
+extern "C" int cw_set_potential_time(cw_ctx *ctx, double t_myr)
+{
+    if (!ctx) return CW_E_INVALID;
+    ctx->pot.t_eval = t_myr;
+    return CW_OK;
+}
+
+// piecewise-cubic coefficients of the interpolant through (t_j, y_j), j = 0..n-1, on interval j in powers of (t - t_j):
+// CW_INTERP_LINEAR, or the natural cubic spline (second derivative zero at both ends; GSL's gsl_interp_cspline)
+static void spline_coefficients(int n, const double *t, const double *y, int interp, double (*c)[4])
+{
+    std::vector<double> M(n, 0.0);
+    if (interp == CW_INTERP_CUBIC && n > 2) {
+        // tridiagonal system for the interior second derivatives (Thomas algorithm)
+        std::vector<double> cp(n, 0.0), dp(n, 0.0);
+        for (int j = 1; j < n - 1; j++) {
+            const double h0 = t[j] - t[j - 1], h1 = t[j + 1] - t[j];
+            const double diag = 2.0 * (h0 + h1);
+            const double rhs = 6.0 * ((y[j + 1] - y[j]) / h1 - (y[j] - y[j - 1]) / h0);
+            const double den = diag - h0 * cp[j - 1];
+            cp[j] = h1 / den;
+            dp[j] = (rhs - h0 * dp[j - 1]) / den;
+        }
+        for (int j = n - 2; j >= 1; j--) M[j] = dp[j] - cp[j] * M[j + 1];
+    }
+    for (int j = 0; j < n; j++) {
+        c[j][0] = y[j]; c[j][1] = c[j][2] = c[j][3] = 0.0;
+        if (j + 1 < n) {
+            const double h = t[j + 1] - t[j];
+            c[j][1] = (y[j + 1] - y[j]) / h - h * (2.0 * M[j] + M[j + 1]) / 6.0;
+            c[j][2] = 0.5 * M[j];
+            c[j][3] = (M[j + 1] - M[j]) / (6.0 * h);
+        }
+    }
+}
+
+static int set_potential_impl(cw_ctx *ctx, double G, int n_comp, const int32_t *types, const double *params_in, int stride,
+                              const double *rotations, const int32_t *knot_off, const double *knot_t,
+                              const double *knot_amp, int interp)
 {
     if (stride < 3 || stride > 6) return fail(ctx, CW_E_INVALID, "cw_set_potential_ex: stride must be 3..6");
     // the three leading parameters in the layout the rest of this function reads
@@ -231,10 +286,61 @@ extern "C" int cw_set_potential_ex(cw_ctx *ctx, double G, int n_comp, const int3
     memset(&P, 0, sizeof P);
     P.n_comp = n_comp;
     P.G = G;
+    bool general = false;
+    // time-interpolated first parameter: the static tables are built for a unit amplitude, the spline carries m(t)
+    if (knot_off) {
+        if (interp != CW_INTERP_LINEAR && interp != CW_INTERP_CUBIC)
+            return fail(ctx, CW_E_INVALID, "cw_set_potential_general: interp must be CW_INTERP_LINEAR or CW_INTERP_CUBIC");
+        if (knot_off[0] != 0 || knot_off[n_comp] > CW_MAX_KNOTS)
+            return fail(ctx, CW_E_INVALID, "cw_set_potential_general: more than CW_MAX_KNOTS knots, or knot_off[0] != 0");
+        for (int i = 0; i < n_comp; i++) {
+            const int a = knot_off[i], b = knot_off[i + 1];
+            if (b < a) return fail(ctx, CW_E_INVALID, "cw_set_potential_general: knot_off must not decrease");
+            P.k_off[i] = a;
+            if (b == a) continue;
+            if (!knot_t || !knot_amp) return fail(ctx, CW_E_INVALID, "cw_set_potential_general: knots without times / amplitudes");
+            const int t = types[i];
+            if (t == CW_COMP_LOGARITHMIC || t == CW_COMP_LOG_TRIAXIAL || t == CW_COMP_LEESUTO_NFW)
+                return fail(ctx, CW_E_UNSUPPORTED, "cw_set_potential_general: a time-dependent v_c is not supported (masses and densities are)");
+            for (int j = a; j < b; j++) {
+                if (!std::isfinite(knot_t[j]) || !std::isfinite(knot_amp[j]) || (j > a && !(knot_t[j] > knot_t[j - 1])))
+                    return fail(ctx, CW_E_INVALID, "cw_set_potential_general: knot times must be finite and strictly increasing");
+                P.k_t[j] = knot_t[j];
+            }
+            spline_coefficients(b - a, knot_t + a, knot_amp + a, interp, P.k_c + a);
+            params[3 * i + 0] = 1.0;
+            general = true;
+        }
+        P.k_off[n_comp] = knot_off[n_comp];
+    }
+    if (rotations) {
+        for (int i = 0; i < n_comp; i++) {
+            const double *Rm = rotations + 9 * (size_t)i;
+            if (std::isnan(Rm[0])) continue;
+            bool identity = true, finite = true;
+            for (int k = 0; k < 9; k++) {
+                finite = finite && std::isfinite(Rm[k]);
+                identity = identity && (Rm[k] == ((k % 4 == 0) ? 1.0 : 0.0));
+            }
+            if (!finite) return fail(ctx, CW_E_INVALID, "cw_set_potential_general: non-finite rotation matrix");
+            if (identity) continue;
+            // orthonormal rows, or grad = R^T grad' is not the gradient
+            for (int r = 0; r < 3; r++)
+                for (int c = r; c < 3; c++) {
+                    const double d = Rm[3 * r] * Rm[3 * c] + Rm[3 * r + 1] * Rm[3 * c + 1] + Rm[3 * r + 2] * Rm[3 * c + 2];
+                    if (fabs(d - (r == c ? 1.0 : 0.0)) > 1e-9)
+                        return fail(ctx, CW_E_INVALID, "cw_set_potential_general: rotation matrix is not orthogonal");
+                }
+            P.has_R[i] = 1;
+            for (int k = 0; k < 9; k++) P.R[i][k] = Rm[k];
+            general = true;
+        }
+    }
     for (int i = 0; i < n_comp; i++) {
         const int t = types[i];
-        if (t < CW_COMP_MIYAMOTO_NAGAI || t > CW_COMP_LOG_TRIAXIAL)
+        if (t < CW_COMP_MIYAMOTO_NAGAI || t > CW_COMP_POWERLAW_CUTOFF)
             return fail(ctx, CW_E_UNSUPPORTED, "cw_set_potential: unknown component type");
+        if (t >= CW_COMP_LONG_MURALI_BAR) general = true;
         P.type[i] = t;
         P.GM[i] = G * params[3 * i + 0];
         P.p1[i] = params[3 * i + 1];
@@ -259,6 +365,32 @@ extern "C" int cw_set_potential_ex(cw_ctx *ctx, double G, int n_comp, const int3
             P.q2[i][1] = 1.0 / (pp[3] * pp[3]);
             P.q2[i][2] = 1.0 / (pp[4] * pp[4]);
         }
+        if (t == CW_COMP_LONG_MURALI_BAR) {
+            if (stride < 4) return fail(ctx, CW_E_INVALID, "cw_set_potential: a Long-Murali bar needs 4 parameters (m, a, b, c)");
+            const double *pp = params_in + (size_t)stride * i;
+            if (!(pp[1] > 0.0 && pp[2] >= 0.0 && pp[3] >= 0.0 && pp[2] + pp[3] > 0.0))
+                return fail(ctx, CW_E_INVALID, "cw_set_potential: Long-Murali bar needs a > 0, b, c >= 0, b + c > 0");
+            P.pe[i][0] = pp[1]; P.pe[i][1] = pp[2]; P.pe[i][2] = pp[3] * pp[3];
+        }
+        if (t == CW_COMP_LEESUTO_NFW) {
+            if (stride < 5) return fail(ctx, CW_E_INVALID, "cw_set_potential: a Lee-Suto NFW needs 5 parameters (v_c, r_s, a, b, c)");
+            const double *pp = params_in + (size_t)stride * i;
+            if (!(pp[1] > 0.0 && pp[2] > 0.0 && pp[3] > 0.0 && pp[4] > 0.0))
+                return fail(ctx, CW_E_INVALID, "cw_set_potential: Lee-Suto NFW needs r_s, a, b, c > 0");
+            const double eb2 = 1.0 - (pp[3] / pp[2]) * (pp[3] / pp[2]), ec2 = 1.0 - (pp[4] / pp[2]) * (pp[4] / pp[2]);
+            const double ln2 = 0.69314718055994530942;
+            P.GM[i] = pp[0] * pp[0] / (ln2 - 0.5 + (ln2 - 0.75) * eb2 + (ln2 - 0.75) * ec2);   // phi0
+            P.pe[i][0] = 1.0 / pp[1]; P.pe[i][1] = eb2; P.pe[i][2] = ec2;
+        }
+        if (t == CW_COMP_POWERLAW_CUTOFF) {
+            const double sg = 1.5 - 0.5 * params[3 * i + 1];
+            if (!(sg > 0.0) || !(params[3 * i + 2] > 0.0))
+                return fail(ctx, CW_E_INVALID, "cw_set_potential: power-law cutoff needs alpha < 3 and r_c > 0");
+            P.pe[i][0] = sg;
+            P.pe[i][1] = 1.0 / (params[3 * i + 2] * params[3 * i + 2]);
+            P.pe[i][2] = lgamma(sg);
+            P.pe[i][3] = (sg > 0.5) ? lgamma(sg - 0.5) : NAN;     // the value needs alpha < 2; the gradient does not
+        }
         if (t == CW_COMP_BURKERT) {
             P.GM[i] = 3.14159265358979323846 * G * params[3 * i + 0] * params[3 * i + 1];   // pi G rho r0
             P.p2[i] = 1.0 / params[3 * i + 1];                                               // 1 / r0
@@ -272,10 +404,10 @@ extern "C" int cw_set_potential_ex(cw_ctx *ctx, double G, int n_comp, const int3
     }
     // recognise the two Milky Way shapes that have specialised kernels
     auto is = [&](int i, int t) { return i < n_comp && types[i] == t; };
-    P.kind = POT_GENERIC;
+    P.kind = general ? POT_GENERAL : POT_GENERIC;
     int nmn = 0;
     while (nmn < n_comp && types[nmn] == CW_COMP_MIYAMOTO_NAGAI) nmn++;
-    if ((nmn == 1 || nmn == 3) && n_comp == nmn + 3 && is(nmn, CW_COMP_HERNQUIST) &&
+    if (!general && (nmn == 1 || nmn == 3) && n_comp == nmn + 3 && is(nmn, CW_COMP_HERNQUIST) &&
         is(nmn + 1, CW_COMP_HERNQUIST) && is(nmn + 2, CW_COMP_NFW_SPHERICAL)) {
         bool shared_b = true;
         for (int i = 1; i < nmn; i++) shared_b = shared_b && (params[3 * i + 2] == params[2]);

@@ -138,7 +138,8 @@ __device__ __forceinline__ double log_fast(double x)
 enum PotKind : int {
     POT_GENERIC = 0, // any ordered list of components (loop + switch)
     POT_MW_V1 = 1,   // MiyamotoNagai + Hernquist + Hernquist + spherical NFW
-    POT_MW_V2 = 2    // 3 x MiyamotoNagai sharing b (MN3 disk) + Hernquist + Hernquist + NFW
+    POT_MW_V2 = 2,   // 3 x MiyamotoNagai sharing b (MN3 disk) + Hernquist + Hernquist + NFW
+    POT_GENERAL = 3  // full gradient vector: rotated / non-diagonal components, time-interpolated amplitudes
 };
 
 struct PotParams {
@@ -159,6 +160,15 @@ struct PotParams {
     // and on sm_100 every non-FP64 instruction costs half an FP64 issue slot (an FP64 warp instruction
     // holds the dispatch port for 2 cycles; measured, tools/exp/pipe_mix2.cu).
     double k_ln2, k_c5, k_c3, k_c158;
+    // ---- POT_GENERAL only (cw_set_potential_general)
+    int32_t has_R[CW_MAX_COMPONENTS];
+    double R[CW_MAX_COMPONENTS][9];        // row-major: q' = R q, grad = R^T grad'
+    double pe[CW_MAX_COMPONENTS][4];       // pre-digested parameters of the non-diagonal components
+    int32_t k_off[CW_MAX_COMPONENTS + 1];  // knots of component i: [k_off[i], k_off[i+1]); empty = static
+    double k_t[CW_MAX_KNOTS];              // knot times [Myr]
+    double k_c[CW_MAX_KNOTS][4];           // amplitude relative to GM[i] on [k_t[j], k_t[j+1]]:
+                                           // c0 + s (c1 + s (c2 + s c3)), s = t - k_t[j]
+    double t_eval;                         // time of the pointwise kernels
 };
 
 __host__ __device__ inline void pot_fill_constants(PotParams &P)
@@ -305,9 +315,125 @@ __device__ __forceinline__ void force_mw(const PotParams &P, LogTab ltab,
     Fz = fma(za, zb, Fxy);
 }
 
+// ------------------------------------------------------------------------------------------
+// POT_GENERAL: every component evaluated on its own, in its own (rotated) frame, with its own clock.
+// Precision before speed here: IEEE sqrt / divide and the CUDA math library.
+// ------------------------------------------------------------------------------------------
+
+// relative amplitude m(t) / m_ref of a gp.TimeInterpolatedPotential component (1 for a static one)
+__device__ __forceinline__ double amplitude_rel(const PotParams &P, int i, double t)
+{
+    const int a = P.k_off[i], b = P.k_off[i + 1];
+    if (b <= a) return 1.0;
+    if (b - a == 1) return P.k_c[a][0];
+    t = fmin(fmax(t, P.k_t[a]), P.k_t[b - 1]);     // the end values are held outside the knots
+    int lo = a, hi = b - 2;                        // interval index: k_t[j] <= t <= k_t[j+1]
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (t >= P.k_t[mid]) lo = mid; else hi = mid - 1;
+    }
+    const double s = t - P.k_t[lo];
+    return fma(s, fma(s, fma(s, P.k_c[lo][3], P.k_c[lo][2]), P.k_c[lo][1]), P.k_c[lo][0]);
+}
+
+// regularised lower incomplete gamma function P(a, x), a > 0, x >= 0: power series for x < a + 1,
+// Lentz continued fraction of Q = 1 - P otherwise (converged to 1 ulp-ish; <= 300 terms)
+__host__ __device__ inline double gamma_p(double a, double x, double lgam_a)
+{
+    if (!(x > 0.0)) return 0.0;
+    const double pref = exp(a * log(x) - x - lgam_a);
+    if (x < a + 1.0) {
+        double ap = a, del = 1.0 / a, sum = del;
+        for (int n = 0; n < 500; n++) {
+            ap += 1.0;
+            del *= x / ap;
+            sum += del;
+            if (fabs(del) < fabs(sum) * 1e-17) break;
+        }
+        return sum * pref;
+    }
+    const double tiny = 1e-300;
+    double bb = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / bb, h = d;
+    for (int n = 1; n < 500; n++) {
+        const double an = -(double)n * ((double)n - a);
+        bb += 2.0;
+        d = an * d + bb;
+        if (fabs(d) < tiny) d = tiny;
+        c = bb + an / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return 1.0 - pref * h;
+}
+
+// gradient (and, when phi != nullptr, value) of ONE non-diagonal component in its own frame; amp = GM[i] * rel
+__device__ __forceinline__ void nondiag_component(const PotParams &P, int i, double amp, double x, double y, double z,
+                                                  double &gx, double &gy, double &gz, double *phi)
+{
+    const int t = P.type[i];
+    if (t == CW_COMP_LONG_MURALI_BAR) {          // pe = (a, b, c^2)
+        const double a = P.pe[i][0];
+        const double sz = sqrt(fma(z, z, P.pe[i][2]));
+        const double B = P.pe[i][1] + sz;
+        const double D = fma(y, y, B * B);
+        const double xm = a - x, xp = a + x;
+        const double Tm = sqrt(fma(xm, xm, D)), Tp = sqrt(fma(xp, xp, D));
+        const double sT = Tm + Tp;
+        const double f1 = amp / (2.0 * Tm * Tp);
+        gx = 4.0 * f1 * x / sT;
+        const double cm = f1 / D * (sT - 4.0 * x * x / sT);
+        gy = cm * y;
+        gz = cm * B * z / sz;
+        if (phi) *phi = amp / (2.0 * a) * log((x - a + Tm) / (x + a + Tp));
+    } else if (t == CW_COMP_LEESUTO_NFW) {       // amp = phi0, pe = (1 / r_s, e_b^2, e_c^2)
+        const double eb2 = P.pe[i][1], ec2 = P.pe[i][2];
+        const double r2 = fma(z, z, fma(y, y, x * x));
+        const double r = sqrt(r2);
+        const double u = r * P.pe[i][0];
+        const double L = log(1.0 + u);
+        const double u2 = u * u, u3 = u2 * u, u4 = u2 * u2, opu = 1.0 + u;
+        const double N = u2 - 3.0 * u - 6.0, Dn = 2.0 * u2 * opu;
+        const double F3 = N / Dn + 3.0 * L / u3;
+        const double dF1 = L / u2 - 1.0 / (u * opu);
+        const double dF2 = 0.5 / u2 - 2.0 / u3 + (3.0 / u4 - 1.0 / u2) * L + (1.0 / u - 1.0 / u3) / opu;
+        const double dF3 = ((2.0 * u - 3.0) * Dn - N * (4.0 * u + 6.0 * u2)) / (Dn * Dn) + 3.0 / (u3 * opu) - 9.0 * L / u4;
+        const double E = 0.5 * (eb2 + ec2);
+        const double S = 0.5 * (eb2 * y * y + ec2 * z * z);
+        const double radial = (dF1 + E * dF2 + S / r2 * dF3) * P.pe[i][0] / r;
+        const double c3 = F3 / r2;
+        const double w = 2.0 * S / r2;
+        gx = amp * (radial * x - c3 * w * x);
+        gy = amp * (radial * y + c3 * (eb2 - w) * y);
+        gz = amp * (radial * z + c3 * (ec2 - w) * z);
+        if (phi) {
+            const double F1 = -L / u;
+            const double F2 = -1.0 / 3.0 + (2.0 * u2 - 3.0 * u + 6.0) / (6.0 * u2) + (1.0 / u - 1.0 / u3) * L;
+            *phi = amp * (F1 + E * F2 + S / r2 * F3);
+        }
+    } else {                                     // CW_COMP_POWERLAW_CUTOFF: pe = (s = 1.5 - alpha/2, 1/r_c^2, lgamma(s), lgamma(s - 0.5))
+        const double r2 = fma(z, z, fma(y, y, x * x));
+        const double r = sqrt(r2);
+        const double xx = r2 * P.pe[i][1];
+        const double Pm = gamma_p(P.pe[i][0], xx, P.pe[i][2]);      // M(<r) / m
+        const double f = amp * Pm / (r2 * r);
+        gx = f * x; gy = f * y; gz = f * z;
+        if (phi) {
+            // -G M(<r)/r - G m Gamma(s - 1/2, x) / (r_c Gamma(s)): the shells outside r  (needs alpha < 2)
+            const double a2 = P.pe[i][0] - 0.5;
+            const double Q2 = 1.0 - gamma_p(a2, xx, P.pe[i][3]);
+            *phi = -amp * (Pm / r + Q2 * exp(P.pe[i][3] - P.pe[i][2]) * sqrt(P.pe[i][1]));
+        }
+    }
+}
+
+__device__ __forceinline__ bool comp_is_nondiag(int t) { return t >= CW_COMP_LONG_MURALI_BAR; }
+
 // Generic composite: components in the caller's order.
-__device__ __forceinline__ void force_generic(const PotParams &P, LogTab ltab,
-                                              double x, double y, double z, double &Fxy, double &Fy, double &Fz)
+__device__ __forceinline__ void force_generic_range(const PotParams &P, LogTab ltab, const int i0, const int i1,
+                                                    double x, double y, double z, double &Fxy, double &Fy, double &Fz)
 {
     const double R2 = fma(y, y, x * x);
     const double z2 = z * z;
@@ -316,7 +442,7 @@ __device__ __forceinline__ void force_generic(const PotParams &P, LogTab ltab,
     double fyx = 0.0;             // Fy - Fxy: non-zero only for components flattened differently in x and y
     double ir = 0.0, r = 0.0;
     bool have_r = false;
-    for (int i = 0; i < P.n_comp; i++) {
+    for (int i = i0; i < i1; i++) {
         const int t = P.type[i];
         if (t == CW_COMP_MIYAMOTO_NAGAI) {
             const double q = fma(P.p2[i], P.p2[i], z2);
@@ -401,6 +527,44 @@ __device__ __forceinline__ void force_generic(const PotParams &P, LogTab ltab,
     Fz = fz;
 }
 
+__device__ __forceinline__ void force_generic(const PotParams &P, LogTab ltab,
+                                              double x, double y, double z, double &Fxy, double &Fy, double &Fz)
+{
+    force_generic_range(P, ltab, 0, P.n_comp, x, y, z, Fxy, Fy, Fz);
+}
+
+// POT_GENERAL: gradient at time t [Myr], components accumulated in the caller's order (c_gradient)
+static __device__ __noinline__ void gradient_general(const PotParams &P, LogTab ltab, double t,
+                                              double x, double y, double z, double &gx, double &gy, double &gz)
+{
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    for (int i = 0; i < P.n_comp; i++) {
+        const double rel = amplitude_rel(P, i, t);
+        double xr = x, yr = y, zr = z;
+        if (P.has_R[i]) {
+            xr = fma(P.R[i][2], z, fma(P.R[i][1], y, P.R[i][0] * x));
+            yr = fma(P.R[i][5], z, fma(P.R[i][4], y, P.R[i][3] * x));
+            zr = fma(P.R[i][8], z, fma(P.R[i][7], y, P.R[i][6] * x));
+        }
+        double cx, cy, cz;
+        if (comp_is_nondiag(P.type[i])) {
+            nondiag_component(P, i, P.GM[i] * rel, xr, yr, zr, cx, cy, cz, nullptr);
+        } else {
+            double Fx, Fy, Fz;
+            force_generic_range(P, ltab, i, i + 1, xr, yr, zr, Fx, Fy, Fz);
+            cx = (Fx * rel) * xr; cy = (Fy * rel) * yr; cz = (Fz * rel) * zr;
+        }
+        if (P.has_R[i]) {
+            ax += fma(P.R[i][6], cz, fma(P.R[i][3], cy, P.R[i][0] * cx));
+            ay += fma(P.R[i][7], cz, fma(P.R[i][4], cy, P.R[i][1] * cx));
+            az += fma(P.R[i][8], cz, fma(P.R[i][5], cy, P.R[i][2] * cx));
+        } else {
+            ax += cx; ay += cy; az += cz;
+        }
+    }
+    gx = ax; gy = ay; gz = az;
+}
+
 // ltab: the CTA's shared-memory log table (log_table_init), or nullptr to use the table-free log.
 // force<KIND> returns the two scalar factors of the axisymmetric composite: grad = (Fxy x, Fxy y, Fz z).
 template <int KIND>
@@ -422,16 +586,38 @@ __device__ __forceinline__ void force3(const PotParams &P, LogTab ltab,
     else { force<KIND>(P, ltab, x, y, z, Fx, Fz); Fy = Fx; }
 }
 
+// t [Myr] is used by POT_GENERAL alone (time-interpolated amplitudes); it costs the other kinds nothing.
 template <int KIND>
-__device__ __forceinline__ void gradient(const PotParams &P, LogTab ltab,
+__device__ __forceinline__ void gradient(const PotParams &P, LogTab ltab, double t,
                                          double x, double y, double z,
                                          double &gx, double &gy, double &gz)
 {
-    double Fx, Fy, Fz;
-    force3<KIND>(P, ltab, x, y, z, Fx, Fy, Fz);
-    gx = Fx * x;
-    gy = Fy * y;
-    gz = Fz * z;
+    if (KIND == POT_GENERAL) {
+        gradient_general(P, ltab, t, x, y, z, gx, gy, gz);
+    } else {
+        double Fx, Fy, Fz;
+        force3<KIND>(P, ltab, x, y, z, Fx, Fy, Fz);
+        gx = Fx * x;
+        gy = Fy * y;
+        gz = Fz * z;
+    }
+}
+
+// The leapfrog's form.  Diagonal kinds: the three factors of grad = (Fx x, Fy y, Fz z), folded into the
+// velocity FMAs by lf_kick.  POT_GENERAL: (Fx, Fy, Fz) IS the gradient.
+template <int KIND>
+__device__ __forceinline__ void force3t(const PotParams &P, LogTab ltab, double t,
+                                        double x, double y, double z, double &Fx, double &Fy, double &Fz)
+{
+    if (KIND == POT_GENERAL) gradient_general(P, ltab, t, x, y, z, Fx, Fy, Fz);
+    else force3<KIND>(P, ltab, x, y, z, Fx, Fy, Fz);
+}
+
+// vh + coef * grad_c, with grad_c = F * pos (diagonal kinds) or F itself (POT_GENERAL)
+template <int KIND>
+__device__ __forceinline__ double lf_kick(double F, double coef, double pos, double vh)
+{
+    return (KIND == POT_GENERAL) ? fma(F, coef, vh) : fma(F * coef, pos, vh);
 }
 
 // dt of a segment = t[1] - t[0] with both nodes converted to Myr first (gala converts the whole
@@ -444,15 +630,28 @@ __device__ __forceinline__ double seg_dt_myr(double t0, double t1, double to_myr
 }
 
 // Phi of the same components (gala *_value functions) -- for the N3 rows, not the hot loop.
-__device__ __forceinline__ double potential_value(const PotParams &P, double x, double y, double z)
+__device__ __forceinline__ double potential_value(const PotParams &P, double x0, double y0, double z0)
 {
-    const double R2 = fma(y, y, x * x);
-    const double z2 = z * z;
-    const double r = sqrt(R2 + z2);
-    double v = 0.0;
+    double vtot = 0.0;
     for (int i = 0; i < P.n_comp; i++) {
         const int t = P.type[i];
-        if (t == CW_COMP_MIYAMOTO_NAGAI) {
+        double x = x0, y = y0, z = z0, rel = 1.0;
+        if (P.kind == POT_GENERAL) {
+            rel = amplitude_rel(P, i, P.t_eval);
+            if (P.has_R[i]) {
+                x = fma(P.R[i][2], z0, fma(P.R[i][1], y0, P.R[i][0] * x0));
+                y = fma(P.R[i][5], z0, fma(P.R[i][4], y0, P.R[i][3] * x0));
+                z = fma(P.R[i][8], z0, fma(P.R[i][7], y0, P.R[i][6] * x0));
+            }
+        }
+        const double R2 = fma(y, y, x * x);
+        const double z2 = z * z;
+        const double r = sqrt(R2 + z2);
+        double v = 0.0;
+        if (comp_is_nondiag(t)) {
+            double cx, cy, cz;
+            nondiag_component(P, i, P.GM[i], x, y, z, cx, cy, cz, &v);
+        } else if (t == CW_COMP_MIYAMOTO_NAGAI) {
             const double zd = P.p1[i] + sqrt(fma(P.p2[i], P.p2[i], z2));
             v -= P.GM[i] / sqrt(fma(zd, zd, R2));
         } else if (t == CW_COMP_HERNQUIST) {
@@ -483,8 +682,9 @@ __device__ __forceinline__ double potential_value(const PotParams &P, double x, 
             const double u = r / P.p1[i];
             v -= (P.GM[i] / P.p1[i]) * log(1.0 + u) / u;
         }
+        vtot = fma(v, rel, vtot);
     }
-    return v;
+    return vtot;
 }
 
 } // namespace cw

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const __grid_constant__ 
             continue;
         }
         double gx, gy, gz;
-        gradient<KIND>(P, ltab, x, y, z, gx, gy, gz);
+        gradient<KIND>(P, ltab, P.t_eval, x, y, z, gx, gy, gz);
         if (mode == 0) {
             out[i] = gx; out[n + i] = gy; out[2 * n + i] = gz;
         } else {
@@ -45,6 +45,7 @@ cudaError_t launch_pointwise(const PotParams &P, int mode, int64_t n, const doub
     switch (P.kind) {
     case POT_MW_V1: pointwise_kernel<POT_MW_V1><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, out); break;
     case POT_MW_V2: pointwise_kernel<POT_MW_V2><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, out); break;
+    case POT_GENERAL: pointwise_kernel<POT_GENERAL><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, out); break;
     default: pointwise_kernel<POT_GENERIC><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, out); break;
     }
     return cudaGetLastError();

@@ -307,9 +307,9 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 } else {
                     if (kicked) { // c_init_velocity of the new segment; the force at this node is already known
                         const double nhdt = -0.5 * s.dt;
-                        s.vhx = fma(s.Fxy * nhdt, s.x, s.vx);
-                        s.vhy = fma(s.Fy * nhdt, s.y, s.vy);
-                        s.vhz = fma(s.Fz * nhdt, s.z, s.vz);
+                        s.vhx = lf_kick<KIND>(s.Fxy, nhdt, s.x, s.vx);
+                        s.vhy = lf_kick<KIND>(s.Fy, nhdt, s.y, s.vy);
+                        s.vhz = lf_kick<KIND>(s.Fz, nhdt, s.z, s.vz);
                     }
                     s.next = (s.e < s.e1) ? A.ev_step[s.e] : s.L;
                 }
@@ -400,11 +400,11 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 staged = true;
             }
             if (s.L == 0) { write_final(A, s); continue; }
-            force3<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+            force3t<KIND>(P, ltab, s.tcur * s.smyr, s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
             const double nhdt = -0.5 * s.dt;
-            s.vhx = fma(s.Fxy * nhdt, s.x, s.vx);
-            s.vhy = fma(s.Fy * nhdt, s.y, s.vy);
-            s.vhz = fma(s.Fz * nhdt, s.z, s.vz);
+            s.vhx = lf_kick<KIND>(s.Fxy, nhdt, s.x, s.vx);
+            s.vhy = lf_kick<KIND>(s.Fy, nhdt, s.y, s.vy);
+            s.vhz = lf_kick<KIND>(s.Fz, nhdt, s.z, s.vz);
             s.next = (s.e < s.e1) ? A.ev_step[s.e] : s.L;
             active = true;
         }
@@ -426,7 +426,29 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
         // with grad = (Fxy x, Fxy y, Fz z) folded into the FMAs: vh = fma(Fxy * (-dt), x, vh).
         const double dt = s.dt, ndt = -s.dt, nhdt = -0.5 * s.dt;
         constexpr bool TRI = (KIND == POT_GENERIC);    // only the generic composite can have Fy != Fx
-        if (!STORE) {
+        constexpr bool GEN = (KIND == POT_GENERAL);    // (Fxy, Fy, Fz) is the gradient itself, evaluated at the node's time
+        // time [Myr] of node J of this lane's orbit (POT_GENERAL only: the gradient of step j-1 -> j is taken at t_j)
+        auto tnode = [&](int J) -> double {
+            if (!GEN) return 0.0;
+            return ((s.append && J == s.L) ? s.t2 : fma((double)J, s.hgrid, s.tcur)) * s.smyr;
+        };
+        if (GEN) {
+            for (int q = 1; q < m; q++) {
+                s.x = fma(s.vhx, dt, s.x);
+                s.y = fma(s.vhy, dt, s.y);
+                s.z = fma(s.vhz, dt, s.z);
+                force3t<KIND>(P, ltab, tnode(s.j + q), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+                if (STORE) {
+                    s.vx = fma(s.Fxy, nhdt, s.vhx);
+                    s.vy = fma(s.Fy, nhdt, s.vhy);
+                    s.vz = fma(s.Fz, nhdt, s.vhz);
+                }
+                s.vhx = fma(s.Fxy, ndt, s.vhx);
+                s.vhy = fma(s.Fy, ndt, s.vhy);
+                s.vhz = fma(s.Fz, ndt, s.vhz);
+                if (STORE && active) tw.stage(col_base + s.j + q, s.x, s.y, s.z, s.vx, s.vy, s.vz);
+            }
+        } else if (!STORE) {
 #pragma unroll 4
             for (int q = 1; q < m; q++) {   // c_leapfrog_step without the synchronised velocity
                 s.x = fma(s.vhx, dt, s.x);
@@ -463,7 +485,18 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 if (active) tw.stage(col_base + s.j + q, s.x, s.y, s.z, s.vx, s.vy, s.vz);
             }
         }
-        {   // full c_leapfrog_step: v = vh - g dt/2 ; vh = vh - g dt
+        if (GEN) {
+            s.x = fma(s.vhx, dt, s.x);
+            s.y = fma(s.vhy, dt, s.y);
+            s.z = fma(s.vhz, dt, s.z);
+            force3t<KIND>(P, ltab, tnode(s.j + m), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+            s.vx = fma(s.Fxy, nhdt, s.vhx);
+            s.vy = fma(s.Fy, nhdt, s.vhy);
+            s.vz = fma(s.Fz, nhdt, s.vhz);
+            s.vhx = fma(s.Fxy, ndt, s.vhx);
+            s.vhy = fma(s.Fy, ndt, s.vhy);
+            s.vhz = fma(s.Fz, ndt, s.vhz);
+        } else {   // full c_leapfrog_step: v = vh - g dt/2 ; vh = vh - g dt
             s.x = fma(s.vhx, dt, s.x);
             s.y = fma(s.vhy, dt, s.y);
             s.z = fma(s.vhz, dt, s.z);
@@ -534,6 +567,8 @@ cudaError_t launch_leapfrog(const PotParams &P, const IntegArgs &A, bool store_a
         return store_all ? launch_lf<POT_MW_V1, true>(P, A, cfg) : launch_lf<POT_MW_V1, false>(P, A, cfg);
     case POT_MW_V2:
         return store_all ? launch_lf<POT_MW_V2, true>(P, A, cfg) : launch_lf<POT_MW_V2, false>(P, A, cfg);
+    case POT_GENERAL:
+        return store_all ? launch_lf<POT_GENERAL, true>(P, A, cfg) : launch_lf<POT_GENERAL, false>(P, A, cfg);
     default:
         return store_all ? launch_lf<POT_GENERIC, true>(P, A, cfg) : launch_lf<POT_GENERIC, false>(P, A, cfg);
     }

@@ -29,6 +29,9 @@ def _host_circular_velocity(pot: CompositePotential, x, y, z):
     for synthetic inputs (upstream of the hot path; the product's own version is cw_circular_velocity)."""
     r = np.sqrt(x * x + y * y + z * z)
     qdotg = np.zeros_like(r)
+    if any(t > 12 for t in pot.types) or pot.rotation_array() is not None or pot.knot_arrays() is not None:
+        raise NotImplementedError("synthetic birth velocities need a static, unrotated potential of the diagonal "
+                                  "components: draw them in one and integrate in the other")
     for t, prm in zip(pot.types, pot.params):
         m, a, b = (tuple(prm) + (0.0, 0.0))[:3]
         GM = pot.G * m

@@ -49,8 +49,14 @@ enum {
     CW_COMP_KUZMIN = 9,         /* (m, a, unused) */
     CW_COMP_BURKERT = 10,       /* (rho [Msun/kpc^3], r0, unused) */
     CW_COMP_NFW_TRIAXIAL = 11,  /* (m, r_s, a, b, c): gp.NFWPotential with flattening; cw_set_potential_ex only */
-    CW_COMP_LOG_TRIAXIAL = 12   /* (v_c, r_h, q1, q2, q3): LogarithmicPotential with axis ratios, phi = 0; _ex only */
+    CW_COMP_LOG_TRIAXIAL = 12,  /* (v_c, r_h, q1, q2, q3): LogarithmicPotential with axis ratios, phi = 0; _ex only */
+    /* components whose gradient is not of the form (Fx x, Fy y, Fz z): cw_set_potential_general only */
+    CW_COMP_LONG_MURALI_BAR = 13, /* (m, a, b, c): gp.LongMuraliBarPotential; its angle alpha travels as a rotation */
+    CW_COMP_LEESUTO_NFW = 14,     /* (v_c [kpc/Myr], r_s, a, b, c): gp.LeeSutoTriaxialNFWPotential */
+    CW_COMP_POWERLAW_CUTOFF = 15  /* (m, alpha, r_c): gp.PowerLawCutoffPotential (BovyMWPotential2014's bulge) */
 };
+#define CW_MAX_KNOTS 64 /* time knots of all components of one potential together */
+enum { CW_INTERP_LINEAR = 0, CW_INTERP_CUBIC = 1 /* natural cubic spline (GSL cspline) */ };
 
 /* integrators = the two gala Integrator classes cogsworth passes (pop.py:130, kicks.py:54) */
 enum {
@@ -165,6 +171,24 @@ int cw_set_potential(cw_ctx *ctx, double G, int n_components, const int32_t *typ
 /* n_components = 0 is gala's NullPotential (free motion). */
 /* The same with `stride` (3..6) doubles per component, for components with more than three parameters. */
 int cw_set_potential_ex(cw_ctx *ctx, double G, int n_components, const int32_t *types, const double *params, int stride);
+/* The general form (its own kernels: full gradient vector, time argument).  Adds, per component,
+ *   rotations : NULL, or n_components x 9 doubles, row-major R with q' = R q evaluated in the component's
+ *               frame and grad = R^T grad' (gala's `R=` argument of every potential class; the `phi` of
+ *               LogarithmicPotential / LM10Potential and the `alpha` of LongMuraliBarPotential).  A row whose
+ *               first entry is NaN means "no rotation".
+ *   knot_off  : NULL, or n_components + 1 offsets (CSR) into knot_t / knot_amp: gp.TimeInterpolatedPotential
+ *               (docs/tutorials/potentials/evolving_potentials.ipynb cells 5 and 13) with a time-dependent first
+ *               parameter (the mass; the other parameters must be constant).  knot_t [Myr] strictly increasing,
+ *               knot_amp = the first parameter at the knots; `interp` = CW_INTERP_LINEAR / CW_INTERP_CUBIC.
+ *               Outside the knots the end values are held.  A component with 0 knots is static.
+ * Potentials that need none of this and contain no non-diagonal component are routed to the same kernels as
+ * cw_set_potential_ex. */
+int cw_set_potential_general(cw_ctx *ctx, double G, int n_components, const int32_t *types, const double *params,
+                             int stride, const double *rotations, const int32_t *knot_off, const double *knot_t,
+                             const double *knot_amp, int interp);
+/* Time [Myr] at which cw_gradient / cw_potential_value / cw_circular_velocity evaluate a time-dependent potential
+ * (default 0; the integrators use each orbit's own clock). */
+int cw_set_potential_time(cw_ctx *ctx, double t_myr);
 
 /* The grid pre-pass alone: node count per orbit and the node index of every event.  Lets the
  * host size trajectory buffers (traj_off) before cw_integrate, and is the bit-exact

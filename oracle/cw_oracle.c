@@ -72,11 +72,26 @@
 #define CWO_E_NONFINITE (-5)
 #define CWO_E_CAPACITY (-6)
 
+#define CWO_COMP_LONG_MURALI_BAR 13 /* (m, a, b, c); the angle alpha is a rotation */
+#define CWO_COMP_LEESUTO_NFW 14     /* (v_c, r_s, a, b, c) */
+#define CWO_COMP_POWERLAW_CUTOFF 15 /* (m, alpha, r_c) */
+#define CWO_MAX_KNOTS 32            /* per component */
+
 typedef struct {
     double G;
     int32_t n;
     int32_t type[CWO_MAX_COMP];
     double p[CWO_MAX_COMP][6];
+    /* gala's generic per-potential rotation (cpotential.c applies R to q, R^T to the gradient) */
+    int32_t has_R[CWO_MAX_COMP];
+    double R[CWO_MAX_COMP][9];
+    /* gp.TimeInterpolatedPotential: p[i][0] at the knots; interp 0 = linear, 1 = natural cubic spline (GSL cspline) */
+    int32_t n_knots[CWO_MAX_COMP];
+    int32_t interp;
+    double knot_t[CWO_MAX_COMP][CWO_MAX_KNOTS];
+    double knot_y[CWO_MAX_COMP][CWO_MAX_KNOTS];
+    double knot_c[CWO_MAX_COMP][CWO_MAX_KNOTS];   /* GSL cspline's c_i (half second derivatives), by cwo_prepare */
+    double t_eval;                                 /* time of cwo_gradient / cwo_value (the integrators pass their own) */
 } cwo_potential;
 
 typedef struct {
@@ -184,32 +199,217 @@ static void triaxial_log_gradient(const double *p, const double *q, double *grad
     grad[2] = grad[2] + fac * q[2] / (p[4] * p[4]);
 }
 
-/* cpotential.c: c_gradient -- zero, then accumulate components in order */
-void cwo_gradient(const cwo_potential *P, const double *q, double *grad)
+/* builtin_potentials.c: longmuralibar_gradient, pars = (G, m, a, b, c) in the bar's own frame [gala-recall]
+ * (Long & Murali 1992: Phi = G m / (2a) ln((x - a + T-) / (x + a + T+)), T+- = sqrt((a +- x)^2 + y^2 + (b + sqrt(c^2 + z^2))^2)) */
+static double longmurali_value(double G, const double *p, const double *q)
 {
-    grad[0] = 0.; grad[1] = 0.; grad[2] = 0.;
-    for (int i = 0; i < P->n; i++) {
-        switch (P->type[i]) {
-        case CWO_COMP_MN: mn_gradient(P->G, P->p[i], q, grad); break;
-        case CWO_COMP_HERNQUIST: hernquist_gradient(P->G, P->p[i], q, grad); break;
-        case CWO_COMP_NFW: nfw_gradient(P->G, P->p[i], q, grad); break;
-        case CWO_COMP_NFW_TRIAXIAL: triaxial_nfw_gradient(P->G, P->p[i], q, grad); break;
-        case CWO_COMP_LOG_TRIAXIAL: triaxial_log_gradient(P->p[i], q, grad); break;
-        case CWO_COMP_KEPLER: case CWO_COMP_PLUMMER: case CWO_COMP_ISOCHRONE: case CWO_COMP_JAFFE:
-        case CWO_COMP_LOGARITHMIC: case CWO_COMP_KUZMIN: case CWO_COMP_BURKERT:
-            extra_gradient(P->type[i], P->G, P->p[i], q, grad); break;
-        default: grad[0] = grad[1] = grad[2] = NAN;
+    double a = p[1], b = p[2], c = p[3];
+    double bz = b + sqrt(c * c + q[2] * q[2]);
+    double Tm = sqrt((a - q[0]) * (a - q[0]) + q[1] * q[1] + bz * bz);
+    double Tp = sqrt((a + q[0]) * (a + q[0]) + q[1] * q[1] + bz * bz);
+    return G * p[0] / (2. * a) * log((q[0] - a + Tm) / (q[0] + a + Tp));
+}
+static void longmurali_gradient(double G, const double *p, const double *q, double *grad)
+{
+    double a = p[1], b = p[2], c = p[3];
+    double x = q[0], y = q[1], z = q[2];
+    double sz = sqrt(c * c + z * z), bz = b + sz;
+    double Tm = sqrt((a - x) * (a - x) + y * y + bz * bz);
+    double Tp = sqrt((a + x) * (a + x) + y * y + bz * bz);
+    double fac1 = G * p[0] / (2. * Tm * Tp);
+    double fac2 = 1. / (y * y + bz * bz);
+    double fac3 = Tm + Tp - 4. * x * x / (Tm + Tp);
+    grad[0] = grad[0] + 4. * fac1 * x / (Tm + Tp);
+    grad[1] = grad[1] + fac1 * y * fac2 * fac3;
+    grad[2] = grad[2] + fac1 * z * fac2 * fac3 * bz / sz;
+}
+
+/* builtin_potentials.c: leesuto_*, pars = (G, v_c, r_s, a, b, c) [gala-recall] (Lee & Suto 2003, eq. 27-29):
+ * Phi = phi0 (F1(u) + (e_b^2 + e_c^2)/2 F2(u) + (e_b^2 y^2 + e_c^2 z^2) / (2 r^2) F3(u)), u = r / r_s */
+static double leesuto_value(const double *p, const double *q)
+{
+    double eb2 = 1. - (p[3] / p[2]) * (p[3] / p[2]), ec2 = 1. - (p[4] / p[2]) * (p[4] / p[2]);
+    double phi0 = p[0] * p[0] / (log(2.) - 0.5 + (log(2.) - 0.75) * eb2 + (log(2.) - 0.75) * ec2);
+    double r2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2], r = sqrt(r2), u = r / p[1];
+    double F1 = -log(1. + u) / u;
+    double F2 = -1. / 3. + (2. * u * u - 3. * u + 6.) / (6. * u * u) + (1. / u - 1. / (u * u * u)) * log(1. + u);
+    double F3 = (u * u - 3. * u - 6.) / (2. * u * u * (1. + u)) + 3. / (u * u * u) * log(1. + u);
+    return phi0 * (F1 + (eb2 + ec2) / 2. * F2 + (eb2 * q[1] * q[1] + ec2 * q[2] * q[2]) / (2. * r2) * F3);
+}
+static void leesuto_gradient(const double *p, const double *q, double *grad)
+{
+    double eb2 = 1. - (p[3] / p[2]) * (p[3] / p[2]), ec2 = 1. - (p[4] / p[2]) * (p[4] / p[2]);
+    double phi0 = p[0] * p[0] / (log(2.) - 0.5 + (log(2.) - 0.75) * eb2 + (log(2.) - 0.75) * ec2);
+    double x = q[0], y = q[1], z = q[2];
+    double r2 = x * x + y * y + z * z, r = sqrt(r2), u = r / p[1], L = log(1. + u);
+    double u2 = u * u, u3 = u2 * u, u4 = u2 * u2;
+    double F3 = (u2 - 3. * u - 6.) / (2. * u2 * (1. + u)) + 3. * L / u3;
+    double dF1 = L / u2 - 1. / (u * (1. + u));
+    double dF2 = 1. / (2. * u2) - 2. / u3 + (3. / u4 - 1. / u2) * L + (1. / u - 1. / u3) / (1. + u);
+    double num = u2 - 3. * u - 6., den = 2. * u2 * (1. + u);
+    double dF3 = ((2. * u - 3.) * den - num * (4. * u + 6. * u2)) / (den * den) + 3. / (u3 * (1. + u)) - 9. * L / u4;
+    double S = (eb2 * y * y + ec2 * z * z) / 2.;
+    double dPhi_du = dF1 + (eb2 + ec2) / 2. * dF2 + S / r2 * dF3;      /* at fixed angles */
+    double rad = dPhi_du / (p[1] * r);                                /* du/dq_i = q_i / (r r_s) */
+    grad[0] = grad[0] + phi0 * (rad * x + F3 * (-2. * S * x / (r2 * r2)));
+    grad[1] = grad[1] + phi0 * (rad * y + F3 * (eb2 * y / r2 - 2. * S * y / (r2 * r2)));
+    grad[2] = grad[2] + phi0 * (rad * z + F3 * (ec2 * z / r2 - 2. * S * z / (r2 * r2)));
+}
+
+/* regularised lower incomplete gamma P(a, x) (what gala takes from GSL: gsl_sf_gamma_inc_P): series / continued fraction */
+static double gamma_inc_P(double a, double x)
+{
+    if (!(x > 0.)) return 0.;
+    double pref = exp(a * log(x) - x - lgamma(a));
+    if (x < a + 1.) {
+        double ap = a, del = 1. / a, sum = del;
+        for (int n = 0; n < 1000; n++) { ap += 1.; del *= x / ap; sum += del; if (fabs(del) < fabs(sum) * 1e-17) break; }
+        return sum * pref;
+    }
+    double tiny = 1e-300, b = x + 1. - a, c = 1. / tiny, d = 1. / b, h = d;
+    for (int n = 1; n < 1000; n++) {
+        double an = -(double)n * ((double)n - a);
+        b += 2.;
+        d = an * d + b; if (fabs(d) < tiny) d = tiny;
+        c = b + an / c; if (fabs(c) < tiny) c = tiny;
+        d = 1. / d;
+        double del = d * c;
+        h *= del;
+        if (fabs(del - 1.) < 1e-16) break;
+    }
+    return 1. - pref * h;
+}
+
+/* builtin_potentials.c: powerlawcutoff_gradient, pars = (G, m, alpha, r_c) [gala-recall]: rho ~ r^-alpha exp(-r^2/r_c^2)
+ * of total mass m, dPhi/dr = G M(<r) / r^2 with M(<r) = m P(3/2 - alpha/2, r^2 / r_c^2) */
+static void powerlawcutoff_gradient(double G, const double *p, const double *q, double *grad)
+{
+    double r2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2], r = sqrt(r2);
+    double dPhi_dr = G * p[0] * gamma_inc_P(1.5 - p[1] / 2., r2 / (p[2] * p[2])) / r2;
+    grad[0] = grad[0] + dPhi_dr * q[0] / r;
+    grad[1] = grad[1] + dPhi_dr * q[1] / r;
+    grad[2] = grad[2] + dPhi_dr * q[2] / r;
+}
+/* Phi = -G M(<r) / r - G m Gamma(1 - alpha/2, r^2/r_c^2) / (r_c Gamma(3/2 - alpha/2)) (zero at infinity; alpha < 2) */
+static double powerlawcutoff_value(double G, const double *p, const double *q)
+{
+    double r2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2], r = sqrt(r2);
+    double s = 1.5 - p[1] / 2., x = r2 / (p[2] * p[2]);
+    if (!(s > 0.5)) return NAN;
+    double Q2 = 1. - gamma_inc_P(s - 0.5, x);
+    return -G * p[0] * (gamma_inc_P(s, x) / r + Q2 * exp(lgamma(s - 0.5) - lgamma(s)) / p[2]);
+}
+
+/* Natural cubic spline exactly as GSL's cspline.c sets it up: c_0 = c_{n-1} = 0, the interior c_i from the
+ * tridiagonal system; evaluation y = y_i + dx (b_i + dx (c_i + dx d_i)). */
+void cwo_prepare(cwo_potential *P)
+{
+    for (int k = 0; k < P->n; k++) {
+        int n = P->n_knots[k];
+        double *c = P->knot_c[k];
+        const double *x = P->knot_t[k], *y = P->knot_y[k];
+        for (int i = 0; i < CWO_MAX_KNOTS; i++) c[i] = 0.;
+        if (n < 3 || P->interp == 0) continue;
+        int m = n - 2;                       /* unknowns c_1 .. c_{n-2} */
+        double diag[CWO_MAX_KNOTS], off[CWO_MAX_KNOTS], g[CWO_MAX_KNOTS];
+        for (int i = 0; i < m; i++) {
+            double h_i = x[i + 1] - x[i], h_ip1 = x[i + 2] - x[i + 1];
+            double yd_i = y[i + 1] - y[i], yd_ip1 = y[i + 2] - y[i + 1];
+            off[i] = h_ip1;
+            diag[i] = 2. * (h_ip1 + h_i);
+            g[i] = 3. * (yd_ip1 / h_ip1 - yd_i / h_i);
+        }
+        /* symmetric tridiagonal solve (Gaussian elimination without pivoting: diagonally dominant) */
+        for (int i = 1; i < m; i++) {
+            double w = off[i - 1] / diag[i - 1];
+            diag[i] -= w * off[i - 1];
+            g[i] -= w * g[i - 1];
+        }
+        for (int i = m - 1; i >= 0; i--) {
+            double v = g[i];
+            if (i + 1 < m) v -= off[i] * c[i + 2];
+            c[i + 1] = v / diag[i];
         }
     }
 }
 
+/* the first parameter of component k at time t; outside the knots the end values are held */
+static double first_parameter(const cwo_potential *P, int k, double t)
+{
+    int n = P->n_knots[k];
+    if (n <= 0) return P->p[k][0];
+    const double *x = P->knot_t[k], *y = P->knot_y[k], *c = P->knot_c[k];
+    if (n == 1 || t <= x[0]) return y[0];
+    if (t >= x[n - 1]) return y[n - 1];
+    int i = 0;
+    while (i + 2 < n && t >= x[i + 1]) i++;
+    double dx = x[i + 1] - x[i], dy = y[i + 1] - y[i], d = t - x[i];
+    if (P->interp == 0) return y[i] + d / dx * dy;
+    double b_i = dy / dx - dx * (c[i + 1] + 2. * c[i]) / 3.;
+    double d_i = (c[i + 1] - c[i]) / (3. * dx);
+    return y[i] + d * (b_i + d * (c[i] + d * d_i));
+}
+
+static void component_gradient(int type, double G, const double *p, const double *q, double *grad)
+{
+    switch (type) {
+    case CWO_COMP_MN: mn_gradient(G, p, q, grad); break;
+    case CWO_COMP_HERNQUIST: hernquist_gradient(G, p, q, grad); break;
+    case CWO_COMP_NFW: nfw_gradient(G, p, q, grad); break;
+    case CWO_COMP_NFW_TRIAXIAL: triaxial_nfw_gradient(G, p, q, grad); break;
+    case CWO_COMP_LOG_TRIAXIAL: triaxial_log_gradient(p, q, grad); break;
+    case CWO_COMP_KEPLER: case CWO_COMP_PLUMMER: case CWO_COMP_ISOCHRONE: case CWO_COMP_JAFFE:
+    case CWO_COMP_LOGARITHMIC: case CWO_COMP_KUZMIN: case CWO_COMP_BURKERT:
+        extra_gradient(type, G, p, q, grad); break;
+    case CWO_COMP_LONG_MURALI_BAR: longmurali_gradient(G, p, q, grad); break;
+    case CWO_COMP_LEESUTO_NFW: leesuto_gradient(p, q, grad); break;
+    case CWO_COMP_POWERLAW_CUTOFF: powerlawcutoff_gradient(G, p, q, grad); break;
+    default: grad[0] = grad[1] = grad[2] = NAN;
+    }
+}
+
+/* cpotential.c: c_gradient -- zero, then accumulate components in order; a component with a rotation sees
+ * q' = R q and contributes R^T grad'; a time-interpolated one is evaluated with its parameters at time t */
+void cwo_gradient_t(const cwo_potential *P, double t, const double *q, double *grad)
+{
+    grad[0] = 0.; grad[1] = 0.; grad[2] = 0.;
+    for (int i = 0; i < P->n; i++) {
+        double p[6];
+        for (int k = 0; k < 6; k++) p[k] = P->p[i][k];
+        p[0] = first_parameter(P, i, t);
+        if (P->has_R[i]) {
+            const double *R = P->R[i];
+            double qr[3], gr[3] = {0., 0., 0.};
+            for (int a = 0; a < 3; a++) qr[a] = R[3 * a] * q[0] + R[3 * a + 1] * q[1] + R[3 * a + 2] * q[2];
+            component_gradient(P->type[i], P->G, p, qr, gr);
+            for (int a = 0; a < 3; a++) grad[a] = grad[a] + (R[a] * gr[0] + R[3 + a] * gr[1] + R[6 + a] * gr[2]);
+        } else {
+            component_gradient(P->type[i], P->G, p, q, grad);
+        }
+    }
+}
+
+void cwo_gradient(const cwo_potential *P, const double *q, double *grad)
+{
+    cwo_gradient_t(P, P->t_eval, q, grad);
+}
+
 /* builtin_potentials.c *_value: Phi of the same components (used by the "next" rows N3) */
-double cwo_value(const cwo_potential *P, const double *q)
+double cwo_value(const cwo_potential *P, const double *q0)
 {
     double v = 0.;
     for (int i = 0; i < P->n; i++) {
-        const double *p = P->p[i];
-        if (P->type[i] == CWO_COMP_MN) {
+        double p[6], q[3] = {q0[0], q0[1], q0[2]};
+        for (int k = 0; k < 6; k++) p[k] = P->p[i][k];
+        p[0] = first_parameter(P, i, P->t_eval);
+        if (P->has_R[i]) {
+            const double *R = P->R[i];
+            for (int a = 0; a < 3; a++) q[a] = R[3 * a] * q0[0] + R[3 * a + 1] * q0[1] + R[3 * a + 2] * q0[2];
+        }
+        if (P->type[i] == CWO_COMP_LONG_MURALI_BAR) v += longmurali_value(P->G, p, q);
+        else if (P->type[i] == CWO_COMP_LEESUTO_NFW) v += leesuto_value(p, q);
+        else if (P->type[i] == CWO_COMP_POWERLAW_CUTOFF) v += powerlawcutoff_value(P->G, p, q);
+        else if (P->type[i] == CWO_COMP_MN) {
             double zd = p[1] + sqrt(q[2] * q[2] + p[2] * p[2]);
             v += -P->G * p[0] / sqrt(q[0] * q[0] + q[1] * q[1] + zd * zd);
         } else if (P->type[i] == CWO_COMP_HERNQUIST) {
@@ -313,13 +513,13 @@ void cwo_leapfrog(const cwo_potential *P, double *w, const double *t, int64_t nt
     if (out) for (int c = 0; c < 6; c++) out[c * stride] = w[c];
     if (nt < 2) return;
     double dt = t[1] - t[0];
-    /* c_init_velocity */
-    cwo_gradient(P, w, grad);
+    /* c_init_velocity at t[0]; every c_leapfrog_step evaluates the gradient at the new node's time t[j] [gala-recall] */
+    cwo_gradient_t(P, t[0], w, grad);
     for (int k = 0; k < 3; k++) vh[k] = w[3 + k] - grad[k] * dt / 2.;
     for (int64_t j = 1; j < nt; j++) {
         /* c_leapfrog_step */
         for (int k = 0; k < 3; k++) w[k] = w[k] + vh[k] * dt;
-        cwo_gradient(P, w, grad);
+        cwo_gradient_t(P, t[j], w, grad);
         for (int k = 0; k < 3; k++) {
             w[3 + k] = vh[k] - grad[k] * dt / 2.;
             vh[k] = vh[k] - grad[k] * dt;
@@ -333,10 +533,10 @@ void cwo_leapfrog(const cwo_potential *P, double *w, const double *t, int64_t nt
 #define NEQ 6
 
 /* Fwrapper in gala's dop853.pyx: f = (dH/dp, -dH/dq) = (v, -grad Phi) */
-static void fcn(const cwo_potential *P, const double *y, double *f)
+static void fcn(const cwo_potential *P, double t, const double *y, double *f)
 {
     double g[3];
-    cwo_gradient(P, y, g);
+    cwo_gradient_t(P, t, y, g);
     f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
     f[3] = -g[0]; f[4] = -g[1]; f[5] = -g[2];
 }
@@ -376,7 +576,7 @@ static int dop853_core(const cwo_potential *P, double x, double *y, double xend,
     double hlamb = 0.0, hnew, xph, err, err2, sk, erri, sqr, deno, fac, fac11;
     int i;
 
-    fcn(P, y, k1);
+    fcn(P, x, y, k1);
     hmax = fabs(hmax);
     if (h == 0.0) return CWO_E_INCONSISTENT;   /* gala always passes dt0 != 0 (hinit not restated) */
     nfcn += 2;
@@ -389,28 +589,28 @@ static int dop853_core(const cwo_potential *P, double x, double *y, double xend,
 
         /* the twelve stages */
         for (i = 0; i < n; i++) yy1[i] = y[i] + h * CW_A0201 * k1[i];
-        fcn(P, yy1, k2);
+        fcn(P, x + CW_C02 * h, yy1, k2);
         for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A0301 * k1[i] + CW_A0302 * k2[i]);
-        fcn(P, yy1, k3);
+        fcn(P, x + CW_C03 * h, yy1, k3);
         for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A0401 * k1[i] + CW_A0403 * k3[i]);
-        fcn(P, yy1, k4);
+        fcn(P, x + CW_C04 * h, yy1, k4);
         for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A0501 * k1[i] + CW_A0503 * k3[i] + CW_A0504 * k4[i]);
-        fcn(P, yy1, k5);
+        fcn(P, x + CW_C05 * h, yy1, k5);
         for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A0601 * k1[i] + CW_A0604 * k4[i] + CW_A0605 * k5[i]);
-        fcn(P, yy1, k6);
+        fcn(P, x + CW_C06 * h, yy1, k6);
         for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A0701 * k1[i] + CW_A0704 * k4[i] + CW_A0705 * k5[i] + CW_A0706 * k6[i]);
-        fcn(P, yy1, k7);
+        fcn(P, x + CW_C07 * h, yy1, k7);
         for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A0801 * k1[i] + CW_A0804 * k4[i] + CW_A0805 * k5[i] + CW_A0806 * k6[i] + CW_A0807 * k7[i]);
-        fcn(P, yy1, k8);
+        fcn(P, x + CW_C08 * h, yy1, k8);
         for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A0901 * k1[i] + CW_A0904 * k4[i] + CW_A0905 * k5[i] + CW_A0906 * k6[i] + CW_A0907 * k7[i] + CW_A0908 * k8[i]);
-        fcn(P, yy1, k9);
+        fcn(P, x + CW_C09 * h, yy1, k9);
         for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A1001 * k1[i] + CW_A1004 * k4[i] + CW_A1005 * k5[i] + CW_A1006 * k6[i] + CW_A1007 * k7[i] + CW_A1008 * k8[i] + CW_A1009 * k9[i]);
-        fcn(P, yy1, k10);
+        fcn(P, x + CW_C10 * h, yy1, k10);
         for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A1101 * k1[i] + CW_A1104 * k4[i] + CW_A1105 * k5[i] + CW_A1106 * k6[i] + CW_A1107 * k7[i] + CW_A1108 * k8[i] + CW_A1109 * k9[i] + CW_A1110 * k10[i]);
-        fcn(P, yy1, k2);
+        fcn(P, x + CW_C11 * h, yy1, k2);
         xph = x + h;
         for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A1201 * k1[i] + CW_A1204 * k4[i] + CW_A1205 * k5[i] + CW_A1206 * k6[i] + CW_A1207 * k7[i] + CW_A1208 * k8[i] + CW_A1209 * k9[i] + CW_A1210 * k10[i] + CW_A1211 * k2[i]);
-        fcn(P, yy1, k3);
+        fcn(P, xph, yy1, k3);
         nfcn += 11;
         for (i = 0; i < n; i++) {
             k4[i] = CW_B01 * k1[i] + CW_B06 * k6[i] + CW_B07 * k7[i] + CW_B08 * k8[i] + CW_B09 * k9[i] + CW_B10 * k10[i] + CW_B11 * k2[i] + CW_B12 * k3[i];
@@ -446,7 +646,7 @@ static int dop853_core(const cwo_potential *P, double x, double *y, double xend,
             /* step accepted */
             facold = max_d(err, 1.0E-4);
             naccpt++;
-            fcn(P, k5, k4);
+            fcn(P, xph, k5, k4);
             nfcn++;
             /* stiffness detection */
             if (!(naccpt % nstiff) || (iasti > 0)) {
@@ -481,11 +681,11 @@ static int dop853_core(const cwo_potential *P, double x, double *y, double xend,
                 }
                 /* the next three function evaluations (k4 = f(x+h, y_new) is stage 13) */
                 for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A1401 * k1[i] + CW_A1407 * k7[i] + CW_A1408 * k8[i] + CW_A1409 * k9[i] + CW_A1410 * k10[i] + CW_A1411 * k2[i] + CW_A1412 * k3[i] + CW_A1413 * k4[i]);
-                fcn(P, yy1, ka);
+                fcn(P, x + 0.1 * h, yy1, ka);
                 for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A1501 * k1[i] + CW_A1506 * k6[i] + CW_A1507 * k7[i] + CW_A1508 * k8[i] + CW_A1511 * k2[i] + CW_A1512 * k3[i] + CW_A1513 * k4[i] + CW_A1514 * ka[i]);
-                fcn(P, yy1, kb);
+                fcn(P, x + 0.2 * h, yy1, kb);
                 for (i = 0; i < n; i++) yy1[i] = y[i] + h * (CW_A1601 * k1[i] + CW_A1606 * k6[i] + CW_A1607 * k7[i] + CW_A1608 * k8[i] + CW_A1609 * k9[i] + CW_A1613 * k4[i] + CW_A1614 * ka[i] + CW_A1615 * kb[i]);
-                fcn(P, yy1, kc);
+                fcn(P, x + 7. / 9. * h, yy1, kc);
                 nfcn += 3;
                 for (i = 0; i < n; i++) {
                     rc[4][i] = h * (rc[4][i] + CW_D413 * k4[i] + CW_D414 * ka[i] + CW_D415 * kb[i] + CW_D416 * kc[i]);

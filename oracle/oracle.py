@@ -17,14 +17,21 @@ MAX_COMP = 16
 LEAPFROG, DOP853, DOP853_DENSE = 0, 1, 2
 FLAG_APPEND_T2 = 1
 
-__all__ = ["build", "lib", "make_potential", "gradient", "value", "circular_velocity", "time_grid",
+__all__ = ["build", "lib", "make_potential", "gradient", "gradient_t", "value", "circular_velocity", "time_grid",
            "leapfrog", "dop853", "dop853_dense", "integrate_orbit", "integrate_batch", "max_threads",
            "LEAPFROG", "DOP853", "DOP853_DENSE", "FLAG_APPEND_T2"]
 
 
+MAX_KNOTS = 32
+
+
 class _Pot(C.Structure):
     _fields_ = [("G", C.c_double), ("n", C.c_int32), ("type", C.c_int32 * MAX_COMP),
-                ("p", (C.c_double * 6) * MAX_COMP)]
+                ("p", (C.c_double * 6) * MAX_COMP),
+                ("has_R", C.c_int32 * MAX_COMP), ("R", (C.c_double * 9) * MAX_COMP),
+                ("n_knots", C.c_int32 * MAX_COMP), ("interp", C.c_int32),
+                ("knot_t", (C.c_double * MAX_KNOTS) * MAX_COMP), ("knot_y", (C.c_double * MAX_KNOTS) * MAX_COMP),
+                ("knot_c", (C.c_double * MAX_KNOTS) * MAX_COMP), ("t_eval", C.c_double)]
 
 
 class _Stats(C.Structure):
@@ -49,6 +56,10 @@ def lib():
         L = C.CDLL(so)
         dp, ip, lp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
         L.cwo_gradient.argtypes = [C.POINTER(_Pot), dp, dp]
+        L.cwo_gradient_t.argtypes = [C.POINTER(_Pot), C.c_double, dp, dp]
+        L.cwo_gradient_t.restype = None
+        L.cwo_prepare.argtypes = [C.POINTER(_Pot)]
+        L.cwo_prepare.restype = None
         L.cwo_value.argtypes = [C.POINTER(_Pot), dp]; L.cwo_value.restype = C.c_double
         L.cwo_circular_velocity.argtypes = [C.POINTER(_Pot), dp]; L.cwo_circular_velocity.restype = C.c_double
         L.cwo_time_grid.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, dp, C.c_int64]
@@ -102,6 +113,24 @@ def make_potential(pot) -> _Pot:
         P.type[i] = int(t)
         for k in range(6):
             P.p[i][k] = float(p[k]) if k < len(p) else 0.0
+    rotations = getattr(pot, "rotations", None) or [None] * P.n
+    for i, Rm in enumerate(rotations):
+        if Rm is not None:
+            P.has_R[i] = 1
+            flat = np.asarray(Rm, dtype=np.float64).reshape(9)
+            for k in range(9):
+                P.R[i][k] = float(flat[k])
+    knots = getattr(pot, "knots", None) or [None] * P.n
+    P.interp = 1 if getattr(pot, "interp", "cubic") == "cubic" else 0
+    for i, kn in enumerate(knots):
+        if kn is not None:
+            t, y = np.asarray(kn[0], dtype=np.float64), np.asarray(kn[1], dtype=np.float64)
+            assert len(t) == len(y) <= MAX_KNOTS
+            P.n_knots[i] = len(t)
+            for k in range(len(t)):
+                P.knot_t[i][k] = float(t[k]); P.knot_y[i][k] = float(y[k])
+    P.t_eval = float(getattr(pot, "t_eval", 0.0))
+    lib().cwo_prepare(C.byref(P))
     return P
 
 
@@ -114,6 +143,14 @@ def gradient(pot, q):
     q = np.ascontiguousarray(q, dtype=np.float64)
     g = np.zeros(3)
     lib().cwo_gradient(C.byref(P), _dp(q), _dp(g))
+    return g
+
+
+def gradient_t(pot, t, q):
+    P = _as_pot(pot)
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    g = np.zeros(3)
+    lib().cwo_gradient_t(C.byref(P), float(t), _dp(q), _dp(g))
     return g
 
 
