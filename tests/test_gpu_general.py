@@ -136,3 +136,27 @@ def test_general_entry_point_validates(ctx):
     with pytest.raises(RuntimeError, match="v_c"):
         ctx.set_potential(P.time_interpolated(log, [0.0, 1.0], [np.array([0.1, 0.2])]))
     ctx.set_potential(P.MilkyWayPotential("v2"))
+
+
+def test_tutorial_evolving_nfw_through_the_reference_signature(ctx, oracle):
+    """evolving_potentials.ipynb cells 4-8: one test particle, 12 Gyr at dt = 1 Myr with the default DOPRI853, in the
+    static and in the growing NFW halo -- through integrate_orbit_with_events, checked against the oracle and against
+    scipy's DOP853 of the same time-dependent equations of motion."""
+    import cogsworth_b200 as cb
+    from scipy.integrate import solve_ivp
+    static = P.CompositePotential(names=["halo"], types=[3], params=[(1e12, 10.0, 0.0)], label="NFW")
+    evolving = P.time_interpolated(static, np.linspace(0, 12000, 20), [np.linspace(1e11, 1e12, 20)])
+    w0 = [8.0, 0.0, 0.0, 50.0, 50.0, -5.0]                       # kpc, km/s (cell 7)
+    k = 1.0 / 977.7922216807891
+    w_gal = np.array(w0[:3] + [v * k for v in w0[3:]])
+    ends = {}
+    for name, pot in (("static", static), ("evolving", evolving)):
+        orb = cb.integrate_orbit_with_events(w0, 0.0, 12.0, 1.0, potential=pot, events=None, store_all=True, context=ctx)
+        assert orb.shape == (12000,) and abs(orb.t[-1] - 11999.0) < 1e-9
+        ref = oracle.integrate_orbit(pot, w_gal, 0.0, 12000.0, 1.0, integrator=oracle.DOP853, store_all=True)
+        assert np.abs(orb.pos.xyz - ref["traj"][:3]).max() < 1e-6
+        sol = solve_ivp(lambda t, y: np.concatenate([y[3:], -oracle.gradient_t(pot, t, y[:3])]), (0.0, 11999.0), w_gal,
+                        method="DOP853", rtol=1e-13, atol=1e-15)
+        assert np.abs(orb.pos.xyz[:, -1] - sol.y[:3, -1]).max() < 1e-6
+        ends[name] = orb.pos.xyz[:, -1]
+    assert np.linalg.norm(ends["static"] - ends["evolving"]) > 1.0       # "the orbits trace very different paths"
