@@ -265,3 +265,49 @@ def test_orbit_wire_format_roundtrip(tmp_path):
     except ImportError:
         with pytest.raises(ImportError):
             save_orbits(str(tmp_path / "pop.h5"), oa)
+
+
+def test_from_gala_translates_rotations_and_time_interpolation():
+    """`from_gala` on stand-ins shaped like gala's classes (class name, .parameters, .R, .items()): the halo angle phi
+    and the bar angle alpha become rotations, an MN3 disk inside a TimeInterpolatedPotential becomes three
+    Miyamoto-Nagai terms whose masses follow the knots (evolving_potentials.ipynb cell 13)."""
+    from cogsworth_b200 import potential as P
+
+    def fake(cls_name, params, **attrs):
+        obj = type(cls_name, (), {})()
+        obj.parameters = params
+        for k, v in attrs.items():
+            setattr(obj, k, v)
+        return obj
+
+    class Composite(dict):
+        G = P.G_GALACTIC
+
+    lm10 = Composite(disk=fake("MiyamotoNagaiPotential", dict(m=1e11, a=6.5, b=0.26)),
+                     bulge=fake("HernquistPotential", dict(m=3.4e10, c=0.7)),
+                     halo=fake("LogarithmicPotential", dict(v_c=0.1762, r_h=12.0, q1=1.38, q2=1.0, q3=1.36,
+                                                            phi=np.deg2rad(97.0))))
+    pot = P.from_gala(lm10)
+    assert pot.types == [P.COMP_MIYAMOTO_NAGAI, P.COMP_HERNQUIST, P.COMP_LOG_TRIAXIAL]
+    assert pot.rotations[0] is None and np.allclose(pot.rotations[2], P.LM10Potential().rotations[2])
+    bar = P.from_gala(fake("LongMuraliBarPotential", dict(m=1e10, a=10.0, b=3.0, c=1.0, alpha=0.3)))
+    assert bar.types == [P.COMP_LONG_MURALI_BAR] and np.allclose(bar.rotations[0], P.rotation_z(0.3))
+    assert bar.params[0] == (1e10, 10.0, 3.0, 1.0)
+
+    knots = np.linspace(0, 12000, 5)
+    frac = np.linspace(0.1, 1.0, 5)
+    MN3 = type("MN3ExponentialDiskPotential", (), {})
+    NFW = type("NFWPotential", (), {})
+    evolving = Composite(
+        disk=fake("TimeInterpolatedPotential", dict(m=6.8e10 * frac, h_R=2.6, h_z=0.3), potential_cls=MN3, time_knots=knots),
+        halo=fake("TimeInterpolatedPotential", dict(m=5.4e11 * frac, r_s=15.63), potential_cls=NFW, time_knots=knots))
+    pot = P.from_gala(evolving)
+    want = P.evolving_milky_way(knots, frac)
+    assert pot.types == [1, 1, 1, 3] and pot.interp == "cubic"
+    off, kt, ka = pot.knot_arrays()
+    assert list(off) == [0, 5, 10, 15, 20] and np.array_equal(kt[:5], knots)
+    assert np.allclose(ka[:15], want.knot_arrays()[2][:15], rtol=1e-14)        # the three MN terms of the same disk
+    assert np.allclose(ka[15:], 5.4e11 * frac)
+    with pytest.raises(NotImplementedError):                                     # a time-dependent scale length
+        P.from_gala(fake("TimeInterpolatedPotential", dict(m=1e12, r_s=np.linspace(10, 20, 5)), potential_cls=NFW,
+                         time_knots=knots))
