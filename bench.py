@@ -59,6 +59,11 @@ WORKLOADS = {
     "config5": dict(cfg_id=5, n_orbits=1_000_000, horizon_gyr=1.0, integrator="dop853", store_all=False,
                     f_sn=1.0, plunging_fraction=0.01, rtol=1e-8, atol=1e-8,
                     desc="1e6 orbits DOPRI853 rtol=atol=1e-8, 1 Gyr, kicks, 1% plunging"),
+    # the tutorial's evolving Milky Way (evolving_potentials.ipynb cell 13) through the general kernels: not a BASELINE
+    # config, the cost of a time-dependent potential beside config 4
+    "config4_evolving": dict(cfg_id=4, n_orbits=2_000_000, horizon_gyr=1.0, integrator="leapfrog", store_all=False,
+                             f_sn=1.0, potential="evolving_mw",
+                             desc="2e6 orbits, evolving Milky Way (TimeInterpolatedPotential masses, 5 knots), leapfrog 1 Gyr dt=1 Myr, kicks, final state"),
 }
 
 
@@ -90,6 +95,15 @@ def build_shard(wl, rank, world, scaling, scale):
         return population_with_n_orbits(n, **kw)
     n = max(int(round(wl["n_binaries"] * share * scale)), 64)
     return make_population(n, **kw)
+
+
+def apply_workload_potential(wl, pop):
+    """Workloads that integrate in another potential than the one the birth velocities were drawn in."""
+    if wl.get("potential") == "evolving_mw":
+        from cogsworth_b200.potential import evolving_milky_way
+        pop.potential = evolving_milky_way(np.linspace(0.0, 12000.0, 5), np.linspace(0.1, 1.0, 5))
+        return "evolving Milky Way: MN3 disk + 2 Hernquist + NFW, masses 10 % -> 100 % over 12 Gyr (general kernels)"
+    return "MilkyWayPotential2022 (MN3 disk + 2 Hernquist + NFW)"
 
 
 class ClockSampler:
@@ -215,6 +229,7 @@ def run_reference(args, wl, rank, world):
         return
     size = wl.get("n_orbits", int(1.8 * wl.get("n_binaries", 0)))
     pop = build_shard(wl, 0, 1, "strong", min(args.scale, 1.0, 2.0 * args.cpu_sample_orbits / size))
+    apply_workload_potential(wl, pop)
     import oracle as O
     threads = O.max_threads()
     n_sample = min(args.cpu_sample_orbits, pop.batch.n_orbits)
@@ -278,6 +293,7 @@ def main():
         return cwdist.reduce_scalar(x, "sum", device=dev)
 
     pop = build_shard(wl, rank, world, args.scaling, args.scale)
+    pot_label = apply_workload_potential(wl, pop)
     b = pop.batch
     n, K = b.n_orbits, b.n_events
     integ = {"leapfrog": _lib.LEAPFROG, "dop853": _lib.DOP853, "dop853_dense": _lib.DOP853_DENSE}[wl["integrator"]]
@@ -387,7 +403,7 @@ def main():
         peak = ctx.measure_fp64_peak(0, 200.0)
         if integ == _lib.LEAPFROG:
             flops = FLOP_PER_STEP["leapfrog_v2"] * steps_per_pass
-            kname, per = "leapfrog_kernel<MW_V2>", FLOP_PER_STEP["leapfrog_v2"]
+            kname, per = ("leapfrog_kernel<GENERAL>" if wl.get("potential") else "leapfrog_kernel<MW_V2>"), FLOP_PER_STEP["leapfrog_v2"]
         else:
             # 12 gradients + 1000 flop of stage algebra per accepted step, per launch
             flops = FLOP_PER_STEP["dop853_v2"] * float(stats_run[0])
@@ -416,7 +432,7 @@ def main():
                 "config": {"workload": f"{args.workload}: {wl['desc']}" + ("" if args.scale == 1.0 else f" [SCALED x{args.scale}: not a valid bench line]"),
                            "n_orbits_total": n_total,
                            "n_kick_events_rank0": K, "orbit_steps_per_step": int(total_steps),
-                           "integrator": wl["integrator"], "potential": "MilkyWayPotential2022 (MN3 disk + 2 Hernquist + NFW)",
+                           "integrator": wl["integrator"], "potential": pot_label,
                            "parallelism": f"orbits sharded by index over {world} GPU(s), no collective"
                                           + (f"; ranks bound to their GPU's NUMA node (rank 0: node {numa_node})" if numa_node is not None else ""),
                            "cache": "inputs + outputs (>= 1 GB per pass) exceed the 126 MB L2; nothing is reused between steps",

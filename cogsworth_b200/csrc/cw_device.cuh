@@ -369,30 +369,35 @@ __host__ __device__ inline double gamma_p(double a, double x, double lgam_a)
     return 1.0 - pref * h;
 }
 
-// gradient (and, when phi != nullptr, value) of ONE non-diagonal component in its own frame; amp = GM[i] * rel
-__device__ __forceinline__ void nondiag_component(const PotParams &P, int i, double amp, double x, double y, double z,
-                                                  double &gx, double &gy, double &gz, double *phi)
+// gradient (and, when want_phi, value) of ONE non-diagonal component in its own frame; amp = GM[i] * rel.
+// Deliberately NOT inlined, with every parameter passed by value: the formulas below leave FMA contraction to the
+// compiler, and one compiled copy is what makes the final-state kernels return the bits of the store_all kernels
+// (an inlined copy per kernel was contracted differently in each -- caught by the bit-equality test).
+struct Vec4 { double x, y, z, w; };
+static __device__ __noinline__ Vec4 nondiag_component_v(int t, double amp, double pe0, double pe1, double pe2, double pe3,
+                                                        double x, double y, double z, bool want_phi)
 {
-    const int t = P.type[i];
+    Vec4 o;
+    o.w = 0.0;
     if (t == CW_COMP_LONG_MURALI_BAR) {          // pe = (a, b, c^2)
-        const double a = P.pe[i][0];
-        const double sz = sqrt(fma(z, z, P.pe[i][2]));
-        const double B = P.pe[i][1] + sz;
+        const double a = pe0;
+        const double sz = sqrt(fma(z, z, pe2));
+        const double B = pe1 + sz;
         const double D = fma(y, y, B * B);
         const double xm = a - x, xp = a + x;
         const double Tm = sqrt(fma(xm, xm, D)), Tp = sqrt(fma(xp, xp, D));
         const double sT = Tm + Tp;
         const double f1 = amp / (2.0 * Tm * Tp);
-        gx = 4.0 * f1 * x / sT;
+        o.x = 4.0 * f1 * x / sT;
         const double cm = f1 / D * (sT - 4.0 * x * x / sT);
-        gy = cm * y;
-        gz = cm * B * z / sz;
-        if (phi) *phi = amp / (2.0 * a) * log((x - a + Tm) / (x + a + Tp));
+        o.y = cm * y;
+        o.z = cm * B * z / sz;
+        if (want_phi) o.w = amp / (2.0 * a) * log((x - a + Tm) / (x + a + Tp));
     } else if (t == CW_COMP_LEESUTO_NFW) {       // amp = phi0, pe = (1 / r_s, e_b^2, e_c^2)
-        const double eb2 = P.pe[i][1], ec2 = P.pe[i][2];
+        const double eb2 = pe1, ec2 = pe2;
         const double r2 = fma(z, z, fma(y, y, x * x));
         const double r = sqrt(r2);
-        const double u = r * P.pe[i][0];
+        const double u = r * pe0;
         const double L = log(1.0 + u);
         const double u2 = u * u, u3 = u2 * u, u4 = u2 * u2, opu = 1.0 + u;
         const double N = u2 - 3.0 * u - 6.0, Dn = 2.0 * u2 * opu;
@@ -402,31 +407,40 @@ __device__ __forceinline__ void nondiag_component(const PotParams &P, int i, dou
         const double dF3 = ((2.0 * u - 3.0) * Dn - N * (4.0 * u + 6.0 * u2)) / (Dn * Dn) + 3.0 / (u3 * opu) - 9.0 * L / u4;
         const double E = 0.5 * (eb2 + ec2);
         const double S = 0.5 * (eb2 * y * y + ec2 * z * z);
-        const double radial = (dF1 + E * dF2 + S / r2 * dF3) * P.pe[i][0] / r;
+        const double radial = (dF1 + E * dF2 + S / r2 * dF3) * pe0 / r;
         const double c3 = F3 / r2;
         const double w = 2.0 * S / r2;
-        gx = amp * (radial * x - c3 * w * x);
-        gy = amp * (radial * y + c3 * (eb2 - w) * y);
-        gz = amp * (radial * z + c3 * (ec2 - w) * z);
-        if (phi) {
+        o.x = amp * (radial * x - c3 * w * x);
+        o.y = amp * (radial * y + c3 * (eb2 - w) * y);
+        o.z = amp * (radial * z + c3 * (ec2 - w) * z);
+        if (want_phi) {
             const double F1 = -L / u;
             const double F2 = -1.0 / 3.0 + (2.0 * u2 - 3.0 * u + 6.0) / (6.0 * u2) + (1.0 / u - 1.0 / u3) * L;
-            *phi = amp * (F1 + E * F2 + S / r2 * F3);
+            o.w = amp * (F1 + E * F2 + S / r2 * F3);
         }
     } else {                                     // CW_COMP_POWERLAW_CUTOFF: pe = (s = 1.5 - alpha/2, 1/r_c^2, lgamma(s), lgamma(s - 0.5))
         const double r2 = fma(z, z, fma(y, y, x * x));
         const double r = sqrt(r2);
-        const double xx = r2 * P.pe[i][1];
-        const double Pm = gamma_p(P.pe[i][0], xx, P.pe[i][2]);      // M(<r) / m
+        const double xx = r2 * pe1;
+        const double Pm = gamma_p(pe0, xx, pe2);      // M(<r) / m
         const double f = amp * Pm / (r2 * r);
-        gx = f * x; gy = f * y; gz = f * z;
-        if (phi) {
+        o.x = f * x; o.y = f * y; o.z = f * z;
+        if (want_phi) {
             // -G M(<r)/r - G m Gamma(s - 1/2, x) / (r_c Gamma(s)): the shells outside r  (needs alpha < 2)
-            const double a2 = P.pe[i][0] - 0.5;
-            const double Q2 = 1.0 - gamma_p(a2, xx, P.pe[i][3]);
-            *phi = -amp * (Pm / r + Q2 * exp(P.pe[i][3] - P.pe[i][2]) * sqrt(P.pe[i][1]));
+            const double Q2 = 1.0 - gamma_p(pe0 - 0.5, xx, pe3);
+            o.w = -amp * (Pm / r + Q2 * exp(pe3 - pe2) * sqrt(pe1));
         }
     }
+    return o;
+}
+
+__device__ __forceinline__ void nondiag_component(const PotParams &P, int i, double amp, double x, double y, double z,
+                                                  double &gx, double &gy, double &gz, double *phi)
+{
+    const Vec4 o = nondiag_component_v(P.type[i], amp, P.pe[i][0], P.pe[i][1], P.pe[i][2], P.pe[i][3], x, y, z,
+                                       phi != nullptr);
+    gx = o.x; gy = o.y; gz = o.z;
+    if (phi) *phi = o.w;
 }
 
 __device__ __forceinline__ bool comp_is_nondiag(int t) { return t >= CW_COMP_LONG_MURALI_BAR; }
@@ -534,7 +548,7 @@ __device__ __forceinline__ void force_generic(const PotParams &P, LogTab ltab,
 }
 
 // POT_GENERAL: gradient at time t [Myr], components accumulated in the caller's order (c_gradient)
-static __device__ __noinline__ void gradient_general(const PotParams &P, LogTab ltab, double t,
+static __device__ __forceinline__ void gradient_general(const PotParams &P, LogTab ltab, double t,
                                               double x, double y, double z, double &gx, double &gy, double &gz)
 {
     double ax = 0.0, ay = 0.0, az = 0.0;
@@ -542,24 +556,26 @@ static __device__ __noinline__ void gradient_general(const PotParams &P, LogTab 
         const double rel = amplitude_rel(P, i, t);
         double xr = x, yr = y, zr = z;
         if (P.has_R[i]) {
-            xr = fma(P.R[i][2], z, fma(P.R[i][1], y, P.R[i][0] * x));
-            yr = fma(P.R[i][5], z, fma(P.R[i][4], y, P.R[i][3] * x));
-            zr = fma(P.R[i][8], z, fma(P.R[i][7], y, P.R[i][6] * x));
+            xr = fma(P.R[i][2], z, fma(P.R[i][1], y, __dmul_rn(P.R[i][0], x)));
+            yr = fma(P.R[i][5], z, fma(P.R[i][4], y, __dmul_rn(P.R[i][3], x)));
+            zr = fma(P.R[i][8], z, fma(P.R[i][7], y, __dmul_rn(P.R[i][6], x)));
         }
         double cx, cy, cz;
         if (comp_is_nondiag(P.type[i])) {
-            nondiag_component(P, i, P.GM[i] * rel, xr, yr, zr, cx, cy, cz, nullptr);
+            nondiag_component(P, i, __dmul_rn(P.GM[i], rel), xr, yr, zr, cx, cy, cz, nullptr);
         } else {
             double Fx, Fy, Fz;
             force_generic_range(P, ltab, i, i + 1, xr, yr, zr, Fx, Fy, Fz);
-            cx = (Fx * rel) * xr; cy = (Fy * rel) * yr; cz = (Fz * rel) * zr;
+            cx = __dmul_rn(__dmul_rn(Fx, rel), xr);
+            cy = __dmul_rn(__dmul_rn(Fy, rel), yr);
+            cz = __dmul_rn(__dmul_rn(Fz, rel), zr);
         }
         if (P.has_R[i]) {
-            ax += fma(P.R[i][6], cz, fma(P.R[i][3], cy, P.R[i][0] * cx));
-            ay += fma(P.R[i][7], cz, fma(P.R[i][4], cy, P.R[i][1] * cx));
-            az += fma(P.R[i][8], cz, fma(P.R[i][5], cy, P.R[i][2] * cx));
+            ax = __dadd_rn(ax, fma(P.R[i][6], cz, fma(P.R[i][3], cy, __dmul_rn(P.R[i][0], cx))));
+            ay = __dadd_rn(ay, fma(P.R[i][7], cz, fma(P.R[i][4], cy, __dmul_rn(P.R[i][1], cx))));
+            az = __dadd_rn(az, fma(P.R[i][8], cz, fma(P.R[i][5], cy, __dmul_rn(P.R[i][2], cx))));
         } else {
-            ax += cx; ay += cy; az += cz;
+            ax = __dadd_rn(ax, cx); ay = __dadd_rn(ay, cy); az = __dadd_rn(az, cz);
         }
     }
     gx = ax; gy = ay; gz = az;

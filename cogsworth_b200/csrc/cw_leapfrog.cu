@@ -240,7 +240,7 @@ __device__ __forceinline__ void write_final(const IntegArgs &A, const Lane &s)
 }
 
 template <int KIND, bool STORE>
-__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? 128 : CW_LF_REGS) leapfrog_kernel(const __grid_constant__ PotParams P,
+__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__((STORE || KIND == POT_GENERAL) ? 128 : CW_LF_REGS) leapfrog_kernel(const __grid_constant__ PotParams P,
                                                             const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
