@@ -286,9 +286,44 @@ static int set_potential_impl(cw_ctx *ctx, double G, int n_comp, const int32_t *
     memset(&P, 0, sizeof P);
     P.n_comp = n_comp;
     P.G = G;
-    bool general = false;
-    // time-interpolated first parameter: the static tables are built for a unit amplitude, the spline carries m(t)
-    if (knot_off) {
+    bool general = false, separable = false;
+    // Separable time dependence: every component carries knots at the same times and every amplitude curve is the
+    // same multiple of its own last value (the tutorial's `mass * mass_fractions`), nothing is rotated or
+    // non-diagonal.  Then Phi(q, t) = f(t) Phi_0(q) and the static kernels run with one scale factor.
+    if (knot_off && n_comp > 0 && knot_t && knot_amp && knot_off[0] == 0 && knot_off[1] >= 2 && knot_off[1] <= CW_MAX_KNOTS &&
+        (interp == CW_INTERP_LINEAR || interp == CW_INTERP_CUBIC)) {
+        const int nk = knot_off[1];
+        separable = true;
+        for (int i = 0; i < n_comp && separable; i++) {
+            const int t = types[i];
+            if (knot_off[i + 1] - knot_off[i] != nk || t >= CW_COMP_LONG_MURALI_BAR || t == CW_COMP_LOGARITHMIC ||
+                t == CW_COMP_LOG_TRIAXIAL || t < CW_COMP_MIYAMOTO_NAGAI) { separable = false; break; }
+            const double *ti = knot_t + knot_off[i], *ai = knot_amp + knot_off[i];
+            const double ref_i = ai[nk - 1], ref_0 = knot_amp[nk - 1];
+            if (!(std::isfinite(ref_i) && ref_i != 0.0 && ref_0 != 0.0)) { separable = false; break; }
+            for (int j = 0; j < nk; j++) {
+                const double r_i = ai[j] / ref_i, r_0 = knot_amp[j] / ref_0;
+                if (!(ti[j] == knot_t[j]) || !std::isfinite(ai[j]) || fabs(r_i - r_0) > 4e-16 * fmax(fabs(r_0), 1.0) ||
+                    (j > 0 && !(ti[j] > ti[j - 1]))) { separable = false; break; }
+            }
+        }
+        if (rotations)
+            for (int i = 0; i < n_comp && separable; i++) {
+                const double *Rm = rotations + 9 * (size_t)i;
+                bool identity = true;
+                for (int k = 0; k < 9; k++) identity = identity && (Rm[k] == ((k % 4 == 0) ? 1.0 : 0.0));
+                if (!std::isnan(Rm[0]) && !identity) separable = false;
+            }
+        if (separable) {
+            std::vector<double> ratio(nk);
+            for (int j = 0; j < nk; j++) { ratio[j] = knot_amp[j] / knot_amp[nk - 1]; P.k_t[j] = knot_t[j]; }
+            spline_coefficients(nk, knot_t, ratio.data(), interp, P.k_c);
+            P.k_off[0] = 0;
+            for (int i = 1; i <= n_comp; i++) P.k_off[i] = nk;      // f(t) lives in the slot of "component 0"
+            for (int i = 0; i < n_comp; i++) params[3 * i + 0] = knot_amp[knot_off[i] + nk - 1];
+        }
+    }
+    if (knot_off && !separable) {
         if (interp != CW_INTERP_LINEAR && interp != CW_INTERP_CUBIC)
             return fail(ctx, CW_E_INVALID, "cw_set_potential_general: interp must be CW_INTERP_LINEAR or CW_INTERP_CUBIC");
         if (knot_off[0] != 0 || knot_off[n_comp] > CW_MAX_KNOTS)
@@ -313,7 +348,16 @@ static int set_potential_impl(cw_ctx *ctx, double G, int n_comp, const int32_t *
         }
         P.k_off[n_comp] = knot_off[n_comp];
     }
-    if (rotations) {
+    // equally spaced knots (np.linspace) are indexed directly
+    for (int i = 0; i < n_comp; i++) {
+        const int a = P.k_off[i], b = P.k_off[i + 1];
+        if (b - a < 3) continue;
+        const double dt = (P.k_t[b - 1] - P.k_t[a]) / (double)(b - a - 1);
+        bool uniform = true;
+        for (int j = a; j < b; j++) uniform = uniform && fabs(P.k_t[j] - (P.k_t[a] + dt * (double)(j - a))) <= 1e-12 * fabs(dt);
+        if (uniform) { P.k_t0[i] = P.k_t[a]; P.k_inv_dt[i] = 1.0 / dt; }
+    }
+    if (rotations && !separable) {
         for (int i = 0; i < n_comp; i++) {
             const double *Rm = rotations + 9 * (size_t)i;
             if (std::isnan(Rm[0])) continue;
@@ -428,6 +472,7 @@ static int set_potential_impl(cw_ctx *ctx, double G, int n_comp, const int32_t *
             P.nfw_inv_rs = 1.0 / P.nfw_rs;
         }
     }
+    if (separable) P.kind = (P.kind == POT_MW_V2) ? POT_MW_V2_T : POT_GENERIC_T;
     pot_fill_constants(P);
     ctx->pot = P;
     ctx->has_pot = true;

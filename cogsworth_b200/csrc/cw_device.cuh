@@ -139,7 +139,16 @@ enum PotKind : int {
     POT_GENERIC = 0, // any ordered list of components (loop + switch)
     POT_MW_V1 = 1,   // MiyamotoNagai + Hernquist + Hernquist + spherical NFW
     POT_MW_V2 = 2,   // 3 x MiyamotoNagai sharing b (MN3 disk) + Hernquist + Hernquist + NFW
-    POT_GENERAL = 3  // full gradient vector: rotated / non-diagonal components, time-interpolated amplitudes
+    POT_GENERAL = 3, // full gradient vector: rotated / non-diagonal components, time-interpolated amplitudes
+    // Separable time dependence Phi(q, t) = f(t) Phi_0(q): every mass follows the same curve (the reference's
+    // evolving-potential tutorial: one mass-fraction array for all components).  The static kernels with one spline
+    // evaluation and three multiplications per gradient; f(t) is stored as the knots of "component 0".
+    POT_MW_V2_T = 4,
+    POT_GENERIC_T = 5
+};
+template <int KIND> struct KindTraits {
+    static constexpr bool TS = (KIND == POT_MW_V2_T || KIND == POT_GENERIC_T);
+    static constexpr int BASE = (KIND == POT_MW_V2_T) ? POT_MW_V2 : (KIND == POT_GENERIC_T) ? POT_GENERIC : KIND;
 };
 
 struct PotParams {
@@ -168,6 +177,8 @@ struct PotParams {
     double k_t[CW_MAX_KNOTS];              // knot times [Myr]
     double k_c[CW_MAX_KNOTS][4];           // amplitude relative to GM[i] on [k_t[j], k_t[j+1]]:
                                            // c0 + s (c1 + s (c2 + s c3)), s = t - k_t[j]
+    double k_t0[CW_MAX_COMPONENTS];        // equally spaced knots (np.linspace): first knot and 1 / spacing, else 0
+    double k_inv_dt[CW_MAX_COMPONENTS];
     double t_eval;                         // time of the pointwise kernels
 };
 
@@ -328,9 +339,15 @@ __device__ __forceinline__ double amplitude_rel(const PotParams &P, int i, doubl
     if (b - a == 1) return P.k_c[a][0];
     t = fmin(fmax(t, P.k_t[a]), P.k_t[b - 1]);     // the end values are held outside the knots
     int lo = a, hi = b - 2;                        // interval index: k_t[j] <= t <= k_t[j+1]
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (t >= P.k_t[mid]) lo = mid; else hi = mid - 1;
+    if (P.k_inv_dt[i] > 0.0) {
+        // equally spaced knots: the index directly.  Rounding may pick the neighbour of the exact interval when t
+        // sits within an ulp of a knot; the two cubics agree there.
+        lo = a + min(max(__double2int_rd((t - P.k_t0[i]) * P.k_inv_dt[i]), 0), hi - a);
+    } else {
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (t >= P.k_t[mid]) lo = mid; else hi = mid - 1;
+        }
     }
     const double s = t - P.k_t[lo];
     return fma(s, fma(s, fma(s, P.k_c[lo][3], P.k_c[lo][2]), P.k_c[lo][1]), P.k_c[lo][0]);
@@ -610,6 +627,13 @@ __device__ __forceinline__ void gradient(const PotParams &P, LogTab ltab, double
 {
     if (KIND == POT_GENERAL) {
         gradient_general(P, ltab, t, x, y, z, gx, gy, gz);
+    } else if (KindTraits<KIND>::TS) {
+        double Fx, Fy, Fz;
+        force3<KindTraits<KIND>::BASE>(P, ltab, x, y, z, Fx, Fy, Fz);
+        const double f = amplitude_rel(P, 0, t);
+        gx = (Fx * f) * x;
+        gy = (Fy * f) * y;
+        gz = (Fz * f) * z;
     } else {
         double Fx, Fy, Fz;
         force3<KIND>(P, ltab, x, y, z, Fx, Fy, Fz);
@@ -625,8 +649,15 @@ template <int KIND>
 __device__ __forceinline__ void force3t(const PotParams &P, LogTab ltab, double t,
                                         double x, double y, double z, double &Fx, double &Fy, double &Fz)
 {
-    if (KIND == POT_GENERAL) gradient_general(P, ltab, t, x, y, z, Fx, Fy, Fz);
-    else force3<KIND>(P, ltab, x, y, z, Fx, Fy, Fz);
+    if (KIND == POT_GENERAL) {
+        gradient_general(P, ltab, t, x, y, z, Fx, Fy, Fz);
+    } else if (KindTraits<KIND>::TS) {
+        force3<KindTraits<KIND>::BASE>(P, ltab, x, y, z, Fx, Fy, Fz);
+        const double f = amplitude_rel(P, 0, t);
+        Fx *= f; Fy *= f; Fz *= f;
+    } else {
+        force3<KIND>(P, ltab, x, y, z, Fx, Fy, Fz);
+    }
 }
 
 // vh + coef * grad_c, with grad_c = F * pos (diagonal kinds) or F itself (POT_GENERAL)
@@ -652,6 +683,7 @@ __device__ __forceinline__ double potential_value(const PotParams &P, double x0,
     for (int i = 0; i < P.n_comp; i++) {
         const int t = P.type[i];
         double x = x0, y = y0, z = z0, rel = 1.0;
+        if (P.kind == POT_MW_V2_T || P.kind == POT_GENERIC_T) rel = amplitude_rel(P, 0, P.t_eval);
         if (P.kind == POT_GENERAL) {
             rel = amplitude_rel(P, i, P.t_eval);
             if (P.has_R[i]) {

@@ -425,11 +425,12 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
         // store_all run bit for bit):  x += vh dt;  F = force(x);  v = vh - grad dt/2;  vh -= grad dt,
         // with grad = (Fxy x, Fxy y, Fz z) folded into the FMAs: vh = fma(Fxy * (-dt), x, vh).
         const double dt = s.dt, ndt = -s.dt, nhdt = -0.5 * s.dt;
-        constexpr bool TRI = (KIND == POT_GENERIC);    // only the generic composite can have Fy != Fx
+        constexpr bool TRI = (KindTraits<KIND>::BASE == POT_GENERIC);    // only the generic composite can have Fy != Fx
+        constexpr bool TS = KindTraits<KIND>::TS;      // Phi = f(t) Phi_0: the factors are scaled by f(t_node)
         constexpr bool GEN = (KIND == POT_GENERAL);    // (Fxy, Fy, Fz) is the gradient itself, evaluated at the node's time
         // time [Myr] of node J of this lane's orbit (POT_GENERAL only: the gradient of step j-1 -> j is taken at t_j)
         auto tnode = [&](int J) -> double {
-            if (!GEN) return 0.0;
+            if (!GEN && !TS) return 0.0;
             return ((s.append && J == s.L) ? s.t2 : fma((double)J, s.hgrid, s.tcur)) * s.smyr;
         };
         if (GEN) {
@@ -454,7 +455,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 s.x = fma(s.vhx, dt, s.x);
                 s.y = fma(s.vhy, dt, s.y);
                 s.z = fma(s.vhz, dt, s.z);
-                force3<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+                force3t<KIND>(P, ltab, tnode(s.j + q), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
                 const double a = s.Fxy * ndt, b = s.Fz * ndt;
                 const double ay = TRI ? s.Fy * ndt : a;
                 s.vhx = fma(a, s.x, s.vhx);
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 s.x = fma(s.vhx, dt, s.x);
                 s.y = fma(s.vhy, dt, s.y);
                 s.z = fma(s.vhz, dt, s.z);
-                force3<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+                force3t<KIND>(P, ltab, tnode(s.j + q), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
                 const double ah = s.Fxy * nhdt, bh = s.Fz * nhdt;
                 const double ahy = TRI ? s.Fy * nhdt : ah;
                 s.vx = fma(ah, s.x, s.vhx);
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
             s.x = fma(s.vhx, dt, s.x);
             s.y = fma(s.vhy, dt, s.y);
             s.z = fma(s.vhz, dt, s.z);
-            force3<KIND>(P, ltab, s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+            force3t<KIND>(P, ltab, tnode(s.j + m), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
             const double ah = s.Fxy * nhdt, bh = s.Fz * nhdt;
             const double ahy = TRI ? s.Fy * nhdt : ah;
             s.vx = fma(ah, s.x, s.vhx);
@@ -569,6 +570,10 @@ cudaError_t launch_leapfrog(const PotParams &P, const IntegArgs &A, bool store_a
         return store_all ? launch_lf<POT_MW_V2, true>(P, A, cfg) : launch_lf<POT_MW_V2, false>(P, A, cfg);
     case POT_GENERAL:
         return store_all ? launch_lf<POT_GENERAL, true>(P, A, cfg) : launch_lf<POT_GENERAL, false>(P, A, cfg);
+    case POT_MW_V2_T:
+        return store_all ? launch_lf<POT_MW_V2_T, true>(P, A, cfg) : launch_lf<POT_MW_V2_T, false>(P, A, cfg);
+    case POT_GENERIC_T:
+        return store_all ? launch_lf<POT_GENERIC_T, true>(P, A, cfg) : launch_lf<POT_GENERIC_T, false>(P, A, cfg);
     default:
         return store_all ? launch_lf<POT_GENERIC, true>(P, A, cfg) : launch_lf<POT_GENERIC, false>(P, A, cfg);
     }
