@@ -182,6 +182,9 @@ constexpr int LF_BLOCK_STORE = 512;
 #ifndef CW_LF_REGS
 #define CW_LF_REGS 64      // experiment knob: 80 -> 3 resident CTAs (measured: see DESIGN.md)
 #endif
+#ifndef CW_LF_GEN_REGS
+#define CW_LF_GEN_REGS 128 // final-state kernel of the general kind (80 spills 470 bytes; not measured)
+#endif
 // Register budgets (__maxnreg__ on the kernel): 64 for the final-state kernel = 4 resident CTAs of 256 threads,
 // 128 for the store_all kernel = its single 512-thread CTA.
 
@@ -240,7 +243,7 @@ __device__ __forceinline__ void write_final(const IntegArgs &A, const Lane &s)
 }
 
 template <int KIND, bool STORE>
-__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__((STORE || KIND == POT_GENERAL) ? 128 : CW_LF_REGS) leapfrog_kernel(const __grid_constant__ PotParams P,
+__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? 128 : (KIND == POT_GENERAL) ? CW_LF_GEN_REGS : CW_LF_REGS) leapfrog_kernel(const __grid_constant__ PotParams P,
                                                             const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;

@@ -182,7 +182,9 @@ int cw_set_potential_ex(cw_ctx *ctx, double G, int n_components, const int32_t *
  *               knot_amp = the first parameter at the knots; `interp` = CW_INTERP_LINEAR / CW_INTERP_CUBIC.
  *               Outside the knots the end values are held.  A component with 0 knots is static.
  * Potentials that need none of this and contain no non-diagonal component are routed to the same kernels as
- * cw_set_potential_ex. */
+ * cw_set_potential_ex.  When every component carries the same knot times and every amplitude curve is the same
+ * multiple of its own last value (one mass-fraction array for all components, as in the tutorial), the potential is
+ * separable, Phi(q, t) = f(t) Phi_0(q), and runs in the static kernels with one scale factor per gradient. */
 int cw_set_potential_general(cw_ctx *ctx, double G, int n_components, const int32_t *types, const double *params,
                              int stride, const double *rotations, const int32_t *knot_off, const double *knot_t,
                              const double *knot_amp, int interp);
