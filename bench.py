@@ -37,7 +37,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FLOP_PER_STEP = {"leapfrog_v2": 114.0, "leapfrog_v1": 78.0, "dop853_v2": 2152.0}
+FLOP_PER_STEP = {"leapfrog_v2": 114.0, "leapfrog_v1": 78.0, "dop853_v2": 2152.0,
+                 # LM10 by the same counting: shared radii 6 + MN 18 + Hernquist 10 + triaxial logarithmic 13
+                 # + its rotation there and back 30 + leapfrog 18
+                 "leapfrog_lm10": 95.0}
 BYTES_PER_STORED_STEP = 48.0
 
 WORKLOADS = {
@@ -64,6 +67,9 @@ WORKLOADS = {
     "config4_evolving": dict(cfg_id=4, n_orbits=2_000_000, horizon_gyr=1.0, integrator="leapfrog", store_all=False,
                              f_sn=1.0, potential="evolving_mw",
                              desc="2e6 orbits, evolving Milky Way (TimeInterpolatedPotential masses, 5 knots), leapfrog 1 Gyr dt=1 Myr, kicks, final state"),
+    "config4_lm10": dict(cfg_id=4, n_orbits=1_000_000, horizon_gyr=1.0, integrator="leapfrog", store_all=False,
+                         f_sn=1.0, potential="lm10",
+                         desc="1e6 orbits, LM10Potential (MN disk + Hernquist bulge + rotated triaxial logarithmic halo), leapfrog 1 Gyr dt=1 Myr, kicks, final state"),
 }
 
 
@@ -103,6 +109,10 @@ def apply_workload_potential(wl, pop):
         from cogsworth_b200.potential import evolving_milky_way
         pop.potential = evolving_milky_way(np.linspace(0.0, 12000.0, 5), np.linspace(0.1, 1.0, 5))
         return "evolving Milky Way: MN3 disk + 2 Hernquist + NFW, masses 10 % -> 100 % over 12 Gyr (general kernels)"
+    if wl.get("potential") == "lm10":
+        from cogsworth_b200.potential import LM10Potential
+        pop.potential = LM10Potential()
+        return "LM10Potential: MN disk + Hernquist bulge + logarithmic halo (q1 = 1.38, q3 = 1.36, phi = 97 deg) (general kernels)"
     return "MilkyWayPotential2022 (MN3 disk + 2 Hernquist + NFW)"
 
 
@@ -402,8 +412,9 @@ def main():
     else:
         peak = ctx.measure_fp64_peak(0, 200.0)
         if integ == _lib.LEAPFROG:
-            flops = FLOP_PER_STEP["leapfrog_v2"] * steps_per_pass
-            kname, per = ("leapfrog_kernel<GENERAL>" if wl.get("potential") else "leapfrog_kernel<MW_V2>"), FLOP_PER_STEP["leapfrog_v2"]
+            per = FLOP_PER_STEP["leapfrog_lm10" if wl.get("potential") == "lm10" else "leapfrog_v2"]
+            flops = per * steps_per_pass
+            kname = {"evolving_mw": "leapfrog_kernel<MW_V2_T>", "lm10": "leapfrog_kernel<GENERAL>"}.get(wl.get("potential"), "leapfrog_kernel<MW_V2>")
         else:
             # 12 gradients + 1000 flop of stage algebra per accepted step, per launch
             flops = FLOP_PER_STEP["dop853_v2"] * float(stats_run[0])

@@ -33,7 +33,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return OUT
     extra = []
-    for knob in ("CW_TRAJ_NOSTORE", "CW_TRAJ_DEBUG", "CW_LF_REGS", "CW_DP_MINB", "CW_STORE_UNROLL"):      # experiment knobs (see cw_traj.cuh / cw_leapfrog.cu)
+    for knob in ("CW_TRAJ_NOSTORE", "CW_TRAJ_DEBUG", "CW_LF_REGS", "CW_LF_GEN_REGS", "CW_DP_MINB", "CW_STORE_UNROLL"):      # experiment knobs (see cw_traj.cuh / cw_leapfrog.cu)
         if os.environ.get(knob):
             extra.append(f"-D{knob}=" + os.environ[knob])
     cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES

@@ -564,6 +564,99 @@ __device__ __forceinline__ void force_generic(const PotParams &P, LogTab ltab,
     force_generic_range(P, ltab, 0, P.n_comp, x, y, z, Fxy, Fy, Fz);
 }
 
+// The three diagonal factors of ONE component (types 1..12) for the general kernels: grad = (Fx x, Fy y, Fz z).
+// The same formulas as force_generic_range, behind a jump table instead of a chain of comparisons and without the
+// bookkeeping that lets a whole composite share one radius.
+__device__ __forceinline__ void diag_component(const PotParams &P, LogTab ltab, const int i,
+                                               double x, double y, double z, double &Fx, double &Fy, double &Fz)
+{
+    const double R2 = fma(y, y, x * x);
+    const double z2 = z * z;
+    const double r2 = R2 + z2;
+    const double GM = P.GM[i], p1 = P.p1[i], p2 = P.p2[i];
+    double f;
+    switch (P.type[i]) {
+    case CW_COMP_MIYAMOTO_NAGAI: {
+        const double q = fma(p2, p2, z2);
+        const double isz = rsqrt_fast(q);
+        const double zd = p1 + q * isz;
+        const double rs = rsqrt_fast(fma(zd, zd, R2));
+        f = (rs * rs) * (GM * rs);
+        Fx = Fy = f;
+        Fz = f * fma(p1, isz, 1.0);
+        return;
+    }
+    case CW_COMP_LOGARITHMIC: {                 // GM = v_c^2, p1 = r_h^2, p2 = 1/q3^2
+        f = GM * rcp_fast(fma(z2, p2, R2 + p1));
+        Fx = Fy = f;
+        Fz = f * p2;
+        return;
+    }
+    case CW_COMP_NFW_TRIAXIAL: {
+        const double m2 = fma(z2, P.q2[i][2], fma(y * y, P.q2[i][1], (x * x) * P.q2[i][0]));
+        const double im = rsqrt_fast(m2);
+        const double u = (m2 * im) * p2;
+        const double w = 1.0 + u;
+        const double bracket = (ltab.on() ? log_tab(P, w, ltab) : log_fast(w)) - u * rcp_fast(w);
+        f = GM * ((im * im) * im) * bracket;
+        Fx = f * P.q2[i][0]; Fy = f * P.q2[i][1]; Fz = f * P.q2[i][2];
+        return;
+    }
+    case CW_COMP_LOG_TRIAXIAL: {                // GM = v_c^2, p1 = r_h^2, q2 = 1 / q_i^2
+        const double S = fma(z2, P.q2[i][2], fma(y * y, P.q2[i][1], fma(x * x, P.q2[i][0], p1)));
+        f = GM * rcp_fast(S);
+        Fx = f * P.q2[i][0]; Fy = f * P.q2[i][1]; Fz = f * P.q2[i][2];
+        return;
+    }
+    case CW_COMP_KUZMIN: {
+        const double az = p1 + fabs(z);
+        const double is = rsqrt_fast(fma(az, az, R2));
+        f = GM * ((is * is) * is);
+        Fx = Fy = f;
+        Fz = (z != 0.0) ? f * (az * rcp_fast(fabs(z))) : 0.0;
+        return;
+    }
+    case CW_COMP_PLUMMER: {                     // p2 = b^2
+        const double is = rsqrt_fast(r2 + p2);
+        f = GM * ((is * is) * is);
+        break;
+    }
+    case CW_COMP_ISOCHRONE: {                   // p1 = b, p2 = b^2
+        const double s2 = r2 + p2;
+        const double is = rsqrt_fast(s2);
+        const double sb = fma(s2, is, p1);
+        f = GM * is * rcp_fast(sb * sb);
+        break;
+    }
+    default: {
+        const double ir = rsqrt_fast(r2);
+        const double r = r2 * ir;
+        switch (P.type[i]) {
+        case CW_COMP_HERNQUIST: {
+            const double rc = r + p1;
+            f = GM * rcp_fast(rc * rc) * ir;
+            break;
+        }
+        case CW_COMP_BURKERT: {                 // GM = pi G rho r0, p1 = r0, p2 = 1 / r0
+            const double xb = r * p2;
+            const double br = log(fma(xb, xb, 1.0)) + 2.0 * log(1.0 + xb) - 2.0 * atan(xb);
+            f = GM * br * rcp_fast(xb * xb) * ir;
+            break;
+        }
+        case CW_COMP_KEPLER: f = GM * ((ir * ir) * ir); break;
+        case CW_COMP_JAFFE: f = GM * (ir * ir) * rcp_fast(r + p1); break;
+        default: {                              // CW_COMP_NFW_SPHERICAL: p2 = 1 / r_s
+            const double u = r * p2;
+            const double w = 1.0 + u;
+            const double bracket = (ltab.on() ? log_tab(P, w, ltab) : log_fast(w)) - u * rcp_fast(w);
+            f = GM * ((ir * ir) * ir) * bracket;
+        }
+        }
+    }
+    }
+    Fx = Fy = Fz = f;
+}
+
 // POT_GENERAL: gradient at time t [Myr], components accumulated in the caller's order (c_gradient)
 static __device__ __forceinline__ void gradient_general(const PotParams &P, LogTab ltab, double t,
                                               double x, double y, double z, double &gx, double &gy, double &gz)
@@ -582,7 +675,7 @@ static __device__ __forceinline__ void gradient_general(const PotParams &P, LogT
             nondiag_component(P, i, __dmul_rn(P.GM[i], rel), xr, yr, zr, cx, cy, cz, nullptr);
         } else {
             double Fx, Fy, Fz;
-            force_generic_range(P, ltab, i, i + 1, xr, yr, zr, Fx, Fy, Fz);
+            diag_component(P, ltab, i, xr, yr, zr, Fx, Fy, Fz);
             cx = __dmul_rn(__dmul_rn(Fx, rel), xr);
             cy = __dmul_rn(__dmul_rn(Fy, rel), yr);
             cz = __dmul_rn(__dmul_rn(Fz, rel), zr);
