@@ -26,7 +26,7 @@ ORBIT_STATUS = {0: "ok", -1: "inconsistent input", -2: "larger nmax is needed",
 
 EXPORTS = ["cw_create", "cw_destroy", "cw_device_count", "cw_set_potential", "cw_set_potential_ex", "cw_set_potential_general",
            "cw_set_potential_time", "cw_count_nodes",
-           "cw_integrate", "cw_gradient", "cw_potential_value", "cw_circular_velocity", "cw_strerror",
+           "cw_integrate", "cw_gradient", "cw_potential_value", "cw_circular_velocity", "cw_pointwise_t", "cw_strerror",
            "cw_last_error", "cw_abi_version", "cw_last_launch_count", "cw_last_kernel_ms",
            "cw_last_total_kernel_ms", "cw_measure_fp64_peak", "cw_measure_scatter_write", "cw_selftest_math"]
 
@@ -91,6 +91,8 @@ def load():
         f = getattr(L, name)
         f.argtypes = [vp, C.c_int, C.c_int64, vp, vp]
         f.restype = C.c_int
+    L.cw_pointwise_t.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp]
+    L.cw_pointwise_t.restype = C.c_int
     L.cw_strerror.argtypes = [C.c_int]
     L.cw_strerror.restype = C.c_char_p
     L.cw_last_error.argtypes = [vp]
@@ -291,14 +293,26 @@ class Context:
         self._check(fn(self._h, MEM_HOST, n, ptr(q), ptr(out)), fn.__name__)
         return out
 
-    def gradient(self, q):
-        return self._pointwise(self._L.cw_gradient, q, 3)
+    def _pointwise_t(self, what, q, t, n_out_rows):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        if q.ndim == 1:
+            q = q.reshape(3, 1)
+        n = q.shape[1]
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(t, dtype=np.float64), (n,)))
+        out = np.empty((n_out_rows, n)) if n_out_rows > 1 else np.empty(n)
+        self._check(self._L.cw_pointwise_t(self._h, what, MEM_HOST, n, ptr(q), ptr(t), ptr(out)), "cw_pointwise_t")
+        return out
 
-    def potential_value(self, q):
-        return self._pointwise(self._L.cw_potential_value, q, 1)
+    def gradient(self, q, t=None):
+        """grad Phi at q (3, n) [kpc]; t [Myr], scalar or per point, matters for time-dependent potentials only."""
+        return self._pointwise(self._L.cw_gradient, q, 3) if t is None else self._pointwise_t(0, q, t, 3)
 
-    def circular_velocity(self, q):
-        return self._pointwise(self._L.cw_circular_velocity, q, 1)
+    def potential_value(self, q, t=None):
+        return self._pointwise(self._L.cw_potential_value, q, 1) if t is None else self._pointwise_t(1, q, t, 1)
+
+    def circular_velocity(self, q, t=None):
+        """sqrt(r |dPhi/dr|) [kpc/Myr] -- `potential.circular_velocity(q, t=...)` of pop.py:1001-1004."""
+        return self._pointwise(self._L.cw_circular_velocity, q, 1) if t is None else self._pointwise_t(2, q, t, 1)
 
     # -- diagnostics ----------------------------------------------------------------------------
     @property

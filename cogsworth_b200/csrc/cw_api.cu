@@ -925,7 +925,7 @@ extern "C" double cw_last_total_kernel_ms(const cw_ctx *ctx, int dev)
 // ---------------------------------------------------------------------------------------------
 // pointwise potential entry points
 
-static int pointwise(cw_ctx *ctx, int mode, int mem_space, int64_t n, const double *q, double *out)
+static int pointwise(cw_ctx *ctx, int mode, int mem_space, int64_t n, const double *q, double *out, const double *tt = nullptr)
 {
     if (!ctx || !q || !out || n < 0) return fail(ctx, CW_E_INVALID, "bad arguments");
     if (!ctx->has_pot) return fail(ctx, CW_E_NO_POTENTIAL, "cw_set_potential has not been called");
@@ -939,12 +939,14 @@ static int pointwise(cw_ctx *ctx, int mode, int mem_space, int64_t n, const doub
     const int64_t n_out = (mode == 0) ? 3 * n : n;
     ctx->last_launches = 1;
     if (mem_space == CW_MEM_DEVICE) {
-        CW_CK(ctx, launch_pointwise(ctx->pot, mode, n, q, out, cfg));
+        CW_CK(ctx, launch_pointwise(ctx->pot, mode, n, q, tt, out, cfg));
     } else {
-        CW_CK(ctx, s.arena.reserve(Arena::padded(3 * n, 8) + Arena::padded(n_out, 8) + 4096));
+        CW_CK(ctx, s.arena.reserve(Arena::padded(3 * n, 8) + Arena::padded(n_out, 8) + Arena::padded(n, 8) + 4096));
         double *dq = s.arena.take<double>(3 * n), *dout = s.arena.take<double>(n_out);
+        double *dt = tt ? s.arena.take<double>(n) : nullptr;
         CW_CK(ctx, cudaMemcpyAsync(dq, q, 3 * n * 8, cudaMemcpyHostToDevice, s.stream));
-        CW_CK(ctx, launch_pointwise(ctx->pot, mode, n, dq, dout, cfg));
+        if (tt) CW_CK(ctx, cudaMemcpyAsync(dt, tt, n * 8, cudaMemcpyHostToDevice, s.stream));
+        CW_CK(ctx, launch_pointwise(ctx->pot, mode, n, dq, dt, dout, cfg));
         CW_CK(ctx, cudaMemcpyAsync(out, dout, n_out * 8, cudaMemcpyDeviceToHost, s.stream));
     }
     CW_CK(ctx, cudaStreamSynchronize(s.stream));
@@ -963,6 +965,12 @@ extern "C" int cw_potential_value(cw_ctx *ctx, int mem_space, int64_t n, const d
 extern "C" int cw_circular_velocity(cw_ctx *ctx, int mem_space, int64_t n, const double *q, double *vcirc)
 {
     return pointwise(ctx, 2, mem_space, n, q, vcirc);
+}
+
+extern "C" int cw_pointwise_t(cw_ctx *ctx, int what, int mem_space, int64_t n, const double *q, const double *t_myr, double *out)
+{
+    if (what < 0 || what > 2) return fail(ctx, CW_E_INVALID, "cw_pointwise_t: what must be CW_GRADIENT, CW_VALUE or CW_VCIRC");
+    return pointwise(ctx, what, mem_space, n, q, out, t_myr);
 }
 
 // ---------------------------------------------------------------------------------------------

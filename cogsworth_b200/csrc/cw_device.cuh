@@ -770,15 +770,15 @@ __device__ __forceinline__ double seg_dt_myr(double t0, double t1, double to_myr
 }
 
 // Phi of the same components (gala *_value functions) -- for the N3 rows, not the hot loop.
-__device__ __forceinline__ double potential_value(const PotParams &P, double x0, double y0, double z0)
+__device__ __forceinline__ double potential_value(const PotParams &P, double x0, double y0, double z0, double t_eval)
 {
     double vtot = 0.0;
     for (int i = 0; i < P.n_comp; i++) {
         const int t = P.type[i];
         double x = x0, y = y0, z = z0, rel = 1.0;
-        if (P.kind == POT_MW_V2_T || P.kind == POT_GENERIC_T) rel = amplitude_rel(P, 0, P.t_eval);
+        if (P.kind == POT_MW_V2_T || P.kind == POT_GENERIC_T) rel = amplitude_rel(P, 0, t_eval);
         if (P.kind == POT_GENERAL) {
-            rel = amplitude_rel(P, i, P.t_eval);
+            rel = amplitude_rel(P, i, t_eval);
             if (P.has_R[i]) {
                 x = fma(P.R[i][2], z0, fma(P.R[i][1], y0, P.R[i][0] * x0));
                 y = fma(P.R[i][5], z0, fma(P.R[i][4], y0, P.R[i][3] * x0));

@@ -10,19 +10,20 @@ namespace cw {
 template <int KIND>
 __global__ void __launch_bounds__(256) pointwise_kernel(const __grid_constant__ PotParams P, int mode,
                                                         int64_t n, const double *__restrict__ q,
-                                                        double *__restrict__ out)
+                                                        const double *__restrict__ tt, double *__restrict__ out)
 {
     __shared__ double2 ltab_mem[LOG_TABLE_N];
     const LogTab ltab = log_table_init(ltab_mem);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double x = q[i], y = q[n + i], z = q[2 * n + i];
+        const double t = tt ? tt[i] : P.t_eval;      // per-point times [Myr] (time-dependent potentials)
         if (mode == 1) {
-            out[i] = potential_value(P, x, y, z);
+            out[i] = potential_value(P, x, y, z, t);
             continue;
         }
         double gx, gy, gz;
-        gradient<KIND>(P, ltab, P.t_eval, x, y, z, gx, gy, gz);
+        gradient<KIND>(P, ltab, t, x, y, z, gx, gy, gz);
         if (mode == 0) {
             out[i] = gx; out[n + i] = gy; out[2 * n + i] = gz;
         } else {
@@ -34,7 +35,7 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const __grid_constant__ 
     }
 }
 
-cudaError_t launch_pointwise(const PotParams &P, int mode, int64_t n, const double *q, double *out,
+cudaError_t launch_pointwise(const PotParams &P, int mode, int64_t n, const double *q, const double *tt, double *out,
                              const LaunchCfg &cfg)
 {
     if (n <= 0) return cudaSuccess;
@@ -43,12 +44,12 @@ cudaError_t launch_pointwise(const PotParams &P, int mode, int64_t n, const doub
     const int64_t cap = (int64_t)cfg.sm_count * 8;
     if (grid > cap) grid = cap;
     switch (P.kind) {
-    case POT_MW_V1: pointwise_kernel<POT_MW_V1><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, out); break;
-    case POT_MW_V2: pointwise_kernel<POT_MW_V2><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, out); break;
-    case POT_GENERAL: pointwise_kernel<POT_GENERAL><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, out); break;
-    case POT_MW_V2_T: pointwise_kernel<POT_MW_V2_T><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, out); break;
-    case POT_GENERIC_T: pointwise_kernel<POT_GENERIC_T><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, out); break;
-    default: pointwise_kernel<POT_GENERIC><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, out); break;
+    case POT_MW_V1: pointwise_kernel<POT_MW_V1><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, tt, out); break;
+    case POT_MW_V2: pointwise_kernel<POT_MW_V2><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, tt, out); break;
+    case POT_GENERAL: pointwise_kernel<POT_GENERAL><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, tt, out); break;
+    case POT_MW_V2_T: pointwise_kernel<POT_MW_V2_T><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, tt, out); break;
+    case POT_GENERIC_T: pointwise_kernel<POT_GENERIC_T><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, tt, out); break;
+    default: pointwise_kernel<POT_GENERIC><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, tt, out); break;
     }
     return cudaGetLastError();
 }

@@ -58,7 +58,7 @@ cudaError_t launch_dop853_pilot(const PotParams &P, const IntegArgs &A, const La
 // Orbit.t of stored trajectories (only when traj_t was requested)
 cudaError_t launch_traj_times(const IntegArgs &A, const LaunchCfg &cfg);
 // pointwise potential kernels (N3 rows); mode 0 gradient (3 x n), 1 value (n), 2 v_circ (n)
-cudaError_t launch_pointwise(const PotParams &P, int mode, int64_t n, const double *q, double *out,
+cudaError_t launch_pointwise(const PotParams &P, int mode, int64_t n, const double *q, const double *tt, double *out,
                              const LaunchCfg &cfg);
 // diagnostics
 cudaError_t launch_dfma_peak(double *sink, int iters, const LaunchCfg &cfg, int *blocks, int *threads);

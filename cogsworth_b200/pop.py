@@ -68,6 +68,7 @@ class GalacticStageB200:
         self._final_pos = None
         self._final_vel = None
         self._observables = None
+        self._escaped = None
 
         ig = self.initial_galaxy
         pos = np.stack([_val(ig.x, "kpc"), _val(ig.y, "kpc"), _val(ig.z, "kpc")])
@@ -168,6 +169,36 @@ class GalacticStageB200:
         inds = np.arange(n)
         inds[self.disrupted] = np.arange(n, n + self.disrupted.sum())
         return self.orbits[inds]
+
+    # -- the steps either side of the path: same potential tables, pointwise kernels --------------
+    def initial_circular_velocity(self):
+        """v_circ [km/s] at every system's birth place AND birth time -- the call
+        ``galactic_potential.circular_velocity(q=[x, y, z], t=max_ev_time - tau)`` that draws the birth velocities
+        (pop.py:1001-1004); the time matters for gp.TimeInterpolatedPotential."""
+        from .kicks import _context
+        ig = self.initial_galaxy
+        q = np.stack([_val(ig.x, "kpc"), _val(ig.y, "kpc"), _val(ig.z, "kpc")])
+        t_birth = (float(_val(self.max_ev_time, "Gyr")) - _val(ig.tau, "Gyr")) * 1000.0            # Myr
+        ctx = _context(self.galactic_potential, getattr(self, "_cw_context", None))
+        return ctx.circular_velocity(q, t=t_birth) * K.KMS_PER_KPC_MYR
+
+    @property
+    def escaped(self):
+        """Mask: final speed >= escape speed sqrt(-2 Phi) at the final position (pop.py:874-895), one entry per row of
+        ``final_pos``.  As in the reference the potential is evaluated with gala's default time argument (t = 0)."""
+        if getattr(self, "_escaped", None) is None:
+            from .kicks import _context
+            fp = np.asarray(_val(self.final_pos, "kpc"), dtype=np.float64)
+            fv = np.asarray(_val(self.final_vel, "km/s"), dtype=np.float64)
+            ok = np.isfinite(fp).all(axis=1)
+            ctx = _context(self.galactic_potential, getattr(self, "_cw_context", None))
+            phi = np.full(len(fp), np.nan)
+            if ok.any():
+                phi[ok] = ctx.potential_value(np.ascontiguousarray(fp[ok].T), t=0.0)
+            with np.errstate(invalid="ignore"):
+                v_esc = np.sqrt(-2.0 * phi) * K.KMS_PER_KPC_MYR
+                self._escaped = np.sqrt((fv ** 2).sum(axis=1)) >= v_esc
+        return self._escaped
 
     @property
     def final_pos(self):

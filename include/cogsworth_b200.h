@@ -207,6 +207,11 @@ int cw_integrate(cw_ctx *ctx, const cw_opts *opts, const cw_batch *batch, const 
 int cw_gradient(cw_ctx *ctx, int mem_space, int64_t n, const double *q, double *grad /* 3 x n */);
 int cw_potential_value(cw_ctx *ctx, int mem_space, int64_t n, const double *q, double *phi /* n */);
 int cw_circular_velocity(cw_ctx *ctx, int mem_space, int64_t n, const double *q, double *vcirc /* n, kpc/Myr */);
+/* The same three with a time per point [Myr] (t_myr = NULL: the time of cw_set_potential_time): what a
+ * time-dependent potential needs for `galactic_potential.circular_velocity(q, t = max_ev_time - tau)` at every
+ * system's own birth time (pop.py:1001-1004).  what: CW_GRADIENT (out 3 x n), CW_VALUE (n), CW_VCIRC (n). */
+enum { CW_GRADIENT = 0, CW_VALUE = 1, CW_VCIRC = 2 };
+int cw_pointwise_t(cw_ctx *ctx, int what, int mem_space, int64_t n, const double *q, const double *t_myr, double *out);
 
 /* Diagnostics */
 const char *cw_strerror(int code);

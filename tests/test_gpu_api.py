@@ -340,3 +340,32 @@ def test_trajectory_slot_too_small_is_reported_not_overrun(ctx):
         m = good["n_nodes"][i]
         assert np.array_equal(tp[:, off[i]:off[i] + m], good["traj_pos"][:, goff[i]:goff[i] + m])
     assert np.array_equal(wf[:, 5], good["w_final"][:, 5]) and np.array_equal(nn, good["n_nodes"])
+
+
+def test_steps_either_side_of_the_path(ctx, oracle):
+    """birth-time circular velocities (pop.py:1001-1004) and the `escaped` mask (pop.py:874-895)
+    from the pointwise kernels, in a static and in an evolving potential."""
+    from test_host import fake_population
+    from cogsworth_b200 import potential as P
+    p = fake_population()
+    p._cw_context = ctx
+    ig = p.initial_galaxy
+    q = np.stack([ig.x, ig.y, ig.z]).astype(float)
+    for pot in (MilkyWayPotential("v2"), P.evolving_milky_way(np.linspace(0, 12000, 5), np.linspace(0.1, 1.0, 5))):
+        p.galactic_potential = pot
+        vc = p.initial_circular_velocity()
+        t_birth = (float(p.max_ev_time) - np.asarray(ig.tau, dtype=float)) * 1000.0
+        for i in range(len(p)):
+            import dataclasses
+            want = oracle.circular_velocity(dataclasses.replace(pot, t_eval=float(t_birth[i])), q[:, i].copy())
+            assert abs(vc[i] - want * K.KMS_PER_KPC_MYR) < 1e-12 * vc[i]
+    # the evolving galaxy is lighter at birth: smaller circular velocities than today's
+    p.galactic_potential = MilkyWayPotential("v2")
+    np.random.seed(3)
+    p.perform_galactic_evolution(progress_bar=False)
+    esc = p.escaped
+    assert esc.shape == (len(p.final_pos),) and esc.dtype == bool
+    fp, fv = np.asarray(p.final_pos, dtype=float), np.asarray(p.final_vel, dtype=float)
+    for i in range(len(fp)):
+        v_esc = np.sqrt(-2.0 * oracle.value(p.galactic_potential, fp[i].copy())) * K.KMS_PER_KPC_MYR
+        assert esc[i] == (np.linalg.norm(fv[i]) >= v_esc)
