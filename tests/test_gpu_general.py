@@ -180,3 +180,20 @@ def test_tutorial_evolving_nfw_through_the_reference_signature(ctx, oracle):
         assert np.abs(orb.pos.xyz[:, -1] - sol.y[:3, -1]).max() < 1e-5      # 12 000 restarted intervals at the default 1e-10
         ends[name] = orb.pos.xyz[:, -1]
     assert np.linalg.norm(ends["static"] - ends["evolving"]) > 1.0       # "the orbits trace very different paths"
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_cuda_path_reproduces_the_frozen_general_cases(ctx, k):
+    """The committed fixtures of tests/golden/oracle_cases.npz (tools/gen_golden_oracle.py) for LM10, BovyMWPotential2014
+    and the per-component evolving Milky Way: kick nodes bit-exact, final states within the north_star tolerances."""
+    import os
+    from _cases import general_cases
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_cases.npz"))
+    name, pot, integ, horizon = general_cases()[k]
+    b = make_population(48, cfg_id=1, potential=P.MilkyWayPotential("v2"), horizon_gyr=horizon).batch
+    ctx.set_potential(pot)
+    r = ctx.integrate(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv, integrator=integ)
+    assert (r["status"] == 0).all()
+    assert np.array_equal(r["ev_step"], G[name + "_ev_step"]) and np.array_equal(r["n_nodes"], G[name + "_n_nodes"])
+    d = rel_diff(r["w_final"], G[name + "_w_final"])
+    assert np.quantile(d, 0.9) < (1e-10 if integ == _lib.LEAPFROG else 1e-7), (name, np.quantile(d, [0.5, 0.9, 1]))

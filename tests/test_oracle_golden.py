@@ -23,3 +23,16 @@ def test_oracle_reproduces_golden(oracle, name, ver, integ):
     assert np.array_equal(r["ev_step"], G[name + "_ev_step"])
     assert np.array_equal(r["n_nodes"], G[name + "_n_nodes"])
     assert np.array_equal(r["w_final"], G[name + "_w_final"])
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_oracle_reproduces_golden_general_potentials(oracle, k):
+    """LM10 (rotated halo), BovyMWPotential2014 (incomplete gamma function) and a per-component evolving Milky Way."""
+    from _cases import general_cases
+    name, pot, integ, horizon = general_cases()[k]
+    b = make_population(48, cfg_id=1, potential=MilkyWayPotential("v2"), horizon_gyr=horizon).batch
+    r = oracle.integrate_batch(pot, b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv,
+                               integrator=integ)
+    assert np.array_equal(r["ev_step"], G[name + "_ev_step"])
+    assert np.array_equal(r["n_nodes"], G[name + "_n_nodes"])
+    assert np.array_equal(r["w_final"], G[name + "_w_final"])

@@ -32,5 +32,19 @@ for name, ver, integ in (("cfg1_leapfrog_v1", "v1", O.LEAPFROG), ("cfg1_dop853_v
     out[name + "_ev_step"] = r["ev_step"]
     out[name + "_n_nodes"] = r["n_nodes"]
     out[name + "_ev_time"] = b.ev_time
+# the general potentials (rotation, per-component time interpolation): birth velocities drawn in the
+# static Milky Way, orbits integrated in the named potential
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from _cases import general_cases  # noqa: E402
+
+for name, pot, integ, horizon in general_cases():
+    pop = make_population(48, cfg_id=1, potential=MilkyWayPotential("v2"), horizon_gyr=horizon)
+    b = pop.batch
+    r = O.integrate_batch(pot, b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv,
+                          integrator=integ, n_threads=1)
+    assert (r["status"] == 0).all()
+    out[name + "_w_final"] = r["w_final"]
+    out[name + "_ev_step"] = r["ev_step"]
+    out[name + "_n_nodes"] = r["n_nodes"]
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "oracle_cases.npz"), **out)
 print({k: v.shape for k, v in out.items()})
