@@ -369,3 +369,24 @@ def test_steps_either_side_of_the_path(ctx, oracle):
     for i in range(len(fp)):
         v_esc = np.sqrt(-2.0 * oracle.value(p.galactic_potential, fp[i].copy())) * K.KMS_PER_KPC_MYR
         assert esc[i] == (np.linalg.norm(fv[i]) >= v_esc)
+
+
+def test_population_in_an_evolving_potential(ctx):
+    """evolving_potentials.ipynb cells 11 and 16: `Population(..., galactic_potential=evolving)` and swapping the
+    potential of an evolved population, then `perform_galactic_evolution()` again."""
+    from test_host import fake_population
+    from cogsworth_b200 import potential as P
+    p = fake_population()
+    p._cw_context = ctx
+    np.random.seed(5)
+    p.perform_galactic_evolution(progress_bar=False)
+    static = np.array(p.final_pos, dtype=float).copy()
+    p.galactic_potential = P.evolving_milky_way(np.linspace(0, 12000, 5), np.linspace(0.1, 1.0, 5))
+    p.perform_galactic_evolution(progress_bar=False)             # same binaries, same kicks (angles persisted)
+    evolving = np.array(p.final_pos, dtype=float)
+    assert evolving.shape == static.shape and np.isfinite(evolving).all()
+    assert np.linalg.norm(evolving - static, axis=1).min() > 0.1     # a lighter young galaxy: different orbits
+    p.integrator = None                                              # the reference's default, DOPRI853
+    p.perform_galactic_evolution(progress_bar=False)
+    dop = np.array(p.final_pos, dtype=float)
+    assert np.isfinite(dop).all() and np.abs(dop - evolving).max() < 0.5   # leapfrog vs DOPRI853 of the same orbits
