@@ -736,6 +736,42 @@ __device__ __forceinline__ void gradient(const PotParams &P, LogTab ltab, double
     }
 }
 
+// The cubic of the knot interval a lane's clock is in, kept in registers by the leapfrog kernels of the separable
+// kinds: an orbit crosses a knot once per Gyr or so, so the table look-up leaves the step.  Before the first and after
+// the last knot the end values are held (constant segments reaching to -inf / +inf).
+struct AmpSeg { double lo, hi, t0, c0, c1, c2, c3; };      // valid for lo <= t < hi
+
+__device__ __forceinline__ void amp_seg_reset(AmpSeg &a) { a.lo = 1.0; a.hi = 0.0; a.t0 = a.c0 = a.c1 = a.c2 = a.c3 = 0.0; }
+
+__device__ __forceinline__ void amp_seg_load(const PotParams &P, double t, AmpSeg &a)
+{
+    const int i0 = P.k_off[0], i1 = P.k_off[1];            // f(t) lives in the slot of "component 0"
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    a.t0 = 0.0; a.c1 = 0.0; a.c2 = 0.0; a.c3 = 0.0;
+    if (i1 - i0 < 2 || !(t >= P.k_t[i0])) {
+        a.lo = -INF; a.hi = (i1 - i0 < 2) ? INF : P.k_t[i0]; a.c0 = (i1 > i0) ? P.k_c[i0][0] : 1.0;
+        return;
+    }
+    if (t >= P.k_t[i1 - 1]) {
+        a.lo = P.k_t[i1 - 1]; a.hi = INF; a.c0 = P.k_c[i1 - 1][0];
+        return;
+    }
+    int lo = i0, hi = i1 - 2;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (t >= P.k_t[mid]) lo = mid; else hi = mid - 1;
+    }
+    a.lo = P.k_t[lo]; a.hi = P.k_t[lo + 1]; a.t0 = P.k_t[lo];
+    a.c0 = P.k_c[lo][0]; a.c1 = P.k_c[lo][1]; a.c2 = P.k_c[lo][2]; a.c3 = P.k_c[lo][3];
+}
+
+__device__ __forceinline__ double amp_seg_eval(const PotParams &P, AmpSeg &a, double t)
+{
+    if (!(t >= a.lo && t < a.hi)) amp_seg_load(P, t, a);
+    const double s = t - a.t0;
+    return fma(s, fma(s, fma(s, a.c3, a.c2), a.c1), a.c0);
+}
+
 // The leapfrog's form.  Diagonal kinds: the three factors of grad = (Fx x, Fy y, Fz z), folded into the
 // velocity FMAs by lf_kick.  POT_GENERAL: (Fx, Fy, Fz) IS the gradient.
 template <int KIND>
@@ -750,6 +786,20 @@ __device__ __forceinline__ void force3t(const PotParams &P, LogTab ltab, double 
         Fx *= f; Fy *= f; Fz *= f;
     } else {
         force3<KIND>(P, ltab, x, y, z, Fx, Fy, Fz);
+    }
+}
+
+// force3t for the leapfrog kernels, which carry the current knot interval of a separable kind in registers
+template <int KIND>
+__device__ __forceinline__ void force3t_seg(const PotParams &P, LogTab ltab, AmpSeg &seg, double t,
+                                            double x, double y, double z, double &Fx, double &Fy, double &Fz)
+{
+    if (KindTraits<KIND>::TS) {
+        force3<KindTraits<KIND>::BASE>(P, ltab, x, y, z, Fx, Fy, Fz);
+        const double f = amp_seg_eval(P, seg, t);
+        Fx *= f; Fy *= f; Fz *= f;
+    } else {
+        force3t<KIND>(P, ltab, t, x, y, z, Fx, Fy, Fz);
     }
 }
 

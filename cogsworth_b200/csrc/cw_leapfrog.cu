@@ -200,6 +200,7 @@ struct Lane {
     int64_t oid;                    // orbit id within the shard
     int j, next, L;                 // current node, next sync node, last node
     bool append;
+    AmpSeg seg;                     // separable time dependence only: the knot interval the orbit's clock is in
 };
 
 // pull one queue position per calling lane (called from divergent code: aggregate over the
@@ -243,7 +244,7 @@ __device__ __forceinline__ void write_final(const IntegArgs &A, const Lane &s)
 }
 
 template <int KIND, bool STORE>
-__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? 128 : (KIND == POT_GENERAL) ? CW_LF_GEN_REGS : CW_LF_REGS) leapfrog_kernel(const __grid_constant__ PotParams P,
+__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? 128 : (KIND == POT_GENERAL || KindTraits<KIND>::TS) ? CW_LF_GEN_REGS : CW_LF_REGS) leapfrog_kernel(const __grid_constant__ PotParams P,
                                                             const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
     s.vhx = s.vhy = s.vhz = 0.0; s.Fxy = s.Fy = s.Fz = 0.0;
     s.dt = 0.0; s.hgrid = 0.0; s.t2 = 0.0; s.smyr = 1.0; s.tcur = 0.0;
     s.e = s.e1 = 0; s.oid = -1; s.j = 0; s.next = 0; s.L = 0; s.append = false;
+    amp_seg_reset(s.seg);
     bool active = false, exhausted = false, staged = false;
     unsigned long long steps_done = 0;
     // STORE: the warp clock.  W counts the steps this warp has executed; an orbit whose first sample lives
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 staged = true;
             }
             if (s.L == 0) { write_final(A, s); continue; }
-            force3t<KIND>(P, ltab, s.tcur * s.smyr, s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+            force3t_seg<KIND>(P, ltab, s.seg, s.tcur * s.smyr, s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
             const double nhdt = -0.5 * s.dt;
             s.vhx = lf_kick<KIND>(s.Fxy, nhdt, s.x, s.vx);
             s.vhy = lf_kick<KIND>(s.Fy, nhdt, s.y, s.vy);
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 s.x = fma(s.vhx, dt, s.x);
                 s.y = fma(s.vhy, dt, s.y);
                 s.z = fma(s.vhz, dt, s.z);
-                force3t<KIND>(P, ltab, tnode(s.j + q), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+                force3t_seg<KIND>(P, ltab, s.seg, tnode(s.j + q), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
                 if (STORE) {
                     s.vx = fma(s.Fxy, nhdt, s.vhx);
                     s.vy = fma(s.Fy, nhdt, s.vhy);
@@ -458,7 +460,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 s.x = fma(s.vhx, dt, s.x);
                 s.y = fma(s.vhy, dt, s.y);
                 s.z = fma(s.vhz, dt, s.z);
-                force3t<KIND>(P, ltab, tnode(s.j + q), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+                force3t_seg<KIND>(P, ltab, s.seg, tnode(s.j + q), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
                 const double a = s.Fxy * ndt, b = s.Fz * ndt;
                 const double ay = TRI ? s.Fy * ndt : a;
                 s.vhx = fma(a, s.x, s.vhx);
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 s.x = fma(s.vhx, dt, s.x);
                 s.y = fma(s.vhy, dt, s.y);
                 s.z = fma(s.vhz, dt, s.z);
-                force3t<KIND>(P, ltab, tnode(s.j + q), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+                force3t_seg<KIND>(P, ltab, s.seg, tnode(s.j + q), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
                 const double ah = s.Fxy * nhdt, bh = s.Fz * nhdt;
                 const double ahy = TRI ? s.Fy * nhdt : ah;
                 s.vx = fma(ah, s.x, s.vhx);
@@ -493,7 +495,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
             s.x = fma(s.vhx, dt, s.x);
             s.y = fma(s.vhy, dt, s.y);
             s.z = fma(s.vhz, dt, s.z);
-            force3t<KIND>(P, ltab, tnode(s.j + m), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+            force3t_seg<KIND>(P, ltab, s.seg, tnode(s.j + m), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
             s.vx = fma(s.Fxy, nhdt, s.vhx);
             s.vy = fma(s.Fy, nhdt, s.vhy);
             s.vz = fma(s.Fz, nhdt, s.vhz);
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
             s.x = fma(s.vhx, dt, s.x);
             s.y = fma(s.vhy, dt, s.y);
             s.z = fma(s.vhz, dt, s.z);
-            force3t<KIND>(P, ltab, tnode(s.j + m), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+            force3t_seg<KIND>(P, ltab, s.seg, tnode(s.j + m), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
             const double ah = s.Fxy * nhdt, bh = s.Fz * nhdt;
             const double ahy = TRI ? s.Fy * nhdt : ah;
             s.vx = fma(ah, s.x, s.vhx);
