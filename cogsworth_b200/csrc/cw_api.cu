@@ -472,6 +472,11 @@ static int set_potential_impl(cw_ctx *ctx, double G, int n_comp, const int32_t *
             P.nfw_inv_rs = 1.0 / P.nfw_rs;
         }
     }
+    if (P.kind == POT_GENERAL)
+        for (int i = n_comp - 1; i >= 0; i--) {
+            const bool plain = !P.has_R[i] && P.k_off[i + 1] == P.k_off[i] && types[i] < CW_COMP_LONG_MURALI_BAR;
+            P.run_end[i] = !plain ? 0 : (i + 1 < n_comp && P.run_end[i + 1] > i + 1) ? P.run_end[i + 1] : i + 1;
+        }
     if (separable) P.kind = (P.kind == POT_MW_V2) ? POT_MW_V2_T : POT_GENERIC_T;
     pot_fill_constants(P);
     ctx->pot = P;

@@ -177,6 +177,8 @@ struct PotParams {
     double k_t[CW_MAX_KNOTS];              // knot times [Myr]
     double k_c[CW_MAX_KNOTS][4];           // amplitude relative to GM[i] on [k_t[j], k_t[j+1]]:
                                            // c0 + s (c1 + s (c2 + s c3)), s = t - k_t[j]
+    int32_t run_end[CW_MAX_COMPONENTS];    // > i: components [i, run_end[i]) are static, unrotated and diagonal: one
+                                           // force_generic_range call that shares the radius between them
     double k_t0[CW_MAX_COMPONENTS];        // equally spaced knots (np.linspace): first knot and 1 / spacing, else 0
     double k_inv_dt[CW_MAX_COMPONENTS];
     double t_eval;                         // time of the pointwise kernels
@@ -663,6 +665,14 @@ static __device__ __forceinline__ void gradient_general(const PotParams &P, LogT
 {
     double ax = 0.0, ay = 0.0, az = 0.0;
     for (int i = 0; i < P.n_comp; i++) {
+        const int e = P.run_end[i];
+        if (e > i) {       // a run of plain components (LM10's disk and bulge beside its rotated halo)
+            double Fx, Fy, Fz;
+            force_generic_range(P, ltab, i, e, x, y, z, Fx, Fy, Fz);
+            ax = __dadd_rn(ax, __dmul_rn(Fx, x)); ay = __dadd_rn(ay, __dmul_rn(Fy, y)); az = __dadd_rn(az, __dmul_rn(Fz, z));
+            i = e - 1;
+            continue;
+        }
         const double rel = amplitude_rel(P, i, t);
         double xr = x, yr = y, zr = z;
         if (P.has_R[i]) {
