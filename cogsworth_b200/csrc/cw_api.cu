@@ -517,11 +517,19 @@ static int64_t traj_shard_cols()
     const long long v = e ? atoll(e) : 0;
     return v > 0 ? (int64_t)v : TRAJ_SHARD_COLS;
 }
-static int64_t host_chunk(int64_t n_on_device)
+// Q > 0: the number of orbits one full grid of the kernel holds (persistent lanes).  Chunks are whole multiples of it,
+// so no chunk ends with a wave that fills a fraction of the GPU (10^6 orbits in LM10 at Q = 113 664: 127k-orbit
+// chunks = 1.12 waves each cost a third of the end-to-end throughput).
+static int64_t host_chunk(int64_t n_on_device, int64_t Q)
 {
     int64_t c = (n_on_device + 7) / 8;
-    c = (c + 4095) & ~int64_t(4095);
-    return std::min(HOST_CHUNK_MAX, std::max(HOST_CHUNK_MIN, c));
+    if (Q <= 0 || getenv("CW_NO_WAVE_CHUNKS")) {
+        c = (c + 4095) & ~int64_t(4095);
+        return std::min(HOST_CHUNK_MAX, std::max(HOST_CHUNK_MIN, c));
+    }
+    c = ((c + Q - 1) / Q) * Q;
+    const int64_t cmax = std::max<int64_t>(Q, (HOST_CHUNK_MAX / Q) * Q);
+    return std::min(cmax, std::max(Q, c));
 }
 
 struct Plan {
@@ -741,7 +749,18 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
         // against 150 ms of kernel): cutting them into chunks would multiply the pilot launches and the tails
         // (measured 3.5e9 vs 6.2e9 intervals/s end to end), so they go to the device in one piece.
         const bool pipelined = !dev_mode && (!integrate || o->integrator == CW_LEAPFROG);
-        const int64_t chunk = pipelined ? host_chunk(b - a) : (b - a);
+        int64_t Q = 0;
+        if (pipelined && integrate && !store_all) {
+            int prev_dev = 0;
+            cudaGetDevice(&prev_dev);
+            cudaSetDevice(ctx->slots[d].dev);
+            Q = leapfrog_lane_capacity(ctx->pot, ctx->slots[d].sm_count);
+            cudaSetDevice(prev_dev);
+            // only batches of several waves: a batch of one or two (10^5 binaries with their own horizons, config 2)
+            // pipelines better in the finer old chunks -- measured 1.34e11 against 0.90e11 steps/s end to end
+            if (getenv("CW_NO_WAVE_CHUNKS") || b - a < 4 * Q) Q = 0;
+        }
+        const int64_t chunk = pipelined ? host_chunk(b - a, Q) : (b - a);
         // The first H2D copy and the last D2H copy have nothing to hide behind: ramp the chunk size up from
         // chunk/8 at the start and back down at the end (the kernels in between keep the full size).
         std::vector<int64_t> sizes;
@@ -750,8 +769,13 @@ static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
         } else {
             std::vector<int64_t> head, tail;
             int64_t used = 0;
-            for (int64_t sz = std::max<int64_t>(chunk / 8, HOST_CHUNK_MIN / 2); sz < chunk; sz *= 2) { head.push_back(sz); used += sz; }
-            for (int64_t sz = std::max<int64_t>(chunk / 4, HOST_CHUNK_MIN / 2); sz < chunk; sz *= 2) { tail.push_back(sz); used += sz; }
+            if (Q > 0) {     // whole waves here too: Q, 2Q, 4Q, ...
+                for (int64_t sz = Q; sz < chunk; sz *= 2) { head.push_back(sz); used += sz; }
+                for (int64_t sz = Q; sz < chunk; sz *= 2) { tail.push_back(sz); used += sz; }
+            } else {
+                for (int64_t sz = std::max<int64_t>(chunk / 8, HOST_CHUNK_MIN / 2); sz < chunk; sz *= 2) { head.push_back(sz); used += sz; }
+                for (int64_t sz = std::max<int64_t>(chunk / 4, HOST_CHUNK_MIN / 2); sz < chunk; sz *= 2) { tail.push_back(sz); used += sz; }
+            }
             int64_t mid = (b - a) - used;
             sizes = head;
             while (mid > 0) { const int64_t sz = std::min(chunk, mid); sizes.push_back(sz); mid -= sz; }

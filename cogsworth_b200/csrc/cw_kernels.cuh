@@ -50,6 +50,9 @@ struct LaunchCfg {
 cudaError_t launch_grid_prepass(const IntegArgs &A, int32_t *iota_out, int32_t *sort_key_out, const LaunchCfg &cfg);
 // fixed-step leapfrog (gala leapfrog_integrate_hamiltonian semantics)
 cudaError_t launch_leapfrog(const PotParams &P, const IntegArgs &A, bool store_all, const LaunchCfg &cfg);
+// orbits one full grid of the final-state leapfrog kernel of this potential kind holds at a time (SMs x resident CTAs x
+// threads) on the CURRENT device; 0 on error.  Host-buffer calls cut their chunks in multiples of it.
+int64_t leapfrog_lane_capacity(const PotParams &P, int sm_count);
 // adaptive DOP853: restarted per grid interval (gala dop853_integrate_hamiltonian semantics), or
 // dense = one call per segment with Hairer's continuous extension at the grid nodes
 cudaError_t launch_dop853(const PotParams &P, const IntegArgs &A, bool store_all, bool dense, const LaunchCfg &cfg);

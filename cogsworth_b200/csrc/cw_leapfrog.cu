@@ -565,6 +565,29 @@ static cudaError_t launch_lf(const PotParams &P, const IntegArgs &A, const Launc
     return cudaGetLastError();
 }
 
+template <int KIND>
+static int64_t lf_capacity(int sm_count)
+{
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, leapfrog_kernel<KIND, false>, LF_BLOCK, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return (int64_t)sm_count * per_sm * LF_BLOCK;
+}
+
+int64_t leapfrog_lane_capacity(const PotParams &P, int sm_count)
+{
+    switch (P.kind) {
+    case POT_MW_V1: return lf_capacity<POT_MW_V1>(sm_count);
+    case POT_MW_V2: return lf_capacity<POT_MW_V2>(sm_count);
+    case POT_GENERAL: return lf_capacity<POT_GENERAL>(sm_count);
+    case POT_MW_V2_T: return lf_capacity<POT_MW_V2_T>(sm_count);
+    case POT_GENERIC_T: return lf_capacity<POT_GENERIC_T>(sm_count);
+    default: return lf_capacity<POT_GENERIC>(sm_count);
+    }
+}
+
 cudaError_t launch_leapfrog(const PotParams &P, const IntegArgs &A, bool store_all, const LaunchCfg &cfg)
 {
     if (A.n <= 0) return cudaSuccess;
