@@ -25,7 +25,7 @@ ORBIT_STATUS = {0: "ok", -1: "inconsistent input", -2: "larger nmax is needed",
                 -5: "non-finite error norm", -6: "trajectory slot too small"}
 
 EXPORTS = ["cw_create", "cw_destroy", "cw_device_count", "cw_set_potential", "cw_set_potential_ex", "cw_set_potential_general",
-           "cw_set_potential_time", "cw_count_nodes",
+           "cw_set_potential_time", "cw_count_nodes", "cw_host_alloc", "cw_host_free", "cw_host_is_pinned",
            "cw_integrate", "cw_gradient", "cw_potential_value", "cw_circular_velocity", "cw_pointwise_t", "cw_strerror",
            "cw_last_error", "cw_abi_version", "cw_last_launch_count", "cw_last_kernel_ms",
            "cw_last_total_kernel_ms", "cw_measure_fp64_peak", "cw_measure_scatter_write", "cw_selftest_math"]
@@ -40,7 +40,16 @@ class CwOpts(C.Structure):
 class CwBatch(C.Structure):
     _fields_ = [("n_orbits", C.c_int64), ("w0", C.c_void_p), ("t1", C.c_void_p), ("t2", C.c_void_p),
                 ("dt", C.c_void_p), ("to_myr", C.c_void_p), ("grid_flags", C.c_void_p),
-                ("ev_off", C.c_void_p), ("ev_time", C.c_void_p), ("ev_dv", C.c_void_p)]
+                ("ev_off", C.c_void_p), ("ev_time", C.c_void_p), ("ev_dv", C.c_void_p),
+                # ABI 2: compact host forms (include/cogsworth_b200.h)
+                ("n_w0", C.c_int64), ("w0_index", C.c_void_p), ("grid_class", C.c_void_p),
+                ("classes", C.c_void_p), ("n_classes", C.c_int32), ("reserved", C.c_int32),
+                ("ev_off32", C.c_void_p)]
+
+
+#: numpy mirror of ``cw_grid_class``
+GRID_CLASS_DTYPE = np.dtype([("t2", "<f8"), ("dt", "<f8"), ("to_myr", "<f8"), ("grid_flags", "<i4"),
+                             ("reserved", "<i4")])
 
 
 class CwResult(C.Structure):
@@ -93,6 +102,12 @@ def load():
         f.restype = C.c_int
     L.cw_pointwise_t.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp]
     L.cw_pointwise_t.restype = C.c_int
+    L.cw_host_alloc.argtypes = [C.c_size_t]
+    L.cw_host_alloc.restype = vp
+    L.cw_host_free.argtypes = [vp]
+    L.cw_host_free.restype = None
+    L.cw_host_is_pinned.argtypes = [vp]
+    L.cw_host_is_pinned.restype = C.c_int
     L.cw_strerror.argtypes = [C.c_int]
     L.cw_strerror.restype = C.c_char_p
     L.cw_last_error.argtypes = [vp]
@@ -112,6 +127,55 @@ def load():
     L.cw_selftest_math.restype = C.c_int
     _LIB = L
     return L
+
+
+class _PinnedBlock:
+    """A page-locked block from the library's cache; returns to the cache when the last array viewing it dies."""
+
+    def __init__(self, nbytes):
+        self._L = load()
+        self.nbytes = int(nbytes)
+        self.addr = self._L.cw_host_alloc(max(self.nbytes, 1))
+        if not self.addr:
+            raise MemoryError("cw_host_alloc failed")
+        self.__array_interface__ = {"shape": (max(self.nbytes, 1),), "typestr": "|u1", "data": (self.addr, False),
+                                    "version": 3}
+
+    def __del__(self):
+        try:
+            if getattr(self, "addr", None):
+                self._L.cw_host_free(self.addr)
+                self.addr = None
+        except Exception:
+            pass
+
+
+#: arrays larger than this are not taken from page-locked memory (host RAM that cannot be swapped is a shared resource)
+PINNED_LIMIT_BYTES = int(os.environ.get("CW_PINNED_LIMIT_MB", "16384")) << 20
+_PINNED_OK = None
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """``np.empty`` in page-locked host memory (DMA-ed by ``cw_integrate`` without staging); plain ``np.empty`` when
+    the library or a CUDA device is missing, or the array is larger than ``PINNED_LIMIT_BYTES``."""
+    global _PINNED_OK
+    dtype = np.dtype(dtype)
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    if _PINNED_OK is False or nbytes == 0 or nbytes > PINNED_LIMIT_BYTES:
+        return np.empty(shape, dtype=dtype)
+    try:
+        blk = _PinnedBlock(nbytes)
+    except (NativeLibraryError, MemoryError, OSError):
+        _PINNED_OK = False
+        return np.empty(shape, dtype=dtype)
+    _PINNED_OK = True
+    return np.asarray(blk)[:nbytes].view(dtype).reshape(shape)
+
+
+def is_pinned(a) -> bool:
+    """True if the array's memory is page-locked (or device) memory known to the CUDA runtime."""
+    return bool(load().cw_host_is_pinned(ptr(a)))
 
 
 def ptr(a) -> Optional[int]:
@@ -203,22 +267,32 @@ class Context:
         return CwOpts(int(integrator), int(mem_space), float(atol), float(rtol), int(nmax),
                       stream, int(bool(no_sync)), 0)
 
+    @staticmethod
+    def _batch(n, w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv, n_w0=0, w0_index=None, grid_class=None,
+               classes=None, ev_off32=None):
+        return CwBatch(int(n), ptr(w0), ptr(t1), ptr(t2), ptr(dt), ptr(to_myr), ptr(flags), ptr(ev_off),
+                       ptr(ev_time), ptr(ev_dv), int(n_w0), ptr(w0_index), ptr(grid_class), ptr(classes),
+                       0 if classes is None else len(classes), 0, ptr(ev_off32))
+
     def integrate_raw(self, n, w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv, w_final, status,
                       n_nodes=None, ev_step=None, traj_off=None, traj_pos=None, traj_vel=None,
                       traj_t=None, stats=None, integrator=LEAPFROG, mem_space=MEM_HOST, atol=1e-10,
-                      rtol=1e-10, nmax=0, stream=None, no_sync=False):
+                      rtol=1e-10, nmax=0, stream=None, no_sync=False, n_w0=0, w0_index=None, grid_class=None,
+                      classes=None, ev_off32=None):
+        """``cw_integrate`` on raw buffers (numpy / torch / int addresses).  The keyword arguments after ``no_sync``
+        are the compact host forms of ABI 2 (``cw_batch`` in include/cogsworth_b200.h)."""
         o = self._opts(integrator, mem_space, atol, rtol, nmax, stream, no_sync)
-        b = CwBatch(int(n), ptr(w0), ptr(t1), ptr(t2), ptr(dt), ptr(to_myr), ptr(flags), ptr(ev_off),
-                    ptr(ev_time), ptr(ev_dv))
+        b = self._batch(n, w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv, n_w0, w0_index, grid_class,
+                        classes, ev_off32)
         r = CwResult(ptr(w_final), ptr(status), ptr(n_nodes), ptr(ev_step), ptr(traj_off), ptr(traj_pos),
                      ptr(traj_vel), ptr(traj_t), ptr(stats))
         self._check(self._L.cw_integrate(self._h, C.byref(o), C.byref(b), C.byref(r)), "cw_integrate")
 
     def count_nodes_raw(self, n, w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv, n_nodes,
-                        ev_step=None, mem_space=MEM_HOST):
+                        ev_step=None, mem_space=MEM_HOST, grid_class=None, classes=None, ev_off32=None):
         o = self._opts(LEAPFROG, mem_space, 0, 0, 0, None, False)
-        b = CwBatch(int(n), ptr(w0), ptr(t1), ptr(t2), ptr(dt), ptr(to_myr), ptr(flags), ptr(ev_off),
-                    ptr(ev_time), ptr(ev_dv))
+        b = self._batch(n, w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv, 0, None, grid_class, classes,
+                        ev_off32)
         self._check(self._L.cw_count_nodes(self._h, C.byref(o), C.byref(b), ptr(n_nodes), ptr(ev_step)),
                     "cw_count_nodes")
 
@@ -248,6 +322,10 @@ class Context:
         return n, K, w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv
 
     def count_nodes(self, w0, t1, t2, dt, to_myr=1.0, flags=0, ev_off=None, ev_time=None, ev_dv=None):
+        """Node count of every orbit and the node index of every event (the grid pre-pass alone); ``w0`` is not
+        read and may be ``None``."""
+        if w0 is None:
+            w0 = np.zeros((6, np.asarray(t1).shape[0]))
         n, K, w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv = self._prep(
             w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv)
         n_nodes = np.zeros(n, dtype=np.int32)
@@ -259,27 +337,58 @@ class Context:
                   integrator=LEAPFROG, store_all=False, atol=1e-10, rtol=1e-10, nmax=0, with_t=True):
         """Integrate a batch held in numpy arrays.  Returns a dict with w_final (6, n), status,
         n_nodes, ev_step, stats and -- when store_all -- traj_off, traj_pos, traj_vel, traj_t."""
-        if self.potential is None:
-            raise RuntimeError("set_potential() has not been called")
         n, K, w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv = self._prep(
             w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv)
-        out = dict(w_final=np.empty((6, n)), status=np.zeros(n, dtype=np.int32),
-                   n_nodes=np.zeros(n, dtype=np.int32), ev_step=np.full(max(K, 1), -1, dtype=np.int32),
-                   stats=np.zeros(4, dtype=np.int64))
+        return self._integrate(n, K, dict(w0=w0, t1=t1, t2=t2, dt=dt, to_myr=to_myr, flags=flags, ev_off=ev_off,
+                                          ev_time=ev_time, ev_dv=ev_dv), integrator, store_all, atol, rtol, nmax, with_t)
+
+    def integrate_batch(self, batch, integrator=LEAPFROG, store_all=False, atol=1e-10, rtol=1e-10, nmax=0,
+                        with_t=True):
+        """The same for an :class:`~cogsworth_b200.batch.OrbitBatch`, in its compact form when it has one (shared
+        initial conditions of disrupted secondaries, one-byte grid classes, 32-bit event offsets)."""
+        a = batch.abi_arrays()
+        if store_all and a.get("w0_index") is not None:
+            a["t1_full"] = batch.t1          # the node-count pass takes one start time per orbit
+        return self._integrate(batch.n_orbits, batch.n_events, a, integrator, store_all, atol, rtol, nmax, with_t)
+
+    def _integrate(self, n, K, a, integrator, store_all, atol, rtol, nmax, with_t):
+        if self.potential is None:
+            raise RuntimeError("set_potential() has not been called")
+        get = a.get
+        # results live in page-locked memory from the library's cache: the D2H copies land in them directly
+        out = dict(w_final=pinned_empty((6, n)), status=pinned_empty(n, np.int32), n_nodes=pinned_empty(n, np.int32),
+                   ev_step=pinned_empty(max(K, 1), np.int32), stats=np.zeros(4, dtype=np.int64))
+        compact = dict(n_w0=get("n_w0", 0), w0_index=get("w0_index"), grid_class=get("grid_class"),
+                       classes=get("classes"), ev_off32=get("ev_off32"))
         traj_off = traj_pos = traj_vel = traj_t = None
         if store_all:
-            nn, _ = self.count_nodes(w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv)
+            # node counts first (the grid pre-pass alone: start times and grid columns, no phase space, no events)
+            nn = pinned_empty(n, np.int32)
+            t1_full = get("t1_full", get("t1"))
+            self.count_nodes_raw(n, None, t1_full, get("t2"), get("dt"), get("to_myr"), get("flags"), None, None, None,
+                                 nn, None, grid_class=compact["grid_class"], classes=compact["classes"])
             traj_off = np.zeros(n + 1, dtype=np.int64)
             np.cumsum(np.maximum(nn, 0), out=traj_off[1:])
             tot = int(traj_off[-1])
-            traj_pos = np.full((3, tot), np.nan)
-            traj_vel = np.full((3, tot), np.nan)
-            traj_t = np.full(tot, np.nan) if with_t else None
-        self.integrate_raw(n, w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv, out["w_final"],
-                           out["status"], out["n_nodes"], out["ev_step"], traj_off, traj_pos, traj_vel,
-                           traj_t, out["stats"], integrator=integrator, mem_space=MEM_HOST, atol=atol,
-                           rtol=rtol, nmax=nmax)
+            traj_pos, traj_vel = pinned_empty((3, tot)), pinned_empty((3, tot))
+            traj_t = pinned_empty(tot) if with_t else None
+        self.integrate_raw(n, get("w0"), get("t1"), get("t2"), get("dt"), get("to_myr"), get("flags"), get("ev_off"),
+                           get("ev_time"), get("ev_dv"), out["w_final"], out["status"], out["n_nodes"], out["ev_step"],
+                           traj_off, traj_pos, traj_vel, traj_t, out["stats"], integrator=integrator,
+                           mem_space=MEM_HOST, atol=atol, rtol=rtol, nmax=nmax, **compact)
+        if K == 0:
+            out["ev_step"][:] = -1
         out["ev_step"] = out["ev_step"][:K]
+        if store_all:
+            # the kernels write nothing for orbits the pre-pass rejected, and stop writing where an orbit fails:
+            # those columns (few) are marked, not the whole buffer
+            bad = np.flatnonzero(out["status"] != 0)
+            for i in bad:
+                sl = slice(int(traj_off[i]), int(traj_off[i + 1]))
+                traj_pos[:, sl] = np.nan
+                traj_vel[:, sl] = np.nan
+                if traj_t is not None:
+                    traj_t[sl] = np.nan
         out.update(traj_off=traj_off, traj_pos=traj_pos, traj_vel=traj_vel, traj_t=traj_t)
         return out
 
@@ -343,8 +452,24 @@ _DEFAULT: Optional[Context] = None
 
 
 def default_context() -> Context:
-    """Process-wide context on every visible device (lazily created)."""
+    """Process-wide context (lazily created): every visible device -- orbits are sharded by index, one host thread per
+    device -- unless this process is one rank of a one-process-per-GPU job (``LOCAL_RANK`` set, or a
+    ``torch.distributed`` group initialised), in which case it owns its rank's device only.  A ``Population`` can be
+    given its own through the ``_cw_context`` attribute."""
     global _DEFAULT
     if _DEFAULT is None:
-        _DEFAULT = Context()
+        devices = None
+        lr = os.environ.get("LOCAL_RANK")
+        if lr is None:
+            try:
+                import sys
+                td = sys.modules.get("torch.distributed")
+                if td is not None and td.is_available() and td.is_initialized():
+                    import torch
+                    lr = td.get_rank() % max(torch.cuda.device_count(), 1)
+            except Exception:
+                lr = None
+        if lr is not None:
+            devices = [int(lr)]
+        _DEFAULT = Context(devices=devices)
     return _DEFAULT

@@ -14,7 +14,7 @@ float, because the kick node index is defined by FP64 comparisons of those value
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional
 
 import numpy as np
@@ -56,45 +56,106 @@ class EventTable:
         return off
 
 
-def rotate_kicks(dv_kms: np.ndarray, phase: np.ndarray, inc: np.ndarray) -> np.ndarray:
+def rotate_kicks(dv_kms: np.ndarray, phase: np.ndarray, inc: np.ndarray, out=None) -> np.ndarray:
     """Vectorised ``get_kick_differential`` (kicks.py:42-46): BSE (vx,vy,vz) -> Galactocentric, km/s."""
     vx, vy, vz = dv_kms[:, 0], dv_kms[:, 1], dv_kms[:, 2]
-    theta, phi = phase, inc
-    v_X = vx * np.cos(theta) - vy * np.sin(theta) * np.cos(phi) + vz * np.sin(theta) * np.sin(phi)
-    v_Y = vx * np.sin(theta) + vy * np.cos(theta) * np.cos(phi) - vz * np.cos(theta) * np.sin(phi)
-    v_Z = vy * np.sin(phi) + vz * np.cos(phi)
-    return np.stack([v_X, v_Y, v_Z], axis=1)
+    st, ct, sp, cp = np.sin(phase), np.cos(phase), np.sin(inc), np.cos(inc)
+    if out is None:
+        out = np.empty((len(phase), 3))
+    out[:, 0] = vx * ct - vy * st * cp + vz * st * sp
+    out[:, 1] = vx * st + vy * ct * cp - vz * ct * sp
+    out[:, 2] = vy * sp + vz * cp
+    return out
 
 
-@dataclass
 class OrbitBatch:
-    """Everything ``cw_integrate`` needs for a set of orbits (see include/cogsworth_b200.h)."""
-    w0: np.ndarray           # (6, n)  kpc, kpc/Myr
-    t1: np.ndarray           # grid unit
-    t2: np.ndarray
-    dt: np.ndarray
-    to_myr: np.ndarray
-    flags: np.ndarray        # int32
-    ev_off: Optional[np.ndarray] = None   # (n+1,) int64
-    ev_time: Optional[np.ndarray] = None  # (K,) grid unit
-    ev_dv: Optional[np.ndarray] = None    # (K, 3) kpc/Myr
-    n_primary: int = 0       # the first n_primary orbits are bound systems / primaries (Q7)
-    secondary_of: Optional[np.ndarray] = None  # population index of each disrupted secondary
-    meta: dict = field(default_factory=dict)
+    """Everything ``cw_integrate`` needs for a set of orbits (see include/cogsworth_b200.h).
+
+    Two representations of the same orbits:
+
+    * the PLAIN layout -- ``w0`` (6, n) kpc & kpc/Myr, ``t1``, ``t2``, ``dt``, ``to_myr`` (n,) in the orbit's grid
+      unit, ``flags`` (n,) int32, events CSR ``ev_off`` (n+1,) int64 / ``ev_time`` (K,) / ``ev_dv`` (K, 3);
+    * the COMPACT form ``build_orbit_batch`` produces (``cw_batch`` ABI 2): the initial conditions and birth times
+      of the ``n_w0`` systems once, ``w0_index`` naming the system every disrupted secondary starts from
+      (pop.py:1186-1193), one byte of ``grid_class`` per orbit into a table of (t2, dt, to_myr, flags) and 32-bit
+      event offsets -- 78 instead of 134 bytes per orbit across the host link for a kicked population.
+
+    The plain arrays of a compact batch are expanded on first access (tests, the retry loop, the CPU oracle);
+    assigning to one of them drops the compact form.
+    """
+
+    _PLAIN = ("w0", "t1", "t2", "dt", "to_myr", "flags", "ev_off")
+
+    def __init__(self, w0=None, t1=None, t2=None, dt=None, to_myr=None, flags=None, ev_off=None, ev_time=None,
+                 ev_dv=None, n_primary=0, secondary_of=None, meta=None, compact=None):
+        d = self.__dict__
+        d["_plain"] = dict(w0=w0, t1=t1, t2=t2, dt=dt, to_myr=to_myr, flags=flags, ev_off=ev_off)
+        d["ev_time"], d["ev_dv"] = ev_time, ev_dv
+        d["n_primary"] = n_primary          # the first n_primary orbits are bound systems / primaries (Q7)
+        d["secondary_of"] = secondary_of    # population index of each disrupted secondary
+        d["meta"] = {} if meta is None else meta
+        d["compact"] = compact              # dict(w0, t1, n_w0, w0_index, grid_class, classes, ev_off32) or None
+
+    # -- plain arrays, expanded from the compact form on demand ---------------------------------------
+    def __getattr__(self, name):
+        if name in OrbitBatch._PLAIN:
+            v = self.__dict__["_plain"][name]
+            if v is None and self.__dict__["compact"] is not None:
+                v = self._expand(name)
+                self.__dict__["_plain"][name] = v
+            return v
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        if name in OrbitBatch._PLAIN:
+            if self.__dict__["compact"] is not None:        # the compact form no longer describes the batch
+                for k in OrbitBatch._PLAIN:
+                    getattr(self, k)
+                self.__dict__["compact"] = None
+            self.__dict__["_plain"][name] = value
+        else:
+            self.__dict__[name] = value
+
+    def _expand(self, name):
+        c = self.compact
+        n_w0, idx = c["n_w0"], c["w0_index"]
+        if name == "w0":
+            w0 = np.empty((6, n_w0 + len(idx)))
+            w0[:, :n_w0] = c["w0"]
+            w0[:, n_w0:] = c["w0"][:, idx]
+            return w0
+        if name == "t1":
+            return np.concatenate([c["t1"], c["t1"][idx]])
+        if name == "ev_off":
+            return None if c["ev_off32"] is None else c["ev_off32"].astype(np.int64)
+        col = {"t2": "t2", "dt": "dt", "to_myr": "to_myr", "flags": "grid_flags"}[name]
+        return np.ascontiguousarray(c["classes"][col][c["grid_class"]])
 
     @property
     def n_orbits(self) -> int:
-        return self.w0.shape[1]
+        c = self.compact
+        return c["n_w0"] + len(c["w0_index"]) if c is not None else self.w0.shape[1]
 
     @property
     def n_events(self) -> int:
-        return 0 if self.ev_off is None else int(self.ev_off[-1])
+        return 0 if self.ev_time is None else int(self.ev_time.shape[0])
+
+    def abi_arrays(self) -> dict:
+        """The arrays of one ``cw_integrate`` call, compact when the batch has that form."""
+        c = self.compact
+        if c is None:
+            return dict(w0=self.w0, t1=self.t1, t2=self.t2, dt=self.dt, to_myr=self.to_myr, flags=self.flags,
+                        ev_off=self.ev_off if self.n_events else None, ev_time=self.ev_time, ev_dv=self.ev_dv)
+        K = self.n_events
+        return dict(w0=c["w0"], t1=c["t1"], n_w0=c["n_w0"], w0_index=c["w0_index"] if len(c["w0_index"]) else None,
+                    grid_class=c["grid_class"], classes=c["classes"], ev_off32=c["ev_off32"] if K else None,
+                    ev_time=self.ev_time if K else None, ev_dv=self.ev_dv if K else None)
 
     def take(self, idx) -> "OrbitBatch":
-        """Sub-batch (used by the retry loop for failed orbits)."""
+        """Sub-batch in the plain layout (used by the retry loop for failed orbits)."""
         idx = np.asarray(idx, dtype=np.int64)
         ev_off = ev_time = ev_dv = None
-        if self.ev_off is not None:
+        if self.ev_off is not None and self.n_events:
             counts = (self.ev_off[1:] - self.ev_off[:-1])[idx]
             ev_off = np.zeros(len(idx) + 1, dtype=np.int64)
             np.cumsum(counts, out=ev_off[1:])
@@ -126,14 +187,47 @@ def _grid_columns(t1_gyr, t2_gyr, dt_myr, kicked):
     return t1, t2, dt, to_myr, flags
 
 
+def _grid_classes(t1_gyr, t2_gyr, dt_myr, kicked):
+    """The grid columns of ``_grid_columns`` as (grid_class uint8 (n,), classes table) -- ``cw_grid_class`` of
+    include/cogsworth_b200.h -- or ``None`` when more than 256 classes would be needed.  Same floats as the plain
+    columns: class 0 = the events branch (seconds, t2 appended), class 1 = gala's own grid (Myr), then one class per
+    distinct span shorter than dt (kicks.py:97)."""
+    from ._lib import GRID_CLASS_DTYPE, pinned_empty
+    n = t1_gyr.shape[0]
+    t2_gyr, dt_myr = float(t2_gyr), float(dt_myr)
+    span_gyr = t2_gyr - t1_gyr
+    clip = np.flatnonzero(span_gyr < dt_myr * K.GYR_PER_MYR)
+    rows = [(t2_gyr * K.SEC_PER_GYR, dt_myr * K.SEC_PER_MYR, K.MYR_PER_SEC, GRID_APPEND_T2),
+            (t2_gyr * K.MYR_PER_GYR, dt_myr, 1.0, 0)]
+    cls = pinned_empty(n, np.uint8)
+    np.logical_not(kicked, out=cls.view(np.bool_))           # kicked -> 0, un-kicked -> 1
+    if len(clip):
+        key = np.stack([span_gyr[clip], kicked[clip].astype(np.float64)], axis=1)
+        uniq, inv = np.unique(key, axis=0, return_inverse=True)
+        if 2 + len(uniq) > 256:
+            return None
+        for sp, kf in uniq:
+            rows.append((t2_gyr * K.SEC_PER_GYR, sp * K.SEC_PER_GYR, K.MYR_PER_SEC, GRID_APPEND_T2) if kf else
+                        (t2_gyr * K.MYR_PER_GYR, sp * K.MYR_PER_GYR, 1.0, 0))
+        cls[clip] = 2 + np.asarray(inv).reshape(-1)
+    classes = np.zeros(len(rows), dtype=GRID_CLASS_DTYPE)
+    for i, (a, b, c, f) in enumerate(rows):
+        classes[i] = (a, b, c, f, 0)
+    return cls, classes
+
+
 def build_orbit_batch(pos_kpc, vel_kms, tau_gyr, max_ev_time_gyr, timestep_myr, disrupted,
                       primary_events: Optional[EventTable] = None,
-                      secondary_events: Optional[EventTable] = None) -> OrbitBatch:
+                      secondary_events: Optional[EventTable] = None, compact: bool = True) -> OrbitBatch:
     """Vectorised ``_iter_orbit_args``: primaries (population order) then disrupted secondaries.
 
     pos_kpc, vel_kms : (3, n) arrays; tau_gyr : (n,) look-back birth times; ``t1 = max_ev_time - tau``
     (pop.py:1180).  ``secondary_events.owner`` indexes the population (not the disrupted subset).
+
+    compact : build the compact form of :class:`OrbitBatch` (what ``cw_integrate`` is sent), with the large arrays in
+    page-locked memory; the plain arrays are then expanded only if something reads them.
     """
+    from ._lib import pinned_empty
     pos_kpc = np.asarray(pos_kpc, dtype=np.float64)
     vel_kms = np.asarray(vel_kms, dtype=np.float64)
     tau_gyr = np.asarray(tau_gyr, dtype=np.float64)
@@ -143,12 +237,7 @@ def build_orbit_batch(pos_kpc, vel_kms, tau_gyr, max_ev_time_gyr, timestep_myr, 
     n_dis = len(dis_idx)
     pe = primary_events if primary_events is not None else EventTable.empty()
     se = secondary_events if secondary_events is not None else EventTable.empty()
-
-    src = np.concatenate([np.arange(n), dis_idx])          # population index of every orbit
     n_orb = n + n_dis
-    w0 = np.empty((6, n_orb))
-    w0[:3] = pos_kpc[:, src]
-    w0[3:] = vel_kms[:, src] * K.KPC_MYR_PER_KMS            # gala: km/s -> kpc/Myr on entry
 
     # events: primary rows keep their owner; secondary rows move to orbit n + rank(owner in disrupted)
     pe_off = pe.csr(n)
@@ -157,29 +246,58 @@ def build_orbit_batch(pos_kpc, vel_kms, tau_gyr, max_ev_time_gyr, timestep_myr, 
     if len(se) and np.any(rank[se.owner] < 0):
         raise ValueError("secondary events given for a binary that is not disrupted")
     se_owner = rank[se.owner] if len(se) else se.owner
-    se_tab = EventTable(se_owner, se.tphys, se.dv, se.phase, se.inc)
-    se_off = se_tab.csr(n_dis)
+    se_off = EventTable(se_owner, se.tphys, se.dv, se.phase, se.inc).csr(n_dis)
     ev_off = np.concatenate([pe_off, pe_off[-1] + se_off[1:]])
-    tphys = np.concatenate([pe.tphys, se.tphys]).astype(np.float64)
-    dv = np.concatenate([pe.dv.reshape(-1, 3), se.dv.reshape(-1, 3)]).astype(np.float64)
-    phase = np.concatenate([pe.phase, se.phase]).astype(np.float64)
-    inc = np.concatenate([pe.inc, se.inc]).astype(np.float64)
-    owner_orbit = np.concatenate([pe.owner, n + se_owner]).astype(np.int64)
+    Kn = len(pe) + len(se)
 
     counts = ev_off[1:] - ev_off[:-1]
     # pop.py:1177-1183: `events` is None unless the binary has a supernova row; disrupted secondaries
     # always take the events branch (pop.py:1186-1193)
     kicked = counts > 0
     kicked[n:] = True
-    t1_gyr = max_ev_time_gyr - tau_gyr[src]
-    t1, t2, dt, to_myr, flags = _grid_columns(t1_gyr, max_ev_time_gyr, timestep_myr, kicked)
+    t1_gyr_src = max_ev_time_gyr - tau_gyr
 
-    Kn = len(tphys)
     ev_time = ev_dv = None
     if Kn:
+        tphys = np.concatenate([pe.tphys, se.tphys]).astype(np.float64)
+        owner_src = np.concatenate([pe.owner, se.owner]).astype(np.int64)     # population index of each event
         # (t1 + tphys * u.Myr) is formed in t1's unit (Gyr) and compared in seconds (kicks.py:134)
-        ev_time = (t1_gyr[owner_orbit] + tphys * K.GYR_PER_MYR) * K.SEC_PER_GYR
-        ev_dv = rotate_kicks(dv, phase, inc) * K.KPC_MYR_PER_KMS
+        ev_time = pinned_empty(Kn)
+        np.multiply(tphys, K.GYR_PER_MYR, out=ev_time)
+        np.add(ev_time, t1_gyr_src[owner_src], out=ev_time)
+        np.multiply(ev_time, K.SEC_PER_GYR, out=ev_time)
+        ev_dv = pinned_empty((Kn, 3))
+        rotate_kicks(np.concatenate([pe.dv.reshape(-1, 3), se.dv.reshape(-1, 3)]).astype(np.float64),
+                     np.concatenate([pe.phase, se.phase]).astype(np.float64),
+                     np.concatenate([pe.inc, se.inc]).astype(np.float64), out=ev_dv)
+        np.multiply(ev_dv, K.KPC_MYR_PER_KMS, out=ev_dv)
+
+    # the compact form needs every disrupted system's own orbit on the events branch (its start time is then the
+    # same float in seconds for the system and its secondary) and few enough distinct grids
+    grid = None
+    if compact and n_orb < 2 ** 31 and Kn < 2 ** 31 and (n_dis == 0 or bool(kicked[dis_idx].all())):
+        t1_gyr = np.concatenate([t1_gyr_src, t1_gyr_src[dis_idx]]) if n_dis else t1_gyr_src
+        grid = _grid_classes(t1_gyr, max_ev_time_gyr, timestep_myr, kicked)
+    if grid is not None:
+        w0 = pinned_empty((6, n))
+        w0[:3] = pos_kpc
+        np.multiply(vel_kms, K.KPC_MYR_PER_KMS, out=w0[3:])     # gala: km/s -> kpc/Myr on entry
+        t1 = pinned_empty(n)
+        np.multiply(t1_gyr_src, np.where(kicked[:n], K.SEC_PER_GYR, K.MYR_PER_GYR), out=t1)
+        idx = pinned_empty(n_dis, np.int32)
+        idx[:] = dis_idx
+        off32 = None
+        if Kn:
+            off32 = pinned_empty(n_orb + 1, np.int32)
+            off32[:] = ev_off
+        c = dict(w0=w0, t1=t1, n_w0=n, w0_index=idx, grid_class=grid[0], classes=grid[1], ev_off32=off32)
+        return OrbitBatch(ev_time=ev_time, ev_dv=ev_dv, n_primary=n, secondary_of=dis_idx, compact=c)
+
+    src = np.concatenate([np.arange(n), dis_idx])          # population index of every orbit
+    w0 = np.empty((6, n_orb))
+    w0[:3] = pos_kpc[:, src]
+    w0[3:] = vel_kms[:, src] * K.KPC_MYR_PER_KMS
+    t1, t2, dt, to_myr, flags = _grid_columns(t1_gyr_src[src], max_ev_time_gyr, timestep_myr, kicked)
     return OrbitBatch(w0=w0, t1=t1, t2=t2, dt=dt, to_myr=to_myr, flags=flags,
                       ev_off=ev_off if Kn else None, ev_time=ev_time, ev_dv=ev_dv,
                       n_primary=n, secondary_of=dis_idx)

@@ -11,11 +11,15 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <climits>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include "cw_host.h"
 #include "cw_kernels.cuh"
 
 using namespace cw;
@@ -69,16 +73,27 @@ struct Slot {
     cudaStream_t stream = nullptr;          // = lanes[0]
     cudaStream_t lanes[N_LANES] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_t0 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;   // diagnostics entry points
-    std::vector<cudaEvent_t> events;        // per-shard timing events (grow-only pool)
+    std::vector<cudaEvent_t> events;        // per-chunk events (grow-only pool)
     Arena arena;                            // diagnostics / pointwise entry points
-    // Integration scratch, ONE ARENA PER STREAM LANE: the shards of a lane run one after another on the lane's
+    // Integration scratch, ONE ARENA PER STREAM LANE: the chunks of a lane run one after another on the lane's
     // stream, so each of them re-uses the lane's buffers (stream order is the only synchronisation needed).
     // Device memory of a host-buffer call is therefore bounded by N_LANES chunks, not by the size of the batch:
     // trajectories larger than HBM stream through.
     Arena lane_arena[N_LANES];
-    Arena meta;                             // queue counter + statistics of every shard of a call (64 B each): NOT
-                                            // re-used within a call, so they can be read back after the last shard
+    Arena meta;                             // queue counter + statistics of every chunk of a call (one padded block
+                                            // each): NOT re-used within a call, so they can be read back at its end
+    // page-locked staging buffers of the lanes (from the library's cache) for pageable caller arrays
+    void *stage_in[N_LANES] = {nullptr, nullptr, nullptr};
+    void *stage_out[N_LANES] = {nullptr, nullptr, nullptr};
+    size_t stage_in_cap[N_LANES] = {0, 0, 0}, stage_out_cap[N_LANES] = {0, 0, 0};
+    cudaEvent_t h2d_done[N_LANES] = {nullptr, nullptr, nullptr};   // the DMA out of stage_in[l] has completed
+    bool h2d_pending[N_LANES] = {false, false, false};
+    // device-mode no_sync calls: the next call is ordered behind this event (they share the scratch above)
+    cudaEvent_t pending = nullptr;
+    bool has_pending = false;
     double last_kernel_ms = 0.0, last_total_ms = 0.0;
+    int64_t launches = 0;                   // kernels launched by the current call on this slot
+    std::string error;                      // failure text of the slot's worker thread
     cudaError_t ensure_events(size_t n)
     {
         while (events.size() < n) {
@@ -173,6 +188,9 @@ extern "C" int cw_create(cw_ctx **out, int n_devices, const int *device_ids)
         if (e == cudaSuccess) e = cudaEventCreate(&s.ev_t0);
         if (e == cudaSuccess) e = cudaEventCreate(&s.ev_k0);
         if (e == cudaSuccess) e = cudaEventCreate(&s.ev_k1);
+        for (int l = 0; l < Slot::N_LANES && e == cudaSuccess; l++)
+            e = cudaEventCreateWithFlags(&s.h2d_done[l], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.pending, cudaEventDisableTiming);
         if (e != cudaSuccess) {
             cudaGetLastError();
             cudaSetDevice(prev);
@@ -202,6 +220,13 @@ extern "C" void cw_destroy(cw_ctx *ctx)
         if (s.ev_t0) cudaEventDestroy(s.ev_t0);
         if (s.ev_k0) cudaEventDestroy(s.ev_k0);
         if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+        if (s.has_pending) cudaEventSynchronize(s.pending);
+        if (s.pending) cudaEventDestroy(s.pending);
+        for (int l = 0; l < Slot::N_LANES; l++) {
+            if (s.h2d_done[l]) cudaEventDestroy(s.h2d_done[l]);
+            pinned_free(s.stage_in[l]);
+            pinned_free(s.stage_out[l]);
+        }
         for (int l = 0; l < Slot::N_LANES; l++)
             if (s.lanes[l]) cudaStreamDestroy(s.lanes[l]);
     }
@@ -485,16 +510,74 @@ static int set_potential_impl(cw_ctx *ctx, double G, int n_comp, const int32_t *
 }
 
 // ---------------------------------------------------------------------------------------------
+// cw_integrate / cw_count_nodes
+//
+// CW_MEM_DEVICE: one shard on the context's first device, every pointer used as it is.
+// CW_MEM_HOST:   the batch is cut by index over the device slots (one host thread per slot) and, within a slot, into
+//                chunks that rotate over N_LANES streams, so the H2D copy of chunk c+1 and the D2H copy of chunk c-1
+//                overlap the kernels of chunk c.  Caller arrays that are page-locked are DMA-ed directly; pageable ones
+//                (plain numpy) go through the lane's page-locked staging buffers, copied by the host thread pool.
+// ---------------------------------------------------------------------------------------------
 
 namespace {
 
-// One unit of work: a contiguous range of orbits on one device slot, on one of its streams.
-struct Shard {
-    int slot = 0, lane = 0; // device slot, stream lane within the slot
-    int64_t a = 0, b = 0;   // orbit range
-    int64_t ea = 0, eb = 0; // event range
-    int64_t ta = 0, tb = 0; // trajectory column range
-};
+constexpr int64_t SORT_THRESHOLD = 4096;
+// About 8 chunks per device, between 2^16 orbits (below that launch overheads show) and 2^20 (bounds the exposed first
+// copy).
+constexpr int64_t HOST_CHUNK_MAX = 1 << 20, HOST_CHUNK_MIN = 1 << 16;
+constexpr int64_t TRAJ_SHARD_COLS = (int64_t)1 << 26;          // trajectory columns per host-mode chunk (3.2 GB)
+constexpr int64_t TRAJ_SHARD_COLS_STAGED = (int64_t)1 << 23;   // ... when they pass through the staging ring (400 MB)
+static int64_t traj_shard_cols(bool staged)
+{
+    const char *e = getenv("CW_TRAJ_SHARD_COLS");       // test hook: force many small shards
+    const long long v = e ? atoll(e) : 0;
+    return v > 0 ? (int64_t)v : (staged ? TRAJ_SHARD_COLS_STAGED : TRAJ_SHARD_COLS);
+}
+// Q > 0: the number of orbits one full grid of the kernel holds (persistent lanes).  Chunks are whole multiples of it,
+// so no chunk ends with a wave that fills a fraction of the GPU (10^6 orbits in LM10 at Q = 113 664: 127k-orbit
+// chunks = 1.12 waves each cost a third of the end-to-end throughput).
+static int64_t host_chunk(int64_t n_on_device, int64_t Q)
+{
+    int64_t c = (n_on_device + 7) / 8;
+    if (const char *e = getenv("CW_HOST_CHUNK")) {      // experiment hook: fixed chunk size in orbits
+        const long long v = atoll(e);
+        if (v > 0) return (int64_t)v;
+    }
+    if (Q <= 0 || getenv("CW_NO_WAVE_CHUNKS")) {
+        c = (c + 4095) & ~int64_t(4095);
+        return std::min(HOST_CHUNK_MAX, std::max(HOST_CHUNK_MIN, c));
+    }
+    c = ((c + Q - 1) / Q) * Q;
+    const int64_t cmax = std::max<int64_t>(Q, (HOST_CHUNK_MAX / Q) * Q);
+    return std::min(cmax, std::max(Q, c));
+}
+
+// orbit counts of the chunks of one device slot holding M orbits
+static std::vector<int64_t> chunk_sizes(int64_t M, bool pipelined, int64_t Q)
+{
+    std::vector<int64_t> sizes;
+    const int64_t chunk = pipelined ? host_chunk(M, Q) : M;
+    // The first H2D copy and the last D2H copy have nothing to hide behind: ramp the chunk size up from a fraction
+    // of it at the start and back down at the end (the kernels in between keep the full size).
+    if (!pipelined || M < 4 * chunk) {
+        for (int64_t c = 0; c < M; c += chunk) sizes.push_back(std::min(chunk, M - c));
+        return sizes;
+    }
+    std::vector<int64_t> head, tail;
+    int64_t used = 0;
+    if (Q > 0) {     // whole waves here too: Q, 2Q, 4Q, ...
+        for (int64_t sz = Q; sz < chunk; sz *= 2) { head.push_back(sz); used += sz; }
+        for (int64_t sz = Q; sz < chunk; sz *= 2) { tail.push_back(sz); used += sz; }
+    } else {
+        for (int64_t sz = std::max<int64_t>(chunk / 8, HOST_CHUNK_MIN / 2); sz < chunk; sz *= 2) { head.push_back(sz); used += sz; }
+        for (int64_t sz = std::max<int64_t>(chunk / 4, HOST_CHUNK_MIN / 2); sz < chunk; sz *= 2) { tail.push_back(sz); used += sz; }
+    }
+    int64_t mid = M - used;
+    sizes = head;
+    while (mid > 0) { const int64_t sz = std::min(chunk, mid); sizes.push_back(sz); mid -= sz; }
+    for (size_t k = tail.size(); k-- > 0;) sizes.push_back(tail[k]);
+    return sizes;
+}
 
 // size of the CUB temp storage for sorting m (key, value) pairs
 size_t sort_temp_bytes(int64_t m)
@@ -503,33 +586,6 @@ size_t sort_temp_bytes(int64_t m)
     cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const int32_t *)nullptr, (int32_t *)nullptr,
                                               (const int32_t *)nullptr, (int32_t *)nullptr, (int)m);
     return bytes;
-}
-
-constexpr int64_t SORT_THRESHOLD = 4096;
-// Host-buffer calls are cut into chunks that rotate over N_LANES streams, so the H2D copy of chunk c+1
-// and the D2H copy of chunk c-1 overlap the kernels of chunk c: about 8 chunks per device, between
-// 2^16 orbits (below that launch overheads show) and 2^20 (bounds the exposed first copy).
-constexpr int64_t HOST_CHUNK_MAX = 1 << 20, HOST_CHUNK_MIN = 1 << 16;
-constexpr int64_t TRAJ_SHARD_COLS = (int64_t)1 << 26;   // trajectory columns per host-mode shard (store_all)
-static int64_t traj_shard_cols()
-{
-    const char *e = getenv("CW_TRAJ_SHARD_COLS");       // test hook: force many small shards
-    const long long v = e ? atoll(e) : 0;
-    return v > 0 ? (int64_t)v : TRAJ_SHARD_COLS;
-}
-// Q > 0: the number of orbits one full grid of the kernel holds (persistent lanes).  Chunks are whole multiples of it,
-// so no chunk ends with a wave that fills a fraction of the GPU (10^6 orbits in LM10 at Q = 113 664: 127k-orbit
-// chunks = 1.12 waves each cost a third of the end-to-end throughput).
-static int64_t host_chunk(int64_t n_on_device, int64_t Q)
-{
-    int64_t c = (n_on_device + 7) / 8;
-    if (Q <= 0 || getenv("CW_NO_WAVE_CHUNKS")) {
-        c = (c + 4095) & ~int64_t(4095);
-        return std::min(HOST_CHUNK_MAX, std::max(HOST_CHUNK_MIN, c));
-    }
-    c = ((c + Q - 1) / Q) * Q;
-    const int64_t cmax = std::max<int64_t>(Q, (HOST_CHUNK_MAX / Q) * Q);
-    return std::min(cmax, std::max(Q, c));
 }
 
 struct Plan {
@@ -543,132 +599,34 @@ struct Plan {
     bool timed = false;
 };
 
-} // namespace
+// failures inside a slot's worker are reported through the slot, not the context (several slots run at once)
+#define CW_SCK(slot, call)                                                                        \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            char _b[512];                                                                         \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            (slot).error = _b;                                                                    \
+            return CW_E_CUDA;                                                                     \
+        }                                                                                         \
+    } while (0)
 
-// bytes of device scratch one shard needs (host mode: everything; device mode: scratch only)
-static size_t shard_bytes(const cw_opts *o, const cw_result *R, const Shard &sh, bool integrate, Plan &pl)
+static int slot_fail(Slot &s, int code, const char *msg)
 {
-    const bool dev_mode = o->mem_space == CW_MEM_DEVICE;
-    const int64_t m = sh.b - sh.a, K = sh.eb - sh.ea, Lt = sh.tb - sh.ta;
-    const bool store_all = integrate && R && R->traj_off;
-    pl.sort = integrate && m >= SORT_THRESHOLD;
-    pl.sort_bytes = pl.sort ? sort_temp_bytes(m) : 0;
-    size_t need = 0;
-    auto add = [&](size_t count, size_t elt) { need += Arena::padded(count, elt); };
-    add(K + 1, sizeof(double));          // ev_tk
-    if (integrate && o->integrator == CW_DOP853_DENSE) add(m, sizeof(double));   // t_last
-    add(1, 64);                          // queue + stats
-    if (pl.sort) { add(m, 4); add(m, 4); add(m, 4); add(m, 4); add(pl.sort_bytes, 1); }
-    if (!dev_mode) {
-        add(6 * m, 8); add(4 * m, 8); add(m, 4); add(m + 1, 8); add(K + 1, 8); add(3 * K + 3, 8);
-        add(m, 4); add(K + 1, 4);               // n_nodes, ev_step
-        add(6 * m, 8); add(m, 4);               // w_final, status
-        if (store_all) { add(m + 1, 8); add(6 * (Lt + 16), 8); add(Lt + 1, 8); }
-    } else {
-        add(m, 4); add(K + 1, 4); add(m, 4);    // n_nodes / ev_step / status if the caller passed NULL
-    }
-    return need + 1024;
+    s.error = msg;
+    return code;
 }
 
-// Carve the shard's buffers out of the slot arena, fill its IntegArgs and enqueue the H2D copies.
-static int plan_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, const cw_batch *B, const cw_result *R,
-                      const Shard &sh, bool integrate, Plan &pl)
-{
-    const bool dev_mode = o->mem_space == CW_MEM_DEVICE;
-    const int64_t m = sh.b - sh.a, K = sh.eb - sh.ea, Lt = sh.tb - sh.ta;
-    const bool store_all = integrate && R && R->traj_off;
-    cudaStream_t stream = pl.stream;
-    Arena &ar = s.lane_arena[sh.lane];
-    ar.used = 0;                            // the previous shard of this lane precedes us in stream order
-
-    IntegArgs &A = pl.A;
-    memset(&A, 0, sizeof A);
-    A.n = m;
-    A.atol = o->atol > 0 ? o->atol : 1e-10;
-    A.rtol = o->rtol > 0 ? o->rtol : 1e-10;
-    A.nmax = o->nmax;
-    A.ev_tk = ar.take<double>(K + 1);
-    if (integrate && o->integrator == CW_DOP853_DENSE) {
-        A.t_last = ar.take<double>(m);
-        if (!A.t_last) return fail(ctx, CW_E_CUDA, "device arena exhausted (internal sizing error)");
-    }
-    unsigned long long *qs = s.meta.take<unsigned long long>(8);
-    A.queue = qs;
-    A.stats = qs + 1;
-    if (pl.sort) {
-        pl.iota = ar.take<int32_t>(m);
-        pl.keys_out = ar.take<int32_t>(m);
-        pl.keys_in = ar.take<int32_t>(m);
-        pl.order = ar.take<int32_t>(m);
-        A.order = pl.order;
-        pl.sort_tmp = ar.take<char>(pl.sort_bytes);
-    }
-    if (!dev_mode) {
-        double *w0 = ar.take<double>(6 * m);
-        double *tt = ar.take<double>(4 * m);
-        int32_t *fl = ar.take<int32_t>(m);
-        int64_t *eo = ar.take<int64_t>(m + 1);
-        double *et = ar.take<double>(K + 1);
-        double *ed = ar.take<double>(3 * K + 3);
-        A.n_nodes = ar.take<int32_t>(m);
-        A.ev_step = ar.take<int32_t>(K + 1);
-        A.w_final = ar.take<double>(6 * m);
-        A.status = ar.take<int32_t>(m);
-        if (!w0 || !tt || !fl || !eo || !et || !ed || !A.w_final || !A.status)
-            return fail(ctx, CW_E_CUDA, "device arena exhausted (internal sizing error)");
-        A.w0 = w0; A.t1 = tt; A.t2 = tt + m; A.dt = tt + 2 * m; A.to_myr = tt + 3 * m; A.flags = fl;
-        for (int c = 0; c < 6; c++)
-            CW_CK(ctx, cudaMemcpyAsync(w0 + c * m, B->w0 + c * B->n_orbits + sh.a, m * 8, cudaMemcpyHostToDevice, stream));
-        CW_CK(ctx, cudaMemcpyAsync(tt, B->t1 + sh.a, m * 8, cudaMemcpyHostToDevice, stream));
-        CW_CK(ctx, cudaMemcpyAsync(tt + m, B->t2 + sh.a, m * 8, cudaMemcpyHostToDevice, stream));
-        CW_CK(ctx, cudaMemcpyAsync(tt + 2 * m, B->dt + sh.a, m * 8, cudaMemcpyHostToDevice, stream));
-        CW_CK(ctx, cudaMemcpyAsync(tt + 3 * m, B->to_myr + sh.a, m * 8, cudaMemcpyHostToDevice, stream));
-        CW_CK(ctx, cudaMemcpyAsync(fl, B->grid_flags + sh.a, m * 4, cudaMemcpyHostToDevice, stream));
-        if (B->ev_off && K > 0) {
-            CW_CK(ctx, cudaMemcpyAsync(eo, B->ev_off + sh.a, (m + 1) * 8, cudaMemcpyHostToDevice, stream));
-            CW_CK(ctx, cudaMemcpyAsync(et, B->ev_time + sh.ea, K * 8, cudaMemcpyHostToDevice, stream));
-            CW_CK(ctx, cudaMemcpyAsync(ed, B->ev_dv + 3 * sh.ea, 3 * K * 8, cudaMemcpyHostToDevice, stream));
-            A.ev_off = eo; A.ev_base = sh.ea; A.ev_time = et; A.ev_dv = ed;
-        }
-        if (store_all) {
-            // device rows are padded to a multiple of 16 columns so every row starts 128-byte aligned
-            // (the trajectory writer's bulk stores need 16-byte aligned destinations)
-            const int64_t Ltp = (Lt + 15) & ~int64_t(15);
-            int64_t *to = ar.take<int64_t>(m + 1);
-            double *tp = ar.take<double>(6 * Ltp);
-            double *ttm = ar.take<double>(Lt + 1);
-            if (!to || !tp || !ttm) return fail(ctx, CW_E_CUDA, "device arena exhausted (internal sizing error)");
-            CW_CK(ctx, cudaMemcpyAsync(to, R->traj_off + sh.a, (m + 1) * 8, cudaMemcpyHostToDevice, stream));
-            A.traj_off = to; A.traj_base = sh.ta; A.traj_total = Ltp;
-            A.traj_pos = tp; A.traj_vel = tp + 3 * Ltp; A.traj_t = R->traj_t ? ttm : nullptr;
-        }
-    } else {
-        A.w0 = B->w0; A.t1 = B->t1; A.t2 = B->t2; A.dt = B->dt; A.to_myr = B->to_myr; A.flags = B->grid_flags;
-        if (B->ev_off && K > 0) { A.ev_off = B->ev_off; A.ev_base = 0; A.ev_time = B->ev_time; A.ev_dv = B->ev_dv; }
-        int32_t *nn = ar.take<int32_t>(m), *es = ar.take<int32_t>(K + 1), *st = ar.take<int32_t>(m);
-        A.n_nodes = (R && R->n_nodes) ? R->n_nodes : nn;
-        A.ev_step = (R && R->ev_step) ? R->ev_step : es;
-        A.status = (R && R->status) ? R->status : st;
-        A.w_final = R ? R->w_final : nullptr;
-        if (store_all) {
-            A.traj_off = R->traj_off; A.traj_base = 0; A.traj_total = Lt;
-            A.traj_pos = R->traj_pos; A.traj_vel = R->traj_vel; A.traj_t = R->traj_t;
-        }
-    }
-    if (!A.ev_tk || !A.queue || !A.n_nodes || !A.ev_step || !A.status)
-        return fail(ctx, CW_E_CUDA, "device arena exhausted (internal sizing error)");
-    return CW_OK;
-}
-
-static int run_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, Plan &pl, bool integrate, bool store_all)
+// grid pre-pass, queue ordering and the integrator kernel of one shard / chunk, on pl.stream
+static int run_kernels(cw_ctx *ctx, Slot &s, const cw_opts *o, Plan &pl, bool integrate, bool store_all)
 {
     cudaStream_t stream = pl.stream;
     LaunchCfg cfg{s.sm_count, stream};
     IntegArgs &A = pl.A;
-    CW_CK(ctx, cudaMemsetAsync(A.queue, 0, 64, stream));
-    CW_CK(ctx, cudaEventRecord(pl.ev_t0, stream));
-    CW_CK(ctx, launch_grid_prepass(A, pl.sort ? pl.iota : nullptr, pl.sort ? pl.keys_in : nullptr, cfg));
-    ctx->last_launches += 1;
+    CW_SCK(s, cudaMemsetAsync(A.queue, 0, 64, stream));
+    CW_SCK(s, cudaEventRecord(pl.ev_t0, stream));
+    CW_SCK(s, launch_grid_prepass(A, pl.sort ? pl.iota : nullptr, pl.sort ? pl.keys_in : nullptr, cfg));
+    s.launches += 1;
     if (integrate) {
         if (pl.sort) {
             // Longest-processing-time-first queue.  Leapfrog: cost = node count.  DOP853: cost = node
@@ -679,251 +637,831 @@ static int run_shard(cw_ctx *ctx, Slot &s, const cw_opts *o, Plan &pl, bool inte
                 A.cost_key = pl.keys_in;
                 A.pilot_intervals = 16;
                 A.order = nullptr;
-                CW_CK(ctx, launch_dop853_pilot(ctx->pot, A, cfg));
-                ctx->last_launches += 1;
-                CW_CK(ctx, cudaMemsetAsync(A.queue, 0, 8, stream));
+                CW_SCK(s, launch_dop853_pilot(ctx->pot, A, cfg));
+                s.launches += 1;
+                CW_SCK(s, cudaMemsetAsync(A.queue, 0, 8, stream));
                 A.order = pl.order;
                 keys = pl.keys_in;
             }
-            CW_CK(ctx, cub::DeviceRadixSort::SortPairsDescending(pl.sort_tmp, pl.sort_bytes, keys,
-                                                                 pl.keys_out, (const int32_t *)pl.iota, A.order,
-                                                                 (int)A.n, 0, 32, stream));
+            CW_SCK(s, cub::DeviceRadixSort::SortPairsDescending(pl.sort_tmp, pl.sort_bytes, keys,
+                                                                pl.keys_out, (const int32_t *)pl.iota, A.order,
+                                                                (int)A.n, 0, 32, stream));
         }
-        CW_CK(ctx, cudaEventRecord(pl.ev_k0, stream));
-        if (o->integrator == CW_LEAPFROG) CW_CK(ctx, launch_leapfrog(ctx->pot, A, store_all, cfg));
-        else CW_CK(ctx, launch_dop853(ctx->pot, A, store_all, o->integrator == CW_DOP853_DENSE, cfg));
-        ctx->last_launches += 1;
-        CW_CK(ctx, cudaEventRecord(pl.ev_k1, stream));
+        CW_SCK(s, cudaEventRecord(pl.ev_k0, stream));
+        if (o->integrator == CW_LEAPFROG) CW_SCK(s, launch_leapfrog(ctx->pot, A, store_all, cfg));
+        else CW_SCK(s, launch_dop853(ctx->pot, A, store_all, o->integrator == CW_DOP853_DENSE, cfg));
+        s.launches += 1;
+        CW_SCK(s, cudaEventRecord(pl.ev_k1, stream));
         pl.timed = true;
         if (store_all && A.traj_t) {
-            CW_CK(ctx, launch_traj_times(A, cfg));
-            ctx->last_launches += 1;
+            CW_SCK(s, launch_traj_times(A, cfg));
+            s.launches += 1;
         }
     }
     return CW_OK;
 }
 
-static int validate(cw_ctx *ctx, const cw_opts *o, const cw_batch *B)
+static int validate(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, bool integrate)
 {
     if (!ctx || !o || !B) return CW_E_INVALID;
-    if (B->n_orbits < 0 || B->n_orbits > (int64_t)1 << 31) return fail(ctx, CW_E_INVALID, "n_orbits out of range");
-    if (B->n_orbits > 0 && (!B->w0 || !B->t1 || !B->t2 || !B->dt || !B->to_myr || !B->grid_flags))
-        return fail(ctx, CW_E_INVALID, "null input array");
+    if (B->n_orbits < 0 || B->n_orbits > (int64_t)INT32_MAX) return fail(ctx, CW_E_INVALID, "n_orbits out of range (at most 2^31 - 1 per call)");
     if (o->mem_space != CW_MEM_HOST && o->mem_space != CW_MEM_DEVICE) return fail(ctx, CW_E_INVALID, "bad mem_space");
+    const bool compact = B->n_w0 != 0 || B->w0_index || B->grid_class || B->classes || B->ev_off32;
+    if (compact && o->mem_space != CW_MEM_HOST)
+        return fail(ctx, CW_E_INVALID, "n_w0 / w0_index / grid_class / ev_off32 are CW_MEM_HOST forms");
+    if (B->n_orbits > 0) {
+        if (!B->t1 || (integrate && !B->w0)) return fail(ctx, CW_E_INVALID, "null input array");
+        if (B->grid_class) {
+            if (!B->classes || B->n_classes < 1 || B->n_classes > 256) return fail(ctx, CW_E_INVALID, "grid_class needs 1..256 classes");
+        } else if (!B->t2 || !B->dt || !B->to_myr || !B->grid_flags) {
+            return fail(ctx, CW_E_INVALID, "null input array");
+        }
+        if (B->n_w0 < 0 || B->n_w0 > B->n_orbits) return fail(ctx, CW_E_INVALID, "n_w0 out of range");
+        if (B->n_w0 > 0 && B->n_w0 < B->n_orbits && !B->w0_index) return fail(ctx, CW_E_INVALID, "n_w0 < n_orbits needs w0_index");
+        if (B->ev_off && B->ev_off32) return fail(ctx, CW_E_INVALID, "give ev_off or ev_off32, not both");
+    }
     if (o->integrator != CW_LEAPFROG && o->integrator != CW_DOP853 && o->integrator != CW_DOP853_DENSE) return fail(ctx, CW_E_UNSUPPORTED, "unknown integrator");
     if (ctx->slots.empty()) return fail(ctx, CW_E_NO_DEVICE, "context has no device");
     return CW_OK;
 }
 
-// read one int64 that may live on the device
-static int fetch_i64(cw_ctx *ctx, const int64_t *p, bool on_device, int64_t *out)
+// =============================================================================================
+// CW_MEM_DEVICE
+// =============================================================================================
+static int integrate_device(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, const cw_result *R, bool integrate,
+                            int32_t *n_nodes_out, int32_t *ev_step_out)
 {
-    if (!on_device) { *out = *p; return CW_OK; }
-    CW_CK(ctx, cudaMemcpy(out, p, 8, cudaMemcpyDeviceToHost));
+    const int64_t n = B->n_orbits;
+    const bool store_all = integrate && R->traj_off;
+    DeviceGuard guard;
+    Slot &s = ctx->slots[0];
+    s.error.clear();
+    s.launches = 0;
+    CW_CK(ctx, cudaSetDevice(s.dev));
+    int64_t K = 0, Lt = 0;
+    if (B->ev_off) CW_CK(ctx, cudaMemcpy(&K, B->ev_off + n, 8, cudaMemcpyDeviceToHost));
+    if (store_all) CW_CK(ctx, cudaMemcpy(&Lt, R->traj_off + n, 8, cudaMemcpyDeviceToHost));
+    if (K < 0 || Lt < 0) return fail(ctx, CW_E_INVALID, "offsets must be non-decreasing");
+    if (K > 0 && (!B->ev_time || !B->ev_dv)) return fail(ctx, CW_E_INVALID, "ev_off lists events but ev_time / ev_dv is null");
+
+    Plan pl;
+    pl.stream = o->stream ? (cudaStream_t)o->stream : s.lanes[0];
+    pl.sort = integrate && n >= SORT_THRESHOLD;
+    pl.sort_bytes = pl.sort ? sort_temp_bytes(n) : 0;
+    size_t need = 0;
+    auto add = [&](size_t count, size_t elt) { need += Arena::padded(count, elt); };
+    add(K + 1, 8);
+    add(n, 8);                                  // t_last
+    if (pl.sort) { add(n, 4); add(n, 4); add(n, 4); add(n, 4); add(pl.sort_bytes, 1); }
+    add(n, 4); add(K + 1, 4); add(n, 4);        // n_nodes / ev_step / status if the caller passed NULL
+    need += 4096;
+    // The scratch arena is the context's: a previous no_sync call may still be running on another stream.  Order
+    // this call behind it on the device (cheap), and wait on the host only when the buffers have to move.
+    if (s.has_pending) {
+        if (need > s.lane_arena[0].cap) CW_CK(ctx, cudaEventSynchronize(s.pending));
+        else CW_CK(ctx, cudaStreamWaitEvent(pl.stream, s.pending, 0));
+        s.has_pending = false;
+    }
+    if (need > s.lane_arena[0].cap) cudaStreamSynchronize(s.lanes[0]);
+    Arena &ar = s.lane_arena[0];
+    CW_CK(ctx, ar.reserve(need));
+    CW_CK(ctx, s.meta.reserve(4096));
+    CW_CK(ctx, s.ensure_events(3));
+    pl.ev_t0 = s.events[0]; pl.ev_k0 = s.events[1]; pl.ev_k1 = s.events[2];
+
+    IntegArgs &A = pl.A;
+    memset(&A, 0, sizeof A);
+    A.n = n;
+    A.atol = o->atol > 0 ? o->atol : 1e-10;
+    A.rtol = o->rtol > 0 ? o->rtol : 1e-10;
+    A.nmax = o->nmax;
+    A.ev_tk = ar.take<double>(K + 1);
+    if (integrate && o->integrator == CW_DOP853_DENSE) A.t_last = ar.take<double>(n);
+    unsigned long long *qs = s.meta.take<unsigned long long>(8);
+    A.queue = qs;
+    A.stats = qs + 1;
+    if (pl.sort) {
+        pl.iota = ar.take<int32_t>(n);
+        pl.keys_out = ar.take<int32_t>(n);
+        pl.keys_in = ar.take<int32_t>(n);
+        pl.order = ar.take<int32_t>(n);
+        A.order = pl.order;
+        pl.sort_tmp = ar.take<char>(pl.sort_bytes);
+    }
+    A.w0 = B->w0; A.t1 = B->t1; A.t2 = B->t2; A.dt = B->dt; A.to_myr = B->to_myr; A.flags = B->grid_flags;
+    if (B->ev_off && K > 0) { A.ev_off = B->ev_off; A.ev_base = 0; A.ev_time = B->ev_time; A.ev_dv = B->ev_dv; }
+    int32_t *nn = ar.take<int32_t>(n), *es = ar.take<int32_t>(K + 1), *st = ar.take<int32_t>(n);
+    int32_t *nn_user = integrate ? R->n_nodes : n_nodes_out, *es_user = integrate ? R->ev_step : ev_step_out;
+    A.n_nodes = nn_user ? nn_user : nn;
+    A.ev_step = es_user ? es_user : es;
+    A.status = (integrate && R->status) ? R->status : st;
+    A.w_final = integrate ? R->w_final : nullptr;
+    if (store_all) {
+        A.traj_off = R->traj_off; A.traj_base = 0; A.traj_total = Lt;
+        A.traj_pos = R->traj_pos; A.traj_vel = R->traj_vel; A.traj_t = R->traj_t;
+    }
+    if (!A.ev_tk || !A.queue || !A.n_nodes || !A.ev_step || !A.status)
+        return fail(ctx, CW_E_CUDA, "device arena exhausted (internal sizing error)");
+
+    int rc = run_kernels(ctx, s, o, pl, integrate, store_all);
+    ctx->last_launches = s.launches;
+    if (rc != CW_OK) { cudaStreamSynchronize(pl.stream); ctx->last_error = s.error; return rc; }
+    if (integrate && R->stats)
+        CW_CK(ctx, cudaMemcpyAsync(R->stats, A.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, pl.stream));
+    if (o->no_sync) {
+        CW_CK(ctx, cudaEventRecord(s.pending, pl.stream));
+        s.has_pending = true;
+        return CW_OK;
+    }
+    CW_CK(ctx, cudaStreamSynchronize(pl.stream));
+    if (pl.timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pl.ev_k0, pl.ev_k1) == cudaSuccess) s.last_kernel_ms += ms;
+        if (cudaEventElapsedTime(&ms, pl.ev_t0, pl.ev_k1) == cudaSuccess) s.last_total_ms += ms;
+    }
     return CW_OK;
 }
+
+// =============================================================================================
+// CW_MEM_HOST
+// =============================================================================================
+
+// expands the compact host forms (cw_batch ABI 2) of one chunk into the plain layout the kernels read
+struct UnpackArgs {
+    int64_t m1, m2, ua;
+    const double *u_w0, *u_t1;
+    const int32_t *u_idx;
+    const uint8_t *u_cls;
+    const cw_grid_class *u_ctab;
+    int32_t n_classes;
+    const void *u_off1, *u_off2;
+    int32_t off_is32, do_w0;
+    const int64_t *u_toff1, *u_toff2;
+    double *k_w0, *k_t1, *k_t2, *k_dt, *k_tm;
+    int32_t *k_fl;
+    int64_t *k_evoff, *k_toff;
+};
+
+__global__ void __launch_bounds__(256) unpack_chunk_kernel(const __grid_constant__ UnpackArgs U)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t m = U.m1 + U.m2;
+    if (i > m) return;
+    if (i < m) {
+        if (U.do_w0 || U.k_t1) {
+            int64_t j = i;
+            bool bad = false;
+            if (i >= U.m1) {
+                j = (int64_t)U.u_idx[i - U.m1] - U.ua;
+                bad = (j < 0 || j >= U.m1);        // not this chunk's source: the caller's w0_index is not sorted
+                if (bad) j = 0;
+            }
+            if (U.do_w0)
+                for (int c = 0; c < 6; c++) U.k_w0[c * m + i] = U.u_w0[c * U.m1 + j];
+            // a NaN start time makes the pre-pass reject the orbit (status CW_ORBIT_INCONSISTENT)
+            if (U.k_t1) U.k_t1[i] = bad ? __longlong_as_double(0x7ff8000000000000LL) : U.u_t1[j];
+        }
+        if (U.u_cls) {
+            const int c = U.u_cls[i];
+            const bool ok = c < U.n_classes;
+            const cw_grid_class g = U.u_ctab[ok ? c : 0];
+            U.k_t2[i] = g.t2;
+            U.k_dt[i] = ok ? g.dt : 0.0;           // dt = 0 is rejected by the pre-pass
+            U.k_tm[i] = g.to_myr;
+            U.k_fl[i] = g.grid_flags;
+        }
+    }
+    auto off_at = [&](const void *p, int64_t k) -> int64_t {
+        return U.off_is32 ? (int64_t)((const int32_t *)p)[k] : ((const int64_t *)p)[k];
+    };
+    if (U.k_evoff) {
+        int64_t v;
+        if (i <= U.m1) v = off_at(U.u_off1, i) - off_at(U.u_off1, 0);
+        else v = (off_at(U.u_off1, U.m1) - off_at(U.u_off1, 0)) + off_at(U.u_off2, i - U.m1) - off_at(U.u_off2, 0);
+        U.k_evoff[i] = v;
+    }
+    if (U.k_toff) {
+        int64_t v;
+        if (i <= U.m1) v = U.u_toff1[i] - U.u_toff1[0];
+        else v = (U.u_toff1[U.m1] - U.u_toff1[0]) + U.u_toff2[i - U.m1] - U.u_toff2[0];
+        U.k_toff[i] = v;
+    }
+}
+
+struct Seg {
+    size_t off = 0, bytes = 0;
+};
+
+// One unit of host-mode work: the sources [ua, ub) with the orbits that start from them -- the primaries [ua, ub) and
+// the secondaries n_src + [sa, sb) -- on one stream lane of one device slot.
+struct Chunk {
+    int slot = 0, lane = 0;
+    int64_t ua = 0, ub = 0, sa = 0, sb = 0, m1 = 0, m2 = 0, m = 0;
+    int64_t e1a = 0, K1 = 0, e2a = 0, K2 = 0, K = 0;      // event rows of the two orbit ranges
+    int64_t c1a = 0, L1 = 0, c2a = 0, L2 = 0, Lt = 0, Ltp = 0;   // trajectory columns
+    bool unpack = false, do_w0 = false;
+    // upload region (mirrored by the lane's stage_in buffer)
+    Seg u_w0, u_t1, u_idx, u_cls, u_ctab, u_t2, u_dt, u_tm, u_fl, u_off1, u_off2, u_evt, u_evd, u_toff1, u_toff2;
+    size_t up_bytes = 0;
+    // download region (mirrored by stage_out): results, then the trajectories
+    size_t down_off = 0, down_bytes = 0;
+    Seg d_wf, d_st, d_nn, d_es, d_tp, d_tt;
+    // device only
+    Seg k_w0, k_t1, k_grid, k_fl, k_evoff, k_toff, k_evtk, k_tlast, k_sort4, k_sorttmp;
+    size_t total_bytes = 0;
+    size_t sort_bytes = 0;
+    bool sort = false;
+    bool staged_in = false, staged_out = false;
+    // drain work: stage_out -> caller arrays, once d2h_done has fired
+    std::vector<CopyTask> drain;
+    cudaEvent_t d2h_done = nullptr;
+    bool drained = true;
+    Plan plan;
+};
+
+// resolved view of the caller's batch for a host-mode call
+struct HostCall {
+    cw_ctx *ctx = nullptr;
+    const cw_opts *o = nullptr;
+    const cw_batch *B = nullptr;
+    cw_result R;                      // outputs (n_nodes / ev_step of cw_count_nodes included)
+    bool integrate = false, store_all = false;
+    int64_t n = 0, n_src = 0, n_sec = 0;
+    const int32_t *idx = nullptr;
+    bool has_ev = false, want_ev = false, classes = false, off32 = false;
+    int64_t total_cols = 0;
+    // which caller arrays can be DMA-ed as they are (page-locked / registered); the others are staged
+    bool p_w0, p_t1, p_t2, p_dt, p_tm, p_fl, p_cls, p_ctab, p_idx, p_off, p_evt, p_evd, p_toff;
+    bool p_wf, p_st, p_nn, p_es, p_tp, p_tv, p_tt;
+
+    int64_t ev_at(int64_t i) const { return off32 ? (int64_t)B->ev_off32[i] : B->ev_off[i]; }
+    // number of secondaries whose source is < u
+    int64_t lb(int64_t u) const
+    {
+        if (!idx) return 0;
+        const int32_t key = (int32_t)std::min<int64_t>(u, INT32_MAX);
+        return (int64_t)(std::lower_bound(idx, idx + n_sec, key) - idx);
+    }
+    int64_t orbits_before(int64_t u) const { return u + lb(u); }
+    int64_t cols_before(int64_t u) const
+    {
+        return (R.traj_off[u] - R.traj_off[0]) + (R.traj_off[n_src + lb(u)] - R.traj_off[n_src]);
+    }
+};
+
+static inline size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
+
+// byte layout of a chunk in its lane's arena
+static void layout_chunk(const HostCall &H, Chunk &c)
+{
+    size_t cur = 0;
+    auto seg = [&](size_t bytes) { Seg s; s.off = cur; s.bytes = bytes; cur += pad256(bytes); return s; };
+    const size_t m = (size_t)c.m, m1 = (size_t)c.m1, m2 = (size_t)c.m2, K = (size_t)c.K;
+    const size_t osz = H.off32 ? 4 : 8;
+    c.unpack = (c.m2 > 0) || H.classes || (H.off32 && H.want_ev);
+    c.do_w0 = H.integrate && c.m2 > 0;
+    // ---- upload
+    if (H.integrate) c.u_w0 = seg(6 * m1 * 8);
+    c.u_t1 = seg(m1 * 8);
+    if (m2) c.u_idx = seg(m2 * 4);
+    if (H.classes) {
+        c.u_cls = seg(m);
+        c.u_ctab = seg((size_t)H.B->n_classes * sizeof(cw_grid_class));
+    } else {
+        c.u_t2 = seg(m * 8); c.u_dt = seg(m * 8); c.u_tm = seg(m * 8); c.u_fl = seg(m * 4);
+    }
+    if (H.want_ev && K > 0) {
+        c.u_off1 = seg((m1 + 1) * osz);
+        if (m2) c.u_off2 = seg((m2 + 1) * osz);
+        c.u_evt = seg(K * 8);
+        if (H.integrate) c.u_evd = seg(3 * K * 8);
+    }
+    if (H.store_all) {
+        c.u_toff1 = seg((m1 + 1) * 8);
+        if (m2) c.u_toff2 = seg((m2 + 1) * 8);
+    }
+    c.up_bytes = cur;
+    // ---- download
+    c.down_off = cur;
+    if (H.integrate) c.d_wf = seg(6 * m * 8);
+    c.d_st = seg(m * 4);
+    c.d_nn = seg(m * 4);
+    c.d_es = seg((K + 1) * 4);
+    if (H.store_all) {
+        c.d_tp = seg(6 * (size_t)c.Ltp * 8 + 256);
+        c.d_tt = seg(((size_t)c.Lt + 1) * 8);
+    }
+    c.down_bytes = cur - c.down_off;
+    // ---- device only
+    if (c.unpack) {
+        if (c.do_w0) { c.k_w0 = seg(6 * m * 8); c.k_t1 = seg(m * 8); }
+        if (H.classes) { c.k_grid = seg(3 * m * 8); c.k_fl = seg(m * 4); }
+        if (H.want_ev && K > 0) c.k_evoff = seg((m + 1) * 8);
+        if (H.store_all) c.k_toff = seg((m + 1) * 8);
+    }
+    c.k_evtk = seg((K + 1) * 8);
+    if (H.integrate && H.o->integrator == CW_DOP853_DENSE) c.k_tlast = seg(m * 8);
+    c.sort = H.integrate && c.m >= SORT_THRESHOLD;
+    c.sort_bytes = c.sort ? sort_temp_bytes(c.m) : 0;
+    if (c.sort) { c.k_sort4 = seg(4 * pad256(m * 4)); c.k_sorttmp = seg(c.sort_bytes); }
+    c.total_bytes = cur + 1024;
+}
+
+// cut the batch: by orbit count over the device slots, then into pipelined chunks
+static int make_chunks(HostCall &H, std::vector<Chunk> &chunks)
+{
+    cw_ctx *ctx = H.ctx;
+    const int64_t n = H.n;
+    const int nslots = (int)std::min<int64_t>((int64_t)ctx->slots.size(), std::max<int64_t>(1, n));
+    // first unit u >= lo with orbits_before(u) >= target
+    auto unit_for = [&](int64_t target, int64_t lo, int64_t hi) {
+        while (lo < hi) {
+            const int64_t mid = lo + (hi - lo) / 2;
+            if (H.orbits_before(mid) >= target) hi = mid; else lo = mid + 1;
+        }
+        return lo;
+    };
+    const bool traj_staged = H.store_all && !(H.p_tp && H.p_tv && (!H.R.traj_t || H.p_tt));
+    const int64_t col_lim = traj_shard_cols(traj_staged);
+    int64_t u_prev = 0;
+    for (int d = 0; d < nslots; d++) {
+        const int64_t u_lo = u_prev;
+        const int64_t u_hi = (d + 1 == nslots) ? H.n_src : unit_for(n * (d + 1) / nslots, u_lo, H.n_src);
+        u_prev = u_hi;
+        if (u_hi <= u_lo) continue;
+        const int64_t base = H.orbits_before(u_lo);
+        const int64_t M = H.orbits_before(u_hi) - base;
+        // DOPRI853 runs are bound by their most expensive orbits, not by the copies (10^6 orbits: 2.4 ms of H2D
+        // against 150 ms of kernel): cutting them into chunks would multiply the pilot launches and the tails
+        // (measured 3.5e9 vs 6.2e9 intervals/s end to end), so they go to the device in one piece.
+        const bool pipelined = !H.integrate || H.o->integrator == CW_LEAPFROG;
+        int64_t Q = 0;
+        if (pipelined && H.integrate && !H.store_all) {
+            cudaSetDevice(ctx->slots[d].dev);
+            Q = leapfrog_lane_capacity(ctx->pot, ctx->slots[d].sm_count);
+            // only batches of several waves: a batch of one or two (10^5 binaries with their own horizons, config 2)
+            // pipelines better in the finer chunks -- measured 1.34e11 against 0.90e11 steps/s end to end
+            if (getenv("CW_NO_WAVE_CHUNKS") || M < 4 * Q) Q = 0;
+        }
+        const std::vector<int64_t> sizes = chunk_sizes(M, pipelined, Q);
+        int lane = 0;
+        int64_t u = u_lo, cum = 0;
+        for (size_t k = 0; k < sizes.size() && u < u_hi; k++) {
+            cum += sizes[k];
+            int64_t ue = (k + 1 == sizes.size()) ? u_hi : unit_for(base + cum, u + 1, u_hi);
+            while (u < ue) {
+                int64_t e1 = ue;
+                if (H.store_all) {
+                    // a chunk's trajectories live in its lane's buffer: also cut by trajectory COLUMNS; with the lane
+                    // buffers re-used this bounds device memory however long the orbits are
+                    const int64_t c0 = H.cols_before(u);
+                    int64_t lo = u + 1, hi = ue;       // largest e in [u+1, ue] with cols <= limit (at least u+1)
+                    while (lo < hi) {
+                        const int64_t mid = lo + (hi - lo + 1) / 2;
+                        if (H.cols_before(mid) - c0 <= col_lim) lo = mid; else hi = mid - 1;
+                    }
+                    e1 = lo;
+                }
+                Chunk c;
+                c.slot = d;
+                c.lane = lane++ % Slot::N_LANES;
+                c.ua = u; c.ub = e1;
+                c.sa = H.lb(u); c.sb = H.lb(e1);
+                c.m1 = c.ub - c.ua; c.m2 = c.sb - c.sa; c.m = c.m1 + c.m2;
+                if (H.has_ev) {
+                    c.e1a = H.ev_at(c.ua); c.K1 = H.ev_at(c.ub) - c.e1a;
+                    c.e2a = H.ev_at(H.n_src + c.sa); c.K2 = H.ev_at(H.n_src + c.sb) - c.e2a;
+                    if (c.K1 < 0 || c.K2 < 0) return fail(ctx, CW_E_INVALID, "offsets must be non-decreasing");
+                    c.K = H.want_ev ? c.K1 + c.K2 : 0;
+                    if (!H.want_ev) c.K1 = c.K2 = 0;
+                }
+                if (H.store_all) {
+                    const int64_t *to = H.R.traj_off;
+                    c.c1a = to[c.ua]; c.L1 = to[c.ub] - c.c1a;
+                    c.c2a = to[H.n_src + c.sa]; c.L2 = to[H.n_src + c.sb] - c.c2a;
+                    if (c.L1 < 0 || c.L2 < 0) return fail(ctx, CW_E_INVALID, "offsets must be non-decreasing");
+                    c.Lt = c.L1 + c.L2;
+                    // device rows are padded to a multiple of 16 columns so every row starts 128-byte aligned
+                    c.Ltp = (c.Lt + 15) & ~int64_t(15);
+                }
+                layout_chunk(H, c);
+                chunks.push_back(std::move(c));
+                u = e1;
+            }
+        }
+    }
+    return CW_OK;
+}
+
+// stage_out -> caller arrays of a chunk whose D2H has completed
+static int drain_chunk(Slot &s, Chunk &c)
+{
+    if (c.drained) return CW_OK;
+    CW_SCK(s, cudaEventSynchronize(c.d2h_done));
+    HostPool::get().run(c.drain);
+    c.drain.clear();
+    c.drained = true;
+    return CW_OK;
+}
+
+// Everything one chunk needs, enqueued on its lane's stream: uploads (direct or staged), unpack, kernels, downloads.
+static int process_chunk(HostCall &H, Slot &s, Chunk &c)
+{
+    cw_ctx *ctx = H.ctx;
+    const cw_batch *B = H.B;
+    const cw_result &R = H.R;
+    const int64_t n = H.n, ns = H.n_src;
+    cudaStream_t stream = s.lanes[c.lane];
+    Arena &ar = s.lane_arena[c.lane];
+    char *dev = ar.base;
+    char *sin = (char *)s.stage_in[c.lane];
+    char *sout = (char *)s.stage_out[c.lane];
+    const int64_t m = c.m, m1 = c.m1, m2 = c.m2;
+    const size_t osz = H.off32 ? 4 : 8;
+
+    // ---- uploads
+    std::vector<CopyTask> tasks;
+    std::vector<std::pair<size_t, size_t>> staged;        // (offset, bytes) runs to DMA from the staging buffer
+    auto up = [&](const Seg &sg, size_t sub, const void *user, size_t bytes, bool dma) -> cudaError_t {
+        if (bytes == 0) return cudaSuccess;
+        if (dma) return cudaMemcpyAsync(dev + sg.off + sub, user, bytes, cudaMemcpyHostToDevice, stream);
+        tasks.push_back(CopyTask{sin + sg.off + sub, user, bytes});
+        if (!staged.empty() && staged.back().first + pad256(staged.back().second) >= sg.off + sub &&
+            staged.back().first <= sg.off + sub)
+            staged.back().second = sg.off + sub + bytes - staged.back().first;     // adjacent: one DMA for both
+        else
+            staged.push_back({sg.off + sub, bytes});
+        return cudaSuccess;
+    };
+    if (H.integrate)
+        for (int r = 0; r < 6; r++) CW_SCK(s, up(c.u_w0, (size_t)r * m1 * 8, B->w0 + (size_t)r * ns + c.ua, m1 * 8, H.p_w0));
+    CW_SCK(s, up(c.u_t1, 0, B->t1 + c.ua, m1 * 8, H.p_t1));
+    if (m2) CW_SCK(s, up(c.u_idx, 0, H.idx + c.sa, m2 * 4, H.p_idx));
+    if (H.classes) {
+        CW_SCK(s, up(c.u_cls, 0, B->grid_class + c.ua, m1, H.p_cls));
+        CW_SCK(s, up(c.u_cls, m1, B->grid_class + ns + c.sa, m2, H.p_cls));
+        CW_SCK(s, up(c.u_ctab, 0, B->classes, (size_t)B->n_classes * sizeof(cw_grid_class), H.p_ctab));
+    } else {
+        CW_SCK(s, up(c.u_t2, 0, B->t2 + c.ua, m1 * 8, H.p_t2));
+        CW_SCK(s, up(c.u_t2, m1 * 8, B->t2 + ns + c.sa, m2 * 8, H.p_t2));
+        CW_SCK(s, up(c.u_dt, 0, B->dt + c.ua, m1 * 8, H.p_dt));
+        CW_SCK(s, up(c.u_dt, m1 * 8, B->dt + ns + c.sa, m2 * 8, H.p_dt));
+        CW_SCK(s, up(c.u_tm, 0, B->to_myr + c.ua, m1 * 8, H.p_tm));
+        CW_SCK(s, up(c.u_tm, m1 * 8, B->to_myr + ns + c.sa, m2 * 8, H.p_tm));
+        CW_SCK(s, up(c.u_fl, 0, B->grid_flags + c.ua, m1 * 4, H.p_fl));
+        CW_SCK(s, up(c.u_fl, m1 * 4, B->grid_flags + ns + c.sa, m2 * 4, H.p_fl));
+    }
+    if (H.want_ev && c.K > 0) {
+        const char *off = H.off32 ? (const char *)B->ev_off32 : (const char *)B->ev_off;
+        CW_SCK(s, up(c.u_off1, 0, off + (size_t)c.ua * osz, (m1 + 1) * osz, H.p_off));
+        if (m2) CW_SCK(s, up(c.u_off2, 0, off + (size_t)(ns + c.sa) * osz, (m2 + 1) * osz, H.p_off));
+        CW_SCK(s, up(c.u_evt, 0, B->ev_time + c.e1a, c.K1 * 8, H.p_evt));
+        CW_SCK(s, up(c.u_evt, c.K1 * 8, B->ev_time + c.e2a, c.K2 * 8, H.p_evt));
+        if (H.integrate) {
+            CW_SCK(s, up(c.u_evd, 0, B->ev_dv + 3 * c.e1a, 3 * c.K1 * 8, H.p_evd));
+            CW_SCK(s, up(c.u_evd, 3 * c.K1 * 8, B->ev_dv + 3 * c.e2a, 3 * c.K2 * 8, H.p_evd));
+        }
+    }
+    if (H.store_all) {
+        CW_SCK(s, up(c.u_toff1, 0, R.traj_off + c.ua, (m1 + 1) * 8, H.p_toff));
+        if (m2) CW_SCK(s, up(c.u_toff2, 0, R.traj_off + ns + c.sa, (m2 + 1) * 8, H.p_toff));
+    }
+    if (!tasks.empty()) {
+        // the lane's staging buffer is free once the previous chunk's DMA out of it has completed
+        if (s.h2d_pending[c.lane]) CW_SCK(s, cudaEventSynchronize(s.h2d_done[c.lane]));
+        HostPool::get().run(tasks);
+        for (const auto &run : staged)
+            CW_SCK(s, cudaMemcpyAsync(dev + run.first, sin + run.first, run.second, cudaMemcpyHostToDevice, stream));
+        CW_SCK(s, cudaEventRecord(s.h2d_done[c.lane], stream));
+        s.h2d_pending[c.lane] = true;
+    }
+
+    // ---- kernel arguments
+    Plan &pl = c.plan;
+    pl.stream = stream;
+    pl.sort = c.sort;
+    pl.sort_bytes = c.sort_bytes;
+    IntegArgs &A = pl.A;
+    memset(&A, 0, sizeof A);
+    A.n = m;
+    A.atol = H.o->atol > 0 ? H.o->atol : 1e-10;
+    A.rtol = H.o->rtol > 0 ? H.o->rtol : 1e-10;
+    A.nmax = H.o->nmax;
+    auto D = [&](const Seg &sg) { return dev + sg.off; };
+    A.ev_tk = (double *)D(c.k_evtk);
+    if (c.k_tlast.bytes) A.t_last = (double *)D(c.k_tlast);
+    if (c.sort) {
+        const size_t stride = pad256((size_t)m * 4);
+        pl.iota = (int32_t *)D(c.k_sort4);
+        pl.keys_out = (int32_t *)(D(c.k_sort4) + stride);
+        pl.keys_in = (int32_t *)(D(c.k_sort4) + 2 * stride);
+        pl.order = (int32_t *)(D(c.k_sort4) + 3 * stride);
+        A.order = pl.order;
+        pl.sort_tmp = D(c.k_sorttmp);
+    }
+    A.w0 = (const double *)(c.do_w0 ? D(c.k_w0) : D(c.u_w0));
+    A.t1 = (const double *)(c.do_w0 ? D(c.k_t1) : D(c.u_t1));
+    if (H.classes) {
+        double *g = (double *)D(c.k_grid);
+        A.t2 = g; A.dt = g + m; A.to_myr = g + 2 * m; A.flags = (const int32_t *)D(c.k_fl);
+    } else {
+        A.t2 = (const double *)D(c.u_t2); A.dt = (const double *)D(c.u_dt);
+        A.to_myr = (const double *)D(c.u_tm); A.flags = (const int32_t *)D(c.u_fl);
+    }
+    if (H.want_ev && c.K > 0) {
+        A.ev_time = (const double *)D(c.u_evt);
+        A.ev_dv = H.integrate ? (const double *)D(c.u_evd) : nullptr;
+        if (c.unpack) { A.ev_off = (const int64_t *)D(c.k_evoff); A.ev_base = 0; }
+        else { A.ev_off = (const int64_t *)D(c.u_off1); A.ev_base = c.e1a; }
+    }
+    A.w_final = H.integrate ? (double *)D(c.d_wf) : nullptr;
+    A.status = (int32_t *)D(c.d_st);
+    A.n_nodes = (int32_t *)D(c.d_nn);
+    A.ev_step = (int32_t *)D(c.d_es);
+    if (H.store_all) {
+        double *tp = (double *)D(c.d_tp);
+        A.traj_total = c.Ltp;
+        A.traj_pos = tp; A.traj_vel = tp + 3 * c.Ltp;
+        A.traj_t = R.traj_t ? (double *)D(c.d_tt) : nullptr;
+        if (c.unpack) { A.traj_off = (const int64_t *)D(c.k_toff); A.traj_base = 0; }
+        else { A.traj_off = (const int64_t *)D(c.u_toff1); A.traj_base = c.c1a; }
+    }
+    unsigned long long *qs = s.meta.take<unsigned long long>(8);
+    if (!qs) return slot_fail(s, CW_E_CUDA, "device arena exhausted (internal sizing error)");
+    A.queue = qs;
+    A.stats = qs + 1;
+
+    if (c.unpack) {
+        UnpackArgs U;
+        memset(&U, 0, sizeof U);
+        U.m1 = m1; U.m2 = m2; U.ua = c.ua;
+        U.u_w0 = (const double *)D(c.u_w0); U.u_t1 = (const double *)D(c.u_t1);
+        U.u_idx = (const int32_t *)D(c.u_idx);
+        U.do_w0 = c.do_w0 ? 1 : 0;
+        if (c.do_w0) { U.k_w0 = (double *)D(c.k_w0); U.k_t1 = (double *)D(c.k_t1); }
+        if (H.classes) {
+            U.u_cls = (const uint8_t *)D(c.u_cls);
+            U.u_ctab = (const cw_grid_class *)D(c.u_ctab);
+            U.n_classes = B->n_classes;
+            double *g = (double *)D(c.k_grid);
+            U.k_t2 = g; U.k_dt = g + m; U.k_tm = g + 2 * m; U.k_fl = (int32_t *)D(c.k_fl);
+        }
+        if (H.want_ev && c.K > 0) {
+            U.u_off1 = D(c.u_off1); U.u_off2 = D(c.u_off2); U.off_is32 = H.off32 ? 1 : 0;
+            U.k_evoff = (int64_t *)D(c.k_evoff);
+        }
+        if (H.store_all) {
+            U.u_toff1 = (const int64_t *)D(c.u_toff1); U.u_toff2 = (const int64_t *)D(c.u_toff2);
+            U.k_toff = (int64_t *)D(c.k_toff);
+        }
+        unpack_chunk_kernel<<<(unsigned)((m + 1 + 255) / 256), 256, 0, stream>>>(U);
+        CW_SCK(s, cudaGetLastError());
+        s.launches += 1;
+    }
+    int rc = run_kernels(ctx, s, H.o, pl, H.integrate, H.store_all);
+    if (rc != CW_OK) return rc;
+
+    // ---- downloads: page-locked destinations directly, pageable ones through the lane's stage_out buffer
+    std::vector<std::pair<size_t, size_t>> sruns;        // (offset within the download region, bytes)
+    c.drain.clear();
+    auto down = [&](const Seg &sg, size_t sub, void *user, size_t bytes, bool dma) -> cudaError_t {
+        if (bytes == 0 || !user) return cudaSuccess;
+        if (dma) return cudaMemcpyAsync(user, dev + sg.off + sub, bytes, cudaMemcpyDeviceToHost, stream);
+        const size_t rel = sg.off + sub - c.down_off;
+        c.drain.push_back(CopyTask{user, sout + rel, bytes});
+        if (!sruns.empty() && sruns.back().first + pad256(sruns.back().second) >= rel && sruns.back().first <= rel)
+            sruns.back().second = rel + bytes - sruns.back().first;
+        else
+            sruns.push_back({rel, bytes});
+        return cudaSuccess;
+    };
+    if (H.integrate) {
+        for (int r = 0; r < 6; r++) {
+            CW_SCK(s, down(c.d_wf, (size_t)r * m * 8, R.w_final + (size_t)r * n + c.ua, m1 * 8, H.p_wf));
+            CW_SCK(s, down(c.d_wf, ((size_t)r * m + m1) * 8, R.w_final + (size_t)r * n + ns + c.sa, m2 * 8, H.p_wf));
+        }
+        CW_SCK(s, down(c.d_st, 0, R.status + c.ua, m1 * 4, H.p_st));
+        CW_SCK(s, down(c.d_st, m1 * 4, R.status + ns + c.sa, m2 * 4, H.p_st));
+    }
+    if (R.n_nodes) {
+        CW_SCK(s, down(c.d_nn, 0, R.n_nodes + c.ua, m1 * 4, H.p_nn));
+        CW_SCK(s, down(c.d_nn, m1 * 4, R.n_nodes + ns + c.sa, m2 * 4, H.p_nn));
+    }
+    if (R.ev_step && H.want_ev && c.K > 0) {
+        CW_SCK(s, down(c.d_es, 0, R.ev_step + c.e1a, c.K1 * 4, H.p_es));
+        CW_SCK(s, down(c.d_es, c.K1 * 4, R.ev_step + c.e2a, c.K2 * 4, H.p_es));
+    }
+    if (H.store_all && c.Lt > 0) {
+        const size_t tc = (size_t)H.total_cols;
+        for (int r = 0; r < 3; r++) {
+            CW_SCK(s, down(c.d_tp, (size_t)r * c.Ltp * 8, R.traj_pos + r * tc + c.c1a, c.L1 * 8, H.p_tp));
+            CW_SCK(s, down(c.d_tp, ((size_t)r * c.Ltp + c.L1) * 8, R.traj_pos + r * tc + c.c2a, c.L2 * 8, H.p_tp));
+            CW_SCK(s, down(c.d_tp, (size_t)(3 + r) * c.Ltp * 8, R.traj_vel + r * tc + c.c1a, c.L1 * 8, H.p_tv));
+            CW_SCK(s, down(c.d_tp, ((size_t)(3 + r) * c.Ltp + c.L1) * 8, R.traj_vel + r * tc + c.c2a, c.L2 * 8, H.p_tv));
+        }
+        if (R.traj_t) {
+            CW_SCK(s, down(c.d_tt, 0, R.traj_t + c.c1a, c.L1 * 8, H.p_tt));
+            CW_SCK(s, down(c.d_tt, c.L1 * 8, R.traj_t + c.c2a, c.L2 * 8, H.p_tt));
+        }
+    }
+    if (!c.drain.empty()) {
+        for (const auto &run : sruns)
+            CW_SCK(s, cudaMemcpyAsync(sout + run.first, dev + c.down_off + run.first, run.second, cudaMemcpyDeviceToHost, stream));
+        CW_SCK(s, cudaEventRecord(c.d2h_done, stream));
+        c.drained = false;
+    }
+    return CW_OK;
+}
+
+// all chunks of one device slot, in order, on the calling thread
+static int run_slot_host(HostCall &H, int d, std::vector<Chunk *> &mine)
+{
+    cw_ctx *ctx = H.ctx;
+    Slot &s = ctx->slots[d];
+    s.error.clear();
+    s.launches = 0;
+    if (mine.empty()) return CW_OK;
+    CW_SCK(s, cudaSetDevice(s.dev));
+    // ---- size and reserve the lane arenas and staging buffers once, for all chunks of the call
+    size_t need[Slot::N_LANES] = {0, 0, 0}, need_in[Slot::N_LANES] = {0, 0, 0}, need_out[Slot::N_LANES] = {0, 0, 0};
+    const bool any_in_staged = !(H.p_w0 && H.p_t1 && H.p_t2 && H.p_dt && H.p_tm && H.p_fl && H.p_cls && H.p_ctab &&
+                                 H.p_idx && H.p_off && H.p_evt && H.p_evd && H.p_toff);
+    const bool any_out_staged = !(H.p_wf && H.p_st && H.p_nn && H.p_es && H.p_tp && H.p_tv && H.p_tt);
+    for (Chunk *c : mine) {
+        need[c->lane] = std::max(need[c->lane], c->total_bytes);
+        if (any_in_staged) need_in[c->lane] = std::max(need_in[c->lane], c->up_bytes);
+        if (any_out_staged) need_out[c->lane] = std::max(need_out[c->lane], c->down_bytes);
+    }
+    for (int l = 0; l < Slot::N_LANES; l++) {
+        if (need[l] == 0) continue;
+        if (need[l] + 4096 > s.lane_arena[l].cap) cudaStreamSynchronize(s.lanes[l]);
+        CW_SCK(s, s.lane_arena[l].reserve(need[l] + 4096));
+        if (need_in[l] > s.stage_in_cap[l]) {
+            pinned_free(s.stage_in[l]);
+            s.stage_in[l] = pinned_alloc(need_in[l] + need_in[l] / 8);
+            s.stage_in_cap[l] = s.stage_in[l] ? need_in[l] + need_in[l] / 8 : 0;
+            if (!s.stage_in[l]) return slot_fail(s, CW_E_CUDA, "cannot allocate the page-locked staging buffer (inputs)");
+        }
+        if (need_out[l] > s.stage_out_cap[l]) {
+            pinned_free(s.stage_out[l]);
+            s.stage_out[l] = pinned_alloc(need_out[l] + need_out[l] / 8);
+            s.stage_out_cap[l] = s.stage_out[l] ? need_out[l] + need_out[l] / 8 : 0;
+            if (!s.stage_out[l]) return slot_fail(s, CW_E_CUDA, "cannot allocate the page-locked staging buffer (outputs)");
+        }
+        s.h2d_pending[l] = false;
+    }
+    const size_t meta_need = Arena::padded(8, 8) * mine.size() + 4096;
+    if (meta_need > s.meta.cap)
+        for (int l = 0; l < Slot::N_LANES; l++) cudaStreamSynchronize(s.lanes[l]);
+    CW_SCK(s, s.meta.reserve(meta_need));
+    CW_SCK(s, s.ensure_events(4 * mine.size()));
+    // ---- enqueue chunk after chunk; a chunk re-uses the buffers of the one three places back, which must have been
+    // drained by then
+    int rc = CW_OK;
+    for (size_t k = 0; k < mine.size() && rc == CW_OK; k++) {
+        Chunk &c = *mine[k];
+        c.plan.ev_t0 = s.events[4 * k]; c.plan.ev_k0 = s.events[4 * k + 1]; c.plan.ev_k1 = s.events[4 * k + 2];
+        c.d2h_done = s.events[4 * k + 3];
+        if (k >= (size_t)Slot::N_LANES) rc = drain_chunk(s, *mine[k - Slot::N_LANES]);
+        // ... and whatever else has already arrived (keeps the tail short)
+        for (size_t j = 0; j < k && rc == CW_OK; j++)
+            if (!mine[j]->drained && cudaEventQuery(mine[j]->d2h_done) == cudaSuccess) rc = drain_chunk(s, *mine[j]);
+        if (rc == CW_OK) rc = process_chunk(H, s, c);
+    }
+    for (size_t k = 0; k < mine.size() && rc == CW_OK; k++) rc = drain_chunk(s, *mine[k]);
+    // ---- wait for the lanes (also on failure: nothing may still be reading or writing caller memory on return)
+    for (int l = 0; l < Slot::N_LANES; l++) {
+        const cudaError_t e = cudaStreamSynchronize(s.lanes[l]);
+        if (e != cudaSuccess && rc == CW_OK) {
+            s.error = std::string("cudaStreamSynchronize failed: ") + cudaGetErrorString(e);
+            rc = CW_E_CUDA;
+        }
+    }
+    cudaGetLastError();
+    return rc;
+}
+
+static int integrate_host(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, const cw_result *R, bool integrate,
+                          int32_t *n_nodes_out, int32_t *ev_step_out)
+{
+    HostCall H;
+    H.ctx = ctx; H.o = o; H.B = B;
+    memset(&H.R, 0, sizeof H.R);
+    if (R) H.R = *R;
+    if (!integrate) { H.R.n_nodes = n_nodes_out; H.R.ev_step = ev_step_out; }
+    H.integrate = integrate;
+    H.store_all = integrate && R->traj_off;
+    H.n = B->n_orbits;
+    H.n_src = (B->n_w0 > 0) ? B->n_w0 : H.n;
+    H.n_sec = H.n - H.n_src;
+    H.idx = H.n_sec > 0 ? B->w0_index : nullptr;
+    if (!integrate && H.n_sec > 0) return fail(ctx, CW_E_UNSUPPORTED, "cw_count_nodes does not take w0_index (pass the plain t1 column)");
+    H.off32 = B->ev_off32 != nullptr;
+    H.has_ev = (B->ev_off || B->ev_off32) && H.ev_at(H.n) > 0;
+    H.want_ev = H.has_ev && (integrate || ev_step_out);
+    if (H.has_ev && H.want_ev && (!B->ev_time || (integrate && !B->ev_dv)))
+        return fail(ctx, CW_E_INVALID, "ev_off lists events but ev_time / ev_dv is null");
+    H.classes = B->grid_class != nullptr;
+    H.total_cols = H.store_all ? R->traj_off[H.n] : 0;
+    if (H.n_sec > 0) {
+        // cheap end checks; an unsorted index is caught per orbit by the unpack kernel (status CW_ORBIT_INCONSISTENT)
+        if (H.n_src < 1 || H.idx[0] < 0 || H.idx[H.n_sec - 1] >= H.n_src || H.idx[0] > H.idx[H.n_sec - 1])
+            return fail(ctx, CW_E_INVALID, "w0_index must be non-decreasing with entries in [0, n_w0)");
+    }
+    auto pin = [](const void *p) { return pointer_is_dma_able(p); };
+    const bool force_stage = getenv("CW_FORCE_STAGING") != nullptr;     // test hook: treat every array as pageable
+    auto P = [&](const void *p) { return !force_stage && pin(p); };
+    H.p_w0 = P(B->w0); H.p_t1 = P(B->t1); H.p_t2 = P(B->t2); H.p_dt = P(B->dt); H.p_tm = P(B->to_myr);
+    H.p_fl = P(B->grid_flags); H.p_cls = P(B->grid_class); H.p_ctab = P(B->classes); H.p_idx = P(H.idx);
+    H.p_off = P(H.off32 ? (const void *)B->ev_off32 : (const void *)B->ev_off);
+    H.p_evt = P(B->ev_time); H.p_evd = P(B->ev_dv); H.p_toff = P(H.R.traj_off);
+    H.p_wf = P(H.R.w_final); H.p_st = P(H.R.status); H.p_nn = P(H.R.n_nodes); H.p_es = P(H.R.ev_step);
+    H.p_tp = P(H.R.traj_pos); H.p_tv = P(H.R.traj_vel); H.p_tt = P(H.R.traj_t);
+
+    DeviceGuard guard;
+    std::vector<Chunk> chunks;
+    int rc = make_chunks(H, chunks);
+    if (rc != CW_OK) return rc;
+    const int nslots = (int)ctx->slots.size();
+    std::vector<std::vector<Chunk *>> per_slot(nslots);
+    for (Chunk &c : chunks) per_slot[c.slot].push_back(&c);
+    // a device-mode call left running (no_sync) must not see its scratch move
+    if (ctx->slots[0].has_pending) {
+        cudaSetDevice(ctx->slots[0].dev);
+        cudaEventSynchronize(ctx->slots[0].pending);
+        ctx->slots[0].has_pending = false;
+    }
+    // ---- one host thread per device slot; the caller's thread takes the first busy slot
+    std::vector<int> rcs(nslots, CW_OK);
+    std::vector<std::thread> workers;
+    int first = -1;
+    for (int d = 0; d < nslots; d++) {
+        if (per_slot[d].empty()) continue;
+        if (first < 0) { first = d; continue; }
+        workers.emplace_back([&, d] { rcs[d] = run_slot_host(H, d, per_slot[d]); });
+    }
+    if (first >= 0) rcs[first] = run_slot_host(H, first, per_slot[first]);
+    for (std::thread &t : workers) t.join();
+    ctx->last_launches = 0;
+    for (int d = 0; d < nslots; d++) {
+        ctx->last_launches += ctx->slots[d].launches;
+        if (rcs[d] != CW_OK && rc == CW_OK) { rc = rcs[d]; ctx->last_error = ctx->slots[d].error; }
+    }
+    if (rc != CW_OK) return rc;
+    // ---- statistics and kernel times
+    int64_t stats[4] = {0, 0, 0, 0};
+    for (int d = 0; d < nslots; d++) {
+        if (per_slot[d].empty()) continue;
+        Slot &s = ctx->slots[d];
+        cudaSetDevice(s.dev);
+        const size_t mstride = Arena::padded(8, 8) / 8;       // one padded block of 8 counters per chunk
+        std::vector<unsigned long long> hs(mstride * per_slot[d].size(), 0ull);
+        if (integrate && R->stats)
+            CW_CK(ctx, cudaMemcpy(hs.data(), s.meta.base, hs.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < per_slot[d].size(); k++) {
+            const Plan &pl = per_slot[d][k]->plan;
+            for (int q = 0; q < 4; q++) stats[q] += (int64_t)hs[mstride * k + 1 + q];
+            if (pl.timed) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, pl.ev_k0, pl.ev_k1) == cudaSuccess) s.last_kernel_ms += ms;
+                if (cudaEventElapsedTime(&ms, pl.ev_t0, pl.ev_k1) == cudaSuccess) s.last_total_ms += ms;
+            }
+        }
+    }
+    if (getenv("CW_DEBUG") && first >= 0 && per_slot[first][0]->plan.timed) {
+        // chunk timeline relative to the first chunk's first kernel: pre-pass start, integrator start / end
+        const Plan &p0 = per_slot[first][0]->plan;
+        cudaSetDevice(ctx->slots[first].dev);
+        for (size_t k = 0; k < per_slot[first].size(); k++) {
+            const Chunk &c = *per_slot[first][k];
+            if (!c.plan.timed) continue;
+            float a = 0.f, b = 0.f, e = 0.f;
+            cudaEventElapsedTime(&a, p0.ev_t0, c.plan.ev_t0);
+            cudaEventElapsedTime(&b, p0.ev_t0, c.plan.ev_k0);
+            cudaEventElapsedTime(&e, p0.ev_t0, c.plan.ev_k1);
+            fprintf(stderr, "[cw] chunk %2zu lane %d orbits %8lld (+%lld): prepass %8.3f  kernel %8.3f .. %8.3f ms\n", k,
+                    c.lane, (long long)c.m1, (long long)c.m2, a, b, e);
+        }
+    }
+    if (integrate && R->stats) memcpy(R->stats, stats, sizeof stats);
+    return CW_OK;
+}
+
+} // namespace
 
 static int integrate_impl(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, const cw_result *R, bool integrate,
                           int32_t *n_nodes_out, int32_t *ev_step_out)
 {
-    int rc = validate(ctx, o, B);
+    int rc = validate(ctx, o, B, integrate);
     if (rc != CW_OK) return rc;
     if (integrate && !ctx->has_pot) return fail(ctx, CW_E_NO_POTENTIAL, "cw_set_potential has not been called");
     if (integrate && (!R || !R->w_final || !R->status)) return fail(ctx, CW_E_INVALID, "w_final and status are required");
     ctx->last_launches = 0;
     for (Slot &s : ctx->slots) { s.last_kernel_ms = s.last_total_ms = 0.0; }
-    const int64_t n = B->n_orbits;
-    if (n == 0) return CW_OK;
-    const bool dev_mode = o->mem_space == CW_MEM_DEVICE;
-    const bool store_all = integrate && R->traj_off;
-    if (store_all && (!R->traj_pos || !R->traj_vel)) return fail(ctx, CW_E_INVALID, "traj_pos / traj_vel missing");
-
-    DeviceGuard guard;
-    const int prev = guard.prev;
-    // ---- cut the batch: by index over the device slots, then (host buffers) into pipelined chunks
-    const int nslots = dev_mode ? 1 : (int)std::min<int64_t>((int64_t)ctx->slots.size(), std::max<int64_t>(1, n));
-    std::vector<Shard> shards;
-    for (int d = 0; d < nslots; d++) {
-        const int64_t a = n * d / nslots, b = n * (d + 1) / nslots;
-        // DOPRI853 runs are bound by their most expensive orbits, not by the copies (10^6 orbits: 2.4 ms of H2D
-        // against 150 ms of kernel): cutting them into chunks would multiply the pilot launches and the tails
-        // (measured 3.5e9 vs 6.2e9 intervals/s end to end), so they go to the device in one piece.
-        const bool pipelined = !dev_mode && (!integrate || o->integrator == CW_LEAPFROG);
-        int64_t Q = 0;
-        if (pipelined && integrate && !store_all) {
-            int prev_dev = 0;
-            cudaGetDevice(&prev_dev);
-            cudaSetDevice(ctx->slots[d].dev);
-            Q = leapfrog_lane_capacity(ctx->pot, ctx->slots[d].sm_count);
-            cudaSetDevice(prev_dev);
-            // only batches of several waves: a batch of one or two (10^5 binaries with their own horizons, config 2)
-            // pipelines better in the finer old chunks -- measured 1.34e11 against 0.90e11 steps/s end to end
-            if (getenv("CW_NO_WAVE_CHUNKS") || b - a < 4 * Q) Q = 0;
-        }
-        const int64_t chunk = pipelined ? host_chunk(b - a, Q) : (b - a);
-        // The first H2D copy and the last D2H copy have nothing to hide behind: ramp the chunk size up from
-        // chunk/8 at the start and back down at the end (the kernels in between keep the full size).
-        std::vector<int64_t> sizes;
-        if (!pipelined || b - a < 4 * chunk) {
-            for (int64_t c = a; c < b; c += chunk) sizes.push_back(std::min(chunk, b - c));
-        } else {
-            std::vector<int64_t> head, tail;
-            int64_t used = 0;
-            if (Q > 0) {     // whole waves here too: Q, 2Q, 4Q, ...
-                for (int64_t sz = Q; sz < chunk; sz *= 2) { head.push_back(sz); used += sz; }
-                for (int64_t sz = Q; sz < chunk; sz *= 2) { tail.push_back(sz); used += sz; }
-            } else {
-                for (int64_t sz = std::max<int64_t>(chunk / 8, HOST_CHUNK_MIN / 2); sz < chunk; sz *= 2) { head.push_back(sz); used += sz; }
-                for (int64_t sz = std::max<int64_t>(chunk / 4, HOST_CHUNK_MIN / 2); sz < chunk; sz *= 2) { tail.push_back(sz); used += sz; }
-            }
-            int64_t mid = (b - a) - used;
-            sizes = head;
-            while (mid > 0) { const int64_t sz = std::min(chunk, mid); sizes.push_back(sz); mid -= sz; }
-            for (size_t k = tail.size(); k-- > 0;) sizes.push_back(tail[k]);
-        }
-        int lane = 0;
-        int64_t c = a;
-        for (int64_t sz : sizes) {
-            // store_all from host buffers: a shard's trajectories live in its lane's buffer, so shards are also
-            // cut by trajectory COLUMNS (<= 2^26 = 3.2 GB of pos + vel); with the lane buffers re-used this
-            // bounds device memory however long the orbits are
-            int64_t s0 = c;
-            const int64_t e0 = c + sz;
-            while (s0 < e0) {
-                int64_t e1 = e0;
-                if (store_all && !dev_mode) {
-                    const int64_t lim = R->traj_off[s0] + traj_shard_cols();
-                    const int64_t *ub = std::upper_bound(R->traj_off + s0 + 1, R->traj_off + e0 + 1, lim);
-                    e1 = std::min(e0, std::max<int64_t>(s0 + 1, (int64_t)(ub - R->traj_off) - 1));
-                }
-                Shard sh;
-                sh.slot = d;
-                sh.lane = dev_mode ? 0 : (lane++ % Slot::N_LANES);
-                sh.a = s0;
-                sh.b = e1;
-                shards.push_back(sh);
-                s0 = e1;
-            }
-            c = e0;
-        }
-    }
-    for (Shard &sh : shards) {
-        if (B->ev_off) {
-            if ((rc = fetch_i64(ctx, B->ev_off + sh.a, dev_mode, &sh.ea)) != CW_OK) return rc;
-            if ((rc = fetch_i64(ctx, B->ev_off + sh.b, dev_mode, &sh.eb)) != CW_OK) return rc;
-        }
-        if (store_all) {
-            if ((rc = fetch_i64(ctx, R->traj_off + sh.a, dev_mode, &sh.ta)) != CW_OK) return rc;
-            if ((rc = fetch_i64(ctx, R->traj_off + sh.b, dev_mode, &sh.tb)) != CW_OK) return rc;
-        }
-        if (sh.eb < sh.ea || sh.tb < sh.ta) return fail(ctx, CW_E_INVALID, "offsets must be non-decreasing");
-        if (sh.eb > sh.ea && (!B->ev_time || !B->ev_dv)) return fail(ctx, CW_E_INVALID, "ev_off lists events but ev_time / ev_dv is null");
-    }
-    cw_result Rl;
-    memset(&Rl, 0, sizeof Rl);
-    if (R) Rl = *R;
-    if (!integrate) { Rl.n_nodes = n_nodes_out; Rl.ev_step = ev_step_out; }
-
-    // ---- size and reserve each slot's arena once, for all of its shards
-    std::vector<Plan> plans(shards.size());
-    std::vector<size_t> need((size_t)nslots * Slot::N_LANES, 0);
-    for (size_t k = 0; k < shards.size(); k++) {
-        size_t &nd = need[(size_t)shards[k].slot * Slot::N_LANES + shards[k].lane];
-        nd = std::max(nd, shard_bytes(o, &Rl, shards[k], integrate, plans[k]));
-    }
-    for (int d = 0; d < nslots; d++) {
-        Slot &s = ctx->slots[d];
-        cudaSetDevice(s.dev);
-        size_t n_sh = 0;
-        for (const Shard &sh : shards) n_sh += (sh.slot == d);
-        for (int l = 0; l < Slot::N_LANES; l++) {
-            const size_t nd = need[(size_t)d * Slot::N_LANES + l];
-            if (nd == 0) continue;
-            // a stream still running a previous no_sync call must not see its buffers move
-            if (nd + 4096 > s.lane_arena[l].cap) cudaStreamSynchronize(s.lanes[l]);
-            CW_CK(ctx, s.lane_arena[l].reserve(nd + 4096));
-        }
-        if (Arena::padded(8, 8) * n_sh + 4096 > s.meta.cap)
-            for (int l = 0; l < Slot::N_LANES; l++) cudaStreamSynchronize(s.lanes[l]);
-        CW_CK(ctx, s.meta.reserve(Arena::padded(8, 8) * n_sh + 4096));
-        CW_CK(ctx, s.ensure_events(3 * n_sh));
-    }
-    // ---- phase 1: enqueue everything (H2D, kernels, D2H) on every device, all asynchronous
-    std::vector<size_t> ev_used(nslots, 0);
-    std::vector<unsigned long long> hs(4 * shards.size(), 0);
-    const int64_t total_cols = (store_all && !dev_mode) ? R->traj_off[n] : 0;
-    for (size_t k = 0; k < shards.size(); k++) {
-        const Shard &sh = shards[k];
-        Slot &s = ctx->slots[sh.slot];
-        Plan &pl = plans[k];
-        cudaSetDevice(s.dev);
-        pl.stream = (dev_mode && o->stream) ? (cudaStream_t)o->stream : s.lanes[sh.lane];
-        pl.ev_t0 = s.events[ev_used[sh.slot]++];
-        pl.ev_k0 = s.events[ev_used[sh.slot]++];
-        pl.ev_k1 = s.events[ev_used[sh.slot]++];
-        rc = plan_shard(ctx, s, o, B, &Rl, sh, integrate, pl);
-        if (rc == CW_OK) rc = run_shard(ctx, s, o, pl, integrate, store_all);
-        if (rc != CW_OK) { cudaSetDevice(prev); return rc; }
-        if (!dev_mode) {
-            cudaStream_t stream = pl.stream;
-            const IntegArgs &A = pl.A;
-            const int64_t m = sh.b - sh.a, K = sh.eb - sh.ea, Lt = sh.tb - sh.ta;
-            int32_t *nn = integrate ? R->n_nodes : n_nodes_out;
-            int32_t *es = integrate ? R->ev_step : ev_step_out;
-            if (nn) CW_CK(ctx, cudaMemcpyAsync(nn + sh.a, A.n_nodes, m * 4, cudaMemcpyDeviceToHost, stream));
-            if (es && K > 0) CW_CK(ctx, cudaMemcpyAsync(es + sh.ea, A.ev_step, K * 4, cudaMemcpyDeviceToHost, stream));
-            if (integrate) {
-                for (int c = 0; c < 6; c++)
-                    CW_CK(ctx, cudaMemcpyAsync(R->w_final + c * n + sh.a, A.w_final + c * m, m * 8, cudaMemcpyDeviceToHost, stream));
-                CW_CK(ctx, cudaMemcpyAsync(R->status + sh.a, A.status, m * 4, cudaMemcpyDeviceToHost, stream));
-                if (store_all && Lt > 0) {
-                    for (int c = 0; c < 3; c++) {
-                        CW_CK(ctx, cudaMemcpyAsync(R->traj_pos + c * total_cols + sh.ta, A.traj_pos + c * A.traj_total, Lt * 8, cudaMemcpyDeviceToHost, stream));
-                        CW_CK(ctx, cudaMemcpyAsync(R->traj_vel + c * total_cols + sh.ta, A.traj_vel + c * A.traj_total, Lt * 8, cudaMemcpyDeviceToHost, stream));
-                    }
-                    if (R->traj_t) CW_CK(ctx, cudaMemcpyAsync(R->traj_t + sh.ta, A.traj_t, Lt * 8, cudaMemcpyDeviceToHost, stream));
-                }
-            }
-        }
-    }
-    if (dev_mode && o->no_sync) { cudaSetDevice(prev); return CW_OK; }
-    // ---- phase 2: wait, gather statistics and kernel times
-    int64_t stats[4] = {0, 0, 0, 0};
-    for (size_t k = 0; k < shards.size(); k++) {
-        Slot &s = ctx->slots[shards[k].slot];
-        cudaSetDevice(s.dev);
-        if (integrate && R->stats)      // (pageable destination: this copy blocks the host, so it comes after every enqueue)
-            CW_CK(ctx, cudaMemcpyAsync(&hs[4 * k], plans[k].A.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, plans[k].stream));
-    }
-    for (size_t k = 0; k < shards.size(); k++) {
-        Slot &s = ctx->slots[shards[k].slot];
-        cudaSetDevice(s.dev);
-        CW_CK(ctx, cudaStreamSynchronize(plans[k].stream));
-        for (int q = 0; q < 4; q++) stats[q] += (int64_t)hs[4 * k + q];
-        if (plans[k].timed) {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, plans[k].ev_k0, plans[k].ev_k1) == cudaSuccess) s.last_kernel_ms += ms;
-            if (cudaEventElapsedTime(&ms, plans[k].ev_t0, plans[k].ev_k1) == cudaSuccess) s.last_total_ms += ms;
-        }
-    }
-    if (getenv("CW_DEBUG") && !shards.empty() && plans[0].timed) {
-        // shard timeline relative to the first shard's first kernel: pre-pass start, integrator start / end
-        for (size_t k = 0; k < shards.size(); k++) {
-            if (shards[k].slot != 0 || !plans[k].timed) continue;
-            float a = 0.f, b = 0.f, c = 0.f;
-            cudaEventElapsedTime(&a, plans[0].ev_t0, plans[k].ev_t0);
-            cudaEventElapsedTime(&b, plans[0].ev_t0, plans[k].ev_k0);
-            cudaEventElapsedTime(&c, plans[0].ev_t0, plans[k].ev_k1);
-            fprintf(stderr, "[cw] shard %2zu lane %d orbits %8lld: prepass %8.3f  kernel %8.3f .. %8.3f ms\n", k,
-                    shards[k].lane, (long long)(shards[k].b - shards[k].a), a, b, c);
-        }
-    }
-    if (integrate && R->stats) {
-        if (dev_mode) CW_CK(ctx, cudaMemcpy(R->stats, stats, sizeof stats, cudaMemcpyHostToDevice));
-        else memcpy(R->stats, stats, sizeof stats);
-    }
-    cudaSetDevice(prev);
-    return CW_OK;
+    if (B->n_orbits == 0) return CW_OK;
+    if (integrate && R->traj_off && (!R->traj_pos || !R->traj_vel)) return fail(ctx, CW_E_INVALID, "traj_pos / traj_vel missing");
+    if (o->mem_space == CW_MEM_DEVICE) return integrate_device(ctx, o, B, R, integrate, n_nodes_out, ev_step_out);
+    return integrate_host(ctx, o, B, R, integrate, n_nodes_out, ev_step_out);
 }
 
 extern "C" int cw_count_nodes(cw_ctx *ctx, const cw_opts *opts, const cw_batch *batch, int32_t *n_nodes, int32_t *ev_step)

@@ -90,26 +90,39 @@ def resolve_integrator(integrator, integrator_kwargs=None):
 def _context(potential, context=None):
     ctx = context if context is not None else _lib.default_context()
     pot = from_gala(potential) if not isinstance(potential, CompositePotential) else potential
-    if ctx.potential is not pot:
+    # compared by value: from_gala returns a fresh object on every call
+    if ctx.potential is not pot and (ctx.potential is None or ctx.potential.fingerprint() != pot.fingerprint()):
         ctx.set_potential(pot)
     return ctx
 
 
 def _grid_times_myr(batch: OrbitBatch, n_nodes):
     """Orbit.t of final-state-only results: the time of the last node (Myr).  For appended grids that
-    is t2; otherwise t1 + (n-1) dt accumulated -- only the label, the kernels never read it."""
-    last_acc = batch.t1.copy()
-    # accumulate (n_nodes - 1) steps for the un-appended grids; they are few in practice
+    is t2; otherwise t1 + (n-1) dt ACCUMULATED as the grid is -- only the label, the kernels never read it."""
     app = (batch.flags & 1) == 1
-    t_last = np.where(app, batch.t2, 0.0)
+    t_last = np.where(app, batch.t2, batch.t1)
     idx = np.flatnonzero(~app)
-    for i in idx:
-        t = batch.t1[i]
-        for _ in range(max(int(n_nodes[i]) - 1, 0)):
-            t += batch.dt[i]
-        t_last[i] = t
-    del last_acc
+    if len(idx):
+        # one vector addition per step over the orbits that still have steps left (they are sorted by length first)
+        steps = np.maximum(np.asarray(n_nodes)[idx].astype(np.int64) - 1, 0)
+        order = np.argsort(-steps, kind="stable")
+        idx, steps = idx[order], steps[order]
+        t, dt = batch.t1[idx].copy(), batch.dt[idx]
+        for j in range(int(steps[0]) if len(steps) else 0):
+            live = int(np.searchsorted(-steps, -j, side="left"))     # orbits with steps > j
+            t[:live] += dt[:live]
+        t_last[idx] = t
     return t_last * batch.to_myr
+
+
+def _ranges(starts, lens):
+    """Concatenation of arange(s, s + l) for every (s, l)."""
+    lens = np.asarray(lens, dtype=np.int64)
+    tot = int(lens.sum())
+    if tot == 0:
+        return np.zeros(0, dtype=np.int64)
+    ends = np.cumsum(lens)
+    return np.repeat(np.asarray(starts, dtype=np.int64) - (ends - lens), lens) + np.arange(tot, dtype=np.int64)
 
 
 def integrate_orbits(batch: OrbitBatch, potential=None, store_all=True, integrator=None, integrator_kwargs=None,
@@ -126,11 +139,10 @@ def integrate_orbits(batch: OrbitBatch, potential=None, store_all=True, integrat
                   nmax=kw.get("nmax", 0) or 0)
 
     def run(b: OrbitBatch):
-        return ctx.integrate(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv,
-                             store_all=store_all, **common)
+        return ctx.integrate_batch(b, store_all=store_all, **common)
 
     res = run(batch)
-    status = res["status"].copy()
+    status = res["status"]
     n = batch.n_orbits
     if np.any(status == -1):
         bad = np.flatnonzero(status == -1)
@@ -141,13 +153,18 @@ def integrate_orbits(batch: OrbitBatch, potential=None, store_all=True, integrat
     pieces = None
     if store_all:
         pieces = dict(off=res["traj_off"], pos=res["traj_pos"], vel=res["traj_vel"], t=res["traj_t"])
-    w_final, n_nodes = res["w_final"], res["n_nodes"].copy()
+    w_final, n_nodes = res["w_final"], res["n_nodes"]
     retry_results = {}
     # retries only exist on the events branch, max_retries attempts in total (reference quirk Q4)
-    kicked = (batch.flags & 1) == 1
+    kicked = None
     dt_scale = 1.0
     for _ in range(max(int(max_retries) - 1, 0)):
-        failed = np.flatnonzero(np.isin(status, _FAILED) & kicked)
+        failed = np.flatnonzero(status != 0)
+        if len(failed) == 0:
+            break
+        if kicked is None:
+            kicked = (batch.flags & 1) == 1
+        failed = failed[np.isin(status[failed], _FAILED) & kicked[failed]]
         if len(failed) == 0:
             break
         dt_scale *= timestep_multiplier
@@ -166,23 +183,26 @@ def integrate_orbits(batch: OrbitBatch, potential=None, store_all=True, integrat
     if store_all:
         off, pos, vel, t = pieces["off"], pieces["pos"], pieces["vel"], pieces["t"]
         if retry_results:   # rebuild the SoA buffers with the re-gridded orbits spliced in
-            lens = (off[1:] - off[:-1]).copy()
+            lens_old = off[1:] - off[:-1]
+            lens = lens_old.copy()
             for i, (p_, v_, t_) in retry_results.items():
                 lens[i] = p_.shape[1]
             noff = np.zeros(n + 1, dtype=np.int64)
             np.cumsum(lens, out=noff[1:])
             npos, nvel, nt = np.empty((3, noff[-1])), np.empty((3, noff[-1])), np.empty(noff[-1])
-            for i in range(n):
-                if i in retry_results:
-                    p_, v_, t_ = retry_results[i]
-                else:
-                    p_, v_, t_ = pos[:, off[i]:off[i + 1]], vel[:, off[i]:off[i + 1]], t[off[i]:off[i + 1]]
+            keep = np.ones(n, dtype=bool)
+            keep[list(retry_results)] = False
+            src, dst = _ranges(off[:-1][keep], lens_old[keep]), _ranges(noff[:-1][keep], lens[keep])
+            npos[:, dst], nvel[:, dst], nt[dst] = pos[:, src], vel[:, src], t[src]
+            for i, (p_, v_, t_) in retry_results.items():
                 npos[:, noff[i]:noff[i + 1]], nvel[:, noff[i]:noff[i + 1]], nt[noff[i]:noff[i + 1]] = p_, v_, t_
             off, pos, vel, t = noff, npos, nvel, nt
         orbits = OrbitArray(off, pos, vel, t, ok)
     else:
-        t_final = _grid_times_myr(batch, n_nodes) if final_times else np.where(
-            kicked, batch.t2 * batch.to_myr, np.nan)
+        if final_times:
+            t_final = _grid_times_myr(batch, n_nodes)
+        else:       # the label of the one stored sample: t2 on the events branch (appended), unknown without a walk
+            t_final = np.where((batch.flags & 1) == 1, batch.t2 * batch.to_myr, np.nan)
         orbits = OrbitArray.from_final(w_final, t_final, ok)
     info = dict(status=status, n_nodes=n_nodes, ev_step=res["ev_step"], stats=res["stats"], w_final=w_final)
     return orbits, info

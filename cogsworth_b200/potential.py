@@ -137,6 +137,18 @@ class CompositePotential:
     def describe(self) -> str:
         return ",".join(self.names)
 
+    def fingerprint(self) -> bytes:
+        """Every number a context receives in ``set_potential``: equal fingerprints = the same device tables, so a
+        fresh but identical object (``from_gala`` builds one per call) does not trigger a re-upload."""
+        import hashlib
+        h = hashlib.sha1()
+        h.update(np.float64(self.G).tobytes() + self.type_array().tobytes() + self.param_array().tobytes())
+        rot, kn = self.rotation_array(), self.knot_arrays()
+        h.update(b"R" + (rot.tobytes() if rot is not None else b"-"))
+        h.update(b"K" + (b"".join(np.asarray(a).tobytes() for a in kn) if kn is not None else b"-"))
+        h.update(self.interp.encode() + np.float64(self.t_eval).tobytes())
+        return h.digest()
+
     def __repr__(self):
         return f"<CompositePotential[{self.label}] {self.describe()}>"
 

@@ -25,13 +25,14 @@
 #ifndef COGSWORTH_B200_H
 #define COGSWORTH_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define CW_ABI_VERSION 1
+#define CW_ABI_VERSION 2
 #define CW_MAX_COMPONENTS 16
 
 /* potential components = gala builtin potentials reachable from MilkyWayPotential v1 / v2
@@ -74,7 +75,7 @@ enum {
 
 /* buffer placement */
 enum {
-    CW_MEM_HOST = 0,  /* every pointer in cw_batch / cw_result is host memory (pinned or pageable) */
+    CW_MEM_HOST = 0,  /* every pointer in cw_batch / cw_result is host memory (page-locked or pageable, see cw_host_alloc) */
     CW_MEM_DEVICE = 1 /* every pointer is device memory on the context's FIRST device */
 };
 
@@ -110,7 +111,9 @@ typedef struct cw_opts {
     double rtol;        /* integrator_kwargs["rtol"], gala default 1e-10 */
     int64_t nmax;       /* integrator_kwargs["nmax"], <= 0 -> 100000 */
     void *stream;       /* CW_MEM_DEVICE only: cudaStream_t to launch on (NULL = the context's own) */
-    int32_t no_sync;    /* CW_MEM_DEVICE only: return without synchronising the stream */
+    int32_t no_sync;    /* CW_MEM_DEVICE only: return without synchronising the stream.  A context has ONE set of
+                           scratch buffers: the next call on the same context (any stream) first waits, on the device,
+                           for the previous no_sync call to finish; results are valid once `stream` is synchronised */
     int32_t reserved;
 } cw_opts;
 
@@ -131,17 +134,38 @@ typedef struct cw_opts {
  * the last node k >= cursor with T_k < ev_time[e] (kicks.py:134); the velocity change ev_dv[e]
  * is get_kick_differential(...) (kicks.py:12-49) already rotated and converted to kpc/Myr.
  */
+/* One class of time grid: the four per-orbit grid columns of the plain layout.  A population has two of them --
+ * the events branch (seconds, t2 appended) and gala's own grid (Myr) -- plus one for every orbit whose span is
+ * shorter than dt (kicks.py:97), so the columns compress to one byte per orbit. */
+typedef struct cw_grid_class {
+    double t2, dt, to_myr;
+    int32_t grid_flags;
+    int32_t reserved;
+} cw_grid_class;
+
 typedef struct cw_batch {
     int64_t n_orbits;
-    const double *w0;          /* 6 x n_orbits */
-    const double *t1;          /* n_orbits */
-    const double *t2;          /* n_orbits */
-    const double *dt;          /* n_orbits */
-    const double *to_myr;      /* n_orbits */
-    const int32_t *grid_flags; /* n_orbits */
-    const int64_t *ev_off;     /* n_orbits + 1, or NULL when no orbit has events */
+    const double *w0;          /* 6 x n_w0 (n_w0 = n_orbits in the plain layout) */
+    const double *t1;          /* n_w0 */
+    const double *t2;          /* n_orbits   (NULL when grid_class is given) */
+    const double *dt;          /* n_orbits   (NULL when grid_class is given) */
+    const double *to_myr;      /* n_orbits   (NULL when grid_class is given) */
+    const int32_t *grid_flags; /* n_orbits   (NULL when grid_class is given) */
+    const int64_t *ev_off;     /* n_orbits + 1, or NULL when no orbit has events (or when ev_off32 is given) */
     const double *ev_time;     /* K = ev_off[n_orbits] */
     const double *ev_dv;       /* K x 3 (row-major: dvx, dvy, dvz per event) */
+    /* ---- ABI 2: compact forms, CW_MEM_HOST only; all zero = the plain layout above.  They exist to cut the bytes
+     * that cross the host link (134 -> 78 B per orbit on a kicked population); a small kernel expands them on the
+     * device, so the integrators see the plain layout either way and return the same bits. */
+    int64_t n_w0;              /* 0 -> n_orbits.  Otherwise orbits [0, n_w0) start from column i of w0 / t1 and orbit
+                                  n_w0 + k from column w0_index[k]: disrupted secondaries re-use their primary's
+                                  initial conditions and birth time (pop.py:1186-1193) */
+    const int32_t *w0_index;   /* n_orbits - n_w0 entries, non-decreasing, each in [0, n_w0) */
+    const uint8_t *grid_class; /* n_orbits: index into classes[] */
+    const cw_grid_class *classes;
+    int32_t n_classes;         /* <= 256 */
+    int32_t reserved;
+    const int32_t *ev_off32;   /* n_orbits + 1: ev_off in 32 bits (K < 2^31) */
 } cw_batch;
 
 /* Outputs.  Any pointer except w_final and status may be NULL. */
@@ -196,6 +220,8 @@ int cw_set_potential_time(cw_ctx *ctx, double t_myr);
  * host size trajectory buffers (traj_off) before cw_integrate, and is the bit-exact
  * kick-timing check on its own. */
 int cw_count_nodes(cw_ctx *ctx, const cw_opts *opts, const cw_batch *batch, int32_t *n_nodes, int32_t *ev_step);
+/* batch->w0 may be NULL here (the grid does not depend on it), and with ev_step == NULL the events are not read
+ * either: sizing the trajectory buffers of a store_all run moves 28 B per orbit (1 B with grid_class). */
 
 /* The hot path: replaces pool.starmap(_orbit_worker, ...) (pop.py:1245-1266).  Orbits are sharded
  * by index over the context's devices; there is no collective. */
@@ -212,6 +238,17 @@ int cw_circular_velocity(cw_ctx *ctx, int mem_space, int64_t n, const double *q,
  * system's own birth time (pop.py:1001-1004).  what: CW_GRADIENT (out 3 x n), CW_VALUE (n), CW_VCIRC (n). */
 enum { CW_GRADIENT = 0, CW_VALUE = 1, CW_VCIRC = 2 };
 int cw_pointwise_t(cw_ctx *ctx, int what, int mem_space, int64_t n, const double *q, const double *t_myr, double *out);
+
+/* Page-locked host memory from the library's cache (cudaHostAlloc, portable; freed blocks are kept for re-use up to
+ * CW_PINNED_CACHE_MB, default 4096).  Host buffers handed to cw_integrate may be ANY host memory: page-locked buffers
+ * (these, torch pinned tensors, cudaHostRegister'ed arrays) are copied from / to directly; pageable ones (plain
+ * numpy) are staged through the library's own page-locked ring by a pool of host threads (CW_HOST_THREADS), chunk by
+ * chunk, overlapped with the kernels.  Replaces the pickling of arguments / results across the process pool
+ * (pop.py:1245-1266). */
+void *cw_host_alloc(size_t bytes);
+void cw_host_free(void *p);
+/* 1 if p is page-locked (or device) memory known to the CUDA runtime, 0 if pageable */
+int cw_host_is_pinned(const void *p);
 
 /* Diagnostics */
 const char *cw_strerror(int code);

@@ -186,7 +186,7 @@ def test_abi_exports_every_declared_symbol(built):
         assert hasattr(lib, name), name
     assert sorted(declared) == sorted(_lib.EXPORTS)
     L = _lib.load()
-    assert L.cw_abi_version() == 1
+    assert L.cw_abi_version() == 2
     assert L.cw_strerror(-4).decode().startswith("no CUDA device")
 
 
