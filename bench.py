@@ -16,8 +16,10 @@ Workloads (synthetic inputs seeded with numpy default_rng(202211
   config5            10^6 orbits DOPRI853 rtol = atol = 1e-8, kicks, 1 % plunging orbits
 
 Output: ONE JSON line on rank 0 (see README / task contract): value = device-resident throughput,
-e2e = through the C-ABI with pinned HOST buffers (H2D + D2H inside the timed region), roofline
-(FP64 pipe, measured DFMA peak), cpu_baseline (the C oracle on the host cores, bounded sample).
+e2e = through the Python API (kicks.integrate_orbits) from HOST memory, H2D + D2H inside the timed region
+(e2e.c_abi: cw_integrate itself; e2e.api_numpy: plain pageable numpy arrays), roofline (FP64 pipe, measured DFMA
+peak), cpu_baseline (the C oracle on the host cores, bounded sample); the default one-GPU run adds other_workloads
+(configs 2, 3, 5) and population_e2e (B200Population.perform_galactic_evolution from DataFrames).
 --impl reference times the CPU implementation only (the gala-equivalent C oracle: gala itself is not
 installable in this image) with all host threads.
 """
@@ -83,6 +85,8 @@ def parse_args():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; marks the line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the other_workloads / population_e2e blocks")
+    ap.add_argument("--no-inprocess", action="store_true", help="N > 1: skip the one-process-all-GPUs end-to-end leg")
     ap.add_argument("--cpu-sample-orbits", type=int, default=200_000)
     return ap.parse_args()
 
@@ -233,13 +237,29 @@ def cpu_baseline(pop, wl, n_sample, threads=0, repeats=1):
 
 
 # ------------------------------------------------------------------------------------------------
+REFERENCE_ARM_NOTE = ("--impl reference: the CPU implementation of the path (gala-equivalent C oracle port on all host threads; "
+                      "gala / astropy / COSMIC are not installable offline) integrates a {n}-orbit SAMPLE of this workload per "
+                      "step and reports the sample's orbit-steps/s")
+
+
+def config_block(args, wl, world, pot_label, numa_note=""):
+    """The static description of the run: the same keys and values in both arms (--impl ours / reference)."""
+    size = wl.get("n_orbits", None)
+    return {"workload": f"{args.workload}: {wl['desc']}" + ("" if args.scale == 1.0 else f" [SCALED x{args.scale}: not a valid bench line]"),
+            "n_orbits": size if size is not None else f"{wl['n_binaries']} binaries + their disrupted secondaries (~1.8x)",
+            "integrator": wl["integrator"], "potential": pot_label,
+            "parallelism": f"orbits sharded by index over {world} GPU(s), no collective" + numa_note,
+            "cache": "inputs + outputs (>= 1 GB per pass) exceed the 126 MB L2; nothing is reused between steps",
+            "reference_sample": REFERENCE_ARM_NOTE.format(n=args.cpu_sample_orbits)}
+
+
 def run_reference(args, wl, rank, world):
     """--impl reference: the CPU implementation of the path on the host cores (rank 0 only)."""
     if rank != 0:
         return
     size = wl.get("n_orbits", int(1.8 * wl.get("n_binaries", 0)))
     pop = build_shard(wl, 0, 1, "strong", min(args.scale, 1.0, 2.0 * args.cpu_sample_orbits / size))
-    apply_workload_potential(wl, pop)
+    pot_label = apply_workload_potential(wl, pop)
     import oracle as O
     threads = O.max_threads()
     n_sample = min(args.cpu_sample_orbits, pop.batch.n_orbits)
@@ -255,15 +275,236 @@ def run_reference(args, wl, rank, world):
     line = {"impl": "reference", "metric": "FP64 orbit-steps/sec", "value": value, "unit": "orbit-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {wl['desc']}",
-                       "reference_arm": "CPU oracle port of gala leapfrog/DOP853 + cogsworth kicks driver "
-                                        "(gala/astropy/COSMIC are not installable offline), all host threads, "
-                                        f"each step = {n_sample} orbits of the workload"},
+            "data": "synthetic", "config": config_block(args, wl, world, pot_label),
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "orbit-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class Workload:
+    """One workload on one rank: device-resident copies for `value`, the OrbitBatch for the end-to-end legs."""
+
+    def __init__(self, name, wl, pop, ctx, dev, torch, _lib):
+        self.name, self.wl, self.pop, self.ctx, self.dev, self.torch, self._lib = name, wl, pop, ctx, dev, torch, _lib
+        b = pop.batch
+        self.b, self.n, self.K = b, b.n_orbits, b.n_events
+        self.integ = {"leapfrog": _lib.LEAPFROG, "dop853": _lib.DOP853, "dop853_dense": _lib.DOP853_DENSE}[wl["integrator"]]
+        self.tol = dict(atol=wl.get("atol", 1e-10), rtol=wl.get("rtol", 1e-10))
+        f64, i32, i64 = torch.float64, torch.int32, torch.int64
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.D = dict(w0=to(b.w0), t1=to(b.t1), t2=to(b.t2), dt=to(b.dt), to_myr=to(b.to_myr), flags=to(b.flags))
+        if self.K:
+            self.D.update(ev_off=to(b.ev_off), ev_time=to(b.ev_time), ev_dv=to(b.ev_dv))
+        else:
+            self.D.update(ev_off=None, ev_time=None, ev_dv=None)
+        self.traj_off_d = self.traj_pos_d = self.traj_vel_d = None
+        if wl["store_all"]:
+            nn, _ = ctx.count_nodes(None, b.t1, b.t2, b.dt, b.to_myr, b.flags)
+            off = np.zeros(self.n + 1, dtype=np.int64)
+            np.cumsum(nn, out=off[1:])
+            self.traj_off_d = to(off)
+            self.traj_pos_d = torch.empty((3, int(off[-1])), dtype=f64, device=dev)
+            self.traj_vel_d = torch.empty((3, int(off[-1])), dtype=f64, device=dev)
+        self.wf_d = torch.empty((6, self.n), dtype=f64, device=dev)
+        self.st_d = torch.empty(self.n, dtype=i32, device=dev)
+        self.stats_d = torch.zeros(4, dtype=i64, device=dev)
+        self.stream = torch.cuda.current_stream(dev)
+        # the plain layout in ordinary (pageable) numpy memory: what a caller without this package's batch builder has
+        self.plain = None
+
+    def step_device(self):
+        D = self.D
+        self.ctx.integrate_raw(self.n, D["w0"], D["t1"], D["t2"], D["dt"], D["to_myr"], D["flags"], D["ev_off"], D["ev_time"],
+                               D["ev_dv"], self.wf_d, self.st_d, None, None, self.traj_off_d, self.traj_pos_d, self.traj_vel_d,
+                               None, self.stats_d, integrator=self.integ, mem_space=self._lib.MEM_DEVICE,
+                               stream=self.stream.cuda_stream, **self.tol)
+
+    def step_api(self, batch=None):
+        """The call a user makes: kicks.integrate_orbits on an OrbitBatch held in HOST memory (H2D of the inputs, the
+        kernels, D2H of final states / statuses, the retry bookkeeping) -> OrbitArray."""
+        from cogsworth_b200 import kicks
+        orbits, info = kicks.integrate_orbits(self.b if batch is None else batch, potential=self.pop.potential,
+                                              store_all=False, integrator=self.wl["integrator"],
+                                              integrator_kwargs=dict(self.tol), context=self.ctx)
+        return orbits, info
+
+    def step_abi(self, out):
+        """cw_integrate(CW_MEM_HOST) itself on the same page-locked arrays, results into page-locked `out`."""
+        a = self.b.abi_arrays()
+        self.ctx.integrate_raw(self.n, a["w0"], a["t1"], a.get("t2"), a.get("dt"), a.get("to_myr"), a.get("flags"),
+                               a.get("ev_off"), a.get("ev_time"), a.get("ev_dv"), out[0], out[1],
+                               integrator=self.integ, mem_space=self._lib.MEM_HOST, n_w0=a.get("n_w0", 0),
+                               w0_index=a.get("w0_index"), grid_class=a.get("grid_class"), classes=a.get("classes"),
+                               ev_off32=a.get("ev_off32"), **self.tol)
+
+    def h2d_bytes(self):
+        a = self.b.abi_arrays()
+        return int(sum(v.nbytes for v in a.values() if isinstance(v, np.ndarray)))
+
+    def free(self):
+        for k in ("D", "traj_off_d", "traj_pos_d", "traj_vel_d", "wf_d", "st_d"):
+            setattr(self, k, None)
+        self.torch.cuda.empty_cache()
+
+
+def measure(W, steps, warmup, barrier, max_over_ranks, sum_over_ranks, peak_fp64, world, args, sampler_index=None,
+            with_api=True, with_variants=False):
+    """value (device-resident), e2e (through the Python API from host memory) and the roofline of one workload."""
+    torch, _lib, ctx, wl = W.torch, W._lib, W.ctx, W.wl
+    for _ in range(warmup):
+        W.step_device()
+    barrier()
+    steps_per_pass = int(W.stats_d.cpu()[3])
+    sampler = ClockSampler(sampler_index) if sampler_index is not None else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, total_kernel_ms, launches = [], [], 0
+    e0.record(W.stream)
+    for _ in range(steps):
+        W.step_device()
+        kernel_ms.append(ctx.last_kernel_ms(0))
+        total_kernel_ms.append(ctx.last_total_kernel_ms(0))
+        launches += ctx.last_launch_count
+    e1.record(W.stream)
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    stats_run = W.stats_d.cpu().numpy().copy()
+    total_steps = sum_over_ranks(float(steps_per_pass))
+    value = total_steps * steps / (dev_ms * 1e-3)
+    n_failed = int((W.st_d != 0).sum().item())
+
+    # ---- end to end from host memory -------------------------------------------------------------------------
+    e2e = None
+    if with_api and not wl["store_all"]:
+        def timed(fn, nwarm=max(1, min(warmup, 2))):
+            for _ in range(nwarm):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                fn()
+            barrier()
+            return max_over_ranks(time.perf_counter() - t0)
+
+        res = {}
+        s_api = timed(lambda: res.__setitem__("o", W.step_api()))
+        orbits, info = res["o"]
+        okd = (W.st_d == 0).cpu().numpy()          # (failed orbits are re-integrated with a finer grid by the API)
+        assert np.array_equal(np.asarray(info["w_final"])[:, okd], W.wf_d.cpu().numpy()[:, okd]), \
+            "host-buffer path and device path disagree"
+        h2d = W.h2d_bytes()
+        d2h = W.n * (48 + 4 + 4) + 4 * W.K + 40
+        e2e = {"value": total_steps * steps / s_api, "unit": "orbit-steps/s",
+               "h2d_bytes_per_step": int(sum_over_ranks(float(h2d))), "d2h_bytes_per_step": int(sum_over_ranks(float(d2h))),
+               "ms_per_step": 1e3 * s_api / steps,
+               "how": "cogsworth_b200.kicks.integrate_orbits(batch, store_all=False) -- the batch form of "
+                      "integrate_orbit_with_events that perform_galactic_evolution calls -- on the OrbitBatch "
+                      "build_orbit_batch makes (host memory, page-locked, compact cw_batch forms): H2D of initial conditions / "
+                      "start times / grid classes / events, grid pre-pass + integrator kernels, D2H of final states, statuses, "
+                      "node counts and kick nodes into page-locked arrays, retry bookkeeping, OrbitArray; host wall clock, "
+                      "max over ranks"}
+        if with_variants:
+            out = (_lib.pinned_empty((6, W.n)), _lib.pinned_empty(W.n, np.int32))
+            s_abi = timed(lambda: W.step_abi(out))
+            e2e["c_abi"] = {"value": total_steps * steps / s_abi, "ms_per_step": 1e3 * s_abi / steps,
+                            "how": "cw_integrate(CW_MEM_HOST) called directly on the same page-locked arrays"}
+            from cogsworth_b200.batch import OrbitBatch
+            b = W.b
+            cp = lambda x: None if x is None else np.array(x, copy=True)
+            plain = OrbitBatch(cp(b.w0), cp(b.t1), cp(b.t2), cp(b.dt), cp(b.to_myr), cp(b.flags), cp(b.ev_off),
+                               cp(b.ev_time), cp(b.ev_dv))
+            s_np = timed(lambda: W.step_api(plain))
+            e2e["api_numpy"] = {"value": total_steps * steps / s_np, "ms_per_step": 1e3 * s_np / steps,
+                                "h2d_bytes_per_step": int(sum_over_ranks(float(sum(
+                                    v.nbytes for v in plain.abi_arrays().values() if isinstance(v, np.ndarray))))),
+                                "how": "the same call on the PLAIN layout in ordinary (pageable) numpy arrays: staged through "
+                                       "the library's page-locked ring by its host thread pool, chunk by chunk"}
+            del plain
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------------
+    k_ms = float(np.mean(kernel_ms))
+    hbm_peak, hbm_src = measured_peaks()
+    traffic, traffic_src, pipe_pct = ncu_traffic(W.name, args.scale, world if args.scaling == "strong" else 1)
+    if wl["store_all"]:
+        ach = BYTES_PER_STORED_STEP * steps_per_pass / (k_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,
+                "kernel": "leapfrog_kernel<MW_V2,STORE>",
+                "kernel_ms": k_ms, "algorithmic_bytes_per_orbit_step": BYTES_PER_STORED_STEP,
+                "algorithmic_bytes_per_launch": BYTES_PER_STORED_STEP * steps_per_pass}
+    else:
+        if W.integ == _lib.LEAPFROG:
+            per = FLOP_PER_STEP["leapfrog_lm10" if wl.get("potential") == "lm10" else "leapfrog_v2"]
+            flops = per * steps_per_pass
+            kname = {"evolving_mw": "leapfrog_kernel<MW_V2_T>", "lm10": "leapfrog_kernel<GENERAL>"}.get(wl.get("potential"), "leapfrog_kernel<MW_V2>")
+        else:
+            # 12 gradients + 1000 flop of stage algebra per accepted step (SURVEY 8d), per launch
+            flops = FLOP_PER_STEP["dop853_v2"] * float(stats_run[0])
+            kname = "dop853_kernel<MW_V2%s>" % (",DENSE" if W.integ == _lib.DOP853_DENSE else "")
+            per = FLOP_PER_STEP["dop853_v2"]
+        ach = flops / (k_ms * 1e-3) / 1e12
+        roof = {"bound": "fp64", "achieved": ach, "peak": peak_fp64, "unit": "TFLOP/s", "frac": ach / peak_fp64,
+                "traffic": traffic if W.integ == _lib.LEAPFROG else None, "traffic_source": traffic_src if W.integ == _lib.LEAPFROG else None,
+                "algorithmic_bytes_per_launch": float(108 * W.n + 28 * W.K),
+                "fp64_pipe_busy_ncu": (pipe_pct / 100.0) if (pipe_pct is not None and W.integ == _lib.LEAPFROG) else None,
+                "peak_source": "measured live: DFMA micro-benchmark cw_measure_fp64_peak (MEASURED_PEAKS.json has no "
+                               "FP64 entry; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
+                "kernel": kname, "kernel_ms": k_ms, "prepass_sort_pilot_ms": float(np.mean(total_kernel_ms)) - k_ms,
+                "algorithmic_flop_per_unit": per,
+                "kernel_share_of_step": k_ms / (dev_ms / steps)}
+    run = {"n_orbits_total": int(sum_over_ranks(float(W.n))), "n_kick_events_rank0": W.K,
+           "orbit_steps_per_step": int(total_steps), "failed_orbits_rank0": n_failed}
+    if W.integ != _lib.LEAPFROG:
+        run["dop853"] = {"accepted_steps": int(stats_run[0]), "rejected_steps": int(stats_run[1]),
+                         "gradient_evals": int(stats_run[2]), "intervals": int(stats_run[3]),
+                         "gradient_evals_per_s": float(stats_run[2]) / (k_ms * 1e-3)}
+    return dict(value=value, ms_per_step=dev_ms / steps, e2e=e2e, roofline=roof, run=run, launches=int(launches),
+                clocks=clocks, total_steps=total_steps)
+
+
+def population_e2e(size_label, n_binaries, horizon_gyr, cfg_id, ctx, reps=1):
+    """B200Population.perform_galactic_evolution() from synthetic bpp / kick_info / initial_binaries DataFrames: the whole
+    galactic stage as a Population user runs it, with the host pipeline itemised."""
+    from cogsworth_b200.batch import build_orbit_batch
+    from cogsworth_b200.events import identify_event_tables
+    from cogsworth_b200.pop import B200Population
+    from cogsworth_b200.synthetic import make_population, population_tables
+    pop = make_population(n_binaries, cfg_id=cfg_id, horizon_gyr=horizon_gyr, f_sn=1.0)
+    galaxy, bpp, kick_info, initial_binaries = population_tables(pop)
+    P = B200Population(galaxy, bpp, kick_info, initial_binaries, galactic_potential=pop.potential, max_ev_time=12.0,
+                       timestep_size=1.0, store_entire_orbits=False, integrator="leapfrog")
+    P._cw_context = ctx
+    P.disrupted                                   # cached by the reference as well (pop.py:861-874)
+    best, items = None, None
+    for _ in range(reps + 1):                     # first pass warms the page-locked cache
+        t0 = time.perf_counter()
+        P.perform_galactic_evolution(progress_bar=False)
+        fp = P.final_pos
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best = dt
+    # itemise the host side by running its stages on their own
+    t0 = time.perf_counter(); pe, se = identify_event_tables(P); t_ev = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    b = build_orbit_batch(pop.pos_kpc, pop.vel_kms, pop.tau_gyr, 12.0, 1.0, P.disrupted, pe, se)
+    t_b = time.perf_counter() - t0
+    from cogsworth_b200 import kicks
+    t0 = time.perf_counter()
+    kicks.integrate_orbits(b, potential=pop.potential, store_all=False, integrator="leapfrog", context=ctx)
+    t_i = time.perf_counter() - t0
+    steps = float(P._last_integration_info["stats"][3])
+    assert np.isfinite(np.asarray(fp)).all()
+    return {"size": size_label, "n_binaries": int(n_binaries), "n_orbits": int(b.n_orbits), "orbit_steps": steps,
+            "seconds": best, "value": steps / best, "unit": "orbit-steps/s",
+            "seconds_itemised": {"identify_event_tables (numpy joins of bpp / kick_info / initial_binaries)": t_ev,
+                                 "build_orbit_batch (w0, start times, grid classes, kick rotation, CSR)": t_b,
+                                 "integrate_orbits (H2D + kernels + D2H + OrbitArray)": t_i,
+                                 "rest (Quantity -> array, stacking, final_pos)": max(best - t_ev - t_b - t_i, 0.0)},
+            "how": "B200Population(initial_galaxy, bpp, kick_info, initial_binaries).perform_galactic_evolution(); "
+                   "final_pos read back; leapfrog, final state only"}
 
 
 def main():
@@ -295,164 +536,83 @@ def main():
         torch.cuda.synchronize()
 
     from cogsworth_b200 import dist as cwdist
+    max_over_ranks = lambda x: cwdist.reduce_scalar(x, "max", device=dev)
+    sum_over_ranks = lambda x: cwdist.reduce_scalar(x, "sum", device=dev)
 
-    def max_over_ranks(x):
-        return cwdist.reduce_scalar(x, "max", device=dev)
-
-    def sum_over_ranks(x):
-        return cwdist.reduce_scalar(x, "sum", device=dev)
-
+    ctx = cb.Context(devices=[local_rank])
+    peak = ctx.measure_fp64_peak(0, 200.0)
     pop = build_shard(wl, rank, world, args.scaling, args.scale)
     pot_label = apply_workload_potential(wl, pop)
-    b = pop.batch
-    n, K = b.n_orbits, b.n_events
-    integ = {"leapfrog": _lib.LEAPFROG, "dop853": _lib.DOP853, "dop853_dense": _lib.DOP853_DENSE}[wl["integrator"]]
-    tol = dict(atol=wl.get("atol", 1e-10), rtol=wl.get("rtol", 1e-10))
-    ctx = cb.Context(devices=[local_rank])
     ctx.set_potential(pop.potential)
-
-    # ---- host (pinned) and device copies of the inputs -------------------------------------------
-    def pinned(a, dtype):
-        t = torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
-        return t.pin_memory()
-
-    f64, i32, i64 = torch.float64, torch.int32, torch.int64
-    H = dict(w0=pinned(b.w0, f64), t1=pinned(b.t1, f64), t2=pinned(b.t2, f64), dt=pinned(b.dt, f64),
-             to_myr=pinned(b.to_myr, f64), flags=pinned(b.flags, i32))
-    if K:
-        H.update(ev_off=pinned(b.ev_off, i64), ev_time=pinned(b.ev_time, f64), ev_dv=pinned(b.ev_dv, f64))
-    else:
-        H.update(ev_off=None, ev_time=None, ev_dv=None)
-    D = {k: (v.to(dev) if v is not None else None) for k, v in H.items()}
-    traj_off_h = traj_off_d = traj_pos_d = traj_vel_d = None
-    total_cols = 0
-    if wl["store_all"]:
-        nn, _ = ctx.count_nodes(b.w0, b.t1, b.t2, b.dt, b.to_myr, b.flags, b.ev_off, b.ev_time, b.ev_dv)
-        off = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum(nn, out=off[1:])
-        total_cols = int(off[-1])
-        traj_off_h = pinned(off, i64)
-        traj_off_d = traj_off_h.to(dev)
-        traj_pos_d = torch.empty((3, total_cols), dtype=f64, device=dev)
-        traj_vel_d = torch.empty((3, total_cols), dtype=f64, device=dev)
-    wf_d = torch.empty((6, n), dtype=f64, device=dev)
-    st_d = torch.empty(n, dtype=i32, device=dev)
-    stats_d = torch.zeros(4, dtype=i64, device=dev)
-    wf_h = torch.empty((6, n), dtype=f64).pin_memory()
-    st_h = torch.empty(n, dtype=i32).pin_memory()
-    stats_h = np.zeros(4, dtype=np.int64)
-    stream = torch.cuda.current_stream(dev)
-
-    def step_device():
-        ctx.integrate_raw(n, D["w0"], D["t1"], D["t2"], D["dt"], D["to_myr"], D["flags"], D["ev_off"], D["ev_time"],
-                          D["ev_dv"], wf_d, st_d, None, None, traj_off_d, traj_pos_d, traj_vel_d, None, stats_d,
-                          integrator=integ, mem_space=_lib.MEM_DEVICE, stream=stream.cuda_stream, **tol)
-
-    def step_host():
-        ctx.integrate_raw(n, H["w0"], H["t1"], H["t2"], H["dt"], H["to_myr"], H["flags"], H["ev_off"], H["ev_time"],
-                          H["ev_dv"], wf_h, st_h, None, None, None, None, None, None, stats_h,
-                          integrator=integ, mem_space=_lib.MEM_HOST, **tol)
-
-    # ---- device-resident throughput ("value") ------------------------------------------------------
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    steps_per_pass = int(stats_d.cpu()[3])
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, total_kernel_ms, launches = [], [], 0
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-        kernel_ms.append(ctx.last_kernel_ms(0))
-        total_kernel_ms.append(ctx.last_total_kernel_ms(0))
-        launches += ctx.last_launch_count
-    e1.record(stream)
-    barrier()
-    dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if sampler else None
-    stats_run = stats_d.cpu().numpy().copy()
-    total_steps = sum_over_ranks(float(steps_per_pass))
-    value = total_steps * args.steps / (dev_ms * 1e-3)
-
-    # ---- end to end through the C ABI with pinned host buffers -------------------------------------
-    e2e = None
-    if not wl["store_all"]:
-        for _ in range(max(1, min(args.warmup, 2))):
-            step_host()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_host()
-        barrier()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
-        assert np.array_equal(wf_h.numpy(), wf_d.cpu().numpy()), "host-buffer path and device path disagree"
-        h2d = sum(v.numel() * v.element_size() for v in H.values() if v is not None)
-        d2h = wf_h.numel() * 8 + st_h.numel() * 4 + 32
-        e2e = {"value": total_steps * args.steps / e2e_s, "unit": "orbit-steps/s",
-               "h2d_bytes_per_step": int(sum_over_ranks(float(h2d))), "d2h_bytes_per_step": int(sum_over_ranks(float(d2h))),
-               "ms_per_step": 1e3 * e2e_s / args.steps,
-               "how": "cw_integrate(CW_MEM_HOST) on pinned host arrays: H2D of w0/t1/t2/dt/to_myr/flags/events, grid "
-                      "pre-pass + integrator kernels, D2H of w_final/status, host wall clock, max over ranks"}
-    n_failed = int((st_d != 0).sum().item())
-    n_total = int(sum_over_ranks(float(n)))
-
-    # ---- roofline of the dominant kernel -------------------------------------------------------------
-    k_ms = float(np.mean(kernel_ms))
-    hbm_peak, hbm_src = measured_peaks()
-    traffic, traffic_src, pipe_pct = ncu_traffic(args.workload, args.scale, world if args.scaling == "strong" else 1)
-    if wl["store_all"]:
-        ach = BYTES_PER_STORED_STEP * steps_per_pass / (k_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,
-                "kernel": "leapfrog_kernel<MW_V2,STORE>",
-                "kernel_ms": k_ms, "algorithmic_bytes_per_orbit_step": BYTES_PER_STORED_STEP,
-                "algorithmic_bytes_per_launch": BYTES_PER_STORED_STEP * steps_per_pass}
-    else:
-        peak = ctx.measure_fp64_peak(0, 200.0)
-        if integ == _lib.LEAPFROG:
-            per = FLOP_PER_STEP["leapfrog_lm10" if wl.get("potential") == "lm10" else "leapfrog_v2"]
-            flops = per * steps_per_pass
-            kname = {"evolving_mw": "leapfrog_kernel<MW_V2_T>", "lm10": "leapfrog_kernel<GENERAL>"}.get(wl.get("potential"), "leapfrog_kernel<MW_V2>")
-        else:
-            # 12 gradients + 1000 flop of stage algebra per accepted step, per launch
-            flops = FLOP_PER_STEP["dop853_v2"] * float(stats_run[0])
-            kname = "dop853_kernel<MW_V2%s>" % (",DENSE" if integ == _lib.DOP853_DENSE else "")
-            per = FLOP_PER_STEP["dop853_v2"]
-        ach = flops / (k_ms * 1e-3) / 1e12
-        roof = {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": traffic if integ == _lib.LEAPFROG else None, "traffic_source": traffic_src if integ == _lib.LEAPFROG else None,
-                "algorithmic_bytes_per_launch": float(108 * n + 28 * K),
-                "fp64_pipe_busy_ncu": (pipe_pct / 100.0) if (pipe_pct is not None and integ == _lib.LEAPFROG) else None,
-                "peak_source": "measured live: DFMA micro-benchmark cw_measure_fp64_peak (MEASURED_PEAKS.json has no "
-                               "FP64 entry; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
-                "kernel": kname, "kernel_ms": k_ms, "prepass_sort_pilot_ms": float(np.mean(total_kernel_ms)) - k_ms,
-                "algorithmic_flop_per_unit": per,
-                "kernel_share_of_step": k_ms / (dev_ms / args.steps)}
-
+    W = Workload(args.workload, wl, pop, ctx, dev, torch, _lib)
+    main_res = measure(W, args.steps, args.warmup, barrier, max_over_ranks, sum_over_ranks, peak, world, args,
+                       sampler_index=local_rank if rank == 0 else None, with_variants=(world == 1))
     cbase = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cbase, _, _ = cpu_baseline(pop, wl, args.cpu_sample_orbits)
+    W.free()
+    del W
+
+    # ---- the other BASELINE configs and the Population-level end-to-end figure (one GPU, rank 0) -----------------
+    others, pop_e2e = None, None
+    single = (lambda x: x)
+    if rank == 0 and world == 1 and args.workload == "config4" and args.scale == 1.0 and not args.no_other_workloads:
+        others = {}
+        for name in ("config2", "config2_dop853", "config5", "config3"):
+            owl = WORKLOADS[name]
+            opop = build_shard(owl, 0, 1, "strong", 1.0)
+            apply_workload_potential(owl, opop)
+            ctx.set_potential(opop.potential)
+            OW = Workload(name, owl, opop, ctx, dev, torch, _lib)
+            r = measure(OW, 2, 2, torch.cuda.synchronize, single, single, peak, 1, args)
+            others[name] = {"workload": owl["desc"], "value": r["value"], "unit": "orbit-steps/s",
+                            "ms_per_step": r["ms_per_step"],
+                            "e2e": None if r["e2e"] is None else {k: r["e2e"][k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+                            "roofline": {k: r["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel", "kernel_ms")},
+                            "run": r["run"], "steps": 2, "warmup": 2}
+            OW.free()
+            del OW, opop
+        ctx.set_potential(pop.potential)
+        pop_e2e = [population_e2e("config 2 (1e5 binaries, Wagg2022 horizons)", 100_000, None, 2, ctx),
+                   population_e2e("config 4 (1e7 orbits = 5.56e6 binaries, 1 Gyr)", int(round(10_000_000 / 1.8)), 1.0, 4, ctx)]
+
+    # ---- N > 1: the same 10^7 orbits through ONE process driving every GPU (what a Population user gets) --------------
+    inproc = None
+    if world > 1 and not args.no_inprocess:
+        barrier()
+        if rank == 0:
+            full = build_shard(wl, 0, 1, "strong", args.scale)
+            apply_workload_potential(wl, full)
+            with cb.Context(devices=list(range(world))) as call:
+                call.set_potential(full.potential)
+                from cogsworth_b200 import kicks
+                run1 = lambda: kicks.integrate_orbits(full.batch, potential=full.potential, store_all=False,
+                                                      integrator=wl["integrator"], context=call)
+                run1(); run1()
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    _, info = run1()
+                dt = time.perf_counter() - t0
+                st = float(info["stats"][3])
+                inproc = {"value": st * args.steps / dt, "unit": "orbit-steps/s", "ms_per_step": 1e3 * dt / args.steps,
+                          "how": f"rank 0 alone, one cw_ctx on all {world} GPUs (one host thread per device, orbits sharded by "
+                                 "index), kicks.integrate_orbits on the whole workload; the other ranks idle at a barrier"}
+        barrier()
 
     if rank == 0:
-        line = {"metric": "FP64 orbit-steps/sec", "value": value, "unit": "orbit-steps/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        numa_note = f"; ranks bound to their GPU's NUMA node (rank 0: node {numa_node})" if numa_node is not None else ""
+        line = {"metric": "FP64 orbit-steps/sec", "value": main_res["value"], "unit": "orbit-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
                 "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
-                "config": {"workload": f"{args.workload}: {wl['desc']}" + ("" if args.scale == 1.0 else f" [SCALED x{args.scale}: not a valid bench line]"),
-                           "n_orbits_total": n_total,
-                           "n_kick_events_rank0": K, "orbit_steps_per_step": int(total_steps),
-                           "integrator": wl["integrator"], "potential": pot_label,
-                           "parallelism": f"orbits sharded by index over {world} GPU(s), no collective"
-                                          + (f"; ranks bound to their GPU's NUMA node (rank 0: node {numa_node})" if numa_node is not None else ""),
-                           "cache": "inputs + outputs (>= 1 GB per pass) exceed the 126 MB L2; nothing is reused between steps",
-                           "failed_orbits_rank0": n_failed},
-                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cbase}
-        if integ != _lib.LEAPFROG:
-            line["config"]["dop853"] = {"accepted_steps": int(stats_run[0]), "rejected_steps": int(stats_run[1]),
-                                        "gradient_evals": int(stats_run[2]), "intervals": int(stats_run[3]),
-                                        "gradient_evals_per_s": float(stats_run[2]) / (k_ms * 1e-3)}
+                "data": "synthetic", "config": config_block(args, wl, world, pot_label, numa_note),
+                "e2e": main_res["e2e"], "gpu_launches": main_res["launches"], "clocks": main_res["clocks"],
+                "roofline": main_res["roofline"], "cpu_baseline": cbase, "run": main_res["run"]}
+        if others is not None:
+            line["other_workloads"] = others
+        if pop_e2e is not None:
+            line["population_e2e"] = pop_e2e
+        if inproc is not None:
+            line["e2e"]["in_process_all_gpus"] = inproc
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

@@ -55,7 +55,7 @@ GRID_CLASS_DTYPE = np.dtype([("t2", "<f8"), ("dt", "<f8"), ("to_myr", "<f8"), ("
 class CwResult(C.Structure):
     _fields_ = [("w_final", C.c_void_p), ("status", C.c_void_p), ("n_nodes", C.c_void_p),
                 ("ev_step", C.c_void_p), ("traj_off", C.c_void_p), ("traj_pos", C.c_void_p),
-                ("traj_vel", C.c_void_p), ("traj_t", C.c_void_p), ("stats", C.c_void_p)]
+                ("traj_vel", C.c_void_p), ("traj_t", C.c_void_p), ("stats", C.c_void_p), ("n_failed", C.c_void_p)]
 
 
 class NativeLibraryError(RuntimeError):
@@ -278,14 +278,14 @@ class Context:
                       n_nodes=None, ev_step=None, traj_off=None, traj_pos=None, traj_vel=None,
                       traj_t=None, stats=None, integrator=LEAPFROG, mem_space=MEM_HOST, atol=1e-10,
                       rtol=1e-10, nmax=0, stream=None, no_sync=False, n_w0=0, w0_index=None, grid_class=None,
-                      classes=None, ev_off32=None):
+                      classes=None, ev_off32=None, n_failed=None):
         """``cw_integrate`` on raw buffers (numpy / torch / int addresses).  The keyword arguments after ``no_sync``
         are the compact host forms of ABI 2 (``cw_batch`` in include/cogsworth_b200.h)."""
         o = self._opts(integrator, mem_space, atol, rtol, nmax, stream, no_sync)
         b = self._batch(n, w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv, n_w0, w0_index, grid_class,
                         classes, ev_off32)
         r = CwResult(ptr(w_final), ptr(status), ptr(n_nodes), ptr(ev_step), ptr(traj_off), ptr(traj_pos),
-                     ptr(traj_vel), ptr(traj_t), ptr(stats))
+                     ptr(traj_vel), ptr(traj_t), ptr(stats), ptr(n_failed))
         self._check(self._L.cw_integrate(self._h, C.byref(o), C.byref(b), C.byref(r)), "cw_integrate")
 
     def count_nodes_raw(self, n, w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv, n_nodes,
@@ -299,7 +299,8 @@ class Context:
     # -- numpy convenience ---------------------------------------------------------------------
     @staticmethod
     def _prep(w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv):
-        w0 = np.ascontiguousarray(w0, dtype=np.float64)
+        if not (isinstance(w0, np.ndarray) and w0.strides[-1] == 0):      # (a broadcast placeholder stays one)
+            w0 = np.ascontiguousarray(w0, dtype=np.float64)
         if w0.ndim != 2 or w0.shape[0] != 6:
             raise ValueError("w0 must have shape (6, n_orbits)")
         n = w0.shape[1]
@@ -324,10 +325,13 @@ class Context:
     def count_nodes(self, w0, t1, t2, dt, to_myr=1.0, flags=0, ev_off=None, ev_time=None, ev_dv=None):
         """Node count of every orbit and the node index of every event (the grid pre-pass alone); ``w0`` is not
         read and may be ``None``."""
-        if w0 is None:
-            w0 = np.zeros((6, np.asarray(t1).shape[0]))
+        no_w0 = w0 is None
+        if no_w0:
+            w0 = np.broadcast_to(np.zeros((6, 1)), (6, np.asarray(t1).shape[0]))
         n, K, w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv = self._prep(
             w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv)
+        if no_w0:
+            w0 = None
         n_nodes = np.zeros(n, dtype=np.int32)
         ev_step = np.full(max(K, 1), -1, dtype=np.int32)
         self.count_nodes_raw(n, w0, t1, t2, dt, to_myr, flags, ev_off, ev_time, ev_dv, n_nodes, ev_step)
@@ -357,7 +361,8 @@ class Context:
         get = a.get
         # results live in page-locked memory from the library's cache: the D2H copies land in them directly
         out = dict(w_final=pinned_empty((6, n)), status=pinned_empty(n, np.int32), n_nodes=pinned_empty(n, np.int32),
-                   ev_step=pinned_empty(max(K, 1), np.int32), stats=np.zeros(4, dtype=np.int64))
+                   ev_step=pinned_empty(max(K, 1), np.int32), stats=np.zeros(4, dtype=np.int64),
+                   n_failed=np.zeros(1, dtype=np.int64))
         compact = dict(n_w0=get("n_w0", 0), w0_index=get("w0_index"), grid_class=get("grid_class"),
                        classes=get("classes"), ev_off32=get("ev_off32"))
         traj_off = traj_pos = traj_vel = traj_t = None
@@ -375,14 +380,15 @@ class Context:
         self.integrate_raw(n, get("w0"), get("t1"), get("t2"), get("dt"), get("to_myr"), get("flags"), get("ev_off"),
                            get("ev_time"), get("ev_dv"), out["w_final"], out["status"], out["n_nodes"], out["ev_step"],
                            traj_off, traj_pos, traj_vel, traj_t, out["stats"], integrator=integrator,
-                           mem_space=MEM_HOST, atol=atol, rtol=rtol, nmax=nmax, **compact)
+                           mem_space=MEM_HOST, atol=atol, rtol=rtol, nmax=nmax, n_failed=out["n_failed"], **compact)
+        out["n_failed"] = int(out["n_failed"][0])
         if K == 0:
             out["ev_step"][:] = -1
         out["ev_step"] = out["ev_step"][:K]
         if store_all:
             # the kernels write nothing for orbits the pre-pass rejected, and stop writing where an orbit fails:
             # those columns (few) are marked, not the whole buffer
-            bad = np.flatnonzero(out["status"] != 0)
+            bad = np.flatnonzero(out["status"] != 0) if out["n_failed"] else ()
             for i in bad:
                 sl = slice(int(traj_off[i]), int(traj_off[i + 1]))
                 traj_pos[:, sl] = np.nan

@@ -151,6 +151,21 @@ class OrbitBatch:
                     grid_class=c["grid_class"], classes=c["classes"], ev_off32=c["ev_off32"] if K else None,
                     ev_time=self.ev_time if K else None, ev_dv=self.ev_dv if K else None)
 
+    def head(self, n_orbits: int) -> "OrbitBatch":
+        """The first ``n_orbits`` orbits; keeps the compact form when only secondaries are dropped."""
+        c = self.compact
+        if c is None or n_orbits < c["n_w0"]:
+            out = self.take(np.arange(n_orbits))
+            out.n_primary = min(self.n_primary, n_orbits)
+            return out
+        k = n_orbits - c["n_w0"]
+        K = int(c["ev_off32"][n_orbits]) if c["ev_off32"] is not None else 0
+        c2 = dict(c, w0_index=c["w0_index"][:k], grid_class=c["grid_class"][:n_orbits],
+                  ev_off32=None if c["ev_off32"] is None else c["ev_off32"][:n_orbits + 1])
+        return OrbitBatch(ev_time=None if self.ev_time is None else self.ev_time[:K],
+                          ev_dv=None if self.ev_dv is None else self.ev_dv[:K], n_primary=self.n_primary,
+                          secondary_of=None if self.secondary_of is None else self.secondary_of[:k], compact=c2)
+
     def take(self, idx) -> "OrbitBatch":
         """Sub-batch in the plain layout (used by the retry loop for failed orbits)."""
         idx = np.asarray(idx, dtype=np.int64)

@@ -768,6 +768,8 @@ static int integrate_device(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, co
     if (rc != CW_OK) { cudaStreamSynchronize(pl.stream); ctx->last_error = s.error; return rc; }
     if (integrate && R->stats)
         CW_CK(ctx, cudaMemcpyAsync(R->stats, A.stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, pl.stream));
+    if (integrate && R->n_failed)
+        CW_CK(ctx, cudaMemcpyAsync(R->n_failed, A.stats + 4, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, pl.stream));
     if (o->no_sync) {
         CW_CK(ctx, cudaEventRecord(s.pending, pl.stream));
         s.has_pending = true;
@@ -1409,18 +1411,19 @@ static int integrate_host(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
     }
     if (rc != CW_OK) return rc;
     // ---- statistics and kernel times
-    int64_t stats[4] = {0, 0, 0, 0};
+    int64_t stats[5] = {0, 0, 0, 0, 0};
+    const bool want_stats = integrate && (R->stats || R->n_failed);
     for (int d = 0; d < nslots; d++) {
         if (per_slot[d].empty()) continue;
         Slot &s = ctx->slots[d];
         cudaSetDevice(s.dev);
         const size_t mstride = Arena::padded(8, 8) / 8;       // one padded block of 8 counters per chunk
         std::vector<unsigned long long> hs(mstride * per_slot[d].size(), 0ull);
-        if (integrate && R->stats)
+        if (want_stats)
             CW_CK(ctx, cudaMemcpy(hs.data(), s.meta.base, hs.size() * 8, cudaMemcpyDeviceToHost));
         for (size_t k = 0; k < per_slot[d].size(); k++) {
             const Plan &pl = per_slot[d][k]->plan;
-            for (int q = 0; q < 4; q++) stats[q] += (int64_t)hs[mstride * k + 1 + q];
+            for (int q = 0; q < 5; q++) stats[q] += (int64_t)hs[mstride * k + 1 + q];
             if (pl.timed) {
                 float ms = 0.f;
                 if (cudaEventElapsedTime(&ms, pl.ev_k0, pl.ev_k1) == cudaSuccess) s.last_kernel_ms += ms;
@@ -1443,7 +1446,8 @@ static int integrate_host(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
                     c.lane, (long long)c.m1, (long long)c.m2, a, b, e);
         }
     }
-    if (integrate && R->stats) memcpy(R->stats, stats, sizeof stats);
+    if (integrate && R->stats) memcpy(R->stats, stats, 4 * sizeof(int64_t));
+    if (integrate && R->n_failed) *R->n_failed = stats[4];
     return CW_OK;
 }
 

@@ -233,7 +233,10 @@ __device__ __forceinline__ void dp_write_final(const IntegArgs &A, const DpLane 
     const int64_t n = A.n;
 #pragma unroll
     for (int c = 0; c < 6; c++) A.w_final[c * n + s.oid] = s.y[c];
-    if (status != CW_ORBIT_OK) A.status[s.oid] = status;
+    if (status != CW_ORBIT_OK) {
+        A.status[s.oid] = status;
+        if (A.stats) atomicAdd(A.stats + 4, 1ull);      // cw_result.n_failed
+    }
 }
 
 // kicks on node s.j: v += dv, the velocity half of k1 follows, the segment restarts with a new dt0

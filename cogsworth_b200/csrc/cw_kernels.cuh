@@ -36,7 +36,7 @@ struct IntegArgs {
     // DOP853
     double atol, rtol;
     int64_t nmax;
-    unsigned long long *stats; // 4: accepted, rejected, gradient evaluations, orbit-steps
+    unsigned long long *stats; // 5: accepted, rejected, gradient evaluations, orbit-steps, orbits with status != OK
     int32_t *cost_key;         // n   DOP853 pilot: float bits of the estimated step attempts per orbit
     int32_t pilot_intervals;   // intervals the pilot integrates
 };

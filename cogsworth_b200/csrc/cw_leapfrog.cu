@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(256) grid_prepass_kernel(const __grid_constant
     if (A.traj_off && st == CW_ORBIT_OK && A.traj_off[i + 1] - A.traj_off[i] < (int64_t)n_nodes) st = CW_ORBIT_CAPACITY;
     A.n_nodes[i] = n_nodes;
     A.status[i] = st;
+    if (st != CW_ORBIT_OK && A.stats) atomicAdd(A.stats + 4, 1ull);     // cw_result.n_failed
     if (A.t_last) A.t_last[i] = Tprev;     // time of node n_acc - 1 (DOP853 dense mode: end of the last segment)
     if (iota) iota[i] = (int32_t)i;
     if (sort_key) {

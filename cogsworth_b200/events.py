@@ -100,13 +100,19 @@ def _primary_secondary(p):
     # ... and only for disrupted binaries, in bin_nums[disrupted] order         (events.py:70)
     bin_nums = np.asarray(p.bin_nums).astype(np.int64)
     dis_bins = bin_nums[np.asarray(p.disrupted, dtype=bool)]
-    sec_rows = []
+    sec_idx = np.zeros(0, dtype=np.int64)
     if len(dis_bins) and len(rows["bin_num"]):
-        o = np.argsort(rows["bin_num"], kind="stable")
-        sb = rows["bin_num"][o]
+        sb = rows["bin_num"]
+        o = None
+        if len(sb) > 1 and np.any(sb[1:] < sb[:-1]):        # bpp is normally grouped by bin_num already
+            o = np.argsort(sb, kind="stable")
+            sb = sb[o]
         lo, hi = np.searchsorted(sb, dis_bins, "left"), np.searchsorted(sb, dis_bins, "right")
-        sec_rows = [o[a:b] for a, b in zip(lo, hi)]
-    sec_idx = np.concatenate(sec_rows) if len(sec_rows) else np.zeros(0, dtype=np.int64)
+        lens = hi - lo
+        ends = np.cumsum(lens)
+        sec_idx = np.repeat(lo - (ends - lens), lens) + np.arange(int(ends[-1]) if len(ends) else 0)
+        if o is not None:
+            sec_idx = o[sec_idx]
     m = np.zeros(len(rows["bin_num"]), dtype=bool)
     sec = _select(rows, sec_idx, dv_sec) if len(sec_idx) else _select(rows, m, dv_sec)
     return prim, sec, bin_nums
@@ -128,11 +134,18 @@ def identify_events(p):
 
 def _table(t, bin_nums):
     """EventTable whose owners are positions in ``bin_nums``, grouped by owner, time order kept."""
-    order_b = np.argsort(bin_nums, kind="stable")
-    owner = order_b[np.searchsorted(bin_nums[order_b], t["bin_num"])] if len(t["bin_num"]) else \
-        np.zeros(0, dtype=np.int64)
-    o = np.argsort(owner, kind="stable")      # stable: keeps the chronological bpp order per system
-    return EventTable(owner[o].astype(np.int64), t["tphys"][o], t["dv"][o], t["phase"][o], t["inc"][o])
+    if not len(t["bin_num"]):
+        return EventTable.empty()
+    if len(bin_nums) > 1 and np.any(bin_nums[1:] < bin_nums[:-1]):
+        order_b = np.argsort(bin_nums, kind="stable")
+        owner = order_b[np.searchsorted(bin_nums[order_b], t["bin_num"])]
+    else:                                     # the population is in bin_num order (the usual case)
+        owner = np.searchsorted(bin_nums, t["bin_num"])
+    owner = owner.astype(np.int64, copy=False)
+    if len(owner) > 1 and np.any(owner[1:] < owner[:-1]):
+        o = np.argsort(owner, kind="stable")  # stable: keeps the chronological bpp order per system
+        return EventTable(owner[o], t["tphys"][o], t["dv"][o], t["phase"][o], t["inc"][o])
+    return EventTable(owner, t["tphys"], t["dv"], t["phase"], t["inc"])
 
 
 def identify_event_tables(p):

@@ -144,7 +144,8 @@ def integrate_orbits(batch: OrbitBatch, potential=None, store_all=True, integrat
     res = run(batch)
     status = res["status"]
     n = batch.n_orbits
-    if np.any(status == -1):
+    clean = res.get("n_failed", -1) == 0           # nothing failed: no per-orbit scan of a 10^7-orbit batch below
+    if not clean and np.any(status == -1):
         bad = np.flatnonzero(status == -1)
         raise ValueError(f"{len(bad)} orbit(s) have inconsistent events/time grid (first: orbit {bad[0]}); "
                          "the reference fails to stitch such orbits (kicks.py:187-189)")
@@ -158,7 +159,7 @@ def integrate_orbits(batch: OrbitBatch, potential=None, store_all=True, integrat
     # retries only exist on the events branch, max_retries attempts in total (reference quirk Q4)
     kicked = None
     dt_scale = 1.0
-    for _ in range(max(int(max_retries) - 1, 0)):
+    for _ in range(0 if clean else max(int(max_retries) - 1, 0)):
         failed = np.flatnonzero(status != 0)
         if len(failed) == 0:
             break
@@ -179,7 +180,7 @@ def integrate_orbits(batch: OrbitBatch, potential=None, store_all=True, integrat
                 if store_all:
                     a, b = r["traj_off"][k], r["traj_off"][k + 1]
                     retry_results[i] = (r["traj_pos"][:, a:b], r["traj_vel"][:, a:b], r["traj_t"][a:b])
-    ok = status == 0
+    ok = None if clean else status == 0
     if store_all:
         off, pos, vel, t = pieces["off"], pieces["pos"], pieces["vel"], pieces["t"]
         if retry_results:   # rebuild the SoA buffers with the re-gridded orbits spliced in
@@ -202,7 +203,8 @@ def integrate_orbits(batch: OrbitBatch, potential=None, store_all=True, integrat
         if final_times:
             t_final = _grid_times_myr(batch, n_nodes)
         else:       # the label of the one stored sample: t2 on the events branch (appended), unknown without a walk
-            t_final = np.where((batch.flags & 1) == 1, batch.t2 * batch.to_myr, np.nan)
+            def t_final():
+                return np.where((batch.flags & 1) == 1, batch.t2 * batch.to_myr, np.nan)
         orbits = OrbitArray.from_final(w_final, t_final, ok)
     info = dict(status=status, n_nodes=n_nodes, ev_step=res["ev_step"], stats=res["stats"], w_final=w_final)
     return orbits, info

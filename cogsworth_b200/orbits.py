@@ -127,30 +127,63 @@ class OrbitArray:
     """
 
     def __init__(self, offsets, pos, vel, t, ok=None, index=None):
-        self.offsets = np.asarray(offsets, dtype=np.int64)
-        self.pos, self.vel, self.t = pos, vel, t
-        n = len(self.offsets) - 1
-        self.ok = np.ones(n, dtype=bool) if ok is None else np.asarray(ok, dtype=bool)
-        self._index = np.arange(n) if index is None else np.asarray(index, dtype=np.int64)
+        # offsets = None: one sample per orbit (final-state runs) -- nothing of size n is built until it is asked for
+        self._offsets = None if offsets is None else np.asarray(offsets, dtype=np.int64)
+        self.pos, self.vel = pos, vel
+        self._t = t                                  # array, or a callable that makes it (labels are rarely read)
+        self._n = pos.shape[1] if offsets is None else len(self._offsets) - 1
+        self._ok = None if ok is None else np.asarray(ok, dtype=bool)     # None = every orbit succeeded
+        self._idx = None if index is None else np.asarray(index, dtype=np.int64)
 
     @classmethod
     def from_final(cls, w_final, t_final, ok=None):
-        """Final-state-only result (store_all=False): every orbit has exactly one sample."""
-        n = w_final.shape[1]
-        return cls(np.arange(n + 1, dtype=np.int64), w_final[:3], w_final[3:], np.asarray(t_final), ok)
+        """Final-state-only result (store_all=False): every orbit has exactly one sample.  ``t_final`` may be a
+        callable returning the (n,) array of time labels."""
+        return cls(None, w_final[:3], w_final[3:], t_final if callable(t_final) else np.asarray(t_final), ok)
+
+    @property
+    def offsets(self):
+        if self._offsets is None:
+            self._offsets = np.arange(self._n + 1, dtype=np.int64)
+        return self._offsets
+
+    @property
+    def t(self):
+        if callable(self._t):
+            self._t = np.asarray(self._t())
+        return self._t
+
+    @property
+    def ok(self):
+        if self._ok is None:
+            self._ok = np.ones(self._n, dtype=bool)
+        return self._ok
+
+    @property
+    def _index(self):
+        if self._idx is None:
+            self._idx = np.arange(self._n)
+        return self._idx
+
+    @property
+    def n_failed(self) -> int:
+        """Number of selected orbits whose integration failed (``None`` entries of the reference's array)."""
+        if self._ok is None:
+            return 0
+        return int((~self._ok[self._index]).sum()) if self._idx is not None else int((~self._ok).sum())
 
     # -- container protocol --------------------------------------------------------------------
     def __len__(self):
-        return len(self._index)
+        return self._n if self._idx is None else len(self._idx)
 
     @property
     def shape(self):
         return (len(self),)
 
     def _materialise(self, i):
-        if not self.ok[i]:
+        if self._ok is not None and not self._ok[i]:
             return None
-        a, b = self.offsets[i], self.offsets[i + 1]
+        a, b = (i, i + 1) if self._offsets is None else (self.offsets[i], self.offsets[i + 1])
         pos, vel, t = self.pos[:, a:b], self.vel[:, a:b], self.t[a:b]
         if _have_gala():
             import astropy.units as u
@@ -160,9 +193,9 @@ class OrbitArray:
 
     def __getitem__(self, key):
         if isinstance(key, (int, np.integer)):
-            return self._materialise(self._index[key])
+            return self._materialise(int(key) % self._n if self._idx is None else self._index[key])
         sub = self._index[key]
-        return OrbitArray(self.offsets, self.pos, self.vel, self.t, self.ok, np.atleast_1d(sub))
+        return OrbitArray(self._offsets, self.pos, self.vel, self._t, self._ok, np.atleast_1d(sub))
 
     def __iter__(self):
         for i in self._index:
@@ -182,6 +215,11 @@ class OrbitArray:
     def final_coords(self):
         """(final_pos [kpc], final_vel [km/s]) of shape (n, 3); ``inf`` rows for failed orbits
         (pop.py:1338-1348)."""
+        if self._offsets is None and self._idx is None:       # one sample per orbit: no gather at all
+            fp, fv = self.pos.T, self.vel.T * K.KMS_PER_KPC_MYR
+            if self._ok is not None and not self._ok.all():
+                fp, fv = np.where(self._ok[:, None], fp, np.inf), np.where(self._ok[:, None], fv, np.inf)
+            return fp, fv
         last = self.offsets[self._index + 1] - 1
         ok = self.ok[self._index] & (last >= self.offsets[self._index])
         last = np.where(ok, last, 0)

@@ -91,8 +91,8 @@ class GalacticStageB200:
             context=getattr(self, "_cw_context", None))
         self._last_integration_info = info
 
-        failed = ~orbits.ok
-        if failed.any():
+        if orbits.n_failed:
+            failed = ~orbits.ok
             orbit_bin_nums = np.concatenate((self.bin_nums, self.bin_nums[self.disrupted]))
             bad_bin_nums = orbit_bin_nums[failed]
             msg = (f"{failed.sum()} orbit(s) failed numerical integration, removing them. This can occur "

@@ -198,6 +198,68 @@ def population_with_n_orbits(n_orbits, **kw) -> SyntheticPopulation:
         nb = int(nb * 1.01) + 16
         pop = make_population(nb, **kw)
     if pop.batch.n_orbits > n_orbits:
-        pop.batch = pop.batch.take(np.arange(n_orbits))
-        pop.batch.n_primary = min(nb, n_orbits)
+        pop.batch = pop.batch.head(n_orbits)
     return pop
+
+
+def population_tables(pop: SyntheticPopulation, bin_num0: int = 0):
+    """The same synthetic population as the TABLES ``Population.perform_galactic_evolution`` reads
+    (pop.py:1195-1313): ``(InitialGalaxy, bpp, kick_info, initial_binaries)``, pandas frames
+    indexed by ``bin_num``, from which ``events.identify_events`` recovers exactly ``pop.primary_events`` /
+    ``pop.secondary_events``.  The first supernova of a system is star 1's (``evol_type`` 15), the second star 2's
+    (16); a disrupted system gets an ``evol_type`` 11 row and ends with ``sep < 0`` (pop.py:861-874).
+    INPUT GENERATION ONLY (stands in for COSMIC)."""
+    import pandas as pd
+    from .pop import InitialGalaxy
+    n = len(pop.tau_gyr)
+    bins = np.arange(n, dtype=np.int64) + int(bin_num0)
+    pe, se = pop.primary_events, pop.secondary_events
+    K_ = len(pe)
+    first = np.ones(K_, dtype=bool)
+    first[1:] = pe.owner[1:] != pe.owner[:-1]
+    star = np.where(first, 1, 2)
+    last = np.ones(K_, dtype=bool)
+    last[:-1] = pe.owner[1:] != pe.owner[:-1]
+    row_disrupted = last & pop.disrupted[pe.owner]
+    # secondary kick of every SN row: what the secondary table holds for disrupted systems, zero elsewhere (unused)
+    dv2 = np.zeros((K_, 3))
+    if len(se):
+        key_p = pe.owner.astype(np.int64) * 4 + star
+        first_s = np.ones(len(se), dtype=bool)
+        first_s[1:] = se.owner[1:] != se.owner[:-1]
+        key_s = se.owner.astype(np.int64) * 4 + np.where(first_s, 1, 2)
+        pos = np.searchsorted(key_p, key_s)
+        dv2[pos] = se.dv
+    kick_info = pd.DataFrame({
+        "star": star.astype(np.float64), "disrupted": row_disrupted.astype(np.float64),
+        "delta_vsysx_1": pe.dv[:, 0], "delta_vsysy_1": pe.dv[:, 1], "delta_vsysz_1": pe.dv[:, 2],
+        "delta_vsysx_2": dv2[:, 0], "delta_vsysy_2": dv2[:, 1], "delta_vsysz_2": dv2[:, 2],
+        "bin_num": bins[pe.owner]})
+    # COSMIC also writes star = 0 rows for systems without a supernova: one per system, ignored by the joins
+    kick_info = pd.concat([pd.DataFrame({c: (bins if c == "bin_num" else np.zeros(n)) for c in kick_info.columns}),
+                           kick_info], ignore_index=True)
+    kick_info = kick_info.sort_values(["bin_num", "star"], kind="stable")
+    kick_info.index = kick_info["bin_num"].values
+
+    # bpp: birth row, the SN rows, the disruption row, the final row -- sorted by system, then time
+    dis_rows = np.flatnonzero(row_disrupted)
+    b_bin = np.concatenate([bins, bins[pe.owner], bins[pe.owner[dis_rows]], bins])
+    b_t = np.concatenate([np.zeros(n), pe.tphys, pe.tphys[dis_rows], pop.tau_gyr * 1000.0])
+    b_type = np.concatenate([np.ones(n), np.where(star == 1, 15.0, 16.0), np.full(len(dis_rows), 11.0), np.full(n, 10.0)])
+    b_sep = np.concatenate([np.full(n, 100.0), np.where(row_disrupted, -1.0, 50.0), np.full(len(dis_rows), -1.0),
+                            np.where(pop.disrupted, -1.0, 10.0)])
+    b_ord = np.concatenate([np.zeros(n), np.ones(K_), np.full(len(dis_rows), 2.0), np.full(n, 3.0)])
+    o = np.lexsort((b_ord, b_t, b_bin))
+    bpp = pd.DataFrame({"tphys": b_t[o], "evol_type": b_type[o], "sep": b_sep[o], "bin_num": b_bin[o]})
+    bpp.index = bpp["bin_num"].values
+
+    ph = np.zeros((n, 2))
+    ic = np.zeros((n, 2))
+    ph[pe.owner, star - 1] = pe.phase
+    ic[pe.owner, star - 1] = pe.inc
+    initial_binaries = pd.DataFrame({"bin_num": bins, "metallicity": np.full(n, 0.02), "phase_sn_1": ph[:, 0],
+                                     "phase_sn_2": ph[:, 1], "inc_sn_1": ic[:, 0], "inc_sn_2": ic[:, 1]})
+    initial_binaries.index = bins
+    galaxy = InitialGalaxy(pop.tau_gyr, pop.pos_kpc[0], pop.pos_kpc[1], pop.pos_kpc[2],
+                           pop.vel_kms[0], pop.vel_kms[1], pop.vel_kms[2])
+    return galaxy, bpp, kick_info, initial_binaries

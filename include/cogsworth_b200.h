@@ -181,6 +181,8 @@ typedef struct cw_result {
     double *traj_vel;        /* 3 x traj_off[n_orbits]  kpc/Myr */
     double *traj_t;          /* traj_off[n_orbits]      Myr (may be NULL) */
     int64_t *stats;          /* 4 : DOP853 accepted steps, rejected steps, gradient evaluations, orbit-steps */
+    int64_t *n_failed;       /* 1 : number of orbits whose status is not CW_ORBIT_OK (ABI 2; may be NULL) -- lets the
+                                caller skip every per-orbit scan of a clean batch */
 } cw_result;
 
 /* Context: owns streams and scratch on each device.  n_devices <= 0 -> every visible device.

@@ -368,9 +368,41 @@ static void component_gradient(int type, double G, const double *p, const double
     }
 }
 
+/* Rounding-noise mode (tests only; off by default).  With eps != 0 every gradient component is multiplied by
+ * 1 + eps * s, s in {-1, 0, +1} drawn from a hash of the position bits and the seed: the arithmetic of ANY equivalent
+ * but differently rounded implementation (another libm, FMA contraction, a GPU's rsqrt / log) differs from this file by
+ * such last-bit factors at every evaluation.  Two runs that differ only in this noise tell which orbits amplify
+ * last-bit differences beyond the parity tolerance -- no implementation can agree with another on those. */
+static double g_noise_eps = 0.0;
+static uint64_t g_noise_seed = 0;
+void cwo_set_rounding_noise(double eps, uint64_t seed) { g_noise_eps = eps; g_noise_seed = seed; }
+
+static void apply_rounding_noise(const double *q, double *grad)
+{
+    uint64_t h = g_noise_seed * 0x9E3779B97F4A7C15ull;
+    for (int a = 0; a < 3; a++) {
+        uint64_t b;
+        memcpy(&b, &q[a], 8);
+        h ^= b + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    }
+    for (int a = 0; a < 3; a++) {
+        h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+        const int s = (int)(h % 3) - 1;
+        grad[a] = grad[a] * (1.0 + g_noise_eps * (double)s);
+    }
+}
+
+static void gradient_exact(const cwo_potential *P, double t, const double *q, double *grad);
+
 /* cpotential.c: c_gradient -- zero, then accumulate components in order; a component with a rotation sees
  * q' = R q and contributes R^T grad'; a time-interpolated one is evaluated with its parameters at time t */
 void cwo_gradient_t(const cwo_potential *P, double t, const double *q, double *grad)
+{
+    gradient_exact(P, t, q, grad);
+    if (g_noise_eps != 0.0) apply_rounding_noise(q, grad);
+}
+
+static void gradient_exact(const cwo_potential *P, double t, const double *q, double *grad)
 {
     grad[0] = 0.; grad[1] = 0.; grad[2] = 0.;
     for (int i = 0; i < P->n; i++) {

@@ -18,7 +18,7 @@ LEAPFROG, DOP853, DOP853_DENSE = 0, 1, 2
 FLAG_APPEND_T2 = 1
 
 __all__ = ["build", "lib", "make_potential", "gradient", "gradient_t", "value", "circular_velocity", "time_grid",
-           "leapfrog", "dop853", "dop853_dense", "integrate_orbit", "integrate_batch", "max_threads",
+           "leapfrog", "dop853", "dop853_dense", "integrate_orbit", "integrate_batch", "max_threads", "set_rounding_noise",
            "LEAPFROG", "DOP853", "DOP853_DENSE", "FLAG_APPEND_T2"]
 
 
@@ -260,6 +260,15 @@ def integrate_batch(pot, w0, t1, t2, dt, to_myr, flags, ev_off=None, ev_time=Non
                               _dp(tp), _dp(tv), _dp(tt), _lp(stats), int(n_threads))
     return dict(w_final=wf, status=status, n_nodes=n_nodes, ev_step=ev_step[:K], traj_pos=tp,
                 traj_vel=tv, traj_t=tt, stats=tuple(int(s) for s in stats))
+
+
+def set_rounding_noise(eps: float = 0.0, seed: int = 0) -> None:
+    """Multiply every gradient component by 1 + eps * {-1, 0, +1} (hash of the position and ``seed``): the last-bit
+    differences any equivalent implementation has.  ``eps = 0`` (default) switches it off.  Process-wide."""
+    L = lib()
+    L.cwo_set_rounding_noise.argtypes = [C.c_double, C.c_uint64]
+    L.cwo_set_rounding_noise.restype = None
+    L.cwo_set_rounding_noise(float(eps), int(seed))
 
 
 def max_threads() -> int:

@@ -6,7 +6,9 @@ DOPRI853 <= 1e-7 relative, kick node index bit-exact.  The kernels use a differe
 arithmetic (fused rsqrt/reciprocal/log, FMA contraction), and leapfrog at dt = 1 Myr does not resolve
 nucleus-grazing orbits (Hernquist c = 0.07 kpc): those amplify last-bit differences chaotically
 (SURVEY.md 7 "hard parts": 0.5 % of orbits beyond 1e-10 after 1000 steps between ANY two roundings).
-So the assertions are on quantiles, and every outlier must be a small-pericentre orbit.
+So the leapfrog assertions are made on the orbits that do NOT amplify last-bit noise -- classified by the oracle
+itself, re-run with rounding noise in its gradient (tests/_cases.py: sensitive_orbits): 100 % of those must meet the
+tolerance, i.e. every orbit beyond it is one the oracle cannot reproduce against its own rounding.
 """
 import json
 import os
@@ -20,16 +22,10 @@ from cogsworth_b200 import constants as K
 from cogsworth_b200.potential import CompositePotential, MilkyWayPotential
 from cogsworth_b200.synthetic import make_population
 
+from _cases import assert_parity_outside_the_sensitive_set, rel_diff, sensitive_orbits
+
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-
-
-def rel_diff(a, b):
-    """Per-orbit worst relative difference over the six coordinates, scaled by the orbit's own size
-    (|pos| for positions, |vel| for velocities) so a coordinate crossing zero does not blow it up."""
-    sp = np.maximum(np.linalg.norm(b[:3], axis=0), 1e-3)
-    sv = np.maximum(np.linalg.norm(b[3:], axis=0), 1e-5)
-    return np.maximum(np.abs(a[:3] - b[:3]).max(axis=0) / sp, np.abs(a[3:] - b[3:]).max(axis=0) / sv)
 
 
 def run_both(ctx, O, pop, integ, **kw):
@@ -66,19 +62,21 @@ def test_config1_leapfrog_v1(ctx, oracle):
     check_bit_exact_bookkeeping(g, o)
     assert (g["status"] == 0).all() and (g["n_nodes"] == 201).all()
     d = rel_diff(g["w_final"], o["w_final"])
-    assert np.median(d) < 1e-13 and np.quantile(d, 0.95) < 1e-10, np.quantile(d, [0.5, 0.9, 0.95, 0.99, 1])
+    sens, _, _ = sensitive_orbits(oracle, pop.potential, pop.batch, oracle.LEAPFROG, ref=o)
+    rep = assert_parity_outside_the_sensitive_set(d, sens, 1e-10, 0.03, "config 1")
+    assert rep["median"] < 1e-13, rep
     out = np.flatnonzero(d >= 1e-10)
-    assert len(out) < 0.05 * len(d)
     if len(out):
         assert (min_radius(oracle, pop, out) < 1.0).all(), "only nucleus-grazing orbits may exceed 1e-10"
-    assert ctx.last_launch_count == 2          # grid pre-pass + integrator
+    assert ctx.last_launch_count <= 3          # (unpack) + grid pre-pass + integrator
     # frozen golden case (same generator, 96 binaries)
     G = np.load(os.path.join(HERE, "golden", "oracle_cases.npz"))
     pop96 = make_population(96, cfg_id=1, potential=MilkyWayPotential("v1"), horizon_gyr=0.2)
     g96, _ = run_both(ctx, oracle, pop96, _lib.LEAPFROG)
     assert np.array_equal(g96["ev_step"], G["cfg1_leapfrog_v1_ev_step"])
     d96 = rel_diff(g96["w_final"], G["cfg1_leapfrog_v1_w_final"])
-    assert np.median(d96) < 1e-13 and np.quantile(d96, 0.9) < 1e-10
+    s96, _, _ = sensitive_orbits(oracle, pop96.potential, pop96.batch, oracle.LEAPFROG)
+    assert_parity_outside_the_sensitive_set(d96, s96, 1e-10, 0.05, "config 1 golden")
     # the frozen DOPRI853 cases (MW v2, same generator), both forms
     pop96v2 = make_population(96, cfg_id=1, potential=MilkyWayPotential("v2"), horizon_gyr=0.2)
     for name, integ in (("cfg1_dop853_v2", _lib.DOP853), ("cfg1_dop853dense_v2", _lib.DOP853_DENSE)):
@@ -97,9 +95,14 @@ def test_config2_wagg_horizons_v2(ctx, oracle, integ, tol):
     check_bit_exact_bookkeeping(g, o)
     assert g["n_nodes"].max() > 9000 and g["n_nodes"].min() < 3000
     d = rel_diff(g["w_final"], o["w_final"])
-    # long horizons: the chaotic share grows with step count (SURVEY: 4.6 % beyond 1e-10 at 12 000 steps)
+    # long horizons: the share of orbits that amplify rounding noise grows with the step count (measured with the
+    # oracle's own noise: 5 % beyond 1e-11 after 1000 steps, 22-25 % after the Wagg2022 horizons of up to 12 000)
     assert np.median(d) < (1e-11 if integ == _lib.LEAPFROG else 1e-9), np.quantile(d, [0.5, 0.8, 0.9, 1])
-    assert np.quantile(d, 0.8) < tol, np.quantile(d, [0.5, 0.8, 0.9, 1])
+    if integ == _lib.LEAPFROG:
+        sens, _, _ = sensitive_orbits(oracle, pop.potential, pop.batch, oracle.LEAPFROG, ref=o)
+        assert_parity_outside_the_sensitive_set(d, sens, tol, 0.35, "config 2 leapfrog")
+    else:
+        assert np.quantile(d, 0.8) < tol, np.quantile(d, [0.5, 0.8, 0.9, 1])
     if integ == _lib.DOP853:
         # same controller: accepted / rejected step counts agree to a fraction of a percent
         assert abs(g["stats"][0] - o["stats"][0]) <= 2e-3 * o["stats"][0]
@@ -180,7 +183,11 @@ def test_results_independent_of_queue_order_and_chunking(ctx, oracle, integ):
                                integrator=integ)
     check_bit_exact_bookkeeping(big, o)
     d = rel_diff(big["w_final"], o["w_final"])
-    assert np.quantile(d, 0.9) < (1e-10 if integ == _lib.LEAPFROG else 1e-7)
+    if integ == _lib.LEAPFROG:
+        sens, _, _ = sensitive_orbits(oracle, pop.potential, b, oracle.LEAPFROG, ref=o)
+        assert_parity_outside_the_sensitive_set(d, sens, 1e-10, 0.08, "queue order / chunking")
+    else:
+        assert np.quantile(d, 0.9) < 1e-7
     if integ == _lib.DOP853:
         assert abs(int(big["stats"][0]) - o["stats"][0]) <= 5e-3 * o["stats"][0]
 
