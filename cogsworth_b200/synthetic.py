@@ -168,7 +168,9 @@ def make_population(n_binaries, cfg_id=0, potential=None, f_sn=1.0, horizon_gyr=
     potential = MilkyWayPotential("v2") if potential is None else potential
     rng = np.random.default_rng(SEED0 + cfg_id if seed is None else seed)
     tau, pos, vel = wagg2022_initial_conditions(n_binaries, rng, potential, galaxy_age=max_ev_time_gyr)
-    if horizon_gyr is not None:
+    if isinstance(horizon_gyr, (tuple, list)):       # every system its own horizon, uniform in [lo, hi] Gyr
+        tau = rng.uniform(float(horizon_gyr[0]), float(horizon_gyr[1]), n_binaries)
+    elif horizon_gyr is not None:
         tau = np.full(n_binaries, float(horizon_gyr))
     if plunging_fraction > 0:
         k = rng.random(n_binaries) < plunging_fraction

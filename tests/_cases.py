@@ -64,3 +64,54 @@ def assert_parity_outside_the_sensitive_set(d, sens, tol, max_sensitive_fraction
     ok = ~sens
     return dict(n=len(d), sensitive=int(sens.sum()), outliers=int(out.sum()),
                 max_regular=float(d[ok].max()) if ok.any() else 0.0, median=float(np.median(d)))
+
+
+# ---- cases pinned against REAL gala by tools/pin_against_gala.py (tests/test_gala_pins.py consumes the file) -------
+def gala_pin_cases():
+    """(name, potential key, integrator name, horizon spec, n_binaries, cfg_id, dt_myr, integrator_kwargs).
+
+    Each case is one seeded synthetic population (cogsworth_b200.synthetic.make_population -- numpy / scipy only, so it
+    is reproducible on the gala machine) integrated orbit by orbit with cogsworth.kicks.integrate_orbit_with_events.
+    Together they cover every [gala-recall] item of the oracle: the leapfrog recipe, the un-kicked end point (Q1), the
+    short appended interval (Q2), restart-vs-dense DOPRI853, and the general potentials' conventions."""
+    return (
+        ("cfg1_leapfrog_v1", "mw_v1", "leapfrog", 0.2, 96, 1, 1.0, {}),
+        ("cfg4_leapfrog_v2", "mw_v2", "leapfrog", 1.0, 96, 4, 1.0, {}),
+        ("cfg2_leapfrog_v2_wagg", "mw_v2", "leapfrog", None, 24, 2, 1.0, {}),
+        ("leapfrog_v2_odd_dt", "mw_v2", "leapfrog", (0.0002, 0.3), 64, 31, 0.7, {}),       # Q1, Q2, clipped dt
+        ("cfg1_dop853_v2", "mw_v2", "dop853", 0.2, 96, 1, 1.0, {}),
+        ("cfg5_dop853_v2_1e-8", "mw_v2", "dop853", 1.0, 48, 5, 1.0, {"atol": 1e-8, "rtol": 1e-8}),
+        ("lm10_leapfrog", "lm10", "leapfrog", 0.2, 48, 1, 1.0, {}),
+        ("bovy2014_dop853", "bovy2014", "dop853", 0.2, 48, 1, 1.0, {}),
+        ("evolving_mw_dop853", "evolving_mw", "dop853", None, 24, 1, 1.0, {}),
+    )
+
+
+def pin_potential(key):
+    """This package's table for a pin-case potential key (tools/pin_against_gala.py builds the gala object)."""
+    if key == "mw_v1":
+        return P.MilkyWayPotential("v1")
+    if key == "mw_v2":
+        return P.MilkyWayPotential("v2")
+    if key == "lm10":
+        return P.LM10Potential()
+    if key == "bovy2014":
+        return P.BovyMWPotential2014()
+    if key == "evolving_mw":
+        return P.evolving_milky_way(np.linspace(0.0, 12000.0, 5), np.linspace(0.1, 1.0, 5))
+    raise KeyError(key)
+
+
+def pin_population(case):
+    """The seeded population of a pin case (birth velocities are always drawn in the static MilkyWayPotential v2)."""
+    from cogsworth_b200.synthetic import make_population
+    name, key, integ, horizon, nb, cfg, dt_myr, kw = case
+    draw_in = P.MilkyWayPotential("v1") if key == "mw_v1" else P.MilkyWayPotential("v2")
+    pop = make_population(nb, cfg_id=cfg, potential=draw_in, horizon_gyr=horizon, timestep_myr=dt_myr)
+    pop.potential = pin_potential(key)
+    return pop
+
+
+#: points [kpc] at which the pin file also holds every potential's gradient / value (conventions of rotated components)
+PIN_POINTS = np.array([[8.5, 0.0, 0.0], [3.2, -4.1, 0.7], [-0.3, 0.2, 0.05], [15.0, 9.0, -20.0], [0.9, 2.2, -1.4],
+                       [-30.0, 2.0, 11.0]]).T
