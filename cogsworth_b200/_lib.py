@@ -26,8 +26,9 @@ ORBIT_STATUS = {0: "ok", -1: "inconsistent input", -2: "larger nmax is needed",
 
 EXPORTS = ["cw_create", "cw_destroy", "cw_device_count", "cw_set_potential", "cw_set_potential_ex", "cw_set_potential_general",
            "cw_set_potential_time", "cw_count_nodes", "cw_host_alloc", "cw_host_free", "cw_host_is_pinned",
+           "cw_host_rotate_kicks",
            "cw_integrate", "cw_gradient", "cw_potential_value", "cw_circular_velocity", "cw_pointwise_t", "cw_strerror",
-           "cw_last_error", "cw_abi_version", "cw_last_launch_count", "cw_last_kernel_ms",
+           "cw_last_error", "cw_abi_version", "cw_last_launch_count", "cw_last_max_attempts", "cw_last_kernel_ms",
            "cw_last_total_kernel_ms", "cw_measure_fp64_peak", "cw_measure_scatter_write", "cw_selftest_math"]
 
 
@@ -108,6 +109,8 @@ def load():
     L.cw_host_free.restype = None
     L.cw_host_is_pinned.argtypes = [vp]
     L.cw_host_is_pinned.restype = C.c_int
+    L.cw_host_rotate_kicks.argtypes = [C.c_int64, vp, vp, vp, C.c_double, vp]
+    L.cw_host_rotate_kicks.restype = None
     L.cw_strerror.argtypes = [C.c_int]
     L.cw_strerror.restype = C.c_char_p
     L.cw_last_error.argtypes = [vp]
@@ -115,6 +118,8 @@ def load():
     L.cw_abi_version.restype = C.c_int
     L.cw_last_launch_count.argtypes = [vp]
     L.cw_last_launch_count.restype = C.c_int64
+    L.cw_last_max_attempts.argtypes = [vp]
+    L.cw_last_max_attempts.restype = C.c_int64
     L.cw_last_kernel_ms.argtypes = [vp, C.c_int]
     L.cw_last_kernel_ms.restype = C.c_double
     L.cw_last_total_kernel_ms.argtypes = [vp, C.c_int]
@@ -433,6 +438,10 @@ class Context:
     @property
     def last_launch_count(self) -> int:
         return int(self._L.cw_last_launch_count(self._h))
+
+    @property
+    def last_max_attempts(self) -> int:
+        return int(self._L.cw_last_max_attempts(self._h))
 
     def last_kernel_ms(self, dev=0) -> float:
         return float(self._L.cw_last_kernel_ms(self._h, dev))

@@ -56,6 +56,21 @@ class EventTable:
         return off
 
 
+def rotate_kicks_threaded(dv_kms, phase, inc, scale, out):
+    """``rotate_kicks(...) * scale`` on the library's host threads (``cw_host_rotate_kicks``): the rotation is four
+    libm calls per event, most of the batch builder's time at 10^7 events.  Returns False when the library is not
+    built (numpy is used then).  libm's last bit may differ from numpy's: the result is AN input of the integration,
+    identical for whoever integrates the batch."""
+    try:
+        from . import _lib
+        L = _lib.load()
+    except Exception:
+        return False
+    dv_kms, phase, inc = (np.ascontiguousarray(a, dtype=np.float64) for a in (dv_kms, phase, inc))
+    L.cw_host_rotate_kicks(len(phase), _lib.ptr(dv_kms), _lib.ptr(phase), _lib.ptr(inc), float(scale), _lib.ptr(out))
+    return True
+
+
 def rotate_kicks(dv_kms: np.ndarray, phase: np.ndarray, inc: np.ndarray, out=None) -> np.ndarray:
     """Vectorised ``get_kick_differential`` (kicks.py:42-46): BSE (vx,vy,vz) -> Galactocentric, km/s."""
     vx, vy, vz = dv_kms[:, 0], dv_kms[:, 1], dv_kms[:, 2]
@@ -233,7 +248,8 @@ def _grid_classes(t1_gyr, t2_gyr, dt_myr, kicked):
 
 def build_orbit_batch(pos_kpc, vel_kms, tau_gyr, max_ev_time_gyr, timestep_myr, disrupted,
                       primary_events: Optional[EventTable] = None,
-                      secondary_events: Optional[EventTable] = None, compact: bool = True) -> OrbitBatch:
+                      secondary_events: Optional[EventTable] = None, compact: bool = True,
+                      threaded_rotation: bool = True) -> OrbitBatch:
     """Vectorised ``_iter_orbit_args``: primaries (population order) then disrupted secondaries.
 
     pos_kpc, vel_kms : (3, n) arrays; tau_gyr : (n,) look-back birth times; ``t1 = max_ev_time - tau``
@@ -241,10 +257,12 @@ def build_orbit_batch(pos_kpc, vel_kms, tau_gyr, max_ev_time_gyr, timestep_myr, 
 
     compact : build the compact form of :class:`OrbitBatch` (what ``cw_integrate`` is sent), with the large arrays in
     page-locked memory; the plain arrays are then expanded only if something reads them.
+    threaded_rotation : rotate the kicks of large batches on the library's host threads instead of numpy.
     """
     from ._lib import pinned_empty
-    pos_kpc = np.asarray(pos_kpc, dtype=np.float64)
-    vel_kms = np.asarray(vel_kms, dtype=np.float64)
+    # (3, n) arrays, or three rows each (no stacking copy of a 10^7-system galaxy)
+    pos_kpc = [np.asarray(r, dtype=np.float64) for r in pos_kpc]
+    vel_kms = [np.asarray(r, dtype=np.float64) for r in vel_kms]
     tau_gyr = np.asarray(tau_gyr, dtype=np.float64)
     n = tau_gyr.shape[0]
     disrupted = np.asarray(disrupted, dtype=bool)
@@ -282,10 +300,12 @@ def build_orbit_batch(pos_kpc, vel_kms, tau_gyr, max_ev_time_gyr, timestep_myr, 
         np.add(ev_time, t1_gyr_src[owner_src], out=ev_time)
         np.multiply(ev_time, K.SEC_PER_GYR, out=ev_time)
         ev_dv = pinned_empty((Kn, 3))
-        rotate_kicks(np.concatenate([pe.dv.reshape(-1, 3), se.dv.reshape(-1, 3)]).astype(np.float64),
-                     np.concatenate([pe.phase, se.phase]).astype(np.float64),
-                     np.concatenate([pe.inc, se.inc]).astype(np.float64), out=ev_dv)
-        np.multiply(ev_dv, K.KPC_MYR_PER_KMS, out=ev_dv)
+        dv_all = np.concatenate([pe.dv.reshape(-1, 3), se.dv.reshape(-1, 3)]).astype(np.float64, copy=False)
+        ph_all = np.concatenate([pe.phase, se.phase]).astype(np.float64, copy=False)
+        in_all = np.concatenate([pe.inc, se.inc]).astype(np.float64, copy=False)
+        if not (threaded_rotation and Kn >= 4096 and rotate_kicks_threaded(dv_all, ph_all, in_all, K.KPC_MYR_PER_KMS, ev_dv)):
+            rotate_kicks(dv_all, ph_all, in_all, out=ev_dv)
+            np.multiply(ev_dv, K.KPC_MYR_PER_KMS, out=ev_dv)
 
     # the compact form needs every disrupted system's own orbit on the events branch (its start time is then the
     # same float in seconds for the system and its secondary) and few enough distinct grids
@@ -295,8 +315,9 @@ def build_orbit_batch(pos_kpc, vel_kms, tau_gyr, max_ev_time_gyr, timestep_myr, 
         grid = _grid_classes(t1_gyr, max_ev_time_gyr, timestep_myr, kicked)
     if grid is not None:
         w0 = pinned_empty((6, n))
-        w0[:3] = pos_kpc
-        np.multiply(vel_kms, K.KPC_MYR_PER_KMS, out=w0[3:])     # gala: km/s -> kpc/Myr on entry
+        for c in range(3):
+            w0[c] = pos_kpc[c]
+            np.multiply(vel_kms[c], K.KPC_MYR_PER_KMS, out=w0[3 + c])     # gala: km/s -> kpc/Myr on entry
         t1 = pinned_empty(n)
         np.multiply(t1_gyr_src, np.where(kicked[:n], K.SEC_PER_GYR, K.MYR_PER_GYR), out=t1)
         idx = pinned_empty(n_dis, np.int32)
@@ -310,8 +331,9 @@ def build_orbit_batch(pos_kpc, vel_kms, tau_gyr, max_ev_time_gyr, timestep_myr, 
 
     src = np.concatenate([np.arange(n), dis_idx])          # population index of every orbit
     w0 = np.empty((6, n_orb))
-    w0[:3] = pos_kpc[:, src]
-    w0[3:] = vel_kms[:, src] * K.KPC_MYR_PER_KMS
+    for c in range(3):
+        w0[c] = pos_kpc[c][src]
+        w0[3 + c] = vel_kms[c][src] * K.KPC_MYR_PER_KMS
     t1, t2, dt, to_myr, flags = _grid_columns(t1_gyr_src[src], max_ev_time_gyr, timestep_myr, kicked)
     return OrbitBatch(w0=w0, t1=t1, t2=t2, dt=dt, to_myr=to_myr, flags=flags,
                       ev_off=ev_off if Kn else None, ev_time=ev_time, ev_dv=ev_dv,

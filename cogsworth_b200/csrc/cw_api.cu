@@ -114,6 +114,7 @@ struct cw_ctx {
     bool has_pot = false;
     std::string last_error;
     int64_t last_launches = 0;
+    int64_t last_max_attempts = 0;          // DOP853: most step attempts of any one orbit in the last call
 };
 
 #define CW_CK(ctx, call)                                                                          \
@@ -776,6 +777,10 @@ static int integrate_device(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, co
         return CW_OK;
     }
     CW_CK(ctx, cudaStreamSynchronize(pl.stream));
+    {
+        unsigned long long mx = 0;
+        if (integrate && cudaMemcpy(&mx, A.stats + 5, 8, cudaMemcpyDeviceToHost) == cudaSuccess) ctx->last_max_attempts = (int64_t)mx;
+    }
     if (pl.timed) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, pl.ev_k0, pl.ev_k1) == cudaSuccess) s.last_kernel_ms += ms;
@@ -1412,7 +1417,8 @@ static int integrate_host(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
     if (rc != CW_OK) return rc;
     // ---- statistics and kernel times
     int64_t stats[5] = {0, 0, 0, 0, 0};
-    const bool want_stats = integrate && (R->stats || R->n_failed);
+    const bool want_stats = integrate;
+    ctx->last_max_attempts = 0;
     for (int d = 0; d < nslots; d++) {
         if (per_slot[d].empty()) continue;
         Slot &s = ctx->slots[d];
@@ -1424,6 +1430,7 @@ static int integrate_host(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
         for (size_t k = 0; k < per_slot[d].size(); k++) {
             const Plan &pl = per_slot[d][k]->plan;
             for (int q = 0; q < 5; q++) stats[q] += (int64_t)hs[mstride * k + 1 + q];
+            ctx->last_max_attempts = std::max(ctx->last_max_attempts, (int64_t)hs[mstride * k + 6]);
             if (pl.timed) {
                 float ms = 0.f;
                 if (cudaEventElapsedTime(&ms, pl.ev_k0, pl.ev_k1) == cudaSuccess) s.last_kernel_ms += ms;
@@ -1480,6 +1487,8 @@ extern "C" int cw_integrate(cw_ctx *ctx, const cw_opts *opts, const cw_batch *ba
 }
 
 extern "C" int64_t cw_last_launch_count(const cw_ctx *ctx) { return ctx ? ctx->last_launches : 0; }
+
+extern "C" int64_t cw_last_max_attempts(const cw_ctx *ctx) { return ctx ? ctx->last_max_attempts : 0; }
 
 extern "C" double cw_last_kernel_ms(const cw_ctx *ctx, int dev)
 {

@@ -228,9 +228,11 @@ __device__ __forceinline__ void fcn(const PotParams &P, LogTab ltab, double t, c
     f[3] = -gx; f[4] = -gy; f[5] = -gz;
 }
 
-__device__ __forceinline__ void dp_write_final(const IntegArgs &A, const DpLane &s, int status)
+__device__ __forceinline__ void dp_write_final(const IntegArgs &A, const DpLane &s, int status, int attempts = 0)
 {
     const int64_t n = A.n;
+    // diagnostics: the most step attempts any one orbit needed (its lane's sequential latency bounds the launch)
+    if (A.stats && attempts > 0) atomicMax(A.stats + 5, (unsigned long long)attempts);
 #pragma unroll
     for (int c = 0; c < 6; c++) A.w_final[c * n + s.oid] = s.y[c];
     if (status != CW_ORBIT_OK) {
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
                 A.cost_key[s.oid] = __float_as_int((float)attempts * ((float)s.L / (float)Lstop));
                 active = false;
             } else if (s.j == s.L) {
-                dp_write_final(A, s, CW_ORBIT_OK);
+                dp_write_final(A, s, CW_ORBIT_OK, attempts);
                 active = false;
             } else {
                 dp_begin_interval<DENSE>(A, s);
@@ -508,9 +510,10 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
                     const double b = k5[i] - yy1[i];
                     stden = fma(b, b, stden);
                 }
-                // hlamb = h sqrt(stnum / stden) > 6.1  <=>  h^2 stnum > 37.21 stden  (no root, no divide); hlamb
-                // keeps its previous verdict when stden == 0, as in dopcor
-                if (stden > 0.0) s.hlamb = (h * h * stnum > 37.21 * stden) ? 7.0 : 0.0;
+                // hlamb = h sqrt(stnum / stden) > 6.1  <=>  h > 0 and h^2 stnum > 37.21 stden  (no root, no divide):
+                // Hairer's hlamb carries the sign of h, so a backward integration (h < 0, hydro/rewind.py) never
+                // trips the test; hlamb keeps its previous verdict when stden == 0, as in dopcor
+                if (stden > 0.0) s.hlamb = (h > 0.0 && h * h * stnum > 37.21 * stden) ? 7.0 : 0.0;
                 bool stiff = false;
                 if (s.hlamb > 6.1) {
                     s.nonsti = 0;

@@ -1,7 +1,9 @@
 // cw_host.cu -- page-locked memory cache, pointer classification and the host staging thread pool (cw_host.h).
 #include "cw_host.h"
 
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -131,7 +133,9 @@ bool pointer_is_dma_able(const void *p)
 namespace {
 
 struct Job {
-    std::vector<CopyTask> pieces;
+    std::vector<CopyTask> pieces;                      // copy job ...
+    const std::function<void(size_t)> *fn = nullptr;   // ... or a parallel loop over n_pieces
+    size_t n_pieces = 0;
     std::atomic<size_t> next{0};
     std::atomic<size_t> done{0};
     std::mutex m;
@@ -142,12 +146,16 @@ constexpr size_t PIECE_BYTES = (size_t)512 << 10;
 
 void work_on(Job &j)
 {
-    const size_t n = j.pieces.size();
+    const size_t n = j.n_pieces;
     for (;;) {
         const size_t i = j.next.fetch_add(1, std::memory_order_relaxed);
         if (i >= n) break;
-        const CopyTask &t = j.pieces[i];
-        memcpy(t.dst, t.src, t.bytes);
+        if (j.fn) {
+            (*j.fn)(i);
+        } else {
+            const CopyTask &t = j.pieces[i];
+            memcpy(t.dst, t.src, t.bytes);
+        }
         if (j.done.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
             std::lock_guard<std::mutex> lk(j.m);
             j.cv.notify_all();
@@ -188,6 +196,8 @@ struct HostPool::Impl {
             });
     }
 };
+
+static void submit_and_wait(HostPool::Impl *p, const std::shared_ptr<Job> &j);
 
 HostPool::HostPool() : p_(new Impl())
 {
@@ -240,23 +250,66 @@ void HostPool::run(const std::vector<CopyTask> &tasks)
             j->pieces.push_back(p);
         }
     }
-    p_->start();
-    {
-        std::lock_guard<std::mutex> lk(p_->m);
-        p_->jobs.push_back(j);
+    j->n_pieces = j->pieces.size();
+    submit_and_wait(p_, j);
+}
+
+void HostPool::parallel_for(size_t n_pieces, const std::function<void(size_t)> &fn)
+{
+    if (n_pieces == 0) return;
+    if (p_->n_workers == 0 || n_pieces == 1) {
+        for (size_t i = 0; i < n_pieces; i++) fn(i);
+        return;
     }
-    p_->cv.notify_all();
+    auto j = std::make_shared<Job>();
+    j->fn = &fn;
+    j->n_pieces = n_pieces;
+    submit_and_wait(p_, j);
+}
+
+static void submit_and_wait(HostPool::Impl *p, const std::shared_ptr<Job> &j)
+{
+    p->start();
+    {
+        std::lock_guard<std::mutex> lk(p->m);
+        p->jobs.push_back(j);
+    }
+    p->cv.notify_all();
     work_on(*j);
     {
         std::unique_lock<std::mutex> lk(j->m);
-        j->cv.wait(lk, [&] { return j->done.load(std::memory_order_acquire) == j->pieces.size(); });
+        j->cv.wait(lk, [&] { return j->done.load(std::memory_order_acquire) == j->n_pieces; });
     }
-    std::lock_guard<std::mutex> lk(p_->m);
-    for (auto it = p_->jobs.begin(); it != p_->jobs.end(); ++it)
-        if (*it == j) { p_->jobs.erase(it); break; }
+    std::lock_guard<std::mutex> lk(p->m);
+    for (auto it = p->jobs.begin(); it != p->jobs.end(); ++it)
+        if (*it == j) { p->jobs.erase(it); break; }
 }
 
 } // namespace cw
+
+// get_kick_differential (cogsworth kicks.py:12-49) for K events on the host thread pool: BSE-frame systemic kick
+// (km/s), orbital phase and inclination -> Galactocentric velocity change, times `scale` (km/s -> kpc/Myr).
+// The vectorised numpy form of cogsworth_b200.batch.rotate_kicks, whose cost is four libm calls per event.
+extern "C" void cw_host_rotate_kicks(int64_t K, const double *dv, const double *phase, const double *inc, double scale,
+                                     double *out)
+{
+    if (K <= 0) return;
+    const int64_t grain = 1 << 15;
+    const size_t pieces = (size_t)((K + grain - 1) / grain);
+    std::function<void(size_t)> fn = [&](size_t p) {
+        const int64_t a = (int64_t)p * grain, b = std::min<int64_t>(K, a + grain);
+        for (int64_t k = a; k < b; k++) {
+            double st, ct, sp, cp;
+            sincos(phase[k], &st, &ct);
+            sincos(inc[k], &sp, &cp);
+            const double vx = dv[3 * k], vy = dv[3 * k + 1], vz = dv[3 * k + 2];
+            out[3 * k + 0] = (vx * ct - vy * st * cp + vz * st * sp) * scale;
+            out[3 * k + 1] = (vx * st + vy * ct * cp - vz * ct * sp) * scale;
+            out[3 * k + 2] = (vy * sp + vz * cp) * scale;
+        }
+    };
+    cw::HostPool::get().parallel_for(pieces, fn);
+}
 
 extern "C" void *cw_host_alloc(size_t bytes) { return cw::pinned_alloc(bytes); }
 extern "C" void cw_host_free(void *p) { cw::pinned_free(p); }

@@ -7,6 +7,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 namespace cw {
@@ -32,11 +33,13 @@ class HostPool {
 public:
     static HostPool &get();
     void run(const std::vector<CopyTask> &tasks);
+    // fn(piece) for piece = 0 .. n_pieces-1, spread over the workers and the calling thread
+    void parallel_for(size_t n_pieces, const std::function<void(size_t)> &fn);
     int workers() const;
+    struct Impl;
 private:
     HostPool();
     ~HostPool();
-    struct Impl;
     Impl *p_;
 };
 

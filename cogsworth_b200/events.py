@@ -43,47 +43,58 @@ def _sn_rows(p):
     draw_sn_angles(initC)
 
     k_star = np.asarray(kick["star"].values)
-    k_keep = k_star > 0.0
-    k_bin = np.asarray(kick["bin_num"].values)[k_keep].astype(np.int64)
-    k_key = k_bin * 4 + k_star[k_keep].astype(np.int64)
+    k_idx = np.flatnonzero(k_star > 0.0)
+    k_key = np.asarray(kick["bin_num"].values)[k_idx].astype(np.int64) * 4 + k_star[k_idx].astype(np.int64)
 
     et = np.asarray(bpp["evol_type"].values)
-    b_keep = (et == 15) | (et == 16)
-    b_bin = np.asarray(bpp["bin_num"].values)[b_keep].astype(np.int64)
-    b_star = np.where(et[b_keep] == 15, 1, 2).astype(np.int64)
+    b_idx = np.flatnonzero((et == 15) | (et == 16))
+    b_bin = np.asarray(bpp["bin_num"].values)[b_idx].astype(np.int64)
+    b_star = np.where(et[b_idx] == 15, 1, 2).astype(np.int64)
     b_key = b_bin * 4 + b_star
-    b_tphys = np.asarray(bpp["tphys"].values, dtype=np.float64)[b_keep]
+    b_tphys = np.asarray(bpp["tphys"].values, dtype=np.float64)[b_idx]
 
     # inner join bpp SN rows with kick rows on (bin_num, star); keys are unique on the kick side
-    order = np.argsort(k_key, kind="stable")
-    pos = np.searchsorted(k_key[order], b_key)
-    pos_c = np.minimum(pos, max(len(order) - 1, 0))
-    hit = (len(order) > 0) & (pos < len(order))
-    if len(order):
-        hit = hit & (k_key[order][pos_c] == b_key)
+    if len(k_key) == len(b_key) and np.array_equal(k_key, b_key):
+        # COSMIC writes both tables in the same (bin_num, time) order: row k of one IS row k of the other
+        hit, krow = slice(None), k_idx
     else:
-        hit = np.zeros(len(b_key), dtype=bool)
-    krow = order[pos_c[hit]] if len(order) else np.zeros(0, dtype=np.int64)
+        order = None
+        ks = k_key
+        if len(ks) > 1 and np.any(ks[1:] < ks[:-1]):
+            order = np.argsort(ks, kind="stable")
+            ks = ks[order]
+        pos = np.searchsorted(ks, b_key)
+        pos_c = np.minimum(pos, max(len(ks) - 1, 0))
+        hit = (pos < len(ks)) & (ks[pos_c] == b_key) if len(ks) else np.zeros(len(b_key), dtype=bool)
+        krow = pos_c[hit] if order is None else order[pos_c[hit]]
+        krow = k_idx[krow] if len(ks) else np.zeros(0, dtype=np.int64)
 
     def kcol(name):
-        return np.asarray(kick[name].values, dtype=np.float64)[k_keep][krow]
+        return np.asarray(kick[name].values, dtype=np.float64)[krow]
 
     bins = b_bin[hit]
     star = b_star[hit]
     # angles: row of initC for each bin_num (initC is indexed by bin_num)
     ic_bins = np.asarray(initC["bin_num"].values if "bin_num" in initC else initC.index.values).astype(np.int64)
-    ic_order = np.argsort(ic_bins, kind="stable")
-    ic_row = ic_order[np.searchsorted(ic_bins[ic_order], bins)]
+    if len(ic_bins) and ic_bins[-1] - ic_bins[0] == len(ic_bins) - 1 and (len(ic_bins) < 2 or np.all(ic_bins[1:] > ic_bins[:-1])):
+        ic_row = bins - ic_bins[0]                    # consecutive bin_nums: the row is the offset
+    elif len(ic_bins) > 1 and np.any(ic_bins[1:] < ic_bins[:-1]):
+        ic_order = np.argsort(ic_bins, kind="stable")
+        ic_row = ic_order[np.searchsorted(ic_bins[ic_order], bins)]
+    else:
+        ic_row = np.searchsorted(ic_bins, bins)
     inc1, inc2 = np.asarray(initC["inc_sn_1"].values), np.asarray(initC["inc_sn_2"].values)
     ph1, ph2 = np.asarray(initC["phase_sn_1"].values), np.asarray(initC["phase_sn_2"].values)
+    K = len(bins)
+    dv1, dv2 = np.empty((K, 3)), np.empty((K, 3))
+    for c, ax in enumerate("xyz"):
+        dv1[:, c] = kcol(f"delta_vsys{ax}_1")
+        dv2[:, c] = kcol(f"delta_vsys{ax}_2")
+    first = star == 1
     return dict(
-        bin_num=bins, star=star, tphys=b_tphys[hit], disrupted=kcol("disrupted"),
-        dv1=np.stack([kcol("delta_vsysx_1"), kcol("delta_vsysy_1"), kcol("delta_vsysz_1")], axis=1)
-        if len(bins) else np.zeros((0, 3)),
-        dv2=np.stack([kcol("delta_vsysx_2"), kcol("delta_vsysy_2"), kcol("delta_vsysz_2")], axis=1)
-        if len(bins) else np.zeros((0, 3)),
-        inc=np.where(star == 1, inc1[ic_row], inc2[ic_row]).astype(np.float64),
-        phase=np.where(star == 1, ph1[ic_row], ph2[ic_row]).astype(np.float64))
+        bin_num=bins, star=star, tphys=b_tphys[hit], disrupted=kcol("disrupted"), dv1=dv1, dv2=dv2,
+        inc=np.where(first, inc1[ic_row], inc2[ic_row]).astype(np.float64, copy=False),
+        phase=np.where(first, ph1[ic_row], ph2[ic_row]).astype(np.float64, copy=False))
 
 
 def _select(rows, mask, dv):
@@ -94,7 +105,7 @@ def _select(rows, mask, dv):
 def _primary_secondary(p):
     rows = _sn_rows(p)
     # primaries: delta_vsys*_1 at every supernova                              (events.py:47-53)
-    prim = _select(rows, np.ones(len(rows["bin_num"]), dtype=bool), rows["dv1"])
+    prim = dict(bin_num=rows["bin_num"], tphys=rows["tphys"], dv=rows["dv1"], inc=rows["inc"], phase=rows["phase"])
     # secondaries: *_2, except *_1 while the binary is still bound             (events.py:56-67)
     dv_sec = np.where((rows["disrupted"] == 0)[:, None], rows["dv1"], rows["dv2"])
     # ... and only for disrupted binaries, in bin_nums[disrupted] order         (events.py:70)
@@ -139,6 +150,8 @@ def _table(t, bin_nums):
     if len(bin_nums) > 1 and np.any(bin_nums[1:] < bin_nums[:-1]):
         order_b = np.argsort(bin_nums, kind="stable")
         owner = order_b[np.searchsorted(bin_nums[order_b], t["bin_num"])]
+    elif bin_nums[-1] - bin_nums[0] == len(bin_nums) - 1 and (len(bin_nums) < 2 or np.all(bin_nums[1:] > bin_nums[:-1])):
+        owner = t["bin_num"] - bin_nums[0]    # consecutive bin_nums
     else:                                     # the population is in bin_num order (the usual case)
         owner = np.searchsorted(bin_nums, t["bin_num"])
     owner = owner.astype(np.int64, copy=False)

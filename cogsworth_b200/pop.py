@@ -71,8 +71,8 @@ class GalacticStageB200:
         self._escaped = None
 
         ig = self.initial_galaxy
-        pos = np.stack([_val(ig.x, "kpc"), _val(ig.y, "kpc"), _val(ig.z, "kpc")])
-        vel = np.stack([_val(ig.v_x, "km/s"), _val(ig.v_y, "km/s"), _val(ig.v_z, "km/s")])
+        pos = [_val(ig.x, "kpc"), _val(ig.y, "kpc"), _val(ig.z, "kpc")]
+        vel = [_val(ig.v_x, "km/s"), _val(ig.v_y, "km/s"), _val(ig.v_z, "km/s")]
         tau = _val(ig.tau, "Gyr")
 
         # per-SN angles are drawn once and persisted (pop.py:1229-1234) so re-runs reproduce

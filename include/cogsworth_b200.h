@@ -251,6 +251,10 @@ void *cw_host_alloc(size_t bytes);
 void cw_host_free(void *p);
 /* 1 if p is page-locked (or device) memory known to the CUDA runtime, 0 if pageable */
 int cw_host_is_pinned(const void *p);
+/* get_kick_differential (kicks.py:12-49) for K events at once, on the library's host threads: dv (K x 3, km/s in the
+ * BSE frame), phase, inc [rad] -> out (K x 3) = R(phase, inc) dv * scale (scale = 1/977.7922216807891 gives the
+ * kpc/Myr that cw_batch.ev_dv wants).  Host-side preparation of the batch, not part of the timed hot path. */
+void cw_host_rotate_kicks(int64_t K, const double *dv, const double *phase, const double *inc, double scale, double *out);
 
 /* Diagnostics */
 const char *cw_strerror(int code);
@@ -258,6 +262,9 @@ const char *cw_last_error(const cw_ctx *ctx);
 int cw_abi_version(void);
 /* kernels launched by the last cw_integrate / cw_count_nodes call, over all devices */
 int64_t cw_last_launch_count(const cw_ctx *ctx);
+/* DOPRI853: the largest number of step attempts any ONE orbit of the last synchronous call needed.  An orbit is
+ * sequential, so attempts x (latency of one attempt) of this orbit is a lower bound of the launch's duration. */
+int64_t cw_last_max_attempts(const cw_ctx *ctx);
 /* device time (ms, CUDA events on the launching stream) of the integrator kernel / of all kernels
  * of the last call on device slot `dev` */
 double cw_last_kernel_ms(const cw_ctx *ctx, int dev);
