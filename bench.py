@@ -579,24 +579,34 @@ def main():
     # ---- N > 1: the same 10^7 orbits through ONE process driving every GPU (what a Population user gets) --------------
     inproc = None
     if world > 1 and not args.no_inprocess:
+        # The other ranks must wait on the HOST: an NCCL barrier is a spinning kernel on their GPU, and rank 0's work on
+        # that GPU would be time-sliced against it (two processes, one device).  They block on the rendezvous store.
+        import datetime
+        from torch.distributed.distributed_c10d import _get_default_store
+        store = _get_default_store()
         barrier()
         if rank == 0:
-            full = build_shard(wl, 0, 1, "strong", args.scale)
-            apply_workload_potential(wl, full)
-            with cb.Context(devices=list(range(world))) as call:
-                call.set_potential(full.potential)
-                from cogsworth_b200 import kicks
-                run1 = lambda: kicks.integrate_orbits(full.batch, potential=full.potential, store_all=False,
-                                                      integrator=wl["integrator"], context=call)
-                run1(); run1()
-                t0 = time.perf_counter()
-                for _ in range(args.steps):
-                    _, info = run1()
-                dt = time.perf_counter() - t0
-                st = float(info["stats"][3])
-                inproc = {"value": st * args.steps / dt, "unit": "orbit-steps/s", "ms_per_step": 1e3 * dt / args.steps,
-                          "how": f"rank 0 alone, one cw_ctx on all {world} GPUs (one host thread per device, orbits sharded by "
-                                 "index), kicks.integrate_orbits on the whole workload; the other ranks idle at a barrier"}
+            try:
+                full = build_shard(wl, 0, 1, "strong", args.scale)
+                apply_workload_potential(wl, full)
+                with cb.Context(devices=list(range(world))) as call:
+                    call.set_potential(full.potential)
+                    from cogsworth_b200 import kicks
+                    run1 = lambda: kicks.integrate_orbits(full.batch, potential=full.potential, store_all=False,
+                                                          integrator=wl["integrator"], context=call)
+                    run1(); run1()
+                    t0 = time.perf_counter()
+                    for _ in range(args.steps):
+                        _, info = run1()
+                    dt = time.perf_counter() - t0
+                    st = float(info["stats"][3])
+                    inproc = {"value": st * args.steps / dt, "unit": "orbit-steps/s", "ms_per_step": 1e3 * dt / args.steps,
+                              "how": f"rank 0 alone, one cw_ctx on all {world} GPUs (one host thread per device, orbits sharded "
+                                     "by index), kicks.integrate_orbits on the whole workload; the other ranks wait on the host"}
+            finally:
+                store.set("cw_inprocess_done", "1")
+        else:
+            store.wait(["cw_inprocess_done"], datetime.timedelta(seconds=900))
         barrier()
 
     if rank == 0:
