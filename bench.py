@@ -460,7 +460,10 @@ def measure(W, steps, warmup, barrier, max_over_ranks, sum_over_ranks, peak_fp64
     if W.integ != _lib.LEAPFROG:
         run["dop853"] = {"accepted_steps": int(stats_run[0]), "rejected_steps": int(stats_run[1]),
                          "gradient_evals": int(stats_run[2]), "intervals": int(stats_run[3]),
-                         "gradient_evals_per_s": float(stats_run[2]) / (k_ms * 1e-3)}
+                         "gradient_evals_per_s": float(stats_run[2]) / (k_ms * 1e-3),
+                         "max_attempts_one_orbit": ctx.last_max_attempts,
+                         "note": "an orbit is sequential: max_attempts_one_orbit x the latency of one 12-stage attempt "
+                                 "bounds the launch from below, whatever the other lanes do"}
     return dict(value=value, ms_per_step=dev_ms / steps, e2e=e2e, roofline=roof, run=run, launches=int(launches),
                 clocks=clocks, total_steps=total_steps)
 

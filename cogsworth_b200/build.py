@@ -18,10 +18,11 @@ HEADERS = ["cw_device.cuh", "cw_kernels.cuh", "cw_traj.cuh", "cw_host.h", "../..
 OUT = os.environ.get("CW_BUILD_OUT") or os.path.join(HERE, "libcogsworth_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
-LINK_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-lcuda"]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread",
+              "-lcuda"]
 # experiment knobs (see cw_traj.cuh / cw_leapfrog.cu / cw_dop853.cu): -DNAME=VALUE when set in the environment
 KNOBS = ("CW_TRAJ_NOSTORE", "CW_TRAJ_DEBUG", "CW_LF_REGS", "CW_LF_GEN_REGS", "CW_DP_MINB", "CW_STORE_UNROLL",
-         "CW_LF_VARIANT", "CW_DP_VARIANT", "CW_TRAJ_VARIANT")
+         "CW_LF_VARIANT", "CW_DP_VARIANT", "CW_TRAJ_VARIANT", "CW_CHECKED", "CW_LF_BLOCK")
 
 
 def _nvcc():

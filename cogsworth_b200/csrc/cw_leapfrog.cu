@@ -174,7 +174,10 @@ cudaError_t launch_traj_times(const IntegArgs &A, const LaunchCfg &cfg)
 // ------------------------------------------------------------------------------------------
 // Leapfrog
 // ------------------------------------------------------------------------------------------
-constexpr int LF_BLOCK = 256;        // final-state kernel: 4 CTAs x 256 threads per SM (64 registers)
+#ifndef CW_LF_BLOCK
+#define CW_LF_BLOCK 256    // experiment knob (with CW_LF_REGS): threads per CTA of the final-state kernel
+#endif
+constexpr int LF_BLOCK = CW_LF_BLOCK; // final-state kernel: 4 CTAs x 256 threads per SM (64 registers)
 // store_all kernel: ONE CTA of 512 threads per SM.  The staging windows (392 B per lane = 196 KB) cap the
 // orbits in flight at 512 per SM, and a kernel that allocates tensor memory is given one CTA per SM by the
 // occupancy calculator whatever it asks for, so the 16 warps live in one CTA that owns all 512 TMEM columns
@@ -378,6 +381,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 if (p >= A.n) { exhausted = true; break; }
                 o = A.order ? (int64_t)A.order[p] : p;
             }
+            CW_ASSERT(o >= 0 && o < A.n);
             const int64_t n = A.n;
             s.oid = o;
             s.x = A.w0[o]; s.y = A.w0[n + o]; s.z = A.w0[2 * n + o];
@@ -401,6 +405,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
             apply_kicks(A, s);          // events at (or before) the first node: kicks.py:155-157
             if (STORE) {
                 col_base = A.traj_off[o] - A.traj_base;
+                CW_ASSERT(col_base >= 0 && col_base + s.L < A.traj_total && A.traj_off[o + 1] - A.traj_off[o] > s.L);
                 if (s.L == 0) traj_store_direct(A, col_base, s.x, s.y, s.z, s.vx, s.vy, s.vz);
                 else tw.put(col_base, s.x, s.y, s.z, s.vx, s.vy, s.vz, false);
                 staged = true;

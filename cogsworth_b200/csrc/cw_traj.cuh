@@ -20,9 +20,18 @@
 // uniform-datapath instruction, so ptxas serialised the 32 lanes with an R2UR/PLOP3/BRA loop -- 466
 // warp instructions per orbit-step, 2.2 TB/s.  See profiles/r1_ncu_store_all_tma_per_lane_summary.md.)
 #pragma once
+#include <cassert>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "cw_kernels.cuh"
+
+// CW_CHECKED=1 (build knob): device-side asserts on every index the trajectory writer forms -- the stand-in for
+// compute-sanitizer memcheck, which is closed on the GPU pool (profiles/r2_compute_sanitizer_closed.md)
+#ifdef CW_CHECKED
+#define CW_ASSERT(x) assert(x)
+#else
+#define CW_ASSERT(x) ((void)0)
+#endif
 
 namespace cw {
 
@@ -128,6 +137,7 @@ struct TrajWriter {
     __device__ __forceinline__ void enable_tmem(uint32_t tmem_base)
     {
         const int warp = threadIdx.x >> 5;
+        CW_ASSERT(((warp >> 2) + 1) * TRAJ_TMEM_COLS_PER_WARP <= TRAJ_TMEM_COLS_PER_CTA);
         taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TRAJ_TMEM_COLS_PER_WARP);
         tmem_on = true;
     }
@@ -137,6 +147,7 @@ struct TrajWriter {
     {
         const int slot = (int)(col & (TRAJ_S - 1));
         if (n == 0) col0 = col;
+        CW_ASSERT(col >= 0 && col < row_stride && n < TRAJ_S && col - col0 == n && (col0 & (TRAJ_S - 1)) + n < TRAJ_S);
         buf[0 * TRAJ_S + slot] = x;
         buf[1 * TRAJ_S + slot] = y;
         buf[2 * TRAJ_S + slot] = z;
@@ -210,6 +221,7 @@ struct TrajWriter {
         for (int g = 0; g < 8; g++) {
             const unsigned char *sg = src + g * 4 * TRAJ_LANE_BYTES;
             const long long c0 = *reinterpret_cast<const long long *>(sg - slot * 8 + TRAJ_DATA_BYTES) >> 4;
+            CW_ASSERT(c0 >= 0 && (c0 & (TRAJ_S - 1)) == 0 && c0 + TRAJ_S <= row_stride);
             double *dp = dst_pos + c0, *dv = dst_vel + c0;
             const double w0 = *reinterpret_cast<const double *>(sg + 0 * TRAJ_S * 8);
             const double w1 = *reinterpret_cast<const double *>(sg + 1 * TRAJ_S * 8);
@@ -241,6 +253,7 @@ struct TrajWriter {
                 const long long c0 = h >> 4;
                 const int cnt = (int)(h & 15);
                 const int s0 = (int)(c0 & (TRAJ_S - 1));
+                CW_ASSERT(c0 >= 0 && cnt >= 1 && s0 + cnt <= TRAJ_S && c0 + cnt <= row_stride);
                 if (slot >= s0 && slot < s0 + cnt) {
                     const double *rowbuf = reinterpret_cast<const double *>(sl) + slot;
                     double *dp = dst_pos + (c0 - s0), *dv = dst_vel + (c0 - s0);
@@ -309,6 +322,7 @@ struct TrajWriter {
 __device__ __forceinline__ void traj_store_direct(const IntegArgs &A, int64_t col, double x, double y, double z,
                                                   double vx, double vy, double vz)
 {
+    CW_ASSERT(col >= 0 && col < A.traj_total);
     A.traj_pos[col] = x;
     A.traj_pos[A.traj_total + col] = y;
     A.traj_pos[2 * A.traj_total + col] = z;
