@@ -1057,8 +1057,9 @@ static int make_chunks(HostCall &H, std::vector<Chunk> &chunks)
                     c.c2a = to[H.n_src + c.sa]; c.L2 = to[H.n_src + c.sb] - c.c2a;
                     if (c.L1 < 0 || c.L2 < 0) return fail(ctx, CW_E_INVALID, "offsets must be non-decreasing");
                     c.Lt = c.L1 + c.L2;
-                    // device rows are padded to a multiple of 16 columns so every row starts 128-byte aligned
-                    c.Ltp = (c.Lt + 15) & ~int64_t(15);
+                    // device rows are padded to a multiple of 32 columns so every row starts 256-byte aligned (the
+                    // trajectory writer's windows are aligned to absolute columns and leave in pairs)
+                    c.Ltp = (c.Lt + 31) & ~int64_t(31);
                 }
                 layout_chunk(H, c);
                 chunks.push_back(std::move(c));
@@ -1604,7 +1605,8 @@ extern "C" double cw_measure_fp64_peak(cw_ctx *ctx, int dev, double ms_target)
 extern "C" double cw_measure_scatter_write(cw_ctx *ctx, int dev, int64_t streams, int64_t stream_bytes, int run_bytes,
                                            int resident_threads_per_sm)
 {
-    const int rb = run_bytes < 0 ? -run_bytes : run_bytes;      // negative: with L2 eviction-priority hints
+    int rb = run_bytes < 0 ? -run_bytes : run_bytes;      // negative: with L2 eviction-priority hints
+    if (run_bytes == 1128) rb = 128;                      // one thread per stream, 128-byte runs as four 32-byte stores
     if (!ctx || dev < 0 || dev >= (int)ctx->slots.size() || rb < 16 || rb > 512 || (rb & 15) || stream_bytes % rb)
         return -1.0;
     Slot &s = ctx->slots[dev];

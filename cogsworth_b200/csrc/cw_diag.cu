@@ -149,9 +149,32 @@ __global__ void __launch_bounds__(256) scatter_write_kernel(double2 *base, long 
         }
 }
 
+// The same pattern written by ONE thread per stream: a run of 128 bytes (one full line) as four 32-byte stores
+// (STG.256, one full sector per lane and instruction) -- no cooperation between lanes, no shared-memory transposition;
+// the L2 receives a sector at a time.  run_bytes code 1128.
+__global__ void __launch_bounds__(256) scatter_write_perlane_kernel(double *base, long long streams, long long stream_bytes)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const long long visits = stream_bytes / 128;
+    const double v = (double)tid;
+    for (long long k = 0; k < visits; k++)
+        for (long long s0 = tid; s0 < streams; s0 += nthreads) {
+            double *p = base + (s0 * stream_bytes) / 8 + k * 16;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p + 4 * j), "d"(v), "d"(v), "d"(v), "d"(v)
+                             : "memory");
+        }
+}
+
 cudaError_t launch_scatter_write(double2 *base, long long streams, long long stream_bytes, int run_bytes,
                                  int blocks, const LaunchCfg &cfg)
 {
+    if (run_bytes == 1128) {
+        scatter_write_perlane_kernel<<<blocks, 256, 0, cfg.stream>>>((double *)base, streams, stream_bytes);
+        return cudaGetLastError();
+    }
     if (run_bytes < 0) scatter_write_kernel<1><<<blocks, 256, 0, cfg.stream>>>(base, streams, stream_bytes, -run_bytes);
     else scatter_write_kernel<0><<<blocks, 256, 0, cfg.stream>>>(base, streams, stream_bytes, run_bytes);
     return cudaGetLastError();

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
     __shared__ double2 ltab_mem[LOG_TABLE_N];
     extern __shared__ __align__(16) unsigned char traj_smem[];
     const LogTab ltab = log_table_init(ltab_mem);
-    TrajWriter tw;
+    TrajWriterDop tw;
     if (STORE && !PILOT) tw.init(traj_smem, A);
     int64_t col_base = 0;
     DpLane s;
@@ -614,7 +614,7 @@ template <int KIND, bool STORE, bool PILOT, bool DENSE>
 static cudaError_t launch_dp(const PotParams &P, const IntegArgs &A, const LaunchCfg &cfg)
 {
     int per_sm = 0;
-    const size_t dyn = (STORE && !PILOT) ? (size_t)DP_BLOCK * TRAJ_LANE_BYTES : 0;
+    const size_t dyn = (STORE && !PILOT) ? (size_t)DP_BLOCK * TrajWriterDop::LANE_BYTES : 0;
     cudaError_t err = cudaSuccess;
     if (dyn) {
         err = cudaFuncSetAttribute(dop853_kernel<KIND, STORE, PILOT, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);

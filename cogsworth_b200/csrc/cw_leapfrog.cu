@@ -182,9 +182,18 @@ constexpr int LF_BLOCK = CW_LF_BLOCK; // final-state kernel: 4 CTAs x 256 thread
 // orbits in flight at 512 per SM, and a kernel that allocates tensor memory is given one CTA per SM by the
 // occupancy calculator whatever it asks for, so the 16 warps live in one CTA that owns all 512 TMEM columns
 // (measured 4.13 TB/s vs 4.00 TB/s for 2 x 256 threads with 256 columns each; 128 registers per thread).
-constexpr int LF_BLOCK_STORE = 512;
+constexpr int LF_BLOCK_STORE = TRAJ_STORE_BLOCK;   // 512 lanes x 8-sample windows, or 256 x 16 (cw_traj.cuh)
 #ifndef CW_LF_REGS
 #define CW_LF_REGS 64      // experiment knob: 80 -> 3 resident CTAs (measured: see DESIGN.md)
+#endif
+// Tensor memory as a second staging level (a completed lower half-line window parked until its upper half arrives):
+// what made 64-byte runs leave as full 128-byte lines with 8-sample windows (round 1).  With 16-sample windows every
+// run IS a full line, and parking only adds shared-memory traffic (measured 3.84 vs 4.20 TB/s): on for TRAJ_S = 8 only.
+#ifndef CW_TRAJ_TMEM
+#define CW_TRAJ_TMEM (CW_TRAJ_S == 8)
+#endif
+#ifndef CW_LF_STORE_REGS
+#define CW_LF_STORE_REGS 168   // trajectory kernel with 256 lanes per SM
 #endif
 #ifndef CW_LF_GEN_REGS
 #define CW_LF_GEN_REGS 80  // final-state kernel of the general kind: 3 resident CTAs (measured +14 % over 128 on LM10)
@@ -248,7 +257,7 @@ __device__ __forceinline__ void write_final(const IntegArgs &A, const Lane &s)
 }
 
 template <int KIND, bool STORE>
-__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? 128 : (KIND == POT_GENERAL || KindTraits<KIND>::TS) ? CW_LF_GEN_REGS : CW_LF_REGS) leapfrog_kernel(const __grid_constant__ PotParams P,
+__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? (LF_BLOCK_STORE == 512 ? 128 : CW_LF_STORE_REGS) : (KIND == POT_GENERAL || KindTraits<KIND>::TS) ? CW_LF_GEN_REGS : CW_LF_REGS) leapfrog_kernel(const __grid_constant__ PotParams P,
                                                             const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
@@ -260,9 +269,11 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
     TrajWriter tw;
     if (STORE) {
         tw.init(traj_smem, A);
-        // 16 warps x 96 columns of tensor memory: second staging level of the trajectory writer
+#if CW_TRAJ_TMEM
+        // tensor memory (16 warps x 96 columns, or 8 x 192): second staging level of the trajectory writer
         tmem_base = traj_tmem_alloc(&tmem_slot);
         tw.enable_tmem(tmem_base);
+#endif
     }
     int64_t col_base = 0;          // STORE: column of sample 0 of the current orbit
     Lane s;
@@ -534,7 +545,9 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
             if (pending) delay -= m;
         }
     }
+#if CW_TRAJ_TMEM
     if (STORE) traj_tmem_free(tmem_base);
+#endif
     if (A.stats) {
         // orbit-steps actually integrated (the bench's unit of work), one atomic per warp
         for (int off = 16; off > 0; off >>= 1) steps_done += __shfl_down_sync(FULL, steps_done, off);
@@ -551,7 +564,7 @@ static cudaError_t launch_lf(const PotParams &P, const IntegArgs &A, const Launc
     // orbits spread evenly over the 148 SMs instead of filling a few of them (results do not depend on it).
     if (!STORE)
         while (block > 64 && (A.n + block - 1) / block < 2 * (int64_t)cfg.sm_count) block >>= 1;
-    const size_t dyn = STORE ? (size_t)block * TRAJ_LANE_BYTES : 0;
+    const size_t dyn = STORE ? (size_t)block * TrajWriter::LANE_BYTES : 0;
     cudaError_t err = cudaSuccess;
     if (STORE) {
         err = cudaFuncSetAttribute(leapfrog_kernel<KIND, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -560,6 +573,10 @@ static cudaError_t launch_lf(const PotParams &P, const IntegArgs &A, const Launc
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, leapfrog_kernel<KIND, STORE>, block, dyn);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
+    if (const char *e = getenv("CW_LF_MAX_CTAS")) {      // experiment hook: fewer resident CTAs per SM
+        const int v = atoi(e);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
     int64_t grid = (int64_t)cfg.sm_count * per_sm;
     const int64_t need = (A.n + block - 1) / block;
     if (grid > need) grid = need;

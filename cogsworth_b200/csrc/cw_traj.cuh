@@ -35,13 +35,28 @@
 
 namespace cw {
 
-constexpr int TRAJ_S = 8;                                    // samples per window
+#ifndef CW_TRAJ_WIDE
+#define CW_TRAJ_WIDE 0     // build knob: pair staging + 16-byte flush for 16-sample windows.  Measured at full size
+                           // (config 3, 48 GB): 3.77 TB/s against 4.07 TB/s for the 8-byte scheme -- half the shared-
+                           // memory instructions, but the kernel is bound by dependent-issue latency at 8 warps per SM
+                           // and by the 128-byte-run write pattern (ceiling 4.5 TB/s), not by MIO; off.
+#endif
+#ifndef CW_TRAJ_S
+#define CW_TRAJ_S 16       // build knob: 8 = round-1 geometry (64-byte runs, 512 lanes per SM), 16 = 128-byte runs, 256 lanes
+#endif
+constexpr int TRAJ_S = CW_TRAJ_S;                            // samples per window
+static_assert(TRAJ_S == 8 || TRAJ_S == 16, "TRAJ_S must be 8 or 16");
 constexpr int TRAJ_ROWS = 6;                                 // x y z vx vy vz
-constexpr int TRAJ_DATA_BYTES = TRAJ_ROWS * TRAJ_S * 8;      // 384: rows of one lane, [row][slot]
-// + 8-byte header {column << 4 | count}.  392 bytes = 98 words = 2 (mod 32): the 8-byte staging stores
+// One lane's rows [row][slot] + an 8-byte header {column << 5 | count}: 392 (776) bytes = 98 (194) words = 2 (mod 32): the 8-byte staging stores
 // of the 32 lanes fall into 32 distinct bank pairs (conflict-free), which a 16-byte-aligned stride
-// cannot give -- so the flush moves 8-byte words (LDS.64 -> STG.64), 8 adjacent lanes per 64-byte run.
-constexpr int TRAJ_LANE_BYTES = TRAJ_DATA_BYTES + 8;
+// cannot give -- so the flush moves 8-byte words (LDS.64 -> STG.64), TRAJ_S adjacent lanes per run of TRAJ_S * 8 bytes.
+constexpr int TRAJ_HDR_SHIFT = 5;                            // header = first column << 5 | samples in the window (<= 16)
+// Lanes of the trajectory-writing leapfrog kernel per SM.  Everything staged per lane is 2 x TRAJ_S samples x 48 B (one
+// window in shared memory, one parked in tensor memory): 512 lanes x 16 samples = 64-byte runs (round 1), 256 lanes x
+// 32 samples = 128-byte runs that leave in pairs, 256 contiguous bytes per stream.  The pure store pattern reaches 4.8
+// TB/s with 128-byte runs and 6.5 TB/s with 256-byte ones (cw_measure_scatter_write), and 8 warps per SM still sustain
+// 1.33e11 orbit-steps/s of the leapfrog arithmetic (tools/gpu_occ_probe.py) = 6.4 TB/s of samples.
+constexpr int TRAJ_STORE_BLOCK = (TRAJ_S == 8) ? 512 : 256;
 
 // ---- tensor memory as a second staging level ---------------------------------------------------------
 // Shared memory caps the staging windows at 8 samples = 64-byte runs, and lock-step 64-byte appends to
@@ -73,8 +88,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v)
                  : "memory");
 }
 
-constexpr int TRAJ_TMEM_COLS_PER_WARP = TRAJ_ROWS * TRAJ_S * 2;   // 96 32-bit columns per lane
-constexpr int TRAJ_TMEM_COLS_PER_CTA = 512;                        // 16 warps: 4 per lane quadrant x 96 = 384 -> 512
+constexpr int TRAJ_TMEM_COLS_PER_CTA = 512;                        // 16 (8) warps: 4 (2) per lane quadrant x 96 (192) = 384 -> 512
 
 // one warp of the CTA allocates; returns the TMEM base address to every thread (0 = not allocated)
 __device__ __forceinline__ uint32_t traj_tmem_alloc(uint32_t *slot)
@@ -99,9 +113,20 @@ __device__ __forceinline__ void traj_tmem_free(uint32_t base)
                      : "memory");
 }
 
-struct TrajWriter {
+template <int S>
+struct TrajWriterT {
+    static_assert(S == 8 || S == 16, "window of 8 or 16 samples");
+    static constexpr int DATA_BYTES = TRAJ_ROWS * S * 8;       // rows of one lane, [row][slot]
+    // + header.  392 / 776 B = 98 / 194 words = 2 (mod 32): conflict-free for the 8-byte staging stores.  WIDE (knob, off):
+    // samples staged in PAIRS with 16-byte stores and flushed with 16-byte loads / stores, which wants 16-byte aligned
+    // rows and a stride that is an odd number of 16-byte units: 784 B = 49 units.
+    static constexpr bool WIDE = (S == 16) && (CW_TRAJ_WIDE != 0);
+    static constexpr int LANE_BYTES = DATA_BYTES + (WIDE ? 16 : 8);
+    static constexpr int RPI = 32 / S;                         // runs one 8-byte store instruction of a warp writes
+    static constexpr int TMEM_COLS_PER_WARP = TRAJ_ROWS * S * 2;
+
     unsigned char *warp_base; // the 32 lane regions of this warp
-    double *buf;              // this lane's rows: buf[row * TRAJ_S + slot]
+    double *buf;              // this lane's rows: buf[row * S + slot]
     double *dst_pos, *dst_vel; // flush role of this lane: row 0 of pos / vel, offset by its slot (lane & 7)
     int64_t row_stride;        // columns per row
     int64_t col0;
@@ -113,17 +138,28 @@ struct TrajWriter {
     int64_t park_col0;        // first column of this lane's parked window
     uint32_t taddr;           // this warp's TMEM block (lane quadrant << 16 | first column)
     bool tmem_on;             // TMEM parking enabled
+    // WIDE: the sample of an even column waits here for its odd neighbour (one 16-byte store for both)
+    double hx, hy, hz, hvx, hvy, hvz;
+    bool held;
+    bool wide_ok;             // destination rows are 16-byte aligned: the lock-step flush may use 16-byte stores
+    double *pos0, *vel0;
 
     __device__ __forceinline__ void init(unsigned char *smem, const IntegArgs &A)
     {
         const int lane = threadIdx.x & 31;
-        warp_base = smem + (size_t)(threadIdx.x - lane) * TRAJ_LANE_BYTES;
-        buf = reinterpret_cast<double *>(warp_base + (size_t)lane * TRAJ_LANE_BYTES);
-        // flush role: lanes 8q..8q+7 move the 64-byte run of source lane 4g + q (slot = lane & 7), one
-        // row per instruction -- every store instruction writes four full runs
-        dst_pos = A.traj_pos + (lane & 7);
-        dst_vel = A.traj_vel + (lane & 7);
+        warp_base = smem + (size_t)(threadIdx.x - lane) * LANE_BYTES;
+        buf = reinterpret_cast<double *>(warp_base + (size_t)lane * LANE_BYTES);
+        // flush role: lanes S q .. S q + S-1 move the run of source lane RPI g + q (slot = lane % S), one
+        // row per instruction -- every store instruction writes RPI full runs
+        dst_pos = A.traj_pos + (lane & (S - 1));
+        dst_vel = A.traj_vel + (lane & (S - 1));
         row_stride = A.traj_total;
+        pos0 = A.traj_pos;
+        vel0 = A.traj_vel;
+        wide_ok = WIDE && ((reinterpret_cast<uintptr_t>(A.traj_pos) | reinterpret_cast<uintptr_t>(A.traj_vel)) & 15) == 0 &&
+                  (A.traj_total & 1) == 0;
+        hx = hy = hz = hvx = hvy = hvz = 0.0;
+        held = false;
         col0 = 0;
         n = 0;
         want = want_last = parked = lane_parked = false;
@@ -137,24 +173,57 @@ struct TrajWriter {
     __device__ __forceinline__ void enable_tmem(uint32_t tmem_base)
     {
         const int warp = threadIdx.x >> 5;
-        CW_ASSERT(((warp >> 2) + 1) * TRAJ_TMEM_COLS_PER_WARP <= TRAJ_TMEM_COLS_PER_CTA);
-        taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TRAJ_TMEM_COLS_PER_WARP);
+        CW_ASSERT(((warp >> 2) + 1) * TMEM_COLS_PER_WARP <= TRAJ_TMEM_COLS_PER_CTA);
+        taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TMEM_COLS_PER_WARP);
         tmem_on = true;
     }
 
     // stage a sample that is known NOT to complete the window (the integrator bounds its runs so)
     __device__ __forceinline__ void stage(int64_t col, double x, double y, double z, double vx, double vy, double vz)
     {
-        const int slot = (int)(col & (TRAJ_S - 1));
+        const int slot = (int)(col & (S - 1));
         if (n == 0) col0 = col;
-        CW_ASSERT(col >= 0 && col < row_stride && n < TRAJ_S && col - col0 == n && (col0 & (TRAJ_S - 1)) + n < TRAJ_S);
-        buf[0 * TRAJ_S + slot] = x;
-        buf[1 * TRAJ_S + slot] = y;
-        buf[2 * TRAJ_S + slot] = z;
-        buf[3 * TRAJ_S + slot] = vx;
-        buf[4 * TRAJ_S + slot] = vy;
-        buf[5 * TRAJ_S + slot] = vz;
+        CW_ASSERT(col >= 0 && col < row_stride && n < S && col - col0 == n && (col0 & (S - 1)) + n < S);
         n++;
+        if (WIDE) {
+            if ((slot & 1) == 0) {          // even column: wait for the neighbour (an even column never ends a window)
+                hx = x; hy = y; hz = z; hvx = vx; hvy = vy; hvz = vz;
+                held = true;
+                return;
+            }
+            if (held) {
+                double2 *b2 = reinterpret_cast<double2 *>(buf + slot - 1);
+                b2[0 * S / 2] = make_double2(hx, x);
+                b2[1 * S / 2] = make_double2(hy, y);
+                b2[2 * S / 2] = make_double2(hz, z);
+                b2[3 * S / 2] = make_double2(hvx, vx);
+                b2[4 * S / 2] = make_double2(hvy, vy);
+                b2[5 * S / 2] = make_double2(hvz, vz);
+                held = false;
+                return;
+            }
+        }
+        buf[0 * S + slot] = x;
+        buf[1 * S + slot] = y;
+        buf[2 * S + slot] = z;
+        buf[3 * S + slot] = vx;
+        buf[4 * S + slot] = vy;
+        buf[5 * S + slot] = vz;
+    }
+
+    // WIDE: the held sample of an even column goes out on its own (its orbit ends on it)
+    __device__ __forceinline__ void release_held(int64_t col)
+    {
+        if (WIDE && held) {
+            const int slot = (int)(col & (S - 1));
+            buf[0 * S + slot] = hx;
+            buf[1 * S + slot] = hy;
+            buf[2 * S + slot] = hz;
+            buf[3 * S + slot] = hvx;
+            buf[4 * S + slot] = hvy;
+            buf[5 * S + slot] = hvz;
+            held = false;
+        }
     }
 
     // stage one sample for absolute column `col`; `last` = final sample of the orbit.
@@ -163,9 +232,10 @@ struct TrajWriter {
                                         bool last)
     {
         stage(col, x, y, z, vx, vy, vz);
-        if ((col & (TRAJ_S - 1)) == TRAJ_S - 1 || last) {
-            *reinterpret_cast<long long *>(reinterpret_cast<unsigned char *>(buf) + TRAJ_DATA_BYTES) =
-                (long long)(col0 << 4) | (long long)n;
+        if ((col & (S - 1)) == S - 1 || last) {
+            release_held(col);
+            *reinterpret_cast<long long *>(reinterpret_cast<unsigned char *>(buf) + DATA_BYTES) =
+                (long long)(col0 << TRAJ_HDR_SHIFT) | (long long)n;
             want = true;
             want_last = last;
         }
@@ -176,14 +246,17 @@ struct TrajWriter {
     {
 #pragma unroll
         for (int r = 0; r < TRAJ_ROWS; r++) {
-            uint32_t v[16];
 #pragma unroll
-            for (int k = 0; k < TRAJ_S; k++) {
-                const double d = buf[r * TRAJ_S + k];
-                v[2 * k] = (uint32_t)__double2loint(d);
-                v[2 * k + 1] = (uint32_t)__double2hiint(d);
+            for (int h = 0; h < S / 8; h++) {      // 8 samples = 16 words per tcgen05.st
+                uint32_t v[16];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const double d = buf[r * S + 8 * h + k];
+                    v[2 * k] = (uint32_t)__double2loint(d);
+                    v[2 * k + 1] = (uint32_t)__double2hiint(d);
+                }
+                tmem_st16(taddr + 2 * S * r + 16 * h, v);
             }
-            tmem_st16(taddr + 16 * r, v);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         park_col0 = col0;
@@ -199,36 +272,40 @@ struct TrajWriter {
     {
 #pragma unroll
         for (int r = 0; r < TRAJ_ROWS; r++) {
-            uint32_t v[16];
-            tmem_ld16(taddr + 16 * r, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (mine) {
 #pragma unroll
-                for (int k = 0; k < TRAJ_S; k++) buf[r * TRAJ_S + k] = __hiloint2double((int)v[2 * k + 1], (int)v[2 * k]);
+            for (int h = 0; h < S / 8; h++) {
+                uint32_t v[16];
+                tmem_ld16(taddr + 2 * S * r + 16 * h, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (mine) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        buf[r * S + 8 * h + k] = __hiloint2double((int)v[2 * k + 1], (int)v[2 * k]);
+                }
             }
         }
         if (mine)
-            *reinterpret_cast<long long *>(reinterpret_cast<unsigned char *>(buf) + TRAJ_DATA_BYTES) =
-                (long long)(park_col0 << 4) | (long long)TRAJ_S;
+            *reinterpret_cast<long long *>(reinterpret_cast<unsigned char *>(buf) + DATA_BYTES) =
+                (long long)(park_col0 << TRAJ_HDR_SHIFT) | (long long)S;
     }
 
     // the lock-step store loop: all 32 lanes hold a complete window + header in shared memory
     __device__ __forceinline__ void store_all_windows(int lane)
     {
-        const int q = lane >> 3, slot = lane & 7;
-        const unsigned char *src = warp_base + q * TRAJ_LANE_BYTES + slot * 8;
+        const int q = lane / S, slot = lane & (S - 1);
+        const unsigned char *src = warp_base + q * LANE_BYTES + slot * 8;
 #pragma unroll
-        for (int g = 0; g < 8; g++) {
-            const unsigned char *sg = src + g * 4 * TRAJ_LANE_BYTES;
-            const long long c0 = *reinterpret_cast<const long long *>(sg - slot * 8 + TRAJ_DATA_BYTES) >> 4;
-            CW_ASSERT(c0 >= 0 && (c0 & (TRAJ_S - 1)) == 0 && c0 + TRAJ_S <= row_stride);
+        for (int g = 0; g < S; g++) {
+            const unsigned char *sg = src + g * RPI * LANE_BYTES;
+            const long long c0 = *reinterpret_cast<const long long *>(sg - slot * 8 + DATA_BYTES) >> TRAJ_HDR_SHIFT;
+            CW_ASSERT(c0 >= 0 && (c0 & (S - 1)) == 0 && c0 + S <= row_stride);
             double *dp = dst_pos + c0, *dv = dst_vel + c0;
-            const double w0 = *reinterpret_cast<const double *>(sg + 0 * TRAJ_S * 8);
-            const double w1 = *reinterpret_cast<const double *>(sg + 1 * TRAJ_S * 8);
-            const double w2 = *reinterpret_cast<const double *>(sg + 2 * TRAJ_S * 8);
-            const double w3 = *reinterpret_cast<const double *>(sg + 3 * TRAJ_S * 8);
-            const double w4 = *reinterpret_cast<const double *>(sg + 4 * TRAJ_S * 8);
-            const double w5 = *reinterpret_cast<const double *>(sg + 5 * TRAJ_S * 8);
+            const double w0 = *reinterpret_cast<const double *>(sg + 0 * S * 8);
+            const double w1 = *reinterpret_cast<const double *>(sg + 1 * S * 8);
+            const double w2 = *reinterpret_cast<const double *>(sg + 2 * S * 8);
+            const double w3 = *reinterpret_cast<const double *>(sg + 3 * S * 8);
+            const double w4 = *reinterpret_cast<const double *>(sg + 4 * S * 8);
+            const double w5 = *reinterpret_cast<const double *>(sg + 5 * S * 8);
             dp[0] = w0;
             dp[row_stride] = w1;
             dp[2 * row_stride] = w2;
@@ -238,29 +315,56 @@ struct TrajWriter {
         }
     }
 
+    // WIDE form of the lock-step store loop: 8 adjacent lanes move one 128-byte run 16 bytes at a time (LDS.128 ->
+    // STG.128), four runs per store instruction, 8 trips
+    __device__ __forceinline__ void store_all_windows_wide(int lane)
+    {
+        const int q = lane >> 3, u = lane & 7;
+        const unsigned char *src = warp_base + q * LANE_BYTES + u * 16;
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const unsigned char *sg = src + g * 4 * LANE_BYTES;
+            const long long c0 = *reinterpret_cast<const long long *>(sg - u * 16 + DATA_BYTES) >> TRAJ_HDR_SHIFT;
+            CW_ASSERT(c0 >= 0 && (c0 & (S - 1)) == 0 && c0 + S <= row_stride);
+            double *dp = pos0 + c0 + 2 * u, *dv = vel0 + c0 + 2 * u;
+            const double2 w0 = *reinterpret_cast<const double2 *>(sg + 0 * S * 8);
+            const double2 w1 = *reinterpret_cast<const double2 *>(sg + 1 * S * 8);
+            const double2 w2 = *reinterpret_cast<const double2 *>(sg + 2 * S * 8);
+            const double2 w3 = *reinterpret_cast<const double2 *>(sg + 3 * S * 8);
+            const double2 w4 = *reinterpret_cast<const double2 *>(sg + 4 * S * 8);
+            const double2 w5 = *reinterpret_cast<const double2 *>(sg + 5 * S * 8);
+            *reinterpret_cast<double2 *>(dp) = w0;
+            *reinterpret_cast<double2 *>(dp + row_stride) = w1;
+            *reinterpret_cast<double2 *>(dp + 2 * row_stride) = w2;
+            *reinterpret_cast<double2 *>(dv) = w3;
+            *reinterpret_cast<double2 *>(dv + row_stride) = w4;
+            *reinterpret_cast<double2 *>(dv + 2 * row_stride) = w5;
+        }
+    }
+
     // The same sweep for ANY subset of lanes and ragged windows (first / last window of an orbit, lanes
     // that are idle or waiting for their start slot): `mask` = source lanes that flush, each window's
     // extent comes from its header.  Eight trips whatever the mask, four 64-byte runs per store instruction.
     __device__ __forceinline__ void store_windows_masked(int lane, unsigned mask)
     {
-        const int q = lane >> 3, slot = lane & 7;
+        const int q = lane / S, slot = lane & (S - 1);
 #pragma unroll
-        for (int g = 0; g < 8; g++) {
-            const int l = 4 * g + q;
+        for (int g = 0; g < S; g++) {
+            const int l = RPI * g + q;
             if ((mask >> l) & 1u) {
-                const unsigned char *sl = warp_base + (size_t)l * TRAJ_LANE_BYTES;
-                const long long h = *reinterpret_cast<const long long *>(sl + TRAJ_DATA_BYTES);
-                const long long c0 = h >> 4;
-                const int cnt = (int)(h & 15);
-                const int s0 = (int)(c0 & (TRAJ_S - 1));
-                CW_ASSERT(c0 >= 0 && cnt >= 1 && s0 + cnt <= TRAJ_S && c0 + cnt <= row_stride);
+                const unsigned char *sl = warp_base + (size_t)l * LANE_BYTES;
+                const long long h = *reinterpret_cast<const long long *>(sl + DATA_BYTES);
+                const long long c0 = h >> TRAJ_HDR_SHIFT;
+                const int cnt = (int)(h & ((1 << TRAJ_HDR_SHIFT) - 1));
+                const int s0 = (int)(c0 & (S - 1));
+                CW_ASSERT(c0 >= 0 && cnt >= 1 && s0 + cnt <= S && c0 + cnt <= row_stride);
                 if (slot >= s0 && slot < s0 + cnt) {
                     const double *rowbuf = reinterpret_cast<const double *>(sl) + slot;
                     double *dp = dst_pos + (c0 - s0), *dv = dst_vel + (c0 - s0);
 #pragma unroll
                     for (int r = 0; r < 3; r++) {
-                        dp[r * row_stride] = rowbuf[r * TRAJ_S];
-                        dv[r * row_stride] = rowbuf[(3 + r) * TRAJ_S];
+                        dp[r * row_stride] = rowbuf[r * S];
+                        dv[r * row_stride] = rowbuf[(3 + r) * S];
                     }
                 }
             }
@@ -277,18 +381,19 @@ struct TrajWriter {
         __syncwarp();                       // the staged samples / headers of the other lanes are visible
         const int lane = threadIdx.x & 31;
         // a complete window on the lower half of a 128-byte line, not the last of its orbit, can wait in TMEM
-        const bool parkable = want && n == TRAJ_S && (col0 & (2 * TRAJ_S - 1)) == 0 && !want_last;
+        const bool parkable = want && n == S && (col0 & (2 * S - 1)) == 0 && !want_last;
         if (tmem_on && !parked && __ballot_sync(FULL, parkable) == m) {
             park();                         // every flushing lane parks; nothing is written
 #ifdef CW_TRAJ_DEBUG
             if (lane == 0) atomicAdd(A.stats + 0, 1ull);
 #endif
         } else {
-            const bool lockstep = (m == FULL) && __all_sync(FULL, n == TRAJ_S);
+            const bool lockstep = (m == FULL) && __all_sync(FULL, n == S);
 #ifdef CW_TRAJ_DEBUG
             if (lane == 0) atomicAdd(A.stats + (lockstep ? 2 : 1), lockstep ? 1ull : (unsigned long long)(__popc(m) + 1000000ull));
 #endif
-            if (lockstep) store_all_windows(lane);
+            if (lockstep && wide_ok) store_all_windows_wide(lane);
+            else if (lockstep) store_all_windows(lane);
             else store_windows_masked(lane, m);
             if (parked) {
                 // The parked lower halves of the lanes that just flushed follow immediately, so both halves of
@@ -302,7 +407,8 @@ struct TrajWriter {
                     __syncwarp();           // the rows just written out are free again
                     unpark_to_smem(mine);
                     __syncwarp();
-                    if (um == FULL) store_all_windows(lane);
+                    if (um == FULL && wide_ok) store_all_windows_wide(lane);
+                    else if (um == FULL) store_all_windows(lane);
                     else store_windows_masked(lane, um);
                     if (mine) lane_parked = false;
                 }
@@ -330,5 +436,10 @@ __device__ __forceinline__ void traj_store_direct(const IntegArgs &A, int64_t co
     A.traj_vel[A.traj_total + col] = vy;
     A.traj_vel[2 * A.traj_total + col] = vz;
 }
+
+// the leapfrog kernels write TRAJ_S-sample windows (build knob); DOPRI853 (compute-bound: 45 FLOP per stored byte) keeps
+// the small windows so that two of its 128-thread CTAs fit an SM
+using TrajWriter = TrajWriterT<TRAJ_S>;
+using TrajWriterDop = TrajWriterT<8>;
 
 } // namespace cw
