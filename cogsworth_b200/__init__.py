@@ -14,6 +14,7 @@ from .orbit_io import load_orbits, save_orbits  # noqa: F401
 from .events import identify_events, identify_event_tables  # noqa: F401
 from .kicks import get_kick_differential, integrate_orbit_with_events, integrate_orbits  # noqa: F401
 from .rewind import rewind_orbits  # noqa: F401
+from .classify import get_rel_speed  # noqa: F401
 from .pop import B200Population, GalacticStageB200, InitialGalaxy, TablePopulation  # noqa: F401
 from ._lib import Context, NativeLibraryError, default_context  # noqa: F401
 

@@ -13,10 +13,11 @@ Here the kernels' output already IS that layout::
 
 so saving is O(bytes) and loading returns a lazy :class:`~cogsworth_b200.orbits.OrbitArray`.
 
-HDF5 files need ``h5py`` (cogsworth's own dependency; not part of this image, where the same four
-arrays go into an ``.npz`` container with the keys ``orbits/offsets`` ... instead).  The container
-is chosen from the file extension; asking for HDF5 without h5py raises -- nothing is silently
-rerouted.
+HDF5 files are written / read with ``h5py`` when it is importable (cogsworth's own dependency) and otherwise with
+:mod:`cogsworth_b200.h5mini`, a ``struct``-only implementation of exactly the subset of the format these four arrays
+need (superblock 0, symbol-table groups, contiguous datasets -- h5py's defaults), so the reference's own container
+works in this image too; ``.npz`` file names select a dependency-free numpy container with the keys
+``orbits/offsets`` ... instead.  Without h5py an ``.h5`` file can only be created, not appended to.
 """
 from __future__ import annotations
 
@@ -40,9 +41,8 @@ def _h5py():
     try:
         import h5py
         return h5py
-    except ImportError as e:      # pragma: no cover - depends on the environment
-        raise ImportError("writing / reading cogsworth .h5 population files needs h5py; use an .npz "
-                          "file name for the dependency-free container") from e
+    except ImportError:           # pragma: no cover - depends on the environment
+        return None
 
 
 def save_orbits(file_name: str, orbits: OrbitArray) -> None:
@@ -57,6 +57,13 @@ def save_orbits(file_name: str, orbits: OrbitArray) -> None:
             "t": np.ascontiguousarray(t)}
     if _is_hdf5(file_name):
         h5 = _h5py()
+        if h5 is None:
+            from . import h5mini
+            if os.path.exists(file_name):
+                raise FileExistsError(f"{file_name} exists: appending the orbits group to a population file needs h5py "
+                                      "(cogsworth_b200.h5mini only creates files)")
+            h5mini.write_datasets(file_name, "orbits", {k: data[k] for k in _KEYS})
+            return
         with h5.File(file_name, "a") as f:
             if "orbits" in f:
                 del f["orbits"]
@@ -77,6 +84,13 @@ def save_orbits(file_name: str, orbits: OrbitArray) -> None:
 def _read(file_name: str):
     if _is_hdf5(file_name):
         h5 = _h5py()
+        if h5 is None:
+            from . import h5mini
+            try:
+                d = h5mini.read_datasets(file_name, "orbits", _KEYS)
+            except KeyError:
+                raise ValueError(f"No orbits found in population file ({file_name})") from None   # pop.py:704-705
+            return tuple(d[k] for k in _KEYS)
         with h5.File(file_name, "r") as f:
             if "orbits" not in f:
                 raise ValueError(f"No orbits found in population file ({file_name})")   # pop.py:704-705

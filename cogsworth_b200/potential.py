@@ -262,6 +262,32 @@ def _plain(v, unit=None):
     return np.asarray(v, dtype=np.float64)
 
 
+def _galactic_value(v, units):
+    """A parameter as a plain number in gala's ``galactic`` unit system (kpc, Myr, Msun, rad).  gala stores parameters
+    as Quantities in the units the user gave (LM10's v_c in km/s, a scale radius in pc, ...): they are DECOMPOSED into
+    the potential's unit system, not read by ``.value``."""
+    if hasattr(v, "decompose") and units is not None:
+        try:
+            return np.asarray(v.decompose(units).value, dtype=np.float64)
+        except Exception:
+            pass
+    return _plain(v)
+
+
+def _require_galactic(units):
+    """Everything below (G, the Myr time grid, kpc / kpc/Myr state) assumes the galactic unit system."""
+    if units is None:
+        return
+    try:
+        import astropy.units as u
+        scale = [float((1.0 * q).decompose(units).value) for q in (u.kpc, u.Myr, u.Msun)]
+    except Exception:
+        return                                    # stand-ins without astropy: nothing to check
+    if not np.allclose(scale, 1.0, rtol=1e-12, atol=0):
+        raise NotImplementedError("cogsworth_b200 integrates in gala's galactic unit system (kpc, Myr, Msun); this "
+                                  f"potential uses {units!r}")
+
+
 def from_gala(potential) -> CompositePotential:
     """Translate a gala potential instance into a parameter table (needs gala; lazy).
 
@@ -278,7 +304,8 @@ def from_gala(potential) -> CompositePotential:
         items = list(potential.items())
     except AttributeError:
         items = [("potential", potential)]
-    G = float(getattr(potential, "G", G_GALACTIC))
+    _require_galactic(getattr(potential, "units", None))
+    G = float(_plain(getattr(potential, "G", G_GALACTIC)))
 
     def add(name, t, p, R=None, kn=None):
         names.append(name); types.append(t); params.append(tuple(float(x) for x in p))
@@ -299,7 +326,8 @@ def from_gala(potential) -> CompositePotential:
             interp = str(getattr(comp, "interpolation_method", getattr(comp, "_interpolation_method", "cubic")))
             if interp not in ("cubic", "linear"):
                 raise NotImplementedError(f"TimeInterpolatedPotential interpolation {interp!r} (cubic and linear are built)")
-        praw = {k: _plain(v) for k, v in comp.parameters.items()}
+        cunits = getattr(comp, "units", None) or getattr(potential, "units", None)
+        praw = {k: _galactic_value(v, cunits) for k, v in comp.parameters.items()}
         varying = [k for k, v in praw.items() if v.ndim > 0 and v.size > 1 and not np.all(v == v.flat[0])]
         if t_knots is None and varying:
             raise NotImplementedError(f"component {name!r}: array-valued parameters {varying}")

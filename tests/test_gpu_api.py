@@ -369,6 +369,17 @@ def test_steps_either_side_of_the_path(ctx, oracle):
     for i in range(len(fp)):
         v_esc = np.sqrt(-2.0 * oracle.value(p.galactic_potential, fp[i].copy())) * K.KMS_PER_KPC_MYR
         assert esc[i] == (np.linalg.norm(fv[i]) >= v_esc)
+    # classify._get_rel_speed (classify.py:117-155) on the same orbits: circular velocity from the kernel, cylindrical
+    # components and the reference's combination on the host
+    from cogsworth_b200.classify import get_rel_speed
+    rel = get_rel_speed(p.orbits, p.galactic_potential, context=ctx)
+    assert rel.shape == (len(fp),)
+    for i in range(len(fp)):
+        vc = oracle.circular_velocity(p.galactic_potential, fp[i].copy()) * K.KMS_PER_KPC_MYR
+        phi = np.arctan2(fp[i, 1], fp[i, 0])
+        v_R = fv[i, 0] * np.cos(phi) + fv[i, 1] * np.sin(phi)
+        v_T = -fv[i, 0] * np.sin(phi) + fv[i, 1] * np.cos(phi)
+        assert abs(rel[i] - np.sqrt((v_R - vc) ** 2 + v_T ** 2 + fv[i, 2] ** 2)) < 1e-9 * rel[i]
 
 
 def test_population_in_an_evolving_potential(ctx):

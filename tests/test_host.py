@@ -260,11 +260,80 @@ def test_orbit_wire_format_roundtrip(tmp_path):
         save_orbits(f, bad)
     with pytest.raises(ValueError):
         load_orbits(str(tmp_path / "pop.npz").replace("pop", "other")) if False else save_orbits(str(tmp_path / "x.bin"), oa)
+
+
+def test_orbit_wire_format_hdf5(tmp_path):
+    """The reference's own container (pop.py:1853-1876: an HDF5 group `orbits` with `offsets`, `pos`, `vel`, `t`)
+    without h5py: cogsworth_b200.h5mini writes and reads the subset of the format h5py's defaults use.  Its reader is
+    pinned on the one real HDF5 file in the image -- scipy's MATLAB v7.3 fixture (a 512-byte user block, a libhdf5 1.8
+    writer), whose `testdouble` is pi/4 * arange(9) by scipy's own test -- and the writer against that reader."""
+    from cogsworth_b200 import constants as K, h5mini
+    from cogsworth_b200.orbit_io import final_coords_from_file, load_orbits, save_orbits
+    from cogsworth_b200.orbits import OrbitArray
+    import scipy.io
+    real = os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data", "testhdf5_7.4_GLNX86.mat")
+    if os.path.exists(real):
+        assert list(h5mini.list_datasets(real, "/")) == ["testdouble"]
+        td = h5mini.read_datasets(real, "/")["testdouble"]
+        assert td.shape == (9, 1) and np.array_equal(td.ravel(), np.pi / 4 * np.arange(9))
+    rng = np.random.default_rng(1)
+    lens = np.array([7, 2, 1, 11, 4])
+    off = np.concatenate([[0], np.cumsum(lens)])
+    pos, vel, t = rng.normal(size=(3, off[-1])), rng.normal(size=(3, off[-1])) * 0.2, np.arange(off[-1], dtype=float)
+    oa = OrbitArray(off, pos, vel, t)
+    f = str(tmp_path / "pop.h5")
+    save_orbits(f, oa)
+    raw = open(f, "rb").read()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and raw[8] == 0                 # signature, superblock version 0
+    assert set(h5mini.list_datasets(f, "orbits")) == {"offsets", "pos", "vel", "t"}
+    d = h5mini.read_datasets(f, "orbits")
+    assert d["offsets"].dtype == np.int64 and np.array_equal(d["offsets"], off)
+    assert d["pos"].shape == (3, off[-1]) and np.array_equal(d["pos"], pos)
+    assert np.allclose(d["vel"], vel * K.KMS_PER_KPC_MYR, rtol=1e-15) and np.array_equal(d["t"], t)   # km/s on disk
+    back = load_orbits(f)
+    assert np.array_equal(back.lengths(), lens) and np.array_equal(back.pos, pos) and np.array_equal(back.t, t)
+    fp, fv = final_coords_from_file(f)
+    assert np.array_equal(fp, oa.final_coords()[0])
     try:
-        import h5py  # noqa: F401
+        import h5py
     except ImportError:
-        with pytest.raises(ImportError):
-            save_orbits(str(tmp_path / "pop.h5"), oa)
+        with pytest.raises(FileExistsError):                              # appending needs the real library
+            save_orbits(f, oa)
+        with pytest.raises(ValueError):
+            h5mini.write_datasets(str(tmp_path / "other.h5"), "x", {"a": np.zeros(3)})
+            load_orbits(str(tmp_path / "other.h5"))
+    else:                                                                 # and h5py reads what h5mini wrote
+        with h5py.File(f, "r") as hf:
+            assert np.array_equal(hf["orbits"]["offsets"][...], off) and np.array_equal(hf["orbits"]["pos"][...], pos)
+
+
+def test_get_rel_speed_expression():
+    """classify._get_rel_speed (classify.py:117-155) restated on arrays: the host-side part (cylindrical components, the
+    reference's own combination) against a direct evaluation; the circular velocity itself is the GPU kernel's
+    (tests/test_gpu_api.py::test_steps_either_side_of_the_path)."""
+    import cogsworth_b200.classify as C
+    from cogsworth_b200.orbits import OrbitArray
+    rng = np.random.default_rng(3)
+    n = 50
+    w = np.vstack([rng.normal(0, 6, (3, n)), rng.normal(0, 0.2, (3, n))])
+
+    class FakeCtx:
+        def circular_velocity(self, q):
+            return 0.22 + 0.01 * q[0]
+
+    import cogsworth_b200.kicks as kk
+    orig = kk._context
+    kk._context = lambda potential, context=None: FakeCtx()
+    try:
+        got = C.get_rel_speed(OrbitArray.from_final(w, np.zeros(n)), potential=None)
+    finally:
+        kk._context = orig
+    from cogsworth_b200 import constants as K
+    phi = np.arctan2(w[1], w[0])
+    vx, vy, vz = w[3:] * K.KMS_PER_KPC_MYR
+    v_R, v_T = vx * np.cos(phi) + vy * np.sin(phi), -vx * np.sin(phi) + vy * np.cos(phi)
+    vc = (0.22 + 0.01 * w[0]) * K.KMS_PER_KPC_MYR
+    assert np.allclose(got, np.sqrt((v_R - vc) ** 2 + v_T ** 2 + vz ** 2), rtol=1e-13)
 
 
 def test_from_gala_translates_rotations_and_time_interpolation():
@@ -311,3 +380,37 @@ def test_from_gala_translates_rotations_and_time_interpolation():
     with pytest.raises(NotImplementedError):                                     # a time-dependent scale length
         P.from_gala(fake("TimeInterpolatedPotential", dict(m=1e12, r_s=np.linspace(10, 20, 5)), potential_cls=NFW,
                          time_knots=knots))
+
+
+def test_from_gala_decomposes_quantities_into_galactic_units():
+    """a parameter kept in the user's units (v_c in km/s, a scale radius in pc) must be decomposed into the
+    potential's unit system, not read by `.value` -- checked with astropy when it is installed."""
+    u = pytest.importorskip("astropy.units")
+    from cogsworth_b200 import potential as P
+    galactic = [u.kpc, u.Myr, u.Msun, u.radian]
+
+    class Units(list):
+        pass
+
+    class Hernquist:
+        def __init__(self):
+            self.parameters = {"m": 5e9 * u.Msun, "c": 1000.0 * u.pc}
+            self.units = Units(galactic)
+    Hernquist.__name__ = "HernquistPotential"
+
+    class Log:
+        def __init__(self):
+            self.parameters = {"v_c": 200.0 * u.km / u.s, "r_h": 12.0 * u.kpc, "q1": 1.0, "q2": 1.0, "q3": 0.8, "phi": 0.0}
+            self.units = Units(galactic)
+    Log.__name__ = "LogarithmicPotential"
+
+    class Comp(dict):
+        units = Units(galactic)
+        G = 4.498502151469553e-12
+    pot = P.from_gala(Comp(bulge=Hernquist(), halo=Log()))
+    assert pot.params[0][:2] == (5e9, 1.0)                                   # 1000 pc -> 1 kpc
+    assert abs(pot.params[1][0] - 200.0 / 977.7922216807891) < 1e-15          # km/s -> kpc/Myr
+    with pytest.raises(NotImplementedError):
+        bad = Comp(bulge=Hernquist())
+        bad.units = Units([u.pc, u.yr, u.Msun, u.radian])
+        P.from_gala(bad)
