@@ -1,12 +1,12 @@
 #!/bin/bash
 # Round profile: launch list of the bench command + one ncu --set full capture per integrator kernel.
 # usage (GPU box): bash tools/profile_round.sh TAG
-T=${1:-r1}
-C4="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
-C3="python bench.py --workload config3 --steps 2 --warmup 1 --no-cpu-baseline --scale 0.2"
-C3K="python bench.py --workload config3k --steps 2 --warmup 1 --no-cpu-baseline --scale 0.2"
-C5="python bench.py --workload config5 --steps 2 --warmup 1 --no-cpu-baseline --scale 0.05"
-C5D="python bench.py --workload config5_dense --steps 2 --warmup 1 --no-cpu-baseline --scale 0.05"
+T=${1:-r2}
+F="--no-cpu-baseline --no-other-workloads"
+C4="python bench.py --steps 2 --warmup 1 $F"
+C3="python bench.py --workload config3 --steps 2 --warmup 1 $F --scale 0.2"
+C3K="python bench.py --workload config3k --steps 2 --warmup 1 $F --scale 0.2"
+C5="python bench.py --workload config5 --steps 2 --warmup 1 $F --scale 0.05"
 $C4 > gpurun_out/${T}_plain_c4.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv $C4 > gpurun_out/${T}_ncu_launch.log 2>&1
 $C4 > /dev/null 2>&1 &&
@@ -17,6 +17,4 @@ $C3K > gpurun_out/${T}_plain_c3k.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:leapfrog_kernel -s 1 -c 1 -f -o gpurun_out/${T}_prof_storek $C3K > gpurun_out/${T}_ncu_c3k.log 2>&1
 $C5 > gpurun_out/${T}_plain_c5.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:dop853_kernel -s 3 -c 1 -f -o gpurun_out/${T}_prof_dop $C5 > gpurun_out/${T}_ncu_c5.log 2>&1
-$C5D > gpurun_out/${T}_plain_c5d.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:dop853_kernel -s 3 -c 1 -f -o gpurun_out/${T}_prof_dopd $C5D > gpurun_out/${T}_ncu_c5d.log 2>&1
-ls -la gpurun_out/${T}_*
+ls -la gpurun_out/${T}_prof_* gpurun_out/${T}_launches.csv
