@@ -581,37 +581,47 @@ def main():
 
     # ---- N > 1: the same 10^7 orbits through ONE process driving every GPU (what a Population user gets) --------------
     inproc = None
+    pg_alive = world > 1
     if world > 1 and not args.no_inprocess:
-        # The other ranks must wait on the HOST: an NCCL barrier is a spinning kernel on their GPU, and rank 0's work on
-        # that GPU would be time-sliced against it (two processes, one device).  They block on the rendezvous store.
+        # A Population user runs ONE process on the node.  The other ranks therefore leave first -- group destroyed,
+        # context closed, process gone, so that rank 0 is alone on every GPU as that user would be -- and rank 0 learns
+        # it from the rendezvous store.  (With the other ranks merely parked the leg measured 69 ms per pass on 8 GPUs
+        # against 10.3 ms for the same call in a process of its own, tools/gpu_inproc_probe.py.)
         import datetime
         from torch.distributed.distributed_c10d import _get_default_store
         store = _get_default_store()
         barrier()
-        if rank == 0:
-            try:
-                full = build_shard(wl, 0, 1, "strong", args.scale)
-                apply_workload_potential(wl, full)
-                with cb.Context(devices=list(range(world))) as call:
-                    call.set_potential(full.potential)
-                    from cogsworth_b200 import kicks
-                    run1 = lambda: kicks.integrate_orbits(full.batch, potential=full.potential, store_all=False,
-                                                          integrator=wl["integrator"], context=call)
-                    for _ in range(3):        # (results are kept as in the timed loop: two generations of page-locked
-                        _, info = run1()      # output buffers are then in the library's cache)
-                    t0 = time.perf_counter()
-                    for _ in range(args.steps):
-                        _, info = run1()
-                    dt = time.perf_counter() - t0
-                    st = float(info["stats"][3])
-                    inproc = {"value": st * args.steps / dt, "unit": "orbit-steps/s", "ms_per_step": 1e3 * dt / args.steps,
-                              "how": f"rank 0 alone, one cw_ctx on all {world} GPUs (one host thread per device, orbits sharded "
-                                     "by index), kicks.integrate_orbits on the whole workload; the other ranks wait on the host"}
-            finally:
-                store.set("cw_inprocess_done", "1")
-        else:
-            store.wait(["cw_inprocess_done"], datetime.timedelta(seconds=900))
-        barrier()
+        ctx.close()
+        dist.destroy_process_group()
+        pg_alive = False
+        if rank != 0:
+            store.set(f"cw_rank_gone_{rank}", "1")
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)            # no interpreter teardown: the CUDA context goes with the process, at once
+        try:
+            store.wait([f"cw_rank_gone_{r}" for r in range(1, world)], datetime.timedelta(seconds=300))
+            time.sleep(2.0)        # the driver tears the other processes' contexts down asynchronously
+            full = build_shard(wl, 0, 1, "strong", args.scale)
+            apply_workload_potential(wl, full)
+            with cb.Context(devices=list(range(world))) as call:
+                call.set_potential(full.potential)
+                from cogsworth_b200 import kicks
+                run1 = lambda: kicks.integrate_orbits(full.batch, potential=full.potential, store_all=False,
+                                                      integrator=wl["integrator"], context=call)
+                for _ in range(3):        # (results are kept as in the timed loop: two generations of page-locked
+                    _, info = run1()      # output buffers are then in the library's cache)
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    _, info = run1()
+                dt = time.perf_counter() - t0
+                st = float(info["stats"][3])
+                inproc = {"value": st * args.steps / dt, "unit": "orbit-steps/s", "ms_per_step": 1e3 * dt / args.steps,
+                          "how": f"rank 0 alone on the node (the other ranks have exited), one cw_ctx on all {world} GPUs "
+                                 "(one host thread per device, orbits sharded by index), kicks.integrate_orbits on the "
+                                 "whole workload in page-locked host memory; host wall clock"}
+        except Exception as exc:          # the headline line must still be printed
+            inproc = {"value": None, "error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         numa_note = f"; ranks bound to their GPU's NUMA node (rank 0: node {numa_node})" if numa_node is not None else ""
@@ -628,10 +638,12 @@ def main():
         if inproc is not None:
             line["e2e"]["in_process_all_gpus"] = inproc
         print(json.dumps(line), flush=True)
-    ctx.close()
-    if world > 1:
+    if pg_alive:
+        ctx.close()
         dist.barrier()
         dist.destroy_process_group()
+    elif world == 1:
+        ctx.close()
 
 
 if __name__ == "__main__":

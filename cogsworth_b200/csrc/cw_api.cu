@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <climits>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <utility>
@@ -487,6 +488,7 @@ static int set_potential_impl(cw_ctx *ctx, double G, int n_comp, const int32_t *
             for (int i = 0; i < nmn; i++) {
                 P.mn_GM[i] = P.GM[i];
                 P.mn_a[i] = params[3 * i + 1];
+                P.mn_GMa[i] = P.GM[i] * params[3 * i + 1];
                 P.mn_b2[i] = params[3 * i + 2] * params[3 * i + 2];
             }
             for (int k = 0; k < 2; k++) {
@@ -916,6 +918,14 @@ struct HostCall {
     bool p_w0, p_t1, p_t2, p_dt, p_tm, p_fl, p_cls, p_ctab, p_idx, p_off, p_evt, p_evd, p_toff;
     bool p_wf, p_st, p_nn, p_es, p_tp, p_tv, p_tt;
 
+    // CW_DEBUG: host wall clock of the call (every slot thread prints its own milestones relative to t_call)
+    bool trace = false;
+    std::chrono::steady_clock::time_point t_call;
+    double ms_since_call() const
+    {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
+    }
+
     int64_t ev_at(int64_t i) const { return off32 ? (int64_t)B->ev_off32[i] : B->ev_off[i]; }
     // number of secondaries whose source is < u
     int64_t lb(int64_t u) const
@@ -1304,6 +1314,7 @@ static int run_slot_host(HostCall &H, int d, std::vector<Chunk *> &mine)
     s.error.clear();
     s.launches = 0;
     if (mine.empty()) return CW_OK;
+    const double tr_start = H.trace ? H.ms_since_call() : 0.0;
     CW_SCK(s, cudaSetDevice(s.dev));
     // ---- size and reserve the lane arenas and staging buffers once, for all chunks of the call
     size_t need[Slot::N_LANES] = {0, 0, 0}, need_in[Slot::N_LANES] = {0, 0, 0}, need_out[Slot::N_LANES] = {0, 0, 0};
@@ -1338,6 +1349,7 @@ static int run_slot_host(HostCall &H, int d, std::vector<Chunk *> &mine)
         for (int l = 0; l < Slot::N_LANES; l++) cudaStreamSynchronize(s.lanes[l]);
     CW_SCK(s, s.meta.reserve(meta_need));
     CW_SCK(s, s.ensure_events(4 * mine.size()));
+    const double tr_reserved = H.trace ? H.ms_since_call() : 0.0;
     // ---- enqueue chunk after chunk; a chunk re-uses the buffers of the one three places back, which must have been
     // drained by then
     int rc = CW_OK;
@@ -1351,7 +1363,9 @@ static int run_slot_host(HostCall &H, int d, std::vector<Chunk *> &mine)
             if (!mine[j]->drained && cudaEventQuery(mine[j]->d2h_done) == cudaSuccess) rc = drain_chunk(s, *mine[j]);
         if (rc == CW_OK) rc = process_chunk(H, s, c);
     }
+    const double tr_enqueued = H.trace ? H.ms_since_call() : 0.0;
     for (size_t k = 0; k < mine.size() && rc == CW_OK; k++) rc = drain_chunk(s, *mine[k]);
+    const double tr_drained = H.trace ? H.ms_since_call() : 0.0;
     // ---- wait for the lanes (also on failure: nothing may still be reading or writing caller memory on return)
     for (int l = 0; l < Slot::N_LANES; l++) {
         const cudaError_t e = cudaStreamSynchronize(s.lanes[l]);
@@ -1361,6 +1375,10 @@ static int run_slot_host(HostCall &H, int d, std::vector<Chunk *> &mine)
         }
     }
     cudaGetLastError();
+    if (H.trace)
+        fprintf(stderr, "[cw] slot %d (device %d): %zu chunks; host thread started %.3f, buffers reserved %.3f, all chunks "
+                        "enqueued %.3f, drained %.3f, lanes idle %.3f ms after the call\n", d, s.dev, mine.size(), tr_start,
+                tr_reserved, tr_enqueued, tr_drained, H.ms_since_call());
     return rc;
 }
 
@@ -1369,6 +1387,8 @@ static int integrate_host(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
 {
     HostCall H;
     H.ctx = ctx; H.o = o; H.B = B;
+    H.trace = getenv("CW_DEBUG") != nullptr;
+    H.t_call = std::chrono::steady_clock::now();
     memset(&H.R, 0, sizeof H.R);
     if (R) H.R = *R;
     if (!integrate) { H.R.n_nodes = n_nodes_out; H.R.ev_step = ev_step_out; }
@@ -1425,6 +1445,7 @@ static int integrate_host(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, cons
     }
     if (first >= 0) rcs[first] = run_slot_host(H, first, per_slot[first]);
     for (std::thread &t : workers) t.join();
+    if (H.trace) fprintf(stderr, "[cw] %zu chunks planned and every slot joined %.3f ms after the call\n", chunks.size(), H.ms_since_call());
     ctx->last_launches = 0;
     for (int d = 0; d < nslots; d++) {
         ctx->last_launches += ctx->slots[d].launches;

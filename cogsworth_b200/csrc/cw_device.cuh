@@ -162,6 +162,7 @@ struct PotParams {
     double q2[CW_MAX_COMPONENTS][3]; // triaxial NFW: 1/a^2, 1/b^2, 1/c^2
     // pre-digested copies for the specialised kinds (MN terms first, then the spherical ones)
     double mn_GM[3], mn_a[3], mn_b2[3];
+    double mn_GMa[3];             // fl(GM_i a_i): the vertical sum of the shared-b disk accumulates GM_i a_i D_i^-3/2
     double h_GM[2], h_c[2];
     double nfw_GM, nfw_rs, nfw_inv_rs;
     // Full 64-bit numeric constants of log_tab.  As kernel parameters they are constant-bank operands
@@ -258,55 +259,7 @@ __device__ __forceinline__ void force_mw(const PotParams &P, LogTab ltab,
     const double z2 = z * z;
     const double r2 = R2 + z2;
 
-    // One Miyamoto-Nagai term needs f = GM D^-3/2, not D^-1/2 itself, so the third-order correction is
-    // applied to the cube directly: with the seed y ~ D^-1/2 and e = 1 - D y^2,
-    //     D^-3/2 = y^3 (1 - e)^-3/2 = y^3 (1 + e (3/2 + 15/8 e) + O(e^3)),   |e| < 2^-21,
-    // and y^2 serves both e and y^3: 7 FP64 instructions per term instead of 5 (rsqrt) + 3.
-    // both branches leave fxy and (za, zb) with fz = fxy + za zb, so that Fz = fma(za, zb, Fxy) below
-    double fxy, za, zb;
-    if (SHARED_B) {
-        // all terms share sqrt(z^2 + b^2): fz = sum f_i (1 + a_i/sz) = fxy + (sum a_i f_i) / sz
-        const double q = z2 + P.mn_b2[0];
-        const double isz = rsqrt_fast(q);
-        const double sz = q * isz;
-        double f[NMN];
-#pragma unroll
-        for (int i = 0; i < NMN; i++) {
-            const double zd = P.mn_a[i] + sz;
-            const double D = fma(zd, zd, R2);
-            const double y = rsqrt_seed(D, zd);            // zd dies here
-            const double y2 = y * y;
-            const double e = fma(-D, y2, 1.0);
-            const double p = fma(P.k_c158, e, 1.5);
-            const double g = y2 * (P.mn_GM[i] * y);
-            f[i] = fma(g * e, p, g);
-        }
-        fxy = f[0];
-        double fa = P.mn_a[0] * f[0];
-#pragma unroll
-        for (int i = 1; i < NMN; i++) {
-            fxy += f[i];
-            fa = fma(P.mn_a[i], f[i], fa);
-        }
-        za = isz;
-        zb = fa;
-    } else {
-        fxy = 0.0;
-        za = 0.0;
-        zb = 1.0;
-#pragma unroll
-        for (int i = 0; i < NMN; i++) {
-            const double q = z2 + P.mn_b2[i];
-            const double isz = rsqrt_fast(q);
-            const double zd = fma(q, isz, P.mn_a[i]);
-            const double rs = rsqrt_fast(fma(zd, zd, R2));
-            const double f = (rs * rs) * (P.mn_GM[i] * rs);
-            fxy = (i == 0) ? f : fxy + f;
-            const double fa = P.mn_a[i] * f;                 // f_i a_i / sz_i accumulates in za (zb = 1)
-            za = (i == 0) ? fa * isz : fma(fa, isz, za);
-        }
-    }
-
+    // ---- the three spherical components over ONE reciprocal square root and ONE reciprocal
     const double ir = rsqrt_fast(r2, R2);                  // seed donors: values whose last use is here
     const double r = r2 * ir;
     // two Hernquist spheres over one reciprocal: GM0/rc0^2 + GM1/rc1^2 = (GM0 rc1^2 + GM1 rc0^2) / (rc0 rc1)^2
@@ -324,8 +277,53 @@ __device__ __forceinline__ void force_mw(const PotParams &P, LogTab ltab,
     // fs = h / r + GM_nfw bracket / r^3 = (h + (GM_nfw / r^2) bracket) / r
     const double fs = ir * fma(P.nfw_GM * (ir * ir), bracket, h);
 
-    Fxy = fxy + fs;     // grad = (Fxy x, Fxy y, Fz z)
-    Fz = fma(za, zb, Fxy);
+    // ---- Miyamoto-Nagai terms.  One term needs f = GM D^-3/2, not D^-1/2 itself, so the third-order correction is
+    // applied to the cube directly: with the seed y ~ D^-1/2 and e = 1 - D y^2,
+    //     D^-3/2 = y^3 (1 - e)^-3/2 = y^3 (1 + e (3/2 + 15/8 e) + O(e^3)),   |e| < 2^-21,
+    // and y^2 serves both e and y^3.
+    if (SHARED_B) {
+        // all terms share sqrt(z^2 + b^2): fz = sum f_i (1 + a_i/sz) = fxy + (sum a_i f_i) / sz.  The masses enter only
+        // in the two accumulations (GM_i and GM_i a_i are constant-bank operands of their FMAs), the first of which
+        // starts from the spherical part: 8 FP64 instructions per term + 6 for the sums (round 1: 9 + 6).
+        const double q = z2 + P.mn_b2[0];
+        const double isz = rsqrt_fast(q);
+        const double sz = q * isz;
+        double t[NMN];
+#pragma unroll
+        for (int i = 0; i < NMN; i++) {
+            const double zd = P.mn_a[i] + sz;
+            const double D = fma(zd, zd, R2);
+            const double y = rsqrt_seed(D, zd);            // zd dies here
+            const double y2 = y * y;
+            const double e = fma(-D, y2, 1.0);
+            const double p = fma(P.k_c158, e, 1.5);
+            const double y3 = y2 * y;
+            t[i] = fma(y3 * e, p, y3);
+        }
+        double fxy = fs, fa = P.mn_GMa[0] * t[0];
+#pragma unroll
+        for (int i = 0; i < NMN; i++) {
+            fxy = fma(P.mn_GM[i], t[i], fxy);
+            if (i > 0) fa = fma(P.mn_GMa[i], t[i], fa);
+        }
+        Fxy = fxy;                   // grad = (Fxy x, Fxy y, Fz z)
+        Fz = fma(isz, fa, fxy);
+    } else {
+        double fxy = fs, za = 0.0;
+#pragma unroll
+        for (int i = 0; i < NMN; i++) {
+            const double q = z2 + P.mn_b2[i];
+            const double isz = rsqrt_fast(q);
+            const double zd = fma(q, isz, P.mn_a[i]);
+            const double rs = rsqrt_fast(fma(zd, zd, R2));
+            const double f = (rs * rs) * (P.mn_GM[i] * rs);
+            fxy += f;
+            const double fa = P.mn_a[i] * f;                 // f_i a_i / sz_i accumulates in za
+            za = (i == 0) ? fa * isz : fma(fa, isz, za);
+        }
+        Fxy = fxy;
+        Fz = fxy + za;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
