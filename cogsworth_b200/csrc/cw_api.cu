@@ -500,7 +500,14 @@ static int set_potential_impl(cw_ctx *ctx, double G, int n_comp, const int32_t *
             P.nfw_inv_rs = 1.0 / P.nfw_rs;
         }
     }
-    if (P.kind == POT_GENERAL)
+    if (P.kind == POT_GENERAL) {
+        // static and diagonal throughout (only rotated frames): the lighter kernels of POT_ROTATED, same bits
+        bool light = true;
+        for (int i = 0; i < n_comp; i++)
+            light = light && P.k_off[i + 1] == P.k_off[i] && types[i] < CW_COMP_LONG_MURALI_BAR;
+        if (light && !getenv("CW_NO_ROTATED_KIND")) P.kind = POT_ROTATED;
+    }
+    if (P.kind == POT_GENERAL || P.kind == POT_ROTATED)
         for (int i = n_comp - 1; i >= 0; i--) {
             const bool plain = !P.has_R[i] && P.k_off[i + 1] == P.k_off[i] && types[i] < CW_COMP_LONG_MURALI_BAR;
             P.run_end[i] = !plain ? 0 : (i + 1 < n_comp && P.run_end[i + 1] > i + 1) ? P.run_end[i + 1] : i + 1;

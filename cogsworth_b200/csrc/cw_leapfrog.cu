@@ -257,7 +257,7 @@ __device__ __forceinline__ void write_final(const IntegArgs &A, const Lane &s)
 }
 
 template <int KIND, bool STORE>
-__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? (LF_BLOCK_STORE == 512 ? 128 : CW_LF_STORE_REGS) : (KIND == POT_GENERAL || KindTraits<KIND>::TS) ? CW_LF_GEN_REGS : CW_LF_REGS) leapfrog_kernel(const __grid_constant__ PotParams P,
+__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? (LF_BLOCK_STORE == 512 ? 128 : CW_LF_STORE_REGS) : (KindTraits<KIND>::VEC || KindTraits<KIND>::TS) ? CW_LF_GEN_REGS : CW_LF_REGS) leapfrog_kernel(const __grid_constant__ PotParams P,
                                                             const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
         const double dt = s.dt, ndt = -s.dt, nhdt = -0.5 * s.dt;
         constexpr bool TRI = (KindTraits<KIND>::BASE == POT_GENERIC);    // only the generic composite can have Fy != Fx
         constexpr bool TS = KindTraits<KIND>::TS;      // Phi = f(t) Phi_0: the factors are scaled by f(t_node)
-        constexpr bool GEN = (KIND == POT_GENERAL);    // (Fxy, Fy, Fz) is the gradient itself, evaluated at the node's time
+        constexpr bool GEN = KindTraits<KIND>::VEC;    // (Fxy, Fy, Fz) is the gradient itself, evaluated at the node's time
         // time [Myr] of node J of this lane's orbit (POT_GENERAL only: the gradient of step j-1 -> j is taken at t_j)
         auto tnode = [&](int J) -> double {
             if (!GEN && !TS) return 0.0;
@@ -605,6 +605,7 @@ int64_t leapfrog_lane_capacity(const PotParams &P, int sm_count)
     case POT_MW_V1: return lf_capacity<POT_MW_V1>(sm_count);
     case POT_MW_V2: return lf_capacity<POT_MW_V2>(sm_count);
     case POT_GENERAL: return lf_capacity<POT_GENERAL>(sm_count);
+    case POT_ROTATED: return lf_capacity<POT_ROTATED>(sm_count);
     case POT_MW_V2_T: return lf_capacity<POT_MW_V2_T>(sm_count);
     case POT_GENERIC_T: return lf_capacity<POT_GENERIC_T>(sm_count);
     default: return lf_capacity<POT_GENERIC>(sm_count);
@@ -621,6 +622,8 @@ cudaError_t launch_leapfrog(const PotParams &P, const IntegArgs &A, bool store_a
         return store_all ? launch_lf<POT_MW_V2, true>(P, A, cfg) : launch_lf<POT_MW_V2, false>(P, A, cfg);
     case POT_GENERAL:
         return store_all ? launch_lf<POT_GENERAL, true>(P, A, cfg) : launch_lf<POT_GENERAL, false>(P, A, cfg);
+    case POT_ROTATED:
+        return store_all ? launch_lf<POT_ROTATED, true>(P, A, cfg) : launch_lf<POT_ROTATED, false>(P, A, cfg);
     case POT_MW_V2_T:
         return store_all ? launch_lf<POT_MW_V2_T, true>(P, A, cfg) : launch_lf<POT_MW_V2_T, false>(P, A, cfg);
     case POT_GENERIC_T:

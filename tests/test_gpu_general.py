@@ -58,6 +58,29 @@ def test_menu_potentials_pointwise_and_integrated(ctx, oracle, name):
     _local_step_check(ctx, oracle, pop, name, tol_v=1e-6 if name == "leesuto" else 1e-9)
 
 
+def test_rotated_kind_returns_the_general_kernels_bits(ctx, monkeypatch):
+    """LM10 (static, diagonal components, one rotated frame) runs in the lighter POT_ROTATED kernels; they must return
+    what the POT_GENERAL kernels return for the same potential, bit for bit, in every integrator and pointwise."""
+    pot = _menu()["lm10"]
+    pop = _population(300, 77, pot)
+    q = np.random.default_rng(5).normal(0, 9, (3, 512))
+    out = {}
+    for general in (False, True):
+        if general:
+            monkeypatch.setenv("CW_NO_ROTATED_KIND", "1")     # read when the potential is set
+        ctx.set_potential(pot)
+        res = [ctx.gradient(q), ctx.potential_value(q)]
+        for integ in (_lib.LEAPFROG, _lib.DOP853, _lib.DOP853_DENSE):
+            r = ctx.integrate_batch(pop.batch, integrator=integ, atol=1e-10, rtol=1e-10)
+            res += [r["w_final"], r["status"], r["stats"]]
+        r = ctx.integrate_batch(pop.batch, integrator=_lib.LEAPFROG, store_all=True)
+        res += [r["traj_pos"][:, : r["traj_off"][-1]], r["traj_vel"][:, : r["traj_off"][-1]]]
+        out[general] = res
+    monkeypatch.delenv("CW_NO_ROTATED_KIND")
+    for a, b in zip(out[False], out[True]):
+        assert np.array_equal(a, b)
+
+
 def test_rotation_is_a_change_of_frame(ctx):
     """An orbit in a rotated bar = the rotated orbit in the unrotated bar (and R = identity changes nothing)."""
     ang = 0.7
