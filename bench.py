@@ -439,7 +439,7 @@ def measure(W, steps, warmup, barrier, max_over_ranks, sum_over_ranks, peak_fp64
         if W.integ == _lib.LEAPFROG:
             per = FLOP_PER_STEP["leapfrog_lm10" if wl.get("potential") == "lm10" else "leapfrog_v2"]
             flops = per * steps_per_pass
-            kname = {"evolving_mw": "leapfrog_kernel<MW_V2_T>", "lm10": "leapfrog_kernel<ROTATED>"}.get(wl.get("potential"), "leapfrog_kernel<MW_V2>")
+            kname = {"evolving_mw": "leapfrog_kernel<MW_V2_T>", "lm10": "leapfrog_kernel<LM10>"}.get(wl.get("potential"), "leapfrog_kernel<MW_V2>")
         else:
             # 12 gradients + 1000 flop of stage algebra per accepted step, per launch
             flops = FLOP_PER_STEP["dop853_v2"] * float(stats_run[0])

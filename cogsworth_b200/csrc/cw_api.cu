@@ -506,8 +506,12 @@ static int set_potential_impl(cw_ctx *ctx, double G, int n_comp, const int32_t *
         for (int i = 0; i < n_comp; i++)
             light = light && P.k_off[i + 1] == P.k_off[i] && types[i] < CW_COMP_LONG_MURALI_BAR;
         if (light && !getenv("CW_NO_ROTATED_KIND")) P.kind = POT_ROTATED;
+        // gala's LM10Potential: the component list the kernels of POT_LM10 are compiled for
+        if (P.kind == POT_ROTATED && n_comp == 3 && types[0] == CW_COMP_MIYAMOTO_NAGAI && types[1] == CW_COMP_HERNQUIST &&
+            types[2] == CW_COMP_LOG_TRIAXIAL && !P.has_R[0] && !P.has_R[1] && P.has_R[2] && !getenv("CW_NO_LM10_KIND"))
+            P.kind = POT_LM10;
     }
-    if (P.kind == POT_GENERAL || P.kind == POT_ROTATED)
+    if (P.kind == POT_GENERAL || P.kind == POT_ROTATED || P.kind == POT_LM10)
         for (int i = n_comp - 1; i >= 0; i--) {
             const bool plain = !P.has_R[i] && P.k_off[i + 1] == P.k_off[i] && types[i] < CW_COMP_LONG_MURALI_BAR;
             P.run_end[i] = !plain ? 0 : (i + 1 < n_comp && P.run_end[i + 1] > i + 1) ? P.run_end[i + 1] : i + 1;

@@ -149,13 +149,17 @@ enum PotKind : int {
     // rotated frames (LM10: disk and bulge beside a rotated triaxial logarithmic halo).  The same arithmetic as
     // POT_GENERAL bit for bit (a static amplitude is the factor 1.0), without the spline look-up and the called
     // non-diagonal function in the kernel: no spills, a third fewer instructions per step.
-    POT_ROTATED = 6
+    POT_ROTATED = 6,
+    // gala's LM10Potential as a compile-time shape of POT_ROTATED: Miyamoto-Nagai disk, Hernquist bulge, triaxial
+    // logarithmic halo in a rotated frame.  The same source expressions with the component list known to the compiler:
+    // no type dispatch, no per-lane constant-bank indices (241 -> ~130 warp instructions per step).
+    POT_LM10 = 7
 };
 template <int KIND> struct KindTraits {
     static constexpr bool TS = (KIND == POT_MW_V2_T || KIND == POT_GENERIC_T);
     static constexpr int BASE = (KIND == POT_MW_V2_T) ? POT_MW_V2 : (KIND == POT_GENERIC_T) ? POT_GENERIC : KIND;
     // the force functions return the gradient vector itself, not three diagonal factors
-    static constexpr bool VEC = (KIND == POT_GENERAL || KIND == POT_ROTATED);
+    static constexpr bool VEC = (KIND == POT_GENERAL || KIND == POT_ROTATED || KIND == POT_LM10);
 };
 
 struct PotParams {
@@ -467,9 +471,30 @@ __device__ __forceinline__ void nondiag_component(const PotParams &P, int i, dou
     if (phi) *phi = o.w;
 }
 
+// The component list as the force functions see it: read from the parameter block (any potential), or fixed at compile
+// time (a named composite: loops unroll, type switches fold, every parameter becomes a uniform operand).
+struct ShapeDyn {
+    static constexpr bool FIXED = false;
+    static __device__ __forceinline__ int n(const PotParams &P) { return P.n_comp; }
+    static __device__ __forceinline__ int type(const PotParams &P, int i) { return P.type[i]; }
+    static __device__ __forceinline__ bool rotated(const PotParams &P, int i) { return P.has_R[i] != 0; }
+    static __device__ __forceinline__ int run_end(const PotParams &P, int i) { return P.run_end[i]; }
+};
+struct ShapeLM10 {
+    static constexpr bool FIXED = true;
+    static __device__ __forceinline__ int n(const PotParams &) { return 3; }
+    static __device__ __forceinline__ int type(const PotParams &, int i)
+    {
+        return i == 0 ? CW_COMP_MIYAMOTO_NAGAI : i == 1 ? CW_COMP_HERNQUIST : CW_COMP_LOG_TRIAXIAL;
+    }
+    static __device__ __forceinline__ bool rotated(const PotParams &, int i) { return i == 2; }
+    static __device__ __forceinline__ int run_end(const PotParams &, int i) { return i < 2 ? 2 : 0; }
+};
+
 __device__ __forceinline__ bool comp_is_nondiag(int t) { return t >= CW_COMP_LONG_MURALI_BAR; }
 
 // Generic composite: components in the caller's order.
+template <class SHAPE = ShapeDyn>
 __device__ __forceinline__ void force_generic_range(const PotParams &P, LogTab ltab, const int i0, const int i1,
                                                     double x, double y, double z, double &Fxy, double &Fy, double &Fz)
 {
@@ -480,8 +505,9 @@ __device__ __forceinline__ void force_generic_range(const PotParams &P, LogTab l
     double fyx = 0.0;             // Fy - Fxy: non-zero only for components flattened differently in x and y
     double ir = 0.0, r = 0.0;
     bool have_r = false;
+#pragma unroll
     for (int i = i0; i < i1; i++) {
-        const int t = P.type[i];
+        const int t = SHAPE::type(P, i);
         if (t == CW_COMP_MIYAMOTO_NAGAI) {
             const double q = fma(P.p2[i], P.p2[i], z2);
             const double isz = rsqrt_fast(q);
@@ -493,7 +519,8 @@ __device__ __forceinline__ void force_generic_range(const PotParams &P, LogTab l
         } else {
             if (!have_r) {
                 ir = rsqrt_fast(r2);
-                r = r2 * ir;
+                r = __dmul_rn(r2, ir);       // a rounded product of its own in every instantiation (with a compile-time
+                                             // component list r + c would otherwise contract into fma(r2, ir, c))
                 have_r = true;
             }
             double f;
@@ -556,8 +583,10 @@ __device__ __forceinline__ void force_generic_range(const PotParams &P, LogTab l
                 const double bracket = (ltab.on() ? log_tab(P, w, ltab) : log_fast(w)) - u * rcp_fast(w);
                 f = P.GM[i] * ((ir * ir) * ir) * bracket;
             }
-            fxy += f;
-            fz += f;
+            // (explicit roundings: where the component list is known at compile time f is a visible product, and a
+            // contraction into these sums would change the bits against the run-time list)
+            fxy = __dadd_rn(fxy, f);
+            fz = __dadd_rn(fz, f);
         }
     }
     Fxy = fxy;
@@ -574,6 +603,7 @@ __device__ __forceinline__ void force_generic(const PotParams &P, LogTab ltab,
 // The three diagonal factors of ONE component (types 1..12) for the general kernels: grad = (Fx x, Fy y, Fz z).
 // The same formulas as force_generic_range, behind a jump table instead of a chain of comparisons and without the
 // bookkeeping that lets a whole composite share one radius.
+template <class SHAPE = ShapeDyn>
 __device__ __forceinline__ void diag_component(const PotParams &P, LogTab ltab, const int i,
                                                double x, double y, double z, double &Fx, double &Fy, double &Fz)
 {
@@ -582,7 +612,7 @@ __device__ __forceinline__ void diag_component(const PotParams &P, LogTab ltab, 
     const double r2 = R2 + z2;
     const double GM = P.GM[i], p1 = P.p1[i], p2 = P.p2[i];
     double f;
-    switch (P.type[i]) {
+    switch (SHAPE::type(P, i)) {
     case CW_COMP_MIYAMOTO_NAGAI: {
         const double q = fma(p2, p2, z2);
         const double isz = rsqrt_fast(q);
@@ -638,7 +668,7 @@ __device__ __forceinline__ void diag_component(const PotParams &P, LogTab ltab, 
     default: {
         const double ir = rsqrt_fast(r2);
         const double r = r2 * ir;
-        switch (P.type[i]) {
+        switch (SHAPE::type(P, i)) {
         case CW_COMP_HERNQUIST: {
             const double rc = r + p1;
             f = GM * rcp_fast(rc * rc) * ir;
@@ -665,38 +695,43 @@ __device__ __forceinline__ void diag_component(const PotParams &P, LogTab ltab, 
 }
 
 // POT_GENERAL: gradient at time t [Myr], components accumulated in the caller's order (c_gradient)
-template <bool STATIC_DIAG>
+template <bool STATIC_DIAG, class SHAPE = ShapeDyn>
 static __device__ __forceinline__ void gradient_general(const PotParams &P, LogTab ltab, double t,
                                               double x, double y, double z, double &gx, double &gy, double &gz)
 {
     double ax = 0.0, ay = 0.0, az = 0.0;
-    for (int i = 0; i < P.n_comp; i++) {
-        const int e = P.run_end[i];
-        if (e > i) {       // a run of plain components (LM10's disk and bulge beside its rotated halo)
-            double Fx, Fy, Fz;
-            force_generic_range(P, ltab, i, e, x, y, z, Fx, Fy, Fz);
-            ax = __dadd_rn(ax, __dmul_rn(Fx, x)); ay = __dadd_rn(ay, __dmul_rn(Fy, y)); az = __dadd_rn(az, __dmul_rn(Fz, z));
-            i = e - 1;
+#pragma unroll
+    for (int i = 0; i < SHAPE::n(P); i++) {
+        const int e = SHAPE::run_end(P, i);
+        if (e > i) {       // a run of plain components (LM10's disk and bulge beside its rotated halo): evaluated as one,
+                           // on its first member
+            if (i == 0 || SHAPE::run_end(P, i - 1) != e) {
+                double Fx, Fy, Fz;
+                force_generic_range<SHAPE>(P, ltab, i, e, x, y, z, Fx, Fy, Fz);
+                ax = __dadd_rn(ax, __dmul_rn(Fx, x)); ay = __dadd_rn(ay, __dmul_rn(Fy, y)); az = __dadd_rn(az, __dmul_rn(Fz, z));
+            }
             continue;
         }
         const double rel = STATIC_DIAG ? 1.0 : amplitude_rel(P, i, t);
+        const bool rot = SHAPE::rotated(P, i);
         double xr = x, yr = y, zr = z;
-        if (P.has_R[i]) {
+        if (rot) {
             xr = fma(P.R[i][2], z, fma(P.R[i][1], y, __dmul_rn(P.R[i][0], x)));
             yr = fma(P.R[i][5], z, fma(P.R[i][4], y, __dmul_rn(P.R[i][3], x)));
             zr = fma(P.R[i][8], z, fma(P.R[i][7], y, __dmul_rn(P.R[i][6], x)));
         }
         double cx, cy, cz;
-        if (!STATIC_DIAG && comp_is_nondiag(P.type[i])) {
+        if (!STATIC_DIAG && comp_is_nondiag(SHAPE::type(P, i))) {
             nondiag_component(P, i, __dmul_rn(P.GM[i], rel), xr, yr, zr, cx, cy, cz, nullptr);
         } else {
             double Fx, Fy, Fz;
-            diag_component(P, ltab, i, xr, yr, zr, Fx, Fy, Fz);
-            cx = __dmul_rn(__dmul_rn(Fx, rel), xr);
-            cy = __dmul_rn(__dmul_rn(Fy, rel), yr);
-            cz = __dmul_rn(__dmul_rn(Fz, rel), zr);
+            diag_component<SHAPE>(P, ltab, i, xr, yr, zr, Fx, Fy, Fz);
+            // (a static amplitude is the factor 1.0: the product it is left out of is exact)
+            cx = __dmul_rn(STATIC_DIAG ? Fx : __dmul_rn(Fx, rel), xr);
+            cy = __dmul_rn(STATIC_DIAG ? Fy : __dmul_rn(Fy, rel), yr);
+            cz = __dmul_rn(STATIC_DIAG ? Fz : __dmul_rn(Fz, rel), zr);
         }
-        if (P.has_R[i]) {
+        if (rot) {
             ax = __dadd_rn(ax, fma(P.R[i][6], cz, fma(P.R[i][3], cy, __dmul_rn(P.R[i][0], cx))));
             ay = __dadd_rn(ay, fma(P.R[i][7], cz, fma(P.R[i][4], cy, __dmul_rn(P.R[i][1], cx))));
             az = __dadd_rn(az, fma(P.R[i][8], cz, fma(P.R[i][5], cy, __dmul_rn(P.R[i][2], cx))));
@@ -705,6 +740,15 @@ static __device__ __forceinline__ void gradient_general(const PotParams &P, LogT
         }
     }
     gx = ax; gy = ay; gz = az;
+}
+
+// the vector-gradient kinds
+template <int KIND>
+static __device__ __forceinline__ void gradient_vec(const PotParams &P, LogTab ltab, double t,
+                                                    double x, double y, double z, double &gx, double &gy, double &gz)
+{
+    if (KIND == POT_LM10) gradient_general<true, ShapeLM10>(P, ltab, t, x, y, z, gx, gy, gz);
+    else gradient_general<KIND == POT_ROTATED, ShapeDyn>(P, ltab, t, x, y, z, gx, gy, gz);
 }
 
 // ltab: the CTA's shared-memory log table (log_table_init), or nullptr to use the table-free log.
@@ -735,7 +779,7 @@ __device__ __forceinline__ void gradient(const PotParams &P, LogTab ltab, double
                                          double &gx, double &gy, double &gz)
 {
     if (KindTraits<KIND>::VEC) {
-        gradient_general<KIND == POT_ROTATED>(P, ltab, t, x, y, z, gx, gy, gz);
+        gradient_vec<KIND>(P, ltab, t, x, y, z, gx, gy, gz);
     } else if (KindTraits<KIND>::TS) {
         double Fx, Fy, Fz;
         force3<KindTraits<KIND>::BASE>(P, ltab, x, y, z, Fx, Fy, Fz);
@@ -795,7 +839,7 @@ __device__ __forceinline__ void force3t(const PotParams &P, LogTab ltab, double 
                                         double x, double y, double z, double &Fx, double &Fy, double &Fz)
 {
     if (KindTraits<KIND>::VEC) {
-        gradient_general<KIND == POT_ROTATED>(P, ltab, t, x, y, z, Fx, Fy, Fz);
+        gradient_vec<KIND>(P, ltab, t, x, y, z, Fx, Fy, Fz);
     } else if (KindTraits<KIND>::TS) {
         force3<KindTraits<KIND>::BASE>(P, ltab, x, y, z, Fx, Fy, Fz);
         const double f = amplitude_rel(P, 0, t);
@@ -843,7 +887,7 @@ __device__ __forceinline__ double potential_value(const PotParams &P, double x0,
         const int t = P.type[i];
         double x = x0, y = y0, z = z0, rel = 1.0;
         if (P.kind == POT_MW_V2_T || P.kind == POT_GENERIC_T) rel = amplitude_rel(P, 0, t_eval);
-        if (P.kind == POT_GENERAL || P.kind == POT_ROTATED) {
+        if (P.kind == POT_GENERAL || P.kind == POT_ROTATED || P.kind == POT_LM10) {
             rel = amplitude_rel(P, i, t_eval);
             if (P.has_R[i]) {
                 x = fma(P.R[i][2], z0, fma(P.R[i][1], y0, P.R[i][0] * x0));

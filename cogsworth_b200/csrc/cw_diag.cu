@@ -48,6 +48,7 @@ cudaError_t launch_pointwise(const PotParams &P, int mode, int64_t n, const doub
     case POT_MW_V2: pointwise_kernel<POT_MW_V2><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, tt, out); break;
     case POT_GENERAL: pointwise_kernel<POT_GENERAL><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, tt, out); break;
     case POT_ROTATED: pointwise_kernel<POT_ROTATED><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, tt, out); break;
+    case POT_LM10: pointwise_kernel<POT_LM10><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, tt, out); break;
     case POT_MW_V2_T: pointwise_kernel<POT_MW_V2_T><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, tt, out); break;
     case POT_GENERIC_T: pointwise_kernel<POT_GENERIC_T><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, tt, out); break;
     default: pointwise_kernel<POT_GENERIC><<<(unsigned)grid, block, 0, cfg.stream>>>(P, mode, n, q, tt, out); break;

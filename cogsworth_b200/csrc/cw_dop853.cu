@@ -647,6 +647,7 @@ cudaError_t launch_dop853(const PotParams &P, const IntegArgs &A, bool store_all
     case POT_MW_V2: return launch_dp_kind<POT_MW_V2>(P, A, store_all, dense, cfg);
     case POT_GENERAL: return launch_dp_kind<POT_GENERAL>(P, A, store_all, dense, cfg);
     case POT_ROTATED: return launch_dp_kind<POT_ROTATED>(P, A, store_all, dense, cfg);
+    case POT_LM10: return launch_dp_kind<POT_LM10>(P, A, store_all, dense, cfg);
     case POT_MW_V2_T: return launch_dp_kind<POT_MW_V2_T>(P, A, store_all, dense, cfg);
     case POT_GENERIC_T: return launch_dp_kind<POT_GENERIC_T>(P, A, store_all, dense, cfg);
     default: return launch_dp_kind<POT_GENERIC>(P, A, store_all, dense, cfg);
@@ -663,6 +664,7 @@ cudaError_t launch_dop853_pilot(const PotParams &P, const IntegArgs &A, const La
     case POT_MW_V2: return launch_dp<POT_MW_V2, false, true, false>(P, A, cfg);
     case POT_GENERAL: return launch_dp<POT_GENERAL, false, true, false>(P, A, cfg);
     case POT_ROTATED: return launch_dp<POT_ROTATED, false, true, false>(P, A, cfg);
+    case POT_LM10: return launch_dp<POT_LM10, false, true, false>(P, A, cfg);
     case POT_MW_V2_T: return launch_dp<POT_MW_V2_T, false, true, false>(P, A, cfg);
     case POT_GENERIC_T: return launch_dp<POT_GENERIC_T, false, true, false>(P, A, cfg);
     default: return launch_dp<POT_GENERIC, false, true, false>(P, A, cfg);

@@ -196,7 +196,9 @@ constexpr int LF_BLOCK_STORE = TRAJ_STORE_BLOCK;   // 512 lanes x 8-sample windo
 #define CW_LF_STORE_REGS 168   // trajectory kernel with 256 lanes per SM
 #endif
 #ifndef CW_LF_GEN_REGS
-#define CW_LF_GEN_REGS 80  // final-state kernel of the general kind: 3 resident CTAs (measured +14 % over 128 on LM10)
+#define CW_LF_GEN_REGS 80  // final-state kernel of the general and separable kinds: 3 resident CTAs (measured +14 % over 128 on
+                           // LM10 in the general kernel, +2 % over 64 in the evolving Milky Way); the static rotated kinds
+                           // (POT_ROTATED, POT_LM10) take the 64 registers of the Milky Way kernels (+4.5 % over 80 on LM10)
 #endif
 // Register budgets (__maxnreg__ on the kernel): 64 for the final-state kernel = 4 resident CTAs of 256 threads,
 // 128 for the store_all kernel = its single 512-thread CTA.
@@ -257,7 +259,7 @@ __device__ __forceinline__ void write_final(const IntegArgs &A, const Lane &s)
 }
 
 template <int KIND, bool STORE>
-__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? (LF_BLOCK_STORE == 512 ? 128 : CW_LF_STORE_REGS) : (KindTraits<KIND>::VEC || KindTraits<KIND>::TS) ? CW_LF_GEN_REGS : CW_LF_REGS) leapfrog_kernel(const __grid_constant__ PotParams P,
+__global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__(STORE ? (LF_BLOCK_STORE == 512 ? 128 : CW_LF_STORE_REGS) : (KIND == POT_GENERAL || KindTraits<KIND>::TS) ? CW_LF_GEN_REGS : CW_LF_REGS) leapfrog_kernel(const __grid_constant__ PotParams P,
                                                             const __grid_constant__ IntegArgs A)
 {
     const unsigned FULL = 0xffffffffu;
@@ -606,6 +608,7 @@ int64_t leapfrog_lane_capacity(const PotParams &P, int sm_count)
     case POT_MW_V2: return lf_capacity<POT_MW_V2>(sm_count);
     case POT_GENERAL: return lf_capacity<POT_GENERAL>(sm_count);
     case POT_ROTATED: return lf_capacity<POT_ROTATED>(sm_count);
+    case POT_LM10: return lf_capacity<POT_LM10>(sm_count);
     case POT_MW_V2_T: return lf_capacity<POT_MW_V2_T>(sm_count);
     case POT_GENERIC_T: return lf_capacity<POT_GENERIC_T>(sm_count);
     default: return lf_capacity<POT_GENERIC>(sm_count);
@@ -624,6 +627,8 @@ cudaError_t launch_leapfrog(const PotParams &P, const IntegArgs &A, bool store_a
         return store_all ? launch_lf<POT_GENERAL, true>(P, A, cfg) : launch_lf<POT_GENERAL, false>(P, A, cfg);
     case POT_ROTATED:
         return store_all ? launch_lf<POT_ROTATED, true>(P, A, cfg) : launch_lf<POT_ROTATED, false>(P, A, cfg);
+    case POT_LM10:
+        return store_all ? launch_lf<POT_LM10, true>(P, A, cfg) : launch_lf<POT_LM10, false>(P, A, cfg);
     case POT_MW_V2_T:
         return store_all ? launch_lf<POT_MW_V2_T, true>(P, A, cfg) : launch_lf<POT_MW_V2_T, false>(P, A, cfg);
     case POT_GENERIC_T:

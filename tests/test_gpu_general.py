@@ -58,16 +58,17 @@ def test_menu_potentials_pointwise_and_integrated(ctx, oracle, name):
     _local_step_check(ctx, oracle, pop, name, tol_v=1e-6 if name == "leesuto" else 1e-9)
 
 
-def test_rotated_kind_returns_the_general_kernels_bits(ctx, monkeypatch):
-    """LM10 (static, diagonal components, one rotated frame) runs in the lighter POT_ROTATED kernels; they must return
-    what the POT_GENERAL kernels return for the same potential, bit for bit, in every integrator and pointwise."""
+def test_rotated_and_lm10_kinds_return_the_general_kernels_bits(ctx, monkeypatch):
+    """LM10 (static, diagonal components, one rotated frame) runs in kernels compiled for its component list (POT_LM10);
+    other such composites in the lighter POT_ROTATED kernels.  Both must return what the POT_GENERAL kernels return for
+    the same potential, bit for bit, in every integrator and pointwise."""
     pot = _menu()["lm10"]
     pop = _population(300, 77, pot)
     q = np.random.default_rng(5).normal(0, 9, (3, 512))
     out = {}
-    for general in (False, True):
-        if general:
-            monkeypatch.setenv("CW_NO_ROTATED_KIND", "1")     # read when the potential is set
+    for kind, env in (("lm10", None), ("rotated", "CW_NO_LM10_KIND"), ("general", "CW_NO_ROTATED_KIND")):
+        if env:
+            monkeypatch.setenv(env, "1")     # read when the potential is set
         ctx.set_potential(pot)
         res = [ctx.gradient(q), ctx.potential_value(q)]
         for integ in (_lib.LEAPFROG, _lib.DOP853, _lib.DOP853_DENSE):
@@ -75,10 +76,12 @@ def test_rotated_kind_returns_the_general_kernels_bits(ctx, monkeypatch):
             res += [r["w_final"], r["status"], r["stats"]]
         r = ctx.integrate_batch(pop.batch, integrator=_lib.LEAPFROG, store_all=True)
         res += [r["traj_pos"][:, : r["traj_off"][-1]], r["traj_vel"][:, : r["traj_off"][-1]]]
-        out[general] = res
+        out[kind] = res
+    monkeypatch.delenv("CW_NO_LM10_KIND")
     monkeypatch.delenv("CW_NO_ROTATED_KIND")
-    for a, b in zip(out[False], out[True]):
-        assert np.array_equal(a, b)
+    for kind in ("lm10", "rotated"):
+        for k, (a, b) in enumerate(zip(out[kind], out["general"])):
+            assert np.array_equal(a, b), (kind, k)
 
 
 def test_rotation_is_a_change_of_frame(ctx):
