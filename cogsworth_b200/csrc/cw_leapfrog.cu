@@ -276,6 +276,11 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
         tmem_base = traj_tmem_alloc(&tmem_slot);
         tw.enable_tmem(tmem_base);
 #endif
+        if (TRAJ_TSTAGE) {
+            // tensor memory as the staging area of the upper half of the CTA's warps (cw_traj.cuh)
+            tmem_base = traj_tmem_alloc(&tmem_slot);
+            if ((int)threadIdx.x >= TRAJ_SMEM_LANES) tw.enable_tmem_stage(tmem_base);
+        }
     }
     int64_t col_base = 0;          // STORE: column of sample 0 of the current orbit
     Lane s;
@@ -315,11 +320,13 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
         // ---- phase A: lanes standing on a sync node (kick node / last node).  When STORE, the sample of
         // the node every active lane stands on has not been staged yet (it must carry the post-kick
         // velocity): stage it here, sync node or not.
+        bool put_a = false;         // TRAJ_TSTAGE: the sample of phase A is staged by the whole warp together, below
         if (active && (s.j == s.next || (STORE && !staged))) {
             const bool at_sync = (s.j == s.next);
             const bool kicked = at_sync ? apply_kicks(A, s) : false;
             if (STORE) {
-                tw.put(col_base + s.j, s.x, s.y, s.z, s.vx, s.vy, s.vz, s.j == s.L);
+                if (TRAJ_TSTAGE) put_a = true;
+                else tw.put(col_base + s.j, s.x, s.y, s.z, s.vx, s.vy, s.vz, s.j == s.L);
                 staged = true;
             }
             if (at_sync) {
@@ -337,6 +344,8 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 }
             }
         }
+        if (STORE && TRAJ_TSTAGE)   // (position and synchronised velocity of the node are untouched by the block above)
+            tw.put_any(put_a, (int)(W & (TRAJ_S - 1)), col_base + s.j, s.x, s.y, s.z, s.vx, s.vy, s.vz, s.j == s.L);
         if (STORE) {
             const bool flushed = tw.flush_warp(A);   // windows completed on this node (incl. the last of an orbit)
             if (dephase && flushed) {
@@ -352,6 +361,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
             }
         }
         // ---- phase B: idle lanes pull the next orbit from the queue
+        bool put_b = false;         // TRAJ_TSTAGE: the first sample of a new orbit, staged by the whole warp after the loop
         do {
         if (STORE) {
             // warp-uniform hand-out from the warp's private block of queue positions
@@ -420,6 +430,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 col_base = A.traj_off[o] - A.traj_base;
                 CW_ASSERT(col_base >= 0 && col_base + s.L < A.traj_total && A.traj_off[o + 1] - A.traj_off[o] > s.L);
                 if (s.L == 0) traj_store_direct(A, col_base, s.x, s.y, s.z, s.vx, s.vy, s.vz);
+                else if (TRAJ_TSTAGE) put_b = true;
                 else tw.put(col_base, s.x, s.y, s.z, s.vx, s.vy, s.vz, false);
                 staged = true;
             }
@@ -433,6 +444,8 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
             active = true;
         }
         } while (STORE && __any_sync(FULL, !active && !pending && !exhausted));   // rejected orbits: hand out again
+        if (STORE && TRAJ_TSTAGE)   // (an orbit starts when the warp clock stands on its first column's phase)
+            tw.put_any(put_b, (int)(W & (TRAJ_S - 1)), col_base, s.x, s.y, s.z, s.vx, s.vy, s.vz, false);
         if (STORE) tw.flush_warp(A);   // a first sample can complete a window (column = 7 mod 8)
         if (!__any_sync(FULL, active || (STORE && pending))) break;
 
@@ -471,7 +484,8 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 s.vhx = fma(s.Fxy, ndt, s.vhx);
                 s.vhy = fma(s.Fy, ndt, s.vhy);
                 s.vhz = fma(s.Fz, ndt, s.vhz);
-                if (STORE && active) tw.stage(col_base + s.j + q, s.x, s.y, s.z, s.vx, s.vy, s.vz);
+                if (STORE && TRAJ_TSTAGE) tw.stage_any(active, (int)((W + (unsigned)q) & (TRAJ_S - 1)), col_base + s.j + q, s.x, s.y, s.z, s.vx, s.vy, s.vz);
+                else if (STORE && active) tw.stage(col_base + s.j + q, s.x, s.y, s.z, s.vx, s.vy, s.vz);
             }
         } else if (!STORE) {
 #pragma unroll 4
@@ -507,7 +521,8 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 s.vhx = fma(a, s.x, s.vhx);
                 s.vhy = fma(ay, s.y, s.vhy);
                 s.vhz = fma(b, s.z, s.vhz);
-                if (active) tw.stage(col_base + s.j + q, s.x, s.y, s.z, s.vx, s.vy, s.vz);
+                if (TRAJ_TSTAGE) tw.stage_any(active, (int)((W + (unsigned)q) & (TRAJ_S - 1)), col_base + s.j + q, s.x, s.y, s.z, s.vx, s.vy, s.vz);
+                else if (active) tw.stage(col_base + s.j + q, s.x, s.y, s.z, s.vx, s.vy, s.vz);
             }
         }
         if (GEN) {
@@ -550,6 +565,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
 #if CW_TRAJ_TMEM
     if (STORE) traj_tmem_free(tmem_base);
 #endif
+    if (STORE && TRAJ_TSTAGE) traj_tmem_free(tmem_base);
     if (A.stats) {
         // orbit-steps actually integrated (the bench's unit of work), one atomic per warp
         for (int off = 16; off > 0; off >>= 1) steps_done += __shfl_down_sync(FULL, steps_done, off);
@@ -566,7 +582,7 @@ static cudaError_t launch_lf(const PotParams &P, const IntegArgs &A, const Launc
     // orbits spread evenly over the 148 SMs instead of filling a few of them (results do not depend on it).
     if (!STORE)
         while (block > 64 && (A.n + block - 1) / block < 2 * (int64_t)cfg.sm_count) block >>= 1;
-    const size_t dyn = STORE ? (size_t)block * TrajWriter::LANE_BYTES : 0;
+    const size_t dyn = STORE ? (size_t)TRAJ_SMEM_LANES * TrajWriter::LANE_BYTES : 0;
     cudaError_t err = cudaSuccess;
     if (STORE) {
         err = cudaFuncSetAttribute(leapfrog_kernel<KIND, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);

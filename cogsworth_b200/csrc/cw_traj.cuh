@@ -56,7 +56,17 @@ constexpr int TRAJ_HDR_SHIFT = 5;                            // header = first c
 // 32 samples = 128-byte runs that leave in pairs, 256 contiguous bytes per stream.  The pure store pattern reaches 4.8
 // TB/s with 128-byte runs and 6.5 TB/s with 256-byte ones (cw_measure_scatter_write), and 8 warps per SM still sustain
 // 1.33e11 orbit-steps/s of the leapfrog arithmetic (tools/gpu_occ_probe.py) = 6.4 TB/s of samples.
-constexpr int TRAJ_STORE_BLOCK = (TRAJ_S == 8) ? 512 : 256;
+// CW_TRAJ_TSTAGE (16-sample windows only): 512 lanes per SM.  Shared memory holds the windows of 256 lanes (196 KB); the
+// other 256 lanes stage theirs in TENSOR MEMORY, written straight from registers (tcgen05.st, two columns per value)
+// and read back at the flush in the 16x256b shape, which hands four adjacent threads four consecutive samples of one
+// orbit: every store instruction writes eight full 32-byte sectors.  16 warps per SM instead of 8: the arithmetic runs
+// at the rate of the final-state kernel and a warp that is flushing leaves three others on its scheduler computing.
+#ifndef CW_TRAJ_TSTAGE
+#define CW_TRAJ_TSTAGE 1
+#endif
+constexpr bool TRAJ_TSTAGE = (CW_TRAJ_TSTAGE != 0) && (TRAJ_S == 16);
+constexpr int TRAJ_SMEM_LANES = (TRAJ_S == 8) ? 512 : 256;   // lanes whose windows live in shared memory
+constexpr int TRAJ_STORE_BLOCK = TRAJ_TSTAGE ? 512 : TRAJ_SMEM_LANES;
 
 // ---- tensor memory as a second staging level ---------------------------------------------------------
 // Shared memory caps the staging windows at 8 samples = 64-byte runs, and lock-step 64-byte appends to
@@ -81,6 +91,25 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t *v)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v)
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+                 "%14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+// one FP64 value = two 32-bit columns of the calling thread's own TMEM lane
+__device__ __forceinline__ void tmem_st_f64(uint32_t taddr, double d)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};"
+                 :: "r"(taddr), "r"((uint32_t)__double2loint(d)), "r"((uint32_t)__double2hiint(d)) : "memory");
+}
+
+// 16 TMEM lanes x 32 columns in the 16x256b shape: thread t receives, for k = 0..3, columns 8k + 2 (t % 4) + {0, 1} of
+// lane t / 4 in v[4k], v[4k+1] and of lane t / 4 + 8 in v[4k+2], v[4k+3]
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t *v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
                  "%14, %15}, [%16];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
@@ -138,6 +167,7 @@ struct TrajWriterT {
     int64_t park_col0;        // first column of this lane's parked window
     uint32_t taddr;           // this warp's TMEM block (lane quadrant << 16 | first column)
     bool tmem_on;             // TMEM parking enabled
+    bool tm;                  // warp-uniform: this warp stages its windows in tensor memory (TRAJ_TSTAGE)
     // WIDE: the sample of an even column waits here for its odd neighbour (one 16-byte store for both)
     double hx, hy, hz, hvx, hvy, hvz;
     bool held;
@@ -147,7 +177,8 @@ struct TrajWriterT {
     __device__ __forceinline__ void init(unsigned char *smem, const IntegArgs &A)
     {
         const int lane = threadIdx.x & 31;
-        warp_base = smem + (size_t)(threadIdx.x - lane) * LANE_BYTES;
+        // (TRAJ_TSTAGE: the warps beyond TRAJ_SMEM_LANES have no rows here and never touch these two)
+        warp_base = smem + (size_t)((threadIdx.x - lane) % TRAJ_SMEM_LANES) * LANE_BYTES;
         buf = reinterpret_cast<double *>(warp_base + (size_t)lane * LANE_BYTES);
         // flush role: lanes S q .. S q + S-1 move the run of source lane RPI g + q (slot = lane % S), one
         // row per instruction -- every store instruction writes RPI full runs
@@ -166,6 +197,96 @@ struct TrajWriterT {
         park_col0 = 0;
         taddr = 0;
         tmem_on = false;
+        tm = false;
+    }
+
+    // TRAJ_TSTAGE: warps TRAJ_SMEM_LANES / 32 .. of the CTA stage in tensor memory.  Warp w addresses TMEM lanes
+    // 32 (w % 4) .. +31 and owns 192 columns there (6 rows x 16 samples x 2).
+    __device__ __forceinline__ void enable_tmem_stage(uint32_t tmem_base)
+    {
+        const int warp = threadIdx.x >> 5;
+        const int k = (warp - TRAJ_SMEM_LANES / 32) >> 2;
+        CW_ASSERT(k >= 0 && (k + 1) * TMEM_COLS_PER_WARP <= TRAJ_TMEM_COLS_PER_CTA);
+        taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(k * TMEM_COLS_PER_WARP);
+        tm = true;
+    }
+
+    // The warp-collective forms (TRAJ_TSTAGE): EVERY lane of the warp calls them together, `live` tells whether this
+    // lane has a sample; `uslot` is the warp clock's column phase (the same for every lane; live lanes' own column
+    // agrees with it).  Lanes without a sample write into their own, idle, TMEM rows.
+    __device__ __forceinline__ void stage_any(bool live, int uslot, int64_t col, double x, double y, double z, double vx,
+                                              double vy, double vz)
+    {
+        if (!tm) {
+            if (live) stage(col, x, y, z, vx, vy, vz);
+            return;
+        }
+        if (live) {
+            if (n == 0) col0 = col;
+            CW_ASSERT(col >= 0 && col < row_stride && n < S && col - col0 == n && (int)(col & (S - 1)) == uslot);
+            n++;
+        }
+        const uint32_t a = taddr + 2u * (uint32_t)uslot;
+        tmem_st_f64(a + 0 * 2 * S, x);
+        tmem_st_f64(a + 1 * 2 * S, y);
+        tmem_st_f64(a + 2 * 2 * S, z);
+        tmem_st_f64(a + 3 * 2 * S, vx);
+        tmem_st_f64(a + 4 * 2 * S, vy);
+        tmem_st_f64(a + 5 * 2 * S, vz);
+    }
+
+    __device__ __forceinline__ void put_any(bool live, int uslot, int64_t col, double x, double y, double z, double vx,
+                                            double vy, double vz, bool last)
+    {
+        if (!tm) {
+            if (live) put(col, x, y, z, vx, vy, vz, last);
+            return;
+        }
+        stage_any(live, uslot, col, x, y, z, vx, vy, vz);
+        if (live && ((col & (S - 1)) == S - 1 || last)) {
+            want = true;
+            want_last = last;
+        }
+    }
+
+    // flush of a TMEM-staging warp: headers travel by shuffle, data through tcgen05.ld in the 16x256b shape
+    __device__ __forceinline__ bool flush_warp_tm()
+    {
+        const unsigned FULL = 0xffffffffu;
+        const unsigned m = __ballot_sync(FULL, want);
+        if (m == 0) return false;
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        const int lane = threadIdx.x & 31;
+        const long long hdr = want ? ((long long)(col0 << TRAJ_HDR_SHIFT) | (long long)n) : 0ll;
+        const int sub = lane & 3;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int La = half * 16 + (lane >> 2), Lb = La + 8;        // the two source lanes this thread serves
+            const long long ha = __shfl_sync(FULL, hdr, La), hb = __shfl_sync(FULL, hdr, Lb);
+            const int cnta = (int)(ha & ((1 << TRAJ_HDR_SHIFT) - 1)), cntb = (int)(hb & ((1 << TRAJ_HDR_SHIFT) - 1));
+            const long long c0a = ha >> TRAJ_HDR_SHIFT, c0b = hb >> TRAJ_HDR_SHIFT;
+            const int s0a = (int)(c0a & (S - 1)), s0b = (int)(c0b & (S - 1));
+            CW_ASSERT(cnta == 0 || (c0a >= 0 && s0a + cnta <= S && c0a + cnta <= row_stride));
+            CW_ASSERT(cntb == 0 || (c0b >= 0 && s0b + cntb <= S && c0b + cntb <= row_stride));
+#pragma unroll
+            for (int r = 0; r < TRAJ_ROWS; r++) {
+                uint32_t v[16];
+                tmem_ld_16x256b_x4(taddr + ((uint32_t)(half * 16) << 16) + (uint32_t)(2 * S * r), v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                double *rowp = (r < 3) ? pos0 + r * row_stride : vel0 + (r - 3) * row_stride;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int sl = 4 * k + sub;
+                    if (sl >= s0a && sl < s0a + cnta) rowp[(c0a - s0a) + sl] = __hiloint2double((int)v[4 * k + 1], (int)v[4 * k]);
+                    if (sl >= s0b && sl < s0b + cntb) rowp[(c0b - s0b) + sl] = __hiloint2double((int)v[4 * k + 3], (int)v[4 * k + 2]);
+                }
+            }
+        }
+        if (want) {
+            want = false;
+            n = 0;
+        }
+        return true;
     }
 
     // tmem_base: value returned by traj_tmem_alloc.  Warp w owns TMEM lanes 32 (w % 4) .. +31 (the only ones
@@ -375,6 +496,7 @@ struct TrajWriterT {
     // completed (warp-uniform).
     __device__ __forceinline__ bool flush_warp(const IntegArgs &A)
     {
+        if (TRAJ_TSTAGE && S == 16 && tm) return flush_warp_tm();
         const unsigned FULL = 0xffffffffu;
         const unsigned m = __ballot_sync(FULL, want);
         if (m == 0) return false;
