@@ -219,9 +219,13 @@ constexpr int LOG_TABLE_N = (1 << LOG_TABLE_BITS) + 1;
 
 struct LogTab {
     uint32_t s;      // shared-window byte address of the table, 0xffffffff = no table (use log_fast)
+    // Seed donors (see rsqrt_seed) for the two reciprocal square roots of the Milky Way gradient whose arguments stay
+    // alive: two values of the CALLER that die at this gradient evaluation (the leapfrog passes the scaled force factors
+    // of the previous step).  Only their low words are read, and no result depends on them.
+    double d0, d1;
     __device__ __forceinline__ bool on() const { return s != 0xffffffffu; }
 };
-__device__ __forceinline__ LogTab no_log_table() { LogTab t; t.s = 0xffffffffu; return t; }
+__device__ __forceinline__ LogTab no_log_table() { LogTab t; t.s = 0xffffffffu; t.d0 = t.d1 = 0.0; return t; }
 
 __device__ __forceinline__ LogTab log_table_init(double2 *tab)
 {
@@ -232,6 +236,7 @@ __device__ __forceinline__ LogTab log_table_init(double2 *tab)
     __syncthreads();
     LogTab t;
     t.s = (uint32_t)__cvta_generic_to_shared(tab);
+    t.d0 = t.d1 = 0.0;
     return t;
 }
 
@@ -271,7 +276,7 @@ __device__ __forceinline__ void force_mw(const PotParams &P, LogTab ltab,
     const double r2 = R2 + z2;
 
     // ---- the three spherical components over ONE reciprocal square root and ONE reciprocal
-    const double ir = rsqrt_fast(r2, R2);                  // seed donors: values whose last use is here
+    const double ir = rsqrt_fast(r2, ltab.d0);             // seed donors: values whose last use is here
     const double r = r2 * ir;
     // two Hernquist spheres over one reciprocal: GM0/rc0^2 + GM1/rc1^2 = (GM0 rc1^2 + GM1 rc0^2) / (rc0 rc1)^2
     const double rc0 = r + P.h_c[0], rc1 = r + P.h_c[1];
@@ -297,7 +302,7 @@ __device__ __forceinline__ void force_mw(const PotParams &P, LogTab ltab,
         // in the two accumulations (GM_i and GM_i a_i are constant-bank operands of their FMAs), the first of which
         // starts from the spherical part: 8 FP64 instructions per term + 6 for the sums (round 1: 9 + 6).
         const double q = z2 + P.mn_b2[0];
-        const double isz = rsqrt_fast(q);
+        const double isz = rsqrt_fast(q, ltab.d1);
         const double sz = q * isz;
         double t[NMN];
 #pragma unroll

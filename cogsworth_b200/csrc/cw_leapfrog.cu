@@ -315,6 +315,16 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
     const unsigned gw = STORE ? (blockIdx.x * (LF_BLOCK_STORE / 32) + (threadIdx.x >> 5)) : 0u;
     long long t_first = STORE ? clock64() : 0;
     int dephase = STORE ? 2 : 0;       // 2: first flush not seen yet, 1: second flush pending, 0: done
+    // Every force evaluation of the kernel.  The factors of the PREVIOUS node die here, so their register pairs serve as
+    // the seed donors of the gradient (LogTab::d0, d1: two moves fewer per step).  Only low words are read and they are
+    // a function of the orbit's own history -- an orbit starts with both factors zero -- so results stay independent
+    // of lane, batch and kernel (final-state and trajectory runs evaluate the same sequence).
+    auto eval_force = [&](double t) {
+        LogTab lt = ltab;
+        lt.d0 = s.Fxy;
+        lt.d1 = s.Fz;
+        force3t_seg<KIND>(P, lt, s.seg, t, s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+    };
 
     for (;;) {
         // ---- phase A: lanes standing on a sync node (kick node / last node).  When STORE, the sample of
@@ -435,7 +445,8 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 staged = true;
             }
             if (s.L == 0) { write_final(A, s); continue; }
-            force3t_seg<KIND>(P, ltab, s.seg, s.tcur * s.smyr, s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+            s.Fxy = 0.0; s.Fz = 0.0;        // (seed donors of the first gradient: not the previous orbit's factors)
+            eval_force(s.tcur * s.smyr);
             const double nhdt = -0.5 * s.dt;
             s.vhx = lf_kick<KIND>(s.Fxy, nhdt, s.x, s.vx);
             s.vhy = lf_kick<KIND>(s.Fy, nhdt, s.y, s.vy);
@@ -475,7 +486,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 s.x = fma(s.vhx, dt, s.x);
                 s.y = fma(s.vhy, dt, s.y);
                 s.z = fma(s.vhz, dt, s.z);
-                force3t_seg<KIND>(P, ltab, s.seg, tnode(s.j + q), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+                eval_force(tnode(s.j + q));
                 if (STORE) {
                     s.vx = fma(s.Fxy, nhdt, s.vhx);
                     s.vy = fma(s.Fy, nhdt, s.vhy);
@@ -493,7 +504,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 s.x = fma(s.vhx, dt, s.x);
                 s.y = fma(s.vhy, dt, s.y);
                 s.z = fma(s.vhz, dt, s.z);
-                force3t_seg<KIND>(P, ltab, s.seg, tnode(s.j + q), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+                eval_force(tnode(s.j + q));
                 const double a = s.Fxy * ndt, b = s.Fz * ndt;
                 const double ay = TRI ? s.Fy * ndt : a;
                 s.vhx = fma(a, s.x, s.vhx);
@@ -510,7 +521,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
                 s.x = fma(s.vhx, dt, s.x);
                 s.y = fma(s.vhy, dt, s.y);
                 s.z = fma(s.vhz, dt, s.z);
-                force3t_seg<KIND>(P, ltab, s.seg, tnode(s.j + q), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+                eval_force(tnode(s.j + q));
                 const double ah = s.Fxy * nhdt, bh = s.Fz * nhdt;
                 const double ahy = TRI ? s.Fy * nhdt : ah;
                 s.vx = fma(ah, s.x, s.vhx);
@@ -529,7 +540,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
             s.x = fma(s.vhx, dt, s.x);
             s.y = fma(s.vhy, dt, s.y);
             s.z = fma(s.vhz, dt, s.z);
-            force3t_seg<KIND>(P, ltab, s.seg, tnode(s.j + m), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+            eval_force(tnode(s.j + m));
             s.vx = fma(s.Fxy, nhdt, s.vhx);
             s.vy = fma(s.Fy, nhdt, s.vhy);
             s.vz = fma(s.Fz, nhdt, s.vhz);
@@ -540,7 +551,7 @@ __global__ void __launch_bounds__(STORE ? LF_BLOCK_STORE : LF_BLOCK) __maxnreg__
             s.x = fma(s.vhx, dt, s.x);
             s.y = fma(s.vhy, dt, s.y);
             s.z = fma(s.vhz, dt, s.z);
-            force3t_seg<KIND>(P, ltab, s.seg, tnode(s.j + m), s.x, s.y, s.z, s.Fxy, s.Fy, s.Fz);
+            eval_force(tnode(s.j + m));
             const double ah = s.Fxy * nhdt, bh = s.Fz * nhdt;
             const double ahy = TRI ? s.Fy * nhdt : ah;
             s.vx = fma(ah, s.x, s.vhx);
