@@ -19,6 +19,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <nvtx3/nvToolsExt.h>      // header-only: ranges show up in Nsight Systems / Compute timelines, cost nothing otherwise
 
 #include "cw_host.h"
 #include "cw_kernels.cuh"
@@ -28,6 +29,14 @@ using namespace cw;
 namespace {
 
 // restores the caller's current device on every exit path (the CW_CK macro returns early on CUDA errors)
+// NVTX range for the host-side timeline (tracing): cw_integrate / per-slot thread / per-chunk enqueue / drain
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+
 struct DeviceGuard {
     int prev = 0;
     DeviceGuard() { cudaGetDevice(&prev); }
@@ -1101,6 +1110,7 @@ static int make_chunks(HostCall &H, std::vector<Chunk> &chunks)
 static int drain_chunk(Slot &s, Chunk &c)
 {
     if (c.drained) return CW_OK;
+    NvtxRange nv("cw: drain chunk (wait D2H, staged outputs -> caller arrays)");
     CW_SCK(s, cudaEventSynchronize(c.d2h_done));
     HostPool::get().run(c.drain);
     c.drain.clear();
@@ -1111,6 +1121,7 @@ static int drain_chunk(Slot &s, Chunk &c)
 // Everything one chunk needs, enqueued on its lane's stream: uploads (direct or staged), unpack, kernels, downloads.
 static int process_chunk(HostCall &H, Slot &s, Chunk &c)
 {
+    NvtxRange nv("cw: enqueue chunk (stage inputs, H2D, pre-pass, sort, integrator, D2H)");
     cw_ctx *ctx = H.ctx;
     const cw_batch *B = H.B;
     const cw_result &R = H.R;
@@ -1325,6 +1336,7 @@ static int run_slot_host(HostCall &H, int d, std::vector<Chunk *> &mine)
     s.error.clear();
     s.launches = 0;
     if (mine.empty()) return CW_OK;
+    NvtxRange nv("cw: device slot (host thread)");
     const double tr_start = H.trace ? H.ms_since_call() : 0.0;
     CW_SCK(s, cudaSetDevice(s.dev));
     // ---- size and reserve the lane arenas and staging buffers once, for all chunks of the call
@@ -1396,6 +1408,7 @@ static int run_slot_host(HostCall &H, int d, std::vector<Chunk *> &mine)
 static int integrate_host(cw_ctx *ctx, const cw_opts *o, const cw_batch *B, const cw_result *R, bool integrate,
                           int32_t *n_nodes_out, int32_t *ev_step_out)
 {
+    NvtxRange nv(integrate ? "cw_integrate (CW_MEM_HOST)" : "cw_count_nodes (CW_MEM_HOST)");
     HostCall H;
     H.ctx = ctx; H.o = o; H.B = B;
     H.trace = getenv("CW_DEBUG") != nullptr;
