@@ -69,6 +69,9 @@ WORKLOADS = {
     "config4_evolving": dict(cfg_id=4, n_orbits=2_000_000, horizon_gyr=1.0, integrator="leapfrog", store_all=False,
                              f_sn=1.0, potential="evolving_mw",
                              desc="2e6 orbits, evolving Milky Way (TimeInterpolatedPotential masses, 5 knots), leapfrog 1 Gyr dt=1 Myr, kicks, final state"),
+    "config5_evolving": dict(cfg_id=5, n_orbits=200_000, horizon_gyr=1.0, integrator="dop853", store_all=False,
+                             f_sn=1.0, potential="evolving_mw",
+                             desc="2e5 orbits, evolving Milky Way, DOPRI853 1e-10 (the tutorial's own integrator), 1 Gyr, kicks, final state"),
     "config4_lm10": dict(cfg_id=4, n_orbits=1_000_000, horizon_gyr=1.0, integrator="leapfrog", store_all=False,
                          f_sn=1.0, potential="lm10",
                          desc="1e6 orbits, LM10Potential (MN disk + Hernquist bulge + rotated triaxial logarithmic halo), leapfrog 1 Gyr dt=1 Myr, kicks, final state"),
@@ -443,7 +446,8 @@ def measure(W, steps, warmup, barrier, max_over_ranks, sum_over_ranks, peak_fp64
         else:
             # 12 gradients + 1000 flop of stage algebra per accepted step, per launch
             flops = FLOP_PER_STEP["dop853_v2"] * float(stats_run[0])
-            kname = "dop853_kernel<MW_V2%s>" % (",DENSE" if W.integ == _lib.DOP853_DENSE else "")
+            kname = "dop853_kernel<MW_V2%s%s>" % ("_T" if wl.get("potential") == "evolving_mw" else "",
+                                                  ",DENSE" if W.integ == _lib.DOP853_DENSE else "")
             per = FLOP_PER_STEP["dop853_v2"]
         ach = flops / (k_ms * 1e-3) / 1e12
         roof = {"bound": "fp64", "achieved": ach, "peak": peak_fp64, "unit": "TFLOP/s", "frac": ach / peak_fp64,

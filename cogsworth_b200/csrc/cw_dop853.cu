@@ -219,11 +219,23 @@ __device__ __forceinline__ int64_t dp_queue_pop(unsigned long long *queue)
     return (int64_t)(base + g.thread_rank());
 }
 
+// f(x, y) = (v, -grad Phi(x, q)).  The separable kinds (Phi = f(t) Phi_0) keep the knot interval the orbit's clock is
+// in as a cubic in registers (AmpSeg, as the leapfrog kernels do): the thirteen gradient evaluations of a step attempt
+// then cost two comparisons and three FMAs for f(t) instead of a table look-up each.
 template <int KIND>
-__device__ __forceinline__ void fcn(const PotParams &P, LogTab ltab, double t, const double *y, double *f)
+__device__ __forceinline__ void fcn(const PotParams &P, LogTab ltab, AmpSeg &seg, double t, const double *y, double *f)
 {
     double gx, gy, gz;
-    gradient<KIND>(P, ltab, t, y[0], y[1], y[2], gx, gy, gz);
+    if (KindTraits<KIND>::TS) {
+        double Fx, Fy, Fz;
+        force3<KindTraits<KIND>::BASE>(P, ltab, y[0], y[1], y[2], Fx, Fy, Fz);
+        const double a = amp_seg_eval(P, seg, t);
+        gx = (Fx * a) * y[0];
+        gy = (Fy * a) * y[1];
+        gz = (Fz * a) * y[2];
+    } else {
+        gradient<KIND>(P, ltab, t, y[0], y[1], y[2], gx, gy, gz);
+    }
     f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
     f[3] = -gx; f[4] = -gy; f[5] = -gz;
 }
@@ -297,6 +309,8 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
     if (STORE && !PILOT) tw.init(traj_smem, A);
     int64_t col_base = 0;
     DpLane s;
+    AmpSeg seg;                        // separable kinds only (dead code otherwise)
+    amp_seg_reset(seg);
 #pragma unroll
     for (int c = 0; c < 6; c++) { s.y[c] = (c == 0) ? 8.0 : 0.0; s.k1[c] = 0.0; }
     s.x = 0.0; s.xend = 1.0; s.h = 1.0; s.hmax = 1.0; s.facold = 1e-4; s.hlamb = 0.0; s.dt0 = 1.0;
@@ -404,7 +418,7 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
                 else dp_write_final(A, s, CW_ORBIT_OK);
                 continue;
             }
-            fcn<KIND>(P, ltab, s.tgrid * s.smyr, s.y, s.k1);
+            fcn<KIND>(P, ltab, seg, s.tgrid * s.smyr, s.y, s.k1);
             n_fcn++;
             dp_begin_interval<DENSE>(A, s);
             active = true;
@@ -433,28 +447,28 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
 
 #define CW_STAGE(EXPR) _Pragma("unroll") for (int i = 0; i < 6; i++) yy1[i] = fma(h, (EXPR), y[i]);
             CW_STAGE(k_A0201 * k1[i])
-            fcn<KIND>(P, ltab, fma(CW_C02, h, s.x), yy1, k2);
+            fcn<KIND>(P, ltab, seg, fma(CW_C02, h, s.x), yy1, k2);
             CW_STAGE(fma(k_A0302, k2[i], k_A0301 * k1[i]))
-            fcn<KIND>(P, ltab, fma(CW_C03, h, s.x), yy1, k3);
+            fcn<KIND>(P, ltab, seg, fma(CW_C03, h, s.x), yy1, k3);
             CW_STAGE(fma(k_A0403, k3[i], k_A0401 * k1[i]))
-            fcn<KIND>(P, ltab, fma(CW_C04, h, s.x), yy1, k4);
+            fcn<KIND>(P, ltab, seg, fma(CW_C04, h, s.x), yy1, k4);
             CW_STAGE(fma(k_A0504, k4[i], fma(k_A0503, k3[i], k_A0501 * k1[i])))
-            fcn<KIND>(P, ltab, fma(CW_C05, h, s.x), yy1, k5);
+            fcn<KIND>(P, ltab, seg, fma(CW_C05, h, s.x), yy1, k5);
             CW_STAGE(fma(k_A0605, k5[i], fma(k_A0604, k4[i], k_A0601 * k1[i])))
-            fcn<KIND>(P, ltab, fma(CW_C06, h, s.x), yy1, k6);
+            fcn<KIND>(P, ltab, seg, fma(CW_C06, h, s.x), yy1, k6);
             CW_STAGE(fma(k_A0706, k6[i], fma(k_A0705, k5[i], fma(k_A0704, k4[i], k_A0701 * k1[i]))))
-            fcn<KIND>(P, ltab, fma(CW_C07, h, s.x), yy1, k7);
+            fcn<KIND>(P, ltab, seg, fma(CW_C07, h, s.x), yy1, k7);
             CW_STAGE(fma(k_A0807, k7[i], fma(k_A0806, k6[i], fma(k_A0805, k5[i], fma(k_A0804, k4[i], k_A0801 * k1[i])))))
-            fcn<KIND>(P, ltab, fma(CW_C08, h, s.x), yy1, k8);
+            fcn<KIND>(P, ltab, seg, fma(CW_C08, h, s.x), yy1, k8);
             CW_STAGE(fma(k_A0908, k8[i], fma(k_A0907, k7[i], fma(k_A0906, k6[i], fma(k_A0905, k5[i], fma(k_A0904, k4[i], k_A0901 * k1[i]))))))
-            fcn<KIND>(P, ltab, fma(CW_C09, h, s.x), yy1, k9);
+            fcn<KIND>(P, ltab, seg, fma(CW_C09, h, s.x), yy1, k9);
             CW_STAGE(fma(k_A1009, k9[i], fma(k_A1008, k8[i], fma(k_A1007, k7[i], fma(k_A1006, k6[i], fma(k_A1005, k5[i], fma(k_A1004, k4[i], k_A1001 * k1[i])))))))
-            fcn<KIND>(P, ltab, fma(CW_C10, h, s.x), yy1, k10);
+            fcn<KIND>(P, ltab, seg, fma(CW_C10, h, s.x), yy1, k10);
             CW_STAGE(fma(k_A1110, k10[i], fma(k_A1109, k9[i], fma(k_A1108, k8[i], fma(k_A1107, k7[i], fma(k_A1106, k6[i], fma(k_A1105, k5[i], fma(k_A1104, k4[i], k_A1101 * k1[i]))))))))
-            fcn<KIND>(P, ltab, fma(CW_C11, h, s.x), yy1, k2);
+            fcn<KIND>(P, ltab, seg, fma(CW_C11, h, s.x), yy1, k2);
             const double xph = __dadd_rn(s.x, h);
             CW_STAGE(fma(k_A1211, k2[i], fma(k_A1210, k10[i], fma(k_A1209, k9[i], fma(k_A1208, k8[i], fma(k_A1207, k7[i], fma(k_A1206, k6[i], fma(k_A1205, k5[i], fma(k_A1204, k4[i], k_A1201 * k1[i])))))))))
-            fcn<KIND>(P, ltab, xph, yy1, k3);
+            fcn<KIND>(P, ltab, seg, xph, yy1, k3);
 #undef CW_STAGE
             n_fcn += 11;
 
@@ -499,7 +513,7 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
                 s.facold = fmax(err, 1.0e-4);
                 s.naccpt++;
                 n_acc++;
-                fcn<KIND>(P, ltab, xph, k5, k4);  // first stage of the next step
+                fcn<KIND>(P, ltab, seg, xph, k5, k4);  // first stage of the next step
                 n_fcn++;
                 // stiffness detection (nstiff = 1: every accepted step)
                 double stnum = 0.0, stden = 0.0;
@@ -545,15 +559,15 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
 #pragma unroll
                         for (int i = 0; i < 6; i++)
                             yd[i] = fma(h, fma(k_A1413, k4[i], fma(k_A1412, k3[i], fma(k_A1411, k2[i], fma(k_A1410, k10[i], fma(k_A1409, k9[i], fma(k_A1408, k8[i], fma(k_A1407, k7[i], k_A1401 * k1[i]))))))), y[i]);
-                        fcn<KIND>(P, ltab, fma(0.1, h, s.x), yd, ka);
+                        fcn<KIND>(P, ltab, seg, fma(0.1, h, s.x), yd, ka);
 #pragma unroll
                         for (int i = 0; i < 6; i++)
                             yd[i] = fma(h, fma(k_A1514, ka[i], fma(k_A1513, k4[i], fma(k_A1512, k3[i], fma(k_A1511, k2[i], fma(k_A1508, k8[i], fma(k_A1507, k7[i], fma(k_A1506, k6[i], k_A1501 * k1[i]))))))), y[i]);
-                        fcn<KIND>(P, ltab, fma(0.2, h, s.x), yd, kb);
+                        fcn<KIND>(P, ltab, seg, fma(0.2, h, s.x), yd, kb);
 #pragma unroll
                         for (int i = 0; i < 6; i++)
                             yd[i] = fma(h, fma(k_A1615, kb[i], fma(k_A1614, ka[i], fma(k_A1613, k4[i], fma(k_A1609, k9[i], fma(k_A1608, k8[i], fma(k_A1607, k7[i], fma(k_A1606, k6[i], k_A1601 * k1[i]))))))), y[i]);
-                        fcn<KIND>(P, ltab, fma(7.0 / 9.0, h, s.x), yd, kc);
+                        fcn<KIND>(P, ltab, seg, fma(7.0 / 9.0, h, s.x), yd, kc);
                         n_fcn += 3;
 #pragma unroll
                         for (int i = 0; i < 6; i++) {
