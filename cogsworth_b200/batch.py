@@ -292,20 +292,25 @@ def build_orbit_batch(pos_kpc, vel_kms, tau_gyr, max_ev_time_gyr, timestep_myr, 
 
     ev_time = ev_dv = None
     if Kn:
-        tphys = np.concatenate([pe.tphys, se.tphys]).astype(np.float64)
-        owner_src = np.concatenate([pe.owner, se.owner]).astype(np.int64)     # population index of each event
-        # (t1 + tphys * u.Myr) is formed in t1's unit (Gyr) and compared in seconds (kicks.py:134)
+        # (t1 + tphys * u.Myr) is formed in t1's unit (Gyr) and compared in seconds (kicks.py:134).  The primary and
+        # the secondary rows are written into their own slices of the outputs: no concatenated copies of the tables.
         ev_time = pinned_empty(Kn)
-        np.multiply(tphys, K.GYR_PER_MYR, out=ev_time)
-        np.add(ev_time, t1_gyr_src[owner_src], out=ev_time)
-        np.multiply(ev_time, K.SEC_PER_GYR, out=ev_time)
         ev_dv = pinned_empty((Kn, 3))
-        dv_all = np.concatenate([pe.dv.reshape(-1, 3), se.dv.reshape(-1, 3)]).astype(np.float64, copy=False)
-        ph_all = np.concatenate([pe.phase, se.phase]).astype(np.float64, copy=False)
-        in_all = np.concatenate([pe.inc, se.inc]).astype(np.float64, copy=False)
-        if not (threaded_rotation and Kn >= 4096 and rotate_kicks_threaded(dv_all, ph_all, in_all, K.KPC_MYR_PER_KMS, ev_dv)):
-            rotate_kicks(dv_all, ph_all, in_all, out=ev_dv)
-            np.multiply(ev_dv, K.KPC_MYR_PER_KMS, out=ev_dv)
+        a = 0
+        for tab in (pe, se):
+            k = len(tab)
+            if k == 0:
+                continue
+            et, ed = ev_time[a:a + k], ev_dv[a:a + k]
+            np.multiply(np.asarray(tab.tphys, dtype=np.float64), K.GYR_PER_MYR, out=et)
+            np.add(et, t1_gyr_src[np.asarray(tab.owner, dtype=np.int64)], out=et)     # population index of each event
+            np.multiply(et, K.SEC_PER_GYR, out=et)
+            dv = np.asarray(tab.dv, dtype=np.float64).reshape(-1, 3)
+            ph, inc = np.asarray(tab.phase, dtype=np.float64), np.asarray(tab.inc, dtype=np.float64)
+            if not (threaded_rotation and Kn >= 4096 and rotate_kicks_threaded(dv, ph, inc, K.KPC_MYR_PER_KMS, ed)):
+                rotate_kicks(dv, ph, inc, out=ed)
+                np.multiply(ed, K.KPC_MYR_PER_KMS, out=ed)
+            a += k
 
     # the compact form needs every disrupted system's own orbit on the events branch (its start time is then the
     # same float in seconds for the system and its secondary) and few enough distinct grids

@@ -204,8 +204,10 @@ HostPool::HostPool() : p_(new Impl())
     int avail = (int)std::thread::hardware_concurrency();
     cpu_set_t set;
     if (sched_getaffinity(0, sizeof set, &set) == 0) avail = CPU_COUNT(&set);
-    int n = avail / 2 - 1;
-    if (n > 8) n = 8;
+    // staging copies saturate the memory system with a few threads, the compute-bound loops (kick rotation: four libm
+    // calls per event) scale with every core: all but one of the cores this process may use, at most 15 workers
+    int n = avail - 1;
+    if (n > 15) n = 15;
     if (const char *e = getenv("CW_HOST_THREADS")) n = atoi(e) - 1;        // CW_HOST_THREADS counts the caller too
     if (n < 0) n = 0;
     p_->n_workers = n;

@@ -161,9 +161,95 @@ def _table(t, bin_nums):
     return EventTable(owner, t["tphys"], t["dv"], t["phase"], t["inc"])
 
 
-def identify_event_tables(p):
+class _Range:
+    """The rows of a population whose bin_num lies in one contiguous range: what the joins above read, sliced."""
+
+    def __init__(self, kick_info, bpp, initC, bin_nums, disrupted):
+        self.kick_info, self.bpp, self.initC, self.bin_nums, self.disrupted = kick_info, bpp, initC, bin_nums, disrupted
+
+
+#: populations at least this large are joined range by range on a thread pool (numpy releases the GIL in every pass)
+PARALLEL_MIN_BINARIES = 1_000_000
+
+
+def _tables_by_range(p, n_threads):
+    """identify_event_tables for a population in bin_num order whose tables are grouped by bin_num (what COSMIC
+    writes): the population is cut into contiguous bin_num ranges, every range is joined on its own by the functions
+    above, concurrently, and the tables are concatenated -- the same rows in the same order as the one-pass join.
+    Returns None when the orderings do not allow it."""
+    from concurrent.futures import ThreadPoolExecutor
+    bin_nums = np.asarray(p.bin_nums).astype(np.int64)
+    n = len(bin_nums)
+    kick, bpp = p.kick_info, p.bpp
+    initC = p.initC if hasattr(p, "initC") else p.initial_binaries
+    kb = np.asarray(kick["bin_num"].values)
+    bb = np.asarray(bpp["bin_num"].values)
+    ib = np.asarray(initC["bin_num"].values if "bin_num" in initC else initC.index.values)
+    disrupted = np.asarray(p.disrupted, dtype=bool)
+    cuts = [(n * k) // n_threads for k in range(n_threads + 1)]
+    edges = bin_nums[[min(c, n - 1) for c in cuts[1:-1]]]          # first bin_num of ranges 1 .. T-1
+    ka = [0] + list(np.searchsorted(kb, edges, "left")) + [len(kb)]
+    ba = [0] + list(np.searchsorted(bb, edges, "left")) + [len(bb)]
+    ia = [0] + list(np.searchsorted(ib, edges, "left")) + [len(ib)]
+
+    def sorted_slice(a, lo, hi, first, last):
+        v = a[lo:hi]
+        return len(v) == 0 or (bool(np.all(v[1:] >= v[:-1])) and v[0] >= first and (last is None or v[-1] < last))
+
+    def work(k):
+        ca, cb = cuts[k], cuts[k + 1]
+        if cb <= ca:
+            return EventTable.empty(), EventTable.empty()
+        first = bin_nums[ca]
+        last = bin_nums[cb] if cb < n else None
+        bn = bin_nums[ca:cb]
+        # the cut is only valid if every table really is ordered by bin_num (searchsorted above assumed it)
+        if not (bool(np.all(bn[1:] > bn[:-1])) and (last is None or bn[-1] < last) and
+                sorted_slice(kb, ka[k], ka[k + 1], first, last) and sorted_slice(bb, ba[k], ba[k + 1], first, last) and
+                sorted_slice(ib, ia[k], ia[k + 1], first, last)):
+            return None
+        r = _Range(kick.iloc[ka[k]:ka[k + 1]], bpp.iloc[ba[k]:ba[k + 1]], initC.iloc[ia[k]:ia[k + 1]], bn, disrupted[ca:cb])
+        prim, sec, _ = _primary_secondary(r)
+        tp, ts = _table(prim, bn), _table(sec, bn)
+        for t in (tp, ts):
+            if len(t):
+                t.owner += ca                                    # positions in the whole population
+        return tp, ts
+
+    with ThreadPoolExecutor(max_workers=n_threads) as ex:
+        parts = list(ex.map(work, range(n_threads)))
+    if any(part is None for part in parts):
+        return None
+    out = []
+    for j in (0, 1):
+        ts = [part[j] for part in parts if len(part[j])]
+        if not ts:
+            out.append(EventTable.empty())
+        elif len(ts) == 1:
+            out.append(ts[0])
+        else:
+            out.append(EventTable(np.concatenate([t.owner for t in ts]), np.concatenate([t.tphys for t in ts]),
+                                  np.concatenate([t.dv for t in ts]), np.concatenate([t.phase for t in ts]),
+                                  np.concatenate([t.inc for t in ts])))
+    return out[0], out[1]
+
+
+def identify_event_tables(p, n_threads=None):
     """Same content as :func:`identify_events` as flat :class:`EventTable` s (owners = positions in
-    ``p.bin_nums``), ready for :func:`cogsworth_b200.batch.build_orbit_batch`."""
+    ``p.bin_nums``), ready for :func:`cogsworth_b200.batch.build_orbit_batch`.  Large populations in bin_num order are
+    joined range by range on ``n_threads`` host threads (default: the cores this process may use, at most 16)."""
+    n = len(p.bin_nums)
+    if n_threads is None:
+        import os
+        try:
+            n_threads = min(len(os.sched_getaffinity(0)), 16)
+        except AttributeError:
+            n_threads = min(os.cpu_count() or 1, 16)
+    if n >= PARALLEL_MIN_BINARIES and n_threads > 1:
+        draw_sn_angles(p.initC if hasattr(p, "initC") else p.initial_binaries)       # once, before the ranges read them
+        res = _tables_by_range(p, n_threads)
+        if res is not None:
+            return res
     prim, sec, bin_nums = _primary_secondary(p)
     return _table(prim, bin_nums), _table(sec, bin_nums)
 

@@ -132,6 +132,30 @@ def test_vectorised_batch_is_bit_identical_to_the_per_binary_loop(tables):
     assert sent < 0.7 * plain
 
 
+def test_range_parallel_join_equals_the_one_pass_join(tables, monkeypatch):
+    """Large populations are joined range by range on host threads (events._tables_by_range): the same rows in the same
+    order as the one-pass join, whatever the number of ranges; tables that are not grouped by bin_num fall back."""
+    from cogsworth_b200 import events
+    _, P, _, _, _ = tables
+    one = events.identify_event_tables(P, n_threads=1)
+    monkeypatch.setattr(events, "PARALLEL_MIN_BINARIES", 100)
+    for T in (2, 3, 7, 16):
+        assert events._tables_by_range(P, T) is not None
+        par = events.identify_event_tables(P, n_threads=T)
+        for a, b in zip(one, par):
+            assert len(a) == len(b) > 3000
+            for f in ("owner", "tphys", "dv", "phase", "inc"):
+                assert np.array_equal(getattr(a, f), getattr(b, f)), (T, f)
+    # kick_info in another order: the range cut is refused and the sorting join takes over, same tables
+    Q = B200Population(P.initial_galaxy, P.bpp, P.kick_info.iloc[::-1], P.initial_binaries, galactic_potential=None,
+                       max_ev_time=12.0, timestep_size=1.0, store_entire_orbits=False, integrator="leapfrog")
+    Q.disrupted
+    assert events._tables_by_range(Q, 4) is None
+    for a, b in zip(one, events.identify_event_tables(Q, n_threads=4)):
+        for f in ("owner", "tphys", "dv", "phase", "inc"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), f
+
+
 @pytest.mark.gpu
 def test_population_stage_on_gpu_matches_oracle_on_literal_arrays(tables, ctx, oracle):
     from _cases import assert_parity_outside_the_sensitive_set, rel_diff, sensitive_orbits
