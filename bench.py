@@ -485,33 +485,38 @@ def population_e2e(size_label, n_binaries, horizon_gyr, cfg_id, ctx, reps=1):
                        timestep_size=1.0, store_entire_orbits=False, integrator="leapfrog")
     P._cw_context = ctx
     P.disrupted                                   # cached by the reference as well (pop.py:861-874)
-    best, items = None, None
-    for _ in range(reps + 1):                     # first pass warms the page-locked cache
+    best, first = None, None
+    for k in range(reps + 1):                     # the first pass also pins the context's staging ring (once per context)
         t0 = time.perf_counter()
         P.perform_galactic_evolution(progress_bar=False)
         fp = P.final_pos
         dt = time.perf_counter() - t0
+        if k == 0:
+            first = dt
         if best is None or dt < best:
             best = dt
-    # itemise the host side by running its stages on their own
-    t0 = time.perf_counter(); pe, se = identify_event_tables(P); t_ev = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    b = build_orbit_batch(pop.pos_kpc, pop.vel_kms, pop.tau_gyr, 12.0, 1.0, P.disrupted, pe, se)
-    t_b = time.perf_counter() - t0
+    # itemise the host side by running its stages on their own (memory policy as inside the stage)
     from cogsworth_b200 import kicks
-    t0 = time.perf_counter()
-    kicks.integrate_orbits(b, potential=pop.potential, store_all=False, integrator="leapfrog", context=ctx)
-    t_i = time.perf_counter() - t0
+    from cogsworth_b200._lib import pinned_policy
+    with pinned_policy("cached"):
+        t0 = time.perf_counter(); pe, se = identify_event_tables(P); t_ev = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        b = build_orbit_batch(pop.pos_kpc, pop.vel_kms, pop.tau_gyr, 12.0, 1.0, P.disrupted, pe, se)
+        t_b = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        kicks.integrate_orbits(b, potential=pop.potential, store_all=False, integrator="leapfrog", context=ctx)
+        t_i = time.perf_counter() - t0
     steps = float(P._last_integration_info["stats"][3])
     assert np.isfinite(np.asarray(fp)).all()
     return {"size": size_label, "n_binaries": int(n_binaries), "n_orbits": int(b.n_orbits), "orbit_steps": steps,
-            "seconds": best, "value": steps / best, "unit": "orbit-steps/s",
+            "seconds": best, "first_call_seconds": first, "value": steps / best, "unit": "orbit-steps/s",
             "seconds_itemised": {"identify_event_tables (numpy joins of bpp / kick_info / initial_binaries)": t_ev,
                                  "build_orbit_batch (w0, start times, grid classes, kick rotation, CSR)": t_b,
                                  "integrate_orbits (H2D + kernels + D2H + OrbitArray)": t_i,
                                  "rest (Quantity -> array, stacking, final_pos)": max(best - t_ev - t_b - t_i, 0.0)},
             "how": "B200Population(initial_galaxy, bpp, kick_info, initial_binaries).perform_galactic_evolution(); "
-                   "final_pos read back; leapfrog, final state only"}
+                   "final_pos read back; leapfrog, final state only; batch and result arrays in ordinary memory (the "
+                   "stage pins nothing but the library's staging ring, once per context: first_call_seconds includes it)"}
 
 
 def main():

@@ -559,9 +559,13 @@ static int64_t traj_shard_cols(bool staged)
 // Q > 0: the number of orbits one full grid of the kernel holds (persistent lanes).  Chunks are whole multiples of it,
 // so no chunk ends with a wave that fills a fraction of the GPU (10^6 orbits in LM10 at Q = 113 664: 127k-orbit
 // chunks = 1.12 waves each cost a third of the end-to-end throughput).
-static int64_t host_chunk(int64_t n_on_device, int64_t Q)
+static int64_t host_chunk(int64_t n_on_device, int64_t Q, bool staged)
 {
     int64_t c = (n_on_device + 7) / 8;
+    // Pageable caller arrays pass through the lanes' page-locked staging buffers, which are as large as the largest
+    // chunk and cost 0.45 ms per MB to pin when a context is first used: two waves per chunk (24 + 18 MB per lane)
+    // instead of up to six keep that below 70 ms for a caller that runs one call.
+    if (staged && Q > 0) c = std::min(c, 2 * Q);
     if (const char *e = getenv("CW_HOST_CHUNK")) {      // experiment hook: fixed chunk size in orbits
         const long long v = atoll(e);
         if (v > 0) return (int64_t)v;
@@ -576,10 +580,10 @@ static int64_t host_chunk(int64_t n_on_device, int64_t Q)
 }
 
 // orbit counts of the chunks of one device slot holding M orbits
-static std::vector<int64_t> chunk_sizes(int64_t M, bool pipelined, int64_t Q)
+static std::vector<int64_t> chunk_sizes(int64_t M, bool pipelined, int64_t Q, bool staged)
 {
     std::vector<int64_t> sizes;
-    const int64_t chunk = pipelined ? host_chunk(M, Q) : M;
+    const int64_t chunk = pipelined ? host_chunk(M, Q, staged) : M;
     // The first H2D copy and the last D2H copy have nothing to hide behind: ramp the chunk size up from a fraction
     // of it at the start and back down at the end (the kernels in between keep the full size).
     if (!pipelined || M < 4 * chunk) {
@@ -1055,7 +1059,9 @@ static int make_chunks(HostCall &H, std::vector<Chunk> &chunks)
             // pipelines better in the finer chunks -- measured 1.34e11 against 0.90e11 steps/s end to end
             if (getenv("CW_NO_WAVE_CHUNKS") || M < 4 * Q) Q = 0;
         }
-        const std::vector<int64_t> sizes = chunk_sizes(M, pipelined, Q);
+        const bool staged = !(H.p_w0 && H.p_t1 && H.p_t2 && H.p_dt && H.p_tm && H.p_fl && H.p_cls && H.p_ctab && H.p_idx &&
+                              H.p_off && H.p_evt && H.p_evd && H.p_toff && H.p_wf && H.p_st && H.p_nn && H.p_es);
+        const std::vector<int64_t> sizes = chunk_sizes(M, pipelined, Q, staged);
         int lane = 0;
         int64_t u = u_lo, cum = 0;
         for (size_t k = 0; k < sizes.size() && u < u_hi; k++) {

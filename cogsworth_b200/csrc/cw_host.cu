@@ -50,24 +50,32 @@ constexpr size_t PIN_GRAIN = (size_t)2 << 20;
 
 } // namespace
 
+// a cached block that fits `bytes`, or nullptr: never calls into the CUDA runtime
+void *pinned_alloc_cached(size_t bytes)
+{
+    if (bytes == 0) bytes = 1;
+    const size_t want = (bytes + PIN_GRAIN - 1) / PIN_GRAIN * PIN_GRAIN;
+    PinnedCache &c = pinned_cache();
+    std::lock_guard<std::mutex> lk(c.m);
+    auto it = c.free_blocks.lower_bound(want);
+    // best fit, but never hand a block that wastes more than a quarter of itself (+ one grain)
+    if (it != c.free_blocks.end() && it->first <= want + want / 4 + PIN_GRAIN) {
+        void *p = it->second;
+        const size_t sz = it->first;
+        c.free_blocks.erase(it);
+        c.cached_bytes -= sz;
+        c.live[p] = sz;
+        return p;
+    }
+    return nullptr;
+}
+
 void *pinned_alloc(size_t bytes)
 {
     if (bytes == 0) bytes = 1;
     const size_t want = (bytes + PIN_GRAIN - 1) / PIN_GRAIN * PIN_GRAIN;
     PinnedCache &c = pinned_cache();
-    {
-        std::lock_guard<std::mutex> lk(c.m);
-        auto it = c.free_blocks.lower_bound(want);
-        // best fit, but never hand a block that wastes more than a quarter of itself (+ one grain)
-        if (it != c.free_blocks.end() && it->first <= want + want / 4 + PIN_GRAIN) {
-            void *p = it->second;
-            const size_t sz = it->first;
-            c.free_blocks.erase(it);
-            c.cached_bytes -= sz;
-            c.live[p] = sz;
-            return p;
-        }
-    }
+    if (void *hit = pinned_alloc_cached(bytes)) return hit;
     void *p = nullptr;
     cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
     if (e != cudaSuccess) {
@@ -314,5 +322,6 @@ extern "C" void cw_host_rotate_kicks(int64_t K, const double *dv, const double *
 }
 
 extern "C" void *cw_host_alloc(size_t bytes) { return cw::pinned_alloc(bytes); }
+extern "C" void *cw_host_alloc_cached(size_t bytes) { return cw::pinned_alloc_cached(bytes); }
 extern "C" void cw_host_free(void *p) { cw::pinned_free(p); }
 extern "C" int cw_host_is_pinned(const void *p) { return (p && cw::pointer_is_dma_able(p)) ? 1 : 0; }

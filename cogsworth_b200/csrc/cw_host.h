@@ -13,7 +13,8 @@
 namespace cw {
 
 // ---- page-locked memory cache (cudaHostAlloc, portable): blocks are handed back to a free list, not to the driver
-void *pinned_alloc(size_t bytes);      // nullptr on failure
+void *pinned_alloc(size_t bytes);             // nullptr on failure
+void *pinned_alloc_cached(size_t bytes);      // a block from the cache, or nullptr (no CUDA call)
 void pinned_free(void *p);
 void pinned_trim();                    // release every cached block
 // true when p is page-locked host memory or device / managed memory known to the runtime (= DMA-able as it is)

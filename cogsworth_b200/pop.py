@@ -79,16 +79,21 @@ class GalacticStageB200:
         draw_sn_angles(self.initial_binaries)
         primary_events, secondary_events = identify_event_tables(self)
 
-        batch = build_orbit_batch(pos, vel, tau, float(_val(self.max_ev_time, "Gyr")),
-                                  float(_val(self.timestep_size, "Myr")), self.disrupted,
-                                  primary_events, secondary_events)
         retry = {"max_retries": 2, "timestep_multiplier": 0.1}
         retry.update(getattr(self, "orbit_integration_retry_settings", None) or {})
-        orbits, info = integrate_orbits(
-            batch, potential=self.galactic_potential, store_all=self.store_entire_orbits,
-            integrator=self.integrator, integrator_kwargs=self.integrator_kwargs,
-            max_retries=retry["max_retries"], timestep_multiplier=retry["timestep_multiplier"],
-            context=getattr(self, "_cw_context", None))
+        # The stage runs once per population: its batch and result arrays take page-locked memory only if the library
+        # already holds some (pinning 1.4 GB for 10^7 orbits would cost ten times the integration itself); ordinary
+        # arrays go through the library's staging ring.
+        from ._lib import pinned_policy
+        with pinned_policy(getattr(self, "_cw_pinned_policy", "cached")):
+            batch = build_orbit_batch(pos, vel, tau, float(_val(self.max_ev_time, "Gyr")),
+                                      float(_val(self.timestep_size, "Myr")), self.disrupted,
+                                      primary_events, secondary_events)
+            orbits, info = integrate_orbits(
+                batch, potential=self.galactic_potential, store_all=self.store_entire_orbits,
+                integrator=self.integrator, integrator_kwargs=self.integrator_kwargs,
+                max_retries=retry["max_retries"], timestep_multiplier=retry["timestep_multiplier"],
+                context=getattr(self, "_cw_context", None))
         self._last_integration_info = info
 
         if orbits.n_failed:
