@@ -146,3 +146,33 @@ def test_no_sync_calls_on_two_streams_share_the_scratch_safely(ctx):
     c, _ = call(s2, True)
     torch.cuda.synchronize()
     assert torch.equal(a, ref) and torch.equal(c, ref)
+
+
+def test_pinned_policy_cached_never_pins_new_memory(ctx):
+    """`pinned_policy("cached")` (what perform_galactic_evolution runs under): page-locked memory only when the
+    library's cache already holds a block that fits, ordinary memory otherwise -- and a batch built that way integrates
+    to the same bits through the staging ring."""
+    from cogsworth_b200 import _lib
+    n = 3_000_017                                   # a size nothing else in the suite has asked for
+    with _lib.pinned_policy("cached"):
+        a = _lib.pinned_empty(n)
+        assert not _lib.is_pinned(a)                # nothing cached: ordinary memory, no cudaHostAlloc
+    b = _lib.pinned_empty(n)                        # default policy: pins
+    assert _lib.is_pinned(b)
+    del b                                           # back to the library's cache
+    with _lib.pinned_policy("cached"):
+        c = _lib.pinned_empty(n)
+        assert _lib.is_pinned(c)                    # the cached block is handed out
+        with pytest.raises(ValueError):
+            _lib.pinned_policy("sometimes")
+    del a, c
+    pop = _pop(4000, horizon=0.3, cfg=4)
+    ctx.set_potential(pop.potential)
+    ref = ctx.integrate_batch(pop.batch)
+    with _lib.pinned_policy("cached"):
+        from cogsworth_b200.batch import build_orbit_batch
+        b2 = build_orbit_batch(pop.pos_kpc, pop.vel_kms, pop.tau_gyr, 12.0, 1.0, pop.disrupted, pop.primary_events,
+                               pop.secondary_events)
+        r2 = ctx.integrate_batch(b2)
+    assert np.array_equal(ref["w_final"], r2["w_final"]) and np.array_equal(ref["status"], r2["status"])
+    assert np.array_equal(ref["ev_step"], r2["ev_step"])
