@@ -25,7 +25,7 @@ ORBIT_STATUS = {0: "ok", -1: "inconsistent input", -2: "larger nmax is needed",
                 -5: "non-finite error norm", -6: "trajectory slot too small"}
 
 EXPORTS = ["cw_create", "cw_destroy", "cw_device_count", "cw_set_potential", "cw_set_potential_ex", "cw_set_potential_general",
-           "cw_set_potential_time", "cw_count_nodes", "cw_host_alloc", "cw_host_alloc_cached", "cw_host_free", "cw_host_is_pinned",
+           "cw_set_potential_time", "cw_count_nodes", "cw_host_alloc", "cw_host_alloc_cached", "cw_host_free", "cw_host_trim", "cw_host_is_pinned",
            "cw_host_rotate_kicks",
            "cw_integrate", "cw_gradient", "cw_potential_value", "cw_circular_velocity", "cw_pointwise_t", "cw_strerror",
            "cw_last_error", "cw_abi_version", "cw_last_launch_count", "cw_last_max_attempts", "cw_last_kernel_ms",
@@ -107,6 +107,8 @@ def load():
     L.cw_host_alloc.restype = vp
     L.cw_host_alloc_cached.argtypes = [C.c_size_t]
     L.cw_host_alloc_cached.restype = vp
+    L.cw_host_trim.argtypes = []
+    L.cw_host_trim.restype = None
     L.cw_host_free.argtypes = [vp]
     L.cw_host_free.restype = None
     L.cw_host_is_pinned.argtypes = [vp]
@@ -207,6 +209,11 @@ def pinned_empty(shape, dtype=np.float64):
         return np.empty(shape, dtype=dtype)
     _PINNED_OK = True
     return np.asarray(blk)[:nbytes].view(dtype).reshape(shape)
+
+
+def pinned_trim():
+    """Release every cached (free) page-locked block back to the driver."""
+    load().cw_host_trim()
 
 
 def is_pinned(a) -> bool:

@@ -187,6 +187,9 @@ __constant__ double k_D715 = CW_D715;
 __constant__ double k_D716 = CW_D716;
 
 constexpr int DP_BLOCK = 128;
+#ifndef CW_DP_SPEC
+#define CW_DP_SPEC 1       // build knob: evaluate the next step's first stage beside the step-size controller (see phase C)
+#endif
 #ifndef CW_DP_MINB
 #define CW_DP_MINB 1       // resident CTAs per SM the kernel is compiled for (experiment knob; 1 = no register cap)
 #endif
@@ -488,6 +491,12 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
                 sq = erri * isk;
                 err = fma(sq, sq, err);
             }
+#if CW_DP_SPEC
+            // f(x + h, y_new), the first stage of the next step, is needed only if this attempt is accepted -- 99.6 % are --
+            // and depends on nothing the controller computes: evaluated HERE, its long dependent chain runs beside the
+            // controller's (four reciprocal square roots in a row), instead of after it.  A rejected attempt discards it.
+            fcn<KIND>(P, ltab, seg, xph, k5, k4);
+#endif
             // Controller arithmetic on the DFMA pipe with the kernels' own branch-free rsqrt / reciprocal (the
             // library sqrt / divide carry slow-path branches and ~4x the instructions; a lane's step attempts
             // are strictly sequential, so every instruction here is on the critical path of the slowest orbit).
@@ -513,7 +522,9 @@ __global__ void __launch_bounds__(DP_BLOCK, CW_DP_MINB) dop853_kernel(const __gr
                 s.facold = fmax(err, 1.0e-4);
                 s.naccpt++;
                 n_acc++;
+#if !CW_DP_SPEC
                 fcn<KIND>(P, ltab, seg, xph, k5, k4);  // first stage of the next step
+#endif
                 n_fcn++;
                 // stiffness detection (nstiff = 1: every accepted step)
                 double stnum = 0.0, stden = 0.0;

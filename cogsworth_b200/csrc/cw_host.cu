@@ -324,4 +324,5 @@ extern "C" void cw_host_rotate_kicks(int64_t K, const double *dv, const double *
 extern "C" void *cw_host_alloc(size_t bytes) { return cw::pinned_alloc(bytes); }
 extern "C" void *cw_host_alloc_cached(size_t bytes) { return cw::pinned_alloc_cached(bytes); }
 extern "C" void cw_host_free(void *p) { cw::pinned_free(p); }
+extern "C" void cw_host_trim(void) { cw::pinned_trim(); }
 extern "C" int cw_host_is_pinned(const void *p) { return (p && cw::pointer_is_dma_able(p)) ? 1 : 0; }

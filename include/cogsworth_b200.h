@@ -254,6 +254,8 @@ void cw_host_free(void *p);
  * page-locked arrays saves over the staging ring, so a caller that runs the stage ONCE (Population.
  * perform_galactic_evolution) asks here and falls back to ordinary memory; a caller in a loop uses cw_host_alloc. */
 void *cw_host_alloc_cached(size_t bytes);
+/* Give every cached (free) page-locked block back to the driver; blocks in use are not touched. */
+void cw_host_trim(void);
 /* 1 if p is page-locked (or device) memory known to the CUDA runtime, 0 if pageable */
 int cw_host_is_pinned(const void *p);
 /* get_kick_differential (kicks.py:12-49) for K events at once, on the library's host threads: dv (K x 3, km/s in the

@@ -153,7 +153,8 @@ def test_pinned_policy_cached_never_pins_new_memory(ctx):
     library's cache already holds a block that fits, ordinary memory otherwise -- and a batch built that way integrates
     to the same bits through the staging ring."""
     from cogsworth_b200 import _lib
-    n = 3_000_017                                   # a size nothing else in the suite has asked for
+    n = 3_000_017
+    _lib.pinned_trim()                              # whatever earlier tests left in the cache goes back to the driver
     with _lib.pinned_policy("cached"):
         a = _lib.pinned_empty(n)
         assert not _lib.is_pinned(a)                # nothing cached: ordinary memory, no cudaHostAlloc
