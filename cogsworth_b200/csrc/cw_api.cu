@@ -1059,8 +1059,9 @@ static int make_chunks(HostCall &H, std::vector<Chunk> &chunks)
             // pipelines better in the finer chunks -- measured 1.34e11 against 0.90e11 steps/s end to end
             if (getenv("CW_NO_WAVE_CHUNKS") || M < 4 * Q) Q = 0;
         }
-        const bool staged = !(H.p_w0 && H.p_t1 && H.p_t2 && H.p_dt && H.p_tm && H.p_fl && H.p_cls && H.p_ctab && H.p_idx &&
-                              H.p_off && H.p_evt && H.p_evd && H.p_toff && H.p_wf && H.p_st && H.p_nn && H.p_es);
+        // (the per-orbit / per-event arrays decide; the few bytes of the class table may well be ordinary memory)
+        const bool staged = !(H.p_w0 && H.p_t1 && H.p_t2 && H.p_dt && H.p_tm && H.p_fl && H.p_cls && H.p_idx &&
+                              H.p_off && H.p_evt && H.p_evd && H.p_wf && H.p_st && H.p_nn && H.p_es);
         const std::vector<int64_t> sizes = chunk_sizes(M, pipelined, Q, staged);
         int lane = 0;
         int64_t u = u_lo, cum = 0;
