@@ -1039,10 +1039,51 @@ static int make_chunks(HostCall &H, std::vector<Chunk> &chunks)
     };
     const bool traj_staged = H.store_all && !(H.p_tp && H.p_tv && (!H.R.traj_t || H.p_tt));
     const int64_t col_lim = traj_shard_cols(traj_staged);
+    // ---- the cut over the device slots.  Slices stay contiguous (no permutation of the caller's arrays, no gather on
+    // the host), but they hold equal WORK, not equal orbit counts: the grid steps of every 256th source unit are
+    // read, weighted with the orbits that start from its block, and the cut points are where the running sum passes
+    // k / nslots of the total.  A population in random order is cut as before; one sorted by age (steps grow along the
+    // index) no longer leaves the last device with twice its share.
+    std::vector<int64_t> slot_end(nslots, H.n_src);
+    const cw_batch *B = H.B;
+    if (nslots > 1) {
+        const int64_t B0 = 256;
+        const int64_t nb = (H.n_src + B0 - 1) / B0;
+        std::vector<double> cum(nb + 1, 0.0);
+        for (int64_t b = 0; b < nb; b++) {
+            const int64_t u = b * B0, ue = std::min(H.n_src, u + B0);
+            double t2, dt;
+            if (H.classes) {
+                const int c = B->grid_class[u];
+                const cw_grid_class g = B->classes[c < B->n_classes ? c : 0];
+                t2 = g.t2; dt = g.dt;
+            } else {
+                t2 = B->t2[u]; dt = B->dt[u];
+            }
+            double steps = (dt != 0.0) ? (t2 - B->t1[u]) / dt : 1.0;
+            if (!(steps >= 1.0)) steps = 1.0;                 // NaN, negative, empty grids
+            if (steps > 1.0e6) steps = 1.0e6;
+            cum[b + 1] = cum[b] + steps * (double)(H.orbits_before(ue) - H.orbits_before(u));
+        }
+        int64_t b = 0;
+        for (int d = 0; d + 1 < nslots; d++) {
+            const double target = cum[nb] * (double)(d + 1) / (double)nslots;
+            while (b < nb && cum[b + 1] <= target) b++;
+            // the block that straddles the target is split in proportion (its orbits are taken to cost the same)
+            int64_t u = b * B0;
+            if (b < nb && cum[b + 1] > cum[b])
+                u += (int64_t)((double)(std::min(H.n_src, u + B0) - u) * (target - cum[b]) / (cum[b + 1] - cum[b]));
+            slot_end[d] = std::min(std::max(u, d > 0 ? slot_end[d - 1] : (int64_t)0), H.n_src);
+        }
+    }
+    if (H.trace && nslots > 1)
+        for (int d = 0; d < nslots; d++)
+            fprintf(stderr, "[cw] slot %d takes source units [%lld, %lld)\n", d, (long long)(d ? slot_end[d - 1] : 0),
+                    (long long)slot_end[d]);
     int64_t u_prev = 0;
     for (int d = 0; d < nslots; d++) {
         const int64_t u_lo = u_prev;
-        const int64_t u_hi = (d + 1 == nslots) ? H.n_src : unit_for(n * (d + 1) / nslots, u_lo, H.n_src);
+        const int64_t u_hi = slot_end[d];
         u_prev = u_hi;
         if (u_hi <= u_lo) continue;
         const int64_t base = H.orbits_before(u_lo);
