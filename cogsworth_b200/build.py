@@ -22,7 +22,7 @@ LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompil
               "-lcuda"]
 # experiment knobs (see cw_traj.cuh / cw_leapfrog.cu / cw_dop853.cu): -DNAME=VALUE when set in the environment
 KNOBS = ("CW_TRAJ_NOSTORE", "CW_TRAJ_DEBUG", "CW_LF_REGS", "CW_LF_GEN_REGS", "CW_DP_MINB", "CW_STORE_UNROLL",
-         "CW_LF_VARIANT", "CW_DP_VARIANT", "CW_TRAJ_VARIANT", "CW_CHECKED", "CW_LF_BLOCK", "CW_TRAJ_S", "CW_LF_STORE_REGS", "CW_TRAJ_TMEM", "CW_TRAJ_WIDE", "CW_TRAJ_TSTAGE", "CW_DP_SPEC")
+         "CW_LF_VARIANT", "CW_DP_VARIANT", "CW_TRAJ_VARIANT", "CW_CHECKED", "CW_LF_BLOCK", "CW_TRAJ_S", "CW_LF_STORE_REGS", "CW_TRAJ_TMEM", "CW_TRAJ_WIDE", "CW_TRAJ_TSTAGE", "CW_DP_SPEC", "CW_DP_BLOCK")
 
 
 def _nvcc():

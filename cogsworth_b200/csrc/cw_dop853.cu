@@ -186,7 +186,10 @@ __constant__ double k_D714 = CW_D714;
 __constant__ double k_D715 = CW_D715;
 __constant__ double k_D716 = CW_D716;
 
-constexpr int DP_BLOCK = 128;
+#ifndef CW_DP_BLOCK
+#define CW_DP_BLOCK 128     // build knob (with CW_DP_MINB): threads per CTA
+#endif
+constexpr int DP_BLOCK = CW_DP_BLOCK;
 #ifndef CW_DP_SPEC
 #define CW_DP_SPEC 1       // build knob: evaluate the next step's first stage beside the step-size controller (see phase C)
 #endif
