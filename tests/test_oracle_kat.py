@@ -188,6 +188,28 @@ def test_leapfrog_reversible_and_energy(oracle):
     assert np.abs(back - w0).max() < 1e-10
 
 
+def test_leapfrog_is_velocity_verlet(oracle):
+    """The oracle's leapfrog (gala's recipe as recalled: half-step velocity initialised backwards, drift, gradient,
+    kick, synchronised velocity by half a kick) against an INDEPENDENT textbook statement written here -- velocity
+    Verlet / kick-drift-kick with the same gradient: the two are the same map up to rounding, so 1000 steps of a disc
+    orbit agree to 1e-11 and every stored sample (not only the last) is the Verlet sample.  Pins the recipe's
+    structure (what is updated with what, which velocity is stored); its rounding order stays [gala-recall]."""
+    v2 = MilkyWayPotential("v2")
+    w0 = np.array([8.0, 0.5, 0.1, 0.01, 0.22, 0.02])
+    dt, n = 1.0, 1000
+    traj = oracle.leapfrog(v2, w0, np.arange(0.0, (n + 1) * dt, dt))
+    q, v = w0[:3].copy(), w0[3:].copy()
+    a = -np.asarray(oracle.gradient(v2, q))
+    worst = 0.0
+    for j in range(1, n + 1):
+        v_half = v + 0.5 * dt * a
+        q = q + dt * v_half
+        a = -np.asarray(oracle.gradient(v2, q))
+        v = v_half + 0.5 * dt * a
+        worst = max(worst, np.abs(traj[:3, j] - q).max() / np.abs(q).max(), np.abs(traj[3:, j] - v).max() / np.abs(v).max())
+    assert worst < 1e-11, worst
+
+
 # ---- dense-output DOP853 (SURVEY.md 8a A8: "implement both modes") ---------------------------------
 
 def test_dop853_dense_interpolant_matches_scipy(oracle):
