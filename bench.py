@@ -427,6 +427,33 @@ def measure(W, steps, warmup, barrier, max_over_ranks, sum_over_ranks, peak_fp64
                                        "the library's page-locked ring by its host thread pool, chunk by chunk"}
             del plain
 
+    if with_api and wl["store_all"]:
+        # Whole trajectories through the Python API (store_entire_orbits=True, the reference's default): a bounded
+        # sample of the workload, because every orbit-step returns 56 bytes (6 coordinates + the time stamp) over the
+        # host link and 10^6 orbits would need 56 GB of host memory.  The figure is the link's, not the kernel's.
+        from cogsworth_b200 import kicks
+        ns = int(min(W.n, 50_000))
+        sub = W.b.take(np.arange(ns))
+        run = lambda: kicks.integrate_orbits(sub, potential=W.pop.potential, store_all=True, integrator=wl["integrator"],
+                                             integrator_kwargs=dict(W.tol), context=ctx)
+        for _ in range(2):
+            orbits, info = run()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            orbits, info = run()
+        s_tr = (time.perf_counter() - t0) / 2
+        st = float(info["stats"][3])
+        nbytes = 56.0 * float(np.asarray(info["n_nodes"], dtype=np.int64).sum())
+        e2e = {"value": st / s_tr, "unit": "orbit-steps/s", "ms_per_step": 1e3 * s_tr,
+               "h2d_bytes_per_step": int(sum(v.nbytes for v in sub.abi_arrays().values() if isinstance(v, np.ndarray))),
+               "d2h_bytes_per_step": int(nbytes) + ns * 56,
+               "d2h_gb_per_s": nbytes / s_tr / 1e9,
+               "sample": f"{ns} orbits of the workload ({int(st)} orbit-steps, {nbytes / 1e9:.2f} GB of trajectories per call)",
+               "how": "cogsworth_b200.kicks.integrate_orbits(batch, store_all=True) on a bounded sample: kernels write the "
+                      "trajectories chunk by chunk into bounded device buffers, D2H into page-locked host arrays overlaps the "
+                      "next chunk's kernel; bound by the host link"}
+        del orbits, info, sub
+
     # ---- roofline of the dominant kernel -----------------------------------------------------------------------
     k_ms = float(np.mean(kernel_ms))
     hbm_peak, hbm_src = measured_peaks()
@@ -579,7 +606,7 @@ def main():
             r = measure(OW, 2, 2, torch.cuda.synchronize, single, single, peak, 1, args)
             others[name] = {"workload": owl["desc"], "value": r["value"], "unit": "orbit-steps/s",
                             "ms_per_step": r["ms_per_step"],
-                            "e2e": None if r["e2e"] is None else {k: r["e2e"][k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+                            "e2e": None if r["e2e"] is None else {k: r["e2e"][k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "d2h_gb_per_s", "sample") if k in r["e2e"]},
                             "roofline": {k: r["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel", "kernel_ms")},
                             "run": r["run"], "steps": 2, "warmup": 2}
             OW.free()
