@@ -178,11 +178,11 @@ cudaError_t launch_traj_times(const IntegArgs &A, const LaunchCfg &cfg)
 #define CW_LF_BLOCK 256    // experiment knob (with CW_LF_REGS): threads per CTA of the final-state kernel
 #endif
 constexpr int LF_BLOCK = CW_LF_BLOCK; // final-state kernel: 4 CTAs x 256 threads per SM (64 registers)
-// store_all kernel: ONE CTA of 512 threads per SM.  The staging windows (392 B per lane = 196 KB) cap the
-// orbits in flight at 512 per SM, and a kernel that allocates tensor memory is given one CTA per SM by the
-// occupancy calculator whatever it asks for, so the 16 warps live in one CTA that owns all 512 TMEM columns
-// (measured 4.13 TB/s vs 4.00 TB/s for 2 x 256 threads with 256 columns each; 128 registers per thread).
-constexpr int LF_BLOCK_STORE = TRAJ_STORE_BLOCK;   // 512 lanes x 8-sample windows, or 256 x 16 (cw_traj.cuh)
+// store_all kernel: ONE CTA of 512 threads per SM (cw_traj.cuh: the windows of 256 lanes fill the shared memory, 776 B
+// per lane = 196 KB; the other 256 lanes stage in tensor memory, and a kernel that allocates tensor memory is given one
+// CTA per SM by the occupancy calculator whatever it asks for, so the 16 warps live in one CTA that owns all 512 TMEM
+// columns); 128 registers per thread.
+constexpr int LF_BLOCK_STORE = TRAJ_STORE_BLOCK;   // 512 (256 without TRAJ_TSTAGE; cw_traj.cuh)
 #ifndef CW_LF_REGS
 #define CW_LF_REGS 64      // experiment knob: 80 -> 3 resident CTAs (measured: see DESIGN.md)
 #endif

@@ -4,16 +4,20 @@
 //
 // One lane integrates one orbit, so consecutive samples of a lane are consecutive in memory but the
 // 32 lanes of a warp write 32 far-apart columns: a plain st.global.f64 per sample would cost a whole
-// 32-byte L2 sector transaction for 8 useful bytes.  Instead every lane stages TRAJ_S (8) consecutive
-// samples of its six coordinates in its own shared-memory rows.  Windows are aligned to ABSOLUTE
-// columns (slot = column & 7), so a complete window is six 64-byte, 64-byte-aligned runs whatever the
-// orbit's offset.  At the two warp-convergent points of the integrator loop the warp votes which lanes
-// completed a window and writes them cooperatively: 8 adjacent lanes move one 64-byte run (LDS.64 ->
-// STG.64), so every store instruction writes four full runs = eight full sectors, no partial-sector
-// traffic.  The ragged first / last window of an orbit goes out through the same path, predicated.
+// 32-byte L2 sector transaction for 8 useful bytes.  Instead every lane stages TRAJ_S (16; 8 in round 1)
+// consecutive samples of its six coordinates.  Windows are aligned to ABSOLUTE columns (slot = column &
+// 15), so a complete window is six full, aligned 128-byte lines whatever the orbit's offset.  Where the
+// windows live depends on the warp (TRAJ_TSTAGE, the shipped form: 512 lanes per SM):
+//   * warps 0..7: the lane's own shared-memory rows; at the two warp-convergent points of the integrator loop
+//     the warp votes which lanes completed a window and writes them cooperatively, 16 adjacent lanes per
+//     128-byte run (LDS.64 -> STG.64), two full lines per store instruction;
+//   * warps 8..15: tensor memory, written straight from registers (tcgen05.st, two columns per value of the
+//     thread's own TMEM lane) and read back in the 16x256b shape, which hands four adjacent threads four
+//     consecutive samples of one orbit: every store instruction writes eight full 32-byte sectors.
+// The ragged first / last window of an orbit goes out through the same paths, predicated.
 //
 // Lock-step is kept by construction, not by luck: the integrator starts an orbit only on a step of its
-// warp clock W with W = (first column of the orbit) mod 16, so every active lane of a warp always stands
+// warp clock W with W = (first column of the orbit) mod 32, so every active lane of a warp always stands
 // on the same column phase, whatever the queue order and however different the orbit lengths are.
 //
 // (Round-1 note: the first version issued per-lane cp.async.bulk (TMA) stores.  UBLKCP is a
