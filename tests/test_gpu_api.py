@@ -186,6 +186,37 @@ def test_in_process_multi_device_sharding(built):
     one.close(); many.close()
 
 
+def test_several_slots_on_one_device(built):
+    """The in-process multi-device path -- work-balanced contiguous cut, one long-lived host thread per slot, per-slot
+    chunk pipelines -- exercised on ONE GPU by naming it several times (cw_create accepts a device more than once: the
+    slots are independent): every slot count returns the single-slot bits, for page-locked compact batches in several
+    chunks per slot and for an age-sorted population whose slices then differ in length."""
+    from cogsworth_b200.batch import build_orbit_batch
+    pop = make_population(150_000, cfg_id=53, horizon_gyr=0.05)
+    srt = make_population(40_000, cfg_id=54, horizon_gyr=(0.01, 0.2))
+    o = np.argsort(srt.tau_gyr, kind="stable")
+    sb = build_orbit_batch(srt.pos_kpc[:, o], srt.vel_kms[:, o], srt.tau_gyr[o], 12.0, 1.0, np.zeros(len(o), dtype=bool))
+    one = cb.Context(devices=[0])
+    one.set_potential(pop.potential)
+    ref, ref_s = one.integrate_batch(pop.batch), one.integrate_batch(sb)
+    for ns in (2, 3, 8):
+        many = cb.Context(devices=[0] * ns)
+        assert many.n_devices == ns
+        many.set_potential(pop.potential)
+        for _ in range(2):                               # (the second call re-uses the slot threads and buffers)
+            r = many.integrate_batch(pop.batch)
+            for k in ("w_final", "status", "n_nodes", "ev_step"):
+                assert np.array_equal(r[k], ref[k]), (ns, k)
+            assert int(r["stats"][3]) == int(ref["stats"][3])
+        rs = many.integrate_batch(sb)
+        assert np.array_equal(rs["w_final"], ref_s["w_final"]) and np.array_equal(rs["n_nodes"], ref_s["n_nodes"])
+        tr = many.integrate_batch(sb, store_all=True)
+        tr1 = one.integrate_batch(sb, store_all=True)
+        assert np.array_equal(tr["traj_pos"], tr1["traj_pos"]) and np.array_equal(tr["traj_off"], tr1["traj_off"])
+        many.close()
+    one.close()
+
+
 def test_rewind_backward_integration(ctx, oracle):
     """cogsworth_b200.rewind.rewind_orbits = the batch form of hydro/rewind.py's _tohspans fan-out: every particle
     integrated from the snapshot time back to its own formation time (dt = -1 Myr, DOPRI853, final state)."""
