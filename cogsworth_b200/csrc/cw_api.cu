@@ -1159,17 +1159,45 @@ static int make_chunks(HostCall &H, std::vector<Chunk> &chunks)
         // (measured 3.5e9 vs 6.2e9 intervals/s end to end), so they go to the device in one piece.
         const bool pipelined = !H.integrate || H.o->integrator == CW_LEAPFROG;
         int64_t Q = 0;
+        bool one_chunk = false;
         if (pipelined && H.integrate && !H.store_all) {
             cudaSetDevice(ctx->slots[d].dev);
             Q = leapfrog_lane_capacity(ctx->pot, ctx->slots[d].sm_count);
+            if (M < 4 * Q && !getenv("CW_HOST_CHUNK")) {
+                // A batch of less than four waves whose copies are small beside its kernel time goes to the device in
+                // ONE piece: nothing is gained by overlapping 0.5 ms of copies with 8 ms of kernel, and the queue is
+                // then ordered longest-first over the whole batch instead of chunk by chunk (10^5 binaries with
+                // Wagg2022 horizons, BASELINE config 2: 9.6 ms against 10.8 ms per call; 3 x 10^5: 25.3 against 29.2).
+                // Kernel time from the grid steps of <= 256 sampled orbits at 1.8e11 steps/s, copies at 140 B per orbit
+                // and 50 GB/s; short orbits (1000 steps: copies are half the kernel time) keep the pipelined cut.
+                const int64_t stride = std::max<int64_t>(1, (u_hi - u_lo) / 256);
+                double steps = 0.0;
+                int64_t ns = 0;
+                for (int64_t u = u_lo; u < u_hi; u += stride, ns++) {
+                    double t2, dt;
+                    if (H.classes) {
+                        const int c = B->grid_class[u];
+                        const cw_grid_class g = B->classes[c < B->n_classes ? c : 0];
+                        t2 = g.t2; dt = g.dt;
+                    } else {
+                        t2 = B->t2[u]; dt = B->dt[u];
+                    }
+                    double st = (dt != 0.0) ? (t2 - B->t1[u]) / dt : 1.0;
+                    if (!(st >= 1.0)) st = 1.0;
+                    steps += std::min(st, 1.0e6);
+                }
+                const double kernel_s = (double)M * (steps / (double)std::max<int64_t>(ns, 1)) / 1.8e11;
+                const double copy_s = (double)M * 140.0 / 50.0e9;
+                one_chunk = copy_s < 0.15 * kernel_s;
+            }
             // only batches of several waves: a batch of one or two (10^5 binaries with their own horizons, config 2)
-            // pipelines better in the finer chunks -- measured 1.34e11 against 0.90e11 steps/s end to end
+            // pipelines better in the finer chunks than in wave-sized ones -- measured 1.34e11 against 0.90e11 steps/s
             if (getenv("CW_NO_WAVE_CHUNKS") || M < 4 * Q) Q = 0;
         }
         // (the per-orbit / per-event arrays decide; the few bytes of the class table may well be ordinary memory)
         const bool staged = !(H.p_w0 && H.p_t1 && H.p_t2 && H.p_dt && H.p_tm && H.p_fl && H.p_cls && H.p_idx &&
                               H.p_off && H.p_evt && H.p_evd && H.p_wf && H.p_st && H.p_nn && H.p_es);
-        const std::vector<int64_t> sizes = chunk_sizes(M, pipelined, Q, staged);
+        const std::vector<int64_t> sizes = one_chunk ? std::vector<int64_t>{M} : chunk_sizes(M, pipelined, Q, staged);
         int lane = 0;
         int64_t u = u_lo, cum = 0;
         for (size_t k = 0; k < sizes.size() && u < u_hi; k++) {
